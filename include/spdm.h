@@ -1,0 +1,125 @@
+/*
+ * spdm.h — C ABI of the B200-native denoising hot path (libspdm.so).
+ *
+ * The reference (rafaelsoStanford/State_Policy_DiffusionModel) has no FFI layer: its
+ * boundary is the PyTorch module surface.  Every entry point below names the reference
+ * call it stands in for (paths relative to /root/reference).  The Python mirror in
+ * state_policy_diffusionmodel_b200/ binds these with ctypes; INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - All tensor arguments are caller-owned, contiguous DEVICE memory (fp32 unless noted).
+ *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it.
+ *   - Return 0 on success, negative on error; spdm_last_error() gives a thread-local message.
+ *   - A plan is bound to one device and is not thread-safe.  There is no CPU fallback.
+ */
+#ifndef SPDM_H
+#define SPDM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct spdm_plan spdm_plan;
+
+enum { SPDM_VARIANT_ATTENTION = 0, SPDM_VARIANT_NO_ATTENTION = 1 };
+enum { SPDM_PRECISION_FP32 = 0, SPDM_PRECISION_BF16 = 1 };
+enum { SPDM_SCHED_DDPM = 0, SPDM_SCHED_DDIM = 1 };
+
+typedef struct spdm_config {
+  int32_t variant;       /* models/Unet_FiLmLayer.py:240 (0) or Unet_FiLmLayer_noAttention.py:240 (1) */
+  int32_t precision;     /* SPDM_PRECISION_*: fp32 = CUDA-core path, bf16 = tcgen05 path            */
+  int32_t batch_max;     /* largest number of trajectories a call will carry                        */
+  int32_t rows;          /* pred_horizon + inpaint_horizon   (models/diffusion_ddpm.py:252)         */
+  int32_t dim;           /* prediction_dim                   (models/diffusion_ddpm.py:252)         */
+  int32_t obs_horizon;   /* T_obs                            (models/diffusion_ddpm.py:283-298)     */
+  int32_t cond_dim;      /* per-frame conditioning width; global_cond_dim = obs_horizon*cond_dim,
+                            0 = unconditional U-Net (Unet_FiLmLayer.py:144,169)                     */
+  int32_t inpaint_rows;  /* inpaint_horizon                  (models/diffusion_ddpm.py:216-219)     */
+  int32_t time_dim;      /* 256                              (models/Unet_FiLmLayer.py:241)         */
+  int32_t device;        /* CUDA device ordinal                                                     */
+  int32_t graph_steps;   /* denoise steps unrolled per CUDA graph launch (0 = no graphs)            */
+  int32_t reserved;
+} spdm_config;
+
+/* Diffusion_DDPM.__init__ (models/diffusion_ddpm.py:22-88): allocate weights + workspace. */
+int spdm_plan_create(spdm_plan** out, const spdm_config* cfg);
+int spdm_plan_destroy(spdm_plan* plan);
+
+/* nn.Module.load_state_dict for noise_estimator.* / vision_encoder.* (SURVEY A.2 key names,
+ * without the Lightning prefix for the U-Net; encoder keys are "vision_encoder.{0,2,4,7}.*").
+ * `src` is fp32 device memory in PyTorch layout; it is repacked into the plan. */
+int spdm_plan_load_weight(spdm_plan* plan, const char* name, const float* src,
+                          const int64_t* shape, int32_t ndim, void* stream);
+/* Number of expected weight tensors still missing (0 = ready); names via spdm_last_error(). */
+int spdm_plan_missing_weights(spdm_plan* plan);
+
+/* DDPMScheduler/DDIMScheduler.set_timesteps (call sites models/diffusion_ddpm.py:204,257;
+ * diffusion_ddim.py:57,67).  coef is HOST memory, K rows of 8 floats:
+ *   {sqrt(1-abar_t), sqrt(abar_t), k_x0, k_x, k_eps, k_noise, 0, 0}
+ *   x0 = (x - c0*eps)/c1 ;  x_prev = k_x0*x0 + k_x*x + k_eps*eps + k_noise*z
+ * timesteps is HOST int64[K] (descending), the value fed to the U-Net time embedding. */
+int spdm_plan_set_schedule(spdm_plan* plan, int32_t kind, int32_t K, const float* coef,
+                           const int64_t* timesteps, void* stream);
+
+/* Autoencoder.encoder (models/encoder/autoencoder.py:11-20): images (n,3,96,96) -> (n,128). */
+int spdm_encode_images(spdm_plan* plan, const float* images, float* out, int32_t n, void* stream);
+
+/* prepare_obs_cond_vectors (models/diffusion_ddpm.py:317-330) + the six FiLM cond_encoder
+ * linears (Unet_FiLmLayer.py:149-154).  images (B,T,3,96,96), position (B,T,2), action (B,T,3),
+ * velocity (B,T,2).  Leaves the conditioning cached in the plan for spdm_sample. */
+int spdm_encode_cond(spdm_plan* plan, const float* images, const float* position,
+                     const float* action, const float* velocity, int32_t B, void* stream);
+/* Same, from an already built obs_cond (B, T*cond_dim). */
+int spdm_set_cond(spdm_plan* plan, const float* obs_cond, int32_t B, void* stream);
+/* Copy of the cached obs_cond (B, T*cond_dim) for inspection / parity tests. */
+int spdm_get_cond(spdm_plan* plan, float* out, int32_t B, void* stream);
+
+/* UNet_Film.forward / UNet_Film_noAttention.forward (Unet_FiLmLayer.py:277-312).
+ * x (B,1,rows,dim); t int64 device, t_count = 1 (broadcast) or B; y (B, T*cond_dim) or NULL
+ * (NULL = reuse the cached conditioning if use_cached_cond, else unconditional). */
+int spdm_unet_forward(spdm_plan* plan, const float* x, const int64_t* t, int32_t t_count,
+                      const float* y, int32_t use_cached_cond, float* out, int32_t B, void* stream);
+
+/* One scheduler.step + add_constraints (models/diffusion_ddpm.py:211-213,216-219) for schedule
+ * index `step` (0..K-1).  noise may be NULL (no noise term).  x_out may alias x. */
+int spdm_step(spdm_plan* plan, const float* x, const float* eps, const float* noise,
+              const float* inpaint, float* x_out, int32_t step, int32_t B, void* stream);
+
+/* Diffusion_DDPM.sample / Diffusion_DDIM.sample loop (diffusion_ddpm.py:269-276,
+ * diffusion_ddim.py:67-74) over all K schedule steps for B trajectories, using the cached
+ * conditioning.  x_T (B,1,rows,dim) is the start sample; noise (K,B,1,rows,dim) or NULL
+ * (NULL: Philox noise from `seed` where the schedule has a noise term); inpaint
+ * (B,1,inpaint_rows,dim) or NULL; out (B,1,rows,dim); history (K+1,B,1,rows,dim) or NULL. */
+int spdm_sample(spdm_plan* plan, const float* x_T, const float* noise, const float* inpaint,
+                float* out, float* history, uint64_t seed, int32_t B, void* stream);
+
+/* DDPMScheduler.add_noise + add_constraints (models/diffusion_ddpm.py:167-168):
+ * x_noisy = sqrt_ab[t_b]*x0 + sqrt_1mab[t_b]*noise, first inpaint_rows rows <- inpaint.
+ * sqrt_ab / sqrt_1mab are device tables indexed by t (int64 device, B entries). */
+int spdm_add_noise(spdm_plan* plan, const float* x0, const float* noise, const int64_t* t,
+                   const float* sqrt_ab, const float* sqrt_1mab, const float* inpaint,
+                   float* out, int32_t B, void* stream);
+
+/* Introspection used by bench.py / tests. */
+int64_t spdm_plan_launch_count(spdm_plan* plan);     /* kernels enqueued so far by this plan  */
+int64_t spdm_plan_workspace_bytes(spdm_plan* plan);
+/* Debug tap: copy an internal activation (by name, e.g. "x1", "down1", "sa1") to fp32
+ * (B, C, H, W) order; returns element count or negative. */
+int64_t spdm_debug_read(spdm_plan* plan, const char* name, float* out, int32_t B, void* stream);
+
+/* tcgen05 implicit-GEMM conv self test entry (tests only): runs one 3x3 conv on the tensor
+ * core path and on the CUDA-core path from the same fp32 inputs; see tests/test_conv_tc.py. */
+int spdm_selftest_conv(int32_t H, int32_t W, int32_t B, int32_t Cin, int32_t Cout,
+                       int32_t taps, const float* in_hbwc, const float* weight_oihw,
+                       float* out_tc, float* out_simt, float* stats_tc, float* stats_simt,
+                       void* stream);
+
+const char* spdm_last_error(void);
+const char* spdm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPDM_H */

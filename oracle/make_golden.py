@@ -1,0 +1,164 @@
+"""oracle/make_golden.py — TEST INFRASTRUCTURE, build-container only.
+
+Runs the UNMODIFIED reference modules from /root/reference (U-Nets as-is; Lightning wrappers behind
+oracle/shim.py) on the deterministic fixtures of oracle/fixtures.py and writes small golden
+input/output vectors to tests/golden/*.npz.  Usage:  python -m oracle.make_golden
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+from . import fixtures, shim
+
+OUT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _np(d):
+    return {k: (v.detach().cpu().numpy() if torch.is_tensor(v) else np.asarray(v)) for k, v in d.items()}
+
+
+def _tap_summary(t):
+    f = t.detach().flatten(1)
+    return torch.stack([f.mean(1), f.std(1), f.abs().max(1).values, f[:, 0], f[:, -1]], dim=1)
+
+
+def golden_unet(attention, t_vals, B, seed, name, rows=31, dim=5):
+    if attention:
+        from models.Unet_FiLmLayer import UNet_Film as Net
+    else:
+        from models.Unet_FiLmLayer_noAttention import UNet_Film_noAttention as Net
+    sd = fixtures.make_unet_weights(attention=attention, seed=seed)
+    net = Net(in_channels=1, out_channels=1, noise_steps=1000, global_cond_dim=1350, time_dim=256).eval()
+    net.load_state_dict(sd, strict=True)  # pins key names + shapes
+    g = torch.Generator().manual_seed(seed + 100)
+    x = torch.rand((B, 1, rows, dim), generator=g)
+    y = torch.randn((B, 1, 10, 135), generator=g)
+    t = torch.tensor(t_vals, dtype=torch.long)
+    taps = {}
+    hooks = []
+    for modname in ("inc", "down1", "down2", "down3", "bot1", "bot2", "bot3", "up1", "up2", "up3",
+                    "sa1", "sa2", "sa3", "sa4", "sa5", "sa6"):
+        if hasattr(net, modname):
+            hooks.append(getattr(net, modname).register_forward_hook(
+                lambda m, i, o, n=modname: taps.__setitem__(n, o.detach().clone())))
+    with torch.no_grad():
+        out = net(x, t, y)
+    for h in hooks:
+        h.remove()
+    with torch.no_grad():
+        out_nocond = net(x, t, None)
+    d = {"x": x, "y": y, "t": t, "out": out, "out_nocond": out_nocond, "seed": seed, "attention": int(attention)}
+    for k, v in taps.items():
+        d["tap_" + k] = _tap_summary(v)
+    # full activation of two layers to pin layout-sensitive ops (upsample/concat, attention)
+    d["full_down1"] = taps["down1"]
+    d["full_up1"] = taps["up1"]
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(d))
+    print(name, "out", tuple(out.shape), float(out.abs().mean()))
+
+
+def golden_encoder():
+    from models.encoder.autoencoder import Autoencoder
+    esd = fixtures.make_encoder_weights()
+    enc = Autoencoder().encoder.eval()
+    enc.load_state_dict(esd, strict=True)
+    g = torch.Generator().manual_seed(5)
+    img = torch.rand((4, 3, 96, 96), generator=g)
+    with torch.no_grad():
+        out = enc(img)
+    np.savez_compressed(os.path.join(OUT, "encoder.npz"), **_np({"img_seed": 5, "out": out}))
+    print("encoder", tuple(out.shape))
+
+
+def _wrapper(kind, model_name, noise_steps, pred_dim, attention, seed):
+    from models.diffusion_ddpm import Diffusion_DDPM
+    from models.diffusion_ddim import Diffusion_DDIM
+    from oracle.schedulers import RefDDIMScheduler
+    cls = Diffusion_DDPM if kind == "ddpm" else Diffusion_DDIM
+    m = cls(noise_steps=noise_steps if kind == "ddpm" else 1000, obs_horizon=10, pred_horizon=30, observation_dim=135,
+            prediction_dim=pred_dim, model=model_name, inpaint_horizon=1).eval()
+    m.noise_estimator.load_state_dict(fixtures.make_unet_weights(attention=attention, seed=seed), strict=True)
+    m.vision_encoder.load_state_dict(fixtures.make_encoder_weights(), strict=True)
+    if kind == "ddim":  # generate.py:28-35
+        m.noise_scheduler = RefDDIMScheduler(num_train_timesteps=noise_steps, beta_schedule="linear",
+                                             clip_sample=False, prediction_type="epsilon")
+        m.noise_steps = noise_steps
+    return m
+
+
+def golden_sample(kind, model_name, attention, noise_steps, pred_dim, name, seed=0, B=2):
+    m = _wrapper(kind, model_name, noise_steps, pred_dim, attention, seed)
+    batch = fixtures.make_batch(B, seed=4321)
+    if pred_dim == 2:
+        # position-only prediction: the committed wrapper still concatenates pos+act for the inpaint vector
+        # (models/diffusion_ddpm.py:340-348; the position-only variant is commented out at diffusion_ddim.py:75-86),
+        # so a 2-wide x_t cannot take a 5-wide inpaint row.  Restate the commented-out variant for this config.
+        m.prepare_inpaint_vectors = lambda ob: ob["position"][:, -m.inpaint_horizon:, :]
+    obs = m.prepare_observation_batch(batch)
+    with torch.no_grad():
+        cond = m.prepare_obs_cond_vectors(obs)
+        inp = m.prepare_inpaint_vectors(obs)
+    torch.manual_seed(1000 + seed)
+    hist = m.sample(batch={k: v.clone() for k, v in obs.items()}, option="sample_history")
+    # replay the RNG stream the wrapper consumed: rand for x_T, then randn per step with t>0 (DDPM only)
+    torch.manual_seed(1000 + seed)
+    x_T = torch.rand(1, 1, 31, pred_dim)
+    noises = []
+    m.noise_scheduler.set_timesteps(noise_steps)
+    for t in m.noise_scheduler.timesteps:
+        if kind == "ddpm" and int(t) > 0:
+            noises.append(torch.randn(1, 1, 31, pred_dim))
+        else:
+            noises.append(torch.zeros(1, 1, 31, pred_dim))
+    assert torch.equal(hist[0], x_T)
+    torch.manual_seed(1000 + seed)
+    final = m.sample(batch={k: v.clone() for k, v in obs.items()})
+    assert torch.allclose(final, hist[-1], atol=0, rtol=0)
+    d = {"batch_seed": 4321, "B": B, "obs_cond": cond, "inpaint": inp, "x_T": x_T, "noise": torch.stack(noises),
+         "history": torch.stack(hist), "timesteps": m.noise_scheduler.timesteps, "unet_seed": seed,
+         "attention": int(attention), "noise_steps": noise_steps, "pred_dim": pred_dim}
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(d))
+    print(name, "final", float(hist[-1].abs().mean()), "steps", len(hist) - 1)
+
+
+def golden_validate_and_train(seed=0):
+    m = _wrapper("ddpm", "UNet_Film", 12, 5, True, seed)
+    B = 3
+    g = torch.Generator().manual_seed(777)
+    full = {"image": torch.rand((B, 40, 3, 96, 96), generator=g), "position": 0.3 * torch.randn((B, 40, 2), generator=g),
+            "velocity": 2 * torch.rand((B, 40, 2), generator=g) - 1, "action": 2 * torch.rand((B, 40, 3), generator=g) - 1}
+    torch.manual_seed(55)
+    x0, obs, inp = m.validate(full)
+    torch.manual_seed(56)
+    with torch.no_grad():
+        loss = m.process_single_batch(full)
+    torch.manual_seed(56)
+    t = torch.randint(0, m.noise_steps, (B,)).long()
+    noise = torch.randn(B, 1, 31, 5)
+    torch.manual_seed(55)
+    x_T = torch.rand(1, 1, 31, 5)
+    noises = [torch.randn(1, 1, 31, 5) if int(tt) > 0 else torch.zeros(1, 1, 31, 5) for tt in range(11, -1, -1)]
+    d = {"full_seed": 777, "validate_x0": x0, "validate_inpaint": inp, "validate_x_T": x_T,
+         "validate_noise": torch.stack(noises), "train_loss": loss, "train_t": t, "train_noise": noise}
+    np.savez_compressed(os.path.join(OUT, "validate_train.npz"), **_np(d))
+    print("validate/train loss", float(loss))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    shim.install()
+    torch.set_num_threads(8)
+    golden_unet(True, [999, 500, 3], 3, 0, "unet_attn")
+    golden_unet(False, [7], 2, 3, "unet_noattn")
+    golden_unet(True, [40], 2, 4, "unet_attn_rows61", rows=61)
+    golden_unet(False, [123], 2, 5, "unet_noattn_pos2", dim=2)
+    golden_encoder()
+    golden_sample("ddim", "UNet_Film", True, 10, 5, "sample_ddim10_attn")
+    golden_sample("ddpm", "UNet_FilmnoAttention", False, 20, 2, "sample_ddpm20_noattn_pos2", seed=3)
+    golden_validate_and_train()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

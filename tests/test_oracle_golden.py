@@ -1,0 +1,94 @@
+"""CPU: the oracle restatement vs golden vectors produced by the REAL reference modules
+(oracle/make_golden.py, run in the build container against /root/reference)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures, sampler_ref, unet_ref
+from oracle.schedulers import RefDDPMScheduler
+
+TOL = dict(rtol=1e-4, atol=2e-5)
+
+
+def _load(golden_dir, name):
+    return {k: torch.from_numpy(v) if v.ndim else v for k, v in np.load(os.path.join(golden_dir, name + ".npz")).items()}
+
+
+def _summary(t):
+    f = t.flatten(1)
+    return torch.stack([f.mean(1), f.std(1), f.abs().max(1).values, f[:, 0], f[:, -1]], dim=1)
+
+
+@pytest.mark.parametrize("name", ["unet_attn", "unet_noattn", "unet_attn_rows61", "unet_noattn_pos2"])
+def test_unet_oracle_matches_reference(golden_dir, name):
+    g = _load(golden_dir, name)
+    attention = bool(int(g["attention"]))
+    sd = fixtures.make_unet_weights(attention=attention, seed=int(g["seed"]))
+    taps = {}
+    with torch.no_grad():
+        out = unet_ref.unet_forward(sd, g["x"], g["t"], g["y"], attention=attention, taps=taps)
+        out_nc = unet_ref.unet_forward(sd, g["x"], g["t"], None, attention=attention)
+    torch.testing.assert_close(out, g["out"], **TOL)
+    torch.testing.assert_close(out_nc, g["out_nocond"], **TOL)
+    torch.testing.assert_close(taps["down1"], g["full_down1"], **TOL)
+    torch.testing.assert_close(taps["up1"], g["full_up1"], **TOL)
+    # module-output summaries: reference hook names -> oracle tap names
+    ren = {"inc": "x1", "bot1": "bot1", "bot2": "bot2", "bot3": "x5", "down1": "down1", "down2": "down2",
+           "down3": "down3", "up1": "up1", "up2": "up2", "up3": "up3", "sa1": "x2", "sa2": "x3", "sa3": "x4",
+           "sa4": "u1", "sa5": "u2", "sa6": "u3"}
+    for k, v in g.items():
+        if k.startswith("tap_"):
+            torch.testing.assert_close(_summary(taps[ren[k[4:]]]), v, rtol=1e-3, atol=1e-4)
+
+
+def test_encoder_oracle(golden_dir):
+    g = _load(golden_dir, "encoder")
+    esd = fixtures.make_encoder_weights()
+    img = torch.rand((4, 3, 96, 96), generator=torch.Generator().manual_seed(int(g["img_seed"])))
+    torch.testing.assert_close(unet_ref.encoder_forward(esd, img), g["out"], **TOL)
+
+
+@pytest.mark.parametrize("name,kind", [("sample_ddim10_attn", "ddim"), ("sample_ddpm20_noattn_pos2", "ddpm")])
+def test_sampling_loop_oracle(golden_dir, name, kind):
+    g = _load(golden_dir, name)
+    attention = bool(int(g["attention"]))
+    pred_dim = int(g["pred_dim"])
+    K = int(g["noise_steps"])
+    sd = fixtures.make_unet_weights(attention=attention, seed=int(g["unet_seed"]))
+    esd = fixtures.make_encoder_weights()
+    batch = fixtures.make_batch(int(g["B"]), seed=int(g["batch_seed"]))
+    cond = unet_ref.obs_cond(esd, batch)
+    torch.testing.assert_close(cond, g["obs_cond"], **TOL)
+    if pred_dim == 2:
+        inp = batch["position"][:, -1:, :]
+    else:
+        inp = unet_ref.inpaint_vector(batch, 1)
+    torch.testing.assert_close(inp, g["inpaint"], rtol=0, atol=0)
+    sched = sampler_ref.make_scheduler(kind, K)
+    hist = sampler_ref.sample_ref(sd, sched, K, g["x_T"], cond[0:1].unsqueeze(1), inp[0:1].unsqueeze(1), 1,
+                                  attention=attention, noise=g["noise"], history=True)
+    assert [int(t) for t in sched.timesteps] == [int(t) for t in g["timesteps"]]
+    torch.testing.assert_close(torch.stack(hist), g["history"], rtol=1e-4, atol=5e-5)
+
+
+def test_validate_and_training_forward_oracle(golden_dir):
+    g = _load(golden_dir, "validate_train")
+    sd = fixtures.make_unet_weights(attention=True, seed=0)
+    esd = fixtures.make_encoder_weights()
+    B = 3
+    gen = torch.Generator().manual_seed(int(g["full_seed"]))
+    full = {"image": torch.rand((B, 40, 3, 96, 96), generator=gen), "position": 0.3 * torch.randn((B, 40, 2), generator=gen),
+            "velocity": 2 * torch.rand((B, 40, 2), generator=gen) - 1, "action": 2 * torch.rand((B, 40, 3), generator=gen) - 1}
+    obs = {k: v[:, :10] for k, v in full.items()}
+    cond = unet_ref.obs_cond(esd, obs)
+    inp = unet_ref.inpaint_vector(obs, 1)
+    sched = RefDDPMScheduler(num_train_timesteps=12, beta_schedule="linear", clip_sample=False)
+    x0 = sampler_ref.sample_ref(sd, sched, 12, g["validate_x_T"], cond[0:1].unsqueeze(1), inp[0:1].unsqueeze(1), 1,
+                                attention=True, noise=g["validate_noise"])
+    torch.testing.assert_close(x0, g["validate_x0"], rtol=1e-4, atol=5e-5)
+    sched = RefDDPMScheduler(num_train_timesteps=12, beta_schedule="linear", clip_sample=False)
+    with torch.no_grad():
+        loss, _, _ = sampler_ref.training_forward_ref(sd, esd, sched, full, 10, 1, g["train_t"], g["train_noise"])
+    torch.testing.assert_close(loss, torch.as_tensor(g["train_loss"]), rtol=1e-5, atol=1e-6)
