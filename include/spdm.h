@@ -7,7 +7,7 @@
  * state_policy_diffusionmodel_b200/ binds these with ctypes; INTEGRATION.md shows the stub.
  *
  * Conventions
- *   - All tensor arguments are caller-owned, contiguous DEVICE memory (fp32 unless noted).
+ *   - All tensor arguments are caller-owned, contiguous DEVICE memory (fp32 unless noted; timesteps int64).
  *   - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it.
  *   - Return 0 on success, negative on error; spdm_last_error() gives a thread-local message.
  *   - A plan is bound to one device and is not thread-safe.  There is no CPU fallback.
@@ -26,6 +26,7 @@ typedef struct spdm_plan spdm_plan;
 enum { SPDM_VARIANT_ATTENTION = 0, SPDM_VARIANT_NO_ATTENTION = 1 };
 enum { SPDM_PRECISION_FP32 = 0, SPDM_PRECISION_BF16 = 1 };
 enum { SPDM_SCHED_DDPM = 0, SPDM_SCHED_DDIM = 1 };
+enum { SPDM_FLAG_SCHEDULER_ONLY = 1 }; /* plan without U-Net weights/workspace: spdm_step, spdm_add_noise only */
 
 typedef struct spdm_config {
   int32_t variant;       /* models/Unet_FiLmLayer.py:240 (0) or Unet_FiLmLayer_noAttention.py:240 (1) */
@@ -40,7 +41,7 @@ typedef struct spdm_config {
   int32_t time_dim;      /* 256                              (models/Unet_FiLmLayer.py:241)         */
   int32_t device;        /* CUDA device ordinal                                                     */
   int32_t graph_steps;   /* denoise steps unrolled per CUDA graph launch (0 = no graphs)            */
-  int32_t reserved;
+  int32_t flags;         /* SPDM_FLAG_*                                                            */
 } spdm_config;
 
 /* Diffusion_DDPM.__init__ (models/diffusion_ddpm.py:22-88): allocate weights + workspace. */
@@ -105,16 +106,12 @@ int spdm_add_noise(spdm_plan* plan, const float* x0, const float* noise, const i
 /* Introspection used by bench.py / tests. */
 int64_t spdm_plan_launch_count(spdm_plan* plan);     /* kernels enqueued so far by this plan  */
 int64_t spdm_plan_workspace_bytes(spdm_plan* plan);
-/* Debug tap: copy an internal activation (by name, e.g. "x1", "down1", "sa1") to fp32
- * (B, C, H, W) order; returns element count or negative. */
-int64_t spdm_debug_read(spdm_plan* plan, const char* name, float* out, int32_t B, void* stream);
-
-/* tcgen05 implicit-GEMM conv self test entry (tests only): runs one 3x3 conv on the tensor
- * core path and on the CUDA-core path from the same fp32 inputs; see tests/test_conv_tc.py. */
-int spdm_selftest_conv(int32_t H, int32_t W, int32_t B, int32_t Cin, int32_t Cout,
-                       int32_t taps, const float* in_hbwc, const float* weight_oihw,
-                       float* out_tc, float* out_simt, float* stats_tc, float* stats_simt,
-                       void* stream);
+/* Debug tap (tests only): spdm_unet_forward that additionally copies the internal activation `tap_name`
+ * ("inc", "down1", "sa1", "x2", "bot3", "up1", "u3", "<block>.first", ... ) to tap_out as fp32
+ * (B, C, H, W).  Returns the element count written, or negative. */
+int64_t spdm_debug_forward(spdm_plan* plan, const float* x, const int64_t* t, int32_t t_count,
+                           const float* y, int32_t use_cached_cond, float* out, int32_t B,
+                           const char* tap_name, float* tap_out, void* stream);
 
 const char* spdm_last_error(void);
 const char* spdm_version(void);

@@ -1,0 +1,86 @@
+"""ctypes binding of libspdm.so — the C ABI declared in include/spdm.h.
+
+This is the only door between the Python mirror of the reference's module surface and the CUDA
+kernels.  It fails loudly when the library or a CUDA device is missing: there is no CPU fallback.
+"""
+import ctypes
+import os
+
+from . import _build
+
+_c = ctypes
+_lib = None
+
+
+class SpdmConfig(_c.Structure):
+    _fields_ = [(n, _c.c_int32) for n in (
+        "variant", "precision", "batch_max", "rows", "dim", "obs_horizon", "cond_dim", "inpaint_rows",
+        "time_dim", "device", "graph_steps", "flags")]
+
+
+VARIANT_ATTENTION, VARIANT_NO_ATTENTION = 0, 1
+PRECISION_FP32, PRECISION_BF16 = 0, 1
+SCHED_DDPM, SCHED_DDIM = 0, 1
+FLAG_SCHEDULER_ONLY = 1
+
+_P = _c.c_void_p
+_PROTOTYPES = {
+    "spdm_plan_create": (_c.c_int, [_c.POINTER(_P), _c.POINTER(SpdmConfig)]),
+    "spdm_plan_destroy": (_c.c_int, [_P]),
+    "spdm_plan_load_weight": (_c.c_int, [_P, _c.c_char_p, _P, _c.POINTER(_c.c_int64), _c.c_int32, _P]),
+    "spdm_plan_missing_weights": (_c.c_int, [_P]),
+    "spdm_plan_set_schedule": (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P, _P, _P]),
+    "spdm_encode_images": (_c.c_int, [_P, _P, _P, _c.c_int32, _P]),
+    "spdm_encode_cond": (_c.c_int, [_P, _P, _P, _P, _P, _c.c_int32, _P]),
+    "spdm_set_cond": (_c.c_int, [_P, _P, _c.c_int32, _P]),
+    "spdm_get_cond": (_c.c_int, [_P, _P, _c.c_int32, _P]),
+    "spdm_unet_forward": (_c.c_int, [_P, _P, _P, _c.c_int32, _P, _c.c_int32, _P, _c.c_int32, _P]),
+    "spdm_debug_forward": (_c.c_int64, [_P, _P, _P, _c.c_int32, _P, _c.c_int32, _P, _c.c_int32, _c.c_char_p, _P, _P]),
+    "spdm_step": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_int32, _c.c_int32, _P]),
+    "spdm_sample": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_uint64, _c.c_int32, _P]),
+    "spdm_add_noise": (_c.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _c.c_int32, _P]),
+    "spdm_plan_launch_count": (_c.c_int64, [_P]),
+    "spdm_plan_workspace_bytes": (_c.c_int64, [_P]),
+    "spdm_last_error": (_c.c_char_p, []),
+    "spdm_version": (_c.c_char_p, []),
+}
+EXPORTED_SYMBOLS = tuple(_PROTOTYPES)
+
+
+def lib_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """dlopen libspdm.so (building it first if the sources are newer) and set the prototypes."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB
+    if build_if_missing and _build.is_stale():
+        try:
+            _build.build()
+        except Exception as e:  # a stale-but-present library is still usable (e.g. no nvcc on the box)
+            if not os.path.exists(path):
+                raise RuntimeError(
+                    "libspdm.so is missing and could not be built (%s). The spdm CUDA path has no CPU "
+                    "fallback; build it with `python -c 'import __graft_entry__ as g; g.build()'`." % e)
+    if not os.path.exists(path):
+        raise RuntimeError("libspdm.so not found at %s — the spdm CUDA path has no CPU fallback" % path)
+    lib = _c.CDLL(path)
+    for name, (res, args) in _PROTOTYPES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+class SpdmError(RuntimeError):
+    pass
+
+
+def check(rc):
+    if rc is not None and rc < 0:
+        raise SpdmError(load().spdm_last_error().decode("utf-8", "replace"))
+    return rc

@@ -1,0 +1,858 @@
+// kernels.cu — CUDA-core kernels of the denoising hot path (sm_100a).
+//
+// Everything that is not a dense bf16 contraction lives here: the fp32 reference-precision implicit
+// GEMM (parity path and odd shapes), GroupNorm statistics / apply (+GELU, +time embedding, +FiLM),
+// max-pool, bilinear upsample, LayerNorm, the small-L multi-head attention core, the first/last
+// 1-channel convolutions, the observation encoder, and the fused posterior update.
+// Reference lines are cited per kernel (paths relative to the reference repo root).
+#include "common.cuh"
+
+static long long g_launches = 0;
+long long kernels_launch_count() { return g_launches; }
+#define COUNT_LAUNCH() (++g_launches)
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// =================================================================================================
+// fp32-accumulate implicit GEMM on CUDA cores.
+//   out[r, n] = epi( sum_{tap, c} in[shift(r, tap), c] * w[tap][c][n] )
+// nn.Conv2d(k=3, pad=1, bias=False)  (models/Unet_FiLmLayer.py:101,103) when taps == 9,
+// nn.Linear / 1x1 when taps == 1.  64x64 tile, BK=16, 256 threads, 4x4 outputs per thread.
+// =================================================================================================
+namespace {
+constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(256) gemm_simt_kernel(GemmSimtArgs a) {
+  __shared__ float As[SG_BK][SG_BM + 4];
+  __shared__ float Bs[SG_BK][SG_BN + 4];
+  const TI* __restrict__ in = reinterpret_cast<const TI*>(a.in);
+  const int tid = threadIdx.x;
+  const int m0 = blockIdx.x * SG_BM, n0 = blockIdx.y * SG_BN;
+  const int tx = tid & 15, ty = tid >> 4;
+
+  // A-load assignment: one row, 4 consecutive k
+  const int a_row = tid >> 2, a_k = (tid & 3) * 4;
+  const int r = m0 + a_row;
+  int rb = 0, rh = 0, rw = 0;
+  const int HW = a.H * a.W;
+  if (a.taps == 9) { rb = r / HW; const int rem = r - rb * HW; rh = rem / a.W; rw = rem - rh * a.W; }
+  (void)rb;
+  // B-load assignment: one k row, 4 consecutive n
+  const int b_k = tid >> 4, b_n = (tid & 15) * 4;
+
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const bool a_vec = (sizeof(TI) == 4) && (a.Cin % 4 == 0) && (a.ld_in % 4 == 0);
+  const bool b_vec = (a.Cout % 4 == 0);
+
+  for (int tap = 0; tap < a.taps; ++tap) {
+    int dy = 0, dx = 0;
+    if (a.taps == 9) { dy = tap / 3 - 1; dx = tap % 3 - 1; }
+    bool valid = r < a.M;
+    long long src = r;
+    if (a.taps == 9) {
+      const int hh = rh + dy, ww = rw + dx;
+      valid = valid && hh >= 0 && hh < a.H && ww >= 0 && ww < a.W;
+      src = (long long)r + dy * a.W + dx;
+    }
+    if (a.taps == 9) {  // whole-block skip of structurally empty taps (W == 1 or H == 1)
+      if ((a.W == 1 && dx != 0) || (a.H == 1 && dy != 0)) continue;
+    }
+    const float* __restrict__ wt = a.w + (size_t)tap * a.Cin * a.Cout;
+    for (int c0 = 0; c0 < a.Cin; c0 += SG_BK) {
+      // ---- load A tile (transposed into As[k][row]) ----
+      float av[4] = {0.f, 0.f, 0.f, 0.f};
+      if (valid) {
+        const TI* p = in + src * a.ld_in + c0 + a_k;
+        if (a_vec && c0 + a_k + 3 < a.Cin) {
+          const float4 t = *reinterpret_cast<const float4*>(p);
+          av[0] = t.x; av[1] = t.y; av[2] = t.z; av[3] = t.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (c0 + a_k + i < a.Cin) av[i] = to_f32<TI>(p[i]);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i) As[a_k + i][a_row] = av[i];
+      // ---- load B tile ----
+      float bv[4] = {0.f, 0.f, 0.f, 0.f};
+      if (c0 + b_k < a.Cin) {
+        const float* p = wt + (size_t)(c0 + b_k) * a.Cout + n0 + b_n;
+        if (b_vec && n0 + b_n + 3 < a.Cout) {
+          const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+          bv[0] = t.x; bv[1] = t.y; bv[2] = t.z; bv[3] = t.w;
+        } else {
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (n0 + b_n + i < a.Cout) bv[i] = __ldg(p + i);
+        }
+      }
+      *reinterpret_cast<float4*>(&Bs[b_k][b_n]) = make_float4(bv[0], bv[1], bv[2], bv[3]);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < SG_BK; ++k) {
+        const float4 av4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 bv4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float ar[4] = {av4.x, av4.y, av4.z, av4.w};
+        const float br[4] = {bv4.x, bv4.y, bv4.z, bv4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+  // ---- epilogue ----
+  TO* __restrict__ out = reinterpret_cast<TO*>(a.out);
+  const TO* __restrict__ resid = reinterpret_cast<const TO*>(a.resid);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= a.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= a.Cout) continue;
+      float v = acc[i][j];
+      if (a.bias) v += __ldg(a.bias + n);
+      if (a.act == ACT_GELU) v = gelu_exact(v);
+      else if (a.act == ACT_RELU) v = fmaxf(v, 0.f);
+      if (resid) v += to_f32<TO>(resid[(size_t)row * a.ld_res + n]);
+      out[(size_t)row * a.ld_out + n] = from_f32<TO>(v);
+    }
+  }
+}
+}  // namespace
+
+template <typename TI, typename TO> void launch_gemm_simt(const GemmSimtArgs& a, cudaStream_t s) {
+  dim3 grid(cdiv(a.M, SG_BM), cdiv(a.Cout, SG_BN));
+  gemm_simt_kernel<TI, TO><<<grid, 256, 0, s>>>(a);
+  COUNT_LAUNCH();
+}
+template void launch_gemm_simt<float, float>(const GemmSimtArgs&, cudaStream_t);
+template void launch_gemm_simt<bf16, bf16>(const GemmSimtArgs&, cudaStream_t);
+template void launch_gemm_simt<float, bf16>(const GemmSimtArgs&, cudaStream_t);
+template void launch_gemm_simt<bf16, float>(const GemmSimtArgs&, cudaStream_t);
+
+// =================================================================================================
+// GroupNorm(1, C) statistics (models/Unet_FiLmLayer.py:105): per-sample (sum, sumsq) over C*H*W.
+// One block per sample, P = 1 partial.  (The tcgen05 conv writes its partials from its epilogue.)
+// =================================================================================================
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ raw, float* __restrict__ stats, int HW, int C, int ld) {
+  const int b = blockIdx.x;
+  const int vec_per_row = C >> 3;
+  const int nvec = HW * vec_per_row;
+  float s = 0.f, q = 0.f;
+  for (int v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const int row = v / vec_per_row, c8 = (v - row * vec_per_row) << 3;
+    float x[8];
+    load8(raw + ((size_t)b * HW + row) * ld + c8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s += x[i]; q = fmaf(x[i], x[i], q); }
+  }
+  __shared__ float ss[8], sq[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((threadIdx.x & 31) == 0) { ss[threadIdx.x >> 5] = s; sq[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float ts = 0.f, tq = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) { ts += ss[i]; tq += sq[i]; }
+    stats[2 * b] = ts;
+    stats[2 * b + 1] = tq;
+  }
+}
+}  // namespace
+template <typename T> void launch_stats(const T* raw, float* stats, int B, int HW, int C, int ld, cudaStream_t s) {
+  stats_kernel<T><<<B, 256, 0, s>>>(raw, stats, HW, C, ld);
+  COUNT_LAUNCH();
+}
+template void launch_stats<float>(const float*, float*, int, int, int, int, cudaStream_t);
+template void launch_stats<bf16>(const bf16*, float*, int, int, int, int, cudaStream_t);
+
+// =================================================================================================
+// GroupNorm apply (+GELU) (+ time embedding) (+ FiLM):
+//   y = (x - mean) * rstd * gamma[c] + beta[c]           models/Unet_FiLmLayer.py:112,115
+//   y = gelu(y)                                           :113       (first conv of a DoubleConvolution)
+//   y = y + temb[c]                                       :165-168   (end of a Down/Up stage)
+//   y = scale[b,c] * y + bias[b,c]                        :171-177   (FiLM)
+// grid (chunks, B); every block first folds the P partial sums of its sample (in double).
+// =================================================================================================
+namespace {
+constexpr int APPLY_THREADS = 128;
+constexpr int APPLY_VEC_PER_THREAD = 4;
+
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(ApplyArgs a) {
+  const int b = blockIdx.y;
+  __shared__ float s_mean, s_rstd;
+  if (threadIdx.x < 32) {
+    double s = 0.0, q = 0.0;
+    for (int p = threadIdx.x; p < a.P; p += 32) {
+      s += (double)a.stats[((size_t)b * a.P + p) * 2];
+      q += (double)a.stats[((size_t)b * a.P + p) * 2 + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+    if (threadIdx.x == 0) {
+      const double n = (double)a.HW * (double)a.C;
+      const double mean = s / n;
+      double var = q / n - mean * mean;
+      if (var < 0.0) var = 0.0;
+      s_mean = (float)mean;
+      s_rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+    }
+  }
+  __syncthreads();
+  const float mean = s_mean, rstd = s_rstd;
+  const TI* __restrict__ raw = reinterpret_cast<const TI*>(a.raw);
+  TO* __restrict__ out = reinterpret_cast<TO*>(a.out);
+  const int vec_per_row = a.C >> 3;
+  const int nvec = a.HW * vec_per_row;
+  const float* temb = nullptr;
+  if (a.temb_mode != TEMB_NONE) {
+    int trow = 0;
+    if (a.temb_mode == TEMB_PER_SAMPLE) trow = b;
+    else if (a.temb_mode == TEMB_STEP) trow = *a.step_ptr;
+    temb = a.temb + (size_t)trow * SPDM_TEMB_WIDTH + a.temb_off;
+  }
+  const float* film = a.film ? a.film + (size_t)b * SPDM_FILM_WIDTH + a.film_off : nullptr;
+  const int v0 = blockIdx.x * (APPLY_THREADS * APPLY_VEC_PER_THREAD);
+#pragma unroll
+  for (int it = 0; it < APPLY_VEC_PER_THREAD; ++it) {
+    const int v = v0 + it * APPLY_THREADS + threadIdx.x;
+    if (v >= nvec) break;
+    const int row = v / vec_per_row, c8 = (v - row * vec_per_row) << 3;
+    float x[8];
+    load8(raw + ((size_t)b * a.HW + row) * a.ld_in + c8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      float y = (x[i] - mean) * rstd * __ldg(a.gamma + c8 + i) + __ldg(a.beta + c8 + i);
+      if (a.act == ACT_GELU) y = gelu_exact(y);
+      if (temb) y += __ldg(temb + c8 + i);
+      if (film) y = __ldg(film + c8 + i) * y + __ldg(film + a.C + c8 + i);
+      x[i] = y;
+    }
+    store8(out + ((size_t)b * a.HW + row) * a.ld_out + c8, x);
+  }
+}
+}  // namespace
+template <typename TI, typename TO> void launch_apply(const ApplyArgs& a, int B, cudaStream_t s) {
+  const int nvec = a.HW * (a.C >> 3);
+  dim3 grid(cdiv(nvec, APPLY_THREADS * APPLY_VEC_PER_THREAD), B);
+  apply_kernel<TI, TO><<<grid, APPLY_THREADS, 0, s>>>(a);
+  COUNT_LAUNCH();
+}
+template void launch_apply<float, float>(const ApplyArgs&, int, cudaStream_t);
+template void launch_apply<bf16, bf16>(const ApplyArgs&, int, cudaStream_t);
+
+// =================================================================================================
+// MaxPool2d(2) (models/Unet_FiLmLayer.py:132) and bilinear x2 upsample, align_corners=True (:191).
+// =================================================================================================
+namespace {
+template <typename T>
+__global__ void pool_kernel(const T* __restrict__ in, int ld_in, T* __restrict__ out, int ld_out, long long total, int Ho, int Wo, int C) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= total) return;
+  const int vec_per_row = C >> 3;
+  const long long orow = v / vec_per_row;
+  const int c8 = (int)(v - orow * vec_per_row) << 3;
+  const int wo = (int)(orow % Wo);
+  const long long t = orow / Wo;
+  const int ho = (int)(t % Ho);
+  const long long b = t / Ho;
+  const int Wi = Wo * 2, Hi = Ho * 2;
+  const long long r00 = (b * Hi + 2 * ho) * Wi + 2 * wo;
+  float m[8], x[8];
+  load8(in + r00 * ld_in + c8, m);
+  load8(in + (r00 + 1) * ld_in + c8, x);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], x[i]);
+  load8(in + (r00 + Wi) * ld_in + c8, x);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], x[i]);
+  load8(in + (r00 + Wi + 1) * ld_in + c8, x);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) m[i] = fmaxf(m[i], x[i]);
+  store8(out + orow * ld_out + c8, m);
+}
+
+template <typename T>
+__global__ void upsample_kernel(const T* __restrict__ in, int ld_in, T* __restrict__ out, int ld_out, long long total, int Hi, int Wi, int C) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= total) return;
+  const int vec_per_row = C >> 3;
+  const long long orow = v / vec_per_row;
+  const int c8 = (int)(v - orow * vec_per_row) << 3;
+  const int Ho = Hi * 2, Wo = Wi * 2;
+  const int wo = (int)(orow % Wo);
+  const long long t = orow / Wo;
+  const int ho = (int)(t % Ho);
+  const long long b = t / Ho;
+  // align_corners=True: src = dst * (in-1)/(out-1)
+  const float sh = (Ho > 1) ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+  const float sw = (Wo > 1) ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  const float fh = sh * ho, fw = sw * wo;
+  const int h0 = (int)fh, w0 = (int)fw;
+  const int h1 = h0 + ((h0 < Hi - 1) ? 1 : 0), w1 = w0 + ((w0 < Wi - 1) ? 1 : 0);
+  const float lh1 = fh - h0, lh0 = 1.f - lh1, lw1 = fw - w0, lw0 = 1.f - lw1;
+  float a00[8], a01[8], a10[8], a11[8], y[8];
+  const long long base = b * Hi;
+  load8(in + ((base + h0) * Wi + w0) * ld_in + c8, a00);
+  load8(in + ((base + h0) * Wi + w1) * ld_in + c8, a01);
+  load8(in + ((base + h1) * Wi + w0) * ld_in + c8, a10);
+  load8(in + ((base + h1) * Wi + w1) * ld_in + c8, a11);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) y[i] = lh0 * (lw0 * a00[i] + lw1 * a01[i]) + lh1 * (lw0 * a10[i] + lw1 * a11[i]);
+  store8(out + orow * ld_out + c8, y);
+}
+}  // namespace
+template <typename T> void launch_pool(const T* in, int ld_in, T* out, int ld_out, int B, int Ho, int Wo, int C, cudaStream_t s) {
+  const long long total = (long long)B * Ho * Wo * (C >> 3);
+  pool_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(in, ld_in, out, ld_out, total, Ho, Wo, C);
+  COUNT_LAUNCH();
+}
+template <typename T> void launch_upsample(const T* in, int ld_in, T* out, int ld_out, int B, int Hi, int Wi, int C, cudaStream_t s) {
+  const long long total = (long long)B * Hi * 2 * Wi * 2 * (C >> 3);
+  upsample_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(in, ld_in, out, ld_out, total, Hi, Wi, C);
+  COUNT_LAUNCH();
+}
+template void launch_pool<float>(const float*, int, float*, int, int, int, int, int, cudaStream_t);
+template void launch_pool<bf16>(const bf16*, int, bf16*, int, int, int, int, int, cudaStream_t);
+template void launch_upsample<float>(const float*, int, float*, int, int, int, int, int, cudaStream_t);
+template void launch_upsample<bf16>(const bf16*, int, bf16*, int, int, int, int, int, cudaStream_t);
+
+// =================================================================================================
+// LayerNorm over C (models/Unet_FiLmLayer.py:51,53): one warp per token row, C in {64,128,256}.
+// =================================================================================================
+namespace {
+template <typename T, int VPL>  // VPL = C / 32 elements per lane
+__global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ in, int ld_in, T* __restrict__ out, int ld_out,
+                                                        const float* __restrict__ g, const float* __restrict__ bta, long long M) {
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= M) return;
+  const int lane = threadIdx.x & 31;
+  const int c0 = lane * VPL;
+  float x[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) x[i] = to_f32<T>(in[row * ld_in + c0 + i]);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) s += x[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)(VPL * 32);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) { const float d = x[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q / (float)(VPL * 32) + 1e-5f);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i)
+    out[row * ld_out + c0 + i] = from_f32<T>((x[i] - mean) * rstd * __ldg(g + c0 + i) + __ldg(bta + c0 + i));
+}
+}  // namespace
+template <typename T> void launch_layernorm(const T* in, int ld_in, T* out, int ld_out, const float* g, const float* b, long long M, int C, cudaStream_t s) {
+  const int grid = cdiv(M, 8);
+  if (C == 64) layernorm_kernel<T, 2><<<grid, 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
+  else if (C == 128) layernorm_kernel<T, 4><<<grid, 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
+  else if (C == 256) layernorm_kernel<T, 8><<<grid, 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
+  else if (C == 512) layernorm_kernel<T, 16><<<grid, 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
+  COUNT_LAUNCH();
+}
+template void launch_layernorm<float>(const float*, int, float*, int, const float*, const float*, long long, int, cudaStream_t);
+template void launch_layernorm<bf16>(const bf16*, int, bf16*, int, const float*, const float*, long long, int, cudaStream_t);
+
+// =================================================================================================
+// Multi-head attention core (nn.MultiheadAttention, 4 heads, models/Unet_FiLmLayer.py:50,76):
+//   o[b, i, h*hd:(h+1)*hd] = softmax_j(q_i . k_j / sqrt(hd)) v_j,   qkv rows = [q | k | v] (3C wide).
+// L = H*W tokens is tiny (4..1024), head_dim 16/32/64: one thread per query row, K/V of the
+// (sample, head) group broadcast from shared memory, online softmax in fp32.
+// =================================================================================================
+namespace {
+template <typename T, int HD>
+__global__ void __launch_bounds__(128) sdpa_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n_groups, int L, int C, int heads,
+                                                   int groups_per_block, int threads_per_group) {
+  extern __shared__ float sm[];  // [groups_per_block][2][L][HD]
+  const int gl = threadIdx.x / threads_per_group;
+  const int tl = threadIdx.x - gl * threads_per_group;
+  const int grp = blockIdx.x * groups_per_block + gl;
+  const bool active = gl < groups_per_block && grp < n_groups;
+  const int b = active ? grp / heads : 0, h = active ? grp - b * heads : 0;
+  float* Ks = sm + (size_t)gl * 2 * L * HD;
+  float* Vs = Ks + (size_t)L * HD;
+  const int ld = 3 * C;
+  if (active) {
+    const int vec_per_row = HD >> 3;
+    for (int v = tl; v < L * vec_per_row; v += threads_per_group) {
+      const int j = v / vec_per_row, d8 = (v - j * vec_per_row) << 3;
+      const T* row = qkv + ((size_t)b * L + j) * ld + h * HD + d8;
+      float k8[8], v8[8];
+      load8(row + C, k8);
+      load8(row + 2 * C, v8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { Ks[j * HD + d8 + i] = k8[i]; Vs[j * HD + d8 + i] = v8[i]; }
+    }
+  }
+  __syncthreads();
+  if (!active) return;
+  const float scale = rsqrtf((float)HD);
+  for (int i = tl; i < L; i += threads_per_group) {
+    float q[HD], acc[HD];
+    const T* qrow = qkv + ((size_t)b * L + i) * ld + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; d += 8) {
+      float t[8];
+      load8(qrow + d, t);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) { q[d + e] = t[e] * scale; acc[d + e] = 0.f; }
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < L; ++j) {
+      const float* kj = Ks + j * HD;
+      float sdot = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) sdot = fmaf(q[d], kj[d], sdot);
+      const float* vj = Vs + j * HD;
+      if (sdot > m) {
+        const float corr = __expf(m - sdot);
+        l = l * corr + 1.f;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] = fmaf(acc[d], corr, vj[d]);
+        m = sdot;
+      } else {
+        const float p = __expf(sdot - m);
+        l += p;
+#pragma unroll
+        for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, vj[d], acc[d]);
+      }
+    }
+    const float inv = 1.f / l;
+    T* orow = out + ((size_t)b * L + i) * C + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; d += 8) {
+      float t[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t[e] = acc[d + e] * inv;
+      store8(orow + d, t);
+    }
+  }
+}
+}  // namespace
+template <typename T> void launch_sdpa(const T* qkv, T* out, int B, int L, int C, int heads, cudaStream_t s) {
+  const int hd = C / heads;
+  const int n_groups = B * heads;
+  const int tpg = L >= 128 ? 128 : (L < 4 ? 4 : L);  // L is a power of two times small factors; groups share a block
+  const int gpb = 128 / tpg;
+  const size_t smem = (size_t)gpb * 2 * L * hd * sizeof(float);
+  const int grid = cdiv(n_groups, gpb);
+#define SDPA_CASE(HD)                                                                                         \
+  {                                                                                                           \
+    static bool attr_set = false;                                                                             \
+    if (!attr_set) {                                                                                          \
+      cudaFuncSetAttribute(sdpa_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);      \
+      attr_set = true;                                                                                        \
+    }                                                                                                         \
+    sdpa_kernel<T, HD><<<grid, 128, smem, s>>>(qkv, out, n_groups, L, C, heads, gpb, tpg);                   \
+  }
+  if (hd == 16) SDPA_CASE(16)
+  else if (hd == 32) SDPA_CASE(32)
+  else if (hd == 64) SDPA_CASE(64)
+#undef SDPA_CASE
+  COUNT_LAUNCH();
+}
+template void launch_sdpa<float>(const float*, float*, int, int, int, int, cudaStream_t);
+template void launch_sdpa<bf16>(const bf16*, bf16*, int, int, int, int, cudaStream_t);
+
+// =================================================================================================
+// inc.first: Conv2d(1 -> 64, 3x3, pad 1) straight from the unpadded sample, pad_to folded in
+// (models/Unet_FiLmLayer.py:15-34,286,101).  outc: Conv2d(64 -> 1, 1x1) + bias + unpad (:264,310).
+// =================================================================================================
+namespace {
+template <typename T>
+__global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /*[9][64]*/, T* __restrict__ out, long long total,
+                               int H, int W, int rows, int dim, int lh, int lw) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= total) return;
+  const long long r = v >> 3;
+  const int c8 = (int)(v & 7) << 3;
+  const int ww = (int)(r % W);
+  const long long t = r / W;
+  const int hh = (int)(t % H);
+  const long long b = t / H;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap) {
+    const int sh = hh + tap / 3 - 1 - lh, sw = ww + tap % 3 - 1 - lw;  // coordinates in the unpadded sample
+    if (sh < 0 || sh >= rows || sw < 0 || sw >= dim) continue;
+    const float xv = __ldg(x + (b * rows + sh) * dim + sw);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, __ldg(w + tap * 64 + c8 + i), acc[i]);
+  }
+  store8(out + r * 64 + c8, acc);
+}
+
+template <typename T>
+__global__ void outc_kernel(const T* __restrict__ x, int ld, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ eps,
+                            long long total, int H, int W, int C, int rows, int dim, int lh, int lw) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= total) return;
+  const int d = (int)(v % dim);
+  const long long t = v / dim;
+  const int rr = (int)(t % rows);
+  const long long b = t / rows;
+  const long long r = (b * H + rr + lh) * W + d + lw;
+  float acc = 0.f;
+  for (int c = 0; c < C; c += 8) {
+    float t8[8];
+    load8(x + r * ld + c, t8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc = fmaf(t8[i], __ldg(w + c + i), acc);
+  }
+  eps[v] = acc + __ldg(bias);
+}
+
+template <typename T>
+__global__ void to_nchw_kernel(const T* __restrict__ in, int ld, float* __restrict__ out, long long total, int HW, int C) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= total) return;
+  const int p = (int)(v % HW);
+  const long long t = v / HW;
+  const int c = (int)(t % C);
+  const long long b = t / C;
+  out[v] = to_f32<T>(in[(b * HW + p) * ld + c]);
+}
+}  // namespace
+template <typename T> void launch_conv_in(const float* x, const float* w, T* out, int B, int H, int W, int rows, int dim, int lh, int lw, cudaStream_t s) {
+  const long long total = (long long)B * H * W * 8;
+  conv_in_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(x, w, out, total, H, W, rows, dim, lh, lw);
+  COUNT_LAUNCH();
+}
+template <typename T> void launch_outc(const T* x, int ld, const float* w, const float* bias, float* eps, int B, int H, int W, int C, int rows, int dim, int lh, int lw, cudaStream_t s) {
+  const long long total = (long long)B * rows * dim;
+  outc_kernel<T><<<cdiv(total, 128), 128, 0, s>>>(x, ld, w, bias, eps, total, H, W, C, rows, dim, lh, lw);
+  COUNT_LAUNCH();
+}
+template <typename T> void launch_to_nchw(const T* in, int ld, float* out, int B, int HW, int C, cudaStream_t s) {
+  const long long total = (long long)B * HW * C;
+  to_nchw_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(in, ld, out, total, HW, C);
+}
+template void launch_conv_in<float>(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+template void launch_conv_in<bf16>(const float*, const float*, bf16*, int, int, int, int, int, int, int, cudaStream_t);
+template void launch_outc<float>(const float*, int, const float*, const float*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
+template void launch_outc<bf16>(const bf16*, int, const float*, const float*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
+template void launch_to_nchw<float>(const float*, int, float*, int, int, int, cudaStream_t);
+template void launch_to_nchw<bf16>(const bf16*, int, float*, int, int, int, cudaStream_t);
+
+// =================================================================================================
+// Posterior update + add_constraints, one fused elementwise kernel per denoising step:
+//   x0     = (x - c0*eps) / c1                       DDPMScheduler/DDIMScheduler.step (diffusers 0.17.1;
+//   x_prev = k_x0*x0 + k_x*x + k_eps*eps + k_n*z      call sites models/diffusion_ddpm.py:211,274, ddim.py:61,72)
+//   x_prev[:, :inpaint] = inpaint                     models/diffusion_ddpm.py:216-219
+// coef row = {c0, c1, k_x0, k_x, k_eps, k_n, 0, 0}; the row index comes from a device counter so the
+// launch is CUDA-graph replayable.  z is injected (parity) or Philox4x32-10 + Box-Muller (throughput).
+// =================================================================================================
+namespace {
+__device__ __forceinline__ uint32_t mulhilo(uint32_t a, uint32_t b, uint32_t* hi) {
+  const unsigned long long p = (unsigned long long)a * b;
+  *hi = (uint32_t)(p >> 32);
+  return (uint32_t)p;
+}
+__device__ __forceinline__ void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0, hi1;
+    const uint32_t lo0 = mulhilo(0xD2511F53u, c[0], &hi0);
+    const uint32_t lo1 = mulhilo(0xCD9E8D57u, c[2], &hi1);
+    const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+__device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned long long idx, uint32_t step) {
+  uint32_t c[4] = {(uint32_t)(idx >> 1), (uint32_t)(idx >> 33), step, 0x5bd1e995u};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  const float u1 = ((float)(c[0] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float u2 = ((float)(c[1] >> 8) + 0.5f) * (1.0f / 16777216.0f);
+  const float rad = sqrtf(-2.0f * __logf(u1));
+  float sn, cs;
+  __sincosf(6.283185307179586f * u2, &sn, &cs);
+  return (idx & 1) ? rad * sn : rad * cs;
+}
+
+__global__ void step_kernel(StepArgs a) {
+  const long long total = (long long)a.B * a.n;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  int step = a.step_host, use_philox = 0;
+  const float* noise = a.noise;
+  const float* inpaint = a.inpaint;
+  float* history = nullptr;
+  unsigned long long seed = 0;
+  if (a.dyn) {
+    step = a.dyn->step;
+    noise = a.dyn->noise ? a.dyn->noise + (size_t)step * total : nullptr;
+    inpaint = a.dyn->inpaint;
+    history = a.dyn->history;
+    seed = a.dyn->seed;
+    use_philox = a.dyn->use_philox;
+  }
+  const float* cf = a.coef + (size_t)step * 8;
+  const float c0 = cf[0], c1 = cf[1], kx0 = cf[2], kx = cf[3], keps = cf[4], kn = cf[5];
+  const long long b = i / a.n;
+  const int e = (int)(i - b * a.n);
+  float r;
+  if (inpaint && e < a.inpaint_elems) {
+    r = inpaint[b * a.inpaint_elems + e];
+  } else {
+    const float x = a.x[i], ep = a.eps[i];
+    const float x0 = (x - c0 * ep) / c1;
+    r = kx0 * x0 + kx * x;
+    if (keps != 0.f) r += keps * ep;
+    if (kn != 0.f) {
+      float z = 0.f;
+      if (noise) z = noise[i];
+      else if (use_philox) z = philox_normal(seed, (unsigned long long)i, (uint32_t)step);
+      r += kn * z;
+    }
+  }
+  a.x_out[i] = r;
+  if (history) history[(size_t)(step + 1) * total + i] = r;
+}
+__global__ void advance_kernel(int* p, int d) { *p += d; }
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+// DDPMScheduler.add_noise + add_constraints (models/diffusion_ddpm.py:167-168)
+__global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const long long* __restrict__ t,
+                                 const float* __restrict__ sa, const float* __restrict__ sb, const float* __restrict__ inpaint,
+                                 float* __restrict__ out, int n, int inpaint_elems, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long b = i / n;
+  const int e = (int)(i - b * n);
+  if (inpaint && e < inpaint_elems) { out[i] = inpaint[b * inpaint_elems + e]; return; }
+  const long long tb = t[b];
+  out[i] = sa[tb] * x0[i] + sb[tb] * noise[i];
+}
+}  // namespace
+void launch_step(const StepArgs& a, cudaStream_t s) {
+  const long long total = (long long)a.B * a.n;
+  step_kernel<<<cdiv(total, 256), 256, 0, s>>>(a);
+  COUNT_LAUNCH();
+}
+void launch_advance(int* step_ptr, int delta, cudaStream_t s) { advance_kernel<<<1, 1, 0, s>>>(step_ptr, delta); COUNT_LAUNCH(); }
+void launch_set_int(int* p, int v, cudaStream_t s) { set_int_kernel<<<1, 1, 0, s>>>(p, v); COUNT_LAUNCH(); }
+void launch_add_noise(const float* x0, const float* noise, const long long* t, const float* sa, const float* sb, const float* inpaint,
+                      float* out, int n, int inpaint_elems, int B, cudaStream_t s) {
+  const long long total = (long long)B * n;
+  add_noise_kernel<<<cdiv(total, 256), 256, 0, s>>>(x0, noise, t, sa, sb, inpaint, out, n, inpaint_elems, total);
+  COUNT_LAUNCH();
+}
+
+// =================================================================================================
+// Time embedding: pos_encoding (models/Unet_FiLmLayer.py:266-274) -> SiLU -> Linear(256 -> C) for
+// all six stages at once (:136-142): out[row][896] = silu(posenc(t_row)) @ w_cat[256][896] + b_cat.
+// One block per row.
+// =================================================================================================
+namespace {
+__global__ void __launch_bounds__(256) temb_kernel(const long long* __restrict__ t_dev, const float* __restrict__ inv_freq,
+                                                   const float* __restrict__ w_cat, const float* __restrict__ b_cat, float* __restrict__ out, int time_dim) {
+  extern __shared__ float pe[];  // [time_dim]
+  const int row = blockIdx.x;
+  const float t = (float)t_dev[row];
+  const int half = time_dim >> 1;
+  for (int i = threadIdx.x; i < time_dim; i += blockDim.x) {
+    const float arg = t * inv_freq[i < half ? i : i - half];
+    const float v = i < half ? sinf(arg) : cosf(arg);
+    pe[i] = v / (1.f + expf(-v));  // SiLU
+  }
+  __syncthreads();
+  for (int n = threadIdx.x; n < SPDM_TEMB_WIDTH; n += blockDim.x) {
+    float acc = 0.f;
+    for (int k = 0; k < time_dim; ++k) acc = fmaf(pe[k], __ldg(w_cat + (size_t)k * SPDM_TEMB_WIDTH + n), acc);
+    out[(size_t)row * SPDM_TEMB_WIDTH + n] = acc + __ldg(b_cat + n);
+  }
+}
+// Mish (models/Unet_FiLmLayer.py:150): x * tanh(softplus(x)), softplus threshold 20 as torch
+__global__ void mish_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float x = in[i];
+  const float sp = x > 20.f ? x : log1pf(expf(x));
+  out[i] = x * tanhf(sp);
+}
+}  // namespace
+void launch_temb(const long long* t_dev, int n_t, const float* inv_freq, const float* w_cat, const float* b_cat, float* out, int time_dim, cudaStream_t s) {
+  temb_kernel<<<n_t, 256, time_dim * sizeof(float), s>>>(t_dev, inv_freq, w_cat, b_cat, out, time_dim);
+  COUNT_LAUNCH();
+}
+void launch_mish(const float* in, float* out, long long n, cudaStream_t s) {
+  mish_kernel<<<cdiv(n, 256), 256, 0, s>>>(in, out, n);
+  COUNT_LAUNCH();
+}
+
+// =================================================================================================
+// Observation encoder, conv part (models/encoder/autoencoder.py:11-17):
+//   Conv(3->16,k2,s2,p1)+ReLU -> Conv(16->32,k2,s2)+ReLU -> Conv(32->64,k2,s2)+ReLU  on 96x96 frames.
+// k == stride == 2, so the three layers are non-overlapping patch contractions: final pixel (i,j) of
+// the 12x12 map depends only on an 8x8 input patch at rows 8i-1..8i+6 (row/col -1 = zero padding; the
+// 49th conv1 row/col is never consumed).  One block per (frame, final row i): the 8x96x3 input strip
+// is staged in shared memory once and all three layers run out of shared memory.
+// Output feat[frame][(i*12+j)*64 + c]  (HWC order; the Linear weight is repacked to match).
+// =================================================================================================
+namespace {
+__global__ void __launch_bounds__(256) enc_convs_kernel(const float* __restrict__ img, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                        const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
+                                                        const float* __restrict__ b3, float* __restrict__ feat) {
+  __shared__ float s_in[3][8][97];    // [c][r][col+1], col -1 -> index 0
+  __shared__ float s_c1[16][4][48];   // conv1 rows 4i..4i+3, cols 0..47
+  __shared__ float s_c2[32][2][24];
+  const int frame = blockIdx.x / 12, i = blockIdx.x % 12;
+  const float* im = img + (size_t)frame * 3 * 96 * 96;
+  for (int e = threadIdx.x; e < 3 * 8 * 97; e += blockDim.x) {
+    const int col = e % 97 - 1;
+    const int r = (e / 97) % 8;
+    const int c = e / (97 * 8);
+    const int gr = 8 * i - 1 + r;
+    float v = 0.f;
+    if (gr >= 0 && gr < 96 && col >= 0 && col < 96) v = im[((size_t)c * 96 + gr) * 96 + col];
+    s_in[c][r][col + 1] = v;
+  }
+  __syncthreads();
+  // conv1: out (ch, rr, cc) <- input rows 2rr-1+{0,1} (strip rows 2rr+{0,1}), cols 2cc-1+{0,1} (index 2cc+{0,1})
+  for (int e = threadIdx.x; e < 16 * 4 * 48; e += blockDim.x) {
+    const int cc = e % 48, rr = (e / 48) % 4, ch = e / (48 * 4);
+    float acc = __ldg(b1 + ch);
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 2; ++kx)
+          acc = fmaf(s_in[c][2 * rr + ky][2 * cc + kx], __ldg(w1 + ((ch * 3 + c) * 2 + ky) * 2 + kx), acc);
+    s_c1[ch][rr][cc] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * 2 * 24; e += blockDim.x) {
+    const int cc = e % 24, rr = (e / 24) % 2, ch = e / 48;
+    float acc = __ldg(b2 + ch);
+    for (int c = 0; c < 16; ++c)
+#pragma unroll
+      for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 2; ++kx)
+          acc = fmaf(s_c1[c][2 * rr + ky][2 * cc + kx], __ldg(w2 + ((ch * 16 + c) * 2 + ky) * 2 + kx), acc);
+    s_c2[ch][rr][cc] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 64 * 12; e += blockDim.x) {
+    const int ch = e % 64, j = e / 64;
+    float acc = __ldg(b3 + ch);
+    for (int c = 0; c < 32; ++c)
+#pragma unroll
+      for (int ky = 0; ky < 2; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < 2; ++kx)
+          acc = fmaf(s_c2[c][ky][2 * j + kx], __ldg(w3 + ((ch * 32 + c) * 2 + ky) * 2 + kx), acc);
+    feat[(size_t)frame * 9216 + (i * 12 + j) * 64 + ch] = fmaxf(acc, 0.f);
+  }
+}
+
+// prepare_obs_cond_vectors (models/diffusion_ddpm.py:317-330): cat[pos(2), act(3), vel(2), img_feat(128)]
+__global__ void build_cond_kernel(const float* __restrict__ pos, const float* __restrict__ act, const float* __restrict__ vel,
+                                  const float* __restrict__ feat, float* __restrict__ cond, long long total, int cond_dim) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int d = (int)(i % cond_dim);
+  const long long bt = i / cond_dim;
+  float v;
+  if (d < 2) v = pos[bt * 2 + d];
+  else if (d < 5) v = act[bt * 3 + d - 2];
+  else if (d < 7) v = vel[bt * 2 + d - 5];
+  else v = feat[bt * (cond_dim - 7) + d - 7];
+  cond[i] = v;
+}
+}  // namespace
+void launch_enc_convs(const float* img, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
+                      const float* b3, float* feat, int n, cudaStream_t s) {
+  enc_convs_kernel<<<n * 12, 256, 0, s>>>(img, w1, b1, w2, b2, w3, b3, feat);
+  COUNT_LAUNCH();
+}
+void launch_build_cond(const float* pos, const float* act, const float* vel, const float* feat, float* cond, int B, int T, int cond_dim, cudaStream_t s) {
+  const long long total = (long long)B * T * cond_dim;
+  build_cond_kernel<<<cdiv(total, 256), 256, 0, s>>>(pos, act, vel, feat, cond, total, cond_dim);
+  COUNT_LAUNCH();
+}
+
+// =================================================================================================
+// Weight repacking (load_state_dict time; PyTorch layouts -> kernel layouts)
+// =================================================================================================
+namespace {
+__global__ void pack_conv_f32_kernel(const float* __restrict__ oihw, float* __restrict__ out, int Cout, int Cin, int kk) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)Cout * Cin * kk;
+  if (i >= total) return;
+  const int o = (int)(i % Cout);
+  const long long t = i / Cout;
+  const int c = (int)(t % Cin);
+  const int tap = (int)(t / Cin);
+  out[i] = oihw[((size_t)o * Cin + c) * kk + tap];
+}
+__global__ void pack_conv_bf16_kernel(const float* __restrict__ oihw, bf16* __restrict__ out, int Cout, int Cin, int kk) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = (long long)Cout * Cin * kk;
+  if (i >= total) return;
+  const int c = (int)(i % Cin);
+  const long long t = i / Cin;
+  const int tap = (int)(t % kk);
+  const int o = (int)(t / kk);
+  out[i] = __float2bfloat16_rn(oihw[((size_t)o * Cin + c) * kk + tap]);
+}
+__global__ void pack_linear_f32_kernel(const float* __restrict__ nk, float* __restrict__ out, int N, int K, int ld_out, int col_off) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * K) return;
+  const int n = (int)(i % N);
+  const int k = (int)(i / N);
+  out[(size_t)k * ld_out + col_off + n] = nk[(size_t)n * K + k];
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+__global__ void pack_enc_linear_kernel(const float* __restrict__ w, float* __restrict__ out) {
+  // w (128, 9216) with k = c*144 + p  ->  out[(p*64 + c)][128]
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128LL * 9216) return;
+  const int n = (int)(i % 128);
+  const int k2 = (int)(i / 128);
+  const int c = k2 % 64, p = k2 / 64;
+  out[i] = w[(size_t)n * 9216 + c * 144 + p];
+}
+}  // namespace
+void launch_pack_conv_f32(const float* oihw, float* out, int Cout, int Cin, int k, cudaStream_t s) {
+  const long long total = (long long)Cout * Cin * k * k;
+  pack_conv_f32_kernel<<<cdiv(total, 256), 256, 0, s>>>(oihw, out, Cout, Cin, k * k);
+}
+void launch_pack_conv_bf16(const float* oihw, bf16* out, int Cout, int Cin, int k, cudaStream_t s) {
+  const long long total = (long long)Cout * Cin * k * k;
+  pack_conv_bf16_kernel<<<cdiv(total, 256), 256, 0, s>>>(oihw, out, Cout, Cin, k * k);
+}
+void launch_pack_linear_f32(const float* nk, float* out, int N, int K, int ld_out, int col_off, cudaStream_t s) {
+  pack_linear_f32_kernel<<<cdiv((long long)N * K, 256), 256, 0, s>>>(nk, out, N, K, ld_out, col_off);
+}
+void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
+  cast_bf16_kernel<<<cdiv(n, 256), 256, 0, s>>>(in, out, n);
+}
+void launch_pack_enc_linear(const float* w, float* out, cudaStream_t s) {
+  pack_enc_linear_kernel<<<cdiv(128LL * 9216, 256), 256, 0, s>>>(w, out);
+}

@@ -1,0 +1,889 @@
+// plan.cu — the C ABI of libspdm.so (include/spdm.h): plan, weights, U-Net forward, sampling loop.
+//
+// A plan owns the repacked weights, the channels-last activation workspace and the CUDA graphs of
+// one (variant, precision, geometry, batch_max) configuration on one device.  All tensor arguments
+// of the ABI are caller-owned device memory; every call only enqueues work on the caller's stream.
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <functional>
+#include <map>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "../../include/spdm.h"
+#include "common.cuh"
+
+// -------------------------------------------------------------------------------------------------
+// errors
+// -------------------------------------------------------------------------------------------------
+static thread_local char g_err[1024] = "";
+static int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof g_err, fmt, ap);
+  va_end(ap);
+  return -1;
+}
+struct SpdmError { std::string msg; };
+#define CUDA_OK(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t _e = (expr);                                                                            \
+    if (_e != cudaSuccess) {                                                                            \
+      char _b[512];                                                                                     \
+      snprintf(_b, sizeof _b, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+      throw SpdmError{_b};                                                                              \
+    }                                                                                                   \
+  } while (0)
+#define REQUIRE(cond, ...)                              \
+  do {                                                  \
+    if (!(cond)) {                                      \
+      char _b[512];                                     \
+      snprintf(_b, sizeof _b, __VA_ARGS__);             \
+      throw SpdmError{_b};                              \
+    }                                                   \
+  } while (0)
+
+extern "C" const char* spdm_last_error(void) { return g_err; }
+extern "C" const char* spdm_version(void) { return "spdm-b200 0.1 (sm_100a)"; }
+
+// -------------------------------------------------------------------------------------------------
+// plan
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+struct GemmW {  // a 3x3 convolution or a Linear layer
+  int Cin = 0, Cout = 0, taps = 1;
+  float* w32 = nullptr;  // [taps][Cin][Cout]   (fp32 path)
+  bf16* w16 = nullptr;   // [Cout][taps*Cin]    (bf16 tcgen05 path)
+  float* bias = nullptr; // [Cout] or null
+};
+struct NormW { float* g = nullptr; float* b = nullptr; int C = 0; };
+struct AttnW { GemmW in_proj, out_proj, ff1, ff2; NormW ln, ff_ln; int C = 0; };
+struct StageInfo { const char* name; int cin, cout; int temb_off, film_off; };
+
+static const StageInfo kStages[6] = {
+    {"down1", 64, 128, 0, 0},      {"down2", 128, 256, 128, 256}, {"down3", 256, 256, 384, 768},
+    {"up1", 512, 128, 640, 1280},  {"up2", 256, 64, 768, 1536},   {"up3", 128, 64, 832, 1664}};
+
+}  // namespace
+
+struct spdm_plan {
+  spdm_config cfg;
+  bool attention = true, bf16_mode = false, sched_only = false;
+  int H0 = 0, W0 = 0, lh = 0, lw = 0;  // padded geometry (pad_to 8) and low-side pads
+  int Bcap = 0, bm = 1;
+  int G = 0;  // global_cond_dim
+  std::vector<void*> allocs;
+  size_t bytes = 0;
+  long long launches = 0;
+
+  // weights
+  std::map<std::string, GemmW> gemms;
+  std::map<std::string, NormW> norms;
+  std::map<std::string, AttnW*> attn;  // views into gemms/norms
+  float* w_in = nullptr;               // inc.first [9][64]
+  float* w_outc = nullptr; float* b_outc = nullptr;
+  float* temb_w = nullptr; float* temb_b = nullptr;  // [256][896], [896]
+  float* film_w = nullptr; float* film_b = nullptr;  // [G][1792], [1792]
+  float* inv_freq = nullptr;                          // [time_dim/2]
+  float *enc_w1 = nullptr, *enc_b1 = nullptr, *enc_w2 = nullptr, *enc_b2 = nullptr, *enc_w3 = nullptr, *enc_b3 = nullptr;
+  float *enc_wl = nullptr, *enc_bl = nullptr;  // [9216][128], [128]
+  std::map<std::string, std::function<void(const float*, const int64_t*, int, cudaStream_t)>> loaders;
+  std::set<std::string> missing_unet, missing_enc;
+
+  // workspace (T = float or bf16, chosen by precision)
+  void *raw[4] = {}, *hbuf[4] = {}, *abuf[4] = {}, *bbuf[4] = {}, *cat[3] = {};
+  void *a_ln[4] = {}, *a_qkv[4] = {}, *a_att[4] = {}, *a_res[4] = {}, *a_ff[4] = {};
+  float* stats = nullptr;   // [Bcap][SPDM_MAX_PARTIALS][2]
+  float* film = nullptr;    // [Bcap][1792]
+  float* cond = nullptr;    // [Bcap][G]
+  float* cond_mish = nullptr;
+  float* temb_call = nullptr;   // [Bcap][896]  (unet_forward with explicit t)
+  float* temb_table = nullptr;  // [K][896]
+  float* coef = nullptr;        // [K][8]
+  long long* timesteps = nullptr;
+  int K = 0, sched_kind = 0;
+  bool temb_table_dirty = true;
+  bool have_cond = false;
+  float* xt = nullptr; float* eps = nullptr;  // [Bcap][n]
+  StepDyn* dyn = nullptr; StepDyn* dyn_host = nullptr;
+  float* enc_feat = nullptr; int enc_chunk = 0;  // [enc_chunk][9216]
+  float* enc_out = nullptr;                       // [Bcap*T][128]
+
+  std::map<std::string, TcGemm*> tc_cache;
+  // graphs keyed by batch: [0] = graph_steps-step body, [1] = 1-step body
+  struct GraphSet { cudaGraphExec_t multi = nullptr, single = nullptr; long long n_multi = 0, n_single = 0; };
+  std::map<long long, GraphSet> graphs;
+
+  // debug tap
+  std::string tap_name; float* tap_out = nullptr; long long tap_count = -1;
+
+  template <typename T> T* alloc(size_t n) {
+    void* p = nullptr;
+    CUDA_OK(cudaMalloc(&p, n * sizeof(T)));
+    CUDA_OK(cudaMemset(p, 0, n * sizeof(T)));
+    allocs.push_back(p);
+    bytes += n * sizeof(T);
+    return reinterpret_cast<T*>(p);
+  }
+  int n_elems() const { return cfg.rows * cfg.dim; }
+  int levelH(int l) const { return H0 >> l; }
+  int levelW(int l) const { return W0 >> l; }
+};
+
+namespace {
+
+long long total_launches() { return kernels_launch_count() + tc_launch_count(); }
+
+// ---- weight registration -------------------------------------------------------------------------
+void check_shape(const std::string& name, const int64_t* shape, int ndim, std::initializer_list<int64_t> want) {
+  bool ok = (int)want.size() == ndim;
+  int i = 0;
+  if (ok) for (auto w : want) ok = ok && shape[i++] == w;
+  if (!ok) {
+    std::string got, exp;
+    for (int k = 0; k < ndim; ++k) got += std::to_string(shape[k]) + (k + 1 < ndim ? "," : "");
+    for (auto w : want) exp += std::to_string(w) + ",";
+    throw SpdmError{"weight " + name + ": shape (" + got + ") != expected (" + exp + ")"};
+  }
+}
+
+void reg_vec(spdm_plan* p, const std::string& name, float* dst, int n, std::set<std::string>& missing) {
+  missing.insert(name);
+  p->loaders[name] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
+    long long cnt = 1;
+    for (int i = 0; i < ndim; ++i) cnt *= shape[i];
+    REQUIRE(cnt == n, "weight %s: %lld elements, expected %d", name.c_str(), cnt, n);
+    CUDA_OK(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  };
+}
+
+GemmW& reg_conv3(spdm_plan* p, const std::string& name, int Cin, int Cout) {
+  GemmW& g = p->gemms[name];
+  g.Cin = Cin; g.Cout = Cout; g.taps = 9;
+  if (p->bf16_mode) g.w16 = p->alloc<bf16>((size_t)9 * Cin * Cout);
+  else g.w32 = p->alloc<float>((size_t)9 * Cin * Cout);
+  p->missing_unet.insert(name + ".weight");
+  GemmW* gp = &g;
+  bool bfm = p->bf16_mode;
+  p->loaders[name + ".weight"] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
+    check_shape(name + ".weight", shape, ndim, {Cout, Cin, 3, 3});
+    if (bfm) launch_pack_conv_bf16(src, gp->w16, Cout, Cin, 3, s);
+    else launch_pack_conv_f32(src, gp->w32, Cout, Cin, 3, s);
+  };
+  return g;
+}
+
+GemmW& reg_linear(spdm_plan* p, const std::string& wname, const std::string& bname, int K, int N) {
+  GemmW& g = p->gemms[wname];
+  g.Cin = K; g.Cout = N; g.taps = 1;
+  if (p->bf16_mode) g.w16 = p->alloc<bf16>((size_t)K * N);
+  else g.w32 = p->alloc<float>((size_t)K * N);
+  g.bias = p->alloc<float>(N);
+  p->missing_unet.insert(wname);
+  GemmW* gp = &g;
+  bool bfm = p->bf16_mode;
+  p->loaders[wname] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
+    check_shape(wname, shape, ndim, {N, K});
+    if (bfm) launch_cast_bf16(src, gp->w16, (long long)K * N, s);  // (N,K) row-major is already the K-major B operand
+    else launch_pack_linear_f32(src, gp->w32, N, K, N, 0, s);
+  };
+  reg_vec(p, bname, g.bias, N, p->missing_unet);
+  return g;
+}
+
+NormW& reg_norm(spdm_plan* p, const std::string& name, int C) {
+  NormW& n = p->norms[name];
+  n.C = C;
+  n.g = p->alloc<float>(C);
+  n.b = p->alloc<float>(C);
+  reg_vec(p, name + ".weight", n.g, C, p->missing_unet);
+  reg_vec(p, name + ".bias", n.b, C, p->missing_unet);
+  return n;
+}
+
+void reg_double_conv(spdm_plan* p, const std::string& name, int Cin, int Cout, bool first_is_input_layer = false) {
+  if (!first_is_input_layer) reg_conv3(p, name + ".first", Cin, Cout);
+  reg_conv3(p, name + ".second", Cout, Cout);
+  reg_norm(p, name + ".norm", Cout);
+}
+
+void register_weights(spdm_plan* p) {
+  const int TD = p->cfg.time_dim;
+  // inc
+  p->w_in = p->alloc<float>(9 * 64);
+  p->missing_unet.insert("inc.first.weight");
+  {
+    float* dst = p->w_in;
+    p->loaders["inc.first.weight"] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
+      check_shape("inc.first.weight", shape, ndim, {64, 1, 3, 3});
+      launch_pack_conv_f32(src, dst, 64, 1, 3, s);
+    };
+  }
+  reg_double_conv(p, "inc", 1, 64, true);
+  p->temb_w = p->alloc<float>((size_t)TD * SPDM_TEMB_WIDTH);
+  p->temb_b = p->alloc<float>(SPDM_TEMB_WIDTH);
+  if (p->G > 0) {
+    p->film_w = p->alloc<float>((size_t)p->G * SPDM_FILM_WIDTH);
+    p->film_b = p->alloc<float>(SPDM_FILM_WIDTH);
+  }
+  for (const StageInfo& st : kStages) {
+    const std::string n = st.name;
+    reg_double_conv(p, n + ".doubleConv1", st.cin, st.cin);
+    reg_double_conv(p, n + ".doubleConv2", st.cin, st.cout);
+    {
+      const std::string wn = n + ".emb_layer.1.weight";
+      p->missing_unet.insert(wn);
+      float* dst = p->temb_w;
+      const int C = st.cout, off = st.temb_off;
+      p->loaders[wn] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
+        check_shape(wn, shape, ndim, {C, TD});
+        launch_pack_linear_f32(src, dst, C, TD, SPDM_TEMB_WIDTH, off, s);
+      };
+      reg_vec(p, n + ".emb_layer.1.bias", p->temb_b + off, C, p->missing_unet);
+    }
+    if (p->G > 0) {
+      const std::string wn = n + ".cond_encoder.2.weight";
+      p->missing_unet.insert(wn);
+      float* dst = p->film_w;
+      const int C2 = 2 * st.cout, off = st.film_off, G = p->G;
+      p->loaders[wn] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
+        check_shape(wn, shape, ndim, {C2, G});
+        launch_pack_linear_f32(src, dst, C2, G, SPDM_FILM_WIDTH, off, s);
+      };
+      reg_vec(p, n + ".cond_encoder.2.bias", p->film_b + off, C2, p->missing_unet);
+    }
+  }
+  reg_double_conv(p, "bot1", 256, 512);
+  reg_double_conv(p, "bot2", 512, 512);
+  reg_double_conv(p, "bot3", 512, 256);
+  if (p->attention) {
+    const struct { const char* n; int C; } sas[6] = {{"sa1", 128}, {"sa2", 256}, {"sa3", 256}, {"sa4", 128}, {"sa5", 64}, {"sa6", 64}};
+    for (auto& sa : sas) {
+      const std::string n = sa.n;
+      const int C = sa.C;
+      reg_linear(p, n + ".attention.in_proj_weight", n + ".attention.in_proj_bias", C, 3 * C);
+      reg_linear(p, n + ".attention.out_proj.weight", n + ".attention.out_proj.bias", C, C);
+      reg_norm(p, n + ".ln", C);
+      reg_norm(p, n + ".ff_self.0", C);
+      reg_linear(p, n + ".ff_self.1.weight", n + ".ff_self.1.bias", C, C);
+      reg_linear(p, n + ".ff_self.3.weight", n + ".ff_self.3.bias", C, C);
+    }
+  }
+  p->w_outc = p->alloc<float>(64);
+  p->b_outc = p->alloc<float>(1);
+  reg_vec(p, "outc.weight", p->w_outc, 64, p->missing_unet);
+  reg_vec(p, "outc.bias", p->b_outc, 1, p->missing_unet);
+
+  // sinusoidal frequencies (models/Unet_FiLmLayer.py:267-270); overridable with the exact torch values
+  {
+    std::vector<float> f(TD / 2);
+    for (int i = 0; i < TD / 2; ++i) {
+      const float e = (float)(2 * i) / (float)TD;
+      f[i] = 1.0f / powf(10000.0f, e);
+    }
+    p->inv_freq = p->alloc<float>(TD / 2);
+    CUDA_OK(cudaMemcpy(p->inv_freq, f.data(), f.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::set<std::string> dummy;
+    reg_vec(p, "pos_encoding.inv_freq", p->inv_freq, TD / 2, dummy);
+  }
+  // vision encoder (models/encoder/autoencoder.py:11-20)
+  p->enc_w1 = p->alloc<float>(16 * 3 * 4);   p->enc_b1 = p->alloc<float>(16);
+  p->enc_w2 = p->alloc<float>(32 * 16 * 4);  p->enc_b2 = p->alloc<float>(32);
+  p->enc_w3 = p->alloc<float>(64 * 32 * 4);  p->enc_b3 = p->alloc<float>(64);
+  p->enc_wl = p->alloc<float>((size_t)9216 * 128);  p->enc_bl = p->alloc<float>(128);
+  reg_vec(p, "vision_encoder.0.weight", p->enc_w1, 16 * 3 * 4, p->missing_enc);
+  reg_vec(p, "vision_encoder.0.bias", p->enc_b1, 16, p->missing_enc);
+  reg_vec(p, "vision_encoder.2.weight", p->enc_w2, 32 * 16 * 4, p->missing_enc);
+  reg_vec(p, "vision_encoder.2.bias", p->enc_b2, 32, p->missing_enc);
+  reg_vec(p, "vision_encoder.4.weight", p->enc_w3, 64 * 32 * 4, p->missing_enc);
+  reg_vec(p, "vision_encoder.4.bias", p->enc_b3, 64, p->missing_enc);
+  p->missing_enc.insert("vision_encoder.7.weight");
+  {
+    float* dst = p->enc_wl;
+    p->loaders["vision_encoder.7.weight"] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
+      check_shape("vision_encoder.7.weight", shape, ndim, {128, 9216});
+      launch_pack_enc_linear(src, dst, s);
+    };
+  }
+  reg_vec(p, "vision_encoder.7.bias", p->enc_bl, 128, p->missing_enc);
+}
+
+// ---- workspace -----------------------------------------------------------------------------------
+template <typename T> void alloc_workspace(spdm_plan* p) {
+  static const int cmax[4] = {128, 256, 512, 512};
+  static const int catt[4] = {64, 128, 256, 256};
+  const size_t Bc = p->Bcap;
+  for (int l = 0; l < 4; ++l) {
+    const size_t hw = (size_t)p->levelH(l) * p->levelW(l);
+    p->raw[l] = p->alloc<T>(Bc * hw * cmax[l]);
+    p->hbuf[l] = p->alloc<T>(Bc * hw * cmax[l]);
+    p->abuf[l] = p->alloc<T>(Bc * hw * cmax[l]);
+    p->bbuf[l] = p->alloc<T>(Bc * hw * cmax[l]);
+    if (l < 3) p->cat[l] = p->alloc<T>(Bc * hw * cmax[l]);
+    if (p->attention) {
+      p->a_ln[l] = p->alloc<T>(Bc * hw * catt[l]);
+      p->a_qkv[l] = p->alloc<T>(Bc * hw * catt[l] * 3);
+      p->a_att[l] = p->alloc<T>(Bc * hw * catt[l]);
+      p->a_res[l] = p->alloc<T>(Bc * hw * catt[l]);
+      p->a_ff[l] = p->alloc<T>(Bc * hw * catt[l]);
+    }
+  }
+}
+
+// ---- forward -------------------------------------------------------------------------------------
+struct FwdCtx {
+  const float* x;        // (B,1,rows,dim) fp32
+  float* out;            // (B,1,rows,dim) fp32
+  const float* temb;     // rows of SPDM_TEMB_WIDTH
+  int temb_mode;
+  const int* step_ptr;
+  const float* film;     // [B][1792] or null
+  int B;
+  cudaStream_t s;
+};
+
+template <typename T> struct Fwd {
+  spdm_plan* p;
+  FwdCtx c;
+  int curP = 1;
+  int Bpad;
+
+  Fwd(spdm_plan* p_, const FwdCtx& c_) : p(p_), c(c_) { Bpad = ((c.B + p->bm - 1) / p->bm) * p->bm; }
+
+  T* buf(void* v) { return reinterpret_cast<T*>(v); }
+
+  void tap(const std::string& name, const T* ptr, int ld, int C, int level) {
+    if (p->tap_out && p->tap_name == name) {
+      const int hw = p->levelH(level) * p->levelW(level);
+      launch_to_nchw<T>(ptr, ld, p->tap_out, c.B, hw, C, c.s);
+      p->tap_count = (long long)c.B * hw * C;
+    }
+  }
+
+  // conv / linear: in [M,Cin] (ld_in) -> out [M,Cout] (ld_out)
+  void gemm(const std::string& wname, const T* in, int ld_in, int level, T* out, int ld_out, int flags, const T* resid = nullptr,
+            int ld_res = 0) {
+    auto it = p->gemms.find(wname);
+    REQUIRE(it != p->gemms.end(), "internal: unknown gemm %s", wname.c_str());
+    GemmW& g = it->second;
+    const int H = p->levelH(level), W = p->levelW(level);
+    if constexpr (sizeof(T) == 2) {
+      char key[160];
+      snprintf(key, sizeof key, "%s|%p|%d", wname.c_str(), (const void*)in, ld_in);
+      TcGemm*& tc = p->tc_cache[key];
+      if (!tc) {
+        tc = tc_gemm_create(reinterpret_cast<const bf16*>(in), ld_in, g.w16, g.Cin, g.Cout, g.taps, H, W, p->Bcap);
+        REQUIRE(tc != nullptr, "%s: %s", wname.c_str(), tc_last_error());
+        REQUIRE(tc_gemm_partials(tc) <= SPDM_MAX_PARTIALS, "%s: too many GroupNorm partials", wname.c_str());
+      }
+      tc_gemm_launch(tc, reinterpret_cast<bf16*>(out), ld_out, p->stats, (flags & EPI_BIAS) ? g.bias : nullptr,
+                     reinterpret_cast<const bf16*>(resid), ld_res, flags, Bpad, c.s);
+      curP = tc_gemm_partials(tc);
+    } else {
+      GemmSimtArgs a{};
+      a.in = in; a.w = g.w32; a.bias = (flags & EPI_BIAS) ? g.bias : nullptr; a.resid = (flags & EPI_RESID) ? resid : nullptr;
+      a.out = out; a.M = c.B * H * W; a.Cin = g.Cin; a.Cout = g.Cout; a.ld_in = ld_in; a.ld_out = ld_out; a.ld_res = ld_res;
+      a.H = H; a.W = W; a.taps = g.taps; a.act = (flags & EPI_GELU) ? ACT_GELU : ACT_NONE;
+      launch_gemm_simt<float, float>(a, c.s);
+      if (flags & EPI_STATS) {
+        launch_stats<T>(out, p->stats, c.B, H * W, g.Cout, ld_out, c.s);
+        curP = 1;
+      }
+    }
+  }
+
+  void apply(const std::string& norm, const T* raw, int ld_in, int C, int level, T* out, int ld_out, int act, const StageInfo* st) {
+    NormW& n = p->norms[norm];
+    ApplyArgs a{};
+    a.raw = raw; a.out = out; a.stats = p->stats; a.P = curP; a.gamma = n.g; a.beta = n.b;
+    a.temb = nullptr; a.temb_mode = TEMB_NONE; a.film = nullptr;
+    if (st) {
+      a.temb = c.temb; a.temb_mode = c.temb_mode; a.temb_off = st->temb_off; a.step_ptr = c.step_ptr;
+      if (c.film) { a.film = c.film; a.film_off = st->film_off; }
+    }
+    a.HW = p->levelH(level) * p->levelW(level); a.C = C; a.ld_in = ld_in; a.ld_out = ld_out; a.act = act; a.eps = 1e-5f;
+    launch_apply<T, T>(a, c.B, c.s);
+  }
+
+  // DoubleConvolution (models/Unet_FiLmLayer.py:85-115); `first_done`: raw already holds conv1's output
+  void double_conv(const std::string& name, const T* in, int ld_in, int Cout, int level, T* out, int ld_out, const StageInfo* st,
+                   bool first_done = false) {
+    T* raw = buf(p->raw[level]);
+    T* h = buf(p->hbuf[level]);
+    if (!first_done) gemm(name + ".first", in, ld_in, level, raw, Cout, EPI_STATS);
+    tap(name + ".first", raw, Cout, Cout, level);
+    apply(name + ".norm", raw, Cout, Cout, level, h, Cout, ACT_GELU, nullptr);
+    gemm(name + ".second", h, Cout, level, raw, Cout, EPI_STATS);
+    tap(name + ".second", raw, Cout, Cout, level);
+    apply(name + ".norm", raw, Cout, Cout, level, out, ld_out, ACT_NONE, st);
+  }
+
+  // SelfAttention (models/Unet_FiLmLayer.py:44-82)
+  void self_attention(const std::string& name, const T* x, int ld_x, int C, int level, T* out, int ld_out) {
+    const int L = p->levelH(level) * p->levelW(level);
+    const long long M = (long long)c.B * L;
+    T* ln = buf(p->a_ln[level]); T* qkv = buf(p->a_qkv[level]); T* att = buf(p->a_att[level]);
+    T* res = buf(p->a_res[level]); T* ff = buf(p->a_ff[level]);
+    NormW& n1 = p->norms[name + ".ln"];
+    NormW& n2 = p->norms[name + ".ff_self.0"];
+    launch_layernorm<T>(x, ld_x, ln, C, n1.g, n1.b, M, C, c.s);
+    gemm(name + ".attention.in_proj_weight", ln, C, level, qkv, 3 * C, EPI_BIAS);
+    launch_sdpa<T>(qkv, att, c.B, L, C, 4, c.s);
+    gemm(name + ".attention.out_proj.weight", att, C, level, res, C, EPI_BIAS | EPI_RESID, x, ld_x);
+    launch_layernorm<T>(res, C, ln, C, n2.g, n2.b, M, C, c.s);
+    gemm(name + ".ff_self.1.weight", ln, C, level, ff, C, EPI_BIAS | EPI_GELU);
+    gemm(name + ".ff_self.3.weight", ff, C, level, out, ld_out, EPI_BIAS | EPI_RESID, res, C);
+  }
+
+  // UNet_Film.forward (models/Unet_FiLmLayer.py:277-312) / UNet_Film_noAttention.forward
+  void run() {
+    const int rows = p->cfg.rows, dim = p->cfg.dim;
+    T* cat3 = buf(p->cat[0]); T* cat2 = buf(p->cat[1]); T* cat1 = buf(p->cat[2]);
+    // ---- inc ----
+    launch_conv_in<T>(c.x, p->w_in, buf(p->raw[0]), c.B, p->H0, p->W0, rows, dim, p->lh, p->lw, c.s);
+    launch_stats<T>(buf(p->raw[0]), p->stats, c.B, p->H0 * p->W0, 64, 64, c.s);
+    curP = 1;
+    double_conv("inc", nullptr, 0, 64, 0, cat3 + 64, 128, nullptr, true);  // x1 -> skip slot of up3
+    tap("x1", cat3 + 64, 128, 64, 0);
+    tap("inc", cat3 + 64, 128, 64, 0);
+
+    // ---- down path ----
+    struct DownCfg { int stage; const char* sa; const T* in; int ld_in; int level; T* dest; int ld_dest; const char* tapname; };
+    const DownCfg downs[3] = {
+        {0, "sa1", cat3 + 64, 128, 1, cat2 + 128, 256, "x2"},
+        {1, "sa2", cat2 + 128, 256, 2, cat1 + 256, 512, "x3"},
+        {2, "sa3", cat1 + 256, 512, 3, buf(p->bbuf[3]), 256, "x4"}};
+    for (const DownCfg& d : downs) {
+      const StageInfo& st = kStages[d.stage];
+      const int l = d.level;
+      T* a = buf(p->abuf[l]); T* b = buf(p->bbuf[l]);
+      launch_pool<T>(d.in, d.ld_in, a, st.cin, c.B, p->levelH(l), p->levelW(l), st.cin, c.s);
+      double_conv(std::string(st.name) + ".doubleConv1", a, st.cin, st.cin, l, b, st.cin, nullptr);
+      if (p->attention) {
+        double_conv(std::string(st.name) + ".doubleConv2", b, st.cin, st.cout, l, a, st.cout, &st);
+        tap(st.name, a, st.cout, st.cout, l);
+        self_attention(d.sa, a, st.cout, st.cout, l, d.dest, d.ld_dest);
+        tap(d.sa, d.dest, d.ld_dest, st.cout, l);
+      } else {
+        double_conv(std::string(st.name) + ".doubleConv2", b, st.cin, st.cout, l, d.dest, d.ld_dest, &st);
+        tap(st.name, d.dest, d.ld_dest, st.cout, l);
+      }
+      tap(d.tapname, d.dest, d.ld_dest, st.cout, l);
+    }
+    // ---- bottleneck ----
+    T* a3 = buf(p->abuf[3]); T* b3 = buf(p->bbuf[3]);
+    double_conv("bot1", b3, 256, 512, 3, a3, 512, nullptr);
+    tap("bot1", a3, 512, 512, 3);
+    double_conv("bot2", a3, 512, 512, 3, b3, 512, nullptr);
+    tap("bot2", b3, 512, 512, 3);
+    double_conv("bot3", b3, 512, 256, 3, a3, 256, nullptr);
+    tap("bot3", a3, 256, 256, 3);
+    tap("x5", a3, 256, 256, 3);
+
+    // ---- up path ----
+    struct UpCfg { int stage; const char* sa; const T* low; int c_low; int level; T* catbuf; const char* tapname; };
+    const UpCfg ups[3] = {
+        {3, "sa4", a3, 256, 2, cat1, "u1"}, {4, "sa5", buf(p->bbuf[2]), 128, 1, cat2, "u2"}, {5, "sa6", buf(p->bbuf[1]), 64, 0, cat3, "u3"}};
+    for (const UpCfg& u : ups) {
+      const StageInfo& st = kStages[u.stage];
+      const int l = u.level;
+      T* a = buf(p->abuf[l]); T* b = buf(p->bbuf[l]);
+      launch_upsample<T>(u.low, u.c_low, u.catbuf, st.cin, c.B, p->levelH(l + 1), p->levelW(l + 1), u.c_low, c.s);
+      double_conv(std::string(st.name) + ".doubleConv1", u.catbuf, st.cin, st.cin, l, a, st.cin, nullptr);
+      if (p->attention) {
+        // doubleConv2 reads a, writes a (safe: the input is dead once its first conv has run)
+        double_conv(std::string(st.name) + ".doubleConv2", a, st.cin, st.cout, l, a, st.cout, &st);
+        tap(st.name, a, st.cout, st.cout, l);
+        self_attention(u.sa, a, st.cout, st.cout, l, b, st.cout);
+        tap(u.sa, b, st.cout, st.cout, l);
+      } else {
+        double_conv(std::string(st.name) + ".doubleConv2", a, st.cin, st.cout, l, b, st.cout, &st);
+        tap(st.name, b, st.cout, st.cout, l);
+      }
+      tap(u.tapname, b, st.cout, st.cout, l);
+    }
+    // ---- outc + unpad ----
+    launch_outc<T>(buf(p->bbuf[0]), 64, p->w_outc, p->b_outc, c.out, c.B, p->H0, p->W0, 64, rows, dim, p->lh, p->lw, c.s);
+  }
+};
+
+void run_forward(spdm_plan* p, const FwdCtx& c) {
+  if (p->bf16_mode) { Fwd<bf16> f(p, c); f.run(); }
+  else { Fwd<float> f(p, c); f.run(); }
+}
+
+void check_ready(spdm_plan* p) {
+  if (p->sched_only) throw SpdmError{"this plan was created scheduler-only (SPDM_FLAG_SCHEDULER_ONLY)"};
+  if (!p->missing_unet.empty()) throw SpdmError{"U-Net weights missing, first: " + *p->missing_unet.begin()};
+}
+
+void ensure_temb_table(spdm_plan* p, cudaStream_t s) {
+  REQUIRE(p->K > 0, "no schedule set (spdm_plan_set_schedule)");
+  if (!p->temb_table_dirty) return;
+  launch_temb(p->timesteps, p->K, p->inv_freq, p->temb_w, p->temb_b, p->temb_table, p->cfg.time_dim, s);
+  p->temb_table_dirty = false;
+}
+
+void compute_film(spdm_plan* p, int B, cudaStream_t s) {
+  launch_mish(p->cond, p->cond_mish, (long long)B * p->G, s);
+  GemmSimtArgs a{};
+  a.in = p->cond_mish; a.w = p->film_w; a.bias = p->film_b; a.out = p->film; a.M = B; a.Cin = p->G; a.Cout = SPDM_FILM_WIDTH;
+  a.ld_in = p->G; a.ld_out = SPDM_FILM_WIDTH; a.H = 1; a.W = 1; a.taps = 1; a.act = ACT_NONE;
+  launch_gemm_simt<float, float>(a, s);
+  p->have_cond = true;
+}
+
+void one_step(spdm_plan* p, int B, bool use_film, cudaStream_t s) {
+  FwdCtx c{};
+  c.x = p->xt; c.out = p->eps; c.temb = p->temb_table; c.temb_mode = TEMB_STEP; c.step_ptr = &p->dyn->step;
+  c.film = use_film ? p->film : nullptr; c.B = B; c.s = s;
+  run_forward(p, c);
+  StepArgs a{};
+  a.x = p->xt; a.eps = p->eps; a.x_out = p->xt; a.coef = p->coef; a.dyn = p->dyn; a.n = p->n_elems();
+  a.inpaint_elems = p->cfg.inpaint_rows * p->cfg.dim; a.B = B;
+  launch_step(a, s);
+  launch_advance(&p->dyn->step, 1, s);
+}
+
+}  // namespace
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+#define API_BEGIN try {
+#define API_END                                   \
+  }                                               \
+  catch (const SpdmError& e) { return fail("%s", e.msg.c_str()); } \
+  catch (const std::exception& e) { return fail("%s", e.what()); }
+
+static void check_async(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) throw SpdmError{std::string(what) + ": " + cudaGetErrorString(e)};
+}
+
+extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
+  API_BEGIN
+  REQUIRE(out && cfg, "null argument");
+  REQUIRE(cfg->rows > 0 && cfg->dim > 0 && cfg->batch_max > 0, "rows/dim/batch_max must be positive");
+  REQUIRE(cfg->time_dim > 0 && cfg->time_dim % 2 == 0 && cfg->time_dim <= 4096, "bad time_dim");
+  REQUIRE(cfg->precision == SPDM_PRECISION_FP32 || cfg->precision == SPDM_PRECISION_BF16, "bad precision");
+  REQUIRE(cfg->inpaint_rows >= 0 && cfg->inpaint_rows <= cfg->rows, "bad inpaint_rows");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) throw SpdmError{"no CUDA device: libspdm has no CPU fallback"};
+  CUDA_OK(cudaSetDevice(cfg->device));
+  cudaDeviceProp prop;
+  CUDA_OK(cudaGetDeviceProperties(&prop, cfg->device));
+  REQUIRE(prop.major == 10, "libspdm is built for sm_100a only (device is sm_%d%d)", prop.major, prop.minor);
+  spdm_plan* p = new spdm_plan();
+  p->cfg = *cfg;
+  p->attention = cfg->variant == SPDM_VARIANT_ATTENTION;
+  p->bf16_mode = cfg->precision == SPDM_PRECISION_BF16;
+  // pad_to(x, 8): models/Unet_FiLmLayer.py:15-34
+  auto up8 = [](int v) { return v % 8 ? v + 8 - v % 8 : v; };
+  p->H0 = up8(cfg->rows); p->W0 = up8(cfg->dim);
+  p->lh = (p->H0 - cfg->rows) / 2; p->lw = (p->W0 - cfg->dim) / 2;
+  p->G = cfg->obs_horizon * cfg->cond_dim;
+  try {
+    if (p->bf16_mode) {
+      REQUIRE(p->W0 <= 128 && 128 % p->W0 == 0, "bf16 path: padded width %d must divide 128", p->W0);
+      p->bm = tc_batch_multiple(p->levelH(3), p->levelW(3));
+      for (int l = 0; l < 4; ++l) {
+        const int hw = p->levelH(l) * p->levelW(l);
+        REQUIRE(hw >= 128 ? hw % 128 == 0 || (128 % p->levelW(l) == 0 && p->levelH(l) % (128 / p->levelW(l)) == 0) : 128 % hw == 0,
+                "bf16 path: level %d geometry %dx%d is not tileable into 128-row tiles", l, p->levelH(l), p->levelW(l));
+      }
+    }
+    p->Bcap = ((cfg->batch_max + p->bm - 1) / p->bm) * p->bm;
+    p->sched_only = (cfg->flags & SPDM_FLAG_SCHEDULER_ONLY) != 0;  // scheduler-only plan: spdm_step / spdm_add_noise, no U-Net
+    if (p->sched_only) { *out = p; return 0; }
+    register_weights(p);
+    if (p->bf16_mode) alloc_workspace<bf16>(p); else alloc_workspace<float>(p);
+    p->stats = p->alloc<float>((size_t)p->Bcap * SPDM_MAX_PARTIALS * 2);
+    p->temb_call = p->alloc<float>((size_t)p->Bcap * SPDM_TEMB_WIDTH);
+    if (p->G > 0) {
+      p->film = p->alloc<float>((size_t)p->Bcap * SPDM_FILM_WIDTH);
+      p->cond = p->alloc<float>((size_t)p->Bcap * p->G);
+      p->cond_mish = p->alloc<float>((size_t)p->Bcap * p->G);
+    }
+    p->xt = p->alloc<float>((size_t)p->Bcap * p->n_elems());
+    p->eps = p->alloc<float>((size_t)p->Bcap * p->n_elems());
+    p->dyn = p->alloc<StepDyn>(1);
+    CUDA_OK(cudaMallocHost((void**)&p->dyn_host, sizeof(StepDyn)));
+  } catch (...) {
+    for (void* q : p->allocs) cudaFree(q);
+    delete p;
+    throw;
+  }
+  *out = p;
+  return 0;
+  API_END
+}
+
+extern "C" int spdm_plan_destroy(spdm_plan* p) {
+  if (!p) return 0;
+  cudaDeviceSynchronize();
+  for (auto& kv : p->graphs) {
+    if (kv.second.multi) cudaGraphExecDestroy(kv.second.multi);
+    if (kv.second.single) cudaGraphExecDestroy(kv.second.single);
+  }
+  for (auto& kv : p->tc_cache) tc_gemm_destroy(kv.second);
+  for (void* q : p->allocs) cudaFree(q);
+  if (p->dyn_host) cudaFreeHost(p->dyn_host);
+  delete p;
+  return 0;
+}
+
+extern "C" int spdm_plan_load_weight(spdm_plan* p, const char* name, const float* src, const int64_t* shape, int32_t ndim, void* stream) {
+  API_BEGIN
+  REQUIRE(p && name && src && shape, "null argument");
+  auto it = p->loaders.find(name);
+  REQUIRE(it != p->loaders.end(), "unexpected weight name '%s'", name);
+  it->second(src, shape, ndim, (cudaStream_t)stream);
+  check_async("load_weight");
+  p->missing_unet.erase(name);
+  p->missing_enc.erase(name);
+  p->temb_table_dirty = true;
+  return 0;
+  API_END
+}
+
+extern "C" int spdm_plan_missing_weights(spdm_plan* p) {
+  if (!p) return fail("null plan");
+  std::string s;
+  for (auto& n : p->missing_unet) s += n + " ";
+  for (auto& n : p->missing_enc) s += n + " ";
+  snprintf(g_err, sizeof g_err, "%s", s.c_str());
+  return (int)(p->missing_unet.size() + p->missing_enc.size());
+}
+
+extern "C" int spdm_plan_set_schedule(spdm_plan* p, int32_t kind, int32_t K, const float* coef, const int64_t* timesteps, void* stream) {
+  API_BEGIN
+  REQUIRE(p && coef && timesteps && K > 0, "bad argument");
+  REQUIRE(kind == SPDM_SCHED_DDPM || kind == SPDM_SCHED_DDIM, "bad schedule kind");
+  cudaStream_t s = (cudaStream_t)stream;
+  if (K > p->K || !p->coef) {  // grow (old buffers stay in the plan's allocation list)
+    p->coef = p->alloc<float>((size_t)K * 8);
+    p->timesteps = p->alloc<long long>(K);
+    p->temb_table = p->alloc<float>((size_t)K * SPDM_TEMB_WIDTH);
+    for (auto& kv : p->graphs) {  // graphs bake the table pointers
+      if (kv.second.multi) cudaGraphExecDestroy(kv.second.multi);
+      if (kv.second.single) cudaGraphExecDestroy(kv.second.single);
+    }
+    p->graphs.clear();
+  }
+  CUDA_OK(cudaStreamSynchronize(s));
+  CUDA_OK(cudaMemcpy(p->coef, coef, (size_t)K * 8 * sizeof(float), cudaMemcpyHostToDevice));
+  CUDA_OK(cudaMemcpy(p->timesteps, timesteps, (size_t)K * sizeof(long long), cudaMemcpyHostToDevice));
+  p->K = K; p->sched_kind = kind; p->temb_table_dirty = true;
+  return 0;
+  API_END
+}
+
+extern "C" int spdm_encode_images(spdm_plan* p, const float* images, float* out, int32_t n, void* stream) {
+  API_BEGIN
+  REQUIRE(p && images && out && n > 0, "bad argument");
+  if (!p->missing_enc.empty()) throw SpdmError{"vision encoder weights missing, first: " + *p->missing_enc.begin()};
+  cudaStream_t s = (cudaStream_t)stream;
+  if (!p->enc_feat) { p->enc_chunk = 4096; p->enc_feat = p->alloc<float>((size_t)p->enc_chunk * 9216); }
+  for (int f0 = 0; f0 < n; f0 += p->enc_chunk) {
+    const int m = n - f0 < p->enc_chunk ? n - f0 : p->enc_chunk;
+    launch_enc_convs(images + (size_t)f0 * 3 * 96 * 96, p->enc_w1, p->enc_b1, p->enc_w2, p->enc_b2, p->enc_w3, p->enc_b3, p->enc_feat, m, s);
+    GemmSimtArgs a{};
+    a.in = p->enc_feat; a.w = p->enc_wl; a.bias = p->enc_bl; a.out = out + (size_t)f0 * 128; a.M = m; a.Cin = 9216; a.Cout = 128;
+    a.ld_in = 9216; a.ld_out = 128; a.H = 1; a.W = 1; a.taps = 1; a.act = ACT_NONE;
+    launch_gemm_simt<float, float>(a, s);
+  }
+  check_async("encode_images");
+  return 0;
+  API_END
+}
+
+extern "C" int spdm_set_cond(spdm_plan* p, const float* obs_cond, int32_t B, void* stream) {
+  API_BEGIN
+  REQUIRE(p && obs_cond && B > 0 && B <= p->cfg.batch_max, "bad argument (B=%d, batch_max=%d)", B, p ? p->cfg.batch_max : 0);
+  REQUIRE(p->G > 0, "plan was created unconditional (cond_dim == 0)");
+  check_ready(p);
+  cudaStream_t s = (cudaStream_t)stream;
+  CUDA_OK(cudaMemcpyAsync(p->cond, obs_cond, (size_t)B * p->G * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  compute_film(p, B, s);
+  check_async("set_cond");
+  return 0;
+  API_END
+}
+
+extern "C" int spdm_encode_cond(spdm_plan* p, const float* images, const float* position, const float* action, const float* velocity,
+                                int32_t B, void* stream) {
+  API_BEGIN
+  REQUIRE(p && images && position && action && velocity && B > 0 && B <= p->cfg.batch_max, "bad argument");
+  REQUIRE(p->cfg.cond_dim == 135, "encode_cond needs cond_dim == 135 (2 pos + 3 act + 2 vel + 128 image features)");
+  check_ready(p);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int T = p->cfg.obs_horizon;
+  if (!p->enc_out) p->enc_out = p->alloc<float>((size_t)p->Bcap * T * 128);
+  int rc = spdm_encode_images(p, images, p->enc_out, B * T, stream);
+  if (rc) return rc;
+  launch_build_cond(position, action, velocity, p->enc_out, p->cond, B, T, p->cfg.cond_dim, s);
+  compute_film(p, B, s);
+  check_async("encode_cond");
+  return 0;
+  API_END
+}
+
+extern "C" int spdm_get_cond(spdm_plan* p, float* out, int32_t B, void* stream) {
+  API_BEGIN
+  REQUIRE(p && out && B > 0 && B <= p->cfg.batch_max && p->G > 0, "bad argument");
+  CUDA_OK(cudaMemcpyAsync(out, p->cond, (size_t)B * p->G * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+  return 0;
+  API_END
+}
+
+static int unet_forward_impl(spdm_plan* p, const float* x, const int64_t* t, int32_t t_count, const float* y, int32_t use_cached_cond,
+                             float* out, int32_t B, void* stream) {
+  REQUIRE(p && x && t && out, "null argument");
+  REQUIRE(B > 0 && B <= p->cfg.batch_max, "B=%d outside 1..batch_max=%d", B, p->cfg.batch_max);
+  REQUIRE(t_count == 1 || t_count == B, "t_count must be 1 or B");
+  check_ready(p);
+  cudaStream_t s = (cudaStream_t)stream;
+  const float* film = nullptr;
+  if (y) {
+    REQUIRE(p->G > 0, "plan was created unconditional");
+    CUDA_OK(cudaMemcpyAsync(p->cond, y, (size_t)B * p->G * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    compute_film(p, B, s);
+    film = p->film;
+  } else if (use_cached_cond) {
+    REQUIRE(p->have_cond, "no cached conditioning (call spdm_set_cond / spdm_encode_cond)");
+    film = p->film;
+  }
+  launch_temb(reinterpret_cast<const long long*>(t), t_count, p->inv_freq, p->temb_w, p->temb_b, p->temb_call, p->cfg.time_dim, s);
+  FwdCtx c{};
+  c.x = x; c.out = out; c.temb = p->temb_call; c.temb_mode = t_count == 1 ? TEMB_ROW0 : TEMB_PER_SAMPLE; c.step_ptr = nullptr;
+  c.film = film; c.B = B; c.s = s;
+  const long long before = total_launches();
+  run_forward(p, c);
+  p->launches += total_launches() - before + 1;
+  check_async("unet_forward");
+  return 0;
+}
+
+extern "C" int spdm_unet_forward(spdm_plan* p, const float* x, const int64_t* t, int32_t t_count, const float* y,
+                                 int32_t use_cached_cond, float* out, int32_t B, void* stream) {
+  API_BEGIN
+  return unet_forward_impl(p, x, t, t_count, y, use_cached_cond, out, B, stream);
+  API_END
+}
+
+extern "C" int64_t spdm_debug_forward(spdm_plan* p, const float* x, const int64_t* t, int32_t t_count, const float* y,
+                                      int32_t use_cached_cond, float* out, int32_t B, const char* tap_name, float* tap_out, void* stream) {
+  API_BEGIN
+  REQUIRE(p && tap_name && tap_out, "null argument");
+  p->tap_name = tap_name; p->tap_out = tap_out; p->tap_count = -1;
+  int rc = unet_forward_impl(p, x, t, t_count, y, use_cached_cond, out, B, stream);
+  p->tap_out = nullptr;
+  if (rc) return rc;
+  REQUIRE(p->tap_count >= 0, "unknown tap '%s'", tap_name);
+  return p->tap_count;
+  API_END
+}
+
+extern "C" int spdm_step(spdm_plan* p, const float* x, const float* eps, const float* noise, const float* inpaint, float* x_out,
+                         int32_t step, int32_t B, void* stream) {
+  API_BEGIN
+  REQUIRE(p && x && eps && x_out, "null argument");
+  REQUIRE(p->K > 0 && step >= 0 && step < p->K, "step %d outside schedule of %d steps", step, p->K);
+  REQUIRE(B > 0, "bad B");
+  StepArgs a{};
+  a.x = x; a.eps = eps; a.x_out = x_out; a.coef = p->coef; a.dyn = nullptr; a.noise = noise;
+  a.inpaint = p->cfg.inpaint_rows > 0 ? inpaint : nullptr; a.step_host = step;
+  a.n = p->n_elems(); a.inpaint_elems = p->cfg.inpaint_rows * p->cfg.dim; a.B = B;
+  launch_step(a, (cudaStream_t)stream);
+  check_async("step");
+  return 0;
+  API_END
+}
+
+extern "C" int spdm_sample(spdm_plan* p, const float* x_T, const float* noise, const float* inpaint, float* out, float* history,
+                           uint64_t seed, int32_t B, void* stream) {
+  API_BEGIN
+  REQUIRE(p && x_T && out, "null argument");
+  REQUIRE(B > 0 && B <= p->cfg.batch_max, "B=%d outside 1..batch_max=%d", B, p->cfg.batch_max);
+  check_ready(p);
+  const bool use_film = p->G > 0;
+  if (use_film) REQUIRE(p->have_cond, "no cached conditioning (call spdm_set_cond / spdm_encode_cond)");
+  cudaStream_t s = (cudaStream_t)stream;
+  ensure_temb_table(p, s);
+  const size_t nb = (size_t)B * p->n_elems() * sizeof(float);
+  // per-call dynamic parameters live in device memory so that the captured graphs are call-independent
+  CUDA_OK(cudaStreamSynchronize(s));  // dyn_host is reused across calls
+  StepDyn d{};
+  d.step = 0; d.seed = seed; d.noise = noise; d.inpaint = p->cfg.inpaint_rows > 0 ? inpaint : nullptr; d.history = history;
+  d.use_philox = noise ? 0 : 1;
+  *p->dyn_host = d;
+  CUDA_OK(cudaMemcpyAsync(p->dyn, p->dyn_host, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
+
+  const int gs = p->cfg.graph_steps;
+  const long long key = ((long long)B << 1) | (use_film ? 1 : 0);
+  const int n_multi = gs > 0 ? p->K / gs : 0, n_single = gs > 0 ? p->K % gs : 0;
+  if (gs > 0) {
+    spdm_plan::GraphSet& g = p->graphs[key];
+    if ((n_multi > 0 && !g.multi) || (n_single > 0 && !g.single)) {
+      // One eager step first: builds the tensor maps and sets the kernel attributes outside of stream capture.
+      const long long before = total_launches();
+      one_step(p, B, use_film, s);
+      p->launches += total_launches() - before;
+      CUDA_OK(cudaMemcpyAsync(p->dyn, p->dyn_host, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
+      auto capture = [&](int steps, cudaGraphExec_t* exec, long long* count) {
+        cudaGraph_t graph;
+        const long long c0 = total_launches();
+        CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        try {
+          for (int k = 0; k < steps; ++k) one_step(p, B, use_film, s);
+        } catch (...) {
+          cudaStreamEndCapture(s, &graph);
+          throw;
+        }
+        CUDA_OK(cudaStreamEndCapture(s, &graph));
+        *count = total_launches() - c0;
+        CUDA_OK(cudaGraphInstantiate(exec, graph, 0));
+        CUDA_OK(cudaGraphDestroy(graph));
+      };
+      if (n_multi > 0 && !g.multi) capture(gs, &g.multi, &g.n_multi);
+      if (n_single > 0 && !g.single) capture(1, &g.single, &g.n_single);
+    }
+  }
+  CUDA_OK(cudaMemcpyAsync(p->xt, x_T, nb, cudaMemcpyDeviceToDevice, s));
+  if (history) CUDA_OK(cudaMemcpyAsync(history, x_T, nb, cudaMemcpyDeviceToDevice, s));
+  if (gs <= 0) {
+    const long long before = total_launches();
+    for (int k = 0; k < p->K; ++k) one_step(p, B, use_film, s);
+    p->launches += total_launches() - before;
+  } else {
+    spdm_plan::GraphSet& g = p->graphs[key];
+    for (int i = 0; i < n_multi; ++i) CUDA_OK(cudaGraphLaunch(g.multi, s));
+    for (int i = 0; i < n_single; ++i) CUDA_OK(cudaGraphLaunch(g.single, s));
+    p->launches += n_multi * g.n_multi + n_single * g.n_single;
+  }
+  CUDA_OK(cudaMemcpyAsync(out, p->xt, nb, cudaMemcpyDeviceToDevice, s));
+  check_async("sample");
+  return 0;
+  API_END
+}
+
+extern "C" int spdm_add_noise(spdm_plan* p, const float* x0, const float* noise, const int64_t* t, const float* sqrt_ab,
+                              const float* sqrt_1mab, const float* inpaint, float* out, int32_t B, void* stream) {
+  API_BEGIN
+  REQUIRE(p && x0 && noise && t && sqrt_ab && sqrt_1mab && out && B > 0, "bad argument");
+  launch_add_noise(x0, noise, reinterpret_cast<const long long*>(t), sqrt_ab, sqrt_1mab, p->cfg.inpaint_rows > 0 ? inpaint : nullptr, out,
+                   p->n_elems(), p->cfg.inpaint_rows * p->cfg.dim, B, (cudaStream_t)stream);
+  check_async("add_noise");
+  return 0;
+  API_END
+}
+
+extern "C" int64_t spdm_plan_launch_count(spdm_plan* p) { return p ? p->launches : 0; }
+extern "C" int64_t spdm_plan_workspace_bytes(spdm_plan* p) { return p ? (int64_t)p->bytes : 0; }

@@ -1,0 +1,291 @@
+"""`Diffusion_DDPM` / `Diffusion_DDIM` with the reference's constructor, attributes and method surface
+(models/diffusion_ddpm.py:22-348, models/diffusion_ddim.py:19-74), running on libspdm.
+
+What stays exactly as in the reference (default behaviour of `sample(batch, option=None)`):
+  * `sample`/`validate` use batch element 0 only and return (1,1,pred_h+ih,pred_dim)      (ddpm:196,246)
+  * x_T ~ U[0,1) from `torch.rand` on the model device                                     (ddpm:205,252)
+  * K = `self.noise_steps` steps of `self.noise_scheduler`, inpainting after every step    (ddpm:268-276)
+  * `option='sample_history'` returns a Python list of K+1 tensors                         (ddpm:254-265)
+What is added behind the same method (keyword-only, default off):
+  * `batched=True` samples every row of the batch; `x_T=` / `noise=` inject the random draws;
+    `mode='validation'` returns `validate(batch)`'s 3-tuple (the call shape the reference's
+    evaluation/*.py scripts use).
+The K-step loop is one C-ABI call (`spdm_sample`): conditioning encoder + FiLM GEMM once, then a
+CUDA-graphed U-Net + posterior update + inpaint per step; no per-step host work.
+"""
+from datetime import datetime
+
+import torch
+import torch.nn as nn
+
+from .schedulers import DDIMScheduler, DDPMScheduler
+from .unet import UNet_Film, UNet_Film_noAttention
+
+try:  # Lightning is optional: the reference subclasses pl.LightningModule, which is absent on the B200 image
+    import pytorch_lightning as pl
+    _Base = pl.LightningModule
+except Exception:  # pragma: no cover - depends on the environment
+    pl = None
+
+    class _Hparams(dict):
+        __getattr__ = dict.get
+
+    class _Base(nn.Module):
+        """Minimal stand-in for pl.LightningModule: hparams, .device, .log, load_from_checkpoint."""
+
+        def __init__(self):
+            super().__init__()
+            self.hparams = _Hparams()
+
+        def save_hyperparameters(self, **kw):
+            self.hparams.update(kw)
+
+        @property
+        def device(self):
+            try:
+                return next(self.parameters()).device
+            except StopIteration:
+                return torch.device("cpu")
+
+        def log(self, *a, **k):
+            pass
+
+        @classmethod
+        def load_from_checkpoint(cls, checkpoint_path, hparams_file=None, map_location=None, **kwargs):
+            ckpt = torch.load(checkpoint_path, map_location=map_location or "cpu", weights_only=False)
+            hp = dict(ckpt.get("hyper_parameters", {}))
+            if hparams_file is not None:
+                import yaml
+                with open(hparams_file) as f:
+                    hp.update(yaml.safe_load(f) or {})
+            hp.update(kwargs)
+            model = cls(**hp)
+            model.load_state_dict(ckpt["state_dict"], strict=True)
+            return model
+
+
+class VisionEncoder(nn.Sequential):
+    """Parameters of Autoencoder.encoder (models/encoder/autoencoder.py:11-20); state_dict keys 0,2,4,7."""
+
+    def __init__(self, channels=3, latent_dim=128):
+        super().__init__(nn.Conv2d(channels, 16, 2, stride=2, padding=1), nn.ReLU(), nn.Conv2d(16, 32, 2, stride=2, padding=0),
+                         nn.ReLU(), nn.Conv2d(32, 64, 2, stride=2, padding=0), nn.ReLU(), nn.Flatten(),
+                         nn.Linear(64 * 12 * 12, latent_dim))
+        self._owner = None
+
+    def forward(self, img):
+        """(N,3,96,96) -> (N,128) on the fused encoder kernels."""
+        if self._owner is None:
+            raise RuntimeError("VisionEncoder is driven through its Diffusion_DDPM owner")
+        return self._owner()._plan().encode_images(img)
+
+
+class Diffusion_DDPM(_Base):
+    def __init__(self, noise_steps=1000, obs_horizon=10, pred_horizon=10, observation_dim=2, prediction_dim=2,
+                 learning_rate=1e-4, model='UNet', vision_encoder=None, noise_scheduler_type='linear', inpaint_horizon=10,
+                 step_size=1, noise_scheduler=None, autoencoder_checkpoint="./tb_logs_autoencoder/version_23/checkpoints/epoch=25.ckpt"):
+        super().__init__()
+        if noise_scheduler is not None:  # train.py:88 passes `noise_scheduler=` (a TypeError in the reference)
+            noise_scheduler_type = noise_scheduler
+        self.save_hyperparameters(noise_steps=noise_steps, obs_horizon=obs_horizon, pred_horizon=pred_horizon,
+                                  observation_dim=observation_dim, prediction_dim=prediction_dim, learning_rate=learning_rate,
+                                  model=model, vision_encoder=vision_encoder, noise_scheduler_type=noise_scheduler_type,
+                                  inpaint_horizon=inpaint_horizon, step_size=step_size)
+        self.date = datetime.today().strftime('%Y_%m_%d_%H-%M-%S')
+        self.noise_steps = noise_steps
+        self.NoiseScheduler = None
+        self.obs_horizon = obs_horizon
+        self.pred_horizon = pred_horizon
+        self.observation_dim = observation_dim
+        self.prediction_dim = prediction_dim
+        self.inpaint_horizon = inpaint_horizon
+        if model == 'UNet_Film':
+            self.model = UNet_Film
+        elif model == 'UNet_FilmnoAttention':
+            self.model = UNet_Film_noAttention
+        else:
+            raise NotImplementedError("model=%r: the legacy simple U-Net (models/simple_Unet.py) is outside the B200 hot path; "
+                                      "use 'UNet_Film' or 'UNet_FilmnoAttention'" % (model,))
+        self.noise_scheduler = DDPMScheduler(num_train_timesteps=self.noise_steps, beta_schedule='linear', clip_sample=False,
+                                             prediction_type='epsilon')
+        self.lr = learning_rate
+        self.loss = nn.MSELoss()
+        self.noise_estimator = self.model(in_channels=1, out_channels=1, noise_steps=noise_steps,
+                                          global_cond_dim=observation_dim * obs_horizon, time_dim=256)
+        self.vision_encoder = VisionEncoder()
+        import os
+        import weakref
+        self.vision_encoder._owner = weakref.ref(self)
+        if autoencoder_checkpoint and os.path.exists(autoencoder_checkpoint):  # ddpm:84-88
+            sd = torch.load(autoencoder_checkpoint, map_location="cpu", weights_only=False)["state_dict"]
+            enc = {k.split("encoder.", 1)[1]: v for k, v in sd.items() if "encoder." in k and "decoder" not in k}
+            self.vision_encoder.load_state_dict(enc, strict=True)
+        self.vision_encoder.eval()
+        # B200 execution options
+        self.precision = "bf16"
+        self.graph_steps = 1
+        self.batch_max = 0
+        self._enc_tag = None
+
+    # ------------------------------------------------------------------------------------------
+    # engine plumbing
+    # ------------------------------------------------------------------------------------------
+    def configure(self, precision=None, graph_steps=None, batch_max=None):
+        if precision is not None:
+            self.precision = precision
+        if graph_steps is not None:
+            self.graph_steps = int(graph_steps)
+        if batch_max is not None:
+            self.batch_max = int(batch_max)
+        return self
+
+    def _plan(self, B=1):
+        ne = self.noise_estimator
+        ne.precision = self.precision
+        ne.batch_max = max(ne.batch_max, self.batch_max)
+        cond_dim = self.observation_dim
+        plan = ne.plan_for(B, self.pred_horizon + self.inpaint_horizon, self.prediction_dim, self.obs_horizon, cond_dim,
+                           inpaint_rows=self.inpaint_horizon, graph_steps=self.graph_steps)
+        tag = (id(plan),) + tuple((p.data_ptr(), p._version) for p in self.vision_encoder.parameters())
+        if self._enc_tag != tag:
+            plan.load_encoder_state_dict(self.vision_encoder.state_dict())
+            self._enc_tag = tag
+        return plan
+
+    def _bind_schedule(self, plan):
+        sch = self.noise_scheduler
+        sch.set_timesteps(self.noise_steps)
+        if not hasattr(sch, "coef_table"):
+            raise TypeError("noise_scheduler must be a state_policy_diffusionmodel_b200.schedulers scheduler "
+                            "(DDPMScheduler / DDIMScheduler)")
+        plan.set_schedule(sch.kind, sch.coef_table(), sch.timesteps)
+
+    # ------------------------------------------------------------------------------------------
+    # training / validation hooks (ddpm:92-125)
+    # ------------------------------------------------------------------------------------------
+    def training_step(self, batch, batch_idx):
+        loss = self.process_single_batch(batch)
+        self.log("train_loss", loss)
+        return loss
+
+    def validation_step(self, batch, batch_idx):
+        loss = self.process_single_batch(batch)
+        self.log("val_loss", loss, sync_dist=True)
+        return loss
+
+    def configure_optimizers(self):
+        optimizer = torch.optim.Adam(self.parameters(), lr=self.lr)
+        scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, 'min', patience=5)
+        return {"optimizer": optimizer, "lr_scheduler": {"scheduler": scheduler, "monitor": "val_loss", "frequency": 1}}
+
+    def process_single_batch(self, batch, t=None, noise=None):
+        """ddpm:128-173 — q-sample + inpaint + U-Net + MSE.  Forward only in this round (loss value, no autograd graph);
+        `t` / `noise` may be injected for parity runs."""
+        observation_batch = self.prepare_observation_batch(batch)
+        prediction_batch = self.prepare_prediction_batch(batch)
+        B = observation_batch['position'].shape[0]
+        plan = self._plan(B)
+        plan.encode_cond(observation_batch['image'], observation_batch['position'], observation_batch['action'],
+                         observation_batch['velocity'])
+        x_0 = self.prepare_prediction_vectors(prediction_batch).unsqueeze(1)
+        x_0_inpaint = self.prepare_inpaint_vectors(observation_batch).unsqueeze(1)
+        if t is None:
+            t = torch.randint(0, self.noise_steps, (B,), device=self.device).long()
+        prediction_vector = torch.cat([x_0_inpaint, x_0], dim=2)
+        if noise is None:
+            noise = torch.randn_like(prediction_vector)
+        ac = self.noise_scheduler.alphas_cumprod
+        x_noisy = plan.add_noise(prediction_vector, noise, t, ac ** 0.5, (1 - ac) ** 0.5,
+                                 inpaint=x_0_inpaint.reshape(B, -1) if self.inpaint_horizon > 0 else None)
+        with torch.no_grad():
+            noise_estimated = plan.unet_forward(x_noisy, t, None, use_cached_cond=True)
+        self._last = (x_noisy, noise_estimated)
+        return self.loss(noise.to(noise_estimated.device), noise_estimated)
+
+    # ------------------------------------------------------------------------------------------
+    # sampling
+    # ------------------------------------------------------------------------------------------
+    def add_constraints(self, x_t, x_inpaint):
+        """ddpm:216-219 (in place)."""
+        x_t[:, :, :self.inpaint_horizon, :] = x_inpaint
+        return x_t
+
+    def _run_loop(self, observation_batch, first_only, history, x_T=None, noise=None, seed=None):
+        if first_only:
+            observation_batch = {k: v[:1] for k, v in observation_batch.items()}
+        B = observation_batch['position'].shape[0]
+        plan = self._plan(B)
+        self._bind_schedule(plan)
+        plan.encode_cond(observation_batch['image'], observation_batch['position'], observation_batch['action'],
+                         observation_batch['velocity'])
+        inpaint = self.prepare_inpaint_vectors(observation_batch).unsqueeze(1)
+        rows = self.pred_horizon + self.inpaint_horizon
+        if x_T is None:
+            x_T = torch.rand(B, 1, rows, self.prediction_dim, device=self.device)
+        if seed is None:
+            seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+        res = plan.sample(x_T, noise=noise, inpaint=inpaint if self.inpaint_horizon > 0 else None, history=history, seed=seed)
+        return res, inpaint
+
+    def validate(self, batch):
+        """ddpm:176-214 — full-window batch -> (x_0, observation_batch, inpaint_vector), batch element 0 only."""
+        observation_batch = self.prepare_observation_batch(batch)
+        x_0, inpaint = self._run_loop(observation_batch, True, False)
+        return x_0, observation_batch, inpaint
+
+    def sample(self, batch, option=None, *, mode=None, batched=False, x_T=None, noise=None, seed=None):
+        """ddpm:223-277 / ddim:23-74."""
+        if mode == 'validation':  # call shape of the reference's evaluation/*.py scripts
+            return self.validate(batch)
+        for key, tensor in batch.items():
+            if torch.is_tensor(tensor):
+                batch[key] = tensor.to(self.device)
+        observation_batch = {k: batch[k].float() for k in ('image', 'position', 'action', 'velocity')}
+        res, _ = self._run_loop(observation_batch, not batched, option == 'sample_history', x_T=x_T, noise=noise, seed=seed)
+        if option == 'sample_history':
+            _, hist = res
+            return [hist[i] for i in range(hist.shape[0])]
+        return res
+
+    # ------------------------------------------------------------------------------------------
+    # batch-prep helpers (ddpm:283-348)
+    # ------------------------------------------------------------------------------------------
+    def _slice(self, batch, sl):
+        return {k: batch[k][:, sl].to(self.device).float() for k in ('image', 'position', 'action', 'velocity')}
+
+    def prepare_observation_batch(self, batch):
+        return self._slice(batch, slice(None, self.obs_horizon))
+
+    def prepare_prediction_batch(self, batch):
+        return self._slice(batch, slice(self.obs_horizon, None))
+
+    def prepare_obs_cond_vectors(self, observation_batch):
+        """encoder + cat[pos, act, vel, img_feat] -> (B, T_obs, 135), computed by the fused conditioning kernels."""
+        B, T = observation_batch['position'].shape[:2]
+        plan = self._plan(B)
+        cond = plan.encode_cond(observation_batch['image'], observation_batch['position'], observation_batch['action'],
+                                observation_batch['velocity'])
+        return cond.reshape(B, T, -1)
+
+    def prepare_prediction_vectors(self, prediction_batch):
+        return torch.cat([prediction_batch['position'], prediction_batch['action']], dim=-1)
+
+    def prepare_inpaint_vectors(self, observation_batch):
+        """ddpm:340-348; for position-only prediction (prediction_dim == 2) the position rows alone
+        (the variant the reference keeps commented out at diffusion_ddim.py:75-86)."""
+        pos = observation_batch['position'][:, -self.inpaint_horizon:, :]
+        if self.prediction_dim == pos.shape[-1]:
+            return pos
+        act = observation_batch['action'][:, -self.inpaint_horizon:, :]
+        return torch.cat([pos, act], dim=-1)
+
+
+class Diffusion_DDIM(Diffusion_DDPM):
+    """models/diffusion_ddim.py:19 — same loop; generate.py:28-35 swaps in a DDIMScheduler and re-purposes
+    `noise_steps` as the number of DDIM steps.  `use_ddim(K)` does exactly that."""
+
+    def use_ddim(self, num_steps):
+        self.noise_scheduler = DDIMScheduler(num_train_timesteps=num_steps, beta_schedule='linear', clip_sample=False,
+                                             prediction_type='epsilon')
+        self.noise_steps = num_steps
+        return self

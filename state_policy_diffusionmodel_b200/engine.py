@@ -1,0 +1,212 @@
+"""Python handle on a libspdm plan (include/spdm.h) — device memory, streams and weights come from torch,
+every computation is a C-ABI call into the hand-written CUDA kernels.
+
+A `DenoisePlan` stands in for the compute of
+  * `UNet_Film.forward` / `UNet_Film_noAttention.forward`   (reference models/Unet_FiLmLayer.py:277-312)
+  * `Autoencoder.encoder` + `prepare_obs_cond_vectors`       (models/encoder/autoencoder.py:11-20,
+                                                              models/diffusion_ddpm.py:317-330)
+  * the K-step loop of `Diffusion_DDPM.sample` / `Diffusion_DDIM.sample`
+                                                             (models/diffusion_ddpm.py:268-276, diffusion_ddim.py:67-73)
+for one (variant, precision, rows x dim, batch_max) configuration on one GPU.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _f32c(t, device):
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+class DenoisePlan:
+    def __init__(self, attention=True, precision="bf16", batch_max=1, rows=31, dim=5, obs_horizon=10, cond_dim=135,
+                 inpaint_rows=1, time_dim=256, device=None, graph_steps=1, scheduler_only=False):
+        if not torch.cuda.is_available():
+            raise RuntimeError("spdm: no CUDA device — the B200 denoising path has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        if precision not in ("fp32", "bf16"):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        cfg = _lib.SpdmConfig(
+            variant=_lib.VARIANT_ATTENTION if attention else _lib.VARIANT_NO_ATTENTION,
+            precision=_lib.PRECISION_BF16 if precision == "bf16" else _lib.PRECISION_FP32,
+            batch_max=int(batch_max), rows=int(rows), dim=int(dim), obs_horizon=int(obs_horizon),
+            cond_dim=int(cond_dim or 0), inpaint_rows=int(inpaint_rows), time_dim=int(time_dim),
+            device=self.device.index or 0, graph_steps=int(graph_steps),
+            flags=_lib.FLAG_SCHEDULER_ONLY if scheduler_only else 0)
+        self.cfg = cfg
+        self.attention, self.precision = attention, precision
+        self.batch_max, self.rows, self.dim = int(batch_max), int(rows), int(dim)
+        self.obs_horizon, self.cond_dim, self.inpaint_rows = int(obs_horizon), int(cond_dim or 0), int(inpaint_rows)
+        self.K = 0
+        handle = ctypes.c_void_p()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_plan_create(ctypes.byref(handle), ctypes.byref(cfg)))
+        self._h = handle
+        self._keep = []  # tensors that must outlive an enqueued call
+
+    # ------------------------------------------------------------------ lifetime
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.spdm_plan_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ------------------------------------------------------------------ weights
+    def load_weight(self, name, tensor):
+        t = _f32c(tensor, self.device)
+        shape = (ctypes.c_int64 * max(t.dim(), 1))(*(t.shape if t.dim() else (1,)))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_plan_load_weight(self._h, name.encode(), _ptr(t), shape, max(t.dim(), 1), _stream()))
+            torch.cuda.current_stream().synchronize()  # `t` may be a temporary
+
+    def load_unet_state_dict(self, sd, prefix=""):
+        """nn.Module.load_state_dict for the noise estimator (SURVEY A.2 key names)."""
+        for k, v in sd.items():
+            if prefix and not k.startswith(prefix):
+                continue
+            self.load_weight(k[len(prefix):], v)
+        # exact torch value of the sinusoidal frequencies (models/Unet_FiLmLayer.py:267-270)
+        td = self.cfg.time_dim
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, td, 2) / td))
+        self.load_weight("pos_encoding.inv_freq", inv_freq)
+
+    def load_encoder_state_dict(self, esd, prefix=""):
+        """Autoencoder.encoder weights: keys `{prefix}{0,2,4,7}.{weight,bias}`."""
+        for k in ("0.weight", "0.bias", "2.weight", "2.bias", "4.weight", "4.bias", "7.weight", "7.bias"):
+            self.load_weight("vision_encoder." + k, esd[prefix + k])
+
+    def missing_weights(self):
+        n = self.lib.spdm_plan_missing_weights(self._h)
+        names = self.lib.spdm_last_error().decode().split()
+        return names if n else []
+
+    # ------------------------------------------------------------------ schedule
+    def set_schedule(self, kind, coef, timesteps):
+        """coef: (K, 8) fp32 host rows {c0, c1, k_x0, k_x, k_eps, k_noise, 0, 0}; timesteps: (K,) int64."""
+        coef = coef.detach().to("cpu", torch.float32).contiguous()
+        ts = timesteps.detach().to("cpu", torch.int64).contiguous()
+        assert coef.shape == (ts.numel(), 8)
+        k = _lib.SCHED_DDPM if kind == "ddpm" else _lib.SCHED_DDIM
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_plan_set_schedule(self._h, k, ts.numel(), _ptr(coef), _ptr(ts), _stream()))
+        self.K = ts.numel()
+
+    # ------------------------------------------------------------------ conditioning
+    def encode_images(self, images):
+        img = _f32c(images, self.device).reshape(-1, 3, 96, 96)
+        out = torch.empty((img.shape[0], 128), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_encode_images(self._h, _ptr(img), _ptr(out), img.shape[0], _stream()))
+        return out
+
+    def encode_cond(self, image, position, action, velocity):
+        B = image.shape[0]
+        img, pos, act, vel = (_f32c(t, self.device) for t in (image, position, action, velocity))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_encode_cond(self._h, _ptr(img), _ptr(pos), _ptr(act), _ptr(vel), B, _stream()))
+        self._keep = [img, pos, act, vel]
+        return self.get_cond(B)
+
+    def set_cond(self, obs_cond):
+        c = _f32c(obs_cond, self.device).reshape(obs_cond.shape[0], -1)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_set_cond(self._h, _ptr(c), c.shape[0], _stream()))
+        self._keep = [c]
+
+    def get_cond(self, B):
+        out = torch.empty((B, self.obs_horizon * self.cond_dim), device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_get_cond(self._h, _ptr(out), B, _stream()))
+        return out
+
+    # ------------------------------------------------------------------ U-Net forward
+    def _prep_fwd(self, x, t, y):
+        x = _f32c(x, self.device)
+        B = x.shape[0]
+        t = t.detach().to(self.device, torch.int64).reshape(-1).contiguous()
+        yy = None if y is None else _f32c(y, self.device).reshape(B, -1)
+        out = torch.empty((B, 1, self.rows, self.dim), device=self.device, dtype=torch.float32)
+        return x, t, yy, out, B
+
+    def unet_forward(self, x, t, y=None, use_cached_cond=False):
+        x, t, yy, out, B = self._prep_fwd(x, t, y)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_unet_forward(self._h, _ptr(x), _ptr(t), t.numel(), _ptr(yy), int(use_cached_cond),
+                                                  _ptr(out), B, _stream()))
+        self._keep = [x, t, yy]
+        return out
+
+    def debug_forward(self, x, t, y, tap, tap_shape):
+        """Runs the forward and returns (out, activation `tap` as (B, C, H, W) fp32)."""
+        x, t, yy, out, B = self._prep_fwd(x, t, y)
+        tap_out = torch.zeros(tap_shape, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            n = self.lib.spdm_debug_forward(self._h, _ptr(x), _ptr(t), t.numel(), _ptr(yy), 0, _ptr(out), B, tap.encode(),
+                                            _ptr(tap_out), _stream())
+            _lib.check(n)
+            torch.cuda.synchronize()
+        assert n == tap_out.numel(), (n, tap_out.shape)
+        return out, tap_out
+
+    # ------------------------------------------------------------------ scheduler step / sampling
+    def step(self, x, eps, step_index, noise=None, inpaint=None):
+        x, eps = _f32c(x, self.device), _f32c(eps, self.device)
+        nz = None if noise is None else _f32c(noise, self.device)
+        ip = None if inpaint is None else _f32c(inpaint, self.device)
+        out = torch.empty_like(x)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_step(self._h, _ptr(x), _ptr(eps), _ptr(nz), _ptr(ip), _ptr(out), int(step_index), x.shape[0],
+                                          _stream()))
+        self._keep = [x, eps, nz, ip]
+        return out
+
+    def sample(self, x_T, noise=None, inpaint=None, history=False, seed=0):
+        """Runs all K schedule steps on the cached conditioning.  Returns x_0 (B,1,rows,dim) [, history (K+1,B,1,rows,dim)]."""
+        x_T = _f32c(x_T, self.device)
+        B = x_T.shape[0]
+        nz = None if noise is None else _f32c(noise, self.device)
+        ip = None if inpaint is None else _f32c(inpaint, self.device).reshape(B, -1)
+        out = torch.empty_like(x_T)
+        hist = torch.empty((self.K + 1,) + tuple(x_T.shape), device=self.device, dtype=torch.float32) if history else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_sample(self._h, _ptr(x_T), _ptr(nz), _ptr(ip), _ptr(out), _ptr(hist), int(seed) & (2**64 - 1),
+                                            B, _stream()))
+        self._keep = [x_T, nz, ip, hist]
+        return (out, hist) if history else out
+
+    def add_noise(self, x0, noise, t, sqrt_ab, sqrt_1mab, inpaint=None):
+        x0, noise = _f32c(x0, self.device), _f32c(noise, self.device)
+        t = t.detach().to(self.device, torch.int64).contiguous()
+        sa, sb = _f32c(sqrt_ab, self.device), _f32c(sqrt_1mab, self.device)
+        ip = None if inpaint is None else _f32c(inpaint, self.device)
+        out = torch.empty_like(x0)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_add_noise(self._h, _ptr(x0), _ptr(noise), _ptr(t), _ptr(sa), _ptr(sb), _ptr(ip), _ptr(out),
+                                               x0.shape[0], _stream()))
+        self._keep = [x0, noise, t, sa, sb, ip]
+        return out
+
+    # ------------------------------------------------------------------ introspection
+    @property
+    def launch_count(self):
+        return int(self.lib.spdm_plan_launch_count(self._h))
+
+    @property
+    def workspace_bytes(self):
+        return int(self.lib.spdm_plan_workspace_bytes(self._h))

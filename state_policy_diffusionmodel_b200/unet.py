@@ -1,0 +1,186 @@
+"""`UNet_Film` / `UNet_Film_noAttention` with the reference's constructor, forward signature and state_dict.
+
+Mirrors models/Unet_FiLmLayer.py:240-312 and models/Unet_FiLmLayer_noAttention.py:240-301 of the
+reference: same sub-module names, same parameter shapes, same construction order (so a given
+`torch.manual_seed` yields the same initial weights and reference checkpoints load with strict=True).
+The sub-modules are parameter containers only — `forward` hands the whole network to libspdm
+(hand-written sm_100a kernels) through `DenoisePlan`; nothing is computed by torch operators.
+"""
+import torch
+import torch.nn as nn
+
+from .engine import DenoisePlan
+
+
+class DoubleConvolution(nn.Module):
+    """Parameters of models/Unet_FiLmLayer.py:85-115 (two bias-free 3x3 convs sharing one GroupNorm(1, C))."""
+
+    def __init__(self, in_channels, out_channels):
+        super().__init__()
+        self.first = nn.Conv2d(in_channels, out_channels, kernel_size=3, padding=1, bias=False)
+        self.second = nn.Conv2d(out_channels, out_channels, kernel_size=3, padding=1, bias=False)
+        self.act = nn.GELU()
+        self.norm = nn.GroupNorm(1, out_channels)
+
+
+class _Stage(nn.Module):
+    """Parameters of DownSample / UpSample (models/Unet_FiLmLayer.py:118-156, 183-214)."""
+
+    def __init__(self, in_channels, out_channels, embeddedTime_dim=256, cond_dim=None):
+        super().__init__()
+        self.doubleConv1 = DoubleConvolution(in_channels, in_channels)
+        self.doubleConv2 = DoubleConvolution(in_channels, out_channels)
+        self.emb_layer = nn.Sequential(nn.SiLU(), nn.Linear(embeddedTime_dim, out_channels))
+        if cond_dim is not None:
+            self.out_channels = out_channels
+            self.cond_encoder = nn.Sequential(nn.Mish(), nn.Flatten(1, -1), nn.Linear(cond_dim, out_channels * 2),
+                                              nn.Unflatten(-1, (-1, 1)))
+
+
+class DownSample(_Stage):
+    pass
+
+
+class UpSample(_Stage):
+    pass
+
+
+class SelfAttention(nn.Module):
+    """Parameters of models/Unet_FiLmLayer.py:44-69 (4-head MHA + LN + 2-layer feed-forward)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.channels = channels
+        self.attention = nn.MultiheadAttention(channels, 4, batch_first=True)
+        self.ln = nn.LayerNorm([channels])
+        self.ff_self = nn.Sequential(nn.LayerNorm([channels]), nn.Linear(channels, channels), nn.GELU(),
+                                     nn.Linear(channels, channels))
+
+
+class _UNetBase(nn.Module):
+    _attention = True
+
+    def __init__(self, in_channels, out_channels, noise_steps, time_dim=256, global_cond_dim=None):
+        super().__init__()
+        if in_channels != 1 or out_channels != 1:
+            raise NotImplementedError("the B200 path implements the reference's wiring in_channels = out_channels = 1 "
+                                      "(models/diffusion_ddpm.py:76-82)")
+        self.time_dim = time_dim
+        self.noise_steps = noise_steps
+        self.global_cond_dim = global_cond_dim
+        sa = self._attention
+        # construction order == reference, so that seeded default init matches
+        self.inc = DoubleConvolution(in_channels, 64)
+        self.down1 = DownSample(64, 128, cond_dim=global_cond_dim)
+        if sa:
+            self.sa1 = SelfAttention(128)
+        self.down2 = DownSample(128, 256, cond_dim=global_cond_dim)
+        if sa:
+            self.sa2 = SelfAttention(256)
+        self.down3 = DownSample(256, 256, cond_dim=global_cond_dim)
+        if sa:
+            self.sa3 = SelfAttention(256)
+        self.bot1 = DoubleConvolution(256, 512)
+        self.bot2 = DoubleConvolution(512, 512)
+        self.bot3 = DoubleConvolution(512, 256)
+        self.up1 = UpSample(512, 128, cond_dim=global_cond_dim)
+        if sa:
+            self.sa4 = SelfAttention(128)
+        self.up2 = UpSample(256, 64, cond_dim=global_cond_dim)
+        if sa:
+            self.sa5 = SelfAttention(64)
+        self.up3 = UpSample(128, 64, cond_dim=global_cond_dim)
+        if sa:
+            self.sa6 = SelfAttention(64)
+        self.outc = nn.Conv2d(64, out_channels, kernel_size=1)
+        # B200 execution options (not part of the state_dict)
+        self.precision = "bf16"   # "bf16": tcgen05 implicit-GEMM path; "fp32": CUDA-core parity path
+        self.batch_max = 0        # 0 = grow on demand
+        self._plan = None
+        self._plan_key = None
+        self._weights_tag = None
+
+    # ----------------------------------------------------------------------------------------
+    def configure(self, precision=None, batch_max=None):
+        if precision is not None:
+            self.precision = precision
+        if batch_max is not None:
+            self.batch_max = int(batch_max)
+        return self
+
+    def pos_encoding(self, t, channels):
+        """models/Unet_FiLmLayer.py:266-274 (kept for API parity; the kernels compute it on the device)."""
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, channels, 2, device=t.device) / channels))
+        a = torch.sin(t.repeat(1, channels // 2) * inv_freq)
+        b = torch.cos(t.repeat(1, channels // 2) * inv_freq)
+        return torch.cat([a, b], dim=-1)
+
+    def _tag(self):
+        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+
+    def plan_for(self, B, rows, dim, obs_horizon=None, cond_dim=None, inpaint_rows=None, graph_steps=None):
+        """Returns a DenoisePlan able to run B samples of rows x dim, (re)building it and (re)loading weights when
+        needed.  `inpaint_rows` / `graph_steps` = None means "whatever the current plan has"."""
+        dev = self.outc.weight.device
+        if dev.type != "cuda":
+            raise RuntimeError("spdm U-Net: parameters are on %s — move the module to a CUDA device (no CPU fallback)" % dev)
+        G = self.global_cond_dim
+        if G is None:
+            T, cd = 1, 0
+        elif obs_horizon is not None and cond_dim is not None and obs_horizon * cond_dim == G:
+            T, cd = int(obs_horizon), int(cond_dim)
+        else:
+            T, cd = 1, int(G)
+        old = self._plan
+        if old is not None:
+            if inpaint_rows is None:
+                inpaint_rows = old.inpaint_rows
+            if graph_steps is None:
+                graph_steps = old.cfg.graph_steps
+            if obs_horizon is None and old.obs_horizon * old.cond_dim == T * cd:
+                T, cd = old.obs_horizon, old.cond_dim
+        inpaint_rows = 0 if inpaint_rows is None else int(inpaint_rows)
+        graph_steps = 1 if graph_steps is None else int(graph_steps)
+        key = (self.precision, rows, dim, T, cd, inpaint_rows, graph_steps, str(dev))
+        if old is None or self._plan_key != key or old.batch_max < B:
+            cap = max(int(B), self.batch_max)
+            if old is not None:
+                if self._plan_key == key:
+                    cap = max(cap, old.batch_max)
+                old.close()
+            self._plan = DenoisePlan(attention=self._attention, precision=self.precision, batch_max=cap, rows=rows, dim=dim,
+                                     obs_horizon=T, cond_dim=cd, inpaint_rows=inpaint_rows, time_dim=self.time_dim, device=dev,
+                                     graph_steps=graph_steps)
+            self._plan_key = key
+            self._weights_tag = None
+        tag = self._tag()
+        if self._weights_tag != tag:
+            self._plan.load_unet_state_dict(self.state_dict())
+            self._weights_tag = tag
+        return self._plan
+
+    def forward(self, x, t, y=None):
+        """x (B,1,rows,dim); t (B,) or (1,) integer timesteps; y (B,1,T_obs,cond_dim) or None -> (B,1,rows,dim)."""
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("spdm: backward kernels are not built yet — call under torch.no_grad() / .eval()")
+        if not x.is_cuda:
+            raise RuntimeError("spdm U-Net: input is on the CPU (no CPU fallback)")
+        B, _, rows, dim = x.shape
+        if y is not None and self.global_cond_dim is None:
+            raise ValueError("conditioning passed to a U-Net built with global_cond_dim=None")
+        T = cd = None
+        if y is not None and y.dim() == 4:
+            T, cd = int(y.shape[2]), int(y.shape[3])
+        plan = self.plan_for(B, rows, dim, T, cd)
+        out = plan.unet_forward(x, t.reshape(-1), y)
+        return out.to(x.dtype)
+
+
+class UNet_Film(_UNetBase):
+    """FiLM U-Net with six SelfAttention blocks (reference models/Unet_FiLmLayer.py:240)."""
+    _attention = True
+
+
+class UNet_Film_noAttention(_UNetBase):
+    """FiLM U-Net without attention (reference models/Unet_FiLmLayer_noAttention.py:240)."""
+    _attention = False

@@ -1,0 +1,303 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libspdm.so) against the CPU oracle and the committed
+golden vectors produced by the unmodified reference modules (tests/golden/*.npz, oracle/make_golden.py).
+
+Tolerances (BASELINE.json north_star): fp32 path rel 1e-4 per U-Net forward and per denoising step;
+bf16 path rel 1e-2 on the final trajectory.  rel(a, b) = max|a - b| / max|b|.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fixtures, sampler_ref, unet_ref
+from oracle.schedulers import RefDDIMScheduler, RefDDPMScheduler
+
+pytestmark = pytest.mark.gpu
+
+FP32_TOL = 1e-4
+BF16_FWD_TOL = 3e-2     # single forward, informational bound for the tensor-core path
+BF16_FINAL_TOL = 1e-2   # final trajectory (the contract)
+
+
+def rel(a, b):
+    a, b = a.detach().float().cpu(), b.detach().float().cpu()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+@pytest.fixture(scope="module")
+def spdm():
+    import state_policy_diffusionmodel_b200 as m
+    assert torch.cuda.is_available()
+    return m
+
+
+def _golden(golden_dir, name):
+    return {k: torch.from_numpy(v) if isinstance(v, np.ndarray) and v.dtype != object else v
+            for k, v in np.load(os.path.join(golden_dir, name + ".npz")).items()}
+
+
+UNET_CASES = [("unet_attn", True, 0, 31, 5), ("unet_noattn", False, 3, 31, 5), ("unet_attn_rows61", True, 4, 61, 5),
+              ("unet_noattn_pos2", False, 5, 31, 2)]
+
+
+@pytest.mark.parametrize("name,attention,seed,rows,dim", UNET_CASES)
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unet_forward_vs_golden(spdm, golden_dir, name, attention, seed, rows, dim, precision):
+    """UNet_Film / UNet_Film_noAttention forward against the reference's own output (golden) and the oracle."""
+    g = _golden(golden_dir, name)
+    sd = fixtures.make_unet_weights(attention=attention, seed=seed)
+    x, y, t = g["x"], g["y"], g["t"]
+    B = x.shape[0]
+    plan = spdm.DenoisePlan(attention=attention, precision=precision, batch_max=B, rows=rows, dim=dim, graph_steps=0)
+    plan.load_unet_state_dict(sd)
+    assert [m for m in plan.missing_weights() if not m.startswith("vision_encoder")] == []
+    tol = FP32_TOL if precision == "fp32" else BF16_FWD_TOL
+    out = plan.unet_forward(x, t, y)
+    assert out.shape == g["out"].shape
+    assert rel(out, g["out"]) < tol
+    out_nc = plan.unet_forward(x, t, None)
+    assert rel(out_nc, g["out_nocond"]) < tol
+    # layout-sensitive intermediate activations pinned by the golden file
+    for tap in ("down1", "up1"):
+        full = g["full_" + tap]
+        _, got = plan.debug_forward(x, t, y, tap, tuple(full.shape))
+        assert rel(got, full) < tol, tap
+    with torch.no_grad():
+        ref = unet_ref.unet_forward(sd, x, t, y, attention=attention)
+    assert rel(out, ref) < tol
+    assert plan.launch_count > 0
+    plan.close()
+
+
+def test_unet_batch_and_t_broadcast(spdm):
+    """t of shape (1,) broadcasts over the batch (models/diffusion_ddpm.py:209); odd batch sizes work on both paths."""
+    sd = fixtures.make_unet_weights(attention=True, seed=0)
+    g = torch.Generator().manual_seed(9)
+    x = torch.rand((5, 1, 31, 5), generator=g)
+    y = torch.randn((5, 1, 10, 135), generator=g)
+    t = torch.tensor([17])
+    with torch.no_grad():
+        ref = unet_ref.unet_forward(sd, x, t, y, attention=True)
+    for precision, tol in (("fp32", FP32_TOL), ("bf16", BF16_FWD_TOL)):
+        plan = spdm.DenoisePlan(attention=True, precision=precision, batch_max=40, graph_steps=0)
+        plan.load_unet_state_dict(sd)
+        out = plan.unet_forward(x, t, y)
+        assert rel(out, ref) < tol
+        # a smaller batch on the same plan must give the same rows
+        out2 = plan.unet_forward(x[:2], t, y[:2])
+        assert rel(out2, ref[:2]) < tol
+        plan.close()
+
+
+def test_encoder_and_cond_vs_golden(spdm, golden_dir):
+    """Autoencoder.encoder (models/encoder/autoencoder.py:11-20) + prepare_obs_cond_vectors (diffusion_ddpm.py:317-330)."""
+    g = _golden(golden_dir, "encoder")
+    esd = fixtures.make_encoder_weights()
+    gen = torch.Generator().manual_seed(5)
+    img = torch.rand((4, 3, 96, 96), generator=gen)
+    plan = spdm.DenoisePlan(attention=False, precision="fp32", batch_max=4, graph_steps=0)
+    plan.load_encoder_state_dict(esd)
+    out = plan.encode_images(img)
+    assert rel(out, g["out"]) < FP32_TOL
+    batch = fixtures.make_batch(3, seed=4321)
+    plan.load_unet_state_dict(fixtures.make_unet_weights(attention=False, seed=3))
+    cond = plan.encode_cond(batch["image"], batch["position"], batch["action"], batch["velocity"])
+    with torch.no_grad():
+        ref = unet_ref.obs_cond(esd, batch)
+    assert rel(cond.reshape(3, 10, 135), ref) < FP32_TOL
+    plan.close()
+
+
+@pytest.mark.parametrize("kind,T,n", [("ddpm", 1000, 1000), ("ddpm", 20, 20), ("ddim", 50, 50), ("ddim", 100, 100), ("ddim", 1000, 50)])
+def test_step_kernel_vs_oracle(spdm, kind, T, n):
+    """One fused posterior update + inpaint per schedule index against the restated diffusers step."""
+    Ref = RefDDPMScheduler if kind == "ddpm" else RefDDIMScheduler
+    Mine = spdm.DDPMScheduler if kind == "ddpm" else spdm.DDIMScheduler
+    kw = dict(num_train_timesteps=T, beta_schedule="linear", clip_sample=False, prediction_type="epsilon")
+    ref, mine = Ref(**kw), Mine(**kw)
+    ref.set_timesteps(n)
+    mine.set_timesteps(n)
+    assert torch.equal(ref.timesteps, mine.timesteps)
+    plan = spdm.DenoisePlan(attention=False, precision="fp32", batch_max=1, rows=31, dim=5, inpaint_rows=1, graph_steps=0,
+                            scheduler_only=True)
+    plan.set_schedule(kind, mine.coef_table(), mine.timesteps)
+    g = torch.Generator().manual_seed(3)
+    B = 7
+    x = torch.randn((B, 1, 31, 5), generator=g)
+    eps = torch.randn((B, 1, 31, 5), generator=g)
+    z = torch.randn((B, 1, 31, 5), generator=g)
+    inp = torch.randn((B, 1, 1, 5), generator=g)
+    for i in sorted(set([0, 1, n // 2, n - 2, n - 1])):
+        t = int(ref.timesteps[i])
+        if kind == "ddpm":
+            want = ref.step(eps, t, x, noise=z).prev_sample
+        else:
+            want = ref.step(eps, t, x).prev_sample
+        want = sampler_ref.add_constraints(want.clone(), inp, 1)
+        got = plan.step(x, eps, i, noise=z, inpaint=inp.reshape(B, -1))
+        assert rel(got, want) < 1e-5, (kind, i, t)
+    plan.close()
+
+
+def test_scheduler_objects_on_gpu(spdm):
+    """DDPMScheduler/DDIMScheduler .step / .add_noise (the objects the reference assigns to `.noise_scheduler`)."""
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn((3, 1, 31, 5), generator=g)
+    eps = torch.randn((3, 1, 31, 5), generator=g)
+    z = torch.randn((3, 1, 31, 5), generator=g)
+    kw = dict(num_train_timesteps=100, beta_schedule="linear", clip_sample=False, prediction_type="epsilon")
+    for Ref, Mine in ((RefDDPMScheduler, spdm.DDPMScheduler), (RefDDIMScheduler, spdm.DDIMScheduler)):
+        ref, mine = Ref(**kw), Mine(**kw)
+        ref.set_timesteps(100)
+        mine.set_timesteps(100)
+        for t in (99, 42, 0):
+            want = ref.step(eps, t, x, noise=z).prev_sample if Ref is RefDDPMScheduler else ref.step(eps, t, x).prev_sample
+            got = mine.step(eps.cuda(), t, x.cuda(), variance_noise=z.cuda()).prev_sample
+            assert rel(got, want) < 1e-5
+        tt = torch.tensor([5, 50, 99])
+        assert rel(mine.add_noise(x.cuda(), z.cuda(), tt.cuda()), ref.add_noise(x, z, tt)) < 1e-6
+
+
+SAMPLE_CASES = [("sample_ddim10_attn", "ddim", True, 0, 5), ("sample_ddpm20_noattn_pos2", "ddpm", False, 3, 2)]
+
+
+@pytest.mark.parametrize("name,kind,attention,seed,dim", SAMPLE_CASES)
+@pytest.mark.parametrize("graph_steps", [0, 1, 4])
+def test_sample_fp32_per_step_vs_golden(spdm, golden_dir, name, kind, attention, seed, dim, graph_steps):
+    """The K-step loop (spdm_sample) with injected x_T and noise against the history the unmodified reference wrapper
+    produced (golden), per denoising step, fp32 path, rel 1e-4."""
+    g = _golden(golden_dir, name)
+    K = int(g["noise_steps"])
+    sd = fixtures.make_unet_weights(attention=attention, seed=seed)
+    Mine = spdm.DDPMScheduler if kind == "ddpm" else spdm.DDIMScheduler
+    sch = Mine(num_train_timesteps=K, beta_schedule="linear", clip_sample=False, prediction_type="epsilon")
+    sch.set_timesteps(K)
+    assert torch.equal(sch.timesteps, g["timesteps"])
+    plan = spdm.DenoisePlan(attention=attention, precision="fp32", batch_max=2, rows=31, dim=dim, inpaint_rows=1,
+                            graph_steps=graph_steps)
+    plan.load_unet_state_dict(sd)
+    plan.set_schedule(kind, sch.coef_table(), sch.timesteps)
+    plan.set_cond(g["obs_cond"][:1].reshape(1, -1))
+    x0, hist = plan.sample(g["x_T"], noise=g["noise"], inpaint=g["inpaint"][:1].reshape(1, -1), history=True)
+    want = g["history"]  # (K+1, 1, 1, 31, dim)
+    assert hist.shape == want.shape
+    for k in range(K + 1):
+        assert rel(hist[k], want[k]) < FP32_TOL, "step %d" % k
+    assert rel(x0, want[-1]) < FP32_TOL
+    plan.close()
+
+
+@pytest.mark.parametrize("kind,attention,K", [("ddim", True, 50), ("ddpm", False, 100)])
+def test_sample_bf16_final_trajectory(spdm, kind, attention, K):
+    """bf16 tensor-core path: final trajectory within rel 1e-2 of the fp32 oracle loop (same x_T, same injected noise)."""
+    B = 4
+    sd = fixtures.make_unet_weights(attention=attention, seed=0)
+    esd = fixtures.make_encoder_weights()
+    batch = fixtures.make_batch(B, seed=1234)
+    x_T = fixtures.make_xT(B)
+    noise = fixtures.make_noise(K, B)
+    with torch.no_grad():
+        cond = unet_ref.obs_cond(esd, batch).unsqueeze(1)
+        inp = unet_ref.inpaint_vector(batch, 1).unsqueeze(1)
+        ref_s = sampler_ref.make_scheduler(kind, K)
+        want = sampler_ref.sample_ref(sd, ref_s, K, x_T, cond, inp, 1, attention=attention, noise=noise)
+    Mine = spdm.DDPMScheduler if kind == "ddpm" else spdm.DDIMScheduler
+    sch = Mine(num_train_timesteps=K, beta_schedule="linear", clip_sample=False, prediction_type="epsilon")
+    sch.set_timesteps(K)
+    results = {}
+    for precision in ("fp32", "bf16"):
+        plan = spdm.DenoisePlan(attention=attention, precision=precision, batch_max=B, inpaint_rows=1, graph_steps=5)
+        plan.load_unet_state_dict(sd)
+        plan.load_encoder_state_dict(esd)
+        plan.set_schedule(kind, sch.coef_table(), sch.timesteps)
+        plan.encode_cond(batch["image"], batch["position"], batch["action"], batch["velocity"])
+        results[precision] = plan.sample(x_T, noise=noise, inpaint=inp.reshape(B, -1))
+        plan.close()
+    assert rel(results["fp32"], want) < 5e-4   # K compounded steps of the 1e-4 per-step path
+    assert rel(results["bf16"], want) < BF16_FINAL_TOL
+
+
+def test_sample_philox_noise_statistics(spdm):
+    """Throughput mode draws z in-kernel (Philox4x32-10 + Box-Muller): check it is N(0,1), seed-reproducible and
+    seed-sensitive, using a 1-step DDPM schedule whose update is x_prev = k_x*x + ... + sigma*z with eps-net output."""
+    sd = fixtures.make_unet_weights(attention=False, seed=0)
+    B, K = 64, 4
+    sch = spdm.DDPMScheduler(num_train_timesteps=K, beta_schedule="linear", clip_sample=False, prediction_type="epsilon")
+    sch.set_timesteps(K)
+    plan = spdm.DenoisePlan(attention=False, precision="bf16", batch_max=B, cond_dim=0, inpaint_rows=0, graph_steps=2)
+    plan.load_unet_state_dict({k: v for k, v in sd.items() if "cond_encoder" not in k})
+    plan.set_schedule("ddpm", sch.coef_table(), sch.timesteps)
+    x_T = fixtures.make_xT(B)
+    a = plan.sample(x_T, seed=1)
+    b = plan.sample(x_T, seed=1)
+    c = plan.sample(x_T, seed=2)
+    assert torch.equal(a, b)
+    assert not torch.equal(a, c)
+    # compare against the injected-noise run with z = 0: the difference is a linear image of the Philox draws
+    zero = torch.zeros((K, B, 1, 31, 5))
+    d = plan.sample(x_T, noise=zero)
+    diff = (a - d).flatten()
+    assert torch.isfinite(diff).all()
+    assert abs(float(diff.mean())) < 0.05 * float(diff.std())
+    plan.close()
+
+
+def test_module_surface(spdm):
+    """The nn.Module / wrapper surface the reference's scripts touch, end to end on the GPU."""
+    torch.manual_seed(0)
+    net = spdm.UNet_Film(in_channels=1, out_channels=1, noise_steps=1000, global_cond_dim=1350).cuda().eval()
+    sd = fixtures.make_unet_weights(attention=True, seed=0)
+    net.load_state_dict(sd, strict=True)
+    net.configure(precision="fp32")
+    g = torch.Generator().manual_seed(100)
+    x = torch.rand((2, 1, 31, 5), generator=g)
+    y = torch.randn((2, 1, 10, 135), generator=g)
+    t = torch.tensor([10])
+    with torch.no_grad():
+        out = net(x.cuda(), t.cuda(), y.cuda())
+        ref = unet_ref.unet_forward(sd, x, t, y, attention=True)
+    assert rel(out, ref) < FP32_TOL
+    with pytest.raises(RuntimeError):
+        net(x, t, y)  # CPU tensors: no fallback
+
+    m = spdm.Diffusion_DDIM(noise_steps=1000, obs_horizon=10, pred_horizon=30, observation_dim=135, prediction_dim=5,
+                            model="UNet_Film", inpaint_horizon=1).cuda().eval()
+    m.noise_estimator.load_state_dict(sd, strict=True)
+    esd = fixtures.make_encoder_weights()
+    m.vision_encoder.load_state_dict(esd, strict=True)
+    m.configure(precision="fp32")
+    m.use_ddim(10)  # generate.py:28-35
+    batch = fixtures.make_batch(2, seed=4321)
+    torch.manual_seed(5)
+    hist = m.sample(batch={k: v.clone() for k, v in batch.items()}, option="sample_history")
+    assert isinstance(hist, list) and len(hist) == 11 and tuple(hist[0].shape) == (1, 1, 31, 5)
+    # same start sample through the oracle loop
+    with torch.no_grad():
+        cond = unet_ref.obs_cond(esd, batch)[:1].unsqueeze(1)
+        inp = unet_ref.inpaint_vector(batch, 1)[:1].unsqueeze(1)
+        want = sampler_ref.sample_ref(sd, sampler_ref.make_scheduler("ddim", 10), 10, hist[0].cpu(), cond, inp, 1, attention=True)
+    assert rel(hist[-1], want) < 5e-4
+    final = m.sample(batch={k: v.clone() for k, v in batch.items()}, x_T=hist[0])
+    assert rel(final, want) < 5e-4
+    x0, obs, inpaint = m.sample(batch={k: torch.cat([v, v, v, v], dim=1) for k, v in batch.items()}, mode="validation")
+    assert tuple(x0.shape) == (1, 1, 31, 5) and tuple(inpaint.shape) == (1, 1, 1, 5) and obs["image"].shape[1] == 10
+    outs = m.sample(batch={k: v.clone() for k, v in batch.items()}, batched=True)
+    assert tuple(outs.shape) == (2, 1, 31, 5)
+
+
+def test_training_forward_loss(spdm, golden_dir):
+    """process_single_batch forward (q-sample + inpaint + U-Net + MSE, diffusion_ddpm.py:128-173) against the golden loss."""
+    g = _golden(golden_dir, "validate_train")
+    B = 3
+    gen = torch.Generator().manual_seed(777)
+    full = {"image": torch.rand((B, 40, 3, 96, 96), generator=gen), "position": 0.3 * torch.randn((B, 40, 2), generator=gen),
+            "velocity": 2 * torch.rand((B, 40, 2), generator=gen) - 1, "action": 2 * torch.rand((B, 40, 3), generator=gen) - 1}
+    m = spdm.Diffusion_DDPM(noise_steps=12, obs_horizon=10, pred_horizon=30, observation_dim=135, prediction_dim=5,
+                            model="UNet_Film", inpaint_horizon=1).cuda().eval()
+    m.noise_estimator.load_state_dict(fixtures.make_unet_weights(attention=True, seed=0), strict=True)
+    m.vision_encoder.load_state_dict(fixtures.make_encoder_weights(), strict=True)
+    m.configure(precision="fp32")
+    with torch.no_grad():
+        loss = m.process_single_batch(full, t=g["train_t"].cuda(), noise=g["train_noise"].cuda())
+    assert abs(float(loss) - float(g["train_loss"])) < 1e-4 * abs(float(g["train_loss"]))
