@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""bench.py — denoised trajectories/sec of the B200 hot path (BASELINE.json metric, configs[1]):
+DDIM-50 sampling, attention FiLM U-Net (UNet_Film), stacked position+action output (31 x 5), batch 256 per GPU,
+random-init weights, synthetic CarRacing-shaped conditioning (10 frames of 96x96 RGB + position/velocity/action).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU; torchrun for N > 1)
+  python bench.py --impl reference --gpus N --steps K ...  the reference's CPU path (oracle port) on the host cores
+
+One "step" = one complete DDIM-50 sampling call over the per-GPU batch: conditioning encode (vision encoder + FiLM GEMM)
+followed by the CUDA-graphed 50-step loop (U-Net forward + posterior update + inpaint per step).
+`value`  : inputs already resident in HBM, C-ABI calls spdm_encode_cond + spdm_sample, CUDA-event timed.
+`e2e`    : the public API call Diffusion_DDIM.sample(batch, batched=True) with pinned HOST buffers, H2D of the
+           conditioning and D2H of the trajectories inside the timed region.
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "denoised trajectories/sec (DDIM-50, UNet_Film attention, 31x5, batch 256/GPU)"
+UNIT = "trajectories/s"
+# algorithmic FLOPs (valid conv taps only), SURVEY.md 8(d): per sample per U-Net forward / per conditioning encode
+FLOP_UNET_ATTN = {31: 603.27e6, 61: 1270.91e6, 121: 2728.18e6}
+FLOP_UNET_NOATTN = {31: 535.75e6, 61: 1095.20e6, 121: 2214.12e6}
+FLOP_COND = 80.0e6
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="spdm", choices=["spdm", "reference"])
+    ap.add_argument("--batch", type=int, default=256, help="trajectories per GPU")
+    ap.add_argument("--ddim-steps", type=int, default=50)
+    ap.add_argument("--sampler", default="ddim", choices=["ddim", "ddpm"])
+    ap.add_argument("--variant", default="attn", choices=["attn", "noattn"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--rows", type=int, default=31)
+    ap.add_argument("--graph-steps", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-only", action="store_true", help="one sampling call, for ncu")
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm=float(d["hbm_gbs"]), tf_burst=float(d["bf16_tflops"]), tf_sust=float(d.get("bf16_tflops_sustained", d["bf16_tflops"])),
+                    source="measured (MEASURED_PEAKS.json)")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+def synth_batch(B, T_obs, seed, pin=False):
+    """SURVEY.md 8(d) synthetic conditioning, host fp32."""
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    image = torch.rand((B, T_obs, 3, 96, 96), generator=g)
+    dpos = 0.02 * torch.randn((B, T_obs, 2), generator=g)
+    dpos[:, 0] = 0
+    batch = {"image": image, "position": torch.cumsum(dpos, dim=1), "velocity": 2 * torch.rand((B, T_obs, 2), generator=g) - 1,
+             "action": 2 * torch.rand((B, T_obs, 3), generator=g) - 1}
+    if pin:
+        batch = {k: v.pin_memory() for k, v in batch.items()}
+    return batch
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.sm, self.reasons, self.sm_max = index, False, [], set(), None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.sm_max = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def run(self):
+        if self.nv is None:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap", nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.sm.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": self.sm_max, "reasons": sorted(self.reasons),
+                "samples": len(sm)}
+
+
+def cpu_oracle_rate(state, enc_state, args, budget_s, b_cpu):
+    """The reference's CPU path (oracle port: fp32 eager torch on the host cores, reference loop structure
+    models/diffusion_ddim.py:67-73): trajectories/s on a bounded sample, extrapolated to K denoising steps."""
+    import torch
+    from oracle import sampler_ref, unet_ref
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    attention = args.variant == "attn"
+    K = args.ddim_steps
+    batch = synth_batch(b_cpu, 10, 999)
+    sd = {k: v.detach().float().cpu() for k, v in state.items()}
+    esd = {k: v.detach().float().cpu() for k, v in enc_state.items()}
+    g = torch.Generator().manual_seed(7)
+    x_t = torch.rand((b_cpu, 1, args.rows, 5), generator=g)
+    sch = sampler_ref.make_scheduler(args.sampler, K)
+    sch.set_timesteps(K)
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        cond = unet_ref.obs_cond(esd, batch).unsqueeze(1)
+        inp = unet_ref.inpaint_vector(batch, 1).unsqueeze(1)
+        t_enc = time.perf_counter() - t0
+        # warm-up step, then timed denoising steps until the budget is used
+        sampler_ref.sample_ref(sd, sch, K, x_t, cond, inp, 1, attention=attention, max_steps=1)
+        n, t_den = 0, 0.0
+        while n < K and (t_den < budget_s or n < 2):
+            t0 = time.perf_counter()
+            sampler_ref.sample_ref(sd, sch, K, x_t, cond, inp, 1, attention=attention, max_steps=1)
+            t_den += time.perf_counter() - t0
+            n += 1
+    per_step = t_den / n
+    rate = b_cpu / (t_enc + K * per_step)
+    sample = "%d trajectories: conditioning encode %.2fs + %d timed denoising steps (%.3fs each), extrapolated to %d steps" % (
+        b_cpu, t_enc, n, per_step, K)
+    return rate, cores, sample
+
+
+def run_reference(args):
+    """--impl reference: the oracle port of the reference's CPU path, all host threads, same metric/config."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from oracle import fixtures
+    attention = args.variant == "attn"
+    sd = fixtures.make_unet_weights(attention=attention, seed=0)
+    esd = fixtures.make_encoder_weights()
+    rates, cores, sample = [], 1, ""
+    for i in range(args.warmup + args.steps):
+        r, cores, sample = cpu_oracle_rate(sd, esd, args, budget_s=6.0, b_cpu=32)
+        if i >= args.warmup:
+            rates.append(r)
+    value = sum(rates) / len(rates)
+    total_B = args.batch * args.gpus
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1000.0 * total_B / value, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, total_B),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def config_dict(args, total_B):
+    return {"workload": "%s-%d sampling, %s, pred 31x5 (rows=%d), obs 10x(96x96x3 + pos/vel/act), random-init weights" % (
+                args.sampler.upper(), args.ddim_steps, "UNet_Film (attention)" if args.variant == "attn" else "UNet_Film_noAttention", args.rows),
+            "global_batch": total_B, "per_gpu_batch": args.batch, "denoise_steps": args.ddim_steps, "precision": args.precision,
+            "parallelism": "batch-sharded x%d, final all_gather" % args.gpus,
+            "cache": "inputs_larger_than_l2 (283 MB of frames per step per GPU)", "graph_steps": args.graph_steps}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    import state_policy_diffusionmodel_b200 as spdm
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the spdm path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    attention = args.variant == "attn"
+    B, K = args.batch, args.ddim_steps
+    rows = args.rows
+
+    # ---- model (random init, same on every rank), public wrapper of the reference surface --------------------
+    torch.manual_seed(0)
+    Wrapper = spdm.Diffusion_DDIM
+    model = Wrapper(noise_steps=1000, obs_horizon=10, pred_horizon=rows - 1, observation_dim=135, prediction_dim=5,
+                    model="UNet_Film" if attention else "UNet_FilmnoAttention", inpaint_horizon=1).to(dev).eval()
+    model.configure(precision=args.precision, graph_steps=args.graph_steps, batch_max=B)
+    if args.sampler == "ddim":
+        model.use_ddim(K)       # generate.py:28-35 convention: DDIMScheduler(num_train_timesteps=K), K steps
+    else:
+        model.noise_steps = K
+        model.noise_scheduler = spdm.DDPMScheduler(num_train_timesteps=K, beta_schedule="linear", clip_sample=False,
+                                                   prediction_type="epsilon")
+
+    # ---- synthetic inputs --------------------------------------------------------------------------------------
+    host = synth_batch(B, 10, 1234 + rank, pin=True)
+    devb = {k: v.to(dev) for k, v in host.items()}
+    g = torch.Generator().manual_seed(77 + rank)
+    x_T = torch.rand((B, 1, rows, 5), generator=g).to(dev)
+    plan = model._plan(B)
+    model._bind_schedule(plan)
+    inpaint = model.prepare_inpaint_vectors(devb).reshape(B, -1).contiguous()
+    gathered = [torch.empty((B, 1, rows, 5), device=dev) for _ in range(world)] if world > 1 else None
+
+    def step_device(i):
+        plan.encode_cond(devb["image"], devb["position"], devb["action"], devb["velocity"])
+        out = plan.sample(x_T, inpaint=inpaint, seed=1000 + i)
+        if world > 1:
+            dist.all_gather(gathered, out)
+        return out
+
+    def step_e2e(i):
+        out = model.sample(dict(host), batched=True, x_T=x_T, seed=1000 + i)
+        if world > 1:
+            dist.all_gather(gathered, out)
+        return out.cpu()
+
+    if args.profile_only:
+        for i in range(2):
+            step_device(i)
+        torch.cuda.synchronize()
+        return
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for i in range(max(args.warmup, 3)):
+        step_device(i)
+    launches0 = plan.launch_count
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(step_device, args.steps)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    launches = plan.launch_count - launches0
+    total_B = B * world
+    value = total_B * args.steps / (ms / 1000.0)
+
+    # ---- e2e through the public API with host buffers -----------------------------------------------------------
+    for i in range(2):
+        step_e2e(i)
+    ms_e2e = timed(step_e2e, args.steps)
+    e2e_value = total_B * args.steps / (ms_e2e / 1000.0)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = B * rows * 5 * 4
+
+    # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), CUDA events around each launch ----------
+    pk = peaks()
+    prof = plan.profile_step(B, reps=5)
+    conv = prof["conv3x3"]
+    ach = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "conv_tc_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    step_ms_total = sum(v["ms"] for v in prof.values())
+    classes = {k: {"ms": round(v["ms"], 4), "launches": round(v["launches"], 1),
+                   "tflops": round(v["flops"] / (v["ms"] * 1e-3) / 1e12, 2) if v["ms"] > 0 and v["flops"] > 0 else None,
+                   "gbs": round(v["bytes"] / (v["ms"] * 1e-3) / 1e9, 1) if v["ms"] > 0 else None,
+                   "share": round(v["ms"] / step_ms_total, 3) if step_ms_total > 0 else None} for k, v in prof.items()}
+    flop_unet = (FLOP_UNET_ATTN if attention else FLOP_UNET_NOATTN).get(rows)
+    whole = None
+    if flop_unet:
+        whole = value * (K * flop_unet + FLOP_COND) / 1e12 / world
+    roofline = {"bound": "tensor", "kernel": "conv_tc_kernel (3x3 implicit GEMM, %d launches per denoising step)" % round(conv["launches"]),
+                "achieved": round(ach, 2), "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": round(ach / pk["tf_burst"], 4),
+                "traffic": traffic, "peak_source": pk["source"] + ", burst figure (kernels timed one by one)",
+                "whole_job_tflops_per_gpu": round(whole, 2) if whole else None,
+                "whole_job_frac_of_sustained": round(whole / pk["tf_sust"], 4) if whole else None,
+                "kernel_classes_per_denoise_step": classes}
+
+    line = {"metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.precision, "data": "synthetic", "config": config_dict(args, total_B),
+            "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": round(ms_e2e / args.steps, 3)},
+            "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roofline}
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, cores, sample = cpu_oracle_rate(model.noise_estimator.state_dict(), model.vision_encoder.state_dict(), args,
+                                              budget_s=12.0, b_cpu=32)
+        line["cpu_baseline"] = {"value": round(rate, 3), "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -103,6 +103,14 @@ int spdm_add_noise(spdm_plan* plan, const float* x0, const float* noise, const i
                    const float* sqrt_ab, const float* sqrt_1mab, const float* inpaint,
                    float* out, int32_t B, void* stream);
 
+/* Kernel-class profile of one denoising step (U-Net forward + posterior update) run EAGERLY with CUDA
+ * events around every launch, averaged over `reps` steps: out[c*4 + {0,1,2,3}] = {ms, launches,
+ * algorithmic FLOPs, algorithmic bytes} for class c.  Needs a schedule and (if conditional) cached cond. */
+#define SPDM_PROFILE_CLASSES 9
+enum { SPDM_PC_CONV3 = 0, SPDM_PC_GEMM1, SPDM_PC_APPLY, SPDM_PC_STATS, SPDM_PC_RESAMPLE, SPDM_PC_LN,
+       SPDM_PC_SDPA, SPDM_PC_IO, SPDM_PC_STEP };
+int spdm_profile_step(spdm_plan* plan, int32_t B, int32_t reps, double* out, void* stream);
+
 /* Introspection used by bench.py / tests. */
 int64_t spdm_plan_launch_count(spdm_plan* plan);     /* kernels enqueued so far by this plan  */
 int64_t spdm_plan_workspace_bytes(spdm_plan* plan);

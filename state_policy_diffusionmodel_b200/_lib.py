@@ -22,6 +22,7 @@ VARIANT_ATTENTION, VARIANT_NO_ATTENTION = 0, 1
 PRECISION_FP32, PRECISION_BF16 = 0, 1
 SCHED_DDPM, SCHED_DDIM = 0, 1
 FLAG_SCHEDULER_ONLY = 1
+PROFILE_CLASSES = ("conv3x3", "gemm1x1", "gn_apply", "gn_stats", "resample", "layernorm", "sdpa", "io_conv", "step")
 
 _P = _c.c_void_p
 _PROTOTYPES = {
@@ -39,6 +40,7 @@ _PROTOTYPES = {
     "spdm_step": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_int32, _c.c_int32, _P]),
     "spdm_sample": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_uint64, _c.c_int32, _P]),
     "spdm_add_noise": (_c.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _c.c_int32, _P]),
+    "spdm_profile_step": (_c.c_int, [_P, _c.c_int32, _c.c_int32, _c.POINTER(_c.c_double), _P]),
     "spdm_plan_launch_count": (_c.c_int64, [_P]),
     "spdm_plan_workspace_bytes": (_c.c_int64, [_P]),
     "spdm_last_error": (_c.c_char_p, []),

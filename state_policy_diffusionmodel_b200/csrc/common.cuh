@@ -21,7 +21,7 @@ enum : int { EPI_STATS = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RESID = 8 };
 
 #define SPDM_FILM_WIDTH 1792 /* sum over the 6 stages of 2*C_out */
 #define SPDM_TEMB_WIDTH 896  /* sum over the 6 stages of C_out   */
-#define SPDM_MAX_PARTIALS 32 /* upper bound on GroupNorm partial slots per sample */
+#define SPDM_MAX_PARTIALS 64 /* upper bound on GroupNorm partial slots per sample */
 
 __device__ __forceinline__ float gelu_exact(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));

@@ -111,6 +111,8 @@ struct spdm_plan {
   bool have_cond = false;
   float* xt = nullptr; float* eps = nullptr;  // [Bcap][n]
   StepDyn* dyn = nullptr; StepDyn* dyn_host = nullptr;
+  cudaStream_t own_stream = nullptr;  // graphs are captured and replayed here (the caller's stream may be the legacy stream)
+  cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   float* enc_feat = nullptr; int enc_chunk = 0;  // [enc_chunk][9216]
   float* enc_out = nullptr;                       // [Bcap*T][128]
 
@@ -118,6 +120,11 @@ struct spdm_plan {
   // graphs keyed by batch: [0] = graph_steps-step body, [1] = 1-step body
   struct GraphSet { cudaGraphExec_t multi = nullptr, single = nullptr; long long n_multi = 0, n_single = 0; };
   std::map<long long, GraphSet> graphs;
+
+  // eager profiling (spdm_profile_step): CUDA events around every launch, summed per kernel class
+  struct ProfRec { int cat; cudaEvent_t e0, e1; double flops, bytes; };
+  bool prof_on = false;
+  std::vector<ProfRec> prof;
 
   // debug tap
   std::string tap_name; float* tap_out = nullptr; long long tap_count = -1;
@@ -347,6 +354,19 @@ struct FwdCtx {
   cudaStream_t s;
 };
 
+enum : int { PC_CONV3 = 0, PC_GEMM1, PC_APPLY, PC_STATS, PC_RESAMPLE, PC_LN, PC_SDPA, PC_IO, PC_STEP, PC_N };
+
+template <typename F> void timed(spdm_plan* p, cudaStream_t s, int cat, double flops, double bytes, F&& f) {
+  if (!p->prof_on) { f(); return; }
+  spdm_plan::ProfRec r{cat, nullptr, nullptr, flops, bytes};
+  CUDA_OK(cudaEventCreate(&r.e0));
+  CUDA_OK(cudaEventCreate(&r.e1));
+  CUDA_OK(cudaEventRecord(r.e0, s));
+  f();
+  CUDA_OK(cudaEventRecord(r.e1, s));
+  p->prof.push_back(r);
+}
+
 template <typename T> struct Fwd {
   spdm_plan* p;
   FwdCtx c;
@@ -379,19 +399,29 @@ template <typename T> struct Fwd {
       if (!tc) {
         tc = tc_gemm_create(reinterpret_cast<const bf16*>(in), ld_in, g.w16, g.Cin, g.Cout, g.taps, H, W, p->Bcap);
         REQUIRE(tc != nullptr, "%s: %s", wname.c_str(), tc_last_error());
-        REQUIRE(tc_gemm_partials(tc) <= SPDM_MAX_PARTIALS, "%s: too many GroupNorm partials", wname.c_str());
+        REQUIRE(!(flags & EPI_STATS) || tc_gemm_partials(tc) <= SPDM_MAX_PARTIALS, "%s: too many GroupNorm partials", wname.c_str());
       }
-      tc_gemm_launch(tc, reinterpret_cast<bf16*>(out), ld_out, p->stats, (flags & EPI_BIAS) ? g.bias : nullptr,
-                     reinterpret_cast<const bf16*>(resid), ld_res, flags, Bpad, c.s);
+      // algorithmic work: taps that fall inside the image only, real batch rows only
+      const double flops = g.taps == 9 ? 2.0 * g.Cin * g.Cout * (3.0 * H - 2) * (3.0 * W - 2) * c.B
+                                       : 2.0 * g.Cin * g.Cout * (double)H * W * c.B;
+      const double bytes = ((double)c.B * H * W * (g.Cin + g.Cout) + (double)g.taps * g.Cin * g.Cout) * 2.0;
+      timed(p, c.s, g.taps == 9 ? PC_CONV3 : PC_GEMM1, flops, bytes, [&] {
+        tc_gemm_launch(tc, reinterpret_cast<bf16*>(out), ld_out, p->stats, (flags & EPI_BIAS) ? g.bias : nullptr,
+                       reinterpret_cast<const bf16*>(resid), ld_res, flags, Bpad, c.s);
+      });
       curP = tc_gemm_partials(tc);
     } else {
       GemmSimtArgs a{};
       a.in = in; a.w = g.w32; a.bias = (flags & EPI_BIAS) ? g.bias : nullptr; a.resid = (flags & EPI_RESID) ? resid : nullptr;
       a.out = out; a.M = c.B * H * W; a.Cin = g.Cin; a.Cout = g.Cout; a.ld_in = ld_in; a.ld_out = ld_out; a.ld_res = ld_res;
       a.H = H; a.W = W; a.taps = g.taps; a.act = (flags & EPI_GELU) ? ACT_GELU : ACT_NONE;
-      launch_gemm_simt<float, float>(a, c.s);
+      const double flops = g.taps == 9 ? 2.0 * g.Cin * g.Cout * (3.0 * H - 2) * (3.0 * W - 2) * c.B
+                                       : 2.0 * g.Cin * g.Cout * (double)H * W * c.B;
+      const double bytes = ((double)c.B * H * W * (g.Cin + g.Cout) + (double)g.taps * g.Cin * g.Cout) * 4.0;
+      timed(p, c.s, g.taps == 9 ? PC_CONV3 : PC_GEMM1, flops, bytes, [&] { launch_gemm_simt<float, float>(a, c.s); });
       if (flags & EPI_STATS) {
-        launch_stats<T>(out, p->stats, c.B, H * W, g.Cout, ld_out, c.s);
+        timed(p, c.s, PC_STATS, 0, (double)c.B * H * W * g.Cout * 4.0,
+              [&] { launch_stats<T>(out, p->stats, c.B, H * W, g.Cout, ld_out, c.s); });
         curP = 1;
       }
     }
@@ -407,7 +437,7 @@ template <typename T> struct Fwd {
       if (c.film) { a.film = c.film; a.film_off = st->film_off; }
     }
     a.HW = p->levelH(level) * p->levelW(level); a.C = C; a.ld_in = ld_in; a.ld_out = ld_out; a.act = act; a.eps = 1e-5f;
-    launch_apply<T, T>(a, c.B, c.s);
+    timed(p, c.s, PC_APPLY, 0, 2.0 * c.B * a.HW * C * sizeof(T), [&] { launch_apply<T, T>(a, c.B, c.s); });
   }
 
   // DoubleConvolution (models/Unet_FiLmLayer.py:85-115); `first_done`: raw already holds conv1's output
@@ -431,11 +461,12 @@ template <typename T> struct Fwd {
     T* res = buf(p->a_res[level]); T* ff = buf(p->a_ff[level]);
     NormW& n1 = p->norms[name + ".ln"];
     NormW& n2 = p->norms[name + ".ff_self.0"];
-    launch_layernorm<T>(x, ld_x, ln, C, n1.g, n1.b, M, C, c.s);
+    const double ln_bytes = 2.0 * M * C * sizeof(T);
+    timed(p, c.s, PC_LN, 0, ln_bytes, [&] { launch_layernorm<T>(x, ld_x, ln, C, n1.g, n1.b, M, C, c.s); });
     gemm(name + ".attention.in_proj_weight", ln, C, level, qkv, 3 * C, EPI_BIAS);
-    launch_sdpa<T>(qkv, att, c.B, L, C, 4, c.s);
+    timed(p, c.s, PC_SDPA, 4.0 * M * L * C, 4.0 * M * C * sizeof(T), [&] { launch_sdpa<T>(qkv, att, c.B, L, C, 4, c.s); });
     gemm(name + ".attention.out_proj.weight", att, C, level, res, C, EPI_BIAS | EPI_RESID, x, ld_x);
-    launch_layernorm<T>(res, C, ln, C, n2.g, n2.b, M, C, c.s);
+    timed(p, c.s, PC_LN, 0, ln_bytes, [&] { launch_layernorm<T>(res, C, ln, C, n2.g, n2.b, M, C, c.s); });
     gemm(name + ".ff_self.1.weight", ln, C, level, ff, C, EPI_BIAS | EPI_GELU);
     gemm(name + ".ff_self.3.weight", ff, C, level, out, ld_out, EPI_BIAS | EPI_RESID, res, C);
   }
@@ -445,8 +476,11 @@ template <typename T> struct Fwd {
     const int rows = p->cfg.rows, dim = p->cfg.dim;
     T* cat3 = buf(p->cat[0]); T* cat2 = buf(p->cat[1]); T* cat1 = buf(p->cat[2]);
     // ---- inc ----
-    launch_conv_in<T>(c.x, p->w_in, buf(p->raw[0]), c.B, p->H0, p->W0, rows, dim, p->lh, p->lw, c.s);
-    launch_stats<T>(buf(p->raw[0]), p->stats, c.B, p->H0 * p->W0, 64, 64, c.s);
+    const double hw0 = (double)p->H0 * p->W0;
+    timed(p, c.s, PC_IO, 2.0 * 9 * 64 * hw0 * c.B, c.B * hw0 * 64 * sizeof(T),
+          [&] { launch_conv_in<T>(c.x, p->w_in, buf(p->raw[0]), c.B, p->H0, p->W0, rows, dim, p->lh, p->lw, c.s); });
+    timed(p, c.s, PC_STATS, 0, c.B * hw0 * 64 * sizeof(T),
+          [&] { launch_stats<T>(buf(p->raw[0]), p->stats, c.B, p->H0 * p->W0, 64, 64, c.s); });
     curP = 1;
     double_conv("inc", nullptr, 0, 64, 0, cat3 + 64, 128, nullptr, true);  // x1 -> skip slot of up3
     tap("x1", cat3 + 64, 128, 64, 0);
@@ -462,7 +496,8 @@ template <typename T> struct Fwd {
       const StageInfo& st = kStages[d.stage];
       const int l = d.level;
       T* a = buf(p->abuf[l]); T* b = buf(p->bbuf[l]);
-      launch_pool<T>(d.in, d.ld_in, a, st.cin, c.B, p->levelH(l), p->levelW(l), st.cin, c.s);
+      timed(p, c.s, PC_RESAMPLE, 0, 5.0 * c.B * p->levelH(l) * p->levelW(l) * st.cin * sizeof(T),
+            [&] { launch_pool<T>(d.in, d.ld_in, a, st.cin, c.B, p->levelH(l), p->levelW(l), st.cin, c.s); });
       double_conv(std::string(st.name) + ".doubleConv1", a, st.cin, st.cin, l, b, st.cin, nullptr);
       if (p->attention) {
         double_conv(std::string(st.name) + ".doubleConv2", b, st.cin, st.cout, l, a, st.cout, &st);
@@ -493,7 +528,9 @@ template <typename T> struct Fwd {
       const StageInfo& st = kStages[u.stage];
       const int l = u.level;
       T* a = buf(p->abuf[l]); T* b = buf(p->bbuf[l]);
-      launch_upsample<T>(u.low, u.c_low, u.catbuf, st.cin, c.B, p->levelH(l + 1), p->levelW(l + 1), u.c_low, c.s);
+      timed(p, c.s, PC_RESAMPLE, 0, 1.25 * c.B * p->levelH(l) * p->levelW(l) * u.c_low * sizeof(T), [&] {
+        launch_upsample<T>(u.low, u.c_low, u.catbuf, st.cin, c.B, p->levelH(l + 1), p->levelW(l + 1), u.c_low, c.s);
+      });
       double_conv(std::string(st.name) + ".doubleConv1", u.catbuf, st.cin, st.cin, l, a, st.cin, nullptr);
       if (p->attention) {
         // doubleConv2 reads a, writes a (safe: the input is dead once its first conv has run)
@@ -508,7 +545,9 @@ template <typename T> struct Fwd {
       tap(u.tapname, b, st.cout, st.cout, l);
     }
     // ---- outc + unpad ----
-    launch_outc<T>(buf(p->bbuf[0]), 64, p->w_outc, p->b_outc, c.out, c.B, p->H0, p->W0, 64, rows, dim, p->lh, p->lw, c.s);
+    timed(p, c.s, PC_IO, 2.0 * 64 * rows * dim * c.B, c.B * hw0 * 64 * sizeof(T), [&] {
+      launch_outc<T>(buf(p->bbuf[0]), 64, p->w_outc, p->b_outc, c.out, c.B, p->H0, p->W0, 64, rows, dim, p->lh, p->lw, c.s);
+    });
   }
 };
 
@@ -546,7 +585,7 @@ void one_step(spdm_plan* p, int B, bool use_film, cudaStream_t s) {
   StepArgs a{};
   a.x = p->xt; a.eps = p->eps; a.x_out = p->xt; a.coef = p->coef; a.dyn = p->dyn; a.n = p->n_elems();
   a.inpaint_elems = p->cfg.inpaint_rows * p->cfg.dim; a.B = B;
-  launch_step(a, s);
+  timed(p, s, PC_STEP, 0, 4.0 * B * p->n_elems() * sizeof(float), [&] { launch_step(a, s); });
   launch_advance(&p->dyn->step, 1, s);
 }
 
@@ -615,6 +654,9 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
     p->eps = p->alloc<float>((size_t)p->Bcap * p->n_elems());
     p->dyn = p->alloc<StepDyn>(1);
     CUDA_OK(cudaMallocHost((void**)&p->dyn_host, sizeof(StepDyn)));
+    CUDA_OK(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
+    CUDA_OK(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
+    CUDA_OK(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
   } catch (...) {
     for (void* q : p->allocs) cudaFree(q);
     delete p;
@@ -635,6 +677,9 @@ extern "C" int spdm_plan_destroy(spdm_plan* p) {
   for (auto& kv : p->tc_cache) tc_gemm_destroy(kv.second);
   for (void* q : p->allocs) cudaFree(q);
   if (p->dyn_host) cudaFreeHost(p->dyn_host);
+  if (p->own_stream) cudaStreamDestroy(p->own_stream);
+  if (p->ev_in) cudaEventDestroy(p->ev_in);
+  if (p->ev_out) cudaEventDestroy(p->ev_out);
   delete p;
   return 0;
 }
@@ -815,7 +860,14 @@ extern "C" int spdm_sample(spdm_plan* p, const float* x_T, const float* noise, c
   check_ready(p);
   const bool use_film = p->G > 0;
   if (use_film) REQUIRE(p->have_cond, "no cached conditioning (call spdm_set_cond / spdm_encode_cond)");
-  cudaStream_t s = (cudaStream_t)stream;
+  cudaStream_t user = (cudaStream_t)stream;
+  cudaStream_t s = user;
+  const int gs = p->cfg.graph_steps;
+  if (gs > 0) {  // fork onto the plan's stream: capture is not allowed on the legacy default stream
+    s = p->own_stream;
+    CUDA_OK(cudaEventRecord(p->ev_in, user));
+    CUDA_OK(cudaStreamWaitEvent(s, p->ev_in, 0));
+  }
   ensure_temb_table(p, s);
   const size_t nb = (size_t)B * p->n_elems() * sizeof(float);
   // per-call dynamic parameters live in device memory so that the captured graphs are call-independent
@@ -826,7 +878,6 @@ extern "C" int spdm_sample(spdm_plan* p, const float* x_T, const float* noise, c
   *p->dyn_host = d;
   CUDA_OK(cudaMemcpyAsync(p->dyn, p->dyn_host, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
 
-  const int gs = p->cfg.graph_steps;
   const long long key = ((long long)B << 1) | (use_film ? 1 : 0);
   const int n_multi = gs > 0 ? p->K / gs : 0, n_single = gs > 0 ? p->K % gs : 0;
   if (gs > 0) {
@@ -869,6 +920,10 @@ extern "C" int spdm_sample(spdm_plan* p, const float* x_T, const float* noise, c
     p->launches += n_multi * g.n_multi + n_single * g.n_single;
   }
   CUDA_OK(cudaMemcpyAsync(out, p->xt, nb, cudaMemcpyDeviceToDevice, s));
+  if (s != user) {  // join back
+    CUDA_OK(cudaEventRecord(p->ev_out, s));
+    CUDA_OK(cudaStreamWaitEvent(user, p->ev_out, 0));
+  }
   check_async("sample");
   return 0;
   API_END
@@ -881,6 +936,47 @@ extern "C" int spdm_add_noise(spdm_plan* p, const float* x0, const float* noise,
   launch_add_noise(x0, noise, reinterpret_cast<const long long*>(t), sqrt_ab, sqrt_1mab, p->cfg.inpaint_rows > 0 ? inpaint : nullptr, out,
                    p->n_elems(), p->cfg.inpaint_rows * p->cfg.dim, B, (cudaStream_t)stream);
   check_async("add_noise");
+  return 0;
+  API_END
+}
+
+static_assert(PC_N == SPDM_PROFILE_CLASSES, "profile class count");
+
+extern "C" int spdm_profile_step(spdm_plan* p, int32_t B, int32_t reps, double* out, void* stream) {
+  API_BEGIN
+  REQUIRE(p && out && B > 0 && B <= p->cfg.batch_max && reps > 0, "bad argument");
+  check_ready(p);
+  const bool use_film = p->G > 0;
+  if (use_film) REQUIRE(p->have_cond, "no cached conditioning");
+  cudaStream_t s = (cudaStream_t)stream;
+  ensure_temb_table(p, s);
+  CUDA_OK(cudaStreamSynchronize(s));
+  StepDyn d{};
+  d.use_philox = 1;
+  *p->dyn_host = d;
+  CUDA_OK(cudaMemcpyAsync(p->dyn, p->dyn_host, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
+  one_step(p, B, use_film, s);  // warm-up (tensor maps, attributes)
+  for (int i = 0; i < SPDM_PROFILE_CLASSES * 4; ++i) out[i] = 0.0;
+  for (int r = 0; r < reps; ++r) {
+    CUDA_OK(cudaMemcpyAsync(p->dyn, p->dyn_host, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
+    p->prof_on = true;
+    p->prof.clear();
+    try { one_step(p, B, use_film, s); } catch (...) { p->prof_on = false; throw; }
+    p->prof_on = false;
+    CUDA_OK(cudaStreamSynchronize(s));
+    for (auto& rec : p->prof) {
+      float ms = 0.f;
+      CUDA_OK(cudaEventElapsedTime(&ms, rec.e0, rec.e1));
+      out[rec.cat * 4 + 0] += ms / reps;
+      out[rec.cat * 4 + 1] += 1.0 / reps;
+      out[rec.cat * 4 + 2] += rec.flops / reps;
+      out[rec.cat * 4 + 3] += rec.bytes / reps;
+      cudaEventDestroy(rec.e0);
+      cudaEventDestroy(rec.e1);
+    }
+    p->prof.clear();
+  }
+  check_async("profile_step");
   return 0;
   API_END
 }

@@ -154,11 +154,15 @@ class Diffusion_DDPM(_Base):
 
     def _bind_schedule(self, plan):
         sch = self.noise_scheduler
-        sch.set_timesteps(self.noise_steps)
         if not hasattr(sch, "coef_table"):
             raise TypeError("noise_scheduler must be a state_policy_diffusionmodel_b200.schedulers scheduler "
                             "(DDPMScheduler / DDIMScheduler)")
+        key = (id(sch), id(plan), int(self.noise_steps), sch.num_train_timesteps)
+        if getattr(self, "_sched_key", None) == key and plan.K == int(self.noise_steps):
+            return  # same scheduler object, same step count, same plan: the device tables are current
+        sch.set_timesteps(self.noise_steps)
         plan.set_schedule(sch.kind, sch.coef_table(), sch.timesteps)
+        self._sched_key = key
 
     # ------------------------------------------------------------------------------------------
     # training / validation hooks (ddpm:92-125)

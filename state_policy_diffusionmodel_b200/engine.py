@@ -202,6 +202,15 @@ class DenoisePlan:
         self._keep = [x0, noise, t, sa, sb, ip]
         return out
 
+    def profile_step(self, B, reps=3):
+        """Eager, CUDA-event-timed denoising step: {class: dict(ms, launches, flops, bytes)} averaged over `reps`."""
+        n = len(_lib.PROFILE_CLASSES)
+        buf = (ctypes.c_double * (n * 4))()
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_profile_step(self._h, int(B), int(reps), buf, _stream()))
+        return {name: dict(ms=buf[i * 4], launches=buf[i * 4 + 1], flops=buf[i * 4 + 2], bytes=buf[i * 4 + 3])
+                for i, name in enumerate(_lib.PROFILE_CLASSES)}
+
     # ------------------------------------------------------------------ introspection
     @property
     def launch_count(self):

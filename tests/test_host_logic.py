@@ -1,0 +1,176 @@
+"""CPU tests (no GPU): product-side host logic against the oracle, the module/state_dict contract, the C-ABI library
+(loads and exports every symbol of include/spdm.h), the drop-in aliases, and the multi-rank sharding path (gloo)."""
+import ctypes
+import os
+import re
+import sys
+
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import state_policy_diffusionmodel_b200 as spdm
+from oracle import fixtures
+from oracle.schedulers import (RefDDIMScheduler, RefDDPMScheduler, ref_cosine_beta_schedule, ref_linear_beta_schedule,
+                               ref_linear_beta_schedule_v2)
+from state_policy_diffusionmodel_b200 import _build, _lib, distributed
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_builds_and_exports_the_c_abi():
+    path = _build.build()
+    lib = ctypes.CDLL(path)
+    header = open(os.path.join(ROOT, "include", "spdm.h")).read()
+    declared = set(re.findall(r"\b(spdm_[a-z_]+)\s*\(", header))
+    assert declared, "no declarations parsed from include/spdm.h"
+    for name in declared:
+        assert hasattr(lib, name), "libspdm.so does not export %s" % name
+    assert declared == set(_lib.EXPORTED_SYMBOLS)
+    lib.spdm_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.spdm_version()
+
+
+def test_no_cpu_fallback():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        spdm.DenoisePlan(batch_max=1)
+    net = spdm.UNet_Film_noAttention(1, 1, 1000, global_cond_dim=1350)
+    with pytest.raises(RuntimeError):
+        net(torch.zeros(1, 1, 31, 5), torch.tensor([1]), None)
+    # the raw ABI also refuses without a device
+    lib = _lib.load()
+    cfg = _lib.SpdmConfig(variant=0, precision=0, batch_max=1, rows=31, dim=5, obs_horizon=10, cond_dim=135, inpaint_rows=1,
+                          time_dim=256, device=0, graph_steps=0, flags=0)
+    h = ctypes.c_void_p()
+    assert lib.spdm_plan_create(ctypes.byref(h), ctypes.byref(cfg)) < 0
+    assert b"CUDA" in lib.spdm_last_error()
+
+
+@pytest.mark.parametrize("attention", [True, False])
+def test_state_dict_contract(attention):
+    """Key names and shapes of SURVEY A.2 (pinned against the real reference modules by oracle/make_golden.py)."""
+    cls = spdm.UNet_Film if attention else spdm.UNet_Film_noAttention
+    net = cls(in_channels=1, out_channels=1, noise_steps=1000, global_cond_dim=1350, time_dim=256)
+    want = fixtures.make_unet_weights(attention=attention)
+    got = net.state_dict()
+    assert set(got) == set(want)
+    for k in want:
+        assert tuple(got[k].shape) == tuple(want[k].shape), k
+    net.load_state_dict(want, strict=True)
+    assert sum(p.numel() for p in net.parameters()) == (24823297 if attention else 23782145)
+    nocond = cls(in_channels=1, out_channels=1, noise_steps=1000, global_cond_dim=None)
+    assert not any("cond_encoder" in k for k in nocond.state_dict())
+
+
+def test_wrapper_surface():
+    m = spdm.Diffusion_DDPM(noise_steps=1000, obs_horizon=10, pred_horizon=30, observation_dim=135, prediction_dim=5,
+                            model="UNet_Film", inpaint_horizon=1, noise_scheduler="linear")  # train.py:88 kwarg accepted
+    for attr in ("noise_scheduler", "noise_steps", "obs_horizon", "pred_horizon", "inpaint_horizon", "prediction_dim", "date",
+                 "device", "hparams", "noise_estimator", "vision_encoder", "sample", "validate", "process_single_batch",
+                 "prepare_observation_batch", "prepare_obs_cond_vectors", "prepare_inpaint_vectors", "add_constraints",
+                 "training_step", "validation_step", "configure_optimizers"):
+        assert hasattr(m, attr), attr
+    assert sum(p.numel() for p in m.parameters()) == 26013617
+    keys = set(m.state_dict())
+    assert "noise_estimator.inc.first.weight" in keys and "vision_encoder.7.weight" in keys
+    m.vision_encoder.load_state_dict(fixtures.make_encoder_weights(), strict=True)
+    d = spdm.Diffusion_DDIM(noise_steps=1000, obs_horizon=10, pred_horizon=30, observation_dim=135, prediction_dim=5,
+                            model="UNet_FilmnoAttention", inpaint_horizon=1)
+    d.use_ddim(100)
+    assert d.noise_steps == 100 and isinstance(d.noise_scheduler, spdm.DDIMScheduler)
+    batch = fixtures.make_batch(2)
+    obs = d.prepare_observation_batch({k: torch.cat([v, v], 1) for k, v in batch.items()})
+    assert obs["image"].shape[1] == 10
+    assert tuple(d.prepare_inpaint_vectors(obs).shape) == (2, 1, 5)
+    x = torch.zeros(2, 1, 31, 5)
+    d.add_constraints(x, torch.ones(2, 1, 1, 5))
+    assert float(x[:, :, 0].sum()) == 10 and float(x[:, :, 1:].abs().sum()) == 0
+
+
+@pytest.mark.parametrize("T,n", [(1000, 1000), (1000, 50), (100, 100), (50, 50), (20, 20)])
+def test_scheduler_coefficients_match_oracle(T, n):
+    kw = dict(num_train_timesteps=T, beta_schedule="linear", clip_sample=False, prediction_type="epsilon")
+    for Ref, Mine in ((RefDDPMScheduler, spdm.DDPMScheduler), (RefDDIMScheduler, spdm.DDIMScheduler)):
+        ref, mine = Ref(**kw), Mine(**kw)
+        ref.set_timesteps(n)
+        mine.set_timesteps(n)
+        assert torch.equal(ref.timesteps, mine.timesteps)
+        assert torch.equal(ref.alphas_cumprod, mine.alphas_cumprod)
+        table = mine.coef_table()
+        assert table.shape == (n, 8) and table.dtype == torch.float32
+        for i in (0, n // 2, n - 1):
+            c = ref.coefficients(int(ref.timesteps[i]))
+            row = table[i]
+            assert float(row[0]) == float(c["sqrt_beta_prod"]) and float(row[1]) == float(c["sqrt_alpha_prod"])
+            if Ref is RefDDPMScheduler:
+                assert float(row[2]) == float(c["c0"]) and float(row[3]) == float(c["cx"]) and float(row[5]) == float(c["sigma"])
+                assert float(row[4]) == 0.0
+            else:
+                assert float(row[2]) == float(c["sqrt_alpha_prev"]) and float(row[4]) == float(c["dir_coef"])
+                assert float(row[3]) == 0.0 and float(row[5]) == 0.0
+    with pytest.raises(ValueError):
+        spdm.DDPMScheduler(**kw).set_timesteps(T + 1)
+
+
+def test_schedule_functions_match_reference_restatement():
+    class Dev:
+        device = torch.device("cpu")
+    for steps in (50, 100, 1000):
+        assert torch.equal(spdm.linear_beta_schedule(Dev(), steps), ref_linear_beta_schedule(steps))
+        assert torch.equal(spdm.linear_beta_schedule_v2(Dev(), steps), ref_linear_beta_schedule_v2(steps))
+        assert torch.equal(spdm.cosine_beta_schedule(Dev(), steps), ref_cosine_beta_schedule(steps))
+    # known-answer values, SURVEY A.4
+    b = spdm.linear_beta_schedule(None, 100)
+    assert abs(float(b[0]) - 1.0000000475e-03) < 1e-10 and abs(float(b[99]) - 0.2) < 1e-7
+
+
+def test_reference_aliases():
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k.split(".")[0] in ("models", "utils", "diffusers")}
+    try:
+        spdm.install_reference_aliases()
+        ns = {}
+        exec("from models.diffusion_ddpm import *\nfrom models.diffusion_ddim import *\n"
+             "from diffusers.schedulers.scheduling_ddim import DDIMScheduler as S2\nfrom utils.schedulers import *", ns)
+        for name in ("Diffusion_DDPM", "Diffusion_DDIM", "DDPMScheduler", "DDIMScheduler", "UNet_Film", "UNet_Film_noAttention",
+                     "torch", "nn", "np", "linear_beta_schedule", "cosine_beta_schedule"):
+            assert name in ns, name
+        assert ns["S2"] is spdm.DDIMScheduler
+    finally:
+        for k in list(sys.modules):
+            if k.split(".")[0] in ("models", "utils", "diffusers") and k not in saved:
+                del sys.modules[k]
+
+
+def test_shard_range():
+    for total in (0, 1, 7, 256, 4096):
+        for world in (1, 2, 3, 8):
+            spans = [distributed.shard_range(total, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def _gloo_worker(rank, world, port, total):
+    import torch.distributed as dist
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(0)
+    batch = {"position": torch.randn((total, 10, 2), generator=g), "action": torch.randn((total, 10, 3), generator=g)}
+    x_T = torch.randn((total, 1, 31, 5), generator=g)
+    noise = torch.randn((4, total, 1, 31, 5), generator=g)
+
+    def fake_sample(local, x_T=None, noise=None):  # a row-wise function of this rank's rows only
+        return x_T * 2 + local["position"][:, -1, :1].reshape(-1, 1, 1, 1) + noise.sum(0)
+
+    out = distributed.sharded_sample(fake_sample, batch, x_T=x_T, noise=noise)
+    want = fake_sample(batch, x_T=x_T, noise=noise)
+    assert out.shape == want.shape and torch.allclose(out, want)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("total", [8, 5, 1])
+def test_sharded_sampling_world2_gloo(total):
+    port = 29500 + (os.getpid() + total) % 2000
+    mp.spawn(_gloo_worker, args=(2, port, total), nprocs=2, join=True)
