@@ -111,6 +111,12 @@ enum { SPDM_PC_CONV3 = 0, SPDM_PC_GEMM1, SPDM_PC_APPLY, SPDM_PC_STATS, SPDM_PC_R
        SPDM_PC_SDPA, SPDM_PC_IO, SPDM_PC_STEP };
 int spdm_profile_step(spdm_plan* plan, int32_t B, int32_t reps, double* out, void* stream);
 
+/* Microbenchmark of one tcgen05 implicit-GEMM launch (3x3 conv when taps == 9, Linear when taps == 1) on
+ * zero-filled scratch buffers: average milliseconds over `iters` launches.  dbg = 0 runs the real kernel;
+ * other values switch parts of it off (perf experiments, tests/perf_conv.py). */
+int spdm_microbench_conv(int32_t H, int32_t W, int32_t B, int32_t Cin, int32_t Cout, int32_t taps,
+                         int32_t dbg, int32_t iters, float* ms_out);
+
 /* Introspection used by bench.py / tests. */
 int64_t spdm_plan_launch_count(spdm_plan* plan);     /* kernels enqueued so far by this plan  */
 int64_t spdm_plan_workspace_bytes(spdm_plan* plan);

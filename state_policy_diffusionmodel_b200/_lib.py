@@ -41,6 +41,7 @@ _PROTOTYPES = {
     "spdm_sample": (_c.c_int, [_P, _P, _P, _P, _P, _P, _c.c_uint64, _c.c_int32, _P]),
     "spdm_add_noise": (_c.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _c.c_int32, _P]),
     "spdm_profile_step": (_c.c_int, [_P, _c.c_int32, _c.c_int32, _c.POINTER(_c.c_double), _P]),
+    "spdm_microbench_conv": (_c.c_int, [_c.c_int32] * 8 + [_c.POINTER(_c.c_float)]),
     "spdm_plan_launch_count": (_c.c_int64, [_P]),
     "spdm_plan_workspace_bytes": (_c.c_int64, [_P]),
     "spdm_last_error": (_c.c_char_p, []),

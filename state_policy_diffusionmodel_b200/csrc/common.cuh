@@ -17,7 +17,7 @@ typedef __nv_bfloat16 bf16;
 
 enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 enum : int { TEMB_NONE = 0, TEMB_ROW0 = 1, TEMB_PER_SAMPLE = 2, TEMB_STEP = 3 };
-enum : int { EPI_STATS = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RESID = 8 };
+enum : int { EPI_STATS = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RESID = 8, EPI_VT = 16 };
 
 #define SPDM_FILM_WIDTH 1792 /* sum over the 6 stages of 2*C_out */
 #define SPDM_TEMB_WIDTH 896  /* sum over the 6 stages of C_out   */
@@ -151,9 +151,21 @@ TcGemm* tc_gemm_create(const bf16* in, int ld_in, const bf16* w_packed, int Cin,
                        int Bcap);
 void tc_gemm_destroy(TcGemm* g);
 // out bf16 [M, Cout] ld_out; stats partials [B][P][2] with EPI_STATS.  B must be a multiple of tc_batch_multiple.
-void tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const float* bias, const bf16* resid,
-                    int ld_res, int flags, int B, cudaStream_t s);
-int tc_gemm_partials(const TcGemm* g);  // P written per sample by EPI_STATS
+// returns P, the number of GroupNorm partial slots per sample that EPI_STATS wrote
+// EPI_VT (in_proj of an attention block, Cout = 3C): the V third of the output is written transposed to
+// vt[row / vt_lk][C][row % vt_lk] for sdpa_tc instead of to `out`.
+int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const float* bias, const bf16* resid,
+                   int ld_res, int flags, int B, cudaStream_t s, bf16* vt = nullptr, int vt_lk = 0);
 const char* tc_last_error();
+void tc_set_debug(int v);  // microbenchmark switches, see TcParams::dbg
 int tc_batch_multiple(int H, int W);  // granularity of B required by the 128-row M tiling at geometry HxW
 long long tc_launch_count();
+
+// tcgen05 attention core (sdpa_tc.cu) ------------------------------------------------------------------
+struct SdpaTc;
+bool sdpa_tc_supported(int L, int C, int heads);
+int sdpa_tc_keys_per_tile(int L);
+// qkv: bf16 [Mcap][3C] (Q | K | unused); vt: bf16 [Mcap / LK][C][LK] written by the in_proj GEMM (EPI_VT)
+SdpaTc* sdpa_tc_create(const bf16* qkv, const bf16* vt, int C, int L, int heads, long long Mcap);
+void sdpa_tc_destroy(SdpaTc* g);
+void sdpa_tc_launch(const SdpaTc* g, bf16* out, long long M, cudaStream_t s);  // out bf16 [M][C], M % 128 == 0

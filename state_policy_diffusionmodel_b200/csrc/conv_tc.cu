@@ -11,13 +11,17 @@
 //   B tile  = 2-D TMA box {64 k, BLOCK_N} of the [Cout][taps*Cin] weight matrix (K-major).
 //   MMA     = tcgen05.mma.cta_group::1.kind::f16, M=128, N=BLOCK_N, K=16, issued by one thread;
 //             accumulator = BLOCK_N TMEM columns.
+//             accumulators = 2 x BLOCK_N TMEM columns (double-buffered).
 //   roles   = warp 0: TMA producer, warp 1: MMA issuer, warps 2..5: epilogue (tcgen05.ld -> bias /
 //             GELU / residual / GroupNorm partial sums -> bf16 global stores).
+//   The kernel is persistent: one CTA per SM walks the (m_tile, n_tile) list; the smem ring keeps
+//   streaming across tile boundaries and the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <stdio.h>
 #include <string.h>
 
 #include "common.cuh"
+#include "tc_ptx.cuh"
 
 static long long g_tc_launches = 0;
 long long tc_launch_count() { return g_tc_launches; }
@@ -37,141 +41,52 @@ struct TcParams {
   int Cin, Cout;
   int taps;               // 1 or 9
   int kb_per_tap;         // Cin / 64
-  int n_tiles;
+  int n_tiles, m_tiles, total_tiles;
   int P;                  // stats partial slots per sample
   int ld_out, ld_res;
   int flags;
+  int dbg;                // microbenchmark switches (tc_set_debug): 1 = no B loads, 2 = no A loads, 4 = no epilogue stores, 8 = centre tap only
   bf16* out;
   float* stats;
   const float* bias;
   const bf16* resid;
+  bf16* vt;               // EPI_VT: columns >= vt_c0 go, transposed, to vt[row / vt_lk][col - vt_c0][row % vt_lk]
+  int vt_c0, vt_C, vt_lk;
 };
 
 // ---------------------------------------------------------------------------------------------
-// PTX wrappers
+// The kernel.  grid = min(total_tiles, #SM); dynamic smem = STAGES*(A+B) + 1024 (alignment slack).
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+struct TileCoord { int m_tile, n_tile, b0, h0, n0; };
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug must trap (error surfaced to the host), never hang the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
-  while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) { printf("spdm conv_tc: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x); __trap(); }
-  }
-}
-__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
-  asm volatile(
-      "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)map) : "memory");
+__device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int block_n) {
+  TileCoord t;
+  t.n_tile = tile % p.n_tiles;  // n fastest: CTAs running side by side share the same A tile in L2
+  t.m_tile = tile / p.n_tiles;
+  const int tiles_per_sample = p.H / p.Hb;  // > 1 only when Bt == 1
+  if (tiles_per_sample > 1) { t.b0 = t.m_tile / tiles_per_sample; t.h0 = (t.m_tile - t.b0 * tiles_per_sample) * p.Hb; }
+  else { t.b0 = t.m_tile * p.Bt; t.h0 = 0; }
+  t.n0 = t.n_tile * block_n;
+  return t;
 }
 
-template <int COLS> __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "n"(COLS) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-template <int COLS> __device__ __forceinline__ void tmem_dealloc(uint32_t addr) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "n"(COLS) : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T   (both operands K-major)
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-// 32 lanes x 32 columns of fp32: thread i of the warp gets row (lane base + i), 32 consecutive columns
-__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t v[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-        "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]),
-        "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]),
-        "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// K-major, 128B-swizzled operand tile: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart.
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);   // start address        bits [0,14)
-  d |= (uint64_t)0 << 16;                        // leading byte offset  bits [16,30)  (unused: one atom along K)
-  d |= (uint64_t)(1024 >> 4) << 32;              // stride byte offset   bits [32,46)
-  d |= (uint64_t)1 << 46;                        // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                        // SWIZZLE_128B
-  return d;
-}
-// kind::f16 instruction descriptor: D=f32, A=B=bf16, both K-major, M=128, N=n
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
-}
-
-// ---------------------------------------------------------------------------------------------
-// The kernel.  grid = (m_tiles, n_tiles); dynamic smem = STAGES*(A+B) + 1024 (alignment slack).
-// ---------------------------------------------------------------------------------------------
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int TMEM_COLS = 2 * BLOCK_N;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-
-  // ---- tile coordinates ----
-  const int m_tile = blockIdx.x, n_tile = blockIdx.y;
-  const int tiles_per_sample = p.H / p.Hb;  // > 1 only when Bt == 1
-  int b0, h0;
-  if (tiles_per_sample > 1) { b0 = m_tile / tiles_per_sample; h0 = (m_tile - b0 * tiles_per_sample) * p.Hb; }
-  else { b0 = m_tile * p.Bt; h0 = 0; }
-  const int n0 = n_tile * BLOCK_N;
 
   // ---- K iteration space: valid taps x 64-channel blocks ----
   const bool skip_dx = (p.taps == 9 && p.W == 1), skip_dy = (p.taps == 9 && p.H == 1);
@@ -184,10 +99,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tma_prefetch_desc(&map_b);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
-    mbar_init(&tmem_full_bar, 1);
+    mbar_init(&tmem_full_bar[0], 1); mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 4); mbar_init(&tmem_empty_bar[1], 4);  // one arrival per epilogue warp
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<BLOCK_N>(&tmem_base_smem);
+  if (warp == 2) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -195,106 +111,151 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0) {
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
-        const int tap_i = it / p.kb_per_tap, kb = it - tap_i * p.kb_per_tap;
-        int dy = 0, dx = 0, tap = 0;
-        if (p.taps == 9) {
-          const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
-          dy = skip_dy ? 0 : ty - 1;
-          dx = skip_dx ? 0 : tx - 1;
-          tap = (dy + 1) * 3 + (dx + 1);
+    if (lane == 0 && !(p.dbg & 16)) {
+      uint32_t kit = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        const TileCoord t = decode_tile(p, tile, BLOCK_N);
+        for (int it = 0; it < k_iters; ++it, ++kit) {
+          const int s = kit % STAGES;
+          const uint32_t ph = (kit / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          const int tap_i = it / p.kb_per_tap, kb = it - tap_i * p.kb_per_tap;
+          int dy = 0, dx = 0, tap = 0;
+          if (p.taps == 9) {
+            const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
+            dy = skip_dy ? 0 : ty - 1;
+            dx = skip_dx ? 0 : tx - 1;
+            tap = (dy + 1) * 3 + (dx + 1);
+          }
+          if (p.dbg & 8) { dx = 0; dy = 0; }
+          mbar_expect_tx(&full_bar[s], ((p.dbg & 2) ? 0 : A_STAGE_BYTES) + ((p.dbg & 1) ? 0 : B_STAGE_BYTES));
+          if (!(p.dbg & 2)) tma_load_4d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t.h0 + dy, t.b0);
+          if (!(p.dbg & 1)) tma_load_2d(smem_b + s * B_STAGE_BYTES, &map_b, &full_bar[s], tap * p.Cin + kb * BLOCK_K, t.n0);
         }
-        mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
-        tma_load_4d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, h0 + dy, b0);
-        tma_load_2d(smem_b + s * B_STAGE_BYTES, &map_b, &full_bar[s], tap * p.Cin + kb * BLOCK_K, n0);
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(BLOCK_N);
-      for (int it = 0; it < k_iters; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (uint32_t)(it / STAGES) & 1u;
-        mbar_wait(&full_bar[s], ph);
+      uint32_t kit = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[acc], aph ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
-        const uint64_t da = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
-        const uint64_t db = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int it = 0; it < k_iters; ++it, ++kit) {
+          const int s = kit % STAGES;
+          const uint32_t ph = (kit / STAGES) & 1u;
+          if (!(p.dbg & 16)) mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-          // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          }
+          if (!(p.dbg & 16)) umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
       }
-      umma_commit(&tmem_full_bar);   // accumulator complete
     }
   } else {
     // ================= epilogue: warps 2..5 -> TMEM lane quarters (warp % 4) =================
     const int q = warp & 3;
     const int r_t = q * 32 + lane;                 // tile row == TMEM lane
     const int rps = p.Hb * p.W;                    // rows per sample inside the tile
-    const long long row0 = ((long long)b0 * p.H + h0) * p.W;  // tile rows are contiguous in the [M, C] map
-    const long long row = row0 + r_t;
-    mbar_wait(&tmem_full_bar, 0);
-    tc_fence_after();
-    float rs = 0.f, rq = 0.f;
-    bf16* orow = p.out + row * p.ld_out + n0;
-    const bf16* rrow = (p.flags & EPI_RESID) ? p.resid + row * p.ld_res + n0 : nullptr;
+    const int tiles_per_sample = p.H / p.Hb;
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      const TileCoord t = decode_tile(p, tile, BLOCK_N);
+      const int acc = lt & 1;
+      const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+      const long long row0 = ((long long)t.b0 * p.H + t.h0) * p.W;  // tile rows are contiguous in the [M, C] map
+      const long long row = row0 + r_t;
+      bf16* orow = p.out + row * p.ld_out + t.n0;
+      const bf16* rrow = (p.flags & EPI_RESID) ? p.resid + row * p.ld_res + t.n0 : nullptr;
+      float rs = 0.f, rq = 0.f;
+      mbar_wait(&tmem_full_bar[acc], aph);
+      tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      if (p.dbg & 32) {  // microbenchmark: hand the accumulator straight back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        continue;
+      }
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
-      tmem_ld_wait();
-      float f[32];
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + (uint32_t)c, v);
+        tmem_ld_wait();
+        if (c + 32 == BLOCK_N) {  // accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        float f[32];
 #pragma unroll
-      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-      if (p.flags & EPI_BIAS) {
+        for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
+        if (p.flags & EPI_BIAS) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] += __ldg(p.bias + n0 + c + i);
-      }
-      if (p.flags & EPI_GELU) {
+          for (int i = 0; i < 32; i += 4) {
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + t.n0 + c + i));
+            f[i] += b4.x; f[i + 1] += b4.y; f[i + 2] += b4.z; f[i + 3] += b4.w;
+          }
+        }
+        if (p.flags & EPI_GELU) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) f[i] = gelu_exact(f[i]);
-      }
-      if (rrow) {
+          for (int i = 0; i < 32; ++i) f[i] = gelu_exact(f[i]);
+        }
+        if (rrow) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8) {
-          float t[8];
-          load8(rrow + c + i, t);
+          for (int i = 0; i < 32; i += 8) {
+            float t8[8];
+            load8(rrow + c + i, t8);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) f[i + e] += t[e];
+            for (int e = 0; e < 8; ++e) f[i + e] += t8[e];
+          }
+        }
+        if (p.flags & EPI_STATS) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { rs += f[i]; rq = fmaf(f[i], f[i], rq); }
+        }
+        if ((p.flags & EPI_VT) && t.n0 + c >= p.vt_c0) {
+          // V^T for the tcgen05 attention core: consecutive lanes are consecutive tokens -> 64-byte segments per column
+          const long long vtile = row / p.vt_lk;
+          const int pos = (int)(row - vtile * p.vt_lk);
+          bf16* dst = p.vt + ((size_t)vtile * p.vt_C + (t.n0 + c - p.vt_c0)) * p.vt_lk + pos;
+#pragma unroll
+          for (int i = 0; i < 32; ++i) dst[(size_t)i * p.vt_lk] = __float2bfloat16_rn(f[i]);
+        } else if (!(p.dbg & 4)) {
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) store8(orow + c + i, f + i);
         }
       }
       if (p.flags & EPI_STATS) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) { rs += f[i]; rq = fmaf(f[i], f[i], rq); }
-      }
-#pragma unroll
-      for (int i = 0; i < 32; i += 8) store8(orow + c + i, f + i);
-    }
-    if (p.flags & EPI_STATS) {
-      // reduce over the lanes that belong to the same sample, one deterministic slot per writer
-      const int span = rps >= 32 ? 32 : rps;  // rps in {128, 64, 32, 16, 8, 4, ...}: power of two
-      for (int o = span >> 1; o > 0; o >>= 1) { rs += __shfl_xor_sync(0xffffffffu, rs, o); rq += __shfl_xor_sync(0xffffffffu, rq, o); }
-      if ((lane & (span - 1)) == 0) {
-        const int b = b0 + r_t / rps;
-        int slot;
-        if (rps >= 32) {
-          const int warps_per_sample_tile = (rps >= 128 ? 128 : rps) / 32;
-          const int tile_in_sample = tiles_per_sample > 1 ? (m_tile % tiles_per_sample) : 0;
-          const int warp_in_sample = (r_t % rps) / 32;
-          slot = (tile_in_sample * warps_per_sample_tile + warp_in_sample) * p.n_tiles + n_tile;
-        } else {
-          slot = n_tile;
+        // reduce over the lanes that belong to the same sample, one deterministic slot per writer
+        const int span = rps >= 32 ? 32 : rps;  // rps in {128, 64, 32, 16, 8, 4, ...}: power of two
+        for (int o = span >> 1; o > 0; o >>= 1) { rs += __shfl_xor_sync(0xffffffffu, rs, o); rq += __shfl_xor_sync(0xffffffffu, rq, o); }
+        if ((lane & (span - 1)) == 0) {
+          const int b = t.b0 + r_t / rps;
+          int slot;
+          if (rps >= 32) {
+            const int warps_per_sample_tile = (rps >= 128 ? 128 : rps) / 32;
+            const int tile_in_sample = tiles_per_sample > 1 ? (t.m_tile % tiles_per_sample) : 0;
+            const int warp_in_sample = (r_t % rps) / 32;
+            slot = (tile_in_sample * warps_per_sample_tile + warp_in_sample) * p.n_tiles + t.n_tile;
+          } else {
+            slot = t.n_tile;
+          }
+          float* dst = p.stats + ((size_t)b * p.P + slot) * 2;
+          dst[0] = rs;
+          dst[1] = rq;
         }
-        float* dst = p.stats + ((size_t)b * p.P + slot) * 2;
-        dst[0] = rs;
-        dst[1] = rq;
       }
     }
     tc_fence_before();
@@ -302,7 +263,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<BLOCK_N>(tmem_base);
+    tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -323,16 +284,27 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
+int num_sms() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
 template <int BLOCK_N, int STAGES> constexpr int smem_bytes() { return STAGES * (A_STAGE_BYTES + BLOCK_N * BLOCK_K * 2) + 1024; }
 
 template <int BLOCK_N, int STAGES>
-void launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int m_tiles, cudaStream_t s) {
+void launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, cudaStream_t s) {
   static bool attr = false;
   if (!attr) {
     cudaFuncSetAttribute(conv_tc_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BLOCK_N, STAGES>());
     attr = true;
   }
-  dim3 grid(m_tiles, p.n_tiles);
+  const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
   conv_tc_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, smem_bytes<BLOCK_N, STAGES>(), s>>>(ma, mb, p);
   ++g_tc_launches;
 }
@@ -340,15 +312,24 @@ void launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p,
 }  // namespace
 
 struct TcGemm {
-  CUtensorMap map_a, map_b;
+  CUtensorMap map_a, map_b, map_b256;
   TcParams p;
-  int block_n;
+  int block_n;      // 64 or 128
+  bool has256;      // Cout % 256 == 0: a 256-wide N tile is available
   int Bcap;
 };
+
+static int g_tc_dbg = 0;
+void tc_set_debug(int v) { g_tc_dbg = v; }
 
 int tc_batch_multiple(int H, int W) {
   const int hw = H * W;
   return hw >= BLOCK_M ? 1 : BLOCK_M / hw;
+}
+
+static int partials_for(const TcParams& p, int n_tiles) {
+  const int rps = p.Hb * p.W;
+  return rps >= 32 ? (p.H / p.Hb) * ((rps >= 128 ? 128 : rps) / 32) * n_tiles : n_tiles;
 }
 
 TcGemm* tc_gemm_create(const bf16* in, int ld_in, const bf16* w_packed, int Cin, int Cout, int taps, int H, int W, int Bcap) {
@@ -369,12 +350,10 @@ TcGemm* tc_gemm_create(const bf16* in, int ld_in, const bf16* w_packed, int Cin,
   memset(g, 0, sizeof(*g));
   g->Bcap = Bcap;
   g->block_n = (Cout % 128 == 0) ? 128 : 64;
+  g->has256 = (Cout % 256 == 0);
   TcParams& p = g->p;
   p.H = H; p.W = W; p.Hb = Hb; p.Bt = Bt; p.Cin = Cin; p.Cout = Cout; p.taps = taps;
   p.kb_per_tap = Cin / BLOCK_K;
-  p.n_tiles = Cout / g->block_n;
-  const int rps = Hb * W;
-  p.P = rps >= 32 ? (H / Hb) * ((rps >= 128 ? 128 : rps) / 32) * p.n_tiles : p.n_tiles;
 
   {  // A: 4-D (C, W, H, B) view of the channels-last activation
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bcap};
@@ -385,27 +364,39 @@ TcGemm* tc_gemm_create(const bf16* in, int ld_in, const bf16* w_packed, int Cin,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(A) failed: %d", (int)r); delete g; return nullptr; }
   }
-  {  // B: 2-D (K, Cout) weights
+  for (int pass = 0; pass < 2; ++pass) {  // B: 2-D (K, Cout) weights, one map per N-tile width
+    if (pass == 1 && !g->has256) break;
+    const int bn = pass == 0 ? g->block_n : 256;
     const cuuint64_t Ktot = (cuuint64_t)taps * Cin;
     cuuint64_t dims[2] = {Ktot, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {Ktot * 2};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)g->block_n};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)bn};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(&g->map_b, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_packed, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r = enc(pass == 0 ? &g->map_b : &g->map_b256, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_packed, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(B) failed: %d", (int)r); delete g; return nullptr; }
   }
   return g;
 }
 
 void tc_gemm_destroy(TcGemm* g) { delete g; }
-int tc_gemm_partials(const TcGemm* g) { return g->p.P; }
 
-void tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const float* bias, const bf16* resid, int ld_res, int flags,
-                    int B, cudaStream_t s) {
+int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const float* bias, const bf16* resid, int ld_res, int flags,
+                   int B, cudaStream_t s, bf16* vt, int vt_lk) {
   TcParams p = g->p;
+  p.dbg = g_tc_dbg;
+  p.vt = vt; p.vt_lk = vt_lk; p.vt_C = p.Cout / 3; p.vt_c0 = 2 * (p.Cout / 3);
   p.out = out; p.ld_out = ld_out; p.stats = stats; p.bias = bias; p.resid = resid; p.ld_res = ld_res; p.flags = flags;
-  const int m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
-  if (g->block_n == 128) launch_cfg<128, 6>(g->map_a, g->map_b, p, m_tiles, s);
-  else launch_cfg<64, 8>(g->map_a, g->map_b, p, m_tiles, s);
+  p.m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
+  // a 256-wide N tile halves the A traffic per FLOP; use it once there are enough tiles to fill the machine
+  const bool use256 = g->has256 && (long long)p.m_tiles * (p.Cout / 256) >= num_sms();
+  const int bn = use256 ? 256 : g->block_n;
+  p.n_tiles = p.Cout / bn;
+  p.total_tiles = p.m_tiles * p.n_tiles;
+  p.P = partials_for(p, p.n_tiles);
+  if (bn == 256) launch_cfg<256, 4>(g->map_a, g->map_b256, p, s);
+  else if (bn == 128) launch_cfg<128, 6>(g->map_a, g->map_b, p, s);
+  else launch_cfg<64, 8>(g->map_a, g->map_b, p, s);
+  return p.P;
 }

@@ -97,7 +97,8 @@ struct spdm_plan {
 
   // workspace (T = float or bf16, chosen by precision)
   void *raw[4] = {}, *hbuf[4] = {}, *abuf[4] = {}, *bbuf[4] = {}, *cat[3] = {};
-  void *a_ln[4] = {}, *a_qkv[4] = {}, *a_att[4] = {}, *a_res[4] = {}, *a_ff[4] = {};
+  void *a_ln[4] = {}, *a_qkv[4] = {}, *a_att[4] = {}, *a_res[4] = {}, *a_ff[4] = {}, *a_vt[4] = {};
+  std::map<std::string, SdpaTc*> sdpa_cache;
   float* stats = nullptr;   // [Bcap][SPDM_MAX_PARTIALS][2]
   float* film = nullptr;    // [Bcap][1792]
   float* cond = nullptr;    // [Bcap][G]
@@ -338,6 +339,7 @@ template <typename T> void alloc_workspace(spdm_plan* p) {
       p->a_att[l] = p->alloc<T>(Bc * hw * catt[l]);
       p->a_res[l] = p->alloc<T>(Bc * hw * catt[l]);
       p->a_ff[l] = p->alloc<T>(Bc * hw * catt[l]);
+      if (sizeof(T) == 2) p->a_vt[l] = p->alloc<T>(Bc * hw * catt[l]);
     }
   }
 }
@@ -372,6 +374,8 @@ template <typename T> struct Fwd {
   FwdCtx c;
   int curP = 1;
   int Bpad;
+  bf16* vt = nullptr;  // set around the in_proj GEMM of an attention block that feeds sdpa_tc (EPI_VT)
+  int vt_lk = 0;
 
   Fwd(spdm_plan* p_, const FwdCtx& c_) : p(p_), c(c_) { Bpad = ((c.B + p->bm - 1) / p->bm) * p->bm; }
 
@@ -399,17 +403,18 @@ template <typename T> struct Fwd {
       if (!tc) {
         tc = tc_gemm_create(reinterpret_cast<const bf16*>(in), ld_in, g.w16, g.Cin, g.Cout, g.taps, H, W, p->Bcap);
         REQUIRE(tc != nullptr, "%s: %s", wname.c_str(), tc_last_error());
-        REQUIRE(!(flags & EPI_STATS) || tc_gemm_partials(tc) <= SPDM_MAX_PARTIALS, "%s: too many GroupNorm partials", wname.c_str());
       }
       // algorithmic work: taps that fall inside the image only, real batch rows only
       const double flops = g.taps == 9 ? 2.0 * g.Cin * g.Cout * (3.0 * H - 2) * (3.0 * W - 2) * c.B
                                        : 2.0 * g.Cin * g.Cout * (double)H * W * c.B;
       const double bytes = ((double)c.B * H * W * (g.Cin + g.Cout) + (double)g.taps * g.Cin * g.Cout) * 2.0;
+      int P = 1;
       timed(p, c.s, g.taps == 9 ? PC_CONV3 : PC_GEMM1, flops, bytes, [&] {
-        tc_gemm_launch(tc, reinterpret_cast<bf16*>(out), ld_out, p->stats, (flags & EPI_BIAS) ? g.bias : nullptr,
-                       reinterpret_cast<const bf16*>(resid), ld_res, flags, Bpad, c.s);
+        P = tc_gemm_launch(tc, reinterpret_cast<bf16*>(out), ld_out, p->stats, (flags & EPI_BIAS) ? g.bias : nullptr,
+                           reinterpret_cast<const bf16*>(resid), ld_res, flags, Bpad, c.s, vt, vt_lk);
       });
-      curP = tc_gemm_partials(tc);
+      REQUIRE(!(flags & EPI_STATS) || P <= SPDM_MAX_PARTIALS, "%s: too many GroupNorm partials (%d)", wname.c_str(), P);
+      curP = P;
     } else {
       GemmSimtArgs a{};
       a.in = in; a.w = g.w32; a.bias = (flags & EPI_BIAS) ? g.bias : nullptr; a.resid = (flags & EPI_RESID) ? resid : nullptr;
@@ -463,8 +468,29 @@ template <typename T> struct Fwd {
     NormW& n2 = p->norms[name + ".ff_self.0"];
     const double ln_bytes = 2.0 * M * C * sizeof(T);
     timed(p, c.s, PC_LN, 0, ln_bytes, [&] { launch_layernorm<T>(x, ld_x, ln, C, n1.g, n1.b, M, C, c.s); });
-    gemm(name + ".attention.in_proj_weight", ln, C, level, qkv, 3 * C, EPI_BIAS);
-    timed(p, c.s, PC_SDPA, 4.0 * M * L * C, 4.0 * M * C * sizeof(T), [&] { launch_sdpa<T>(qkv, att, c.B, L, C, 4, c.s); });
+    bool tc_sdpa = false;
+    if constexpr (sizeof(T) == 2) tc_sdpa = sdpa_tc_supported(L, C, 4);
+    if (tc_sdpa) {
+      if constexpr (sizeof(T) == 2) {
+        SdpaTc*& sd = p->sdpa_cache[name];
+        if (!sd) {
+          sd = sdpa_tc_create(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(p->a_vt[level]), C, L, 4,
+                              (long long)p->Bcap * L);
+          REQUIRE(sd != nullptr, "%s: sdpa_tc_create failed", name.c_str());
+        }
+        vt = reinterpret_cast<bf16*>(p->a_vt[level]);
+        vt_lk = sdpa_tc_keys_per_tile(L);
+        gemm(name + ".attention.in_proj_weight", ln, C, level, qkv, 3 * C, EPI_BIAS | EPI_VT);
+        vt = nullptr;
+        vt_lk = 0;
+        const long long Mpad = (long long)Bpad * L;
+        timed(p, c.s, PC_SDPA, 4.0 * M * L * C, 4.0 * M * C * sizeof(T),
+              [&] { sdpa_tc_launch(sd, reinterpret_cast<bf16*>(att), Mpad, c.s); });
+      }
+    } else {
+      gemm(name + ".attention.in_proj_weight", ln, C, level, qkv, 3 * C, EPI_BIAS);
+      timed(p, c.s, PC_SDPA, 4.0 * M * L * C, 4.0 * M * C * sizeof(T), [&] { launch_sdpa<T>(qkv, att, c.B, L, C, 4, c.s); });
+    }
     gemm(name + ".attention.out_proj.weight", att, C, level, res, C, EPI_BIAS | EPI_RESID, x, ld_x);
     timed(p, c.s, PC_LN, 0, ln_bytes, [&] { launch_layernorm<T>(res, C, ln, C, n2.g, n2.b, M, C, c.s); });
     gemm(name + ".ff_self.1.weight", ln, C, level, ff, C, EPI_BIAS | EPI_GELU);
@@ -675,6 +701,7 @@ extern "C" int spdm_plan_destroy(spdm_plan* p) {
     if (kv.second.single) cudaGraphExecDestroy(kv.second.single);
   }
   for (auto& kv : p->tc_cache) tc_gemm_destroy(kv.second);
+  for (auto& kv : p->sdpa_cache) sdpa_tc_destroy(kv.second);
   for (void* q : p->allocs) cudaFree(q);
   if (p->dyn_host) cudaFreeHost(p->dyn_host);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
@@ -977,6 +1004,44 @@ extern "C" int spdm_profile_step(spdm_plan* p, int32_t B, int32_t reps, double* 
     p->prof.clear();
   }
   check_async("profile_step");
+  return 0;
+  API_END
+}
+
+// Microbenchmark of one tcgen05 implicit-GEMM launch on zero-filled buffers (tests/perf_conv.py): average ms over
+// `iters` back-to-back launches.  `dbg` = TcParams::dbg switches (0 = the real kernel).
+extern "C" int spdm_microbench_conv(int32_t H, int32_t W, int32_t B, int32_t Cin, int32_t Cout, int32_t taps, int32_t dbg,
+                                    int32_t iters, float* ms_out) {
+  API_BEGIN
+  REQUIRE(ms_out && iters > 0, "bad argument");
+  const size_t M = (size_t)B * H * W;
+  bf16 *in = nullptr, *w = nullptr, *out = nullptr;
+  float* stats = nullptr;
+  CUDA_OK(cudaMalloc(&in, M * Cin * 2));
+  CUDA_OK(cudaMalloc(&w, (size_t)taps * Cin * Cout * 2));
+  CUDA_OK(cudaMalloc(&out, M * Cout * 2));
+  CUDA_OK(cudaMalloc(&stats, (size_t)B * SPDM_MAX_PARTIALS * 2 * 4));
+  CUDA_OK(cudaMemset(in, 0, M * Cin * 2));
+  CUDA_OK(cudaMemset(w, 0, (size_t)taps * Cin * Cout * 2));
+  TcGemm* g = tc_gemm_create(in, Cin, w, Cin, Cout, taps, H, W, B);
+  REQUIRE(g != nullptr, "%s", tc_last_error());
+  tc_set_debug(dbg);
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  for (int i = 0; i < 3; ++i) tc_gemm_launch(g, out, Cout, stats, nullptr, nullptr, 0, EPI_STATS, B, 0);
+  CUDA_OK(cudaEventRecord(e0, 0));
+  for (int i = 0; i < iters; ++i) tc_gemm_launch(g, out, Cout, stats, nullptr, nullptr, 0, EPI_STATS, B, 0);
+  CUDA_OK(cudaEventRecord(e1, 0));
+  cudaError_t e = cudaEventSynchronize(e1);
+  tc_set_debug(0);
+  CUDA_OK(e);
+  float ms = 0.f;
+  CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+  *ms_out = ms / iters;
+  tc_gemm_destroy(g);
+  cudaFree(in); cudaFree(w); cudaFree(out); cudaFree(stats);
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
   return 0;
   API_END
 }

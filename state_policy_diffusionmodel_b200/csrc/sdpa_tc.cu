@@ -1,0 +1,262 @@
+// sdpa_tc.cu — attention core of the SelfAttention blocks on tcgen05 (sm_100a).
+//
+//   o[b, i, h] = softmax_j( q_i . k_j / sqrt(hd) ) v_j        nn.MultiheadAttention(channels, 4, batch_first=True),
+//                                                              reference models/Unet_FiLmLayer.py:50,76
+// The token count per sample is tiny (L = H*W in {4,16,64,256}), so a whole softmax row fits in tensor memory:
+//   CTA        = one 128-token query tile x one 64-channel block (= 64/hd heads) of one attention tile
+//   keys       = the LK in {128,256} tokens of the attention tile: 128/L whole samples when L <= 128 (block-diagonal
+//                mask in the softmax), or the 256 tokens of the query's sample when L == 256
+//   S = Q K^T  : tcgen05.mma M=128, N=LK, K=hd; Q and K tiles are plain 2-D TMA boxes of the qkv activation
+//                ([tokens][3C], K-major, 128B swizzle); a head is a 2*hd-byte column offset inside the 128-byte row
+//   softmax    : one thread per query row reads its S row from TMEM (two passes: max, then exp2/sum), writes P as
+//                bf16 into shared memory in the canonical K-major 128B-swizzled layout
+//   O = P V    : tcgen05.mma M=128, N=hd, K=LK; V^T tiles ([C][LK], K-major) are written by the in_proj GEMM
+//                epilogue (EPI_VT), so both operands of both GEMMs are K-major
+//   epilogue   : O row / rowsum -> bf16 -> att[token][C]
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+struct SdpaParams {
+  int C, L, hd, heads_per_blk;
+  float scale_log2;  // log2(e) / sqrt(hd)
+  bf16* out;         // [M][C]
+};
+
+template <int LK>
+__global__ void __launch_bounds__(128)
+sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_vt, const SdpaParams p) {
+  constexpr int KB = LK / 64;  // key blocks of 64
+  constexpr int SQ = 16384, SK = LK * 128, SVT = KB * 8192;
+  constexpr int TMEM_COLS = (LK == 256) ? 512 : 256;  // S: LK columns, O: up to 64 columns
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + SQ;
+  uint8_t* sVt = sK + SK;
+  uint8_t* sP = sVt + SVT;
+  __shared__ __align__(8) uint64_t bar_load;
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_smem;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int q_row0 = blockIdx.x * 128;
+  const int cb = blockIdx.y;
+  const int kv_tile = q_row0 / LK;
+  const int key_row0 = kv_tile * LK;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_vt);
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+
+  if (tid == 0) {
+    mbar_expect_tx(&bar_load, SQ + SK + SVT);
+    tma_load_2d(sQ, &map_qkv, &bar_load, cb * 64, q_row0);
+#pragma unroll
+    for (int i = 0; i < LK / 128; ++i) tma_load_2d(sK + i * 16384, &map_qkv, &bar_load, p.C + cb * 64, key_row0 + i * 128);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) tma_load_2d(sVt + kb * 8192, &map_vt, &bar_load, kb * 64, kv_tile * p.C + cb * 64);
+  }
+  mbar_wait(&bar_load, 0);
+
+  const int r = tid;  // query row inside the tile == TMEM lane
+  int k_lo = 0, k_hi = LK;
+  if (p.L < LK) {  // several samples share the tile: a query only sees the keys of its own sample
+    const int pos = (q_row0 - key_row0) + r;
+    k_lo = (pos / p.L) * p.L;
+    k_hi = k_lo + p.L;
+  }
+  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t idesc_s = make_idesc(LK), idesc_o = make_idesc(p.hd);
+  uint32_t mma_phase = 0;
+
+  for (int h = 0; h < p.heads_per_blk; ++h) {
+    // ---------------- S = Q_h K_h^T ----------------
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t head_off = (uint64_t)((h * p.hd * 2) >> 4);
+      const uint64_t dq = make_smem_desc(smem_u32(sQ)) + head_off;
+      const uint64_t dk = make_smem_desc(smem_u32(sK)) + head_off;
+      for (int kk = 0; kk < p.hd / 16; ++kk) umma_bf16(tmem, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc_s, kk > 0 ? 1u : 0u);
+      umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+
+    // ---------------- softmax over the row ----------------
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int c = 0; c < LK; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + (uint32_t)c, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int col = c + i;
+        if (col >= k_lo && col < k_hi) m = fmaxf(m, __uint_as_float(v[i]));
+      }
+    }
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < LK; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + (uint32_t)c, v);
+      tmem_ld_wait();
+      uint32_t packed[16];
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const int col = c + i;
+        float p0 = (col >= k_lo && col < k_hi) ? exp2f((__uint_as_float(v[i]) - m) * p.scale_log2) : 0.f;
+        float p1 = (col + 1 >= k_lo && col + 1 < k_hi) ? exp2f((__uint_as_float(v[i + 1]) - m) * p.scale_log2) : 0.f;
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+        sum += __low2float(b2) + __high2float(b2);
+        packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+      }
+      // row r of key block kb = c/64, 16-byte chunks j0..j0+3, 128B swizzle: chunk j lives at (j ^ (r & 7))
+      uint8_t* rowp = sP + (c >> 6) * 16384 + r * 128;
+      const int j0 = (c & 63) >> 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const uint4 val = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+        *reinterpret_cast<uint4*>(rowp + (((j0 + j) ^ (r & 7)) << 4)) = val;
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+
+    // ---------------- O = P V_h ----------------
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll 1
+      for (int kb = 0; kb < KB; ++kb) {
+        const uint64_t dp = make_smem_desc(smem_u32(sP + kb * 16384));
+        const uint64_t dv = make_smem_desc(smem_u32(sVt + kb * 8192 + h * p.hd * 128));
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          umma_bf16(tmem + (uint32_t)LK, dp + (uint64_t)(2 * kk), dv + (uint64_t)(2 * kk), idesc_o, (kb > 0 || kk > 0) ? 1u : 0u);
+      }
+      umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+
+    const float inv = 1.f / sum;
+    bf16* orow = p.out + (size_t)(q_row0 + r) * p.C + cb * 64 + h * p.hd;
+#pragma unroll 1
+    for (int c = 0; c < p.hd; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + (uint32_t)(LK + c), v);
+      tmem_ld_wait();
+      const int n = p.hd - c < 32 ? p.hd - c : 32;
+      for (int i = 0; i < n; i += 8) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i + e]) * inv;
+        store8(orow + c + i, f);
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // S, P and O are reused by the next head
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+}  // namespace
+
+struct SdpaTc {
+  CUtensorMap map_qkv, map_vt;
+  SdpaParams p;
+  int LK;
+};
+
+bool sdpa_tc_supported(int L, int C, int heads) {
+  if (heads <= 0 || C % heads || C % 64) return false;
+  const int hd = C / heads;
+  if (hd != 16 && hd != 32 && hd != 64) return false;
+  return (L <= 128 && 128 % L == 0) || L == 256;
+}
+int sdpa_tc_keys_per_tile(int L) { return L <= 128 ? 128 : L; }
+
+SdpaTc* sdpa_tc_create(const bf16* qkv, const bf16* vt, int C, int L, int heads, long long Mcap) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc || !sdpa_tc_supported(L, C, heads)) return nullptr;
+  SdpaTc* g = new SdpaTc();
+  memset(g, 0, sizeof(*g));
+  g->LK = sdpa_tc_keys_per_tile(L);
+  const int hd = C / heads;
+  g->p.C = C; g->p.L = L; g->p.hd = hd; g->p.heads_per_blk = 64 / hd;
+  g->p.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)3 * C, (cuuint64_t)Mcap};
+    cuuint64_t strides[1] = {(cuuint64_t)3 * C * 2};
+    cuuint32_t box[2] = {64, 128};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&g->map_qkv, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)qkv, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      delete g;
+      return nullptr;
+    }
+  }
+  {
+    cuuint64_t dims[2] = {(cuuint64_t)g->LK, (cuuint64_t)(Mcap / g->LK) * C};
+    cuuint64_t strides[1] = {(cuuint64_t)g->LK * 2};
+    cuuint32_t box[2] = {64, 64};
+    cuuint32_t estr[2] = {1, 1};
+    if (enc(&g->map_vt, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)vt, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+      delete g;
+      return nullptr;
+    }
+  }
+  return g;
+}
+void sdpa_tc_destroy(SdpaTc* g) { delete g; }
+
+void sdpa_tc_launch(const SdpaTc* g, bf16* out, long long M, cudaStream_t s) {
+  SdpaParams p = g->p;
+  p.out = out;
+  dim3 grid((unsigned)(M / 128), (unsigned)(p.C / 64));
+  if (g->LK == 128) {
+    constexpr int smem = 16384 + 128 * 128 + 2 * 8192 + 2 * 16384 + 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(sdpa_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    sdpa_tc_kernel<128><<<grid, 128, smem, s>>>(g->map_qkv, g->map_vt, p);
+  } else {
+    constexpr int smem = 16384 + 256 * 128 + 4 * 8192 + 4 * 16384 + 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(sdpa_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    sdpa_tc_kernel<256><<<grid, 128, smem, s>>>(g->map_qkv, g->map_vt, p);
+  }
+}
