@@ -222,8 +222,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           }
         }
         if (p.flags & EPI_STATS) {
+          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-          for (int i = 0; i < 32; ++i) { rs += f[i]; rq = fmaf(f[i], f[i], rq); }
+          for (int i = 0; i < 32; ++i) { s4[i & 3] += f[i]; q4[i & 3] = fmaf(f[i], f[i], q4[i & 3]); }
+          rs += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          rq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
         }
         if ((p.flags & EPI_VT) && t.n0 + c >= p.vt_c0) {
           // V^T for the tcgen05 attention core: consecutive lanes are consecutive tokens -> 64-byte segments per column
@@ -256,6 +259,195 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           dst[0] = rs;
           dst[1] = rq;
         }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Swapped-operand variant for narrow outputs (Cout = 64 or 128).
+//
+// A tcgen05.mma in SS mode costs ~128 cycles per 128-row A operand regardless of N (measured: tests/perf_conv.py),
+// so an N = 64/128 tile runs the tensor pipe at 25-50 %.  Here the roles are exchanged: D^T[Cout][pixels] =
+// W[Cout][K] * X^T[K][pixels] with M = 128 weight rows (rows >= Cout are TMA out-of-bounds zeros) and N = 256 pixels
+// (two stacked 128-row boxes of the activation).  The accumulator then holds channels in TMEM lanes and pixels in
+// columns; the epilogue writes the channels-last output with 64-byte warp stores (one pixel per instruction).
+// Only EPI_STATS epilogues (the 3x3 convolutions) take this path.
+// ---------------------------------------------------------------------------------------------
+template <int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+  constexpr int PIX_BYTES = 2 * A_STAGE_BYTES;           // 256 pixels x 64 ch
+  constexpr int W_BYTES = BLOCK_M * BLOCK_K * 2;         // 128 weight rows x 64 k
+  constexpr int NPIX = 256;
+  constexpr int TMEM_COLS = 2 * NPIX;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_pix = smem;
+  uint8_t* smem_w = smem + STAGES * PIX_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar[2];
+  __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  __shared__ uint32_t tmem_base_smem;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const bool skip_dx = (p.W == 1), skip_dy = (p.H == 1);
+  const int ntx = skip_dx ? 1 : 3, nty = skip_dy ? 1 : 3;
+  const int k_iters = ntx * nty * p.kb_per_tap;
+  const int c_tiles = p.n_tiles;             // tiles of 128 output channels
+  const int total = p.total_tiles;           // (m_tiles / 2) * c_tiles
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_w);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar[0], 1); mbar_init(&tmem_full_bar[1], 1);
+    mbar_init(&tmem_empty_bar[0], 4); mbar_init(&tmem_empty_bar[1], 4);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  TcParams pm = p;       // decode_tile works on 128-row tiles with n_tiles == 1
+  pm.n_tiles = 1;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t kit = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int c_tile = tile % c_tiles, pt = tile / c_tiles;
+        const TileCoord t0 = decode_tile(pm, 2 * pt, 0), t1 = decode_tile(pm, 2 * pt + 1, 0);
+        for (int it = 0; it < k_iters; ++it, ++kit) {
+          const int s = kit % STAGES;
+          const uint32_t ph = (kit / STAGES) & 1u;
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          const int tap_i = it / p.kb_per_tap, kb = it - tap_i * p.kb_per_tap;
+          const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
+          const int dy = skip_dy ? 0 : ty - 1, dx = skip_dx ? 0 : tx - 1;
+          const int tap = (dy + 1) * 3 + (dx + 1);
+          mbar_expect_tx(&full_bar[s], PIX_BYTES + W_BYTES);
+          tma_load_4d(smem_pix + s * PIX_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t0.h0 + dy, t0.b0);
+          tma_load_4d(smem_pix + s * PIX_BYTES + A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t1.h0 + dy, t1.b0);
+          tma_load_2d(smem_w + s * W_BYTES, &map_w, &full_bar[s], tap * p.Cin + kb * BLOCK_K, c_tile * BLOCK_M);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(NPIX);
+      uint32_t kit = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[acc], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NPIX);
+        for (int it = 0; it < k_iters; ++it, ++kit) {
+          const int s = kit % STAGES;
+          const uint32_t ph = (kit / STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t dw = make_smem_desc(smem_u32(smem_w + s * W_BYTES));      // "A": 128 weight rows
+          const uint64_t dp = make_smem_desc(smem_u32(smem_pix + s * PIX_BYTES));  // "B": 256 pixel rows
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(d_tmem, dw + (uint64_t)(2 * k), dp + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int ch_local = q * 32 + lane;                 // TMEM lane == output channel inside the 128-channel tile
+    const int pps = p.H * p.W;                          // pixels per sample
+    const int tiles_per_sample = pps > NPIX ? pps / NPIX : 1;
+    const int nw = (p.Cout >= BLOCK_M) ? 4 : p.Cout / 32;  // epilogue warps that own real channels
+    int lt = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+      const int c_tile = tile % c_tiles, pt = tile / c_tiles;
+      const int acc = lt & 1;
+      const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+      const long long row0 = (long long)pt * NPIX;      // the 256 pixel rows of the tile are contiguous
+      mbar_wait(&tmem_full_bar[acc], aph);
+      tc_fence_after();
+      const bool active = q < nw;
+      const int ch = c_tile * BLOCK_M + ch_local;
+      const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NPIX);
+      float rs = 0.f, rq = 0.f;
+      if (active) {
+#pragma unroll 1
+        for (int c = 0; c < NPIX; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (c + 32 == NPIX) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          bf16* optr = p.out + (row0 + c) * p.ld_out + ch;
+          if (pps >= 32) {
+            float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float f = __uint_as_float(v[i]);
+              s4[i & 3] += f; q4[i & 3] = fmaf(f, f, q4[i & 3]);
+              optr[(size_t)i * p.ld_out] = __float2bfloat16_rn(f);
+            }
+            rs += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+            rq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
+            const int span = pps < NPIX ? pps : NPIX;   // columns per (sample, tile)
+            if ((c + 32) % span == 0) {                 // end of a sample's columns: publish this warp's partial
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) { rs += __shfl_xor_sync(0xffffffffu, rs, o); rq += __shfl_xor_sync(0xffffffffu, rq, o); }
+              if (lane == 0) {
+                const long long b = (row0 + c) / pps;
+                const int tile_in_sample = (int)(pt % tiles_per_sample);
+                const int slot = (tile_in_sample * c_tiles + c_tile) * nw + q;
+                float* dst = p.stats + ((size_t)b * p.P + slot) * 2;
+                dst[0] = rs; dst[1] = rq;
+              }
+              rs = 0.f; rq = 0.f;
+            }
+          } else {  // pps == 16: two samples per 32-column chunk
+            float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              const float f = __uint_as_float(v[i]);
+              if (i < 16) { sa += f; qa = fmaf(f, f, qa); } else { sb += f; qb = fmaf(f, f, qb); }
+              optr[(size_t)i * p.ld_out] = __float2bfloat16_rn(f);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+              sa += __shfl_xor_sync(0xffffffffu, sa, o); qa += __shfl_xor_sync(0xffffffffu, qa, o);
+              sb += __shfl_xor_sync(0xffffffffu, sb, o); qb += __shfl_xor_sync(0xffffffffu, qb, o);
+            }
+            if (lane == 0) {
+              const long long b = (row0 + c) / 16;
+              const int slot = c_tile * nw + q;
+              float* dst = p.stats + ((size_t)b * p.P + slot) * 2;
+              dst[0] = sa; dst[1] = qa;
+              dst[(size_t)p.P * 2] = sb; dst[(size_t)p.P * 2 + 1] = qb;
+            }
+          }
+        }
+      } else {  // this warp's TMEM lanes hold the zero rows of a 64-channel layer
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
       }
     }
     tc_fence_before();
@@ -312,7 +504,8 @@ void launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p,
 }  // namespace
 
 struct TcGemm {
-  CUtensorMap map_a, map_b, map_b256;
+  CUtensorMap map_a, map_b, map_b256, map_wswap;
+  bool can_swap;    // 3x3, Cout in {64,128}, geometry allows 256-pixel tiles with per-sample statistics
   TcParams p;
   int block_n;      // 64 or 128
   bool has256;      // Cout % 256 == 0: a 256-wide N tile is available
@@ -364,15 +557,20 @@ TcGemm* tc_gemm_create(const bf16* in, int ld_in, const bf16* w_packed, int Cin,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(A) failed: %d", (int)r); delete g; return nullptr; }
   }
-  for (int pass = 0; pass < 2; ++pass) {  // B: 2-D (K, Cout) weights, one map per N-tile width
-    if (pass == 1 && !g->has256) break;
-    const int bn = pass == 0 ? g->block_n : 256;
+  {
+    const int pps = H * W;
+    g->can_swap = taps == 9 && (Cout == 64 || Cout == 128) && (pps == 16 || (pps >= 32 && pps % 32 == 0 && (pps >= 256 ? pps % 256 == 0 : 256 % pps == 0)));
+  }
+  for (int pass = 0; pass < 3; ++pass) {  // B: 2-D (K, Cout) weights, one map per tile height
+    if (pass == 1 && !g->has256) continue;
+    if (pass == 2 && !g->can_swap) continue;
+    const int bn = pass == 0 ? g->block_n : (pass == 1 ? 256 : BLOCK_M);
     const cuuint64_t Ktot = (cuuint64_t)taps * Cin;
     cuuint64_t dims[2] = {Ktot, (cuuint64_t)Cout};
     cuuint64_t strides[1] = {Ktot * 2};
     cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)bn};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(pass == 0 ? &g->map_b : &g->map_b256, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_packed, dims, strides, box, estr,
+    CUresult r = enc(pass == 0 ? &g->map_b : (pass == 1 ? &g->map_b256 : &g->map_wswap), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_packed, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(B) failed: %d", (int)r); delete g; return nullptr; }
@@ -389,8 +587,23 @@ int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const f
   p.vt = vt; p.vt_lk = vt_lk; p.vt_C = p.Cout / 3; p.vt_c0 = 2 * (p.Cout / 3);
   p.out = out; p.ld_out = ld_out; p.stats = stats; p.bias = bias; p.resid = resid; p.ld_res = ld_res; p.flags = flags;
   p.m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
-  // a 256-wide N tile halves the A traffic per FLOP; use it once there are enough tiles to fill the machine
-  const bool use256 = g->has256 && (long long)p.m_tiles * (p.Cout / 256) >= num_sms();
+  if (g->can_swap && flags == EPI_STATS && p.m_tiles % 2 == 0 && !(g_tc_dbg & 64)) {
+    p.n_tiles = (p.Cout + BLOCK_M - 1) / BLOCK_M;
+    p.total_tiles = (p.m_tiles / 2) * p.n_tiles;
+    const int pps = p.H * p.W;
+    const int nw = p.Cout >= BLOCK_M ? 4 : p.Cout / 32;
+    p.P = (pps > 256 ? pps / 256 : 1) * p.n_tiles * nw;
+    constexpr int STG = 4;
+    constexpr int smem = STG * (2 * A_STAGE_BYTES + BLOCK_M * BLOCK_K * 2) + 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(conv_tc_swap_kernel<STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    conv_tc_swap_kernel<STG><<<grid, NUM_THREADS, smem, s>>>(g->map_a, g->map_wswap, p);
+    ++g_tc_launches;
+    return p.P;
+  }
+  // the MMA issue cost does not depend on N (the 128-row A operand read dominates): the widest N tile wins
+  const bool use256 = g->has256 && !(g_tc_dbg & 128);
   const int bn = use256 ? 256 : g->block_n;
   p.n_tiles = p.Cout / bn;
   p.total_tiles = p.m_tiles * p.n_tiles;

@@ -191,55 +191,76 @@ namespace {
 constexpr int APPLY_THREADS = 128;
 constexpr int APPLY_VEC_PER_THREAD = 4;
 
-template <typename TI, typename TO>
+// erf to ~1.5e-7 absolute (Abramowitz-Stegun 7.1.26): enough for the bf16 path, a third of erff's cost
+__device__ __forceinline__ float erf_fast(float x) {
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  return copysignf(1.0f - poly * __expf(-ax * ax), x);
+}
+
+template <typename TI, typename TO, bool EXACT>
 __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(ApplyArgs a) {
   const int b = blockIdx.y;
-  __shared__ float s_mean, s_rstd;
-  if (threadIdx.x < 32) {
-    double s = 0.0, q = 0.0;
-    for (int p = threadIdx.x; p < a.P; p += 32) {
-      s += (double)a.stats[((size_t)b * a.P + p) * 2];
-      q += (double)a.stats[((size_t)b * a.P + p) * 2 + 1];
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
-    if (threadIdx.x == 0) {
-      const double n = (double)a.HW * (double)a.C;
-      const double mean = s / n;
-      double var = q / n - mean * mean;
-      if (var < 0.0) var = 0.0;
-      s_mean = (float)mean;
-      s_rstd = (float)(1.0 / sqrt(var + (double)a.eps));
-    }
+  // every thread folds the P partial sums of its sample itself (broadcast loads, no barrier)
+  double s = 0.0, q = 0.0;
+  for (int p = 0; p < a.P; ++p) {
+    const float2 sq = __ldg(reinterpret_cast<const float2*>(a.stats) + (size_t)b * a.P + p);
+    s += (double)sq.x;
+    q += (double)sq.y;
   }
-  __syncthreads();
-  const float mean = s_mean, rstd = s_rstd;
+  const double n = (double)a.HW * (double)a.C;
+  const double dmean = s / n;
+  double var = q / n - dmean * dmean;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)dmean;
+  const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+
   const TI* __restrict__ raw = reinterpret_cast<const TI*>(a.raw);
   TO* __restrict__ out = reinterpret_cast<TO*>(a.out);
-  const int vec_per_row = a.C >> 3;
+  const int vec_per_row = a.C >> 3;  // a power of two <= APPLY_THREADS: a thread keeps the same 8 channels
   const int nvec = a.HW * vec_per_row;
-  const float* temb = nullptr;
-  if (a.temb_mode != TEMB_NONE) {
+  const int c8 = (threadIdx.x & (vec_per_row - 1)) << 3;
+  float g[8], be[8], te[8], fs[8], fb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { te[i] = 0.f; fs[i] = 1.f; fb[i] = 0.f; }
+  load8(a.gamma + c8, g);
+  load8(a.beta + c8, be);
+  const bool has_temb = a.temb_mode != TEMB_NONE, has_film = a.film != nullptr;
+  if (has_temb) {
     int trow = 0;
     if (a.temb_mode == TEMB_PER_SAMPLE) trow = b;
     else if (a.temb_mode == TEMB_STEP) trow = *a.step_ptr;
-    temb = a.temb + (size_t)trow * SPDM_TEMB_WIDTH + a.temb_off;
+    load8(a.temb + (size_t)trow * SPDM_TEMB_WIDTH + a.temb_off + c8, te);
   }
-  const float* film = a.film ? a.film + (size_t)b * SPDM_FILM_WIDTH + a.film_off : nullptr;
+  if (has_film) {
+    const float* film = a.film + (size_t)b * SPDM_FILM_WIDTH + a.film_off;
+    load8(film + c8, fs);
+    load8(film + a.C + c8, fb);
+  }
+  if (!EXACT) {  // fold the normalisation into one FMA per element
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float ga = rstd * g[i]; be[i] = fmaf(-mean, ga, be[i]); g[i] = ga; }
+  }
   const int v0 = blockIdx.x * (APPLY_THREADS * APPLY_VEC_PER_THREAD);
 #pragma unroll
   for (int it = 0; it < APPLY_VEC_PER_THREAD; ++it) {
     const int v = v0 + it * APPLY_THREADS + threadIdx.x;
     if (v >= nvec) break;
-    const int row = v / vec_per_row, c8 = (v - row * vec_per_row) << 3;
+    const int row = v / vec_per_row;
     float x[8];
     load8(raw + ((size_t)b * a.HW + row) * a.ld_in + c8, x);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      float y = (x[i] - mean) * rstd * __ldg(a.gamma + c8 + i) + __ldg(a.beta + c8 + i);
-      if (a.act == ACT_GELU) y = gelu_exact(y);
-      if (temb) y += __ldg(temb + c8 + i);
-      if (film) y = __ldg(film + c8 + i) * y + __ldg(film + a.C + c8 + i);
+      float y;
+      if (EXACT) y = (x[i] - mean) * rstd * g[i] + be[i];
+      else y = fmaf(x[i], g[i], be[i]);
+      if (a.act == ACT_GELU) {
+        if (EXACT) y = gelu_exact(y);
+        else y = 0.5f * y * (1.0f + erf_fast(y * 0.70710678118654752440f));
+      }
+      if (has_temb) y += te[i];
+      if (has_film) y = fs[i] * y + fb[i];
       x[i] = y;
     }
     store8(out + ((size_t)b * a.HW + row) * a.ld_out + c8, x);
@@ -249,7 +270,8 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(ApplyArgs a) {
 template <typename TI, typename TO> void launch_apply(const ApplyArgs& a, int B, cudaStream_t s) {
   const int nvec = a.HW * (a.C >> 3);
   dim3 grid(cdiv(nvec, APPLY_THREADS * APPLY_VEC_PER_THREAD), B);
-  apply_kernel<TI, TO><<<grid, APPLY_THREADS, 0, s>>>(a);
+  if (sizeof(TI) == 4) apply_kernel<TI, TO, true><<<grid, APPLY_THREADS, 0, s>>>(a);
+  else apply_kernel<TI, TO, false><<<grid, APPLY_THREADS, 0, s>>>(a);
   COUNT_LAUNCH();
 }
 template void launch_apply<float, float>(const ApplyArgs&, int, cudaStream_t);
@@ -335,39 +357,66 @@ template void launch_upsample<bf16>(const bf16*, int, bf16*, int, int, int, int,
 // LayerNorm over C (models/Unet_FiLmLayer.py:51,53): one warp per token row, C in {64,128,256}.
 // =================================================================================================
 namespace {
-template <typename T, int VPL>  // VPL = C / 32 elements per lane
+template <typename T, int LANES>  // LANES = C / 8 lanes per token row (8 channels = one 16-byte vector per lane)
 __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ in, int ld_in, T* __restrict__ out, int ld_out,
                                                         const float* __restrict__ g, const float* __restrict__ bta, long long M) {
+  constexpr int ROWS_PER_WARP = 32 / LANES;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / LANES, l = lane % LANES;
+  const long long row = ((long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * ROWS_PER_WARP + sub;
+  const bool ok = row < M;
+  const int c0 = l * 8;
+  constexpr float inv_c = 1.0f / (float)(LANES * 8);
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = 0.f;
+  if (ok) load8(in + row * ld_in + c0, x);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += x[i];
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s * inv_c;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float d = x[i] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = LANES / 2; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = rsqrtf(q * inv_c + 1e-5f);
+  if (!ok) return;
+  float gg[8], bb[8];
+  load8(g + c0, gg);
+  load8(bta + c0, bb);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = (x[i] - mean) * rstd * gg[i] + bb[i];
+  store8(out + row * ld_out + c0, x);
+}
+// wide rows (C = 512): one warp per row, 16 channels per lane
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_wide_kernel(const T* __restrict__ in, int ld_in, T* __restrict__ out, int ld_out,
+                                                             const float* __restrict__ g, const float* __restrict__ bta, long long M, int C) {
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
-  const int c0 = lane * VPL;
-  float x[VPL];
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) x[i] = to_f32<T>(in[row * ld_in + c0 + i]);
   float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) s += x[i];
+  for (int c = lane; c < C; c += 32) s += to_f32<T>(in[row * ld_in + c]);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)(VPL * 32);
+  const float mean = s / (float)C;
   float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPL; ++i) { const float d = x[i] - mean; q = fmaf(d, d, q); }
+  for (int c = lane; c < C; c += 32) { const float d = to_f32<T>(in[row * ld_in + c]) - mean; q = fmaf(d, d, q); }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = rsqrtf(q / (float)(VPL * 32) + 1e-5f);
-#pragma unroll
-  for (int i = 0; i < VPL; ++i)
-    out[row * ld_out + c0 + i] = from_f32<T>((x[i] - mean) * rstd * __ldg(g + c0 + i) + __ldg(bta + c0 + i));
+  const float rstd = rsqrtf(q / (float)C + 1e-5f);
+  for (int c = lane; c < C; c += 32)
+    out[row * ld_out + c] = from_f32<T>((to_f32<T>(in[row * ld_in + c]) - mean) * rstd * __ldg(g + c) + __ldg(bta + c));
 }
 }  // namespace
 template <typename T> void launch_layernorm(const T* in, int ld_in, T* out, int ld_out, const float* g, const float* b, long long M, int C, cudaStream_t s) {
-  const int grid = cdiv(M, 8);
-  if (C == 64) layernorm_kernel<T, 2><<<grid, 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
-  else if (C == 128) layernorm_kernel<T, 4><<<grid, 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
-  else if (C == 256) layernorm_kernel<T, 8><<<grid, 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
-  else if (C == 512) layernorm_kernel<T, 16><<<grid, 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
+  if (C == 64) layernorm_kernel<T, 8><<<cdiv(M, 8 * 4), 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
+  else if (C == 128) layernorm_kernel<T, 16><<<cdiv(M, 8 * 2), 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
+  else if (C == 256) layernorm_kernel<T, 32><<<cdiv(M, 8), 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
+  else layernorm_wide_kernel<T><<<cdiv(M, 8), 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M, C);
   COUNT_LAUNCH();
 }
 template void launch_layernorm<float>(const float*, int, float*, int, const float*, const float*, long long, int, cudaStream_t);
