@@ -44,6 +44,7 @@ def parse():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--rows", type=int, default=31)
     ap.add_argument("--graph-steps", type=int, default=10)
+    ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches per denoising step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="one sampling call, for ncu")
     return ap.parse_args()
@@ -180,7 +181,7 @@ def config_dict(args, total_B):
                 args.sampler.upper(), args.ddim_steps, "UNet_Film (attention)" if args.variant == "attn" else "UNet_Film_noAttention", args.rows),
             "global_batch": total_B, "per_gpu_batch": args.batch, "denoise_steps": args.ddim_steps, "precision": args.precision,
             "parallelism": "batch-sharded x%d, final all_gather" % args.gpus,
-            "cache": "inputs_larger_than_l2 (283 MB of frames per step per GPU)", "graph_steps": args.graph_steps}
+            "cache": "inputs_larger_than_l2 (283 MB of frames per step per GPU)", "graph_steps": args.graph_steps, "concurrent_sub_batches": args.split}
 
 
 def main():
@@ -210,7 +211,7 @@ def main():
     Wrapper = spdm.Diffusion_DDIM
     model = Wrapper(noise_steps=1000, obs_horizon=10, pred_horizon=rows - 1, observation_dim=135, prediction_dim=5,
                     model="UNet_Film" if attention else "UNet_FilmnoAttention", inpaint_horizon=1).to(dev).eval()
-    model.configure(precision=args.precision, graph_steps=args.graph_steps, batch_max=B)
+    model.configure(precision=args.precision, graph_steps=args.graph_steps, batch_max=B, split=args.split)
     if args.sampler == "ddim":
         model.use_ddim(K)       # generate.py:28-35 convention: DDIMScheduler(num_train_timesteps=K), K steps
     else:

@@ -27,6 +27,7 @@ enum { SPDM_VARIANT_ATTENTION = 0, SPDM_VARIANT_NO_ATTENTION = 1 };
 enum { SPDM_PRECISION_FP32 = 0, SPDM_PRECISION_BF16 = 1 };
 enum { SPDM_SCHED_DDPM = 0, SPDM_SCHED_DDIM = 1 };
 enum { SPDM_FLAG_SCHEDULER_ONLY = 1 }; /* plan without U-Net weights/workspace: spdm_step, spdm_add_noise only */
+#define SPDM_FLAG_SPLIT(n) (((n) & 0xF) << 8) /* run n sub-batches of every denoising step concurrently (spdm_sample) */
 
 typedef struct spdm_config {
   int32_t variant;       /* models/Unet_FiLmLayer.py:240 (0) or Unet_FiLmLayer_noAttention.py:240 (1) */

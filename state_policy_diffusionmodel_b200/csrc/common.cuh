@@ -23,6 +23,30 @@ enum : int { EPI_STATS = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RESID = 8, EPI_VT = 
 #define SPDM_TEMB_WIDTH 896  /* sum over the 6 stages of C_out   */
 #define SPDM_MAX_PARTIALS 64 /* upper bound on GroupNorm partial slots per sample */
 
+// Programmatic dependent launch: every kernel of the forward path is launched with the programmatic-stream-
+// serialization attribute.  pdl_wait() blocks until the preceding kernel in the stream has completed and its
+// writes are visible (so everything after it is ordinary stream order); whatever a kernel does before it (barrier
+// init, TMEM allocation, descriptor prefetch) overlaps with the tail of its predecessor.  pdl_trigger() lets the
+// successor start that prologue as soon as every CTA of this kernel is resident.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+extern int g_spdm_pdl;  // 1: launch with the PDL attribute (default), 0: plain launches (kernels.cu)
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_spdm_pdl ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float gelu_exact(float x) {
   return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
@@ -114,7 +138,8 @@ struct StepArgs {
   int step_host;
   int n;                 // elements per sample (rows*dim)
   int inpaint_elems;     // inpaint_rows*dim
-  int B;
+  int B;                 // samples handled by this launch: [b0, b0 + B) of a batch of B_total
+  int b0, B_total;
 };
 
 // launchers implemented in kernels.cu ------------------------------------------------------------
@@ -131,6 +156,7 @@ template <typename T> void launch_to_nchw(const T* in, int ld, float* out, int B
 void launch_step(const StepArgs& a, cudaStream_t s);
 void launch_advance(int* step_ptr, int delta, cudaStream_t s);
 void launch_set_int(int* p, int v, cudaStream_t s);
+void launch_delay(long long cycles, cudaStream_t s);  // spin kernel (profiling: lets the host run ahead)
 void launch_temb(const long long* t_dev, int n_t, const float* inv_freq, const float* w_cat, const float* b_cat, float* out, int time_dim, cudaStream_t s);
 void launch_mish(const float* in, float* out, long long n, cudaStream_t s);
 void launch_enc_convs(const float* img, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3, float* feat, int n, cudaStream_t s);

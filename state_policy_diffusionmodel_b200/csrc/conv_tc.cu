@@ -108,6 +108,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();     // everything above overlapped with the previous kernel's tail; global memory is touched only below
+  pdl_trigger();
 
   if (warp == 0) {
     // ================= TMA producer =================
@@ -319,6 +321,8 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();     // everything above overlapped with the previous kernel's tail; global memory is touched only below
+  pdl_trigger();
   TcParams pm = p;       // decode_tile works on 128-row tiles with n_tiles == 1
   pm.n_tiles = 1;
 
@@ -497,7 +501,7 @@ void launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p,
     attr = true;
   }
   const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-  conv_tc_kernel<BLOCK_N, STAGES><<<grid, NUM_THREADS, smem_bytes<BLOCK_N, STAGES>(), s>>>(ma, mb, p);
+  launch_pdl(conv_tc_kernel<BLOCK_N, STAGES>, dim3(grid), dim3(NUM_THREADS), smem_bytes<BLOCK_N, STAGES>(), s, ma, mb, p);
   ++g_tc_launches;
 }
 
@@ -598,7 +602,7 @@ int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const f
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(conv_tc_swap_kernel<STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    conv_tc_swap_kernel<STG><<<grid, NUM_THREADS, smem, s>>>(g->map_a, g->map_wswap, p);
+    launch_pdl(conv_tc_swap_kernel<STG>, dim3(grid), dim3(NUM_THREADS), smem, s, g->map_a, g->map_wswap, p);
     ++g_tc_launches;
     return p.P;
   }

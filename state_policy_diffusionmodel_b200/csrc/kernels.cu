@@ -8,6 +8,7 @@
 #include "common.cuh"
 
 static long long g_launches = 0;
+int g_spdm_pdl = 1;
 long long kernels_launch_count() { return g_launches; }
 #define COUNT_LAUNCH() (++g_launches)
 
@@ -24,6 +25,8 @@ constexpr int SG_BM = 64, SG_BN = 64, SG_BK = 16;
 
 template <typename TI, typename TO>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmSimtArgs a) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float As[SG_BK][SG_BM + 4];
   __shared__ float Bs[SG_BK][SG_BN + 4];
   const TI* __restrict__ in = reinterpret_cast<const TI*>(a.in);
@@ -133,7 +136,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmSimtArgs a) {
 
 template <typename TI, typename TO> void launch_gemm_simt(const GemmSimtArgs& a, cudaStream_t s) {
   dim3 grid(cdiv(a.M, SG_BM), cdiv(a.Cout, SG_BN));
-  gemm_simt_kernel<TI, TO><<<grid, 256, 0, s>>>(a);
+  launch_pdl(gemm_simt_kernel<TI, TO>, dim3(grid), dim3(256), 0, s, a);
   COUNT_LAUNCH();
 }
 template void launch_gemm_simt<float, float>(const GemmSimtArgs&, cudaStream_t);
@@ -148,6 +151,8 @@ template void launch_gemm_simt<bf16, float>(const GemmSimtArgs&, cudaStream_t);
 namespace {
 template <typename T>
 __global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ raw, float* __restrict__ stats, int HW, int C, int ld) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.x;
   const int vec_per_row = C >> 3;
   const int nvec = HW * vec_per_row;
@@ -173,7 +178,7 @@ __global__ void __launch_bounds__(256) stats_kernel(const T* __restrict__ raw, f
 }
 }  // namespace
 template <typename T> void launch_stats(const T* raw, float* stats, int B, int HW, int C, int ld, cudaStream_t s) {
-  stats_kernel<T><<<B, 256, 0, s>>>(raw, stats, HW, C, ld);
+  launch_pdl(stats_kernel<T>, dim3(B), dim3(256), 0, s, raw, stats, HW, C, ld);
   COUNT_LAUNCH();
 }
 template void launch_stats<float>(const float*, float*, int, int, int, int, cudaStream_t);
@@ -201,6 +206,8 @@ __device__ __forceinline__ float erf_fast(float x) {
 
 template <typename TI, typename TO, bool EXACT>
 __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(ApplyArgs a) {
+  pdl_wait();
+  pdl_trigger();
   const int b = blockIdx.y;
   // every thread folds the P partial sums of its sample itself (broadcast loads, no barrier)
   double s = 0.0, q = 0.0;
@@ -270,8 +277,8 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(ApplyArgs a) {
 template <typename TI, typename TO> void launch_apply(const ApplyArgs& a, int B, cudaStream_t s) {
   const int nvec = a.HW * (a.C >> 3);
   dim3 grid(cdiv(nvec, APPLY_THREADS * APPLY_VEC_PER_THREAD), B);
-  if (sizeof(TI) == 4) apply_kernel<TI, TO, true><<<grid, APPLY_THREADS, 0, s>>>(a);
-  else apply_kernel<TI, TO, false><<<grid, APPLY_THREADS, 0, s>>>(a);
+  if (sizeof(TI) == 4) launch_pdl(apply_kernel<TI, TO, true>, dim3(grid), dim3(APPLY_THREADS), 0, s, a);
+  else launch_pdl(apply_kernel<TI, TO, false>, dim3(grid), dim3(APPLY_THREADS), 0, s, a);
   COUNT_LAUNCH();
 }
 template void launch_apply<float, float>(const ApplyArgs&, int, cudaStream_t);
@@ -283,6 +290,8 @@ template void launch_apply<bf16, bf16>(const ApplyArgs&, int, cudaStream_t);
 namespace {
 template <typename T>
 __global__ void pool_kernel(const T* __restrict__ in, int ld_in, T* __restrict__ out, int ld_out, long long total, int Ho, int Wo, int C) {
+  pdl_wait();
+  pdl_trigger();
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= total) return;
   const int vec_per_row = C >> 3;
@@ -310,6 +319,8 @@ __global__ void pool_kernel(const T* __restrict__ in, int ld_in, T* __restrict__
 
 template <typename T>
 __global__ void upsample_kernel(const T* __restrict__ in, int ld_in, T* __restrict__ out, int ld_out, long long total, int Hi, int Wi, int C) {
+  pdl_wait();
+  pdl_trigger();
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= total) return;
   const int vec_per_row = C >> 3;
@@ -340,12 +351,12 @@ __global__ void upsample_kernel(const T* __restrict__ in, int ld_in, T* __restri
 }  // namespace
 template <typename T> void launch_pool(const T* in, int ld_in, T* out, int ld_out, int B, int Ho, int Wo, int C, cudaStream_t s) {
   const long long total = (long long)B * Ho * Wo * (C >> 3);
-  pool_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(in, ld_in, out, ld_out, total, Ho, Wo, C);
+  launch_pdl(pool_kernel<T>, dim3(cdiv(total, 256)), dim3(256), 0, s, in, ld_in, out, ld_out, total, Ho, Wo, C);
   COUNT_LAUNCH();
 }
 template <typename T> void launch_upsample(const T* in, int ld_in, T* out, int ld_out, int B, int Hi, int Wi, int C, cudaStream_t s) {
   const long long total = (long long)B * Hi * 2 * Wi * 2 * (C >> 3);
-  upsample_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(in, ld_in, out, ld_out, total, Hi, Wi, C);
+  launch_pdl(upsample_kernel<T>, dim3(cdiv(total, 256)), dim3(256), 0, s, in, ld_in, out, ld_out, total, Hi, Wi, C);
   COUNT_LAUNCH();
 }
 template void launch_pool<float>(const float*, int, float*, int, int, int, int, int, cudaStream_t);
@@ -360,6 +371,8 @@ namespace {
 template <typename T, int LANES>  // LANES = C / 8 lanes per token row (8 channels = one 16-byte vector per lane)
 __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ in, int ld_in, T* __restrict__ out, int ld_out,
                                                         const float* __restrict__ g, const float* __restrict__ bta, long long M) {
+  pdl_wait();
+  pdl_trigger();
   constexpr int ROWS_PER_WARP = 32 / LANES;
   const int lane = threadIdx.x & 31;
   const int sub = lane / LANES, l = lane % LANES;
@@ -395,6 +408,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(const T* __restrict__ in
 template <typename T>
 __global__ void __launch_bounds__(256) layernorm_wide_kernel(const T* __restrict__ in, int ld_in, T* __restrict__ out, int ld_out,
                                                              const float* __restrict__ g, const float* __restrict__ bta, long long M, int C) {
+  pdl_wait();
+  pdl_trigger();
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= M) return;
   const int lane = threadIdx.x & 31;
@@ -413,10 +428,10 @@ __global__ void __launch_bounds__(256) layernorm_wide_kernel(const T* __restrict
 }
 }  // namespace
 template <typename T> void launch_layernorm(const T* in, int ld_in, T* out, int ld_out, const float* g, const float* b, long long M, int C, cudaStream_t s) {
-  if (C == 64) layernorm_kernel<T, 8><<<cdiv(M, 8 * 4), 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
-  else if (C == 128) layernorm_kernel<T, 16><<<cdiv(M, 8 * 2), 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
-  else if (C == 256) layernorm_kernel<T, 32><<<cdiv(M, 8), 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M);
-  else layernorm_wide_kernel<T><<<cdiv(M, 8), 256, 0, s>>>(in, ld_in, out, ld_out, g, b, M, C);
+  if (C == 64) launch_pdl(layernorm_kernel<T, 8>, dim3(cdiv(M, 8 * 4)), dim3(256), 0, s, in, ld_in, out, ld_out, g, b, M);
+  else if (C == 128) launch_pdl(layernorm_kernel<T, 16>, dim3(cdiv(M, 8 * 2)), dim3(256), 0, s, in, ld_in, out, ld_out, g, b, M);
+  else if (C == 256) launch_pdl(layernorm_kernel<T, 32>, dim3(cdiv(M, 8)), dim3(256), 0, s, in, ld_in, out, ld_out, g, b, M);
+  else launch_pdl(layernorm_wide_kernel<T>, dim3(cdiv(M, 8)), dim3(256), 0, s, in, ld_in, out, ld_out, g, b, M, C);
   COUNT_LAUNCH();
 }
 template void launch_layernorm<float>(const float*, int, float*, int, const float*, const float*, long long, int, cudaStream_t);
@@ -432,6 +447,8 @@ namespace {
 template <typename T, int HD>
 __global__ void __launch_bounds__(128) sdpa_kernel(const T* __restrict__ qkv, T* __restrict__ out, int n_groups, int L, int C, int heads,
                                                    int groups_per_block, int threads_per_group) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float sm[];  // [groups_per_block][2][L][HD]
   const int gl = threadIdx.x / threads_per_group;
   const int tl = threadIdx.x - gl * threads_per_group;
@@ -512,7 +529,7 @@ template <typename T> void launch_sdpa(const T* qkv, T* out, int B, int L, int C
       cudaFuncSetAttribute(sdpa_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);      \
       attr_set = true;                                                                                        \
     }                                                                                                         \
-    sdpa_kernel<T, HD><<<grid, 128, smem, s>>>(qkv, out, n_groups, L, C, heads, gpb, tpg);                   \
+    launch_pdl(sdpa_kernel<T, HD>, dim3(grid), dim3(128), smem, s, qkv, out, n_groups, L, C, heads, gpb, tpg);                   \
   }
   if (hd == 16) SDPA_CASE(16)
   else if (hd == 32) SDPA_CASE(32)
@@ -531,6 +548,8 @@ namespace {
 template <typename T>
 __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /*[9][64]*/, T* __restrict__ out, long long total,
                                int H, int W, int rows, int dim, int lh, int lw) {
+  pdl_wait();
+  pdl_trigger();
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= total) return;
   const long long r = v >> 3;
@@ -554,6 +573,8 @@ __global__ void conv_in_kernel(const float* __restrict__ x, const float* __restr
 template <typename T>
 __global__ void outc_kernel(const T* __restrict__ x, int ld, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ eps,
                             long long total, int H, int W, int C, int rows, int dim, int lh, int lw) {
+  pdl_wait();
+  pdl_trigger();
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= total) return;
   const int d = (int)(v % dim);
@@ -573,6 +594,8 @@ __global__ void outc_kernel(const T* __restrict__ x, int ld, const float* __rest
 
 template <typename T>
 __global__ void to_nchw_kernel(const T* __restrict__ in, int ld, float* __restrict__ out, long long total, int HW, int C) {
+  pdl_wait();
+  pdl_trigger();
   const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (v >= total) return;
   const int p = (int)(v % HW);
@@ -584,17 +607,17 @@ __global__ void to_nchw_kernel(const T* __restrict__ in, int ld, float* __restri
 }  // namespace
 template <typename T> void launch_conv_in(const float* x, const float* w, T* out, int B, int H, int W, int rows, int dim, int lh, int lw, cudaStream_t s) {
   const long long total = (long long)B * H * W * 8;
-  conv_in_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(x, w, out, total, H, W, rows, dim, lh, lw);
+  launch_pdl(conv_in_kernel<T>, dim3(cdiv(total, 256)), dim3(256), 0, s, x, w, out, total, H, W, rows, dim, lh, lw);
   COUNT_LAUNCH();
 }
 template <typename T> void launch_outc(const T* x, int ld, const float* w, const float* bias, float* eps, int B, int H, int W, int C, int rows, int dim, int lh, int lw, cudaStream_t s) {
   const long long total = (long long)B * rows * dim;
-  outc_kernel<T><<<cdiv(total, 128), 128, 0, s>>>(x, ld, w, bias, eps, total, H, W, C, rows, dim, lh, lw);
+  launch_pdl(outc_kernel<T>, dim3(cdiv(total, 128)), dim3(128), 0, s, x, ld, w, bias, eps, total, H, W, C, rows, dim, lh, lw);
   COUNT_LAUNCH();
 }
 template <typename T> void launch_to_nchw(const T* in, int ld, float* out, int B, int HW, int C, cudaStream_t s) {
   const long long total = (long long)B * HW * C;
-  to_nchw_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(in, ld, out, total, HW, C);
+  launch_pdl(to_nchw_kernel<T>, dim3(cdiv(total, 256)), dim3(256), 0, s, in, ld, out, total, HW, C);
 }
 template void launch_conv_in<float>(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 template void launch_conv_in<bf16>(const float*, const float*, bf16*, int, int, int, int, int, int, int, cudaStream_t);
@@ -640,9 +663,12 @@ __device__ __forceinline__ float philox_normal(unsigned long long seed, unsigned
 }
 
 __global__ void step_kernel(StepArgs a) {
-  const long long total = (long long)a.B * a.n;
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
+  pdl_wait();
+  pdl_trigger();
+  const long long total = (long long)a.B_total * a.n;  // elements of the whole batch (noise / history strides)
+  const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= (long long)a.B * a.n) return;
+  const long long i = (long long)a.b0 * a.n + li;      // element inside the whole batch
   int step = a.step_host, use_philox = 0;
   const float* noise = a.noise;
   const float* inpaint = a.inpaint;
@@ -678,13 +704,25 @@ __global__ void step_kernel(StepArgs a) {
   a.x_out[i] = r;
   if (history) history[(size_t)(step + 1) * total + i] = r;
 }
-__global__ void advance_kernel(int* p, int d) { *p += d; }
-__global__ void set_int_kernel(int* p, int v) { *p = v; }
+__global__ void advance_kernel(int* p, int d) {
+  pdl_wait();
+  pdl_trigger(); *p += d; }
+__global__ void delay_kernel(long long cycles) {
+  pdl_wait();
+  pdl_trigger();
+  const long long t0 = clock64();
+  while (clock64() - t0 < cycles) {}
+}
+__global__ void set_int_kernel(int* p, int v) {
+  pdl_wait();
+  pdl_trigger(); *p = v; }
 
 // DDPMScheduler.add_noise + add_constraints (models/diffusion_ddpm.py:167-168)
 __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const long long* __restrict__ t,
                                  const float* __restrict__ sa, const float* __restrict__ sb, const float* __restrict__ inpaint,
                                  float* __restrict__ out, int n, int inpaint_elems, long long total) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const long long b = i / n;
@@ -696,15 +734,16 @@ __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __re
 }  // namespace
 void launch_step(const StepArgs& a, cudaStream_t s) {
   const long long total = (long long)a.B * a.n;
-  step_kernel<<<cdiv(total, 256), 256, 0, s>>>(a);
+  launch_pdl(step_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, a);
   COUNT_LAUNCH();
 }
-void launch_advance(int* step_ptr, int delta, cudaStream_t s) { advance_kernel<<<1, 1, 0, s>>>(step_ptr, delta); COUNT_LAUNCH(); }
-void launch_set_int(int* p, int v, cudaStream_t s) { set_int_kernel<<<1, 1, 0, s>>>(p, v); COUNT_LAUNCH(); }
+void launch_delay(long long cycles, cudaStream_t s) { launch_pdl(delay_kernel, dim3(1), dim3(1), 0, s, cycles); }
+void launch_advance(int* step_ptr, int delta, cudaStream_t s) { launch_pdl(advance_kernel, dim3(1), dim3(1), 0, s, step_ptr, delta); COUNT_LAUNCH(); }
+void launch_set_int(int* p, int v, cudaStream_t s) { launch_pdl(set_int_kernel, dim3(1), dim3(1), 0, s, p, v); COUNT_LAUNCH(); }
 void launch_add_noise(const float* x0, const float* noise, const long long* t, const float* sa, const float* sb, const float* inpaint,
                       float* out, int n, int inpaint_elems, int B, cudaStream_t s) {
   const long long total = (long long)B * n;
-  add_noise_kernel<<<cdiv(total, 256), 256, 0, s>>>(x0, noise, t, sa, sb, inpaint, out, n, inpaint_elems, total);
+  launch_pdl(add_noise_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, x0, noise, t, sa, sb, inpaint, out, n, inpaint_elems, total);
   COUNT_LAUNCH();
 }
 
@@ -716,6 +755,8 @@ void launch_add_noise(const float* x0, const float* noise, const long long* t, c
 namespace {
 __global__ void __launch_bounds__(256) temb_kernel(const long long* __restrict__ t_dev, const float* __restrict__ inv_freq,
                                                    const float* __restrict__ w_cat, const float* __restrict__ b_cat, float* __restrict__ out, int time_dim) {
+  pdl_wait();
+  pdl_trigger();
   extern __shared__ float pe[];  // [time_dim]
   const int row = blockIdx.x;
   const float t = (float)t_dev[row];
@@ -734,6 +775,8 @@ __global__ void __launch_bounds__(256) temb_kernel(const long long* __restrict__
 }
 // Mish (models/Unet_FiLmLayer.py:150): x * tanh(softplus(x)), softplus threshold 20 as torch
 __global__ void mish_kernel(const float* __restrict__ in, float* __restrict__ out, long long n) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float x = in[i];
@@ -742,11 +785,11 @@ __global__ void mish_kernel(const float* __restrict__ in, float* __restrict__ ou
 }
 }  // namespace
 void launch_temb(const long long* t_dev, int n_t, const float* inv_freq, const float* w_cat, const float* b_cat, float* out, int time_dim, cudaStream_t s) {
-  temb_kernel<<<n_t, 256, time_dim * sizeof(float), s>>>(t_dev, inv_freq, w_cat, b_cat, out, time_dim);
+  launch_pdl(temb_kernel, dim3(n_t), dim3(256), time_dim * sizeof(float), s, t_dev, inv_freq, w_cat, b_cat, out, time_dim);
   COUNT_LAUNCH();
 }
 void launch_mish(const float* in, float* out, long long n, cudaStream_t s) {
-  mish_kernel<<<cdiv(n, 256), 256, 0, s>>>(in, out, n);
+  launch_pdl(mish_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, in, out, n);
   COUNT_LAUNCH();
 }
 
@@ -763,6 +806,8 @@ namespace {
 __global__ void __launch_bounds__(256) enc_convs_kernel(const float* __restrict__ img, const float* __restrict__ w1, const float* __restrict__ b1,
                                                         const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
                                                         const float* __restrict__ b3, float* __restrict__ feat) {
+  pdl_wait();
+  pdl_trigger();
   __shared__ float s_in[3][8][97];    // [c][r][col+1], col -1 -> index 0
   __shared__ float s_c1[16][4][48];   // conv1 rows 4i..4i+3, cols 0..47
   __shared__ float s_c2[32][2][24];
@@ -820,6 +865,8 @@ __global__ void __launch_bounds__(256) enc_convs_kernel(const float* __restrict_
 // prepare_obs_cond_vectors (models/diffusion_ddpm.py:317-330): cat[pos(2), act(3), vel(2), img_feat(128)]
 __global__ void build_cond_kernel(const float* __restrict__ pos, const float* __restrict__ act, const float* __restrict__ vel,
                                   const float* __restrict__ feat, float* __restrict__ cond, long long total, int cond_dim) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int d = (int)(i % cond_dim);
@@ -834,12 +881,12 @@ __global__ void build_cond_kernel(const float* __restrict__ pos, const float* __
 }  // namespace
 void launch_enc_convs(const float* img, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
                       const float* b3, float* feat, int n, cudaStream_t s) {
-  enc_convs_kernel<<<n * 12, 256, 0, s>>>(img, w1, b1, w2, b2, w3, b3, feat);
+  launch_pdl(enc_convs_kernel, dim3(n * 12), dim3(256), 0, s, img, w1, b1, w2, b2, w3, b3, feat);
   COUNT_LAUNCH();
 }
 void launch_build_cond(const float* pos, const float* act, const float* vel, const float* feat, float* cond, int B, int T, int cond_dim, cudaStream_t s) {
   const long long total = (long long)B * T * cond_dim;
-  build_cond_kernel<<<cdiv(total, 256), 256, 0, s>>>(pos, act, vel, feat, cond, total, cond_dim);
+  launch_pdl(build_cond_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, pos, act, vel, feat, cond, total, cond_dim);
   COUNT_LAUNCH();
 }
 
@@ -848,6 +895,8 @@ void launch_build_cond(const float* pos, const float* act, const float* vel, con
 // =================================================================================================
 namespace {
 __global__ void pack_conv_f32_kernel(const float* __restrict__ oihw, float* __restrict__ out, int Cout, int Cin, int kk) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)Cout * Cin * kk;
   if (i >= total) return;
@@ -858,6 +907,8 @@ __global__ void pack_conv_f32_kernel(const float* __restrict__ oihw, float* __re
   out[i] = oihw[((size_t)o * Cin + c) * kk + tap];
 }
 __global__ void pack_conv_bf16_kernel(const float* __restrict__ oihw, bf16* __restrict__ out, int Cout, int Cin, int kk) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const long long total = (long long)Cout * Cin * kk;
   if (i >= total) return;
@@ -868,6 +919,8 @@ __global__ void pack_conv_bf16_kernel(const float* __restrict__ oihw, bf16* __re
   out[i] = __float2bfloat16_rn(oihw[((size_t)o * Cin + c) * kk + tap]);
 }
 __global__ void pack_linear_f32_kernel(const float* __restrict__ nk, float* __restrict__ out, int N, int K, int ld_out, int col_off) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (long long)N * K) return;
   const int n = (int)(i % N);
@@ -875,10 +928,14 @@ __global__ void pack_linear_f32_kernel(const float* __restrict__ nk, float* __re
   out[(size_t)k * ld_out + col_off + n] = nk[(size_t)n * K + k];
 }
 __global__ void cast_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, long long n) {
+  pdl_wait();
+  pdl_trigger();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) out[i] = __float2bfloat16_rn(in[i]);
 }
 __global__ void pack_enc_linear_kernel(const float* __restrict__ w, float* __restrict__ out) {
+  pdl_wait();
+  pdl_trigger();
   // w (128, 9216) with k = c*144 + p  ->  out[(p*64 + c)][128]
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 128LL * 9216) return;
@@ -890,18 +947,18 @@ __global__ void pack_enc_linear_kernel(const float* __restrict__ w, float* __res
 }  // namespace
 void launch_pack_conv_f32(const float* oihw, float* out, int Cout, int Cin, int k, cudaStream_t s) {
   const long long total = (long long)Cout * Cin * k * k;
-  pack_conv_f32_kernel<<<cdiv(total, 256), 256, 0, s>>>(oihw, out, Cout, Cin, k * k);
+  launch_pdl(pack_conv_f32_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, oihw, out, Cout, Cin, k * k);
 }
 void launch_pack_conv_bf16(const float* oihw, bf16* out, int Cout, int Cin, int k, cudaStream_t s) {
   const long long total = (long long)Cout * Cin * k * k;
-  pack_conv_bf16_kernel<<<cdiv(total, 256), 256, 0, s>>>(oihw, out, Cout, Cin, k * k);
+  launch_pdl(pack_conv_bf16_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, oihw, out, Cout, Cin, k * k);
 }
 void launch_pack_linear_f32(const float* nk, float* out, int N, int K, int ld_out, int col_off, cudaStream_t s) {
-  pack_linear_f32_kernel<<<cdiv((long long)N * K, 256), 256, 0, s>>>(nk, out, N, K, ld_out, col_off);
+  launch_pdl(pack_linear_f32_kernel, dim3(cdiv((long long)N * K, 256)), dim3(256), 0, s, nk, out, N, K, ld_out, col_off);
 }
 void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
-  cast_bf16_kernel<<<cdiv(n, 256), 256, 0, s>>>(in, out, n);
+  launch_pdl(cast_bf16_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, in, out, n);
 }
 void launch_pack_enc_linear(const float* w, float* out, cudaStream_t s) {
-  pack_enc_linear_kernel<<<cdiv(128LL * 9216, 256), 256, 0, s>>>(w, out);
+  launch_pdl(pack_enc_linear_kernel, dim3(cdiv(128LL * 9216, 256)), dim3(256), 0, s, w, out);
 }

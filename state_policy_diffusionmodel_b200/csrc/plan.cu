@@ -6,6 +6,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <functional>
@@ -114,6 +115,9 @@ struct spdm_plan {
   StepDyn* dyn = nullptr; StepDyn* dyn_host = nullptr;
   cudaStream_t own_stream = nullptr;  // graphs are captured and replayed here (the caller's stream may be the legacy stream)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
+  int split = 1;                       // sub-batches run concurrently per denoising step
+  cudaStream_t lane_stream[7] = {};
+  cudaEvent_t ev_fork = nullptr, ev_lane[7] = {};
   float* enc_feat = nullptr; int enc_chunk = 0;  // [enc_chunk][9216]
   float* enc_out = nullptr;                       // [Bcap*T][128]
 
@@ -126,6 +130,8 @@ struct spdm_plan {
   struct ProfRec { int cat; cudaEvent_t e0, e1; double flops, bytes; };
   bool prof_on = false;
   std::vector<ProfRec> prof;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
 
   // debug tap
   std::string tap_name; float* tap_out = nullptr; long long tap_count = -1;
@@ -353,6 +359,7 @@ struct FwdCtx {
   const int* step_ptr;
   const float* film;     // [B][1792] or null
   int B;
+  int b0;                // first sample of this sub-batch inside the plan's workspace (lanes run concurrently)
   cudaStream_t s;
 };
 
@@ -361,8 +368,13 @@ enum : int { PC_CONV3 = 0, PC_GEMM1, PC_APPLY, PC_STATS, PC_RESAMPLE, PC_LN, PC_
 template <typename F> void timed(spdm_plan* p, cudaStream_t s, int cat, double flops, double bytes, F&& f) {
   if (!p->prof_on) { f(); return; }
   spdm_plan::ProfRec r{cat, nullptr, nullptr, flops, bytes};
-  CUDA_OK(cudaEventCreate(&r.e0));
-  CUDA_OK(cudaEventCreate(&r.e1));
+  while (p->ev_pool.size() < p->ev_used + 2) {  // events are pooled: creation is far slower than a small kernel
+    cudaEvent_t e;
+    CUDA_OK(cudaEventCreate(&e));
+    p->ev_pool.push_back(e);
+  }
+  r.e0 = p->ev_pool[p->ev_used++];
+  r.e1 = p->ev_pool[p->ev_used++];
   CUDA_OK(cudaEventRecord(r.e0, s));
   f();
   CUDA_OK(cudaEventRecord(r.e1, s));
@@ -379,7 +391,16 @@ template <typename T> struct Fwd {
 
   Fwd(spdm_plan* p_, const FwdCtx& c_) : p(p_), c(c_) { Bpad = ((c.B + p->bm - 1) / p->bm) * p->bm; }
 
-  T* buf(void* v) { return reinterpret_cast<T*>(v); }
+  // workspace of this sub-batch: every buffer is [Bcap][hw(level)][capacity] -> offset by b0 whole samples
+  T* act(void* v, int level) const {
+    static const int cmax[4] = {128, 256, 512, 512};
+    return reinterpret_cast<T*>(v) + (size_t)c.b0 * p->levelH(level) * p->levelW(level) * cmax[level];
+  }
+  T* att(void* v, int level, int mult = 1) const {
+    static const int catt[4] = {64, 128, 256, 256};
+    return reinterpret_cast<T*>(v) + (size_t)c.b0 * p->levelH(level) * p->levelW(level) * catt[level] * mult;
+  }
+  float* stats() const { return p->stats + (size_t)c.b0 * SPDM_MAX_PARTIALS * 2; }
 
   void tap(const std::string& name, const T* ptr, int ld, int C, int level) {
     if (p->tap_out && p->tap_name == name) {
@@ -410,7 +431,7 @@ template <typename T> struct Fwd {
       const double bytes = ((double)c.B * H * W * (g.Cin + g.Cout) + (double)g.taps * g.Cin * g.Cout) * 2.0;
       int P = 1;
       timed(p, c.s, g.taps == 9 ? PC_CONV3 : PC_GEMM1, flops, bytes, [&] {
-        P = tc_gemm_launch(tc, reinterpret_cast<bf16*>(out), ld_out, p->stats, (flags & EPI_BIAS) ? g.bias : nullptr,
+        P = tc_gemm_launch(tc, reinterpret_cast<bf16*>(out), ld_out, stats(), (flags & EPI_BIAS) ? g.bias : nullptr,
                            reinterpret_cast<const bf16*>(resid), ld_res, flags, Bpad, c.s, vt, vt_lk);
       });
       REQUIRE(!(flags & EPI_STATS) || P <= SPDM_MAX_PARTIALS, "%s: too many GroupNorm partials (%d)", wname.c_str(), P);
@@ -426,7 +447,7 @@ template <typename T> struct Fwd {
       timed(p, c.s, g.taps == 9 ? PC_CONV3 : PC_GEMM1, flops, bytes, [&] { launch_gemm_simt<float, float>(a, c.s); });
       if (flags & EPI_STATS) {
         timed(p, c.s, PC_STATS, 0, (double)c.B * H * W * g.Cout * 4.0,
-              [&] { launch_stats<T>(out, p->stats, c.B, H * W, g.Cout, ld_out, c.s); });
+              [&] { launch_stats<T>(out, stats(), c.B, H * W, g.Cout, ld_out, c.s); });
         curP = 1;
       }
     }
@@ -435,7 +456,7 @@ template <typename T> struct Fwd {
   void apply(const std::string& norm, const T* raw, int ld_in, int C, int level, T* out, int ld_out, int act, const StageInfo* st) {
     NormW& n = p->norms[norm];
     ApplyArgs a{};
-    a.raw = raw; a.out = out; a.stats = p->stats; a.P = curP; a.gamma = n.g; a.beta = n.b;
+    a.raw = raw; a.out = out; a.stats = stats(); a.P = curP; a.gamma = n.g; a.beta = n.b;
     a.temb = nullptr; a.temb_mode = TEMB_NONE; a.film = nullptr;
     if (st) {
       a.temb = c.temb; a.temb_mode = c.temb_mode; a.temb_off = st->temb_off; a.step_ptr = c.step_ptr;
@@ -448,8 +469,8 @@ template <typename T> struct Fwd {
   // DoubleConvolution (models/Unet_FiLmLayer.py:85-115); `first_done`: raw already holds conv1's output
   void double_conv(const std::string& name, const T* in, int ld_in, int Cout, int level, T* out, int ld_out, const StageInfo* st,
                    bool first_done = false) {
-    T* raw = buf(p->raw[level]);
-    T* h = buf(p->hbuf[level]);
+    T* raw = act(p->raw[level], level);
+    T* h = act(p->hbuf[level], level);
     if (!first_done) gemm(name + ".first", in, ld_in, level, raw, Cout, EPI_STATS);
     tap(name + ".first", raw, Cout, Cout, level);
     apply(name + ".norm", raw, Cout, Cout, level, h, Cout, ACT_GELU, nullptr);
@@ -462,8 +483,8 @@ template <typename T> struct Fwd {
   void self_attention(const std::string& name, const T* x, int ld_x, int C, int level, T* out, int ld_out) {
     const int L = p->levelH(level) * p->levelW(level);
     const long long M = (long long)c.B * L;
-    T* ln = buf(p->a_ln[level]); T* qkv = buf(p->a_qkv[level]); T* att = buf(p->a_att[level]);
-    T* res = buf(p->a_res[level]); T* ff = buf(p->a_ff[level]);
+    T* ln = att(p->a_ln[level], level); T* qkv = att(p->a_qkv[level], level, 3); T* attn = att(p->a_att[level], level);
+    T* res = att(p->a_res[level], level); T* ff = att(p->a_ff[level], level);
     NormW& n1 = p->norms[name + ".ln"];
     NormW& n2 = p->norms[name + ".ff_self.0"];
     const double ln_bytes = 2.0 * M * C * sizeof(T);
@@ -472,26 +493,26 @@ template <typename T> struct Fwd {
     if constexpr (sizeof(T) == 2) tc_sdpa = sdpa_tc_supported(L, C, 4);
     if (tc_sdpa) {
       if constexpr (sizeof(T) == 2) {
-        SdpaTc*& sd = p->sdpa_cache[name];
+        SdpaTc*& sd = p->sdpa_cache[name + "|" + std::to_string(c.b0)];
         if (!sd) {
-          sd = sdpa_tc_create(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(p->a_vt[level]), C, L, 4,
+          sd = sdpa_tc_create(reinterpret_cast<const bf16*>(qkv), reinterpret_cast<const bf16*>(att(p->a_vt[level], level)), C, L, 4,
                               (long long)p->Bcap * L);
           REQUIRE(sd != nullptr, "%s: sdpa_tc_create failed", name.c_str());
         }
-        vt = reinterpret_cast<bf16*>(p->a_vt[level]);
+        vt = reinterpret_cast<bf16*>(att(p->a_vt[level], level));
         vt_lk = sdpa_tc_keys_per_tile(L);
         gemm(name + ".attention.in_proj_weight", ln, C, level, qkv, 3 * C, EPI_BIAS | EPI_VT);
         vt = nullptr;
         vt_lk = 0;
         const long long Mpad = (long long)Bpad * L;
         timed(p, c.s, PC_SDPA, 4.0 * M * L * C, 4.0 * M * C * sizeof(T),
-              [&] { sdpa_tc_launch(sd, reinterpret_cast<bf16*>(att), Mpad, c.s); });
+              [&] { sdpa_tc_launch(sd, reinterpret_cast<bf16*>(attn), Mpad, c.s); });
       }
     } else {
       gemm(name + ".attention.in_proj_weight", ln, C, level, qkv, 3 * C, EPI_BIAS);
-      timed(p, c.s, PC_SDPA, 4.0 * M * L * C, 4.0 * M * C * sizeof(T), [&] { launch_sdpa<T>(qkv, att, c.B, L, C, 4, c.s); });
+      timed(p, c.s, PC_SDPA, 4.0 * M * L * C, 4.0 * M * C * sizeof(T), [&] { launch_sdpa<T>(qkv, attn, c.B, L, C, 4, c.s); });
     }
-    gemm(name + ".attention.out_proj.weight", att, C, level, res, C, EPI_BIAS | EPI_RESID, x, ld_x);
+    gemm(name + ".attention.out_proj.weight", attn, C, level, res, C, EPI_BIAS | EPI_RESID, x, ld_x);
     timed(p, c.s, PC_LN, 0, ln_bytes, [&] { launch_layernorm<T>(res, C, ln, C, n2.g, n2.b, M, C, c.s); });
     gemm(name + ".ff_self.1.weight", ln, C, level, ff, C, EPI_BIAS | EPI_GELU);
     gemm(name + ".ff_self.3.weight", ff, C, level, out, ld_out, EPI_BIAS | EPI_RESID, res, C);
@@ -500,13 +521,13 @@ template <typename T> struct Fwd {
   // UNet_Film.forward (models/Unet_FiLmLayer.py:277-312) / UNet_Film_noAttention.forward
   void run() {
     const int rows = p->cfg.rows, dim = p->cfg.dim;
-    T* cat3 = buf(p->cat[0]); T* cat2 = buf(p->cat[1]); T* cat1 = buf(p->cat[2]);
+    T* cat3 = act(p->cat[0], 0); T* cat2 = act(p->cat[1], 1); T* cat1 = act(p->cat[2], 2);
     // ---- inc ----
     const double hw0 = (double)p->H0 * p->W0;
     timed(p, c.s, PC_IO, 2.0 * 9 * 64 * hw0 * c.B, c.B * hw0 * 64 * sizeof(T),
-          [&] { launch_conv_in<T>(c.x, p->w_in, buf(p->raw[0]), c.B, p->H0, p->W0, rows, dim, p->lh, p->lw, c.s); });
+          [&] { launch_conv_in<T>(c.x, p->w_in, act(p->raw[0], 0), c.B, p->H0, p->W0, rows, dim, p->lh, p->lw, c.s); });
     timed(p, c.s, PC_STATS, 0, c.B * hw0 * 64 * sizeof(T),
-          [&] { launch_stats<T>(buf(p->raw[0]), p->stats, c.B, p->H0 * p->W0, 64, 64, c.s); });
+          [&] { launch_stats<T>(act(p->raw[0], 0), stats(), c.B, p->H0 * p->W0, 64, 64, c.s); });
     curP = 1;
     double_conv("inc", nullptr, 0, 64, 0, cat3 + 64, 128, nullptr, true);  // x1 -> skip slot of up3
     tap("x1", cat3 + 64, 128, 64, 0);
@@ -517,11 +538,11 @@ template <typename T> struct Fwd {
     const DownCfg downs[3] = {
         {0, "sa1", cat3 + 64, 128, 1, cat2 + 128, 256, "x2"},
         {1, "sa2", cat2 + 128, 256, 2, cat1 + 256, 512, "x3"},
-        {2, "sa3", cat1 + 256, 512, 3, buf(p->bbuf[3]), 256, "x4"}};
+        {2, "sa3", cat1 + 256, 512, 3, act(p->bbuf[3], 3), 256, "x4"}};
     for (const DownCfg& d : downs) {
       const StageInfo& st = kStages[d.stage];
       const int l = d.level;
-      T* a = buf(p->abuf[l]); T* b = buf(p->bbuf[l]);
+      T* a = act(p->abuf[l], l); T* b = act(p->bbuf[l], l);
       timed(p, c.s, PC_RESAMPLE, 0, 5.0 * c.B * p->levelH(l) * p->levelW(l) * st.cin * sizeof(T),
             [&] { launch_pool<T>(d.in, d.ld_in, a, st.cin, c.B, p->levelH(l), p->levelW(l), st.cin, c.s); });
       double_conv(std::string(st.name) + ".doubleConv1", a, st.cin, st.cin, l, b, st.cin, nullptr);
@@ -537,7 +558,7 @@ template <typename T> struct Fwd {
       tap(d.tapname, d.dest, d.ld_dest, st.cout, l);
     }
     // ---- bottleneck ----
-    T* a3 = buf(p->abuf[3]); T* b3 = buf(p->bbuf[3]);
+    T* a3 = act(p->abuf[3], 3); T* b3 = act(p->bbuf[3], 3);
     double_conv("bot1", b3, 256, 512, 3, a3, 512, nullptr);
     tap("bot1", a3, 512, 512, 3);
     double_conv("bot2", a3, 512, 512, 3, b3, 512, nullptr);
@@ -549,11 +570,11 @@ template <typename T> struct Fwd {
     // ---- up path ----
     struct UpCfg { int stage; const char* sa; const T* low; int c_low; int level; T* catbuf; const char* tapname; };
     const UpCfg ups[3] = {
-        {3, "sa4", a3, 256, 2, cat1, "u1"}, {4, "sa5", buf(p->bbuf[2]), 128, 1, cat2, "u2"}, {5, "sa6", buf(p->bbuf[1]), 64, 0, cat3, "u3"}};
+        {3, "sa4", a3, 256, 2, cat1, "u1"}, {4, "sa5", act(p->bbuf[2], 2), 128, 1, cat2, "u2"}, {5, "sa6", act(p->bbuf[1], 1), 64, 0, cat3, "u3"}};
     for (const UpCfg& u : ups) {
       const StageInfo& st = kStages[u.stage];
       const int l = u.level;
-      T* a = buf(p->abuf[l]); T* b = buf(p->bbuf[l]);
+      T* a = act(p->abuf[l], l); T* b = act(p->bbuf[l], l);
       timed(p, c.s, PC_RESAMPLE, 0, 1.25 * c.B * p->levelH(l) * p->levelW(l) * u.c_low * sizeof(T), [&] {
         launch_upsample<T>(u.low, u.c_low, u.catbuf, st.cin, c.B, p->levelH(l + 1), p->levelW(l + 1), u.c_low, c.s);
       });
@@ -572,7 +593,7 @@ template <typename T> struct Fwd {
     }
     // ---- outc + unpad ----
     timed(p, c.s, PC_IO, 2.0 * 64 * rows * dim * c.B, c.B * hw0 * 64 * sizeof(T), [&] {
-      launch_outc<T>(buf(p->bbuf[0]), 64, p->w_outc, p->b_outc, c.out, c.B, p->H0, p->W0, 64, rows, dim, p->lh, p->lw, c.s);
+      launch_outc<T>(act(p->bbuf[0], 0), 64, p->w_outc, p->b_outc, c.out, c.B, p->H0, p->W0, 64, rows, dim, p->lh, p->lw, c.s);
     });
   }
 };
@@ -603,15 +624,43 @@ void compute_film(spdm_plan* p, int B, cudaStream_t s) {
   p->have_cond = true;
 }
 
-void one_step(spdm_plan* p, int B, bool use_film, cudaStream_t s) {
+void one_lane(spdm_plan* p, int b0, int Bsub, int B, bool use_film, cudaStream_t s) {
+  const size_t n = p->n_elems();
   FwdCtx c{};
-  c.x = p->xt; c.out = p->eps; c.temb = p->temb_table; c.temb_mode = TEMB_STEP; c.step_ptr = &p->dyn->step;
-  c.film = use_film ? p->film : nullptr; c.B = B; c.s = s;
+  c.x = p->xt + (size_t)b0 * n; c.out = p->eps + (size_t)b0 * n; c.temb = p->temb_table; c.temb_mode = TEMB_STEP;
+  c.step_ptr = &p->dyn->step;
+  c.film = use_film ? p->film + (size_t)b0 * SPDM_FILM_WIDTH : nullptr; c.B = Bsub; c.b0 = b0; c.s = s;
   run_forward(p, c);
   StepArgs a{};
   a.x = p->xt; a.eps = p->eps; a.x_out = p->xt; a.coef = p->coef; a.dyn = p->dyn; a.n = p->n_elems();
-  a.inpaint_elems = p->cfg.inpaint_rows * p->cfg.dim; a.B = B;
-  timed(p, s, PC_STEP, 0, 4.0 * B * p->n_elems() * sizeof(float), [&] { launch_step(a, s); });
+  a.inpaint_elems = p->cfg.inpaint_rows * p->cfg.dim; a.B = Bsub; a.b0 = b0; a.B_total = B;
+  timed(p, s, PC_STEP, 0, 4.0 * Bsub * p->n_elems() * sizeof(float), [&] { launch_step(a, s); });
+}
+
+// One denoising step for B trajectories.  With split > 1 the batch is cut into sub-batches ("lanes") that run the
+// whole U-Net concurrently on separate streams (forked from and joined back into `s`, also under stream capture, where
+// they become parallel graph branches): the many small-grid kernels of the deep levels then overlap instead of
+// leaving most SMs idle.
+void one_step(spdm_plan* p, int B, bool use_film, cudaStream_t s) {
+  int split = p->split;
+  int chunk = (B + split - 1) / split;
+  chunk = ((chunk + p->bm - 1) / p->bm) * p->bm;
+  if (split <= 1 || chunk >= B) {
+    one_lane(p, 0, B, B, use_film, s);
+  } else {
+    CUDA_OK(cudaEventRecord(p->ev_fork, s));
+    int lane = 0;
+    for (int b0 = 0; b0 < B; b0 += chunk, ++lane) {
+      const int Bsub = B - b0 < chunk ? B - b0 : chunk;
+      cudaStream_t ls = lane == 0 ? s : p->lane_stream[lane - 1];
+      if (lane > 0) CUDA_OK(cudaStreamWaitEvent(ls, p->ev_fork, 0));
+      one_lane(p, b0, Bsub, B, use_film, ls);
+      if (lane > 0) {
+        CUDA_OK(cudaEventRecord(p->ev_lane[lane - 1], ls));
+        CUDA_OK(cudaStreamWaitEvent(s, p->ev_lane[lane - 1], 0));
+      }
+    }
+  }
   launch_advance(&p->dyn->step, 1, s);
 }
 
@@ -634,6 +683,7 @@ static void check_async(const char* what) {
 extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
   API_BEGIN
   REQUIRE(out && cfg, "null argument");
+  if (const char* e = getenv("SPDM_PDL")) g_spdm_pdl = atoi(e) != 0;  // A/B switch for programmatic dependent launch
   REQUIRE(cfg->rows > 0 && cfg->dim > 0 && cfg->batch_max > 0, "rows/dim/batch_max must be positive");
   REQUIRE(cfg->time_dim > 0 && cfg->time_dim % 2 == 0 && cfg->time_dim <= 4096, "bad time_dim");
   REQUIRE(cfg->precision == SPDM_PRECISION_FP32 || cfg->precision == SPDM_PRECISION_BF16, "bad precision");
@@ -683,6 +733,15 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
     CUDA_OK(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
+    p->split = (cfg->flags >> 8) & 0xF;
+    if (const char* e = getenv("SPDM_SPLIT")) p->split = atoi(e);
+    if (p->split < 1) p->split = 1;
+    if (p->split > 8) p->split = 8;
+    CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+    for (int i = 0; i < 7; ++i) {
+      CUDA_OK(cudaStreamCreateWithFlags(&p->lane_stream[i], cudaStreamNonBlocking));
+      CUDA_OK(cudaEventCreateWithFlags(&p->ev_lane[i], cudaEventDisableTiming));
+    }
   } catch (...) {
     for (void* q : p->allocs) cudaFree(q);
     delete p;
@@ -702,11 +761,17 @@ extern "C" int spdm_plan_destroy(spdm_plan* p) {
   }
   for (auto& kv : p->tc_cache) tc_gemm_destroy(kv.second);
   for (auto& kv : p->sdpa_cache) sdpa_tc_destroy(kv.second);
+  for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   for (void* q : p->allocs) cudaFree(q);
   if (p->dyn_host) cudaFreeHost(p->dyn_host);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   if (p->ev_in) cudaEventDestroy(p->ev_in);
   if (p->ev_out) cudaEventDestroy(p->ev_out);
+  if (p->ev_fork) cudaEventDestroy(p->ev_fork);
+  for (int i = 0; i < 7; ++i) {
+    if (p->lane_stream[i]) cudaStreamDestroy(p->lane_stream[i]);
+    if (p->ev_lane[i]) cudaEventDestroy(p->ev_lane[i]);
+  }
   delete p;
   return 0;
 }
@@ -871,7 +936,7 @@ extern "C" int spdm_step(spdm_plan* p, const float* x, const float* eps, const f
   REQUIRE(B > 0, "bad B");
   StepArgs a{};
   a.x = x; a.eps = eps; a.x_out = x_out; a.coef = p->coef; a.dyn = nullptr; a.noise = noise;
-  a.inpaint = p->cfg.inpaint_rows > 0 ? inpaint : nullptr; a.step_host = step;
+  a.inpaint = p->cfg.inpaint_rows > 0 ? inpaint : nullptr; a.step_host = step; a.b0 = 0; a.B_total = B;
   a.n = p->n_elems(); a.inpaint_elems = p->cfg.inpaint_rows * p->cfg.dim; a.B = B;
   launch_step(a, (cudaStream_t)stream);
   check_async("step");
@@ -984,10 +1049,20 @@ extern "C" int spdm_profile_step(spdm_plan* p, int32_t B, int32_t reps, double* 
   CUDA_OK(cudaMemcpyAsync(p->dyn, p->dyn_host, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
   one_step(p, B, use_film, s);  // warm-up (tensor maps, attributes)
   for (int i = 0; i < SPDM_PROFILE_CLASSES * 4; ++i) out[i] = 0.0;
+  {  // size the event pool before timing
+    p->prof_on = true; p->prof.clear(); p->ev_used = 0;
+    try { one_step(p, B, use_film, s); } catch (...) { p->prof_on = false; throw; }
+    p->prof_on = false;
+    CUDA_OK(cudaStreamSynchronize(s));
+  }
   for (int r = 0; r < reps; ++r) {
     CUDA_OK(cudaMemcpyAsync(p->dyn, p->dyn_host, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
+    // a ~3 ms spin kernel lets the host enqueue the whole step ahead of the GPU, so the event intervals are
+    // back-to-back kernel durations and not host launch latency
+    launch_delay(6000000LL, s);
     p->prof_on = true;
     p->prof.clear();
+    p->ev_used = 0;
     try { one_step(p, B, use_film, s); } catch (...) { p->prof_on = false; throw; }
     p->prof_on = false;
     CUDA_OK(cudaStreamSynchronize(s));
@@ -998,8 +1073,6 @@ extern "C" int spdm_profile_step(spdm_plan* p, int32_t B, int32_t reps, double* 
       out[rec.cat * 4 + 1] += 1.0 / reps;
       out[rec.cat * 4 + 2] += rec.flops / reps;
       out[rec.cat * 4 + 3] += rec.bytes / reps;
-      cudaEventDestroy(rec.e0);
-      cudaEventDestroy(rec.e1);
     }
     p->prof.clear();
   }

@@ -60,6 +60,8 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
+  pdl_wait();
+  pdl_trigger();
 
   if (tid == 0) {
     mbar_expect_tx(&bar_load, SQ + SK + SVT);
@@ -252,11 +254,11 @@ void sdpa_tc_launch(const SdpaTc* g, bf16* out, long long M, cudaStream_t s) {
     constexpr int smem = 16384 + 128 * 128 + 2 * 8192 + 2 * 16384 + 1024;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(sdpa_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    sdpa_tc_kernel<128><<<grid, 128, smem, s>>>(g->map_qkv, g->map_vt, p);
+    launch_pdl(sdpa_tc_kernel<128>, dim3(grid), dim3(128), smem, s, g->map_qkv, g->map_vt, p);
   } else {
     constexpr int smem = 16384 + 256 * 128 + 4 * 8192 + 4 * 16384 + 1024;
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(sdpa_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    sdpa_tc_kernel<256><<<grid, 128, smem, s>>>(g->map_qkv, g->map_vt, p);
+    launch_pdl(sdpa_tc_kernel<256>, dim3(grid), dim3(128), smem, s, g->map_qkv, g->map_vt, p);
   }
 }

@@ -130,13 +130,15 @@ class Diffusion_DDPM(_Base):
     # ------------------------------------------------------------------------------------------
     # engine plumbing
     # ------------------------------------------------------------------------------------------
-    def configure(self, precision=None, graph_steps=None, batch_max=None):
+    def configure(self, precision=None, graph_steps=None, batch_max=None, split=None):
         if precision is not None:
             self.precision = precision
         if graph_steps is not None:
             self.graph_steps = int(graph_steps)
         if batch_max is not None:
             self.batch_max = int(batch_max)
+        if split is not None:
+            self.noise_estimator.split = int(split)
         return self
 
     def _plan(self, B=1):

@@ -30,7 +30,7 @@ def _f32c(t, device):
 
 class DenoisePlan:
     def __init__(self, attention=True, precision="bf16", batch_max=1, rows=31, dim=5, obs_horizon=10, cond_dim=135,
-                 inpaint_rows=1, time_dim=256, device=None, graph_steps=1, scheduler_only=False):
+                 inpaint_rows=1, time_dim=256, device=None, graph_steps=1, scheduler_only=False, split=1):
         if not torch.cuda.is_available():
             raise RuntimeError("spdm: no CUDA device — the B200 denoising path has no CPU fallback")
         self.lib = _lib.load()
@@ -43,7 +43,7 @@ class DenoisePlan:
             batch_max=int(batch_max), rows=int(rows), dim=int(dim), obs_horizon=int(obs_horizon),
             cond_dim=int(cond_dim or 0), inpaint_rows=int(inpaint_rows), time_dim=int(time_dim),
             device=self.device.index or 0, graph_steps=int(graph_steps),
-            flags=_lib.FLAG_SCHEDULER_ONLY if scheduler_only else 0)
+            flags=(_lib.FLAG_SCHEDULER_ONLY if scheduler_only else 0) | ((int(split) & 0xF) << 8))
         self.cfg = cfg
         self.attention, self.precision = attention, precision
         self.batch_max, self.rows, self.dim = int(batch_max), int(rows), int(dim)

@@ -96,6 +96,7 @@ class _UNetBase(nn.Module):
         # B200 execution options (not part of the state_dict)
         self.precision = "bf16"   # "bf16": tcgen05 implicit-GEMM path; "fp32": CUDA-core parity path
         self.batch_max = 0        # 0 = grow on demand
+        self.split = 1            # sub-batches run concurrently inside the graphed sampling loop
         self._plan = None
         self._plan_key = None
         self._weights_tag = None
@@ -141,7 +142,7 @@ class _UNetBase(nn.Module):
                 T, cd = old.obs_horizon, old.cond_dim
         inpaint_rows = 0 if inpaint_rows is None else int(inpaint_rows)
         graph_steps = 1 if graph_steps is None else int(graph_steps)
-        key = (self.precision, rows, dim, T, cd, inpaint_rows, graph_steps, str(dev))
+        key = (self.precision, rows, dim, T, cd, inpaint_rows, graph_steps, str(dev), self.split)
         if old is None or self._plan_key != key or old.batch_max < B:
             cap = max(int(B), self.batch_max)
             if old is not None:
@@ -150,7 +151,7 @@ class _UNetBase(nn.Module):
                 old.close()
             self._plan = DenoisePlan(attention=self._attention, precision=self.precision, batch_max=cap, rows=rows, dim=dim,
                                      obs_horizon=T, cond_dim=cd, inpaint_rows=inpaint_rows, time_dim=self.time_dim, device=dev,
-                                     graph_steps=graph_steps)
+                                     graph_steps=graph_steps, split=self.split)
             self._plan_key = key
             self._weights_tag = None
         tag = self._tag()
