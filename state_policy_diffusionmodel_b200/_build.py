@@ -10,7 +10,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libspdm.so")
-SOURCES = ["kernels.cu", "conv_tc.cu", "sdpa_tc.cu", "plan.cu"]
+SOURCES = ["kernels.cu", "conv_tc.cu", "sdpa_tc.cu", "attn_tc.cu", "plan.cu"]
 HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_ptx.cuh"), os.path.join(os.path.dirname(HERE), "include", "spdm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

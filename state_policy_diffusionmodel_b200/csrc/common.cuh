@@ -195,3 +195,11 @@ int sdpa_tc_keys_per_tile(int L);
 SdpaTc* sdpa_tc_create(const bf16* qkv, const bf16* vt, int C, int L, int heads, long long Mcap);
 void sdpa_tc_destroy(SdpaTc* g);
 void sdpa_tc_launch(const SdpaTc* g, bf16* out, long long M, cudaStream_t s);  // out bf16 [M][C], M % 128 == 0
+
+// fused SelfAttention tail (attn_tc.cu): out = FF(LN(out_proj(att) + x)) + (out_proj(att) + x) ------------------
+struct AttnTail;
+bool attn_tail_supported(int C);
+AttnTail* attn_tail_create(const bf16* att, long long Mcap, int C, const bf16* wo, const bf16* w1, const bf16* w2, const float* bo,
+                           const float* b1, const float* b2, const float* ln_g, const float* ln_b);
+void attn_tail_destroy(AttnTail* g);
+void attn_tail_launch(const AttnTail* g, const bf16* x, int ld_x, bf16* out, int ld_out, long long M, cudaStream_t s);

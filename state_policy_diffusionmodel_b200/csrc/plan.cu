@@ -100,6 +100,7 @@ struct spdm_plan {
   void *raw[4] = {}, *hbuf[4] = {}, *abuf[4] = {}, *bbuf[4] = {}, *cat[3] = {};
   void *a_ln[4] = {}, *a_qkv[4] = {}, *a_att[4] = {}, *a_res[4] = {}, *a_ff[4] = {}, *a_vt[4] = {};
   std::map<std::string, SdpaTc*> sdpa_cache;
+  std::map<std::string, AttnTail*> tail_cache;
   float* stats = nullptr;   // [Bcap][SPDM_MAX_PARTIALS][2]
   float* film = nullptr;    // [Bcap][1792]
   float* cond = nullptr;    // [Bcap][G]
@@ -512,6 +513,24 @@ template <typename T> struct Fwd {
       gemm(name + ".attention.in_proj_weight", ln, C, level, qkv, 3 * C, EPI_BIAS);
       timed(p, c.s, PC_SDPA, 4.0 * M * L * C, 4.0 * M * C * sizeof(T), [&] { launch_sdpa<T>(qkv, attn, c.B, L, C, 4, c.s); });
     }
+    if constexpr (sizeof(T) == 2) {
+      if (attn_tail_supported(C) && !getenv("SPDM_NO_ATTN_TAIL")) {
+        AttnTail*& tl = p->tail_cache[name + "|" + std::to_string(c.b0)];
+        if (!tl) {
+          GemmW& wo = p->gemms[name + ".attention.out_proj.weight"];
+          GemmW& w1 = p->gemms[name + ".ff_self.1.weight"];
+          GemmW& w2 = p->gemms[name + ".ff_self.3.weight"];
+          tl = attn_tail_create(reinterpret_cast<const bf16*>(attn), (long long)p->Bcap * L, C, wo.w16, w1.w16, w2.w16, wo.bias, w1.bias,
+                                w2.bias, n2.g, n2.b);
+          REQUIRE(tl != nullptr, "%s: attn_tail_create failed", name.c_str());
+        }
+        const long long Mpad = (long long)Bpad * L;
+        timed(p, c.s, PC_GEMM1, 6.0 * M * C * C, (4.0 * M * C + 3.0 * C * C) * 2.0, [&] {
+          attn_tail_launch(tl, reinterpret_cast<const bf16*>(x), ld_x, reinterpret_cast<bf16*>(out), ld_out, Mpad, c.s);
+        });
+        return;
+      }
+    }
     gemm(name + ".attention.out_proj.weight", attn, C, level, res, C, EPI_BIAS | EPI_RESID, x, ld_x);
     timed(p, c.s, PC_LN, 0, ln_bytes, [&] { launch_layernorm<T>(res, C, ln, C, n2.g, n2.b, M, C, c.s); });
     gemm(name + ".ff_self.1.weight", ln, C, level, ff, C, EPI_BIAS | EPI_GELU);
@@ -762,6 +781,7 @@ extern "C" int spdm_plan_destroy(spdm_plan* p) {
   for (auto& kv : p->tc_cache) tc_gemm_destroy(kv.second);
   for (auto& kv : p->sdpa_cache) sdpa_tc_destroy(kv.second);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
+  for (auto& kv : p->tail_cache) attn_tail_destroy(kv.second);
   for (void* q : p->allocs) cudaFree(q);
   if (p->dyn_host) cudaFreeHost(p->dyn_host);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
