@@ -279,6 +279,10 @@ def main():
     total_B = B * world
     value = total_B * args.steps / (ms / 1000.0)
 
+    # ---- split of a step: conditioning encode vs. the graphed denoising loop --------------------------------------
+    ms_enc = timed(lambda i: plan.encode_cond(devb["image"], devb["position"], devb["action"], devb["velocity"]), args.steps)
+    ms_loop = timed(lambda i: plan.sample(x_T, inpaint=inpaint, seed=i), args.steps)
+
     # ---- e2e through the public API with host buffers -----------------------------------------------------------
     for i in range(2):
         step_e2e(i)
@@ -318,7 +322,9 @@ def main():
             "dtype": args.precision, "data": "synthetic", "config": config_dict(args, total_B),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / args.steps, 3)},
-            "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roofline}
+            "gpu_launches": int(launches), "clocks": sampler.result(), "roofline": roofline,
+            "step_breakdown_ms": {"conditioning_encode": round(ms_enc / args.steps, 3), "denoising_loop": round(ms_loop / args.steps, 3),
+                                  "per_denoise_step": round(ms_loop / args.steps / K, 4)}}
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, cores, sample = cpu_oracle_rate(model.noise_estimator.state_dict(), model.vision_encoder.state_dict(), args,

@@ -159,7 +159,10 @@ void launch_set_int(int* p, int v, cudaStream_t s);
 void launch_delay(long long cycles, cudaStream_t s);  // spin kernel (profiling: lets the host run ahead)
 void launch_temb(const long long* t_dev, int n_t, const float* inv_freq, const float* w_cat, const float* b_cat, float* out, int time_dim, cudaStream_t s);
 void launch_mish(const float* in, float* out, long long n, cudaStream_t s);
-void launch_enc_convs(const float* img, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3, const float* b3, float* feat, int n, cudaStream_t s);
+// w2t / w3t: conv weights transposed to [Cin*4][Cout]; feat: [n][9216] in (pixel, channel) order, fp32 or bf16
+template <typename TO> void launch_enc_convs(const float* img, const float* w1, const float* b1, const float* w2t, const float* b2, const float* w3t, const float* b3, TO* feat, int n, cudaStream_t s);
+void launch_cast_f32(const bf16* in, float* out, long long n, cudaStream_t s);
+void launch_pack_enc_linear_bf16(const float* w, bf16* out, cudaStream_t s);  // (128, 9216 chw) -> bf16 [128][9216 hwc]
 void launch_build_cond(const float* pos, const float* act, const float* vel, const float* feat, float* cond, int B, int T, int cond_dim, cudaStream_t s);
 void launch_add_noise(const float* x0, const float* noise, const long long* t, const float* sa, const float* sb, const float* inpaint, float* out, int n, int inpaint_elems, int B, cudaStream_t s);
 // weight repack (fp32 PyTorch layout -> kernel layout)

@@ -803,63 +803,111 @@ void launch_mish(const float* in, float* out, long long n, cudaStream_t s) {
 // Output feat[frame][(i*12+j)*64 + c]  (HWC order; the Linear weight is repacked to match).
 // =================================================================================================
 namespace {
+// One block per frame; the three layers of one 12-pixel output row run out of shared memory, weights staged once per
+// block in [k][channel] order so that a warp (32 consecutive channels of one position) reads them conflict-free while
+// the activation is a broadcast.  w2t = [16*4][32], w3t = [32*4][64] (transposed at load time), w1 = (16,3,2,2).
+template <typename TO>
 __global__ void __launch_bounds__(256) enc_convs_kernel(const float* __restrict__ img, const float* __restrict__ w1, const float* __restrict__ b1,
-                                                        const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
-                                                        const float* __restrict__ b3, float* __restrict__ feat) {
+                                                        const float* __restrict__ w2t, const float* __restrict__ b2, const float* __restrict__ w3t,
+                                                        const float* __restrict__ b3, TO* __restrict__ feat) {
+  extern __shared__ float es[];
+  float* w3s = es;                 // 128*64
+  float* w2s = w3s + 128 * 64;     // 64*32
+  float* w1s = w2s + 64 * 32;      // 12*16
+  float* s_in = w1s + 12 * 16;     // [3][8][97]
+  float* s_c1 = s_in + 3 * 8 * 97; // [16][4][48]
+  float* s_c2 = s_c1 + 16 * 4 * 48;// [32][2][24]
+  const int tid = threadIdx.x;
+  // weights are constants: stage them before waiting on the previous kernel
+  for (int e = tid; e < 128 * 64; e += 256) w3s[e] = __ldg(w3t + e);
+  for (int e = tid; e < 64 * 32; e += 256) w2s[e] = __ldg(w2t + e);
+  for (int e = tid; e < 12 * 16; e += 256) w1s[e] = __ldg(w1 + (e % 16) * 12 + e / 16);
   pdl_wait();
   pdl_trigger();
-  __shared__ float s_in[3][8][97];    // [c][r][col+1], col -1 -> index 0
-  __shared__ float s_c1[16][4][48];   // conv1 rows 4i..4i+3, cols 0..47
-  __shared__ float s_c2[32][2][24];
-  const int frame = blockIdx.x / 12, i = blockIdx.x % 12;
+  const int frame = blockIdx.x;
   const float* im = img + (size_t)frame * 3 * 96 * 96;
-  for (int e = threadIdx.x; e < 3 * 8 * 97; e += blockDim.x) {
-    const int col = e % 97 - 1;
-    const int r = (e / 97) % 8;
-    const int c = e / (97 * 8);
-    const int gr = 8 * i - 1 + r;
-    float v = 0.f;
-    if (gr >= 0 && gr < 96 && col >= 0 && col < 96) v = im[((size_t)c * 96 + gr) * 96 + col];
-    s_in[c][r][col + 1] = v;
+  const int ch1 = tid & 15, ch2 = tid & 31, ch3 = tid & 63;
+  const float bias1 = __ldg(b1 + ch1), bias2 = __ldg(b2 + ch2), bias3 = __ldg(b3 + ch3);
+  for (int i = 0; i < 12; ++i) {
+    __syncthreads();
+    for (int e = tid; e < 3 * 8 * 97; e += 256) {
+      const int col = e % 97 - 1;
+      const int r = (e / 97) % 8;
+      const int c = e / (97 * 8);
+      const int gr = 8 * i - 1 + r;
+      float v = 0.f;
+      if (gr >= 0 && gr < 96 && col >= 0 && col < 96) v = im[((size_t)c * 96 + gr) * 96 + col];
+      s_in[e] = v;
+    }
+    __syncthreads();
+    // conv1: (ch1, pos) pos = tid/16 + 16k, k < 12  -> rr = pos/48, cc = pos%48
+#pragma unroll 4
+    for (int k = 0; k < 12; ++k) {
+      const int pos = (tid >> 4) + 16 * k;
+      const int rr = pos / 48, cc = pos - rr * 48;
+      float acc = bias1;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk)
+          acc = fmaf(s_in[(c * 8 + 2 * rr + (kk >> 1)) * 97 + 2 * cc + (kk & 1)], w1s[(c * 4 + kk) * 16 + ch1], acc);
+      s_c1[(ch1 * 4 + rr) * 48 + cc] = fmaxf(acc, 0.f);
+    }
+    __syncthreads();
+    // conv2: (ch2, pos) pos = tid/32 + 8k, k < 6 -> rr = pos/24, cc = pos%24
+    {
+      float acc[6];
+      int off[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int pos = (tid >> 5) + 8 * k;
+        const int rr = pos / 24, cc = pos - rr * 24;
+        acc[k] = bias2;
+        off[k] = (2 * rr) * 48 + 2 * cc;
+      }
+      for (int c = 0; c < 16; ++c) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float w = w2s[(c * 4 + kk) * 32 + ch2];
+          const int o = c * 4 * 48 + (kk >> 1) * 48 + (kk & 1);
+#pragma unroll
+          for (int k = 0; k < 6; ++k) acc[k] = fmaf(s_c1[o + off[k]], w, acc[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        const int pos = (tid >> 5) + 8 * k;
+        const int rr = pos / 24, cc = pos - rr * 24;
+        s_c2[(ch2 * 2 + rr) * 24 + cc] = fmaxf(acc[k], 0.f);
+      }
+    }
+    __syncthreads();
+    // conv3: (ch3, j) j = tid/64 + 4k, k < 3
+    {
+      float acc[3] = {bias3, bias3, bias3};
+      for (int c = 0; c < 32; ++c) {
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          const float w = w3s[(c * 4 + kk) * 64 + ch3];
+          const int o = (c * 2 + (kk >> 1)) * 24 + (kk & 1);
+#pragma unroll
+          for (int k = 0; k < 3; ++k) acc[k] = fmaf(s_c2[o + 2 * ((tid >> 6) + 4 * k)], w, acc[k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const int j = (tid >> 6) + 4 * k;
+        feat[(size_t)frame * 9216 + (i * 12 + j) * 64 + ch3] = from_f32<TO>(fmaxf(acc[k], 0.f));
+      }
+    }
   }
-  __syncthreads();
-  // conv1: out (ch, rr, cc) <- input rows 2rr-1+{0,1} (strip rows 2rr+{0,1}), cols 2cc-1+{0,1} (index 2cc+{0,1})
-  for (int e = threadIdx.x; e < 16 * 4 * 48; e += blockDim.x) {
-    const int cc = e % 48, rr = (e / 48) % 4, ch = e / (48 * 4);
-    float acc = __ldg(b1 + ch);
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-#pragma unroll
-      for (int ky = 0; ky < 2; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 2; ++kx)
-          acc = fmaf(s_in[c][2 * rr + ky][2 * cc + kx], __ldg(w1 + ((ch * 3 + c) * 2 + ky) * 2 + kx), acc);
-    s_c1[ch][rr][cc] = fmaxf(acc, 0.f);
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < 32 * 2 * 24; e += blockDim.x) {
-    const int cc = e % 24, rr = (e / 24) % 2, ch = e / 48;
-    float acc = __ldg(b2 + ch);
-    for (int c = 0; c < 16; ++c)
-#pragma unroll
-      for (int ky = 0; ky < 2; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 2; ++kx)
-          acc = fmaf(s_c1[c][2 * rr + ky][2 * cc + kx], __ldg(w2 + ((ch * 16 + c) * 2 + ky) * 2 + kx), acc);
-    s_c2[ch][rr][cc] = fmaxf(acc, 0.f);
-  }
-  __syncthreads();
-  for (int e = threadIdx.x; e < 64 * 12; e += blockDim.x) {
-    const int ch = e % 64, j = e / 64;
-    float acc = __ldg(b3 + ch);
-    for (int c = 0; c < 32; ++c)
-#pragma unroll
-      for (int ky = 0; ky < 2; ++ky)
-#pragma unroll
-        for (int kx = 0; kx < 2; ++kx)
-          acc = fmaf(s_c2[c][ky][2 * j + kx], __ldg(w3 + ((ch * 32 + c) * 2 + ky) * 2 + kx), acc);
-    feat[(size_t)frame * 9216 + (i * 12 + j) * 64 + ch] = fmaxf(acc, 0.f);
-  }
+}
+
+__global__ void cast_f32_kernel(const bf16* __restrict__ in, float* __restrict__ out, long long n) {
+  pdl_wait();
+  pdl_trigger();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = __bfloat162float(in[i]);
 }
 
 // prepare_obs_cond_vectors (models/diffusion_ddpm.py:317-330): cat[pos(2), act(3), vel(2), img_feat(128)]
@@ -879,9 +927,19 @@ __global__ void build_cond_kernel(const float* __restrict__ pos, const float* __
   cond[i] = v;
 }
 }  // namespace
-void launch_enc_convs(const float* img, const float* w1, const float* b1, const float* w2, const float* b2, const float* w3,
-                      const float* b3, float* feat, int n, cudaStream_t s) {
-  launch_pdl(enc_convs_kernel, dim3(n * 12), dim3(256), 0, s, img, w1, b1, w2, b2, w3, b3, feat);
+template <typename TO>
+void launch_enc_convs(const float* img, const float* w1, const float* b1, const float* w2t, const float* b2, const float* w3t,
+                      const float* b3, TO* feat, int n, cudaStream_t s) {
+  constexpr size_t smem = (128 * 64 + 64 * 32 + 12 * 16 + 3 * 8 * 97 + 16 * 4 * 48 + 32 * 2 * 24) * sizeof(float);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(enc_convs_kernel<TO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  launch_pdl(enc_convs_kernel<TO>, dim3(n), dim3(256), smem, s, img, w1, b1, w2t, b2, w3t, b3, feat);
+  COUNT_LAUNCH();
+}
+template void launch_enc_convs<float>(const float*, const float*, const float*, const float*, const float*, const float*, const float*, float*, int, cudaStream_t);
+template void launch_enc_convs<bf16>(const float*, const float*, const float*, const float*, const float*, const float*, const float*, bf16*, int, cudaStream_t);
+void launch_cast_f32(const bf16* in, float* out, long long n, cudaStream_t s) {
+  launch_pdl(cast_f32_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, in, out, n);
   COUNT_LAUNCH();
 }
 void launch_build_cond(const float* pos, const float* act, const float* vel, const float* feat, float* cond, int B, int T, int cond_dim, cudaStream_t s) {
@@ -958,6 +1016,19 @@ void launch_pack_linear_f32(const float* nk, float* out, int N, int K, int ld_ou
 }
 void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s) {
   launch_pdl(cast_bf16_kernel, dim3(cdiv(n, 256)), dim3(256), 0, s, in, out, n);
+}
+namespace {
+__global__ void pack_enc_linear_bf16_kernel(const float* __restrict__ w, bf16* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128LL * 9216) return;
+  const int k2 = (int)(i % 9216);
+  const int n = (int)(i / 9216);
+  const int c = k2 % 64, p = k2 / 64;
+  out[i] = __float2bfloat16_rn(w[(size_t)n * 9216 + c * 144 + p]);
+}
+}  // namespace
+void launch_pack_enc_linear_bf16(const float* w, bf16* out, cudaStream_t s) {
+  launch_pdl(pack_enc_linear_bf16_kernel, dim3(cdiv(128LL * 9216, 256)), dim3(256), 0, s, w, out);
 }
 void launch_pack_enc_linear(const float* w, float* out, cudaStream_t s) {
   launch_pdl(pack_enc_linear_kernel, dim3(cdiv(128LL * 9216, 256)), dim3(256), 0, s, w, out);

@@ -93,6 +93,8 @@ struct spdm_plan {
   float* inv_freq = nullptr;                          // [time_dim/2]
   float *enc_w1 = nullptr, *enc_b1 = nullptr, *enc_w2 = nullptr, *enc_b2 = nullptr, *enc_w3 = nullptr, *enc_b3 = nullptr;
   float *enc_wl = nullptr, *enc_bl = nullptr;  // [9216][128], [128]
+  bf16* enc_wl16 = nullptr;                    // bf16 plan: [128][9216] K-major for the tcgen05 GEMM
+  bf16* enc_feat16 = nullptr; bf16* enc_out16 = nullptr; TcGemm* enc_tc = nullptr;
   std::map<std::string, std::function<void(const float*, const int64_t*, int, cudaStream_t)>> loaders;
   std::set<std::string> missing_unet, missing_enc;
 
@@ -313,16 +315,33 @@ void register_weights(spdm_plan* p) {
   p->enc_wl = p->alloc<float>((size_t)9216 * 128);  p->enc_bl = p->alloc<float>(128);
   reg_vec(p, "vision_encoder.0.weight", p->enc_w1, 16 * 3 * 4, p->missing_enc);
   reg_vec(p, "vision_encoder.0.bias", p->enc_b1, 16, p->missing_enc);
-  reg_vec(p, "vision_encoder.2.weight", p->enc_w2, 32 * 16 * 4, p->missing_enc);
+  p->missing_enc.insert("vision_encoder.2.weight");
+  {
+    float* dst = p->enc_w2;  // stored transposed: [16*4][32]
+    p->loaders["vision_encoder.2.weight"] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
+      check_shape("vision_encoder.2.weight", shape, ndim, {32, 16, 2, 2});
+      launch_pack_linear_f32(src, dst, 32, 64, 32, 0, s);
+    };
+  }
   reg_vec(p, "vision_encoder.2.bias", p->enc_b2, 32, p->missing_enc);
-  reg_vec(p, "vision_encoder.4.weight", p->enc_w3, 64 * 32 * 4, p->missing_enc);
+  p->missing_enc.insert("vision_encoder.4.weight");
+  {
+    float* dst = p->enc_w3;  // stored transposed: [32*4][64]
+    p->loaders["vision_encoder.4.weight"] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
+      check_shape("vision_encoder.4.weight", shape, ndim, {64, 32, 2, 2});
+      launch_pack_linear_f32(src, dst, 64, 128, 64, 0, s);
+    };
+  }
   reg_vec(p, "vision_encoder.4.bias", p->enc_b3, 64, p->missing_enc);
   p->missing_enc.insert("vision_encoder.7.weight");
   {
     float* dst = p->enc_wl;
+    if (p->bf16_mode) p->enc_wl16 = p->alloc<bf16>((size_t)9216 * 128);
+    bf16* dst16 = p->enc_wl16;
     p->loaders["vision_encoder.7.weight"] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
       check_shape("vision_encoder.7.weight", shape, ndim, {128, 9216});
       launch_pack_enc_linear(src, dst, s);
+      if (dst16) launch_pack_enc_linear_bf16(src, dst16, s);
     };
   }
   reg_vec(p, "vision_encoder.7.bias", p->enc_bl, 128, p->missing_enc);
@@ -779,6 +798,7 @@ extern "C" int spdm_plan_destroy(spdm_plan* p) {
     if (kv.second.single) cudaGraphExecDestroy(kv.second.single);
   }
   for (auto& kv : p->tc_cache) tc_gemm_destroy(kv.second);
+  if (p->enc_tc) tc_gemm_destroy(p->enc_tc);
   for (auto& kv : p->sdpa_cache) sdpa_tc_destroy(kv.second);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   for (auto& kv : p->tail_cache) attn_tail_destroy(kv.second);
@@ -847,14 +867,32 @@ extern "C" int spdm_encode_images(spdm_plan* p, const float* images, float* out,
   REQUIRE(p && images && out && n > 0, "bad argument");
   if (!p->missing_enc.empty()) throw SpdmError{"vision encoder weights missing, first: " + *p->missing_enc.begin()};
   cudaStream_t s = (cudaStream_t)stream;
+  if (p->bf16_mode) {
+    // bf16 plan: conv stack writes bf16 features, Linear(9216 -> 128) runs on the tcgen05 GEMM (one 128-frame tile per CTA)
+    if (!p->enc_feat16) {
+      p->enc_chunk = 4096;
+      p->enc_feat16 = p->alloc<bf16>((size_t)p->enc_chunk * 9216);
+      p->enc_out16 = p->alloc<bf16>((size_t)p->enc_chunk * 128);
+      p->enc_tc = tc_gemm_create(p->enc_feat16, 9216, p->enc_wl16, 9216, 128, 1, 1, 1, p->enc_chunk);
+      REQUIRE(p->enc_tc != nullptr, "encoder GEMM: %s", tc_last_error());
+    }
+    for (int f0 = 0; f0 < n; f0 += p->enc_chunk) {
+      const int m = n - f0 < p->enc_chunk ? n - f0 : p->enc_chunk;
+      launch_enc_convs<bf16>(images + (size_t)f0 * 3 * 96 * 96, p->enc_w1, p->enc_b1, p->enc_w2, p->enc_b2, p->enc_w3, p->enc_b3,
+                             p->enc_feat16, m, s);
+      tc_gemm_launch(p->enc_tc, p->enc_out16, 128, nullptr, p->enc_bl, nullptr, 0, EPI_BIAS, ((m + 127) / 128) * 128, s);
+      launch_cast_f32(p->enc_out16, out + (size_t)f0 * 128, (long long)m * 128, s);
+    }
+  } else {
   if (!p->enc_feat) { p->enc_chunk = 4096; p->enc_feat = p->alloc<float>((size_t)p->enc_chunk * 9216); }
   for (int f0 = 0; f0 < n; f0 += p->enc_chunk) {
     const int m = n - f0 < p->enc_chunk ? n - f0 : p->enc_chunk;
-    launch_enc_convs(images + (size_t)f0 * 3 * 96 * 96, p->enc_w1, p->enc_b1, p->enc_w2, p->enc_b2, p->enc_w3, p->enc_b3, p->enc_feat, m, s);
+    launch_enc_convs<float>(images + (size_t)f0 * 3 * 96 * 96, p->enc_w1, p->enc_b1, p->enc_w2, p->enc_b2, p->enc_w3, p->enc_b3, p->enc_feat, m, s);
     GemmSimtArgs a{};
     a.in = p->enc_feat; a.w = p->enc_wl; a.bias = p->enc_bl; a.out = out + (size_t)f0 * 128; a.M = m; a.Cin = 9216; a.Cout = 128;
     a.ld_in = 9216; a.ld_out = 128; a.H = 1; a.W = 1; a.taps = 1; a.act = ACT_NONE;
     launch_gemm_simt<float, float>(a, s);
+  }
   }
   check_async("encode_images");
   return 0;
