@@ -59,9 +59,14 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
   __shared__ __align__(8) uint64_t bar_load;
   __shared__ __align__(8) uint64_t bar_mma;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_bo[C], s_b1[C], s_b2[C], s_g[C], s_b[C];  // per-column constants (weights: no dependency)
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row0 = blockIdx.x * 128;
+  for (int i = tid; i < C; i += 128) {
+    s_bo[i] = __ldg(p.bo + i); s_b1[i] = __ldg(p.b1 + i); s_b2[i] = __ldg(p.b2 + i);
+    s_g[i] = __ldg(p.ln_g + i); s_b[i] = __ldg(p.ln_b + i);
+  }
   if (tid == 0) {
     tma_prefetch_desc(&map_att); tma_prefetch_desc(&map_wo); tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_w2);
     mbar_init(&bar_load, 1);
@@ -108,6 +113,10 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
     issue_gemm();
   }
   load_phase ^= 1u;
+  const bf16* xrow = p.x + row * p.ld_x;
+  uint4 xn[4];   // residual row, prefetched one 32-column chunk ahead of the accumulator reads
+#pragma unroll
+  for (int j = 0; j < 4; ++j) xn[j] = *reinterpret_cast<const uint4*>(xrow + 8 * j);
   mbar_wait(&bar_mma, mma_phase);
   mma_phase ^= 1u;
   tc_fence_after();
@@ -117,25 +126,31 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
   }
   // epilogue 1: a = acc + bo + x  (kept fp32 in TMEM region R), LayerNorm statistics
   float s = 0.f, q = 0.f;
-  const bf16* xrow = p.x + row * p.ld_x;
 #pragma unroll 1
   for (int c = 0; c < C; c += 32) {
+    uint4 xc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) xc[j] = xn[j];
+    if (c + 32 < C) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) xn[j] = *reinterpret_cast<const uint4*>(xrow + c + 32 + 8 * j);
+    }
     uint32_t v[32];
     tmem_ld_32x32(t_lane + (uint32_t)c, v);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-      float x8[8];
-      load8(xrow + c + i, x8);
-      const float4 ba = __ldg(reinterpret_cast<const float4*>(p.bo + c + i));
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(p.bo + c + i + 4));
-      const float b8[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xc[j]);
 #pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float a = __uint_as_float(v[i + e]) + b8[e] + x8[e];
-        s += a;
-        q = fmaf(a, a, q);
-        v[i + e] = __float_as_uint(a);
+      for (int e = 0; e < 4; ++e) {
+        const int i = 8 * j + 2 * e;
+        const float a0 = __uint_as_float(v[i]) + s_bo[c + i] + __low2float(h2[e]);
+        const float a1 = __uint_as_float(v[i + 1]) + s_bo[c + i + 1] + __high2float(h2[e]);
+        s += a0 + a1;
+        q = fmaf(a0, a0, q);
+        q = fmaf(a1, a1, q);
+        v[i] = __float_as_uint(a0);
+        v[i + 1] = __float_as_uint(a1);
       }
     }
     tmem_st_32x32(t_lane + (uint32_t)(C + c), v);
@@ -151,8 +166,8 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
     float f[32];
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ln_g + c + i));
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ln_b + c + i));
+      const float4 g4 = *reinterpret_cast<const float4*>(s_g + c + i);
+      const float4 b4 = *reinterpret_cast<const float4*>(s_b + c + i);
       f[i] = (__uint_as_float(v[i]) - mean) * rstd * g4.x + b4.x;
       f[i + 1] = (__uint_as_float(v[i + 1]) - mean) * rstd * g4.y + b4.y;
       f[i + 2] = (__uint_as_float(v[i + 2]) - mean) * rstd * g4.z + b4.z;
@@ -187,7 +202,7 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
     float f[32];
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b1 + c + i));
+      const float4 b4 = *reinterpret_cast<const float4*>(s_b1 + c + i);
       const float bb[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
@@ -222,7 +237,7 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
     float f[32];
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
-      const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.b2 + c + i));
+      const float4 b4 = *reinterpret_cast<const float4*>(s_b2 + c + i);
       f[i] = __uint_as_float(v[i]) + b4.x + __uint_as_float(a[i]);
       f[i + 1] = __uint_as_float(v[i + 1]) + b4.y + __uint_as_float(a[i + 1]);
       f[i + 2] = __uint_as_float(v[i + 2]) + b4.z + __uint_as_float(a[i + 2]);

@@ -26,12 +26,16 @@ struct SdpaParams {
   bf16* out;         // [M][C]
 };
 
-template <int LK>
-__global__ void __launch_bounds__(128)
+// 256 threads: warps 0-3 and 4-7 both map onto the four TMEM lane quarters (warp % 4); the two groups split the key
+// columns of every softmax row between them, which halves the per-thread instruction stream and gives each SM
+// sub-partition two warps to hide the TMEM / MUFU latencies.
+template <int LK, bool MASKED>
+__global__ void __launch_bounds__(256)
 sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_vt, const SdpaParams p) {
   constexpr int KB = LK / 64;  // key blocks of 64
   constexpr int SQ = 16384, SK = LK * 128, SVT = KB * 8192;
   constexpr int TMEM_COLS = (LK == 256) ? 512 : 256;  // S: LK columns, O: up to 64 columns
+  constexpr int HALF = LK / 2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* sQ = smem;
@@ -41,8 +45,11 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
   __shared__ __align__(8) uint64_t bar_load;
   __shared__ __align__(8) uint64_t bar_mma;
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_red[2][128];   // per-row partial max / partial sum of the two column halves
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;             // which half of the key columns this thread handles
+  const int r = (warp & 3) * 32 + lane;   // query row inside the tile == TMEM lane
   const int q_row0 = blockIdx.x * 128;
   const int cb = blockIdx.y;
   const int kv_tile = q_row0 / LK;
@@ -73,16 +80,16 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
   }
   mbar_wait(&bar_load, 0);
 
-  const int r = tid;  // query row inside the tile == TMEM lane
   int k_lo = 0, k_hi = LK;
-  if (p.L < LK) {  // several samples share the tile: a query only sees the keys of its own sample
+  if (MASKED) {  // several samples share the tile: a query only sees the keys of its own sample
     const int pos = (q_row0 - key_row0) + r;
     k_lo = (pos / p.L) * p.L;
     k_hi = k_lo + p.L;
   }
-  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t idesc_s = make_idesc(LK), idesc_o = make_idesc(p.hd);
   uint32_t mma_phase = 0;
+  const int c_begin = half * HALF, c_end = c_begin + HALF;
 
   for (int h = 0; h < p.heads_per_blk; ++h) {
     // ---------------- S = Q_h K_h^T ----------------
@@ -98,35 +105,47 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     mma_phase ^= 1u;
     tc_fence_after();
 
-    // ---------------- softmax over the row ----------------
+    // ---------------- softmax over the row (this thread: columns [c_begin, c_end)) ----------------
     float m = -INFINITY;
 #pragma unroll 1
-    for (int c = 0; c < LK; c += 32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       uint32_t v[32];
       tmem_ld_32x32(t_lane + (uint32_t)c, v);
       tmem_ld_wait();
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int i = 0; i < 32; ++i) {
-        const int col = c + i;
-        if (col >= k_lo && col < k_hi) m = fmaxf(m, __uint_as_float(v[i]));
+        const float x = __uint_as_float(v[i]);
+        if (!MASKED || (c + i >= k_lo && c + i < k_hi)) m4[i & 3] = fmaxf(m4[i & 3], x);
       }
+      m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
     }
+    s_red[half][r] = m;
+    __syncthreads();
+    m = fmaxf(s_red[0][r], s_red[1][r]);
+    const float mscaled = m * p.scale_log2;
     float sum = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < LK; c += 32) {
+    for (int c = c_begin; c < c_end; c += 32) {
       uint32_t v[32];
       tmem_ld_32x32(t_lane + (uint32_t)c, v);
       tmem_ld_wait();
       uint32_t packed[16];
+      float s2[2] = {0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
-        const int col = c + i;
-        float p0 = (col >= k_lo && col < k_hi) ? exp2f((__uint_as_float(v[i]) - m) * p.scale_log2) : 0.f;
-        float p1 = (col + 1 >= k_lo && col + 1 < k_hi) ? exp2f((__uint_as_float(v[i + 1]) - m) * p.scale_log2) : 0.f;
+        float p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -mscaled));
+        float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mscaled));
+        if (MASKED) {
+          if (!(c + i >= k_lo && c + i < k_hi)) p0 = 0.f;
+          if (!(c + i + 1 >= k_lo && c + i + 1 < k_hi)) p1 = 0.f;
+        }
         const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-        sum += __low2float(b2) + __high2float(b2);
+        s2[0] += __low2float(b2);
+        s2[1] += __high2float(b2);
         packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
       }
+      sum += s2[0] + s2[1];
       // row r of key block kb = c/64, 16-byte chunks j0..j0+3, 128B swizzle: chunk j lives at (j ^ (r & 7))
       uint8_t* rowp = sP + (c >> 6) * 16384 + r * 128;
       const int j0 = (c & 63) >> 3;
@@ -136,6 +155,8 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
         *reinterpret_cast<uint4*>(rowp + (((j0 + j) ^ (r & 7)) << 4)) = val;
       }
     }
+    __syncthreads();            // every thread has consumed the partial maxima
+    s_red[half][r] = sum;
     fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
@@ -157,23 +178,25 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     mma_phase ^= 1u;
     tc_fence_after();
 
-    const float inv = 1.f / sum;
-    bf16* orow = p.out + (size_t)(q_row0 + r) * p.C + cb * 64 + h * p.hd;
+    if (half == 0) {
+      const float inv = 1.f / (s_red[0][r] + s_red[1][r]);
+      bf16* orow = p.out + (size_t)(q_row0 + r) * p.C + cb * 64 + h * p.hd;
 #pragma unroll 1
-    for (int c = 0; c < p.hd; c += 32) {
-      uint32_t v[32];
-      tmem_ld_32x32(t_lane + (uint32_t)(LK + c), v);
-      tmem_ld_wait();
-      const int n = p.hd - c < 32 ? p.hd - c : 32;
-      for (int i = 0; i < n; i += 8) {
-        float f[8];
+      for (int c = 0; c < p.hd; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + (uint32_t)(LK + c), v);
+        tmem_ld_wait();
+        const int n = p.hd - c < 32 ? p.hd - c : 32;
+        for (int i = 0; i < n; i += 8) {
+          float f[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i + e]) * inv;
-        store8(orow + c + i, f);
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i + e]) * inv;
+          store8(orow + c + i, f);
+        }
       }
     }
     tc_fence_before();
-    __syncthreads();  // S, P and O are reused by the next head
+    __syncthreads();  // S, P, O and s_red are reused by the next head
   }
   if (warp == 0) {
     tc_fence_after();
@@ -246,19 +269,19 @@ SdpaTc* sdpa_tc_create(const bf16* qkv, const bf16* vt, int C, int L, int heads,
 }
 void sdpa_tc_destroy(SdpaTc* g) { delete g; }
 
+template <int LK, bool MASKED>
+static void sdpa_launch_cfg(const SdpaTc* g, const SdpaParams& p, dim3 grid, cudaStream_t s) {
+  constexpr int smem = 16384 + LK * 128 + (LK / 64) * 8192 + (LK / 64) * 16384 + 1024;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(sdpa_tc_kernel<LK, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  launch_pdl(sdpa_tc_kernel<LK, MASKED>, grid, dim3(256), smem, s, g->map_qkv, g->map_vt, p);
+}
+
 void sdpa_tc_launch(const SdpaTc* g, bf16* out, long long M, cudaStream_t s) {
   SdpaParams p = g->p;
   p.out = out;
   dim3 grid((unsigned)(M / 128), (unsigned)(p.C / 64));
-  if (g->LK == 128) {
-    constexpr int smem = 16384 + 128 * 128 + 2 * 8192 + 2 * 16384 + 1024;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(sdpa_tc_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    launch_pdl(sdpa_tc_kernel<128>, dim3(grid), dim3(128), smem, s, g->map_qkv, g->map_vt, p);
-  } else {
-    constexpr int smem = 16384 + 256 * 128 + 4 * 8192 + 4 * 16384 + 1024;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(sdpa_tc_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    launch_pdl(sdpa_tc_kernel<256>, dim3(grid), dim3(128), smem, s, g->map_qkv, g->map_vt, p);
-  }
+  if (g->LK == 256) sdpa_launch_cfg<256, false>(g, p, grid, s);
+  else if (p.L == 128) sdpa_launch_cfg<128, false>(g, p, grid, s);
+  else sdpa_launch_cfg<128, true>(g, p, grid, s);
 }
