@@ -74,7 +74,7 @@ template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
-  constexpr int TMEM_COLS = 2 * BLOCK_N;
+  constexpr int TMEM_COLS = 2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);  // power of two
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint8_t* smem_a = smem;
@@ -546,7 +546,7 @@ TcGemm* tc_gemm_create(const bf16* in, int ld_in, const bf16* w_packed, int Cin,
   TcGemm* g = new TcGemm();
   memset(g, 0, sizeof(*g));
   g->Bcap = Bcap;
-  g->block_n = (Cout % 128 == 0) ? 128 : 64;
+  g->block_n = (Cout % 128 == 0) ? 128 : (Cout == 192 ? 192 : 64);  // in_proj of a 64-channel block: one 192-wide tile
   g->has256 = (Cout % 256 == 0);
   TcParams& p = g->p;
   p.H = H; p.W = W; p.Hb = Hb; p.Bt = Bt; p.Cin = Cin; p.Cout = Cout; p.taps = taps;
@@ -613,6 +613,7 @@ int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const f
   p.total_tiles = p.m_tiles * p.n_tiles;
   p.P = partials_for(p, p.n_tiles);
   if (bn == 256) launch_cfg<256, 4>(g->map_a, g->map_b256, p, s);
+  else if (bn == 192) launch_cfg<192, 4>(g->map_a, g->map_b, p, s);
   else if (bn == 128) launch_cfg<128, 6>(g->map_a, g->map_b, p, s);
   else launch_cfg<64, 8>(g->map_a, g->map_b, p, s);
   return p.P;

@@ -194,7 +194,6 @@ template void launch_stats<bf16>(const bf16*, float*, int, int, int, int, cudaSt
 // =================================================================================================
 namespace {
 constexpr int APPLY_THREADS = 128;
-constexpr int APPLY_VEC_PER_THREAD = 4;
 
 // erf to ~1.5e-7 absolute (Abramowitz-Stegun 7.1.26): enough for the bf16 path, a third of erff's cost
 __device__ __forceinline__ float erf_fast(float x) {
@@ -204,7 +203,7 @@ __device__ __forceinline__ float erf_fast(float x) {
   return copysignf(1.0f - poly * __expf(-ax * ax), x);
 }
 
-template <typename TI, typename TO, bool EXACT>
+template <typename TI, typename TO, bool EXACT, int APPLY_VEC_PER_THREAD>
 __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(ApplyArgs a) {
   pdl_wait();
   pdl_trigger();
@@ -276,9 +275,14 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(ApplyArgs a) {
 }  // namespace
 template <typename TI, typename TO> void launch_apply(const ApplyArgs& a, int B, cudaStream_t s) {
   const int nvec = a.HW * (a.C >> 3);
-  dim3 grid(cdiv(nvec, APPLY_THREADS * APPLY_VEC_PER_THREAD), B);
-  if (sizeof(TI) == 4) launch_pdl(apply_kernel<TI, TO, true>, dim3(grid), dim3(APPLY_THREADS), 0, s, a);
-  else launch_pdl(apply_kernel<TI, TO, false>, dim3(grid), dim3(APPLY_THREADS), 0, s, a);
+  // the per-thread prologue (statistics fold, 40 per-channel constants) is amortised over more vectors once the
+  // launch is large enough to fill the machine anyway
+  const bool big = (long long)B * nvec >= 148LL * 8 * APPLY_THREADS * 16;
+  const int vpt = big ? 16 : 4;
+  dim3 grid(cdiv(nvec, APPLY_THREADS * vpt), B);
+  if (sizeof(TI) == 4) launch_pdl(apply_kernel<TI, TO, true, 4>, dim3(cdiv(nvec, APPLY_THREADS * 4), B), dim3(APPLY_THREADS), 0, s, a);
+  else if (big) launch_pdl(apply_kernel<TI, TO, false, 16>, grid, dim3(APPLY_THREADS), 0, s, a);
+  else launch_pdl(apply_kernel<TI, TO, false, 4>, grid, dim3(APPLY_THREADS), 0, s, a);
   COUNT_LAUNCH();
 }
 template void launch_apply<float, float>(const ApplyArgs&, int, cudaStream_t);

@@ -301,3 +301,39 @@ def test_training_forward_loss(spdm, golden_dir):
     with torch.no_grad():
         loss = m.process_single_batch(full, t=g["train_t"].cuda(), noise=g["train_noise"].cuda())
     assert abs(float(loss) - float(g["train_loss"])) < 1e-4 * abs(float(g["train_loss"]))
+
+
+def test_concurrent_sub_batches_are_bitwise_identical(spdm):
+    """SPDM_FLAG_SPLIT: running the U-Net of a denoising step as concurrent sub-batches must not change any sample
+    (every op is per-sample; GroupNorm partial sums are per sample)."""
+    B, K = 96, 6
+    sd = fixtures.make_unet_weights(attention=True, seed=0)
+    esd = fixtures.make_encoder_weights()
+    batch = fixtures.make_batch(B, seed=21)
+    x_T = fixtures.make_xT(B)
+    sch = spdm.DDPMScheduler(num_train_timesteps=K, beta_schedule="linear", clip_sample=False, prediction_type="epsilon")
+    sch.set_timesteps(K)
+    outs = []
+    for split in (1, 2, 3):
+        plan = spdm.DenoisePlan(attention=True, precision="bf16", batch_max=B, inpaint_rows=1, graph_steps=3, split=split)
+        plan.load_unet_state_dict(sd)
+        plan.load_encoder_state_dict(esd)
+        plan.set_schedule("ddpm", sch.coef_table(), sch.timesteps)
+        plan.encode_cond(batch["image"], batch["position"], batch["action"], batch["velocity"])
+        inp = torch.cat([batch["position"][:, -1:], batch["action"][:, -1:]], dim=-1).reshape(B, -1)
+        outs.append(plan.sample(x_T, inpaint=inp, seed=5).cpu())
+        plan.close()
+    assert torch.isfinite(outs[0]).all()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+
+
+def test_bf16_encoder_path(spdm, golden_dir):
+    """bf16 plans run the encoder's Linear(9216 -> 128) on the tcgen05 GEMM: features within bf16 rounding of the golden."""
+    g = _golden(golden_dir, "encoder")
+    gen = torch.Generator().manual_seed(5)
+    img = torch.rand((4, 3, 96, 96), generator=gen)
+    plan = spdm.DenoisePlan(attention=False, precision="bf16", batch_max=4, graph_steps=0)
+    plan.load_encoder_state_dict(fixtures.make_encoder_weights())
+    out = plan.encode_images(img)
+    assert rel(out, g["out"]) < 1e-2
+    plan.close()
