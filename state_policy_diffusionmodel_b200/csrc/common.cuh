@@ -17,7 +17,7 @@ typedef __nv_bfloat16 bf16;
 
 enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 enum : int { TEMB_NONE = 0, TEMB_ROW0 = 1, TEMB_PER_SAMPLE = 2, TEMB_STEP = 3 };
-enum : int { EPI_STATS = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RESID = 8, EPI_VT = 16 };
+enum : int { EPI_STATS = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RESID = 8, EPI_VT = 16, EPI_APPLY = 32 };
 
 #define SPDM_FILM_WIDTH 1792 /* sum over the 6 stages of 2*C_out */
 #define SPDM_TEMB_WIDTH 896  /* sum over the 6 stages of C_out   */
@@ -184,7 +184,11 @@ void tc_gemm_destroy(TcGemm* g);
 // EPI_VT (in_proj of an attention block, Cout = 3C): the V third of the output is written transposed to
 // vt[row / vt_lk][C][row % vt_lk] for sdpa_tc instead of to `out`.
 int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const float* bias, const bf16* resid,
-                   int ld_res, int flags, int B, cudaStream_t s, bf16* vt = nullptr, int vt_lk = 0);
+                   int ld_res, int flags, int B, cudaStream_t s, bf16* vt = nullptr, int vt_lk = 0,
+                   const ApplyArgs* fuse = nullptr);
+// True when a launch for B samples keeps whole samples and all channels inside one tile, so that GroupNorm apply
+// (+GELU, +temb, +FiLM) can run in the conv epilogue (pass `fuse`; `out` then receives the activated map).
+bool tc_gemm_can_fuse_apply(const TcGemm* g, int B);
 const char* tc_last_error();
 void tc_set_debug(int v);  // microbenchmark switches, see TcParams::dbg
 int tc_batch_multiple(int H, int W);  // granularity of B required by the 128-row M tiling at geometry HxW

@@ -50,6 +50,7 @@ struct TcParams {
   float* stats;
   const float* bias;
   const bf16* resid;
+  ApplyArgs ap;           // EPI_APPLY: GroupNorm apply (+GELU, +temb, +FiLM) fused behind the accumulator (raw/out/stats unused)
   bf16* vt;               // EPI_VT: columns >= vt_c0 go, transposed, to vt[row / vt_lk][col - vt_c0][row % vt_lk]
   int vt_c0, vt_C, vt_lk;
 };
@@ -58,6 +59,25 @@ struct TcParams {
 // The kernel.  grid = min(total_tiles, #SM); dynamic smem = STAGES*(A+B) + 1024 (alignment slack).
 // ---------------------------------------------------------------------------------------------
 struct TileCoord { int m_tile, n_tile, b0, h0, n0; };
+
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
+
+__device__ __forceinline__ float erf_fast_tc(float x) {  // Abramowitz-Stegun 7.1.26, |err| < 1.5e-7
+  const float ax = fabsf(x);
+  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
+  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
+  return copysignf(1.0f - poly * __expf(-ax * ax), x);
+}
+__device__ __forceinline__ float gelu_fast_tc(float y) { return 0.5f * y * (1.0f + erf_fast_tc(y * 0.70710678118654752440f)); }
+
+// row of the time-embedding table used by this launch (or null)
+__device__ __forceinline__ const float* temb_row(const ApplyArgs& ap, int b) {
+  if (ap.temb_mode == TEMB_NONE) return nullptr;
+  int trow = 0;
+  if (ap.temb_mode == TEMB_PER_SAMPLE) trow = b;
+  else if (ap.temb_mode == TEMB_STEP) trow = *ap.step_ptr;
+  return ap.temb + (size_t)trow * SPDM_TEMB_WIDTH + ap.temb_off;
+}
 
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int block_n) {
   TileCoord t;
@@ -84,6 +104,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_part[2][4][2];   // EPI_APPLY: per-warp (sum, sumsq) of the tile's samples, double-buffered like TMEM
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -188,6 +209,82 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        continue;
+      }
+      if (p.flags & EPI_APPLY) {
+        // The tile holds whole samples and all their channels (host guarantees n_tiles == 1, H == Hb), so GroupNorm(1, C)
+        // is tile-local: statistics from the fp32 accumulator, then normalise + GELU / time embedding / FiLM on a second
+        // pass over TMEM and store the activated map directly -- the raw conv output never touches HBM.
+        float ps = 0.f, pq = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + (uint32_t)c, v);
+          tmem_ld_wait();
+          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int i = 0; i < 32; ++i) { const float f = __uint_as_float(v[i]); s4[i & 3] += f; q4[i & 3] = fmaf(f, f, q4[i & 3]); }
+          ps += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+          pq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
+        }
+        const int span = rps >= 32 ? 32 : rps;
+        for (int o = span >> 1; o > 0; o >>= 1) { ps += __shfl_xor_sync(0xffffffffu, ps, o); pq += __shfl_xor_sync(0xffffffffu, pq, o); }
+        if (rps >= 32) {  // a sample spans rps/32 warps: combine their partials in a fixed order
+          if (lane == 0) { s_part[acc][q][0] = ps; s_part[acc][q][1] = pq; }
+          epi_bar_sync();
+          const int wps = rps / 32, q0 = (q / wps) * wps;
+          ps = 0.f; pq = 0.f;
+          for (int j = 0; j < wps; ++j) { ps += s_part[acc][q0 + j][0]; pq += s_part[acc][q0 + j][1]; }
+        }
+        const float inv_n = 1.0f / ((float)rps * (float)p.Cout);
+        const float mean = ps * inv_n;
+        const float rstd = rsqrtf(fmaxf(pq * inv_n - mean * mean, 0.f) + p.ap.eps);
+        const int b = t.b0 + r_t / rps;
+        const float* te = temb_row(p.ap, b);
+        const float* fi = p.ap.film ? p.ap.film + (size_t)b * SPDM_FILM_WIDTH + p.ap.film_off : nullptr;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (c + 32 == BLOCK_N) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+          float f[32];
+#pragma unroll
+          for (int i = 0; i < 32; i += 4) {
+            const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.ap.gamma + c + i));
+            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.ap.beta + c + i));
+            f[i] = (__uint_as_float(v[i]) - mean) * rstd * g4.x + b4.x;
+            f[i + 1] = (__uint_as_float(v[i + 1]) - mean) * rstd * g4.y + b4.y;
+            f[i + 2] = (__uint_as_float(v[i + 2]) - mean) * rstd * g4.z + b4.z;
+            f[i + 3] = (__uint_as_float(v[i + 3]) - mean) * rstd * g4.w + b4.w;
+          }
+          if (p.ap.act == ACT_GELU) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) f[i] = gelu_fast_tc(f[i]);
+          }
+          if (te) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 t4 = __ldg(reinterpret_cast<const float4*>(te + c + i));
+              f[i] += t4.x; f[i + 1] += t4.y; f[i + 2] += t4.z; f[i + 3] += t4.w;
+            }
+          }
+          if (fi) {
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+              const float4 s4 = __ldg(reinterpret_cast<const float4*>(fi + c + i));
+              const float4 o4 = __ldg(reinterpret_cast<const float4*>(fi + p.Cout + c + i));
+              f[i] = fmaf(s4.x, f[i], o4.x); f[i + 1] = fmaf(s4.y, f[i + 1], o4.y);
+              f[i + 2] = fmaf(s4.z, f[i + 2], o4.z); f[i + 3] = fmaf(s4.w, f[i + 3], o4.w);
+            }
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 8) store8(orow + c + i, f + i);
+        }
         continue;
       }
 #pragma unroll 1
@@ -298,6 +395,8 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_part[2][16][4][2];  // EPI_APPLY: per-sample, per-warp (sum, sumsq); double-buffered like TMEM
+  __shared__ float s_mr[2][16][2];       // per-sample (mean, rstd)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -391,6 +490,110 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int ch = c_tile * BLOCK_M + ch_local;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NPIX);
       float rs = 0.f, rq = 0.f;
+      if (p.flags & EPI_APPLY) {
+        // The 256-pixel tile holds NPIX/pps whole samples and every channel (host guarantees Cout <= 128, pps | 256):
+        // GroupNorm is tile-local.  Pass 1 over TMEM: per-sample statistics; pass 2: normalise (+GELU/temb/FiLM) and store.
+        const int n_s = NPIX / pps;
+        if (active) {
+#pragma unroll 1
+          for (int c = 0; c < NPIX; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_addr + (uint32_t)c, v);
+            tmem_ld_wait();
+            if (pps >= 32) {
+              float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+              for (int i = 0; i < 32; ++i) { const float f = __uint_as_float(v[i]); s4[i & 3] += f; q4[i & 3] = fmaf(f, f, q4[i & 3]); }
+              rs += (s4[0] + s4[1]) + (s4[2] + s4[3]);
+              rq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
+              if ((c + 32) % pps == 0) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) { rs += __shfl_xor_sync(0xffffffffu, rs, o); rq += __shfl_xor_sync(0xffffffffu, rq, o); }
+                if (lane == 0) { s_part[acc][c / pps][q][0] = rs; s_part[acc][c / pps][q][1] = rq; }
+                rs = 0.f; rq = 0.f;
+              }
+            } else {  // pps == 16
+              float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
+#pragma unroll
+              for (int i = 0; i < 16; ++i) {
+                const float fa = __uint_as_float(v[i]), fb = __uint_as_float(v[16 + i]);
+                sa += fa; qa = fmaf(fa, fa, qa); sb += fb; qb = fmaf(fb, fb, qb);
+              }
+#pragma unroll
+              for (int o = 16; o > 0; o >>= 1) {
+                sa += __shfl_xor_sync(0xffffffffu, sa, o); qa += __shfl_xor_sync(0xffffffffu, qa, o);
+                sb += __shfl_xor_sync(0xffffffffu, sb, o); qb += __shfl_xor_sync(0xffffffffu, qb, o);
+              }
+              if (lane == 0) {
+                s_part[acc][c / 16][q][0] = sa; s_part[acc][c / 16][q][1] = qa;
+                s_part[acc][c / 16 + 1][q][0] = sb; s_part[acc][c / 16 + 1][q][1] = qb;
+              }
+            }
+          }
+        }
+        epi_bar_sync();
+        {
+          const int et = (int)threadIdx.x - 64;  // 0..127 over the epilogue warps
+          if (et >= 0 && et < n_s) {
+            float ts = 0.f, tq = 0.f;
+            for (int j = 0; j < nw; ++j) { ts += s_part[acc][et][j][0]; tq += s_part[acc][et][j][1]; }
+            const float inv_n = 1.0f / ((float)pps * (float)p.Cout);
+            const float mean = ts * inv_n;
+            s_mr[acc][et][0] = mean;
+            s_mr[acc][et][1] = rsqrtf(fmaxf(tq * inv_n - mean * mean, 0.f) + p.ap.eps);
+          }
+        }
+        epi_bar_sync();
+        if (active) {
+          const float g = __ldg(p.ap.gamma + ch), be = __ldg(p.ap.beta + ch);
+          const long long b_first = row0 / pps;
+          float te = 0.f;
+          const bool has_film = p.ap.film != nullptr;
+          int cur_s = -1;
+          float A = 0.f, Bc = 0.f, fs = 1.f, fb = 0.f;
+          auto set_sample = [&](int sl) {
+            if (sl == cur_s) return;
+            cur_s = sl;
+            const float mean = s_mr[acc][sl][0], rstd = s_mr[acc][sl][1];
+            A = rstd * g;
+            Bc = fmaf(-mean, A, be);
+            const float* tr = temb_row(p.ap, (int)(b_first + sl));
+            te = tr ? __ldg(tr + ch) : 0.f;
+            if (has_film) {
+              const float* fi = p.ap.film + (size_t)(b_first + sl) * SPDM_FILM_WIDTH + p.ap.film_off;
+              fs = __ldg(fi + ch);
+              fb = __ldg(fi + p.Cout + ch);
+            }
+          };
+#pragma unroll 1
+          for (int c = 0; c < NPIX; c += 32) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_addr + (uint32_t)c, v);
+            tmem_ld_wait();
+            if (c + 32 == NPIX) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            }
+            bf16* optr = p.out + (row0 + c) * p.ld_out + ch;
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+              if (pps >= 32) { if (i == 0) set_sample(c / pps); }
+              else if ((i & 15) == 0) set_sample((c + i) / pps);
+              float y = fmaf(__uint_as_float(v[i]), A, Bc);
+              if (p.ap.act == ACT_GELU) y = gelu_fast_tc(y);
+              y += te;
+              y = fmaf(fs, y, fb);
+              optr[(size_t)i * p.ld_out] = __float2bfloat16_rn(y);
+            }
+          }
+        } else {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        }
+        continue;
+      }
       if (active) {
 #pragma unroll 1
         for (int c = 0; c < NPIX; c += 32) {
@@ -584,14 +787,30 @@ TcGemm* tc_gemm_create(const bf16* in, int ld_in, const bf16* w_packed, int Cin,
 
 void tc_gemm_destroy(TcGemm* g) { delete g; }
 
+static bool swap_taken(const TcGemm* g, int m_tiles, int flags) {
+  return g->can_swap && (flags & ~EPI_APPLY) == EPI_STATS && m_tiles % 2 == 0 && !(g_tc_dbg & 64);
+}
+
+bool tc_gemm_can_fuse_apply(const TcGemm* g, int B) {
+  if (g_tc_dbg & 256) return false;
+  const TcParams& p = g->p;
+  const int m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
+  const int pps = p.H * p.W;
+  if (p.taps != 9) return false;
+  if (swap_taken(g, m_tiles, EPI_STATS)) return pps <= 256 && 256 % pps == 0 && pps >= 16;
+  const int bn = g->has256 ? 256 : g->block_n;
+  return p.Cout == bn && p.H == p.Hb;  // one N tile, whole samples per M tile
+}
+
 int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const float* bias, const bf16* resid, int ld_res, int flags,
-                   int B, cudaStream_t s, bf16* vt, int vt_lk) {
+                   int B, cudaStream_t s, bf16* vt, int vt_lk, const ApplyArgs* fuse) {
   TcParams p = g->p;
+  if (fuse) { p.ap = *fuse; flags |= EPI_APPLY; }
   p.dbg = g_tc_dbg;
   p.vt = vt; p.vt_lk = vt_lk; p.vt_C = p.Cout / 3; p.vt_c0 = 2 * (p.Cout / 3);
   p.out = out; p.ld_out = ld_out; p.stats = stats; p.bias = bias; p.resid = resid; p.ld_res = ld_res; p.flags = flags;
   p.m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
-  if (g->can_swap && flags == EPI_STATS && p.m_tiles % 2 == 0 && !(g_tc_dbg & 64)) {
+  if (swap_taken(g, p.m_tiles, flags)) {
     p.n_tiles = (p.Cout + BLOCK_M - 1) / BLOCK_M;
     p.total_tiles = (p.m_tiles / 2) * p.n_tiles;
     const int pps = p.H * p.W;

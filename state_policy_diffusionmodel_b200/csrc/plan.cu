@@ -119,6 +119,8 @@ struct spdm_plan {
   cudaStream_t own_stream = nullptr;  // graphs are captured and replayed here (the caller's stream may be the legacy stream)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int split = 1;                       // sub-batches run concurrently per denoising step
+  bool no_fuse = false;                // SPDM_NO_FUSE_APPLY=1: keep GroupNorm apply as a separate kernel (A/B switch)
+  int fuse_mode = 0;                   // SPDM_FUSE_MODE: 0 none (default: measured faster, the 4-warp epilogue is the bottleneck), 1 GELU-free convs, 2 all
   cudaStream_t lane_stream[7] = {};
   cudaEvent_t ev_fork = nullptr, ev_lane[7] = {};
   float* enc_feat = nullptr; int enc_chunk = 0;  // [enc_chunk][9216]
@@ -430,21 +432,36 @@ template <typename T> struct Fwd {
     }
   }
 
+  TcGemm* get_tc(const std::string& wname, GemmW& g, const T* in, int ld_in, int level) {
+    char key[160];
+    snprintf(key, sizeof key, "%s|%p|%d", wname.c_str(), (const void*)in, ld_in);
+    TcGemm*& tc = p->tc_cache[key];
+    if (!tc) {
+      tc = tc_gemm_create(reinterpret_cast<const bf16*>(in), ld_in, g.w16, g.Cin, g.Cout, g.taps, p->levelH(level), p->levelW(level), p->Bcap);
+      REQUIRE(tc != nullptr, "%s: %s", wname.c_str(), tc_last_error());
+    }
+    return tc;
+  }
+
+  // can GroupNorm apply run inside this conv's epilogue (whole samples and all channels in one tile)?
+  bool can_fuse(const std::string& wname, const T* in, int ld_in, int level) {
+    if constexpr (sizeof(T) == 2) {
+      if (p->no_fuse) return false;
+      GemmW& g = p->gemms[wname];
+      return tc_gemm_can_fuse_apply(get_tc(wname, g, in, ld_in, level), Bpad);
+    }
+    return false;
+  }
+
   // conv / linear: in [M,Cin] (ld_in) -> out [M,Cout] (ld_out)
   void gemm(const std::string& wname, const T* in, int ld_in, int level, T* out, int ld_out, int flags, const T* resid = nullptr,
-            int ld_res = 0) {
+            int ld_res = 0, const ApplyArgs* fuse = nullptr) {
     auto it = p->gemms.find(wname);
     REQUIRE(it != p->gemms.end(), "internal: unknown gemm %s", wname.c_str());
     GemmW& g = it->second;
     const int H = p->levelH(level), W = p->levelW(level);
     if constexpr (sizeof(T) == 2) {
-      char key[160];
-      snprintf(key, sizeof key, "%s|%p|%d", wname.c_str(), (const void*)in, ld_in);
-      TcGemm*& tc = p->tc_cache[key];
-      if (!tc) {
-        tc = tc_gemm_create(reinterpret_cast<const bf16*>(in), ld_in, g.w16, g.Cin, g.Cout, g.taps, H, W, p->Bcap);
-        REQUIRE(tc != nullptr, "%s: %s", wname.c_str(), tc_last_error());
-      }
+      TcGemm* tc = get_tc(wname, g, in, ld_in, level);
       // algorithmic work: taps that fall inside the image only, real batch rows only
       const double flops = g.taps == 9 ? 2.0 * g.Cin * g.Cout * (3.0 * H - 2) * (3.0 * W - 2) * c.B
                                        : 2.0 * g.Cin * g.Cout * (double)H * W * c.B;
@@ -452,9 +469,9 @@ template <typename T> struct Fwd {
       int P = 1;
       timed(p, c.s, g.taps == 9 ? PC_CONV3 : PC_GEMM1, flops, bytes, [&] {
         P = tc_gemm_launch(tc, reinterpret_cast<bf16*>(out), ld_out, stats(), (flags & EPI_BIAS) ? g.bias : nullptr,
-                           reinterpret_cast<const bf16*>(resid), ld_res, flags, Bpad, c.s, vt, vt_lk);
+                           reinterpret_cast<const bf16*>(resid), ld_res, flags, Bpad, c.s, vt, vt_lk, fuse);
       });
-      REQUIRE(!(flags & EPI_STATS) || P <= SPDM_MAX_PARTIALS, "%s: too many GroupNorm partials (%d)", wname.c_str(), P);
+      REQUIRE(fuse || !(flags & EPI_STATS) || P <= SPDM_MAX_PARTIALS, "%s: too many GroupNorm partials (%d)", wname.c_str(), P);
       curP = P;
     } else {
       GemmSimtArgs a{};
@@ -473,30 +490,54 @@ template <typename T> struct Fwd {
     }
   }
 
-  void apply(const std::string& norm, const T* raw, int ld_in, int C, int level, T* out, int ld_out, int act, const StageInfo* st) {
+  ApplyArgs make_apply(const std::string& norm, int C, int level, int act, const StageInfo* st) {
     NormW& n = p->norms[norm];
     ApplyArgs a{};
-    a.raw = raw; a.out = out; a.stats = stats(); a.P = curP; a.gamma = n.g; a.beta = n.b;
+    a.stats = stats(); a.P = curP; a.gamma = n.g; a.beta = n.b;
     a.temb = nullptr; a.temb_mode = TEMB_NONE; a.film = nullptr;
     if (st) {
       a.temb = c.temb; a.temb_mode = c.temb_mode; a.temb_off = st->temb_off; a.step_ptr = c.step_ptr;
       if (c.film) { a.film = c.film; a.film_off = st->film_off; }
     }
-    a.HW = p->levelH(level) * p->levelW(level); a.C = C; a.ld_in = ld_in; a.ld_out = ld_out; a.act = act; a.eps = 1e-5f;
+    a.HW = p->levelH(level) * p->levelW(level); a.C = C; a.act = act; a.eps = 1e-5f;
+    return a;
+  }
+
+  void apply(const std::string& norm, const T* raw, int ld_in, int C, int level, T* out, int ld_out, int act, const StageInfo* st) {
+    ApplyArgs a = make_apply(norm, C, level, act, st);
+    a.raw = raw; a.out = out; a.ld_in = ld_in; a.ld_out = ld_out;
     timed(p, c.s, PC_APPLY, 0, 2.0 * c.B * a.HW * C * sizeof(T), [&] { launch_apply<T, T>(a, c.B, c.s); });
   }
 
-  // DoubleConvolution (models/Unet_FiLmLayer.py:85-115); `first_done`: raw already holds conv1's output
+  // DoubleConvolution (models/Unet_FiLmLayer.py:85-115); `first_done`: raw already holds conv1's output.
+  // On the tensor-core path GroupNorm apply runs inside the conv epilogue whenever a tile holds whole samples.
   void double_conv(const std::string& name, const T* in, int ld_in, int Cout, int level, T* out, int ld_out, const StageInfo* st,
                    bool first_done = false) {
     T* raw = act(p->raw[level], level);
     T* h = act(p->hbuf[level], level);
-    if (!first_done) gemm(name + ".first", in, ld_in, level, raw, Cout, EPI_STATS);
-    tap(name + ".first", raw, Cout, Cout, level);
-    apply(name + ".norm", raw, Cout, Cout, level, h, Cout, ACT_GELU, nullptr);
-    gemm(name + ".second", h, Cout, level, raw, Cout, EPI_STATS);
-    tap(name + ".second", raw, Cout, Cout, level);
-    apply(name + ".norm", raw, Cout, Cout, level, out, ld_out, ACT_NONE, st);
+    const bool tap1 = p->tap_out && p->tap_name == name + ".first", tap2 = p->tap_out && p->tap_name == name + ".second";
+    bool fused = false;
+    if (!first_done) {
+      if (!tap1 && p->fuse_mode >= 2 && can_fuse(name + ".first", in, ld_in, level)) {
+        const ApplyArgs a = make_apply(name + ".norm", Cout, level, ACT_GELU, nullptr);
+        gemm(name + ".first", in, ld_in, level, h, Cout, EPI_STATS, nullptr, 0, &a);
+        fused = true;
+      } else {
+        gemm(name + ".first", in, ld_in, level, raw, Cout, EPI_STATS);
+      }
+    }
+    if (!fused) {
+      tap(name + ".first", raw, Cout, Cout, level);
+      apply(name + ".norm", raw, Cout, Cout, level, h, Cout, ACT_GELU, nullptr);
+    }
+    if (!tap2 && p->fuse_mode >= 1 && can_fuse(name + ".second", h, Cout, level)) {
+      const ApplyArgs a = make_apply(name + ".norm", Cout, level, ACT_NONE, st);
+      gemm(name + ".second", h, Cout, level, out, ld_out, EPI_STATS, nullptr, 0, &a);
+    } else {
+      gemm(name + ".second", h, Cout, level, raw, Cout, EPI_STATS);
+      tap(name + ".second", raw, Cout, Cout, level);
+      apply(name + ".norm", raw, Cout, Cout, level, out, ld_out, ACT_NONE, st);
+    }
   }
 
   // SelfAttention (models/Unet_FiLmLayer.py:44-82)
@@ -773,6 +814,8 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
     CUDA_OK(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
     p->split = (cfg->flags >> 8) & 0xF;
     if (const char* e = getenv("SPDM_SPLIT")) p->split = atoi(e);
+    if (const char* e = getenv("SPDM_NO_FUSE_APPLY")) p->no_fuse = atoi(e) != 0;
+    if (const char* e = getenv("SPDM_FUSE_MODE")) p->fuse_mode = atoi(e);
     if (p->split < 1) p->split = 1;
     if (p->split > 8) p->split = 8;
     CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
