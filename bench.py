@@ -23,7 +23,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "denoised trajectories/sec (DDIM-50, UNet_Film attention, 31x5, batch 256/GPU)"
+METRIC = "denoised trajectories/sec"  # BASELINE.json metric; sampler / steps / model / batch are spelled out in `config`
 UNIT = "trajectories/s"
 # algorithmic FLOPs (valid conv taps only), SURVEY.md 8(d): per sample per U-Net forward / per conditioning encode
 FLOP_UNET_ATTN = {31: 603.27e6, 61: 1270.91e6, 121: 2728.18e6}
@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--variant", default="attn", choices=["attn", "noattn"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--rows", type=int, default=31)
+    ap.add_argument("--dim", type=int, default=5, help="prediction_dim (5 = position+action, 2 = position only)")
     ap.add_argument("--graph-steps", type=int, default=10)
     ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches per denoising step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -127,13 +128,13 @@ def cpu_oracle_rate(state, enc_state, args, budget_s, b_cpu):
     sd = {k: v.detach().float().cpu() for k, v in state.items()}
     esd = {k: v.detach().float().cpu() for k, v in enc_state.items()}
     g = torch.Generator().manual_seed(7)
-    x_t = torch.rand((b_cpu, 1, args.rows, 5), generator=g)
+    x_t = torch.rand((b_cpu, 1, args.rows, args.dim), generator=g)
     sch = sampler_ref.make_scheduler(args.sampler, K)
     sch.set_timesteps(K)
     with torch.no_grad():
         t0 = time.perf_counter()
         cond = unet_ref.obs_cond(esd, batch).unsqueeze(1)
-        inp = unet_ref.inpaint_vector(batch, 1).unsqueeze(1)
+        inp = unet_ref.inpaint_vector(batch, 1).unsqueeze(1)[..., :args.dim]
         t_enc = time.perf_counter() - t0
         # warm-up step, then timed denoising steps until the budget is used
         sampler_ref.sample_ref(sd, sch, K, x_t, cond, inp, 1, attention=attention, max_steps=1)
@@ -178,7 +179,7 @@ def run_reference(args):
 
 def config_dict(args, total_B):
     return {"workload": "%s-%d sampling, %s, pred 31x5 (rows=%d), obs 10x(96x96x3 + pos/vel/act), random-init weights" % (
-                args.sampler.upper(), args.ddim_steps, "UNet_Film (attention)" if args.variant == "attn" else "UNet_Film_noAttention", args.rows),
+                args.sampler.upper(), args.ddim_steps, "UNet_Film (attention)" if args.variant == "attn" else "UNet_Film_noAttention", args.rows) + ("" if args.dim == 5 else ", prediction_dim=%d" % args.dim),
             "global_batch": total_B, "per_gpu_batch": args.batch, "denoise_steps": args.ddim_steps, "precision": args.precision,
             "parallelism": "batch-sharded x%d, final all_gather" % args.gpus,
             "cache": "inputs_larger_than_l2 (283 MB of frames per step per GPU)", "graph_steps": args.graph_steps, "concurrent_sub_batches": args.split}
@@ -209,7 +210,7 @@ def main():
     # ---- model (random init, same on every rank), public wrapper of the reference surface --------------------
     torch.manual_seed(0)
     Wrapper = spdm.Diffusion_DDIM
-    model = Wrapper(noise_steps=1000, obs_horizon=10, pred_horizon=rows - 1, observation_dim=135, prediction_dim=5,
+    model = Wrapper(noise_steps=1000, obs_horizon=10, pred_horizon=rows - 1, observation_dim=135, prediction_dim=args.dim,
                     model="UNet_Film" if attention else "UNet_FilmnoAttention", inpaint_horizon=1).to(dev).eval()
     model.configure(precision=args.precision, graph_steps=args.graph_steps, batch_max=B, split=args.split)
     if args.sampler == "ddim":
@@ -223,11 +224,11 @@ def main():
     host = synth_batch(B, 10, 1234 + rank, pin=True)
     devb = {k: v.to(dev) for k, v in host.items()}
     g = torch.Generator().manual_seed(77 + rank)
-    x_T = torch.rand((B, 1, rows, 5), generator=g).to(dev)
+    x_T = torch.rand((B, 1, rows, args.dim), generator=g).to(dev)
     plan = model._plan(B)
     model._bind_schedule(plan)
     inpaint = model.prepare_inpaint_vectors(devb).reshape(B, -1).contiguous()
-    gathered = [torch.empty((B, 1, rows, 5), device=dev) for _ in range(world)] if world > 1 else None
+    gathered = [torch.empty((B, 1, rows, args.dim), device=dev) for _ in range(world)] if world > 1 else None
 
     def step_device(i):
         plan.encode_cond(devb["image"], devb["position"], devb["action"], devb["velocity"])
@@ -289,7 +290,7 @@ def main():
     ms_e2e = timed(step_e2e, args.steps)
     e2e_value = total_B * args.steps / (ms_e2e / 1000.0)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = B * rows * 5 * 4
+    d2h = B * rows * args.dim * 4
 
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), CUDA events around each launch ----------
     pk = peaks()

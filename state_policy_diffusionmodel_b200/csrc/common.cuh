@@ -145,6 +145,9 @@ struct StepArgs {
 // launchers implemented in kernels.cu ------------------------------------------------------------
 template <typename TI, typename TO> void launch_gemm_simt(const GemmSimtArgs& a, cudaStream_t s);
 template <typename TI, typename TO> void launch_apply(const ApplyArgs& a, int B, cudaStream_t s);
+// GroupNorm (statistics + apply, +GELU/temb/FiLM) of a split-K conv: sums the S fp32 partial tiles per element first.
+// One block per sample; HW*C <= 16384 and a multiple of 1024.  a.raw is ignored, partial = [S][M][C] fp32.
+void launch_apply_partial(const ApplyArgs& a, const float* partial, int S, long long M, int B, cudaStream_t s);
 template <typename T> void launch_stats(const T* raw, float* stats, int B, int HW, int C, int ld, cudaStream_t s);  // P = 1
 template <typename T> void launch_pool(const T* in, int ld_in, T* out, int ld_out, int B, int Ho, int Wo, int C, cudaStream_t s);
 template <typename T> void launch_upsample(const T* in, int ld_in, T* out, int ld_out, int B, int Hi, int Wi, int C, cudaStream_t s);
@@ -185,7 +188,10 @@ void tc_gemm_destroy(TcGemm* g);
 // vt[row / vt_lk][C][row % vt_lk] for sdpa_tc instead of to `out`.
 int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const float* bias, const bf16* resid,
                    int ld_res, int flags, int B, cudaStream_t s, bf16* vt = nullptr, int vt_lk = 0,
-                   const ApplyArgs* fuse = nullptr);
+                   const ApplyArgs* fuse = nullptr, int ksplit = 1, float* partial = nullptr);
+// Split-K factor worth using for a 3x3 conv launch of B samples (1 = none).  With ksplit > 1 tc_gemm_launch writes
+// fp32 partial tiles [ksplit][B*H*W][Cout] to `partial` instead of `out`; launch_apply_partial sums them.
+int tc_gemm_split(const TcGemm* g, int B);
 // True when a launch for B samples keeps whole samples and all channels inside one tile, so that GroupNorm apply
 // (+GELU, +temb, +FiLM) can run in the conv epilogue (pass `fuse`; `out` then receives the activated map).
 bool tc_gemm_can_fuse_apply(const TcGemm* g, int B);

@@ -50,6 +50,8 @@ struct TcParams {
   float* stats;
   const float* bias;
   const bf16* resid;
+  int ksplit;             // > 1: the K loop of every tile is cut into ksplit pieces run by different CTAs (split-K)
+  float* partial;         // ksplit > 1: fp32 partial tiles [ksplit][m_tiles*128][Cout], summed by apply_partial_kernel
   ApplyArgs ap;           // EPI_APPLY: GroupNorm apply (+GELU, +temb, +FiLM) fused behind the accumulator (raw/out/stats unused)
   bf16* vt;               // EPI_VT: columns >= vt_c0 go, transposed, to vt[row / vt_lk][col - vt_c0][row % vt_lk]
   int vt_c0, vt_C, vt_lk;
@@ -58,7 +60,7 @@ struct TcParams {
 // ---------------------------------------------------------------------------------------------
 // The kernel.  grid = min(total_tiles, #SM); dynamic smem = STAGES*(A+B) + 1024 (alignment slack).
 // ---------------------------------------------------------------------------------------------
-struct TileCoord { int m_tile, n_tile, b0, h0, n0; };
+struct TileCoord { int m_tile, n_tile, b0, h0, n0, ks; };
 
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
 
@@ -81,6 +83,8 @@ __device__ __forceinline__ const float* temb_row(const ApplyArgs& ap, int b) {
 
 __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, int block_n) {
   TileCoord t;
+  t.ks = 0;
+  if (p.ksplit > 1) { t.ks = tile % p.ksplit; tile /= p.ksplit; }
   t.n_tile = tile % p.n_tiles;  // n fastest: CTAs running side by side share the same A tile in L2
   t.m_tile = tile / p.n_tiles;
   const int tiles_per_sample = p.H / p.Hb;  // > 1 only when Bt == 1
@@ -138,7 +142,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       uint32_t kit = 0;
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         const TileCoord t = decode_tile(p, tile, BLOCK_N);
-        for (int it = 0; it < k_iters; ++it, ++kit) {
+        const int it_begin = p.ksplit > 1 ? t.ks * k_iters / p.ksplit : 0;
+        const int it_end = p.ksplit > 1 ? (t.ks + 1) * k_iters / p.ksplit : k_iters;
+        for (int it = it_begin; it < it_end; ++it, ++kit) {
           const int s = kit % STAGES;
           const uint32_t ph = (kit / STAGES) & 1u;
           mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -169,7 +175,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         mbar_wait(&tmem_empty_bar[acc], aph ^ 1u);  // epilogue has drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int it = 0; it < k_iters; ++it, ++kit) {
+        int it_begin = 0, it_end = k_iters;
+        if (p.ksplit > 1) { const int ks = tile % p.ksplit; it_begin = ks * k_iters / p.ksplit; it_end = (ks + 1) * k_iters / p.ksplit; }
+        for (int it = it_begin; it < it_end; ++it, ++kit) {
           const int s = kit % STAGES;
           const uint32_t ph = (kit / STAGES) & 1u;
           if (!(p.dbg & 16)) mbar_wait(&full_bar[s], ph);
@@ -179,7 +187,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
+            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > it_begin || k > 0) ? 1u : 0u);
           }
           if (!(p.dbg & 16)) umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
         }
@@ -209,6 +217,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         tc_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        continue;
+      }
+      if (p.ksplit > 1) {  // split-K: this CTA owns one slice of the K loop; fp32 partial tile, reduced by apply_partial_kernel
+        float* prow = p.partial + ((size_t)t.ks * ((size_t)p.m_tiles * BLOCK_M) + (size_t)row) * p.Cout + t.n0;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 32) {
+          uint32_t v[32];
+          tmem_ld_32x32(t_addr + (uint32_t)c, v);
+          tmem_ld_wait();
+          if (c + 32 == BLOCK_N) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          }
+#pragma unroll
+          for (int i = 0; i < 32; i += 4)
+            *reinterpret_cast<uint4*>(prow + c + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+        }
         continue;
       }
       if (p.flags & EPI_APPLY) {
@@ -791,6 +817,24 @@ static bool swap_taken(const TcGemm* g, int m_tiles, int flags) {
   return g->can_swap && (flags & ~EPI_APPLY) == EPI_STATS && m_tiles % 2 == 0 && !(g_tc_dbg & 64);
 }
 
+// Split-K factor for a 3x3 conv launch of B samples: > 1 when the 128x256 tiles alone would leave most SMs idle
+// (the K loop of a tile is a serial chain of ~150-cycle MMAs, so at small batch the deep levels are latency-bound).
+int tc_gemm_split(const TcGemm* g, int B) {
+  if (g_tc_dbg & 512) return 1;
+  const TcParams& p = g->p;
+  if (p.taps != 9) return 1;
+  const int m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
+  const int bn = g->has256 ? 256 : g->block_n;
+  const int tiles = m_tiles * (p.Cout / bn);
+  const bool skip_dx = p.W == 1, skip_dy = p.H == 1;
+  const int k_iters = (skip_dx ? 1 : 3) * (skip_dy ? 1 : 3) * p.kb_per_tap;
+  if (tiles * 2 > num_sms() || k_iters < 8) return 1;
+  int s = num_sms() / tiles;
+  if (s > k_iters / 4) s = k_iters / 4;
+  if (s > 8) s = 8;
+  return s < 2 ? 1 : s;
+}
+
 bool tc_gemm_can_fuse_apply(const TcGemm* g, int B) {
   if (g_tc_dbg & 256) return false;
   const TcParams& p = g->p;
@@ -803,14 +847,16 @@ bool tc_gemm_can_fuse_apply(const TcGemm* g, int B) {
 }
 
 int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const float* bias, const bf16* resid, int ld_res, int flags,
-                   int B, cudaStream_t s, bf16* vt, int vt_lk, const ApplyArgs* fuse) {
+                   int B, cudaStream_t s, bf16* vt, int vt_lk, const ApplyArgs* fuse, int ksplit, float* partial) {
   TcParams p = g->p;
   if (fuse) { p.ap = *fuse; flags |= EPI_APPLY; }
+  p.ksplit = ksplit > 1 ? ksplit : 1;
+  p.partial = partial;
   p.dbg = g_tc_dbg;
   p.vt = vt; p.vt_lk = vt_lk; p.vt_C = p.Cout / 3; p.vt_c0 = 2 * (p.Cout / 3);
   p.out = out; p.ld_out = ld_out; p.stats = stats; p.bias = bias; p.resid = resid; p.ld_res = ld_res; p.flags = flags;
   p.m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
-  if (swap_taken(g, p.m_tiles, flags)) {
+  if (p.ksplit == 1 && swap_taken(g, p.m_tiles, flags)) {
     p.n_tiles = (p.Cout + BLOCK_M - 1) / BLOCK_M;
     p.total_tiles = (p.m_tiles / 2) * p.n_tiles;
     const int pps = p.H * p.W;
@@ -829,7 +875,7 @@ int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const f
   const bool use256 = g->has256 && !(g_tc_dbg & 128);
   const int bn = use256 ? 256 : g->block_n;
   p.n_tiles = p.Cout / bn;
-  p.total_tiles = p.m_tiles * p.n_tiles;
+  p.total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
   p.P = partials_for(p, p.n_tiles);
   if (bn == 256) launch_cfg<256, 4>(g->map_a, g->map_b256, p, s);
   else if (bn == 192) launch_cfg<192, 4>(g->map_a, g->map_b, p, s);

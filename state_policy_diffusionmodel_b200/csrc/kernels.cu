@@ -273,6 +273,92 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(ApplyArgs a) {
   }
 }
 }  // namespace
+namespace {
+// Split-K reduction + GroupNorm(1, C) + apply in one pass: a block owns one sample, whose HW*C values (<= 16384) stay
+// in registers between the statistics pass and the normalisation pass.  Output bf16.
+template <int EPT>  // float4 groups per thread: HW*C = 256 threads * EPT * 4
+__global__ void __launch_bounds__(256) apply_partial_kernel(ApplyArgs a, const float* __restrict__ partial, int S, long long M) {
+  pdl_wait();
+  pdl_trigger();
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = a.HW * a.C;
+  const size_t sample0 = (size_t)b * n;              // partial tiles are [M][C] with ld == C: a sample is contiguous
+  const size_t slice = (size_t)M * a.C;
+  float4 x[EPT];
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int idx = (k * 256 + tid) * 4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (idx < n) {
+      for (int sp = 0; sp < S; ++sp) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(partial + sp * slice + sample0 + idx));
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    x[k] = acc;
+    s += (acc.x + acc.y) + (acc.z + acc.w);
+    q = fmaf(acc.x, acc.x, q); q = fmaf(acc.y, acc.y, q); q = fmaf(acc.z, acc.z, q); q = fmaf(acc.w, acc.w, q);
+  }
+  __shared__ float ss[8], sq[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((tid & 31) == 0) { ss[tid >> 5] = s; sq[tid >> 5] = q; }
+  __syncthreads();
+  float ts = 0.f, tq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { ts += ss[i]; tq += sq[i]; }
+  const float inv_n = 1.0f / (float)n;
+  const float mean = ts * inv_n;
+  const float rstd = rsqrtf(fmaxf(tq * inv_n - mean * mean, 0.f) + a.eps);
+  const float* temb = nullptr;
+  if (a.temb_mode != TEMB_NONE) {
+    int trow = 0;
+    if (a.temb_mode == TEMB_PER_SAMPLE) trow = b;
+    else if (a.temb_mode == TEMB_STEP) trow = *a.step_ptr;
+    temb = a.temb + (size_t)trow * SPDM_TEMB_WIDTH + a.temb_off;
+  }
+  const float* film = a.film ? a.film + (size_t)b * SPDM_FILM_WIDTH + a.film_off : nullptr;
+  bf16* __restrict__ out = reinterpret_cast<bf16*>(a.out);
+#pragma unroll
+  for (int k = 0; k < EPT; ++k) {
+    const int idx = (k * 256 + tid) * 4;
+    if (idx >= n) break;
+    const int row = idx / a.C, c = idx - row * a.C;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(a.gamma + c));
+    const float4 be = __ldg(reinterpret_cast<const float4*>(a.beta + c));
+    float y[4] = {(x[k].x - mean) * rstd * g.x + be.x, (x[k].y - mean) * rstd * g.y + be.y,
+                  (x[k].z - mean) * rstd * g.z + be.z, (x[k].w - mean) * rstd * g.w + be.w};
+    if (a.act == ACT_GELU) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[i] = 0.5f * y[i] * (1.0f + erf_fast(y[i] * 0.70710678118654752440f));
+    }
+    if (temb) {
+      const float4 t4 = __ldg(reinterpret_cast<const float4*>(temb + c));
+      y[0] += t4.x; y[1] += t4.y; y[2] += t4.z; y[3] += t4.w;
+    }
+    if (film) {
+      const float4 f0 = __ldg(reinterpret_cast<const float4*>(film + c));
+      const float4 f1 = __ldg(reinterpret_cast<const float4*>(film + a.C + c));
+      y[0] = fmaf(f0.x, y[0], f1.x); y[1] = fmaf(f0.y, y[1], f1.y); y[2] = fmaf(f0.z, y[2], f1.z); y[3] = fmaf(f0.w, y[3], f1.w);
+    }
+    uint2 o;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+    ho[0] = __floats2bfloat162_rn(y[0], y[1]);
+    ho[1] = __floats2bfloat162_rn(y[2], y[3]);
+    *reinterpret_cast<uint2*>(out + ((size_t)b * a.HW + row) * a.ld_out + c) = o;
+  }
+}
+}  // namespace
+void launch_apply_partial(const ApplyArgs& a, const float* partial, int S, long long M, int B, cudaStream_t s) {
+  const int n = a.HW * a.C;
+  const int ept = (n + 1023) / 1024;
+  if (ept <= 2) launch_pdl(apply_partial_kernel<2>, dim3(B), dim3(256), 0, s, a, partial, S, M);
+  else if (ept <= 4) launch_pdl(apply_partial_kernel<4>, dim3(B), dim3(256), 0, s, a, partial, S, M);
+  else if (ept <= 8) launch_pdl(apply_partial_kernel<8>, dim3(B), dim3(256), 0, s, a, partial, S, M);
+  else launch_pdl(apply_partial_kernel<16>, dim3(B), dim3(256), 0, s, a, partial, S, M);
+  COUNT_LAUNCH();
+}
 template <typename TI, typename TO> void launch_apply(const ApplyArgs& a, int B, cudaStream_t s) {
   const int nvec = a.HW * (a.C >> 3);
   // the per-thread prologue (statistics fold, 40 per-channel constants) is amortised over more vectors once the

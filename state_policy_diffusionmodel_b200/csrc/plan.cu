@@ -119,6 +119,9 @@ struct spdm_plan {
   cudaStream_t own_stream = nullptr;  // graphs are captured and replayed here (the caller's stream may be the legacy stream)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int split = 1;                       // sub-batches run concurrently per denoising step
+  std::map<int, float*> partial;       // split-K fp32 partial tiles, one buffer per concurrent lane (keyed by b0)
+  std::map<int, size_t> partial_cap;
+  bool no_splitk = false;              // SPDM_NO_SPLITK=1 (A/B switch)
   bool no_fuse = false;                // SPDM_NO_FUSE_APPLY=1: keep GroupNorm apply as a separate kernel (A/B switch)
   int fuse_mode = 0;                   // SPDM_FUSE_MODE: 0 none (default: measured faster, the 4-warp epilogue is the bottleneck), 1 GELU-free convs, 2 all
   cudaStream_t lane_stream[7] = {};
@@ -443,6 +446,25 @@ template <typename T> struct Fwd {
     return tc;
   }
 
+  // split-K factor for this conv at the current batch (1 = none); sizes the lane's partial buffer on first use
+  int split_for(const std::string& wname, const T* in, int ld_in, int level, int Cout) {
+    if constexpr (sizeof(T) == 2) {
+      if (p->no_splitk) return 1;
+      const int n = p->levelH(level) * p->levelW(level) * Cout;
+      if (n > 16384 || n % 1024) return 1;
+      GemmW& g = p->gemms[wname];
+      const int S = tc_gemm_split(get_tc(wname, g, in, ld_in, level), Bpad);
+      if (S > 1) {
+        const size_t need = (size_t)S * Bpad * n;
+        float*& buf = p->partial[c.b0];
+        size_t& cap = p->partial_cap[c.b0];
+        if (cap < need) { buf = p->alloc<float>(need); cap = need; }  // first (eager) step only; graphs reuse it
+      }
+      return S;
+    }
+    return 1;
+  }
+
   // can GroupNorm apply run inside this conv's epilogue (whole samples and all channels in one tile)?
   bool can_fuse(const std::string& wname, const T* in, int ld_in, int level) {
     if constexpr (sizeof(T) == 2) {
@@ -455,7 +477,7 @@ template <typename T> struct Fwd {
 
   // conv / linear: in [M,Cin] (ld_in) -> out [M,Cout] (ld_out)
   void gemm(const std::string& wname, const T* in, int ld_in, int level, T* out, int ld_out, int flags, const T* resid = nullptr,
-            int ld_res = 0, const ApplyArgs* fuse = nullptr) {
+            int ld_res = 0, const ApplyArgs* fuse = nullptr, int ksplit = 1, float* partial = nullptr) {
     auto it = p->gemms.find(wname);
     REQUIRE(it != p->gemms.end(), "internal: unknown gemm %s", wname.c_str());
     GemmW& g = it->second;
@@ -469,7 +491,7 @@ template <typename T> struct Fwd {
       int P = 1;
       timed(p, c.s, g.taps == 9 ? PC_CONV3 : PC_GEMM1, flops, bytes, [&] {
         P = tc_gemm_launch(tc, reinterpret_cast<bf16*>(out), ld_out, stats(), (flags & EPI_BIAS) ? g.bias : nullptr,
-                           reinterpret_cast<const bf16*>(resid), ld_res, flags, Bpad, c.s, vt, vt_lk, fuse);
+                           reinterpret_cast<const bf16*>(resid), ld_res, flags, Bpad, c.s, vt, vt_lk, fuse, ksplit, partial);
       });
       REQUIRE(fuse || !(flags & EPI_STATS) || P <= SPDM_MAX_PARTIALS, "%s: too many GroupNorm partials (%d)", wname.c_str(), P);
       curP = P;
@@ -517,8 +539,16 @@ template <typename T> struct Fwd {
     T* h = act(p->hbuf[level], level);
     const bool tap1 = p->tap_out && p->tap_name == name + ".first", tap2 = p->tap_out && p->tap_name == name + ".second";
     bool fused = false;
+    const long long Mpad = (long long)Bpad * p->levelH(level) * p->levelW(level);
     if (!first_done) {
-      if (!tap1 && p->fuse_mode >= 2 && can_fuse(name + ".first", in, ld_in, level)) {
+      const int S = tap1 ? 1 : split_for(name + ".first", in, ld_in, level, Cout);
+      if (S > 1) {
+        gemm(name + ".first", in, ld_in, level, raw, Cout, EPI_STATS, nullptr, 0, nullptr, S, p->partial[c.b0]);
+        ApplyArgs a = make_apply(name + ".norm", Cout, level, ACT_GELU, nullptr);
+        a.out = h; a.ld_out = Cout;
+        timed(p, c.s, PC_APPLY, 0, (4.0 * S + 2.0) * c.B * a.HW * Cout, [&] { launch_apply_partial(a, p->partial[c.b0], S, Mpad, c.B, c.s); });
+        fused = true;
+      } else if (!tap1 && p->fuse_mode >= 2 && can_fuse(name + ".first", in, ld_in, level)) {
         const ApplyArgs a = make_apply(name + ".norm", Cout, level, ACT_GELU, nullptr);
         gemm(name + ".first", in, ld_in, level, h, Cout, EPI_STATS, nullptr, 0, &a);
         fused = true;
@@ -530,7 +560,13 @@ template <typename T> struct Fwd {
       tap(name + ".first", raw, Cout, Cout, level);
       apply(name + ".norm", raw, Cout, Cout, level, h, Cout, ACT_GELU, nullptr);
     }
-    if (!tap2 && p->fuse_mode >= 1 && can_fuse(name + ".second", h, Cout, level)) {
+    const int S2 = tap2 ? 1 : split_for(name + ".second", h, Cout, level, Cout);
+    if (S2 > 1) {
+      gemm(name + ".second", h, Cout, level, raw, Cout, EPI_STATS, nullptr, 0, nullptr, S2, p->partial[c.b0]);
+      ApplyArgs a = make_apply(name + ".norm", Cout, level, ACT_NONE, st);
+      a.out = out; a.ld_out = ld_out;
+      timed(p, c.s, PC_APPLY, 0, (4.0 * S2 + 2.0) * c.B * a.HW * Cout, [&] { launch_apply_partial(a, p->partial[c.b0], S2, Mpad, c.B, c.s); });
+    } else if (!tap2 && p->fuse_mode >= 1 && can_fuse(name + ".second", h, Cout, level)) {
       const ApplyArgs a = make_apply(name + ".norm", Cout, level, ACT_NONE, st);
       gemm(name + ".second", h, Cout, level, out, ld_out, EPI_STATS, nullptr, 0, &a);
     } else {
@@ -816,6 +852,7 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
     if (const char* e = getenv("SPDM_SPLIT")) p->split = atoi(e);
     if (const char* e = getenv("SPDM_NO_FUSE_APPLY")) p->no_fuse = atoi(e) != 0;
     if (const char* e = getenv("SPDM_FUSE_MODE")) p->fuse_mode = atoi(e);
+    if (const char* e = getenv("SPDM_NO_SPLITK")) p->no_splitk = atoi(e) != 0;
     if (p->split < 1) p->split = 1;
     if (p->split > 8) p->split = 8;
     CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
