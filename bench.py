@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=31)
     ap.add_argument("--dim", type=int, default=5, help="prediction_dim (5 = position+action, 2 = position only)")
     ap.add_argument("--graph-steps", type=int, default=10)
-    ap.add_argument("--split", type=int, default=2, help="concurrent sub-batches per denoising step")
+    ap.add_argument("--split", type=int, default=1, help="concurrent sub-batches per denoising step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="one sampling call, for ncu")
     return ap.parse_args()
