@@ -18,6 +18,7 @@
 //   streaming across tile boundaries and the epilogue of tile i overlaps the MMAs of tile i+1.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -405,11 +406,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 // columns; the epilogue writes the channels-last output with 64-byte warp stores (one pixel per instruction).
 // Only EPI_STATS epilogues (the 3x3 convolutions) take this path.
 // ---------------------------------------------------------------------------------------------
-template <int STAGES>
+// WM = weight rows per tile = M of the MMA: 128 (rows >= Cout are TMA zero fill) or 64 for the 64-channel layers, whose
+// accumulator then sits in 16 lanes of each TMEM lane quarter (row i -> lane 32*(i/16) + i%16).
+template <int STAGES, int WM>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   constexpr int PIX_BYTES = 2 * A_STAGE_BYTES;           // 256 pixels x 64 ch
-  constexpr int W_BYTES = BLOCK_M * BLOCK_K * 2;         // 128 weight rows x 64 k
+  constexpr int W_BYTES = WM * BLOCK_K * 2;              // WM weight rows x 64 k
   constexpr int NPIX = 256;
   constexpr int TMEM_COLS = 2 * NPIX;
   extern __shared__ uint8_t smem_raw[];
@@ -468,13 +471,13 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           mbar_expect_tx(&full_bar[s], PIX_BYTES + W_BYTES);
           tma_load_4d(smem_pix + s * PIX_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t0.h0 + dy, t0.b0);
           tma_load_4d(smem_pix + s * PIX_BYTES + A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t1.h0 + dy, t1.b0);
-          tma_load_2d(smem_w + s * W_BYTES, &map_w, &full_bar[s], tap * p.Cin + kb * BLOCK_K, c_tile * BLOCK_M);
+          tma_load_2d(smem_w + s * W_BYTES, &map_w, &full_bar[s], tap * p.Cin + kb * BLOCK_K, c_tile * WM);
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(NPIX);
+      constexpr uint32_t idesc = make_idesc_m(WM, NPIX);
       uint32_t kit = 0;
       int lt = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
@@ -500,10 +503,13 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else {
     const int q = warp & 3;
-    const int ch_local = q * 32 + lane;                 // TMEM lane == output channel inside the 128-channel tile
+    // TMEM lane -> output channel inside the tile
+    const bool layout_b = (p.dbg & 1024) != 0;          // M = 64 alternative hypothesis: rows 0..63 in lanes 0..63
+    const int ch_local = (WM == 128 || layout_b) ? q * 32 + lane : q * 16 + lane;
+    const bool lane_ok = (WM == 128 || layout_b) ? true : lane < 16;
     const int pps = p.H * p.W;                          // pixels per sample
     const int tiles_per_sample = pps > NPIX ? pps / NPIX : 1;
-    const int nw = (p.Cout >= BLOCK_M) ? 4 : p.Cout / 32;  // epilogue warps that own real channels
+    const int nw = WM == 128 ? ((p.Cout >= BLOCK_M) ? 4 : p.Cout / 32) : (layout_b ? 2 : 4);  // warps that own real channels
     int lt = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
       const int c_tile = tile % c_tiles, pt = tile / c_tiles;
@@ -513,7 +519,7 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_wait(&tmem_full_bar[acc], aph);
       tc_fence_after();
       const bool active = q < nw;
-      const int ch = c_tile * BLOCK_M + ch_local;
+      const int ch = c_tile * WM + ch_local;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NPIX);
       float rs = 0.f, rq = 0.f;
       if (p.flags & EPI_APPLY) {
@@ -636,9 +642,9 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float f = __uint_as_float(v[i]);
+              const float f = lane_ok ? __uint_as_float(v[i]) : 0.f;
               s4[i & 3] += f; q4[i & 3] = fmaf(f, f, q4[i & 3]);
-              optr[(size_t)i * p.ld_out] = __float2bfloat16_rn(f);
+              if (lane_ok) optr[(size_t)i * p.ld_out] = __float2bfloat16_rn(f);
             }
             rs += (s4[0] + s4[1]) + (s4[2] + s4[3]);
             rq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
@@ -659,9 +665,9 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             float sa = 0.f, qa = 0.f, sb = 0.f, qb = 0.f;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-              const float f = __uint_as_float(v[i]);
+              const float f = lane_ok ? __uint_as_float(v[i]) : 0.f;
               if (i < 16) { sa += f; qa = fmaf(f, f, qa); } else { sb += f; qb = fmaf(f, f, qb); }
-              optr[(size_t)i * p.ld_out] = __float2bfloat16_rn(f);
+              if (lane_ok) optr[(size_t)i * p.ld_out] = __float2bfloat16_rn(f);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
@@ -864,10 +870,22 @@ int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const f
     p.P = (pps > 256 ? pps / 256 : 1) * p.n_tiles * nw;
     constexpr int STG = 4;
     constexpr int smem = STG * (2 * A_STAGE_BYTES + BLOCK_M * BLOCK_K * 2) + 1024;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(conv_tc_swap_kernel<STG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    static int m64_mode = -1;  // SPDM_M64: 0 = off, 1 = on (TMEM layout A), 2 = on (layout B)
+    if (m64_mode < 0) { const char* e = getenv("SPDM_M64"); m64_mode = e ? atoi(e) : 1; }
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
-    launch_pdl(conv_tc_swap_kernel<STG>, dim3(grid), dim3(NUM_THREADS), smem, s, g->map_a, g->map_wswap, p);
+    if (p.Cout == 64 && !fuse && m64_mode > 0) {  // 64-row MMA: no zero rows, half the operand-read time per instruction
+      const int nw64 = m64_mode == 2 ? 2 : 4;
+      p.P = (pps > 256 ? pps / 256 : 1) * p.n_tiles * nw64;
+      if (m64_mode == 2) p.dbg |= 1024;
+      static bool attr64 = false;
+      if (!attr64) { cudaFuncSetAttribute(conv_tc_swap_kernel<STG, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr64 = true; }
+      launch_pdl(conv_tc_swap_kernel<STG, 64>, dim3(grid), dim3(NUM_THREADS), smem, s, g->map_a, g->map_b, p);
+      ++g_tc_launches;
+      return p.P;
+    }
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(conv_tc_swap_kernel<STG, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    launch_pdl(conv_tc_swap_kernel<STG, 128>, dim3(grid), dim3(NUM_THREADS), smem, s, g->map_a, g->map_wswap, p);
     ++g_tc_launches;
     return p.P;
   }

@@ -338,3 +338,56 @@ def test_bf16_encoder_path(spdm, golden_dir):
     out = plan.encode_images(img)
     assert rel(out, g["out"]) < 1e-2
     plan.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unet_forward_4x_horizon(spdm, precision):
+    """Prediction horizon 4x the repo default (rows = 121 -> 128x8 padded map, 1024-token attention at the top level):
+    the geometry of BASELINE configs[4]; checked against the oracle (pinned to the reference at rows 31 and 61)."""
+    sd = fixtures.make_unet_weights(attention=True, seed=2)
+    g = torch.Generator().manual_seed(31)
+    B = 2
+    x = torch.rand((B, 1, 121, 5), generator=g)
+    y = torch.randn((B, 1, 10, 135), generator=g)
+    t = torch.tensor([250, 3])
+    with torch.no_grad():
+        ref = unet_ref.unet_forward(sd, x, t, y, attention=True)
+    plan = spdm.DenoisePlan(attention=True, precision=precision, batch_max=B, rows=121, dim=5, graph_steps=0)
+    plan.load_unet_state_dict(sd)
+    out = plan.unet_forward(x, t, y)
+    assert out.shape == ref.shape
+    assert rel(out, ref) < (FP32_TOL if precision == "fp32" else BF16_FWD_TOL)
+    plan.close()
+
+
+def test_error_paths_are_loud(spdm):
+    """No silent fallback: misuse of the C ABI reports an error message instead of computing something else."""
+    from state_policy_diffusionmodel_b200._lib import SpdmError
+    sd = fixtures.make_unet_weights(attention=False, seed=0)
+    plan = spdm.DenoisePlan(attention=False, precision="bf16", batch_max=4, graph_steps=1)
+    x = torch.rand((2, 1, 31, 5))
+    with pytest.raises(SpdmError, match="weights missing"):
+        plan.unet_forward(x, torch.tensor([1]), None)
+    with pytest.raises(SpdmError, match="unexpected weight name"):
+        plan.load_weight("inc.third.weight", torch.zeros(3))
+    with pytest.raises(SpdmError, match="shape"):
+        plan.load_weight("inc.second.weight", torch.zeros(64, 64, 1, 1))
+    plan.load_unet_state_dict(sd)
+    with pytest.raises(SpdmError, match="batch_max"):
+        plan.unet_forward(torch.rand((5, 1, 31, 5)), torch.tensor([1]), None)
+    with pytest.raises(SpdmError, match="conditioning"):
+        plan.sample(x)
+    plan.set_cond(torch.zeros((2, 1350)))
+    with pytest.raises(SpdmError, match="no schedule"):
+        plan.sample(x)
+    sch = spdm.DDIMScheduler(num_train_timesteps=4, beta_schedule="linear", clip_sample=False, prediction_type="epsilon")
+    sch.set_timesteps(4)
+    plan.set_schedule("ddim", sch.coef_table(), sch.timesteps)
+    assert torch.isfinite(plan.sample(x)).all()
+    with pytest.raises(SpdmError, match="t_count"):
+        plan.unet_forward(x, torch.tensor([1, 2, 3]), None)
+    plan.close()
+    with pytest.raises(NotImplementedError):
+        spdm.DDPMScheduler(num_train_timesteps=10, clip_sample=True)
+    with pytest.raises(NotImplementedError):
+        spdm.Diffusion_DDPM(model="UNet")
