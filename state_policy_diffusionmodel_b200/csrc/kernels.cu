@@ -635,29 +635,52 @@ template void launch_sdpa<bf16>(const bf16*, bf16*, int, int, int, int, cudaStre
 // (models/Unet_FiLmLayer.py:15-34,286,101).  outc: Conv2d(64 -> 1, 1x1) + bias + unpad (:264,310).
 // =================================================================================================
 namespace {
+// One block per sample: the unpadded sample and the 9x64 weights sit in shared memory, every thread keeps 8 channels
+// of a pixel, and the block also produces the sample's GroupNorm (sum, sumsq) (P = 1 partial) -- no separate pass.
 template <typename T>
-__global__ void conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /*[9][64]*/, T* __restrict__ out, long long total,
-                               int H, int W, int rows, int dim, int lh, int lw) {
+__global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ x, const float* __restrict__ w /*[9][64]*/, T* __restrict__ out,
+                                                      float* __restrict__ stats, int H, int W, int rows, int dim, int lh, int lw) {
+  extern __shared__ float csm[];  // [9*64] weights, then [rows*dim] sample
+  float* sw = csm;
+  float* sx = csm + 9 * 64;
+  const int tid = threadIdx.x, b = blockIdx.x;
+  for (int i = tid; i < 9 * 64; i += 256) sw[i] = __ldg(w + i);
   pdl_wait();
   pdl_trigger();
-  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= total) return;
-  const long long r = v >> 3;
-  const int c8 = (int)(v & 7) << 3;
-  const int ww = (int)(r % W);
-  const long long t = r / W;
-  const int hh = (int)(t % H);
-  const long long b = t / H;
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int i = tid; i < rows * dim; i += 256) sx[i] = x[(size_t)b * rows * dim + i];
+  __syncthreads();
+  const int c8 = (tid & 7) << 3;
+  float s = 0.f, q = 0.f;
+  for (int px = tid >> 3; px < H * W; px += 32) {
+    const int hh = px / W, ww = px - hh * W;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-  for (int tap = 0; tap < 9; ++tap) {
-    const int sh = hh + tap / 3 - 1 - lh, sw = ww + tap % 3 - 1 - lw;  // coordinates in the unpadded sample
-    if (sh < 0 || sh >= rows || sw < 0 || sw >= dim) continue;
-    const float xv = __ldg(x + (b * rows + sh) * dim + sw);
+    for (int tap = 0; tap < 9; ++tap) {
+      const int sh = hh + tap / 3 - 1 - lh, sw_ = ww + tap % 3 - 1 - lw;  // coordinates in the unpadded sample
+      if (sh < 0 || sh >= rows || sw_ < 0 || sw_ >= dim) continue;
+      const float xv = sx[sh * dim + sw_];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, __ldg(w + tap * 64 + c8 + i), acc[i]);
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(xv, sw[tap * 64 + c8 + i], acc[i]);
+    }
+    store8(out + ((size_t)b * H * W + px) * 64 + c8, acc);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float r = to_f32<T>(from_f32<T>(acc[i]));  // statistics of the values the next kernel will read
+      s += r;
+      q = fmaf(r, r, q);
+    }
   }
-  store8(out + r * 64 + c8, acc);
+  __shared__ float ss[8], sq[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((tid & 31) == 0) { ss[tid >> 5] = s; sq[tid >> 5] = q; }
+  __syncthreads();
+  if (tid == 0) {
+    float ts = 0.f, tq = 0.f;
+    for (int i = 0; i < 8; ++i) { ts += ss[i]; tq += sq[i]; }
+    stats[2 * b] = ts;
+    stats[2 * b + 1] = tq;
+  }
 }
 
 template <typename T>
@@ -695,9 +718,9 @@ __global__ void to_nchw_kernel(const T* __restrict__ in, int ld, float* __restri
   out[v] = to_f32<T>(in[(b * HW + p) * ld + c]);
 }
 }  // namespace
-template <typename T> void launch_conv_in(const float* x, const float* w, T* out, int B, int H, int W, int rows, int dim, int lh, int lw, cudaStream_t s) {
-  const long long total = (long long)B * H * W * 8;
-  launch_pdl(conv_in_kernel<T>, dim3(cdiv(total, 256)), dim3(256), 0, s, x, w, out, total, H, W, rows, dim, lh, lw);
+template <typename T> void launch_conv_in(const float* x, const float* w, T* out, float* stats, int B, int H, int W, int rows, int dim, int lh, int lw, cudaStream_t s) {
+  const size_t smem = (size_t)(9 * 64 + rows * dim) * sizeof(float);
+  launch_pdl(conv_in_kernel<T>, dim3(B), dim3(256), smem, s, x, w, out, stats, H, W, rows, dim, lh, lw);
   COUNT_LAUNCH();
 }
 template <typename T> void launch_outc(const T* x, int ld, const float* w, const float* bias, float* eps, int B, int H, int W, int C, int rows, int dim, int lh, int lw, cudaStream_t s) {
@@ -709,8 +732,8 @@ template <typename T> void launch_to_nchw(const T* in, int ld, float* out, int B
   const long long total = (long long)B * HW * C;
   launch_pdl(to_nchw_kernel<T>, dim3(cdiv(total, 256)), dim3(256), 0, s, in, ld, out, total, HW, C);
 }
-template void launch_conv_in<float>(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
-template void launch_conv_in<bf16>(const float*, const float*, bf16*, int, int, int, int, int, int, int, cudaStream_t);
+template void launch_conv_in<float>(const float*, const float*, float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+template void launch_conv_in<bf16>(const float*, const float*, bf16*, float*, int, int, int, int, int, int, int, cudaStream_t);
 template void launch_outc<float>(const float*, int, const float*, const float*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
 template void launch_outc<bf16>(const bf16*, int, const float*, const float*, float*, int, int, int, int, int, int, int, int, cudaStream_t);
 template void launch_to_nchw<float>(const float*, int, float*, int, int, int, cudaStream_t);
@@ -794,6 +817,54 @@ __global__ void step_kernel(StepArgs a) {
   a.x_out[i] = r;
   if (history) history[(size_t)(step + 1) * total + i] = r;
 }
+// outc (Conv2d(64 -> 1, 1x1) + bias + unpad, models/Unet_FiLmLayer.py:264,310) fused with the posterior update: the
+// noise estimate of an element is consumed by that element's update only, so it never has to exist in memory.
+template <typename T>
+__global__ void outc_step_kernel(StepArgs a, const T* __restrict__ act, int ld, const float* __restrict__ w, const float* __restrict__ bias,
+                                 int H, int W, int C, int rows, int dim, int lh, int lw) {
+  pdl_wait();
+  pdl_trigger();
+  const long long total = (long long)a.B_total * a.n;
+  const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (li >= (long long)a.B * a.n) return;
+  const long long i = (long long)a.b0 * a.n + li;
+  const int step = a.dyn->step;
+  const float* noise = a.dyn->noise ? a.dyn->noise + (size_t)step * total : nullptr;
+  const float* inpaint = a.dyn->inpaint;
+  float* history = a.dyn->history;
+  const float* cf = a.coef + (size_t)step * 8;
+  const float c0 = cf[0], c1 = cf[1], kx0 = cf[2], kx = cf[3], keps = cf[4], kn = cf[5];
+  const long long b = i / a.n;
+  const int e = (int)(i - b * a.n);
+  float r;
+  if (inpaint && e < a.inpaint_elems) {
+    r = inpaint[b * a.inpaint_elems + e];
+  } else {
+    const int d = e % dim, rr = e / dim;
+    const long long lb = li / a.n;  // sample inside this lane's activation buffer
+    const T* arow = act + ((lb * H + rr + lh) * W + d + lw) * ld;
+    float ep = 0.f;
+    for (int c = 0; c < C; c += 8) {
+      float t8[8];
+      load8(arow + c, t8);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) ep = fmaf(t8[k], __ldg(w + c + k), ep);
+    }
+    ep += __ldg(bias);
+    const float x = a.x[i];
+    const float x0 = (x - c0 * ep) / c1;
+    r = kx0 * x0 + kx * x;
+    if (keps != 0.f) r += keps * ep;
+    if (kn != 0.f) {
+      float z = 0.f;
+      if (noise) z = noise[i];
+      else if (a.dyn->use_philox) z = philox_normal(a.dyn->seed, (unsigned long long)i, (uint32_t)step);
+      r += kn * z;
+    }
+  }
+  a.x_out[i] = r;
+  if (history) history[(size_t)(step + 1) * total + i] = r;
+}
 __global__ void advance_kernel(int* p, int d) {
   pdl_wait();
   pdl_trigger(); *p += d; }
@@ -827,6 +898,15 @@ void launch_step(const StepArgs& a, cudaStream_t s) {
   launch_pdl(step_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, a);
   COUNT_LAUNCH();
 }
+template <typename T>
+void launch_outc_step(const StepArgs& a, const T* act, int ld, const float* w, const float* bias, int H, int W, int C, int rows, int dim,
+                      int lh, int lw, cudaStream_t s) {
+  const long long total = (long long)a.B * a.n;
+  launch_pdl(outc_step_kernel<T>, dim3(cdiv(total, 128)), dim3(128), 0, s, a, act, ld, w, bias, H, W, C, rows, dim, lh, lw);
+  COUNT_LAUNCH();
+}
+template void launch_outc_step<float>(const StepArgs&, const float*, int, const float*, const float*, int, int, int, int, int, int, int, cudaStream_t);
+template void launch_outc_step<bf16>(const StepArgs&, const bf16*, int, const float*, const float*, int, int, int, int, int, int, int, cudaStream_t);
 void launch_delay(long long cycles, cudaStream_t s) { launch_pdl(delay_kernel, dim3(1), dim3(1), 0, s, cycles); }
 void launch_advance(int* step_ptr, int delta, cudaStream_t s) { launch_pdl(advance_kernel, dim3(1), dim3(1), 0, s, step_ptr, delta); COUNT_LAUNCH(); }
 void launch_set_int(int* p, int v, cudaStream_t s) { launch_pdl(set_int_kernel, dim3(1), dim3(1), 0, s, p, v); COUNT_LAUNCH(); }

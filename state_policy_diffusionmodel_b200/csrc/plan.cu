@@ -384,6 +384,7 @@ struct FwdCtx {
   const int* step_ptr;
   const float* film;     // [B][1792] or null
   int B;
+  const StepArgs* fuse_step;  // non-null: replace outc by outc + posterior update (the sampling loop)
   int b0;                // first sample of this sub-batch inside the plan's workspace (lanes run concurrently)
   cudaStream_t s;
 };
@@ -639,10 +640,9 @@ template <typename T> struct Fwd {
     T* cat3 = act(p->cat[0], 0); T* cat2 = act(p->cat[1], 1); T* cat1 = act(p->cat[2], 2);
     // ---- inc ----
     const double hw0 = (double)p->H0 * p->W0;
-    timed(p, c.s, PC_IO, 2.0 * 9 * 64 * hw0 * c.B, c.B * hw0 * 64 * sizeof(T),
-          [&] { launch_conv_in<T>(c.x, p->w_in, act(p->raw[0], 0), c.B, p->H0, p->W0, rows, dim, p->lh, p->lw, c.s); });
-    timed(p, c.s, PC_STATS, 0, c.B * hw0 * 64 * sizeof(T),
-          [&] { launch_stats<T>(act(p->raw[0], 0), stats(), c.B, p->H0 * p->W0, 64, 64, c.s); });
+    timed(p, c.s, PC_IO, 2.0 * 9 * 64 * hw0 * c.B, c.B * hw0 * 64 * sizeof(T), [&] {
+      launch_conv_in<T>(c.x, p->w_in, act(p->raw[0], 0), stats(), c.B, p->H0, p->W0, rows, dim, p->lh, p->lw, c.s);
+    });
     curP = 1;
     double_conv("inc", nullptr, 0, 64, 0, cat3 + 64, 128, nullptr, true);  // x1 -> skip slot of up3
     tap("x1", cat3 + 64, 128, 64, 0);
@@ -707,6 +707,12 @@ template <typename T> struct Fwd {
       tap(u.tapname, b, st.cout, st.cout, l);
     }
     // ---- outc + unpad ----
+    if (c.fuse_step) {  // graphed loop: outc + posterior update + inpaint in one kernel, eps never stored
+      timed(p, c.s, PC_STEP, 2.0 * 64 * rows * dim * c.B, c.B * hw0 * 64 * sizeof(T), [&] {
+        launch_outc_step<T>(*c.fuse_step, act(p->bbuf[0], 0), 64, p->w_outc, p->b_outc, p->H0, p->W0, 64, rows, dim, p->lh, p->lw, c.s);
+      });
+      return;
+    }
     timed(p, c.s, PC_IO, 2.0 * 64 * rows * dim * c.B, c.B * hw0 * 64 * sizeof(T), [&] {
       launch_outc<T>(act(p->bbuf[0], 0), 64, p->w_outc, p->b_outc, c.out, c.B, p->H0, p->W0, 64, rows, dim, p->lh, p->lw, c.s);
     });
@@ -745,11 +751,11 @@ void one_lane(spdm_plan* p, int b0, int Bsub, int B, bool use_film, cudaStream_t
   c.x = p->xt + (size_t)b0 * n; c.out = p->eps + (size_t)b0 * n; c.temb = p->temb_table; c.temb_mode = TEMB_STEP;
   c.step_ptr = &p->dyn->step;
   c.film = use_film ? p->film + (size_t)b0 * SPDM_FILM_WIDTH : nullptr; c.B = Bsub; c.b0 = b0; c.s = s;
-  run_forward(p, c);
   StepArgs a{};
   a.x = p->xt; a.eps = p->eps; a.x_out = p->xt; a.coef = p->coef; a.dyn = p->dyn; a.n = p->n_elems();
   a.inpaint_elems = p->cfg.inpaint_rows * p->cfg.dim; a.B = Bsub; a.b0 = b0; a.B_total = B;
-  timed(p, s, PC_STEP, 0, 4.0 * Bsub * p->n_elems() * sizeof(float), [&] { launch_step(a, s); });
+  c.fuse_step = &a;
+  run_forward(p, c);
 }
 
 // One denoising step for B trajectories.  With split > 1 the batch is cut into sub-batches ("lanes") that run the

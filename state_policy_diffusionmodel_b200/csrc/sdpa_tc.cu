@@ -204,6 +204,205 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
   }
 }
 
+// Long sequences (L = 512 or 1024 tokens per sample: the 64x8 / 128x8 maps of the 2x / 4x prediction horizons): the
+// keys of a sample are walked in blocks of 256.  Two passes, so that no accumulator ever has to be rescaled:
+//   pass A  per key block, per head: S = Q K^T -> running row maximum
+//   pass B  per key block, per head: S again -> P = exp2(S - max) -> smem -> O_h += P V_h   (O_h: own TMEM columns)
+// K and V^T blocks are loaded once per pass and shared by the 64/hd heads of the channel block.
+__global__ void __launch_bounds__(256)
+sdpa_tc_long_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_vt, const SdpaParams p) {
+  constexpr int LK = 256, KB = 4, HALF = 128;
+  constexpr int SQ = 16384, SK = LK * 128, SVT = KB * 8192;
+  constexpr int TMEM_COLS = 512;  // S: 256 columns, O: 64 columns (all heads of the channel block)
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + SQ;
+  uint8_t* sVt = sK + SK;
+  uint8_t* sP = sVt + SVT;
+  __shared__ __align__(8) uint64_t bar_load;
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_red[2][128];
+  __shared__ float s_sum[2][4][128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;
+  const int r = (warp & 3) * 32 + lane;
+  const int q_row0 = blockIdx.x * 128;
+  const int cb = blockIdx.y;
+  const int sample = q_row0 / p.L;
+  const int key_row0 = sample * p.L;
+  const int nkb = p.L / LK;
+  const int nh = p.heads_per_blk;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_vt);
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+  pdl_wait();
+  pdl_trigger();
+
+  const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t idesc_s = make_idesc(LK), idesc_o = make_idesc(p.hd);
+  uint32_t mma_phase = 0, load_phase = 0;
+  const int c_begin = half * HALF, c_end = c_begin + HALF;
+  float mrow[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  float srow[4] = {0.f, 0.f, 0.f, 0.f};
+
+  auto issue_s = [&](int h) {  // S = Q_h K_blk,h^T
+    tc_fence_after();
+    const uint64_t head_off = (uint64_t)((h * p.hd * 2) >> 4);
+    const uint64_t dq = make_smem_desc(smem_u32(sQ)) + head_off;
+    const uint64_t dk = make_smem_desc(smem_u32(sK)) + head_off;
+    for (int kk = 0; kk < p.hd / 16; ++kk) umma_bf16(tmem, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc_s, kk > 0 ? 1u : 0u);
+    umma_commit(&bar_mma);
+  };
+
+  // ---------------- pass A: row maxima ----------------
+  for (int jb = 0; jb < nkb; ++jb) {
+    if (tid == 0) {
+      mbar_expect_tx(&bar_load, (jb == 0 ? SQ : 0) + SK);
+      if (jb == 0) tma_load_2d(sQ, &map_qkv, &bar_load, cb * 64, q_row0);
+      tma_load_2d(sK, &map_qkv, &bar_load, p.C + cb * 64, key_row0 + jb * LK);
+      tma_load_2d(sK + 16384, &map_qkv, &bar_load, p.C + cb * 64, key_row0 + jb * LK + 128);
+    }
+    mbar_wait(&bar_load, load_phase);
+    load_phase ^= 1u;
+    for (int h = 0; h < nh; ++h) {
+      if (tid == 0) issue_s(h);
+      mbar_wait(&bar_mma, mma_phase);
+      mma_phase ^= 1u;
+      tc_fence_after();
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + (uint32_t)c, v);
+        tmem_ld_wait();
+        float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+        m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+      }
+      mrow[h] = fmaxf(mrow[h], m);
+      tc_fence_before();
+      __syncthreads();  // S and sK are reused by the next head / key block
+    }
+  }
+  // combine the two column halves of every row
+  for (int h = 0; h < nh; ++h) {
+    s_red[half][r] = mrow[h];
+    __syncthreads();
+    mrow[h] = fmaxf(s_red[0][r], s_red[1][r]) * p.scale_log2;  // pre-scaled maximum
+    __syncthreads();
+  }
+
+  // ---------------- pass B: P = exp2(S - max), O_h += P V_h ----------------
+  for (int jb = 0; jb < nkb; ++jb) {
+    if (tid == 0) {
+      mbar_expect_tx(&bar_load, SK + SVT);
+      tma_load_2d(sK, &map_qkv, &bar_load, p.C + cb * 64, key_row0 + jb * LK);
+      tma_load_2d(sK + 16384, &map_qkv, &bar_load, p.C + cb * 64, key_row0 + jb * LK + 128);
+#pragma unroll
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(sVt + kb * 8192, &map_vt, &bar_load, jb * LK + kb * 64, sample * p.C + cb * 64);
+    }
+    mbar_wait(&bar_load, load_phase);
+    load_phase ^= 1u;
+    for (int h = 0; h < nh; ++h) {
+      if (tid == 0) issue_s(h);
+      mbar_wait(&bar_mma, mma_phase);
+      mma_phase ^= 1u;
+      tc_fence_after();
+      float sum = 0.f;
+#pragma unroll 1
+      for (int c = c_begin; c < c_end; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + (uint32_t)c, v);
+        tmem_ld_wait();
+        uint32_t packed[16];
+        float s2[2] = {0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = exp2f(fmaf(__uint_as_float(v[i]), p.scale_log2, -mrow[h]));
+          const float p1 = exp2f(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mrow[h]));
+          const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+          s2[0] += __low2float(b2);
+          s2[1] += __high2float(b2);
+          packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+        }
+        sum += s2[0] + s2[1];
+        uint8_t* rowp = sP + (c >> 6) * 16384 + r * 128;
+        const int j0 = (c & 63) >> 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint4 val = make_uint4(packed[4 * j], packed[4 * j + 1], packed[4 * j + 2], packed[4 * j + 3]);
+          *reinterpret_cast<uint4*>(rowp + (((j0 + j) ^ (r & 7)) << 4)) = val;
+        }
+      }
+      srow[h] += sum;
+      fence_proxy_async_smem();
+      tc_fence_before();
+      __syncthreads();
+      if (tid == 0) {
+        tc_fence_after();
+#pragma unroll 1
+        for (int kb = 0; kb < KB; ++kb) {
+          const uint64_t dp = make_smem_desc(smem_u32(sP + kb * 16384));
+          const uint64_t dv = make_smem_desc(smem_u32(sVt + kb * 8192 + h * p.hd * 128));
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            umma_bf16(tmem + (uint32_t)(LK + h * p.hd), dp + (uint64_t)(2 * kk), dv + (uint64_t)(2 * kk), idesc_o,
+                      (jb > 0 || kb > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&bar_mma);
+      }
+      mbar_wait(&bar_mma, mma_phase);   // P, S and (after the last head) sK / sVt may be overwritten
+      mma_phase ^= 1u;
+      tc_fence_after();
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // ---------------- epilogue: O_h / rowsum ----------------
+  for (int h = 0; h < nh; ++h) s_sum[half][h][r] = srow[h];
+  __syncthreads();
+  if (half == 0) {
+    for (int h = 0; h < nh; ++h) {
+      const float inv = 1.f / (s_sum[0][h][r] + s_sum[1][h][r]);
+      bf16* orow = p.out + (size_t)(q_row0 + r) * p.C + cb * 64 + h * p.hd;
+#pragma unroll 1
+      for (int c = 0; c < p.hd; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + (uint32_t)(LK + h * p.hd + c), v);
+        tmem_ld_wait();
+        const int n = p.hd - c < 32 ? p.hd - c : 32;
+        for (int i = 0; i < n; i += 8) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i + e]) * inv;
+          store8(orow + c + i, f);
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -230,7 +429,7 @@ bool sdpa_tc_supported(int L, int C, int heads) {
   if (heads <= 0 || C % heads || C % 64) return false;
   const int hd = C / heads;
   if (hd != 16 && hd != 32 && hd != 64) return false;
-  return (L <= 128 && 128 % L == 0) || L == 256;
+  return (L <= 128 && 128 % L == 0) || L == 256 || L == 512 || L == 1024;
 }
 int sdpa_tc_keys_per_tile(int L) { return L <= 128 ? 128 : L; }
 
@@ -281,7 +480,12 @@ void sdpa_tc_launch(const SdpaTc* g, bf16* out, long long M, cudaStream_t s) {
   SdpaParams p = g->p;
   p.out = out;
   dim3 grid((unsigned)(M / 128), (unsigned)(p.C / 64));
-  if (g->LK == 256) sdpa_launch_cfg<256, false>(g, p, grid, s);
+  if (p.L > 256) {
+    constexpr int smem = 16384 + 256 * 128 + 4 * 8192 + 4 * 16384 + 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(sdpa_tc_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    launch_pdl(sdpa_tc_long_kernel, grid, dim3(256), smem, s, g->map_qkv, g->map_vt, p);
+  } else if (g->LK == 256) sdpa_launch_cfg<256, false>(g, p, grid, s);
   else if (p.L == 128) sdpa_launch_cfg<128, false>(g, p, grid, s);
   else sdpa_launch_cfg<128, true>(g, p, grid, s);
 }
