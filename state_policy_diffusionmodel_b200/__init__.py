@@ -12,9 +12,9 @@ from .schedulers import (DDIMScheduler, DDPMScheduler, cosine_beta_schedule, lin
                          linear_beta_schedule_v2)
 from .engine import DenoisePlan  # noqa: F401
 from .unet import UNet_Film, UNet_Film_noAttention  # noqa: F401
-from .diffusion import Diffusion_DDIM, Diffusion_DDPM  # noqa: F401
+from .diffusion import Diffusion_DDIM, Diffusion_DDPM, SamplingPipeline  # noqa: F401
 from .compat import install_reference_aliases  # noqa: F401
 
 __all__ = ["UNet_Film", "UNet_Film_noAttention", "Diffusion_DDPM", "Diffusion_DDIM", "DDPMScheduler", "DDIMScheduler",
-           "linear_beta_schedule", "linear_beta_schedule_v2", "cosine_beta_schedule", "DenoisePlan",
+           "linear_beta_schedule", "linear_beta_schedule_v2", "cosine_beta_schedule", "DenoisePlan", "SamplingPipeline",
            "install_reference_aliases"]

@@ -161,7 +161,6 @@ template <typename T> void launch_outc(const T* x, int ld, const float* w, const
 template <typename T> void launch_to_nchw(const T* in, int ld, float* out, int B, int HW, int C, cudaStream_t s);
 void launch_step(const StepArgs& a, cudaStream_t s);
 void launch_advance(int* step_ptr, int delta, cudaStream_t s);
-void launch_set_int(int* p, int v, cudaStream_t s);
 void launch_delay(long long cycles, cudaStream_t s);  // spin kernel (profiling: lets the host run ahead)
 void launch_temb(const long long* t_dev, int n_t, const float* inv_freq, const float* w_cat, const float* b_cat, float* out, int time_dim, cudaStream_t s);
 void launch_mish(const float* in, float* out, long long n, cudaStream_t s);

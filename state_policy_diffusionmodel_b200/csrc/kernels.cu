@@ -874,9 +874,6 @@ __global__ void delay_kernel(long long cycles) {
   const long long t0 = clock64();
   while (clock64() - t0 < cycles) {}
 }
-__global__ void set_int_kernel(int* p, int v) {
-  pdl_wait();
-  pdl_trigger(); *p = v; }
 
 // DDPMScheduler.add_noise + add_constraints (models/diffusion_ddpm.py:167-168)
 __global__ void add_noise_kernel(const float* __restrict__ x0, const float* __restrict__ noise, const long long* __restrict__ t,
@@ -909,7 +906,6 @@ template void launch_outc_step<float>(const StepArgs&, const float*, int, const 
 template void launch_outc_step<bf16>(const StepArgs&, const bf16*, int, const float*, const float*, int, int, int, int, int, int, int, cudaStream_t);
 void launch_delay(long long cycles, cudaStream_t s) { launch_pdl(delay_kernel, dim3(1), dim3(1), 0, s, cycles); }
 void launch_advance(int* step_ptr, int delta, cudaStream_t s) { launch_pdl(advance_kernel, dim3(1), dim3(1), 0, s, step_ptr, delta); COUNT_LAUNCH(); }
-void launch_set_int(int* p, int v, cudaStream_t s) { launch_pdl(set_int_kernel, dim3(1), dim3(1), 0, s, p, v); COUNT_LAUNCH(); }
 void launch_add_noise(const float* x0, const float* noise, const long long* t, const float* sa, const float* sb, const float* inpaint,
                       float* out, int n, int inpaint_elems, int B, cudaStream_t s) {
   const long long total = (long long)B * n;

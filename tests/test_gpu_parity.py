@@ -391,3 +391,20 @@ def test_error_paths_are_loud(spdm):
         spdm.DDPMScheduler(num_train_timesteps=10, clip_sample=True)
     with pytest.raises(NotImplementedError):
         spdm.Diffusion_DDPM(model="UNet")
+
+
+def test_sampling_pipeline_matches_sequential(spdm):
+    """SamplingPipeline (independent batches in flight on separate plans/streams) returns what sample() returns."""
+    m = spdm.Diffusion_DDIM(noise_steps=1000, obs_horizon=10, pred_horizon=30, observation_dim=135, prediction_dim=5,
+                            model="UNet_FilmnoAttention", inpaint_horizon=1).cuda().eval()
+    m.noise_estimator.load_state_dict(fixtures.make_unet_weights(attention=False, seed=3), strict=True)
+    m.vision_encoder.load_state_dict(fixtures.make_encoder_weights(), strict=True)
+    m.configure(precision="bf16", graph_steps=4, batch_max=8).use_ddim(8)
+    batches = [fixtures.make_batch(8, seed=50 + i) for i in range(5)]
+    xs = [fixtures.make_xT(8, seed=70 + i) for i in range(5)]
+    want = [m.sample({k: v.clone() for k, v in b.items()}, batched=True, x_T=x, seed=1).cpu() for b, x in zip(batches, xs)]
+    pipe = spdm.SamplingPipeline(m, depth=3, batch_max=8)
+    tickets = [pipe.submit(b, x_T=x.cuda(), seed=1) for b, x in zip(batches, xs)]
+    got = [pipe.result(t).cpu() for t in tickets]
+    for g, w in zip(got, want):
+        assert torch.equal(g, w)
