@@ -146,6 +146,40 @@ def golden_validate_and_train(seed=0):
     print("validate/train loss", float(loss))
 
 
+def golden_train_grads(seed=0):
+    """loss.backward() + clip_grad_norm_(0.5) + one torch.optim.Adam step on the reference's own Diffusion_DDPM
+    (U-Net + vision encoder), injected t / noise: per-tensor fingerprints of the gradients and of the updated weights."""
+    from . import train_ref
+    for attention, model_name, name in ((True, "UNet_Film", "train_grads"), (False, "UNet_FilmnoAttention", "train_grads_noattn")):
+        m = _wrapper("ddpm", model_name, 1000, 5, attention, seed).train()
+        B = 3
+        g = torch.Generator().manual_seed(778)
+        full = {"image": torch.rand((B, 40, 3, 96, 96), generator=g), "position": 0.3 * torch.randn((B, 40, 2), generator=g),
+                "velocity": 2 * torch.rand((B, 40, 2), generator=g) - 1, "action": 2 * torch.rand((B, 40, 3), generator=g) - 1}
+        t = torch.tensor([3, 500, 997], dtype=torch.long)
+        noise = torch.randn((B, 1, 31, 5), generator=g)
+        # process_single_batch draws t then noise from the global RNG (ddpm:158-161): patch the two draws
+        real_randint, real_randn_like = torch.randint, torch.randn_like
+        torch.randint = lambda *a, **k: t.clone()
+        torch.randn_like = lambda x, *a, **k: noise.clone()
+        try:
+            loss = m.process_single_batch(full)
+        finally:
+            torch.randint, torch.randn_like = real_randint, real_randn_like
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4)
+        opt.zero_grad()
+        loss.backward()
+        named = [(k[len("noise_estimator."):] if k.startswith("noise_estimator.") else k, p) for k, p in m.named_parameters()]
+        d = {"full_seed": 778, "t": t, "noise": noise, "loss": loss.detach(), "names": np.array([k for k, _ in named])}
+        d["grad_fp"] = torch.stack([train_ref.summary(p.grad if p.grad is not None else torch.zeros_like(p)) for _, p in named])
+        total = torch.nn.utils.clip_grad_norm_(m.parameters(), 0.5)
+        opt.step()
+        d["total_norm"] = total
+        d["param_fp_after"] = torch.stack([train_ref.summary(p) for _, p in named])
+        np.savez_compressed(os.path.join(OUT, name + ".npz"), **_np(d))
+        print(name, "loss", float(loss), "total_norm", float(total), "tensors", len(named))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     shim.install()
@@ -158,6 +192,7 @@ def main():
     golden_sample("ddim", "UNet_Film", True, 10, 5, "sample_ddim10_attn")
     golden_sample("ddpm", "UNet_FilmnoAttention", False, 20, 2, "sample_ddpm20_noattn_pos2", seed=3)
     golden_validate_and_train()
+    golden_train_grads()
 
 
 if __name__ == "__main__":

@@ -1,19 +1,23 @@
 """Builds libspdm.so (hand-written sm_100a CUDA + the C ABI of include/spdm.h) in-tree with nvcc.
 
 The library is compiled for sm_100a only (tcgen05 / TMEM / TMA instructions); there is no other
-backend and no CPU fallback.
+backend and no CPU fallback.  Every source is compiled to its own object (in parallel, only when it
+or a header changed) and the objects are linked into the shared library.
 """
 import os
 import shutil
 import subprocess
+from concurrent.futures import ThreadPoolExecutor
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
+OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libspdm.so")
-SOURCES = ["kernels.cu", "conv_tc.cu", "sdpa_tc.cu", "attn_tc.cu", "plan.cu"]
-HEADERS = [os.path.join(CSRC, "common.cuh"), os.path.join(CSRC, "tc_ptx.cuh"), os.path.join(os.path.dirname(HERE), "include", "spdm.h")]
+SOURCES = ["kernels.cu", "conv_tc.cu", "sdpa_tc.cu", "attn_tc.cu", "bwd_kernels.cu", "wgrad_tc.cu", "plan.cu"]
+HEADERS = [os.path.join(CSRC, h) for h in ("common.cuh", "tc_ptx.cuh", "train.cuh", "train_impl.inl")] + [
+    os.path.join(os.path.dirname(HERE), "include", "spdm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
+              "-Xcompiler", "-fPIC"]
 
 
 def _nvcc():
@@ -23,22 +27,49 @@ def _nvcc():
     raise RuntimeError("nvcc not found: libspdm.so cannot be built (set NVCC=/path/to/nvcc)")
 
 
+def _mtime(path):
+    return os.path.getmtime(path) if os.path.exists(path) else 0.0
+
+
+def _obj(src):
+    return os.path.join(OBJ, os.path.splitext(src)[0] + ".o")
+
+
+def _obj_stale(src):
+    t = _mtime(_obj(src))
+    return t == 0.0 or any(_mtime(d) > t for d in [os.path.join(CSRC, src)] + HEADERS)
+
+
 def is_stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
-    return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
+    return any(_mtime(d) > t for d in deps)
 
 
 def build(force=False, verbose=False):
     """Compile csrc/*.cu into libspdm.so next to this file.  Returns the library path."""
     if not force and not is_stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-o", LIB] + [os.path.join(CSRC, s) for s in SOURCES]
+    nvcc = _nvcc()
+    os.makedirs(OBJ, exist_ok=True)
+
+    def compile_one(src):
+        cmd = [nvcc] + NVCC_FLAGS + ["-c", "-o", _obj(src), os.path.join(CSRC, src)]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed on %s:\n%s%s" % (src, res.stdout, res.stderr))
+
+    todo = [s for s in SOURCES if force or _obj_stale(s)]
+    with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 1))) as ex:
+        list(ex.map(compile_one, todo))
+    cmd = [nvcc, "-shared", "-o", LIB] + [_obj(s) for s in SOURCES]
     if verbose:
-        print(" ".join(cmd))
+        print(" ".join(cmd), flush=True)
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("link failed:\n" + res.stdout + res.stderr)
     return LIB

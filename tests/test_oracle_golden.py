@@ -92,3 +92,37 @@ def test_validate_and_training_forward_oracle(golden_dir):
     with torch.no_grad():
         loss, _, _ = sampler_ref.training_forward_ref(sd, esd, sched, full, 10, 1, g["train_t"], g["train_noise"])
     torch.testing.assert_close(loss, torch.as_tensor(g["train_loss"]), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("name", ["train_grads", "train_grads_noattn"])
+def test_training_gradients_and_adam_oracle(golden_dir, name):
+    """oracle/train_ref.py (autograd over the restatement, clip, Adam) vs loss.backward() / clip_grad_norm_ /
+    torch.optim.Adam.step() on the reference's own Diffusion_DDPM (oracle/make_golden.py::golden_train_grads)."""
+    from oracle import train_ref
+    raw = np.load(os.path.join(golden_dir, name + ".npz"))
+    attention = name == "train_grads"
+    sd = fixtures.make_unet_weights(attention=attention, seed=0)
+    esd = fixtures.make_encoder_weights()
+    B = 3
+    gen = torch.Generator().manual_seed(int(raw["full_seed"]))
+    full = {"image": torch.rand((B, 40, 3, 96, 96), generator=gen), "position": 0.3 * torch.randn((B, 40, 2), generator=gen),
+            "velocity": 2 * torch.rand((B, 40, 2), generator=gen) - 1, "action": 2 * torch.rand((B, 40, 3), generator=gen) - 1}
+    t, noise = torch.from_numpy(raw["t"]), torch.from_numpy(raw["noise"])
+    sched = RefDDPMScheduler(num_train_timesteps=1000, beta_schedule="linear", clip_sample=False)
+    loss, grads = train_ref.loss_and_grads(sd, esd, sched, full, 10, 1, t, noise, attention=attention)
+    torch.testing.assert_close(loss, torch.as_tensor(raw["loss"]), rtol=1e-5, atol=1e-6)
+    names = [str(n) for n in raw["names"]]
+    assert sorted(names) == sorted(grads)  # exactly the tensors the reference hands to Adam (U-Net + vision encoder)
+    got = torch.stack([train_ref.summary(grads[n]) for n in names])
+    want = torch.from_numpy(raw["grad_fp"])
+    scale = want[:, 2:3].clamp_min(1e-12)  # per-tensor l2 norm
+    assert float(((got - want).abs() / scale).max()) < 2e-3
+    total, clipped = train_ref.clip_grad_norm(grads, 0.5)
+    torch.testing.assert_close(total, torch.as_tensor(raw["total_norm"]), rtol=1e-4, atol=1e-6)
+    params = dict(sd)
+    params.update({train_ref.ENC_PREFIX + k: v for k, v in esd.items()})
+    zeros = {k: torch.zeros_like(v) for k, v in params.items()}
+    new_p, _, _ = train_ref.adam_step(params, clipped, zeros, dict(zeros), 1, lr=1e-4)
+    got_p = torch.stack([train_ref.summary(new_p[n]) for n in names])
+    want_p = torch.from_numpy(raw["param_fp_after"])
+    assert float(((got_p - want_p).abs() / want_p[:, 2:3].clamp_min(1e-12)).max()) < 1e-4
