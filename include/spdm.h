@@ -104,6 +104,30 @@ int spdm_add_noise(spdm_plan* plan, const float* x0, const float* noise, const i
                    const float* sqrt_ab, const float* sqrt_1mab, const float* inpaint,
                    float* out, int32_t B, void* stream);
 
+/* ---- training step (models/diffusion_ddpm.py:115-173, train.py:104-107) ------------------------------------------
+ * The caller owns two flat fp32 device buffers (parameters, gradients) holding every trainable tensor in PyTorch
+ * layout; nn.Parameter storage can alias them, so torch optimizers and NCCL all-reduces see ordinary tensors. */
+/* Allocate the data-gradient weight twins; every weight must be uploaded (again) afterwards. */
+int spdm_train_enable(spdm_plan* plan);
+/* Tensor `name` (load_weight names) lives at `offset` floats into both flat buffers. */
+int spdm_train_bind(spdm_plan* plan, const char* name, int64_t offset, const int64_t* shape, int32_t ndim);
+int spdm_train_set_buffers(spdm_plan* plan, float* params, float* grads, int64_t total);
+/* load_state_dict from the flat parameter buffer (after every optimizer step). */
+int spdm_train_sync_weights(spdm_plan* plan, void* stream);
+/* Diffusion_DDPM.process_single_batch + loss.backward() (ddpm:128-173): images (B,T,3,96,96), position (B,T,2),
+ * action (B,T,3), velocity (B,T,2) = the observation window; x0 (B,1,rows,dim) = cat[inpaint rows, prediction];
+ * noise (B,1,rows,dim); t int64 (B,); sqrt_ab / sqrt_1mab = DDPMScheduler.add_noise tables; inpaint (B,inpaint_rows*dim).
+ * Zeroes the gradient buffer, then leaves d loss / d parameter in it; loss_out = one device float (MSE, mean). */
+int spdm_train_fwd_bwd(spdm_plan* plan, const float* images, const float* position, const float* action,
+                       const float* velocity, const float* x0, const float* noise, const int64_t* t,
+                       const float* sqrt_ab, const float* sqrt_1mab, const float* inpaint, float* loss_out,
+                       int32_t B, void* stream);
+/* torch.nn.utils.clip_grad_norm_(max_norm) (Lightning gradient_clip_val=0.5, train.py:107; max_norm <= 0: off) followed
+ * by torch.optim.Adam.step() (ddpm:115-125) over n floats; `step` counts from 1; grad_scale multiplies the gradient first
+ * (1/world_size after a summing all-reduce); scratch = one device float. */
+int spdm_adam_step(float* params, float* grads, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                   float eps, int32_t step, float max_norm, float grad_scale, float* scratch, void* stream);
+
 /* Kernel-class profile of one denoising step (U-Net forward + posterior update) run EAGERLY with CUDA
  * events around every launch, averaged over `reps` steps: out[c*4 + {0,1,2,3}] = {ms, launches,
  * algorithmic FLOPs, algorithmic bytes} for class c.  Needs a schedule and (if conditional) cached cond. */

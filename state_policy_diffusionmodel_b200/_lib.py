@@ -42,6 +42,13 @@ _PROTOTYPES = {
     "spdm_add_noise": (_c.c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _c.c_int32, _P]),
     "spdm_profile_step": (_c.c_int, [_P, _c.c_int32, _c.c_int32, _c.POINTER(_c.c_double), _P]),
     "spdm_microbench_conv": (_c.c_int, [_c.c_int32] * 8 + [_c.POINTER(_c.c_float)]),
+    "spdm_train_enable": (_c.c_int, [_P]),
+    "spdm_train_bind": (_c.c_int, [_P, _c.c_char_p, _c.c_int64, _c.POINTER(_c.c_int64), _c.c_int32]),
+    "spdm_train_set_buffers": (_c.c_int, [_P, _P, _P, _c.c_int64]),
+    "spdm_train_sync_weights": (_c.c_int, [_P, _P]),
+    "spdm_train_fwd_bwd": (_c.c_int, [_P] + [_P] * 11 + [_c.c_int32, _P]),
+    "spdm_adam_step": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_int32,
+                                  _c.c_float, _c.c_float, _P, _P]),
     "spdm_plan_launch_count": (_c.c_int64, [_P]),
     "spdm_plan_workspace_bytes": (_c.c_int64, [_P]),
     "spdm_last_error": (_c.c_char_p, []),

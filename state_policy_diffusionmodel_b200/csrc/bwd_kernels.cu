@@ -1,0 +1,1116 @@
+// bwd_kernels.cu — CUDA-core kernels of the training step (sm_100a): everything of `loss.backward()` and the
+// optimizer that is not a dense bf16 contraction.  GroupNorm / GELU / FiLM / time-embedding backward, max-pool and
+// bilinear-upsample backward, LayerNorm and attention-core backward, the MSE loss + outc backward, the fp32 weight-
+// gradient GEMM of the parity path, the vision-encoder backward and fused clip + Adam.
+// Reference lines are cited per kernel (paths relative to the reference repo root).
+#include <math.h>
+
+#include "train.cuh"
+
+static long long g_bwd_launches = 0;
+long long bwd_launch_count() { return g_bwd_launches; }
+#define COUNT_LAUNCH() (++g_bwd_launches)
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+namespace {
+__device__ __forceinline__ float gelu_grad(float u) {  // d/du [0.5 u (1 + erf(u / sqrt 2))]
+  return 0.5f * (1.0f + erff(u * 0.70710678118654752440f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+// sum over the 256 threads of a block, result broadcast to every thread (scratch: 8 floats)
+__device__ __forceinline__ float block_sum_256(float v, float* scratch) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float t = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t += scratch[i];
+  return t;
+}
+}  // namespace
+
+// =================================================================================================
+// GroupNorm(1, C) backward (models/Unet_FiLmLayer.py:105,112-115) fused with what follows it in the forward:
+//   first conv of a DoubleConvolution:  out = gelu(gn(raw))                              (:113)
+//   last conv of a Down/Up stage:       out = scale * (gn(raw) + temb) + bias             (:165-177)
+// One block per sample (the normalisation group is the whole sample):
+//   pass 1: g = d out / d gn ; per-channel sums (d gamma, d beta, d FiLM scale/bias, d temb), per-sample
+//           sums s1 = sum g*gamma, s2 = sum g*gamma*xhat
+//   pass 2: dx = rstd * (g*gamma - s1/N - xhat * s2/N)
+// =================================================================================================
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) gn_bwd_kernel(GnBwdArgs a) {
+  __shared__ float red[256 * 8];
+  __shared__ float scratch[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  double s = 0.0, q = 0.0;
+  for (int p = 0; p < a.P; ++p) {
+    const float2 sq = __ldg(reinterpret_cast<const float2*>(a.stats) + (size_t)b * a.P + p);
+    s += (double)sq.x;
+    q += (double)sq.y;
+  }
+  const double n = (double)a.HW * (double)a.C;
+  const double dmean = s / n;
+  double var = q / n - dmean * dmean;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)dmean;
+  const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+
+  const T* __restrict__ dy = reinterpret_cast<const T*>(a.dy);
+  const T* __restrict__ raw = reinterpret_cast<const T*>(a.raw);
+  T* __restrict__ dx = reinterpret_cast<T*>(a.dx);
+  const int vpr = a.C >> 3;           // 8-channel vectors per row: 8..64, divides 256
+  const int lane_c = tid % vpr;       // this thread always handles the same 8 channels
+  const int row0 = tid / vpr, row_step = 256 / vpr;
+  const int c8 = lane_c << 3;
+  float g[8], be[8], te[8], fs[8];
+  load8(a.gamma + c8, g);
+  load8(a.beta + c8, be);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { te[i] = 0.f; fs[i] = 1.f; }
+  const bool has_film = a.film != nullptr, has_temb = a.temb != nullptr;
+  if (has_temb) load8(a.temb + (size_t)b * SPDM_TEMB_WIDTH + a.temb_off + c8, te);
+  if (has_film) load8(a.film + (size_t)b * SPDM_FILM_WIDTH + a.film_off + c8, fs);
+
+  float acc_dg[8], acc_db[8], acc_fb[8], acc_fs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc_dg[i] = 0.f; acc_db[i] = 0.f; acc_fb[i] = 0.f; acc_fs[i] = 0.f; }
+  float s1 = 0.f, s2 = 0.f;
+  for (int row = row0; row < a.HW; row += row_step) {
+    float d[8], x[8];
+    load8(dy + ((size_t)b * a.HW + row) * a.ld_dy + c8, d);
+    load8(raw + ((size_t)b * a.HW + row) * a.ld_raw + c8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (x[i] - mean) * rstd;
+      const float u = xh * g[i] + be[i];
+      float go = d[i];
+      if (has_film) { acc_fb[i] += d[i]; acc_fs[i] = fmaf(d[i], u + te[i], acc_fs[i]); go = d[i] * fs[i]; }
+      else if (has_temb) acc_fb[i] += d[i];
+      if (a.act == ACT_GELU) go *= gelu_grad(u);
+      acc_dg[i] = fmaf(go, xh, acc_dg[i]);
+      acc_db[i] += go;
+      const float gg = go * g[i];
+      s1 += gg;
+      s2 = fmaf(gg, xh, s2);
+    }
+  }
+  s1 = block_sum_256(s1, scratch);
+  s2 = block_sum_256(s2, scratch);
+  const float inv_n = 1.0f / ((float)a.HW * (float)a.C);
+  const float m1 = s1 * inv_n, m2 = s2 * inv_n;
+
+  // per-channel reductions across the row groups: one quantity at a time through shared memory
+  auto reduce_channels = [&](const float (&acc)[8], float (&out)[8]) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[tid * 8 + i] = acc[i];
+    __syncthreads();
+    if (tid < vpr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out[i] = 0.f;
+      for (int r = 0; r < row_step; ++r)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) out[i] += red[(r * vpr + tid) * 8 + i];
+    }
+  };
+  float tot[8];
+  reduce_channels(acc_dg, tot);
+  if (tid < vpr)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(a.dgamma + c8 + i, tot[i]);
+  reduce_channels(acc_db, tot);
+  if (tid < vpr) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(a.dbeta + c8 + i, tot[i]);
+  }
+  if (has_film || has_temb) {
+    reduce_channels(acc_fb, tot);  // sum_hw dy
+    if (tid < vpr) {
+      if (has_film) store8(a.d_film + (size_t)b * SPDM_FILM_WIDTH + a.film_off + a.C + c8, tot);
+      if (has_temb) {
+        float dt[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dt[i] = tot[i] * fs[i];  // d temb = scale * sum_hw dy
+        store8(a.d_temb + (size_t)b * SPDM_TEMB_WIDTH + a.temb_off + c8, dt);
+      }
+    }
+    if (has_film) {
+      reduce_channels(acc_fs, tot);
+      if (tid < vpr) store8(a.d_film + (size_t)b * SPDM_FILM_WIDTH + a.film_off + c8, tot);
+    }
+  }
+  // pass 2
+  for (int row = row0; row < a.HW; row += row_step) {
+    float d[8], x[8];
+    load8(dy + ((size_t)b * a.HW + row) * a.ld_dy + c8, d);
+    load8(raw + ((size_t)b * a.HW + row) * a.ld_raw + c8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xh = (x[i] - mean) * rstd;
+      float go = d[i] * fs[i];
+      if (a.act == ACT_GELU) go *= gelu_grad(xh * g[i] + be[i]);
+      x[i] = rstd * (go * g[i] - m1 - xh * m2);
+    }
+    store8(dx + ((size_t)b * a.HW + row) * a.ld_dx + c8, x);
+  }
+}
+}  // namespace
+template <typename T> void launch_gn_bwd(const GnBwdArgs& a, int B, cudaStream_t s) {
+  gn_bwd_kernel<T><<<B, 256, 0, s>>>(a);
+  COUNT_LAUNCH();
+}
+template void launch_gn_bwd<float>(const GnBwdArgs&, int, cudaStream_t);
+template void launch_gn_bwd<bf16>(const GnBwdArgs&, int, cudaStream_t);
+
+// =================================================================================================
+// Weight gradient on CUDA cores (fp32 accumulate): 64(ci) x 64(co) tile per block, split over the pixel
+// dimension; the partial tile is added to dw (PyTorch layout) with atomics.
+//   nn.Conv2d(k=3, pad=1) weight grad (models/Unet_FiLmLayer.py:101,103) / nn.Linear weight grad.
+// =================================================================================================
+namespace {
+template <typename TX, typename TDY>
+__global__ void __launch_bounds__(256) wgrad_simt_kernel(WgradArgs a, int ksplit) {
+  __shared__ float Xs[16][64 + 4];
+  __shared__ float Ds[16][64 + 4];
+  const TX* __restrict__ x = reinterpret_cast<const TX*>(a.x);
+  const TDY* __restrict__ dy = reinterpret_cast<const TDY*>(a.dy);
+  const int tid = threadIdx.x;
+  const int co_tiles = (a.Cout + 63) / 64;
+  const int ci0 = (blockIdx.x / co_tiles) * 64, co0 = (blockIdx.x % co_tiles) * 64;
+  const int tap = blockIdx.y;
+  int ddy = 0, ddx = 0;
+  if (a.taps == 9) { ddy = tap / 3 - 1; ddx = tap % 3 - 1; }
+  if (a.taps == 9 && ((a.W == 1 && ddx != 0) || (a.H == 1 && ddy != 0))) return;  // structurally empty tap
+  const long long per = ((a.M + ksplit - 1) / ksplit + 15) / 16 * 16;
+  const long long m_begin = (long long)blockIdx.z * per;
+  long long m_end = m_begin + per;
+  if (m_end > a.M) m_end = a.M;
+  const int tx = tid & 15, ty = tid >> 4;      // outputs: ci = ci0 + ty*4 + i, co = co0 + tx*4 + j
+  const int lrow = tid >> 4, lc = (tid & 15) * 4;  // loads: row lrow of the 16-row chunk, 4 channels at lc
+  const int HW = a.H * a.W;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  for (long long m0 = m_begin; m0 < m_end; m0 += 16) {
+    const long long m = m0 + lrow;
+    float xv[4] = {0.f, 0.f, 0.f, 0.f}, dv[4] = {0.f, 0.f, 0.f, 0.f};
+    if (m < m_end) {
+      bool valid = true;
+      long long src = m;
+      if (a.taps == 9) {
+        const int rem = (int)(m % HW);
+        const int hh = rem / a.W + ddy, ww = rem % a.W + ddx;
+        valid = hh >= 0 && hh < a.H && ww >= 0 && ww < a.W;
+        src = m + ddy * a.W + ddx;
+      }
+      if (valid) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (ci0 + lc + i < a.Cin) xv[i] = to_f32<TX>(x[src * a.ld_x + ci0 + lc + i]);
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (co0 + lc + i < a.Cout) dv[i] = to_f32<TDY>(dy[m * a.ld_dy + co0 + lc + i]);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { Xs[lrow][lc + i] = xv[i]; Ds[lrow][lc + i] = dv[i]; }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const float4 xa = *reinterpret_cast<const float4*>(&Xs[k][ty * 4]);
+      const float4 da = *reinterpret_cast<const float4*>(&Ds[k][tx * 4]);
+      const float xr[4] = {xa.x, xa.y, xa.z, xa.w};
+      const float dr[4] = {da.x, da.y, da.z, da.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(xr[i], dr[j], acc[i][j]);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int ci = ci0 + ty * 4 + i;
+    if (ci >= a.Cin) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int co = co0 + tx * 4 + j;
+      if (co >= a.Cout) continue;
+      atomicAdd(a.dw + ((size_t)co * a.Cin + ci) * a.taps + tap, acc[i][j]);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, int ld, long long M, int N, float* __restrict__ out, long long rows_per_block) {
+  __shared__ float sm[4][64];
+  const int c = blockIdx.x * 64 + (threadIdx.x & 63), rg = threadIdx.x >> 6;
+  const long long m0 = (long long)blockIdx.y * rows_per_block;
+  long long m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  float acc = 0.f;
+  if (c < N)
+    for (long long m = m0 + rg; m < m1; m += 4) acc += to_f32<T>(dy[m * ld + c]);
+  sm[rg][threadIdx.x & 63] = acc;
+  __syncthreads();
+  if (rg == 0 && c < N) atomicAdd(out + c, sm[0][threadIdx.x] + sm[1][threadIdx.x] + sm[2][threadIdx.x] + sm[3][threadIdx.x]);
+}
+}  // namespace
+template <typename TX, typename TDY> void launch_wgrad_simt(const WgradArgs& a, cudaStream_t s) {
+  const int tiles = cdiv(a.Cin, 64) * cdiv(a.Cout, 64);
+  long long ks = (2 * 148 + (long long)tiles * a.taps - 1) / ((long long)tiles * a.taps);
+  const long long max_ks = (a.M + 127) / 128;
+  if (ks > max_ks) ks = max_ks;
+  if (ks < 1) ks = 1;
+  wgrad_simt_kernel<TX, TDY><<<dim3(tiles, a.taps, (unsigned)ks), 256, 0, s>>>(a, (int)ks);
+  COUNT_LAUNCH();
+}
+template void launch_wgrad_simt<float, float>(const WgradArgs&, cudaStream_t);
+template void launch_wgrad_simt<bf16, bf16>(const WgradArgs&, cudaStream_t);
+template void launch_wgrad_simt<float, bf16>(const WgradArgs&, cudaStream_t);
+template <typename T> void launch_colsum(const T* dy, int ld, long long M, int N, float* out, cudaStream_t s) {
+  int gy = (int)((M + 1023) / 1024);
+  if (gy > 64) gy = 64;
+  const long long rpb = (M + gy - 1) / gy;
+  colsum_kernel<T><<<dim3(cdiv(N, 64), gy), 256, 0, s>>>(dy, ld, M, N, out, rpb);
+  COUNT_LAUNCH();
+}
+template void launch_colsum<float>(const float*, int, long long, int, float*, cudaStream_t);
+template void launch_colsum<bf16>(const bf16*, int, long long, int, float*, cudaStream_t);
+
+// =================================================================================================
+// MaxPool2d(2) backward (models/Unet_FiLmLayer.py:132) + skip-connection gradient add;
+// bilinear x2 align_corners=True backward (:191) in gather form.
+// =================================================================================================
+namespace {
+template <typename T>
+__global__ void pool_bwd_kernel(const T* __restrict__ x, int ld_x, const T* __restrict__ dy, int ld_dy, const T* __restrict__ add, int ld_add,
+                                T* __restrict__ dx, int ld_dx, long long total, int Ho, int Wo, int C) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= total) return;
+  const int vpr = C >> 3;
+  const long long orow = v / vpr;
+  const int c8 = (int)(v - orow * vpr) << 3;
+  const int wo = (int)(orow % Wo);
+  const long long t = orow / Wo;
+  const int ho = (int)(t % Ho);
+  const long long b = t / Ho;
+  const int Wi = Wo * 2, Hi = Ho * 2;
+  const long long r00 = (b * Hi + 2 * ho) * Wi + 2 * wo;
+  const long long rr[4] = {r00, r00 + 1, r00 + Wi, r00 + Wi + 1};
+  float xin[4][8], d[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) load8(x + rr[k] * ld_x + c8, xin[k]);
+  load8(dy + orow * ld_dy + c8, d);
+  int arg[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {  // first maximum in window scan order (strict >), as ATen's max_pool2d
+    float m = xin[0][i];
+    int am = 0;
+#pragma unroll
+    for (int k = 1; k < 4; ++k)
+      if (xin[k][i] > m) { m = xin[k][i]; am = k; }
+    arg[i] = am;
+  }
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    float o[8];
+    if (add) load8(add + rr[k] * ld_add + c8, o);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] = 0.f;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] += (arg[i] == k) ? d[i] : 0.f;
+    store8(dx + rr[k] * ld_dx + c8, o);
+  }
+}
+
+template <typename T>
+__global__ void upsample_bwd_kernel(const T* __restrict__ dy, int ld_dy, T* __restrict__ dx, int ld_dx, long long total, int Hi, int Wi, int C) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= total) return;
+  const int vpr = C >> 3;
+  const long long irow = v / vpr;
+  const int c8 = (int)(v - irow * vpr) << 3;
+  const int wi = (int)(irow % Wi);
+  const long long t = irow / Wi;
+  const int hi = (int)(t % Hi);
+  const long long b = t / Hi;
+  const int Ho = Hi * 2, Wo = Wi * 2;
+  const float sh = (Ho > 1) ? (float)(Hi - 1) / (float)(Ho - 1) : 0.f;
+  const float sw = (Wo > 1) ? (float)(Wi - 1) / (float)(Wo - 1) : 0.f;
+  // candidate outputs: src(o) = o*s in (i-1, i+1)
+  int ho_lo = 0, ho_hi = Ho - 1, wo_lo = 0, wo_hi = Wo - 1;
+  if (sh > 0.f) { ho_lo = max(0, (int)floorf((hi - 1) / sh) - 1); ho_hi = min(Ho - 1, (int)ceilf((hi + 1) / sh) + 1); }
+  if (sw > 0.f) { wo_lo = max(0, (int)floorf((wi - 1) / sw) - 1); wo_hi = min(Wo - 1, (int)ceilf((wi + 1) / sw) + 1); }
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int ho = ho_lo; ho <= ho_hi; ++ho) {
+    // identical arithmetic to upsample_kernel (kernels.cu)
+    const float fh = sh * ho;
+    const int h0 = (int)fh;
+    const int h1 = h0 + ((h0 < Hi - 1) ? 1 : 0);
+    const float lh1 = fh - h0, lh0 = 1.f - lh1;
+    const float wh = (h0 == hi ? lh0 : 0.f) + (h1 == hi ? lh1 : 0.f);
+    if (wh == 0.f) continue;
+    for (int wo = wo_lo; wo <= wo_hi; ++wo) {
+      const float fw = sw * wo;
+      const int w0 = (int)fw;
+      const int w1 = w0 + ((w0 < Wi - 1) ? 1 : 0);
+      const float lw1 = fw - w0, lw0 = 1.f - lw1;
+      const float ww = (w0 == wi ? lw0 : 0.f) + (w1 == wi ? lw1 : 0.f);
+      if (ww == 0.f) continue;
+      float d[8];
+      load8(dy + ((b * Ho + ho) * Wo + wo) * ld_dy + c8, d);
+      const float wgt = wh * ww;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] = fmaf(wgt, d[i], acc[i]);
+    }
+  }
+  store8(dx + irow * ld_dx + c8, acc);
+}
+}  // namespace
+template <typename T>
+void launch_pool_bwd(const T* x, int ld_x, const T* dy, int ld_dy, const T* add, int ld_add, T* dx, int ld_dx, int B, int Ho, int Wo, int C,
+                     cudaStream_t s) {
+  const long long total = (long long)B * Ho * Wo * (C >> 3);
+  pool_bwd_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(x, ld_x, dy, ld_dy, add, ld_add, dx, ld_dx, total, Ho, Wo, C);
+  COUNT_LAUNCH();
+}
+template <typename T> void launch_upsample_bwd(const T* dy, int ld_dy, T* dx, int ld_dx, int B, int Hi, int Wi, int C, cudaStream_t s) {
+  const long long total = (long long)B * Hi * Wi * (C >> 3);
+  upsample_bwd_kernel<T><<<cdiv(total, 256), 256, 0, s>>>(dy, ld_dy, dx, ld_dx, total, Hi, Wi, C);
+  COUNT_LAUNCH();
+}
+template void launch_pool_bwd<float>(const float*, int, const float*, int, const float*, int, float*, int, int, int, int, int, cudaStream_t);
+template void launch_pool_bwd<bf16>(const bf16*, int, const bf16*, int, const bf16*, int, bf16*, int, int, int, int, int, cudaStream_t);
+template void launch_upsample_bwd<float>(const float*, int, float*, int, int, int, int, int, cudaStream_t);
+template void launch_upsample_bwd<bf16>(const bf16*, int, bf16*, int, int, int, int, int, cudaStream_t);
+
+// =================================================================================================
+// LayerNorm backward (models/Unet_FiLmLayer.py:51,53): one warp per token row, C <= 256.
+// =================================================================================================
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, int ld_dy, const T* __restrict__ x, int ld_x,
+                                                            const float* __restrict__ g, const T* __restrict__ add, int ld_add, T* __restrict__ dx,
+                                                            int ld_dx, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C) {
+  __shared__ float sg[256], sb[256];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < C; i += 256) { sg[i] = 0.f; sb[i] = 0.f; }
+  __syncthreads();
+  const int c0 = lane * 8;
+  const bool act = c0 < C;
+  float gg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (act) load8(g + c0, gg);
+  float adg[8], adb[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { adg[i] = 0.f; adb[i] = 0.f; }
+  const float inv_c = 1.0f / (float)C;
+  for (long long row = (long long)blockIdx.x * 8 + warp; row < M; row += (long long)gridDim.x * 8) {
+    float xv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (act) { load8(x + row * ld_x + c0, xv); load8(dy + row * ld_dy + c0, d); }
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) sum += xv[i];
+    const float mean = warp_sum(sum) * inv_c;
+    float qq = 0.f;
+    if (act) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { const float t = xv[i] - mean; qq = fmaf(t, t, qq); }
+    }
+    const float rstd = rsqrtf(warp_sum(qq) * inv_c + 1e-5f);
+    float a1 = 0.f, a2 = 0.f, xh[8], dh[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      xh[i] = act ? (xv[i] - mean) * rstd : 0.f;
+      dh[i] = d[i] * gg[i];
+      a1 += dh[i];
+      a2 = fmaf(dh[i], xh[i], a2);
+      adg[i] = fmaf(d[i], xh[i], adg[i]);
+      adb[i] += d[i];
+    }
+    a1 = warp_sum(a1) * inv_c;
+    a2 = warp_sum(a2) * inv_c;
+    if (act) {
+      float o[8];
+      if (add) load8(add + row * ld_add + c0, o);
+      else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) o[i] += rstd * (dh[i] - a1 - xh[i] * a2);
+      store8(dx + row * ld_dx + c0, o);
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { atomicAdd(&sg[c0 + i], adg[i]); atomicAdd(&sb[c0 + i], adb[i]); }
+  }
+  __syncthreads();
+  for (int i = tid; i < C; i += 256) { atomicAdd(dgamma + i, sg[i]); atomicAdd(dbeta + i, sb[i]); }
+}
+}  // namespace
+template <typename T>
+void launch_layernorm_bwd(const T* dy, int ld_dy, const T* x, int ld_x, const float* g, const T* add, int ld_add, T* dx, int ld_dx,
+                          float* dgamma, float* dbeta, long long M, int C, cudaStream_t s) {
+  int grid = cdiv(M, 8);
+  if (grid > 148 * 4) grid = 148 * 4;
+  layernorm_bwd_kernel<T><<<grid, 256, 0, s>>>(dy, ld_dy, x, ld_x, g, add, ld_add, dx, ld_dx, dgamma, dbeta, M, C);
+  COUNT_LAUNCH();
+}
+template void launch_layernorm_bwd<float>(const float*, int, const float*, int, const float*, const float*, int, float*, int, float*, float*,
+                                          long long, int, cudaStream_t);
+template void launch_layernorm_bwd<bf16>(const bf16*, int, const bf16*, int, const float*, const bf16*, int, bf16*, int, float*, float*,
+                                         long long, int, cudaStream_t);
+
+// =================================================================================================
+// Attention core backward (nn.MultiheadAttention, 4 heads; models/Unet_FiLmLayer.py:50,76).
+// One block per (sample, head): Q, K, V, dO of the group live in shared memory as fp32.
+//   pass 1 (thread per query i): log-sum-exp of the scores, D_i = dO_i . O_i, dQ_i = scale * sum_j dS_ij K_j
+//   pass 2 (thread per key j):   dV_j = sum_i P_ij dO_i ; dK_j = scale * sum_i dS_ij Q_i
+//   with P_ij = exp(scale q_i.k_j - lse_i), dS_ij = P_ij (dO_i . V_j - D_i)
+// =================================================================================================
+namespace {
+template <typename T, int HD>
+__global__ void __launch_bounds__(128) sdpa_bwd_kernel(const T* __restrict__ qkv, const T* __restrict__ o, const T* __restrict__ d_o,
+                                                       T* __restrict__ d_qkv, int L, int C, int heads) {
+  extern __shared__ float sm[];
+  float* Qs = sm;
+  float* Ks = Qs + (size_t)L * HD;
+  float* Vs = Ks + (size_t)L * HD;
+  float* Gs = Vs + (size_t)L * HD;  // dO
+  float* lse = Gs + (size_t)L * HD;
+  float* Dd = lse + L;
+  const int b = blockIdx.x / heads, h = blockIdx.x - b * heads;
+  const int ld = 3 * C;
+  const int tid = threadIdx.x;
+  const int vpr = HD >> 3;
+  for (int v = tid; v < L * vpr; v += 128) {
+    const int j = v / vpr, d8 = (v - j * vpr) << 3;
+    const T* row = qkv + ((size_t)b * L + j) * ld + h * HD + d8;
+    float t8[8];
+    load8(row, t8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Qs[j * HD + d8 + i] = t8[i];
+    load8(row + C, t8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Ks[j * HD + d8 + i] = t8[i];
+    load8(row + 2 * C, t8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Vs[j * HD + d8 + i] = t8[i];
+    load8(d_o + ((size_t)b * L + j) * C + h * HD + d8, t8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Gs[j * HD + d8 + i] = t8[i];
+  }
+  __syncthreads();
+  const float scale = rsqrtf((float)HD);
+  for (int i = tid; i < L; i += 128) {
+    float q[HD], g[HD], dq[HD];
+    float Di = 0.f;
+    const T* orow = o + ((size_t)b * L + i) * C + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; d += 8) {
+      float t8[8];
+      load8(orow + d, t8);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        q[d + e] = Qs[i * HD + d + e] * scale;
+        g[d + e] = Gs[i * HD + d + e];
+        dq[d + e] = 0.f;
+        Di = fmaf(g[d + e], t8[e], Di);
+      }
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int j = 0; j < L; ++j) {
+      float sdot = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) sdot = fmaf(q[d], Ks[j * HD + d], sdot);
+      if (sdot > m) { l = l * __expf(m - sdot) + 1.f; m = sdot; }
+      else l += __expf(sdot - m);
+    }
+    const float ls = m + __logf(l);
+    for (int j = 0; j < L; ++j) {
+      float sdot = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) { sdot = fmaf(q[d], Ks[j * HD + d], sdot); dp = fmaf(g[d], Vs[j * HD + d], dp); }
+      const float ds = __expf(sdot - ls) * (dp - Di);
+#pragma unroll
+      for (int d = 0; d < HD; ++d) dq[d] = fmaf(ds, Ks[j * HD + d], dq[d]);
+    }
+    lse[i] = ls;
+    Dd[i] = Di;
+    T* drow = d_qkv + ((size_t)b * L + i) * ld + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; d += 8) {
+      float t8[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) t8[e] = dq[d + e] * scale;
+      store8(drow + d, t8);
+    }
+  }
+  __syncthreads();
+  for (int j = tid; j < L; j += 128) {
+    float dk[HD], dv[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+    for (int i = 0; i < L; ++i) {
+      float sdot = 0.f, dp = 0.f;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) {
+        sdot = fmaf(Qs[i * HD + d], Ks[j * HD + d], sdot);
+        dp = fmaf(Gs[i * HD + d], Vs[j * HD + d], dp);
+      }
+      const float p = __expf(sdot * scale - lse[i]);
+      const float ds = p * (dp - Dd[i]) * scale;
+#pragma unroll
+      for (int d = 0; d < HD; ++d) { dv[d] = fmaf(p, Gs[i * HD + d], dv[d]); dk[d] = fmaf(ds, Qs[i * HD + d], dk[d]); }
+    }
+    T* drow = d_qkv + ((size_t)b * L + j) * ld + h * HD;
+#pragma unroll
+    for (int d = 0; d < HD; d += 8) {
+      store8(drow + C + d, dk + d);
+      store8(drow + 2 * C + d, dv + d);
+    }
+  }
+}
+
+template <typename T> __global__ void gelu_fwd_kernel(const T* __restrict__ x, T* __restrict__ y, long long nvec) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvec) return;
+  float t[8];
+  load8(x + v * 8, t);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = gelu_exact(t[i]);
+  store8(y + v * 8, t);
+}
+template <typename T> __global__ void gelu_bwd_kernel(const T* __restrict__ dy, const T* __restrict__ pre, T* __restrict__ dx, long long nvec) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvec) return;
+  float d[8], u[8];
+  load8(dy + v * 8, d);
+  load8(pre + v * 8, u);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) d[i] *= gelu_grad(u[i]);
+  store8(dx + v * 8, d);
+}
+}  // namespace
+template <typename T> void launch_sdpa_bwd(const T* qkv, const T* o, const T* d_o, T* d_qkv, int B, int L, int C, int heads, cudaStream_t s) {
+  const int hd = C / heads;
+  const size_t smem = ((size_t)4 * L * hd + 2 * L) * sizeof(float);
+#define SDPA_BWD_CASE(HD)                                                                                       \
+  {                                                                                                             \
+    static bool attr_set = false;                                                                               \
+    if (!attr_set) {                                                                                            \
+      cudaFuncSetAttribute(sdpa_bwd_kernel<T, HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);    \
+      attr_set = true;                                                                                          \
+    }                                                                                                           \
+    sdpa_bwd_kernel<T, HD><<<B * heads, 128, smem, s>>>(qkv, o, d_o, d_qkv, L, C, heads);                       \
+  }
+  if (hd == 16) SDPA_BWD_CASE(16)
+  else if (hd == 32) SDPA_BWD_CASE(32)
+  else if (hd == 64) SDPA_BWD_CASE(64)
+#undef SDPA_BWD_CASE
+  COUNT_LAUNCH();
+}
+template void launch_sdpa_bwd<float>(const float*, const float*, const float*, float*, int, int, int, int, cudaStream_t);
+template void launch_sdpa_bwd<bf16>(const bf16*, const bf16*, const bf16*, bf16*, int, int, int, int, cudaStream_t);
+template <typename T> void launch_gelu_fwd(const T* x, T* y, long long n, cudaStream_t s) {
+  gelu_fwd_kernel<T><<<cdiv(n / 8, 256), 256, 0, s>>>(x, y, n / 8);
+  COUNT_LAUNCH();
+}
+template <typename T> void launch_gelu_bwd(const T* dy, const T* pre, T* dx, long long n, cudaStream_t s) {
+  gelu_bwd_kernel<T><<<cdiv(n / 8, 256), 256, 0, s>>>(dy, pre, dx, n / 8);
+  COUNT_LAUNCH();
+}
+template void launch_gelu_fwd<float>(const float*, float*, long long, cudaStream_t);
+template void launch_gelu_fwd<bf16>(const bf16*, bf16*, long long, cudaStream_t);
+template void launch_gelu_bwd<float>(const float*, const float*, float*, long long, cudaStream_t);
+template void launch_gelu_bwd<bf16>(const bf16*, const bf16*, bf16*, long long, cudaStream_t);
+
+// =================================================================================================
+// MSELoss + outc backward (models/diffusion_ddpm.py:171; Unet_FiLmLayer.py:264,310-311): one block per sample.
+//   e = 2 (eps_hat - noise) / N on the unpadded window, zero on the pad ring
+//   d_act[px][c] = e[px] * w[c] ;  d_w[c] += sum_px e[px] act[px][c] ;  d_b += sum e ;  loss += sum (eps_hat-noise)^2 / N
+// inc.first weight gradient (:101 with pad_to :15-34 folded in): one block per sample.
+// =================================================================================================
+namespace {
+template <typename T>
+__global__ void __launch_bounds__(256) mse_outc_bwd_kernel(const float* __restrict__ eps_hat, const float* __restrict__ noise, const T* __restrict__ act,
+                                                           int ld, const float* __restrict__ w, T* __restrict__ d_act, float* __restrict__ d_w,
+                                                           float* __restrict__ d_b, float* __restrict__ loss, float inv_n, int H, int W, int C,
+                                                           int rows, int dim, int lh, int lw) {
+  extern __shared__ float se[];  // [H*W] e per padded pixel, then [256*8] reduction scratch
+  float* red = se + H * W;
+  __shared__ float scratch[8];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  float lsum = 0.f, esum = 0.f;
+  for (int px = tid; px < H * W; px += 256) {
+    const int hh = px / W - lh, ww = px % W - lw;
+    float e = 0.f;
+    if (hh >= 0 && hh < rows && ww >= 0 && ww < dim) {
+      const size_t i = ((size_t)b * rows + hh) * dim + ww;
+      const float d = eps_hat[i] - noise[i];
+      lsum = fmaf(d, d, lsum);
+      e = 2.f * d * inv_n;
+      esum += e;
+    }
+    se[px] = e;
+  }
+  lsum = block_sum_256(lsum, scratch);
+  esum = block_sum_256(esum, scratch);
+  if (tid == 0) { atomicAdd(loss, lsum * inv_n); atomicAdd(d_b, esum); }
+  const int vpr = C >> 3, c8 = (tid % vpr) << 3, row_step = 256 / vpr;
+  float wv[8], acc[8];
+  load8(w + c8, wv);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+  for (int px = tid / vpr; px < H * W; px += row_step) {
+    const float e = se[px];
+    float a8[8], o[8];
+    load8(act + ((size_t)b * H * W + px) * ld + c8, a8);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { o[i] = e * wv[i]; acc[i] = fmaf(e, a8[i], acc[i]); }
+    store8(d_act + ((size_t)b * H * W + px) * C + c8, o);
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[tid * 8 + i] = acc[i];
+  __syncthreads();
+  if (tid < vpr) {
+    float t[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int r = 0; r < row_step; ++r)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] += red[(r * vpr + tid) * 8 + i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(d_w + c8 + i, t[i]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const float* __restrict__ x, const T* __restrict__ d_raw, float* __restrict__ dw, int H,
+                                                            int W, int rows, int dim, int lh, int lw) {
+  extern __shared__ float sx[];   // [rows*dim] sample, then [64*9] block accumulator
+  float* sacc = sx + rows * dim;
+  const int b = blockIdx.x, tid = threadIdx.x;
+  for (int i = tid; i < rows * dim; i += 256) sx[i] = x[(size_t)b * rows * dim + i];
+  for (int i = tid; i < 64 * 9; i += 256) sacc[i] = 0.f;
+  __syncthreads();
+  const int c8 = (tid & 7) << 3;
+  float acc[9][8];
+#pragma unroll
+  for (int t = 0; t < 9; ++t)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[t][i] = 0.f;
+  for (int px = tid >> 3; px < H * W; px += 32) {
+    const int hh = px / W, ww = px - hh * W;
+    float d[8];
+    load8(d_raw + ((size_t)b * H * W + px) * 64 + c8, d);
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int sh = hh + tap / 3 - 1 - lh, sw_ = ww + tap % 3 - 1 - lw;
+      if (sh < 0 || sh >= rows || sw_ < 0 || sw_ >= dim) continue;
+      const float xv = sx[sh * dim + sw_];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[tap][i] = fmaf(xv, d[i], acc[tap][i]);
+    }
+  }
+#pragma unroll
+  for (int tap = 0; tap < 9; ++tap)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) atomicAdd(&sacc[(c8 + i) * 9 + tap], acc[tap][i]);
+  __syncthreads();
+  for (int i = tid; i < 64 * 9; i += 256) atomicAdd(dw + i, sacc[i]);  // (64, 1, 3, 3) is [c][tap]
+}
+}  // namespace
+template <typename T>
+void launch_mse_outc_bwd(const float* eps_hat, const float* noise, const T* act, int ld, const float* w, T* d_act, float* d_w, float* d_b,
+                         float* loss, int B, int H, int W, int C, int rows, int dim, int lh, int lw, cudaStream_t s) {
+  const size_t smem = ((size_t)H * W + 256 * 8) * sizeof(float);
+  const float inv_n = 1.0f / ((float)B * rows * dim);
+  mse_outc_bwd_kernel<T><<<B, 256, smem, s>>>(eps_hat, noise, act, ld, w, d_act, d_w, d_b, loss, inv_n, H, W, C, rows, dim, lh, lw);
+  COUNT_LAUNCH();
+}
+template <typename T>
+void launch_conv_in_wgrad(const float* x, const T* d_raw, float* dw, int B, int H, int W, int rows, int dim, int lh, int lw, cudaStream_t s) {
+  const size_t smem = ((size_t)rows * dim + 64 * 9) * sizeof(float);
+  conv_in_wgrad_kernel<T><<<B, 256, smem, s>>>(x, d_raw, dw, H, W, rows, dim, lh, lw);
+  COUNT_LAUNCH();
+}
+template void launch_mse_outc_bwd<float>(const float*, const float*, const float*, int, const float*, float*, float*, float*, float*, int, int, int,
+                                         int, int, int, int, int, cudaStream_t);
+template void launch_mse_outc_bwd<bf16>(const float*, const float*, const bf16*, int, const float*, bf16*, float*, float*, float*, int, int, int,
+                                        int, int, int, int, int, cudaStream_t);
+template void launch_conv_in_wgrad<float>(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
+template void launch_conv_in_wgrad<bf16>(const float*, const bf16*, float*, int, int, int, int, int, int, int, cudaStream_t);
+
+// =================================================================================================
+// Conditioning: silu(pos_encoding(t)) rows (Unet_FiLmLayer.py:266-274,136-142), Mish backward (:150),
+// gather of the image-feature gradient out of d obs_cond (models/diffusion_ddpm.py:317-330).
+// =================================================================================================
+namespace {
+__global__ void posenc_silu_kernel(const long long* __restrict__ t_dev, const float* __restrict__ inv_freq, float* __restrict__ out, int time_dim) {
+  const int row = blockIdx.x;
+  const float t = (float)t_dev[row];
+  const int half = time_dim >> 1;
+  for (int i = threadIdx.x; i < time_dim; i += blockDim.x) {
+    const float arg = t * inv_freq[i < half ? i : i - half];
+    const float v = i < half ? sinf(arg) : cosf(arg);
+    out[(size_t)row * time_dim + i] = v / (1.f + expf(-v));
+  }
+}
+__global__ void mish_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x, float* __restrict__ dx, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float v = x[i];
+  const float sp = v > 20.f ? v : log1pf(expf(v));
+  const float th = tanhf(sp);
+  const float sig = 1.f / (1.f + expf(-v));
+  dx[i] = dy[i] * (th + v * (1.f - th * th) * sig);
+}
+__global__ void gather_feat_grad_kernel(const float* __restrict__ d_cond, float* __restrict__ d_feat, long long total, int cond_dim) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int f = cond_dim - 7;
+  const long long bt = i / f;
+  const int j = (int)(i - bt * f);
+  d_feat[i] = d_cond[bt * cond_dim + 7 + j];
+}
+}  // namespace
+void launch_posenc_silu(const long long* t, int n, const float* inv_freq, float* out, int time_dim, cudaStream_t s) {
+  posenc_silu_kernel<<<n, 256, 0, s>>>(t, inv_freq, out, time_dim);
+  COUNT_LAUNCH();
+}
+void launch_mish_bwd(const float* dy, const float* x, float* dx, long long n, cudaStream_t s) {
+  mish_bwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(dy, x, dx, n);
+  COUNT_LAUNCH();
+}
+void launch_gather_feat_grad(const float* d_cond, float* d_feat, int B, int T, int cond_dim, cudaStream_t s) {
+  const long long total = (long long)B * T * (cond_dim - 7);
+  gather_feat_grad_kernel<<<cdiv(total, 256), 256, 0, s>>>(d_cond, d_feat, total, cond_dim);
+  COUNT_LAUNCH();
+}
+
+// =================================================================================================
+// Vision encoder conv stack backward (models/encoder/autoencoder.py:11-17).  k == stride == 2: the three layers are
+// non-overlapping patch contractions, so the backward is strip-local too.  A block walks frames; per 8-row input strip
+// it recomputes conv1/conv2 (+ReLU) in shared memory exactly like enc_convs_kernel, then back-propagates
+// d feat (12 x 64) -> d c2 (32 x 2 x 24) -> d c1 (16 x 4 x 48), accumulating every weight gradient in thread-owned
+// registers across all strips and frames of the block; one atomicAdd per element per block at the end.
+// =================================================================================================
+namespace {
+__global__ void __launch_bounds__(256) enc_convs_bwd_kernel(const float* __restrict__ img, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                            const float* __restrict__ w2t, const float* __restrict__ b2, const float* __restrict__ w3t,
+                                                            const float* __restrict__ feat, const float* __restrict__ d_feat,
+                                                            float* __restrict__ dw1, float* __restrict__ db1, float* __restrict__ dw2,
+                                                            float* __restrict__ db2, float* __restrict__ dw3, float* __restrict__ db3, int n) {
+  extern __shared__ float es[];
+  float* w3s = es;                   // [128][64]  ((c*4+kk), o)
+  float* w2s = w3s + 128 * 64;       // [64][32]
+  float* w1s = w2s + 64 * 32;        // [12][16]
+  float* s_in = w1s + 12 * 16;       // [3][8][97]
+  float* s_c1 = s_in + 3 * 8 * 97;   // [16][4][48]  post-ReLU
+  float* s_c2 = s_c1 + 16 * 4 * 48;  // [32][2][24]  post-ReLU
+  float* s_d3 = s_c2 + 32 * 2 * 24;  // [12][64]     gradient of pre-ReLU conv3
+  float* s_d2 = s_d3 + 12 * 64;      // [32][2][24]  gradient of pre-ReLU conv2
+  float* s_d1 = s_d2 + 32 * 2 * 24;  // [16][4][48]  gradient of pre-ReLU conv1
+  const int tid = threadIdx.x;
+  for (int e = tid; e < 128 * 64; e += 256) w3s[e] = __ldg(w3t + e);
+  for (int e = tid; e < 64 * 32; e += 256) w2s[e] = __ldg(w2t + e);
+  for (int e = tid; e < 12 * 16; e += 256) w1s[e] = __ldg(w1 + (e % 16) * 12 + e / 16);
+  const int ch1 = tid & 15, ch2 = tid & 31, ch3 = tid & 63;
+  const float bias1 = __ldg(b1 + ch1), bias2 = __ldg(b2 + ch2);
+  // thread-owned weight-gradient accumulators
+  float a3[32];   // dW3 element (o = tid%64, ck = tid/64 + 4r)
+  float a2[8];    // dW2 element (o2 = tid%32, ck = tid/32 + 8r), ck = c1*4+kk in [0,64)
+  float a1 = 0.f; // dW1 element tid < 192: (o1 = tid%16, ck = tid/16), ck = c*4+kk in [0,12)
+  float ab = 0.f; // bias gradient: tid < 64 -> db3[tid]; 64..95 -> db2; 96..111 -> db1
+#pragma unroll
+  for (int r = 0; r < 32; ++r) a3[r] = 0.f;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) a2[r] = 0.f;
+
+  for (int frame = blockIdx.x; frame < n; frame += gridDim.x) {
+    const float* im = img + (size_t)frame * 3 * 96 * 96;
+    for (int i = 0; i < 12; ++i) {
+      __syncthreads();
+      for (int e = tid; e < 3 * 8 * 97; e += 256) {
+        const int col = e % 97 - 1;
+        const int r = (e / 97) % 8;
+        const int c = e / (97 * 8);
+        const int gr = 8 * i - 1 + r;
+        float v = 0.f;
+        if (gr >= 0 && gr < 96 && col >= 0 && col < 96) v = im[((size_t)c * 96 + gr) * 96 + col];
+        s_in[e] = v;
+      }
+      for (int e = tid; e < 12 * 64; e += 256) {  // d conv3 (pre-ReLU) = d feat where feat > 0
+        const size_t gi = (size_t)frame * 9216 + (size_t)i * 12 * 64 + e;
+        s_d3[e] = feat[gi] > 0.f ? d_feat[gi] : 0.f;
+      }
+      __syncthreads();
+      // ---- recompute conv1 ----
+#pragma unroll 4
+      for (int k = 0; k < 12; ++k) {
+        const int pos = (tid >> 4) + 16 * k;
+        const int rr = pos / 48, cc = pos - rr * 48;
+        float acc = bias1;
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            acc = fmaf(s_in[(c * 8 + 2 * rr + (kk >> 1)) * 97 + 2 * cc + (kk & 1)], w1s[(c * 4 + kk) * 16 + ch1], acc);
+        s_c1[(ch1 * 4 + rr) * 48 + cc] = fmaxf(acc, 0.f);
+      }
+      __syncthreads();
+      // ---- recompute conv2 ----
+      for (int k = 0; k < 6; ++k) {
+        const int pos = (tid >> 5) + 8 * k;
+        const int rr = pos / 24, cc = pos - rr * 24;
+        float acc = bias2;
+        for (int c = 0; c < 16; ++c)
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk)
+            acc = fmaf(s_c1[(c * 4 + 2 * rr + (kk >> 1)) * 48 + 2 * cc + (kk & 1)], w2s[(c * 4 + kk) * 32 + ch2], acc);
+        s_c2[(ch2 * 2 + rr) * 24 + cc] = fmaxf(acc, 0.f);
+      }
+      __syncthreads();
+      // ---- dW3 / db3 ----
+      {
+        const int o = ch3;
+#pragma unroll 4
+        for (int r = 0; r < 32; ++r) {
+          const int ck = (tid >> 6) + 4 * r, c = ck >> 2, kk = ck & 3;
+          const float* c2p = s_c2 + (c * 2 + (kk >> 1)) * 24 + (kk & 1);
+          float acc = a3[r];
+#pragma unroll
+          for (int j = 0; j < 12; ++j) acc = fmaf(s_d3[j * 64 + o], c2p[2 * j], acc);
+          a3[r] = acc;
+        }
+        if (tid < 64) {
+#pragma unroll
+          for (int j = 0; j < 12; ++j) ab += s_d3[j * 64 + tid];
+        }
+      }
+      // ---- d c2 = W3^T d3, masked by c2 > 0 ----
+      for (int k = 0; k < 6; ++k) {
+        const int pos = (tid >> 5) + 8 * k;   // 48 positions: rr = pos / 24, cc = pos % 24
+        const int rr = pos / 24, cc = pos - rr * 24;
+        const int j = cc >> 1, kk = rr * 2 + (cc & 1);
+        const float* wp = w3s + (ch2 * 4 + kk) * 64;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int o = 0; o < 64; ++o) acc = fmaf(s_d3[j * 64 + o], wp[o], acc);
+        const int idx = (ch2 * 2 + rr) * 24 + cc;
+        s_d2[idx] = s_c2[idx] > 0.f ? acc : 0.f;
+      }
+      __syncthreads();
+      // ---- dW2 / db2 ----
+      {
+        const int o2 = ch2;
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+          const int ck = (tid >> 5) + 8 * r, c = ck >> 2, kk = ck & 3;
+          float acc = a2[r];
+          for (int pos = 0; pos < 48; ++pos) {
+            const int rr = pos / 24, cc = pos - rr * 24;
+            acc = fmaf(s_d2[(o2 * 2 + rr) * 24 + cc], s_c1[(c * 4 + 2 * rr + (kk >> 1)) * 48 + 2 * cc + (kk & 1)], acc);
+          }
+          a2[r] = acc;
+        }
+        if (tid >= 64 && tid < 96) {
+          const int o = tid - 64;
+          for (int pos = 0; pos < 48; ++pos) ab += s_d2[o * 48 + pos];
+        }
+      }
+      // ---- d c1 = W2^T d2, masked by c1 > 0 ----
+      for (int k = 0; k < 12; ++k) {
+        const int pos = (tid >> 4) + 16 * k;  // 192 positions: rr = pos / 48, cc = pos % 48
+        const int rr = pos / 48, cc = pos - rr * 48;
+        const int r2 = rr >> 1, c2 = cc >> 1, kk = (rr & 1) * 2 + (cc & 1);
+        const float* wp = w2s + (ch1 * 4 + kk) * 32;
+        float acc = 0.f;
+#pragma unroll 8
+        for (int o = 0; o < 32; ++o) acc = fmaf(s_d2[(o * 2 + r2) * 24 + c2], wp[o], acc);
+        const int idx = (ch1 * 4 + rr) * 48 + cc;
+        s_d1[idx] = s_c1[idx] > 0.f ? acc : 0.f;
+      }
+      __syncthreads();
+      // ---- dW1 / db1 ----
+      if (tid < 192) {
+        const int o1 = tid & 15, ck = tid >> 4, c = ck >> 2, kk = ck & 3;
+        float acc = a1;
+        for (int pos = 0; pos < 192; ++pos) {
+          const int rr = pos / 48, cc = pos - rr * 48;
+          acc = fmaf(s_d1[(o1 * 4 + rr) * 48 + cc], s_in[(c * 8 + 2 * rr + (kk >> 1)) * 97 + 2 * cc + (kk & 1)], acc);
+        }
+        a1 = acc;
+      }
+      if (tid >= 96 && tid < 112) {
+        const int o = tid - 96;
+        for (int pos = 0; pos < 192; ++pos) ab += s_d1[o * 192 + pos];
+      }
+    }
+  }
+  // ---- flush: PyTorch layouts (64,32,2,2) = [o][ck], (32,16,2,2) = [o2][ck], (16,3,2,2) = [o1][ck] ----
+#pragma unroll
+  for (int r = 0; r < 32; ++r) atomicAdd(dw3 + ch3 * 128 + (tid >> 6) + 4 * r, a3[r]);
+#pragma unroll
+  for (int r = 0; r < 8; ++r) atomicAdd(dw2 + ch2 * 64 + (tid >> 5) + 8 * r, a2[r]);
+  if (tid < 192) atomicAdd(dw1 + (tid & 15) * 12 + (tid >> 4), a1);
+  if (tid < 64) atomicAdd(db3 + tid, ab);
+  else if (tid < 96) atomicAdd(db2 + tid - 64, ab);
+  else if (tid < 112) atomicAdd(db1 + tid - 96, ab);
+}
+
+__global__ void enc_linear_grad_permute_kernel(const float* __restrict__ tmp, float* __restrict__ dwl) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128LL * 9216) return;
+  const int k2 = (int)(i % 9216);   // hwc index p*64 + c
+  const int nrow = (int)(i / 9216);
+  const int c = k2 % 64, p = k2 / 64;
+  dwl[(size_t)nrow * 9216 + c * 144 + p] += tmp[i];
+}
+__global__ void pack_enc_linear_t_kernel(const float* __restrict__ w, float* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128LL * 9216) return;
+  const int k2 = (int)(i % 9216);
+  const int nrow = (int)(i / 9216);
+  const int c = k2 % 64, p = k2 / 64;
+  out[i] = w[(size_t)nrow * 9216 + c * 144 + p];
+}
+}  // namespace
+void launch_enc_convs_bwd(const float* img, const float* w1, const float* b1, const float* w2t, const float* b2, const float* w3t,
+                          const float* feat, const float* d_feat, float* dw1, float* db1, float* dw2, float* db2, float* dw3, float* db3,
+                          int n, cudaStream_t s) {
+  constexpr size_t smem = (128 * 64 + 64 * 32 + 12 * 16 + 3 * 8 * 97 + 2 * (16 * 4 * 48) + 2 * (32 * 2 * 24) + 12 * 64) * sizeof(float);
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(enc_convs_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr = true; }
+  int grid = n < 148 * 2 ? n : 148 * 2;
+  enc_convs_bwd_kernel<<<grid, 256, smem, s>>>(img, w1, b1, w2t, b2, w3t, feat, d_feat, dw1, db1, dw2, db2, dw3, db3, n);
+  COUNT_LAUNCH();
+}
+void launch_enc_linear_grad_permute(const float* tmp_hwc, float* dwl, cudaStream_t s) {
+  enc_linear_grad_permute_kernel<<<cdiv(128LL * 9216, 256), 256, 0, s>>>(tmp_hwc, dwl);
+  COUNT_LAUNCH();
+}
+void launch_pack_enc_linear_t(const float* w, float* out, cudaStream_t s) {
+  pack_enc_linear_t_kernel<<<cdiv(128LL * 9216, 256), 256, 0, s>>>(w, out);
+}
+
+// =================================================================================================
+// dgrad weight packs: d x = conv(d y, W') with W'[tap'][co][ci] = W[co][ci][8 - tap'] (3x3, pad 1) and
+// d x = d y W for a Linear y = x W^T.
+// =================================================================================================
+namespace {
+__global__ void pack_conv_dgrad_f32_kernel(const float* __restrict__ oihw, float* __restrict__ out, int Cout, int Cin) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cout * Cin * 9) return;
+  const int ci = (int)(i % Cin);          // out index = (tap' * Cout + co) * Cin + ci
+  const long long t = i / Cin;
+  const int co = (int)(t % Cout);
+  const int tp = (int)(t / Cout);
+  out[i] = oihw[((size_t)co * Cin + ci) * 9 + (8 - tp)];
+}
+__global__ void pack_conv_dgrad_bf16_kernel(const float* __restrict__ oihw, bf16* __restrict__ out, int Cout, int Cin) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cout * Cin * 9) return;
+  const int co = (int)(i % Cout);         // out index = (ci * 9 + tap') * Cout + co
+  const long long t = i / Cout;
+  const int tp = (int)(t % 9);
+  const int ci = (int)(t / 9);
+  out[i] = __float2bfloat16_rn(oihw[((size_t)co * Cin + ci) * 9 + (8 - tp)]);
+}
+__global__ void pack_linear_dgrad_bf16_kernel(const float* __restrict__ nk, bf16* __restrict__ out, int N, int K) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)N * K) return;
+  const int nn = (int)(i % N);            // out [K][N]
+  const int k = (int)(i / N);
+  out[i] = __float2bfloat16_rn(nk[(size_t)nn * K + k]);
+}
+}  // namespace
+namespace {
+__global__ void unpack_conv_grad_kernel(const float* __restrict__ packed, float* __restrict__ dst, int Cout, int Cin) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // index into packed [tap][co][ci]
+  if (i >= (long long)Cout * Cin * 9) return;
+  const int ci = (int)(i % Cin);
+  const long long t = i / Cin;
+  const int co = (int)(t % Cout);
+  const int tap = (int)(t / Cout);
+  dst[((size_t)co * Cin + ci) * 9 + tap] = packed[i];
+}
+}  // namespace
+void launch_unpack_conv_grad(const float* packed, float* dst, int Cout, int Cin, cudaStream_t s) {
+  unpack_conv_grad_kernel<<<cdiv((long long)Cout * Cin * 9, 256), 256, 0, s>>>(packed, dst, Cout, Cin);
+  COUNT_LAUNCH();
+}
+void launch_pack_conv_dgrad_f32(const float* oihw, float* out, int Cout, int Cin, cudaStream_t s) {
+  pack_conv_dgrad_f32_kernel<<<cdiv((long long)Cout * Cin * 9, 256), 256, 0, s>>>(oihw, out, Cout, Cin);
+}
+void launch_pack_conv_dgrad_bf16(const float* oihw, bf16* out, int Cout, int Cin, cudaStream_t s) {
+  pack_conv_dgrad_bf16_kernel<<<cdiv((long long)Cout * Cin * 9, 256), 256, 0, s>>>(oihw, out, Cout, Cin);
+}
+void launch_pack_linear_dgrad_bf16(const float* nk, bf16* out, int N, int K, cudaStream_t s) {
+  pack_linear_dgrad_bf16_kernel<<<cdiv((long long)N * K, 256), 256, 0, s>>>(nk, out, N, K);
+}
+
+// =================================================================================================
+// Optimizer: clip_grad_norm_ (Lightning gradient_clip_val, train.py:107) + torch.optim.Adam (ddpm:115-125).
+// =================================================================================================
+namespace {
+__global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  __shared__ float scratch[8];
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) acc = fmaf(g[i], g[i], acc);
+  acc = block_sum_256(acc, scratch);
+  if (threadIdx.x == 0) atomicAdd(out, acc);
+}
+__global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
+                                                   long long n, float lr, float beta1, float beta2, float eps, float bc1, float bc2_sqrt,
+                                                   const float* __restrict__ sumsq, float max_norm, float grad_scale) {
+  float coef = grad_scale;
+  if (sumsq) {
+    const float total = sqrtf(*sumsq) * grad_scale;
+    float c = max_norm / (total + 1e-6f);
+    if (c > 1.f) c = 1.f;
+    coef *= c;
+  }
+  const float step_size = lr / bc1;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float gi = g[i] * coef;
+    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
+    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+    const float denom = sqrtf(vi) / bc2_sqrt + eps;
+    p[i] -= step_size * (mi / denom);
+    m[i] = mi;
+    v[i] = vi;
+    g[i] = gi;
+  }
+}
+}  // namespace
+void launch_sumsq(const float* g, long long n, float* out, cudaStream_t s) {
+  int grid = cdiv(n, 256 * 8);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  sumsq_kernel<<<grid, 256, 0, s>>>(g, n, out);
+  COUNT_LAUNCH();
+}
+void launch_adam(float* p, float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps, int step,
+                 const float* sumsq, float max_norm, float grad_scale, cudaStream_t s) {
+  int grid = cdiv(n, 256 * 4);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid < 1) grid = 1;
+  const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
+  const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
+  adam_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, sumsq, max_norm, grad_scale);
+  COUNT_LAUNCH();
+}

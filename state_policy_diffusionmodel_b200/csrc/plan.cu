@@ -17,6 +17,7 @@
 
 #include "../../include/spdm.h"
 #include "common.cuh"
+#include "train.cuh"
 
 // -------------------------------------------------------------------------------------------------
 // errors
@@ -61,6 +62,7 @@ struct GemmW {  // a 3x3 convolution or a Linear layer
   float* w32 = nullptr;  // [taps][Cin][Cout]   (fp32 path)
   bf16* w16 = nullptr;   // [Cout][taps*Cin]    (bf16 tcgen05 path)
   float* bias = nullptr; // [Cout] or null
+  GemmW* twin = nullptr; // training: the data-gradient GEMM (Cin/Cout exchanged, transposed / tap-flipped weights)
 };
 struct NormW { float* g = nullptr; float* b = nullptr; int C = 0; };
 struct StageInfo { const char* name; int cin, cout; int temb_off, film_off; };
@@ -139,6 +141,8 @@ struct spdm_plan {
   std::vector<cudaEvent_t> ev_pool;
   size_t ev_used = 0;
 
+  struct TrainState* tr = nullptr;  // training step state (train_impl.inl), null until spdm_train_enable
+
   // debug tap
   std::string tap_name; float* tap_out = nullptr; long long tap_count = -1;
 
@@ -157,7 +161,11 @@ struct spdm_plan {
 
 namespace {
 
-long long total_launches() { return kernels_launch_count() + tc_launch_count(); }
+long long total_launches() { return kernels_launch_count() + tc_launch_count() + bwd_launch_count() + wgrad_tc_launch_count_value; }
+
+float* train_film_wT(spdm_plan* p);  // training-only transposed weight copies (null when training is not enabled)
+float* train_enc_wlT(spdm_plan* p);
+void train_destroy(spdm_plan* p);
 
 // ---- weight registration -------------------------------------------------------------------------
 void check_shape(const std::string& name, const int64_t* shape, int ndim, std::initializer_list<int64_t> want) {
@@ -194,6 +202,10 @@ GemmW& reg_conv3(spdm_plan* p, const std::string& name, int Cin, int Cout) {
     check_shape(name + ".weight", shape, ndim, {Cout, Cin, 3, 3});
     if (bfm) launch_pack_conv_bf16(src, gp->w16, Cout, Cin, 3, s);
     else launch_pack_conv_f32(src, gp->w32, Cout, Cin, 3, s);
+    if (gp->twin) {
+      if (bfm) launch_pack_conv_dgrad_bf16(src, gp->twin->w16, Cout, Cin, s);
+      else launch_pack_conv_dgrad_f32(src, gp->twin->w32, Cout, Cin, s);
+    }
   };
   return g;
 }
@@ -211,6 +223,10 @@ GemmW& reg_linear(spdm_plan* p, const std::string& wname, const std::string& bna
     check_shape(wname, shape, ndim, {N, K});
     if (bfm) launch_cast_bf16(src, gp->w16, (long long)K * N, s);  // (N,K) row-major is already the K-major B operand
     else launch_pack_linear_f32(src, gp->w32, N, K, N, 0, s);
+    if (gp->twin) {  // d x = d y W: [Cin_g = N][Cout_g = K] fp32 is the PyTorch layout itself; bf16 wants it K-major = [K][N]
+      if (bfm) launch_pack_linear_dgrad_bf16(src, gp->twin->w16, N, K, s);
+      else CUDA_OK(cudaMemcpyAsync(gp->twin->w32, src, (size_t)N * K * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    }
   };
   reg_vec(p, bname, g.bias, N, p->missing_unet);
   return g;
@@ -274,6 +290,8 @@ void register_weights(spdm_plan* p) {
       p->loaders[wn] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
         check_shape(wn, shape, ndim, {C2, G});
         launch_pack_linear_f32(src, dst, C2, G, SPDM_FILM_WIDTH, off, s);
+        if (float* wt = train_film_wT(p))  // [1792][G]: rows off.. = this stage's (2C, G) weight as stored by PyTorch
+          CUDA_OK(cudaMemcpyAsync(wt + (size_t)off * G, src, (size_t)C2 * G * sizeof(float), cudaMemcpyDeviceToDevice, s));
       };
       reg_vec(p, n + ".cond_encoder.2.bias", p->film_b + off, C2, p->missing_unet);
     }
@@ -345,6 +363,7 @@ void register_weights(spdm_plan* p) {
       check_shape("vision_encoder.7.weight", shape, ndim, {128, 9216});
       launch_pack_enc_linear(src, dst, s);
       if (dst16) launch_pack_enc_linear_bf16(src, dst16, s);
+      if (float* wt = train_enc_wlT(p)) launch_pack_enc_linear_t(src, wt, s);
     };
   }
   reg_vec(p, "vision_encoder.7.bias", p->enc_bl, 128, p->missing_enc);
@@ -412,6 +431,7 @@ template <typename T> struct Fwd {
   int Bpad;
   bf16* vt = nullptr;  // set around the in_proj GEMM of an attention block that feeds sdpa_tc (EPI_VT)
   int vt_lk = 0;
+  float* stats_ov = nullptr;  // training: every conv keeps its own GroupNorm partial sums for the backward pass
 
   Fwd(spdm_plan* p_, const FwdCtx& c_) : p(p_), c(c_) { Bpad = ((c.B + p->bm - 1) / p->bm) * p->bm; }
 
@@ -424,7 +444,7 @@ template <typename T> struct Fwd {
     static const int catt[4] = {64, 128, 256, 256};
     return reinterpret_cast<T*>(v) + (size_t)c.b0 * p->levelH(level) * p->levelW(level) * catt[level] * mult;
   }
-  float* stats() const { return p->stats + (size_t)c.b0 * SPDM_MAX_PARTIALS * 2; }
+  float* stats() const { return stats_ov ? stats_ov : p->stats + (size_t)c.b0 * SPDM_MAX_PARTIALS * 2; }
 
   void tap(const std::string& name, const T* ptr, int ld, int C, int level) {
     if (p->tap_out && p->tap_name == name) {
@@ -887,6 +907,7 @@ extern "C" int spdm_plan_destroy(spdm_plan* p) {
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   for (auto& kv : p->tail_cache) attn_tail_destroy(kv.second);
   for (void* q : p->allocs) cudaFree(q);
+  train_destroy(p);
   if (p->dyn_host) cudaFreeHost(p->dyn_host);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   if (p->ev_in) cudaEventDestroy(p->ev_in);
@@ -1263,3 +1284,5 @@ extern "C" int spdm_microbench_conv(int32_t H, int32_t W, int32_t B, int32_t Cin
 
 extern "C" int64_t spdm_plan_launch_count(spdm_plan* p) { return p ? p->launches : 0; }
 extern "C" int64_t spdm_plan_workspace_bytes(spdm_plan* p) { return p ? (int64_t)p->bytes : 0; }
+
+#include "train_impl.inl"

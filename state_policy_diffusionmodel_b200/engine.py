@@ -202,6 +202,80 @@ class DenoisePlan:
         self._keep = [x0, noise, t, sa, sb, ip]
         return out
 
+    # ------------------------------------------------------------------ training step
+    def enable_training(self, named_tensors):
+        """Turns the plan into a training plan (reference: `process_single_batch` + `loss.backward()` + Adam,
+        models/diffusion_ddpm.py:115-173).  `named_tensors`: ordered {name: tensor} of every trainable tensor — U-Net
+        state_dict names, encoder tensors as `vision_encoder.<k>`.  Allocates the flat fp32 parameter / gradient /
+        Adam-moment buffers (one NCCL all-reduce and one optimizer kernel cover all of them), uploads the weights and
+        returns {name: (offset, shape)}."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_train_enable(self._h))
+            self.train_offsets, off = {}, 0
+            for name, t in named_tensors.items():
+                self.train_offsets[name] = (off, tuple(t.shape))
+                off += (t.numel() + 3) // 4 * 4
+            self.train_total = off
+            self.params_flat = torch.zeros(off, device=self.device, dtype=torch.float32)
+            self.grads_flat = torch.zeros_like(self.params_flat)
+            self.adam_m = torch.zeros_like(self.params_flat)
+            self.adam_v = torch.zeros_like(self.params_flat)
+            self._adam_scratch = torch.zeros(1, device=self.device, dtype=torch.float32)
+            self.adam_steps = 0
+            for name, t in named_tensors.items():
+                o, shp = self.train_offsets[name]
+                self.params_flat[o:o + t.numel()].copy_(t.detach().reshape(-1).to(self.device, torch.float32))
+                shape = (ctypes.c_int64 * max(len(shp), 1))(*(shp if len(shp) else (1,)))
+                _lib.check(self.lib.spdm_train_bind(self._h, name.encode(), o, shape, max(len(shp), 1)))
+            _lib.check(self.lib.spdm_train_set_buffers(self._h, _ptr(self.params_flat), _ptr(self.grads_flat), off))
+            td = self.cfg.time_dim
+            self.load_weight("pos_encoding.inv_freq", 1.0 / (10000 ** (torch.arange(0, td, 2) / td)))
+            self.sync_weights()
+        return self.train_offsets
+
+    def param_view(self, name, flat=None):
+        o, shp = self.train_offsets[name]
+        n = 1
+        for d in shp:
+            n *= d
+        return (self.params_flat if flat is None else flat)[o:o + n].view(shp)
+
+    def grad_view(self, name):
+        return self.param_view(name, self.grads_flat)
+
+    def sync_weights(self):
+        """Repack the flat fp32 parameters into the kernel layouts (forward operands and data-gradient twins)."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_train_sync_weights(self._h, _stream()))
+
+    def train_fwd_bwd(self, image, position, action, velocity, x0, noise, t, sqrt_ab, sqrt_1mab, inpaint=None):
+        """q-sample + inpaint + encoder + U-Net forward, MSE loss, full backward.  Gradients (fp32, PyTorch layout) are left
+        in `grads_flat`; returns the loss as a 1-element device tensor."""
+        B = x0.shape[0]
+        img, pos, act, vel = (_f32c(v, self.device) for v in (image, position, action, velocity))
+        x0, noise = _f32c(x0, self.device), _f32c(noise, self.device)
+        t = t.detach().to(self.device, torch.int64).contiguous()
+        sa, sb = _f32c(sqrt_ab, self.device), _f32c(sqrt_1mab, self.device)
+        ip = None if inpaint is None else _f32c(inpaint, self.device)
+        loss = torch.empty(1, device=self.device, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_train_fwd_bwd(self._h, _ptr(img), _ptr(pos), _ptr(act), _ptr(vel), _ptr(x0), _ptr(noise), _ptr(t),
+                                                   _ptr(sa), _ptr(sb), _ptr(ip), _ptr(loss), B, _stream()))
+        self._keep = [img, pos, act, vel, x0, noise, t, sa, sb, ip]
+        return loss
+
+    def adam_step(self, lr=1e-4, betas=(0.9, 0.999), eps=1e-8, max_norm=0.5, grad_scale=1.0, sync=True):
+        """clip_grad_norm_(max_norm) (train.py:107) + torch.optim.Adam.step() (ddpm:115-125) on the flat buffers, then
+        re-upload the weights.  grad_scale = 1 / world_size after a summing all-reduce."""
+        self.adam_steps += 1
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.spdm_adam_step(_ptr(self.params_flat), _ptr(self.grads_flat), _ptr(self.adam_m), _ptr(self.adam_v),
+                                               self.train_total, float(lr), float(betas[0]), float(betas[1]), float(eps),
+                                               int(self.adam_steps), float(max_norm or 0.0), float(grad_scale),
+                                               _ptr(self._adam_scratch), _stream()))
+            if sync:
+                self.sync_weights()
+
     def profile_step(self, B, reps=3):
         """Eager, CUDA-event-timed denoising step: {class: dict(ms, launches, flops, bytes)} averaged over `reps`."""
         n = len(_lib.PROFILE_CLASSES)
