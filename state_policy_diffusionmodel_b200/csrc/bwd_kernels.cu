@@ -278,8 +278,8 @@ template void launch_wgrad_simt<float, float>(const WgradArgs&, cudaStream_t);
 template void launch_wgrad_simt<bf16, bf16>(const WgradArgs&, cudaStream_t);
 template void launch_wgrad_simt<float, bf16>(const WgradArgs&, cudaStream_t);
 template <typename T> void launch_colsum(const T* dy, int ld, long long M, int N, float* out, cudaStream_t s) {
-  int gy = (int)((M + 1023) / 1024);
-  if (gy > 64) gy = 64;
+  int gy = (int)((M + 255) / 256);
+  if (gy > 148 * 4) gy = 148 * 4;
   const long long rpb = (M + gy - 1) / gy;
   colsum_kernel<T><<<dim3(cdiv(N, 64), gy), 256, 0, s>>>(dy, ld, M, N, out, rpb);
   COUNT_LAUNCH();
@@ -1112,5 +1112,194 @@ void launch_adam(float* p, float* g, float* m, float* v, long long n, float lr, 
   const float bc1 = (float)(1.0 - pow((double)beta1, (double)step));
   const float bc2_sqrt = (float)sqrt(1.0 - pow((double)beta2, (double)step));
   adam_kernel<<<grid, 256, 0, s>>>(p, g, m, v, n, lr, beta1, beta2, eps, bc1, bc2_sqrt, sumsq, max_norm, grad_scale);
+  COUNT_LAUNCH();
+}
+
+// =================================================================================================
+// Vision encoder on the tensor cores (bf16 training path; models/encoder/autoencoder.py:11-20).
+// k == stride == 2 makes conv2 / conv3 plain GEMMs once the activations are stored patch-major:
+//   c1p [M2 = n*576][64]  : row = ((frame*144 + p3)*4 + kk3) = one 2x2 patch of conv1 pixels, col = kk2*16 + ch
+//   c2  [M2][64] (ch >= 32 are zero padding)  ==  [M3 = n*144][256] : row = conv3 patch p3, col = kk3*64 + ch
+//   feat [M3][64] == [n][9216] in (pixel, channel) order
+// so conv2 = c1p @ W2p^T (64 -> 64, half of it padding), conv3 = c2 @ W3p^T (256 -> 64), both through conv_tc.cu with a
+// bias + ReLU epilogue, and their backward is wgrad_tc.cu + the same GEMM with transposed weights.  What stays on CUDA
+// cores: conv1 (3 -> 16, K = 12), its weight gradient, the ReLU masks and the tiny weight (un)packs.
+// =================================================================================================
+namespace {
+// one block per (frame, conv3 row r3): 192 conv1 pixels, one thread each, 16 channels per thread
+__global__ void __launch_bounds__(192) enc_conv1_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w1, const float* __restrict__ b1,
+                                                            bf16* __restrict__ c1p) {
+  __shared__ float s_in[3 * 8 * 97];
+  __shared__ __align__(16) float w1s[12 * 16];
+  __shared__ __align__(16) float b1s[16];
+  const int tid = threadIdx.x;
+  const int frame = blockIdx.x / 12, r3 = blockIdx.x % 12;
+  const float* im = img + (size_t)frame * 3 * 96 * 96;
+  for (int e = tid; e < 12 * 16; e += 192) w1s[e] = __ldg(w1 + (e % 16) * 12 + e / 16);
+  if (tid < 16) b1s[tid] = __ldg(b1 + tid);
+  for (int e = tid; e < 3 * 8 * 97; e += 192) {
+    const int col = e % 97 - 1;
+    const int r = (e / 97) % 8;
+    const int c = e / (97 * 8);
+    const int gr = 8 * r3 - 1 + r;
+    float v = 0.f;
+    if (gr >= 0 && gr < 96 && col >= 0 && col < 96) v = im[((size_t)c * 96 + gr) * 96 + col];
+    s_in[e] = v;
+  }
+  __syncthreads();
+  // tid = (c3*4 + kk3)*4 + kk2 : consecutive threads write consecutive 32-byte pixel slots of c1p
+  const int kk2 = tid & 3, kk3 = (tid >> 2) & 3, c3 = tid >> 4;
+  const int yl = 2 * (kk3 >> 1) + (kk2 >> 1);        // conv1 row inside the strip (0..3)
+  const int x = 2 * (2 * c3 + (kk3 & 1)) + (kk2 & 1);  // conv1 column (0..47)
+  float acc[16];
+#pragma unroll
+  for (int o = 0; o < 16; ++o) acc[o] = b1s[o];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const float xv = s_in[(c * 8 + 2 * yl + (kk >> 1)) * 97 + 2 * x + (kk & 1)];
+      const float4* wp = reinterpret_cast<const float4*>(w1s + (c * 4 + kk) * 16);
+#pragma unroll
+      for (int o4 = 0; o4 < 4; ++o4) {
+        const float4 w = wp[o4];
+        acc[o4 * 4 + 0] = fmaf(xv, w.x, acc[o4 * 4 + 0]);
+        acc[o4 * 4 + 1] = fmaf(xv, w.y, acc[o4 * 4 + 1]);
+        acc[o4 * 4 + 2] = fmaf(xv, w.z, acc[o4 * 4 + 2]);
+        acc[o4 * 4 + 3] = fmaf(xv, w.w, acc[o4 * 4 + 3]);
+      }
+    }
+#pragma unroll
+  for (int o = 0; o < 16; ++o) acc[o] = fmaxf(acc[o], 0.f);
+  bf16* dst = c1p + ((size_t)blockIdx.x * 192 + tid) * 16;  // (frame*144 + r3*12 + c3)*4*64 + kk3*64 + kk2*16
+  store8(dst, acc);
+  store8(dst + 8, acc + 8);
+}
+
+// dW1 (16,3,2,2) and db1 from d1 [M2][64] (gradient of the pre-ReLU conv1 output, same layout as c1p).
+// Thread (o, ck) owns one weight; a block walks (frame, r3) strips; the strip's 192 pixels come from shared memory.
+__global__ void __launch_bounds__(192) enc_conv1_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ d1, float* __restrict__ dw1,
+                                                              float* __restrict__ db1, int n_strips) {
+  __shared__ float s_in[3 * 8 * 97];
+  __shared__ float s_d[192 * 16];
+  const int tid = threadIdx.x;
+  const int o = tid & 15, ck = tid >> 4, c = ck >> 2, kk = ck & 3;
+  float acc = 0.f, accb = 0.f;
+  for (int strip = blockIdx.x; strip < n_strips; strip += gridDim.x) {
+    const int frame = strip / 12, r3 = strip % 12;
+    const float* im = img + (size_t)frame * 3 * 96 * 96;
+    __syncthreads();
+    for (int e = tid; e < 3 * 8 * 97; e += 192) {
+      const int col = e % 97 - 1;
+      const int r = (e / 97) % 8;
+      const int cc = e / (97 * 8);
+      const int gr = 8 * r3 - 1 + r;
+      float v = 0.f;
+      if (gr >= 0 && gr < 96 && col >= 0 && col < 96) v = im[((size_t)cc * 96 + gr) * 96 + col];
+      s_in[e] = v;
+    }
+    {
+      float t8[8];
+      const bf16* src = d1 + ((size_t)strip * 192 + tid) * 16;
+      load8(src, t8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_d[tid * 16 + i] = t8[i];
+      load8(src + 8, t8);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_d[tid * 16 + 8 + i] = t8[i];
+    }
+    __syncthreads();
+#pragma unroll 4
+    for (int px = 0; px < 192; ++px) {
+      const int kk2 = px & 3, kk3 = (px >> 2) & 3, c3 = px >> 4;
+      const int yl = 2 * (kk3 >> 1) + (kk2 >> 1);
+      const int x = 2 * (2 * c3 + (kk3 & 1)) + (kk2 & 1);
+      const float d = s_d[px * 16 + o];
+      acc = fmaf(d, s_in[(c * 8 + 2 * yl + (kk >> 1)) * 97 + 2 * x + (kk & 1)], acc);
+      if (ck == 0) accb += d;
+    }
+  }
+  atomicAdd(dw1 + o * 12 + ck, acc);
+  if (ck == 0) atomicAdd(db1 + o, accb);
+}
+
+// out = act > 0 ? d : 0   (ReLU backward), 8 bf16 per thread; in place allowed
+__global__ void relu_mask_kernel(const bf16* __restrict__ d, const bf16* __restrict__ act, bf16* __restrict__ out, long long nvec) {
+  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= nvec) return;
+  float a[8], g[8];
+  load8(act + v * 8, a);
+  load8(d + v * 8, g);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) g[i] = a[i] > 0.f ? g[i] : 0.f;
+  store8(out + v * 8, g);
+}
+
+// weight packs of the patch-GEMM encoder (see header of this section)
+__global__ void enc_pack_tc_kernel(const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
+                                   bf16* __restrict__ w2p, bf16* __restrict__ w2pT, bf16* __restrict__ w3p, bf16* __restrict__ w3pT,
+                                   float* __restrict__ b2p) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 64 * 64) {   // W2p[o][k], k = kk2*16 + c1 ; PyTorch (32,16,2,2): o*64 + c1*4 + kk2
+    const int o = i / 64, k = i % 64, kk2 = k / 16, c1 = k % 16;
+    const float v = o < 32 ? w2[o * 64 + c1 * 4 + kk2] : 0.f;
+    w2p[i] = __float2bfloat16_rn(v);
+    w2pT[k * 64 + o] = __float2bfloat16_rn(v);
+  }
+  if (i < 64 * 256) {  // W3p[o][k], k = kk3*64 + c2 (c2 < 32 real) ; PyTorch (64,32,2,2): o*128 + c2*4 + kk3
+    const int o = i / 256, k = i % 256, kk3 = k / 64, c2 = k % 64;
+    const float v = c2 < 32 ? w3[o * 128 + c2 * 4 + kk3] : 0.f;
+    w3p[i] = __float2bfloat16_rn(v);
+    w3pT[k * 64 + o] = __float2bfloat16_rn(v);
+  }
+  if (i < 64) b2p[i] = i < 32 ? b2[i] : 0.f;
+}
+// (128, 9216 chw) fp32 -> bf16 [9216 hwc][128]  (B operand of d feat = d enc_out @ Wl)
+__global__ void enc_pack_linear_T16_kernel(const float* __restrict__ w, bf16* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 128LL * 9216) return;
+  const int nrow = (int)(i % 128);
+  const int k2 = (int)(i / 128);
+  const int c = k2 % 64, p = k2 / 64;
+  out[i] = __float2bfloat16_rn(w[(size_t)nrow * 9216 + c * 144 + p]);
+}
+// padded patch-GEMM weight gradients -> PyTorch layouts (accumulating)
+__global__ void enc_unpack_grads_kernel(const float* __restrict__ g2 /*[64][64]*/, const float* __restrict__ g3 /*[64][256]*/,
+                                        const float* __restrict__ gb2 /*[64]*/, float* __restrict__ dw2, float* __restrict__ db2,
+                                        float* __restrict__ dw3) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 32 * 64) {   // dw2 (32,16,2,2): o*64 + c1*4 + kk2
+    const int o = i / 64, r = i % 64, c1 = r / 4, kk2 = r % 4;
+    dw2[i] += g2[o * 64 + kk2 * 16 + c1];
+  }
+  if (i < 64 * 128) {  // dw3 (64,32,2,2): o*128 + c2*4 + kk3
+    const int o = i / 128, r = i % 128, c2 = r / 4, kk3 = r % 4;
+    dw3[i] += g3[o * 256 + kk3 * 64 + c2];
+  }
+  if (i < 32) db2[i] += gb2[i];
+}
+}  // namespace
+void launch_enc_conv1_fwd(const float* img, const float* w1, const float* b1, bf16* c1p, int n, cudaStream_t s) {
+  enc_conv1_fwd_kernel<<<n * 12, 192, 0, s>>>(img, w1, b1, c1p);
+  COUNT_LAUNCH();
+}
+void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float* db1, int n, cudaStream_t s) {
+  int grid = n * 12;
+  if (grid > 148 * 8) grid = 148 * 8;
+  enc_conv1_wgrad_kernel<<<grid, 192, 0, s>>>(img, d1, dw1, db1, n * 12);
+  COUNT_LAUNCH();
+}
+void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, cudaStream_t s) {
+  relu_mask_kernel<<<cdiv(n / 8, 256), 256, 0, s>>>(d, act, out, n / 8);
+  COUNT_LAUNCH();
+}
+void launch_enc_pack_tc(const float* w2, const float* b2, const float* w3, bf16* w2p, bf16* w2pT, bf16* w3p, bf16* w3pT, float* b2p, cudaStream_t s) {
+  enc_pack_tc_kernel<<<cdiv(64 * 256, 256), 256, 0, s>>>(w2, b2, w3, w2p, w2pT, w3p, w3pT, b2p);
+}
+void launch_enc_pack_linear_T16(const float* w, bf16* out, cudaStream_t s) {
+  enc_pack_linear_T16_kernel<<<cdiv(128LL * 9216, 256), 256, 0, s>>>(w, out);
+}
+void launch_enc_unpack_grads(const float* g2, const float* g3, const float* gb2, float* dw2, float* db2, float* dw3, cudaStream_t s) {
+  enc_unpack_grads_kernel<<<cdiv(64 * 128, 256), 256, 0, s>>>(g2, g3, gb2, dw2, db2, dw3);
   COUNT_LAUNCH();
 }

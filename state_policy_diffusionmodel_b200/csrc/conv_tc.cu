@@ -338,6 +338,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; ++i) f[i] = gelu_exact(f[i]);
         }
+        if (p.flags & EPI_RELU) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
+        }
         if (rrow) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {

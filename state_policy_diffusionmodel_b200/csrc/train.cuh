@@ -81,6 +81,14 @@ void launch_enc_linear_grad_permute(const float* tmp_hwc, float* dwl, cudaStream
 // (128, 9216 chw) -> [128][9216 hwc] fp32 (B operand of the feature-gradient GEMM)
 void launch_pack_enc_linear_t(const float* w, float* out, cudaStream_t s);
 
+// ---- vision encoder as patch GEMMs on the tensor cores (bf16 training path; layouts in bwd_kernels.cu) ----------
+void launch_enc_conv1_fwd(const float* img, const float* w1, const float* b1, bf16* c1p, int n, cudaStream_t s);
+void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float* db1, int n, cudaStream_t s);
+void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, cudaStream_t s);
+void launch_enc_pack_tc(const float* w2, const float* b2, const float* w3, bf16* w2p, bf16* w2pT, bf16* w3p, bf16* w3pT, float* b2p, cudaStream_t s);
+void launch_enc_pack_linear_T16(const float* w, bf16* out, cudaStream_t s);
+void launch_enc_unpack_grads(const float* g2, const float* g3, const float* gb2, float* dw2, float* db2, float* dw3, cudaStream_t s);
+
 // ---- dgrad weight packs (the data gradient of a conv/Linear is a forward GEMM with these weights) ----------
 void launch_pack_conv_dgrad_f32(const float* oihw, float* out, int Cout, int Cin, cudaStream_t s);   // -> [tap'][Cout][Cin], tap' = 8 - tap
 void launch_pack_conv_dgrad_bf16(const float* oihw, bf16* out, int Cout, int Cin, cudaStream_t s);  // -> [Cin][tap'][Cout]

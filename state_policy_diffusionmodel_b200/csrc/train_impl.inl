@@ -21,6 +21,10 @@ struct TrainState {
   float* packed = nullptr; size_t packed_elems = 0;  // bf16 path: conv weight gradients as [tap][Cout][Cin]
   std::map<std::string, size_t> packed_off;
   float* loss_dev = nullptr;
+  // bf16 path: vision encoder as patch GEMMs (layouts: bwd_kernels.cu, "Vision encoder on the tensor cores")
+  bf16 *enc_w2p = nullptr, *enc_w2pT = nullptr, *enc_w3p = nullptr, *enc_w3pT = nullptr, *enc_wlT16 = nullptr;
+  float* enc_b2p = nullptr;
+  bool enc_simt = false;      // SPDM_ENC_SIMT=1: CUDA-core encoder on the bf16 path too (A/B switch)
   bool wgrad_simt = false;    // SPDM_WGRAD_SIMT=1: CUDA-core weight gradients on the bf16 path too (A/B switch)
 };
 
@@ -373,6 +377,13 @@ extern "C" int spdm_train_enable(spdm_plan* p) {
   if (p->G > 0) tr->film_wT = p->alloc<float>((size_t)SPDM_FILM_WIDTH * p->G);
   tr->enc_wlT = p->alloc<float>((size_t)128 * 9216);
   tr->loss_dev = p->alloc<float>(1);
+  if (const char* e = getenv("SPDM_ENC_SIMT")) tr->enc_simt = atoi(e) != 0;
+  if (p->bf16_mode && !tr->enc_simt) {
+    tr->enc_w2p = p->alloc<bf16>(64 * 64); tr->enc_w2pT = p->alloc<bf16>(64 * 64);
+    tr->enc_w3p = p->alloc<bf16>(64 * 256); tr->enc_w3pT = p->alloc<bf16>(256 * 64);
+    tr->enc_wlT16 = p->alloc<bf16>((size_t)9216 * 128);
+    tr->enc_b2p = p->alloc<float>(64);
+  }
   // every weight has to be uploaded again so that the twins are filled
   for (auto& kv : p->loaders) {
     if (kv.first.rfind("vision_encoder.", 0) == 0) p->missing_enc.insert(kv.first);
@@ -412,6 +423,17 @@ extern "C" int spdm_train_sync_weights(spdm_plan* p, void* stream) {
     p->missing_unet.erase(kv.first);
     p->missing_enc.erase(kv.first);
   }
+  if (p->tr->enc_w2p) {
+    auto P = [&](const char* n) {
+      auto it = p->tr->bind.find(n);
+      REQUIRE(it != p->tr->bind.end(), "training: parameter '%s' is not bound", n);
+      return p->tr->params + it->second.off;
+    };
+    TrainState* tr = p->tr;
+    launch_enc_pack_tc(P("vision_encoder.2.weight"), P("vision_encoder.2.bias"), P("vision_encoder.4.weight"), tr->enc_w2p, tr->enc_w2pT,
+                       tr->enc_w3p, tr->enc_w3pT, tr->enc_b2p, (cudaStream_t)stream);
+    launch_enc_pack_linear_T16(P("vision_encoder.7.weight"), tr->enc_wlT16, (cudaStream_t)stream);
+  }
   p->temb_table_dirty = true;
   check_async("train_sync_weights");
   return 0;
@@ -445,10 +467,38 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
   launch_add_noise(x0, noise, reinterpret_cast<const long long*>(t), sqrt_ab, sqrt_1mab, p->cfg.inpaint_rows > 0 ? inpaint : nullptr, x_noisy,
                    p->n_elems(), p->cfg.inpaint_rows * p->cfg.dim, B, s);
   // ---- conditioning: encoder -> obs_cond -> Mish -> the six FiLM Linears (ddpm:317-330, Unet_FiLmLayer.py:149-154) ----
-  float* feat = F((size_t)n_frames * 9216);
+  const bool enc_tc = tr->enc_w2p != nullptr;
+  const long long n_pad = ((long long)n_frames + 127) / 128 * 128, M2 = (long long)n_frames * 576, M3 = (long long)n_frames * 144;
+  auto H16 = [&](size_t n) { return reinterpret_cast<bf16*>(arena_alloc(p, n * sizeof(bf16))); };
+  // flat tensor-core GEMM (taps = 1) on `rows` rows: out = epi(in @ w^T)
+  auto tc_flat = [&](const char* tag, const bf16* in, int ld_in, const bf16* w, int Cin, int Cout, long long rows, bf16* out, int ld_out,
+                     const float* bias, int flags) {
+    char key[96];
+    snprintf(key, sizeof key, "enc|%s|%p|%lld", tag, (const void*)in, rows);
+    TcGemm*& g = p->tc_cache[key];
+    if (!g) {
+      g = tc_gemm_create(in, ld_in, w, Cin, Cout, 1, 1, 1, (int)rows);
+      REQUIRE(g != nullptr, "encoder GEMM %s: %s", tag, tc_last_error());
+    }
+    tc_gemm_launch(g, out, ld_out, nullptr, bias, nullptr, 0, flags, (int)rows, s);
+  };
+  float* feat = nullptr;
   float* enc_out = F((size_t)n_frames * 128);
-  launch_enc_convs<float>(images, p->enc_w1, p->enc_b1, p->enc_w2, p->enc_b2, p->enc_w3, p->enc_b3, feat, n_frames, s);
-  {
+  bf16 *c1p = nullptr, *c2 = nullptr, *feat16 = nullptr;
+  if (enc_tc) {
+    REQUIRE(n_frames % 8 == 0, "bf16 training: B * obs_horizon (%d) must be a multiple of 8", n_frames);
+    c1p = H16((size_t)M2 * 64);
+    c2 = H16((size_t)M2 * 64);
+    feat16 = H16((size_t)n_pad * 9216);
+    bf16* enc_out16 = H16((size_t)n_pad * 128);
+    launch_enc_conv1_fwd(images, p->enc_w1, p->enc_b1, c1p, n_frames, s);
+    tc_flat("conv2", c1p, 64, tr->enc_w2p, 64, 64, M2, c2, 64, tr->enc_b2p, EPI_BIAS | EPI_RELU);
+    tc_flat("conv3", c2, 256, tr->enc_w3p, 256, 64, M3, feat16, 64, p->enc_b3, EPI_BIAS | EPI_RELU);
+    tc_flat("linear", feat16, 9216, p->enc_wl16, 9216, 128, n_pad, enc_out16, 128, p->enc_bl, EPI_BIAS);
+    launch_cast_f32(enc_out16, enc_out, (long long)n_frames * 128, s);
+  } else {
+    feat = F((size_t)n_frames * 9216);
+    launch_enc_convs<float>(images, p->enc_w1, p->enc_b1, p->enc_w2, p->enc_b2, p->enc_w3, p->enc_b3, feat, n_frames, s);
     GemmSimtArgs a{};
     a.in = feat; a.w = p->enc_wl; a.bias = p->enc_bl; a.out = enc_out; a.M = n_frames; a.Cin = 9216; a.Cout = 128;
     a.ld_in = 9216; a.ld_out = 128; a.H = 1; a.W = 1; a.taps = 1; a.act = ACT_NONE;
@@ -497,6 +547,35 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
   launch_mish_bwd(d_cond_mish, p->cond, d_cond, (long long)B * p->G, s);
   float* d_enc_out = F((size_t)n_frames * 128);
   launch_gather_feat_grad(d_cond, d_enc_out, B, T, p->cfg.cond_dim, s);
+  if (enc_tc) {
+    auto wg = [&](const bf16* x, int ld_x, const bf16* dy, int ld_dy, long long M, int Cin, int Cout, float* dst) {
+      const int rc = wgrad_tc_launch(x, ld_x, dy, ld_dy, M, Cin, Cout, 1, 1, 1, dst, s);
+      REQUIRE(rc == 0, "encoder wgrad: %s", wgrad_tc_last_error());
+    };
+    bf16* d_eo16 = H16((size_t)n_pad * 128);
+    launch_cast_bf16(d_enc_out, d_eo16, (long long)n_frames * 128, s);
+    float* tmp = F((size_t)128 * 9216 + 64 * 256 + 64 * 64 + 64);  // hwc-ordered Linear grad | padded conv3 | padded conv2 | padded b2
+    float *g3 = tmp + (size_t)128 * 9216, *g2 = g3 + 64 * 256, *gb2 = g2 + 64 * 64;
+    CUDA_OK(cudaMemsetAsync(tmp, 0, ((size_t)128 * 9216 + 64 * 256 + 64 * 64 + 64) * sizeof(float), s));
+    wg(feat16, 9216, d_eo16, 128, n_pad, 9216, 128, tmp);
+    launch_enc_linear_grad_permute(tmp, G("vision_encoder.7.weight"), s);
+    launch_colsum<float>(d_enc_out, 128, n_frames, 128, G("vision_encoder.7.bias"), s);
+    bf16* d3 = H16((size_t)n_pad * 9216);   // d feat, then masked in place = gradient of the pre-ReLU conv3 output [M3][64]
+    tc_flat("d_feat", d_eo16, 128, tr->enc_wlT16, 128, 9216, n_pad, d3, 9216, nullptr, 0);
+    launch_relu_mask(d3, feat16, d3, M3 * 64, s);
+    wg(c2, 256, d3, 64, M3, 256, 64, g3);
+    launch_colsum<bf16>(d3, 64, M3, 64, G("vision_encoder.4.bias"), s);
+    bf16* d2 = H16((size_t)M2 * 64);        // [M3][256] == [M2][64]
+    tc_flat("d_c2", d3, 64, tr->enc_w3pT, 64, 256, M3, d2, 256, nullptr, 0);
+    launch_relu_mask(d2, c2, d2, M2 * 64, s);
+    wg(c1p, 64, d2, 64, M2, 64, 64, g2);
+    launch_colsum<bf16>(d2, 64, M2, 64, gb2, s);
+    bf16* d1 = H16((size_t)M2 * 64);
+    tc_flat("d_c1", d2, 64, tr->enc_w2pT, 64, 64, M2, d1, 64, nullptr, 0);
+    launch_relu_mask(d1, c1p, d1, M2 * 64, s);
+    launch_enc_conv1_wgrad(images, d1, G("vision_encoder.0.weight"), G("vision_encoder.0.bias"), n_frames, s);
+    launch_enc_unpack_grads(g2, g3, gb2, G("vision_encoder.2.weight"), G("vision_encoder.2.bias"), G("vision_encoder.4.weight"), s);
+  } else {
   {  // Linear(9216 -> 128): weight gradient in the kernel's hwc column order first, then permuted into (128, 9216 chw)
     float* tmp = F((size_t)128 * 9216);
     CUDA_OK(cudaMemsetAsync(tmp, 0, (size_t)128 * 9216 * sizeof(float), s));
@@ -516,6 +595,7 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
   launch_enc_convs_bwd(images, p->enc_w1, p->enc_b1, p->enc_w2, p->enc_b2, p->enc_w3, feat, d_feat, G("vision_encoder.0.weight"),
                        G("vision_encoder.0.bias"), G("vision_encoder.2.weight"), G("vision_encoder.2.bias"), G("vision_encoder.4.weight"),
                        G("vision_encoder.4.bias"), n_frames, s);
+  }
   CUDA_OK(cudaMemcpyAsync(loss_out, tr->loss_dev, sizeof(float), cudaMemcpyDeviceToDevice, s));
   p->launches += total_launches() - before;
   check_async("train_fwd_bwd");
