@@ -64,6 +64,19 @@ except Exception:  # pragma: no cover - depends on the environment
             return model
 
 
+class _NativeLoss(torch.autograd.Function):
+    """The loss returned by a native training step: its gradients already sit in the parameters' `.grad` (written by
+    spdm_train_fwd_bwd), so `loss.backward()` — which Lightning / user loops call — has nothing left to do."""
+
+    @staticmethod
+    def forward(ctx, loss, anchor):
+        return loss.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return None, None
+
+
 class VisionEncoder(nn.Sequential):
     """Parameters of Autoencoder.encoder (models/encoder/autoencoder.py:11-20); state_dict keys 0,2,4,7."""
 
@@ -184,9 +197,92 @@ class Diffusion_DDPM(_Base):
         scheduler = torch.optim.lr_scheduler.ReduceLROnPlateau(optimizer, 'min', patience=5)
         return {"optimizer": optimizer, "lr_scheduler": {"scheduler": scheduler, "monitor": "val_loss", "frequency": 1}}
 
+    # ------------------------------------------------------------------------------------------
+    # native training step: forward + backward + optimizer in libspdm (ddpm:115-173, train.py:104-107)
+    # ------------------------------------------------------------------------------------------
+    def named_trainable(self):
+        """Every tensor the reference hands to Adam (`self.parameters()`: U-Net and vision encoder), under libspdm names."""
+        named = {k: p for k, p in self.noise_estimator.named_parameters()}
+        named.update({"vision_encoder." + k: p for k, p in self.vision_encoder.named_parameters()})
+        return named
+
+    def _training_plan(self, B):
+        from .engine import DenoisePlan
+        plan = getattr(self, "_tplan", None)
+        key = (self.precision, self.pred_horizon + self.inpaint_horizon, self.prediction_dim, self.obs_horizon, self.observation_dim,
+               self.inpaint_horizon, str(self.device))
+        if plan is None or self._tplan_key != key or plan.batch_max < B:
+            named = self.named_trainable()
+            if plan is not None:  # keep the current values: they live in the old plan's flat buffer
+                named = {k: p.detach().clone() for k, p in named.items()}
+                plan.close()
+            ne = self.noise_estimator
+            plan = DenoisePlan(attention=ne._attention, precision=self.precision, batch_max=max(int(B), self.batch_max),
+                               rows=self.pred_horizon + self.inpaint_horizon, dim=self.prediction_dim, obs_horizon=self.obs_horizon,
+                               cond_dim=self.observation_dim, inpaint_rows=self.inpaint_horizon, time_dim=ne.time_dim, device=self.device)
+            plan.enable_training(named)
+            # nn.Parameters now alias the plan's flat fp32 buffers: any torch optimizer / all-reduce works on them unchanged
+            for k, p in self.named_trainable().items():
+                p.data = plan.param_view(k)
+                p.grad = plan.grad_view(k)
+            self._tplan, self._tplan_key = plan, key
+            self._tplan_versions = None
+        return plan
+
+    def _param_versions(self):
+        return tuple(p._version for p in self.parameters())
+
+    def _native_training_step(self, batch, t=None, noise=None):
+        observation_batch = self.prepare_observation_batch(batch)
+        prediction_batch = self.prepare_prediction_batch(batch)
+        B = observation_batch['position'].shape[0]
+        plan = self._training_plan(B)
+        if self._tplan_versions != self._param_versions():  # a torch optimizer (or load_state_dict) changed the weights
+            plan.sync_weights()
+            self._weights_changed()
+        x_0 = self.prepare_prediction_vectors(prediction_batch).unsqueeze(1)
+        x_0_inpaint = self.prepare_inpaint_vectors(observation_batch).unsqueeze(1)
+        if t is None:
+            t = torch.randint(0, self.noise_steps, (B,), device=self.device).long()
+        prediction_vector = torch.cat([x_0_inpaint, x_0], dim=2)
+        if noise is None:
+            noise = torch.randn_like(prediction_vector)
+        ac = self.noise_scheduler.alphas_cumprod
+        loss = plan.train_fwd_bwd(observation_batch['image'], observation_batch['position'], observation_batch['action'],
+                                  observation_batch['velocity'], prediction_vector, noise, t, ac ** 0.5, (1 - ac) ** 0.5,
+                                  inpaint=x_0_inpaint.reshape(B, -1) if self.inpaint_horizon > 0 else None)
+        anchor = None
+        for k, p in self.named_trainable().items():  # optimizer.zero_grad(set_to_none=True) drops the aliases: restore them
+            if p.grad is None or p.grad.data_ptr() != plan.grad_view(k).data_ptr():
+                p.grad = plan.grad_view(k)
+            anchor = p
+        self._tplan_versions = self._param_versions()
+        return _NativeLoss.apply(loss.reshape(()), anchor)
+
+    def _weights_changed(self):
+        self.noise_estimator._weights_epoch += 1
+        self._enc_tag = None
+
+    def allreduce_gradients(self, group=None):
+        """Data-parallel training: one NCCL all-reduce (sum) over the flat gradient buffer.  Returns the factor
+        (1 / world_size) that `optimizer_step` folds into the update."""
+        from .distributed import allreduce_sum_
+        return allreduce_sum_(self._tplan.grads_flat, group=group)
+
+    def optimizer_step(self, lr=None, betas=(0.9, 0.999), eps=1e-8, gradient_clip_val=0.5, grad_scale=1.0):
+        """Fused clip_grad_norm_(gradient_clip_val) + Adam over all parameters (one kernel pair on the flat buffers);
+        equivalent to `clip_grad_norm_` + `configure_optimizers()['optimizer'].step()` of the reference."""
+        plan = self._tplan
+        plan.adam_step(lr=self.lr if lr is None else lr, betas=betas, eps=eps, max_norm=gradient_clip_val, grad_scale=grad_scale)
+        self._weights_changed()
+        self._tplan_versions = self._param_versions()
+
     def process_single_batch(self, batch, t=None, noise=None):
-        """ddpm:128-173 — q-sample + inpaint + U-Net + MSE.  Forward only in this round (loss value, no autograd graph);
+        """ddpm:128-173 — q-sample + inpaint + U-Net + MSE.  In training mode with autograd enabled the whole step
+        (forward, loss, backward) runs in libspdm and the parameter gradients are left in `.grad`; otherwise forward only.
         `t` / `noise` may be injected for parity runs."""
+        if self.training and torch.is_grad_enabled():
+            return self._native_training_step(batch, t=t, noise=noise)
         observation_batch = self.prepare_observation_batch(batch)
         prediction_batch = self.prepare_prediction_batch(batch)
         B = observation_batch['position'].shape[0]

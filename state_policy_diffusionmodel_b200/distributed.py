@@ -52,3 +52,28 @@ def sharded_sample(sample_fn, batch, group=None, **kw):
         tail = tuple(ref.shape[1:]) if ref is not None else ()
         out = torch.zeros((0,) + tail, device=next(iter(batch.values())).device)
     return gather_rows(out, total, group)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Data-parallel training: replicas, per-GPU batch, ONE all-reduce over the flat gradient buffer.
+# ---------------------------------------------------------------------------------------------------
+def allreduce_sum_(flat, group=None, buckets=1):
+    """In-place summing all-reduce of a flat gradient buffer, optionally in `buckets` contiguous pieces (each piece is
+    an independent collective, so a caller can launch them as the backward pass retires them).  Returns 1/world_size,
+    the factor the optimizer folds into the update (clip_grad_norm_ and Adam then see the mean gradient)."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    world = dist.get_world_size(group)
+    n = flat.numel()
+    buckets = max(1, min(int(buckets), n))
+    step = (n + buckets - 1) // buckets
+    for lo in range(0, n, step):
+        dist.all_reduce(flat[lo:lo + step], op=dist.ReduceOp.SUM, group=group)
+    return 1.0 / world
+
+
+def broadcast_params_(flat, src=0, group=None):
+    """Replicas start from rank `src`'s weights (what DDP does at construction)."""
+    if dist.is_available() and dist.is_initialized():
+        dist.broadcast(flat, src=src, group=group)
+    return flat

@@ -100,6 +100,7 @@ class _UNetBase(nn.Module):
         self._plan = None
         self._plan_key = None
         self._weights_tag = None
+        self._weights_epoch = 0   # bumped when the weights change behind torch's back (fused native optimizer step)
 
     # ----------------------------------------------------------------------------------------
     def configure(self, precision=None, batch_max=None):
@@ -117,7 +118,7 @@ class _UNetBase(nn.Module):
         return torch.cat([a, b], dim=-1)
 
     def _tag(self):
-        return tuple((p.data_ptr(), p._version) for p in self.parameters())
+        return (self._weights_epoch,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
     def plan_for(self, B, rows, dim, obs_horizon=None, cond_dim=None, inpaint_rows=None, graph_steps=None):
         """Returns a DenoisePlan able to run B samples of rows x dim, (re)building it and (re)loading weights when
@@ -163,7 +164,9 @@ class _UNetBase(nn.Module):
     def forward(self, x, t, y=None):
         """x (B,1,rows,dim); t (B,) or (1,) integer timesteps; y (B,1,T_obs,cond_dim) or None -> (B,1,rows,dim)."""
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("spdm: backward kernels are not built yet — call under torch.no_grad() / .eval()")
+            raise NotImplementedError("spdm: the U-Net module alone has no autograd graph — the training step (forward + "
+                                      "backward + optimizer) is Diffusion_DDPM.training_step / process_single_batch; "
+                                      "call this forward under torch.no_grad() / .eval()")
         if not x.is_cuda:
             raise RuntimeError("spdm U-Net: input is on the CPU (no CPU fallback)")
         B, _, rows, dim = x.shape

@@ -174,3 +174,35 @@ def _gloo_worker(rank, world, port, total):
 def test_sharded_sampling_world2_gloo(total):
     port = 29500 + (os.getpid() + total) % 2000
     mp.spawn(_gloo_worker, args=(2, port, total), nprocs=2, join=True)
+
+
+def _gloo_train_worker(rank, world, port):
+    """Data-parallel training host logic on CPU tensors: per-rank gradients of per-rank shards, one summing all-reduce over
+    the flat buffer (in buckets), 1/world folded into the clip + Adam restatement == the single-process full-batch update."""
+    import torch.distributed as dist
+    from oracle import train_ref
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(3)
+    n = 1001
+    w0 = torch.randn(n, generator=g)
+    X = torch.randn((8, n), generator=g)  # 8 samples, loss = mean_b 0.5 * (x_b . w)^2
+    full_grad = ((X @ w0)[:, None] * X).mean(0)
+    lo, hi = distributed.shard_range(8, rank, world)
+    local_grad = ((X[lo:hi] @ w0)[:, None] * X[lo:hi]).mean(0)  # mean over the LOCAL batch, like each replica's loss
+    flat = local_grad.clone()
+    params = w0.clone()
+    distributed.broadcast_params_(params, src=0)
+    scale = distributed.allreduce_sum_(flat, buckets=3)
+    assert scale == 1.0 / world
+    torch.testing.assert_close(flat * scale, full_grad, rtol=1e-5, atol=1e-6)
+    total, clipped = train_ref.clip_grad_norm({"w": flat * scale}, 0.5)
+    new_p, _, _ = train_ref.adam_step({"w": params}, clipped, {"w": torch.zeros(n)}, {"w": torch.zeros(n)}, 1)
+    total1, clipped1 = train_ref.clip_grad_norm({"w": full_grad}, 0.5)
+    want_p, _, _ = train_ref.adam_step({"w": w0}, clipped1, {"w": torch.zeros(n)}, {"w": torch.zeros(n)}, 1)
+    torch.testing.assert_close(new_p["w"], want_p["w"], rtol=1e-5, atol=1e-7)
+    dist.destroy_process_group()
+
+
+def test_data_parallel_training_world2_gloo():
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_gloo_train_worker, args=(2, port), nprocs=2, join=True)
