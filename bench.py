@@ -48,6 +48,10 @@ def parse():
     ap.add_argument("--split", type=int, default=1, help="concurrent sub-batches per denoising step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="one sampling call, for ncu")
+    ap.add_argument("--workload", default="sample", choices=["sample", "train"],
+                    help="sample: BASELINE configs[1] (headline); train: configs[2], training step of the attention U-Net + encoder")
+    ap.add_argument("--train-batch", type=int, default=512, help="training samples per GPU (configs[2])")
+    ap.add_argument("--no-train", action="store_true", help="skip the short training-step measurement appended to the sampling line")
     ap.add_argument("--pipeline-depth", type=int, default=2,
                     help="extra measurement: independent batches kept in flight on separate streams/plans (reported separately)")
     return ap.parse_args()
@@ -179,6 +183,79 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+# nominal FLOPs of one training step per sample: U-Net fwd+bwd + 3 x the conditioning encode
+FLOP_TRAIN_ATTN, FLOP_TRAIN_NOATTN = 2464.6e6 + 240e6, 2262.1e6 + 240e6
+
+
+def bench_train(args, dev, world, rank, steps, warmup):
+    """BASELINE configs[2]: one optimizer step of Diffusion_DDPM (attention FiLM U-Net + vision encoder), bf16, per-GPU batch
+    512, data-parallel replicas: spdm_train_fwd_bwd, one NCCL all-reduce over the flat gradient buffer (N > 1), fused
+    clip_grad_norm_(0.5) + Adam, weight re-upload.  Inputs resident in HBM; t and the noise are drawn on the device each
+    step, as the reference does (ddpm:158-161)."""
+    import torch
+    import torch.distributed as dist
+    import state_policy_diffusionmodel_b200 as spdm
+    from state_policy_diffusionmodel_b200.distributed import broadcast_params_
+    attention = args.variant == "attn"
+    B = args.train_batch
+    torch.manual_seed(0)
+    model = spdm.Diffusion_DDPM(noise_steps=1000, obs_horizon=10, pred_horizon=args.rows - 1, observation_dim=135, prediction_dim=args.dim,
+                                model="UNet_Film" if attention else "UNet_FilmnoAttention", inpaint_horizon=1).to(dev).train()
+    model.configure(precision=args.precision, batch_max=B)
+    g = torch.Generator(device=dev).manual_seed(4321 + rank)
+    T = 10 + args.rows - 1
+    batch = {"image": torch.rand((B, T, 3, 96, 96), device=dev, generator=g),
+             "position": torch.cumsum(0.02 * torch.randn((B, T, 2), device=dev, generator=g), dim=1),
+             "velocity": 2 * torch.rand((B, T, 2), device=dev, generator=g) - 1,
+             "action": 2 * torch.rand((B, T, 3), device=dev, generator=g) - 1}
+    losses = []
+
+    def step(i):
+        loss = model.training_step(batch, i)
+        scale = model.allreduce_gradients() if world > 1 else 1.0
+        model.optimizer_step(gradient_clip_val=0.5, grad_scale=scale)
+        losses.append(loss.detach())
+
+    step(0)
+    if world > 1:
+        broadcast_params_(model._tplan.params_flat)
+        model._tplan.sync_weights()
+    for i in range(max(warmup, 3)):
+        step(i)
+    l0 = model._tplan.launch_count
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item()) / steps
+    value = B * world / (ms / 1000.0)
+    flop = FLOP_TRAIN_ATTN if attention else FLOP_TRAIN_NOATTN
+    pk = peaks()
+    res = {"metric": "train samples/s", "value": round(value, 1), "unit": "samples/s", "ms_per_step": round(ms, 3), "per_gpu_batch": B,
+           "global_batch": B * world, "precision": args.precision,
+           "workload": "training step: %s + vision encoder, fwd + bwd + clip + Adam%s" % (
+               "UNet_Film (attention)" if attention else "UNet_Film_noAttention", ", NCCL all-reduce of 26.0 M fp32 grads" if world > 1 else ""),
+           "gpu_launches_per_step": int((model._tplan.launch_count - l0) // steps),
+           "nominal_tflops_per_gpu": round(value / world * flop / 1e12, 1),
+           "frac_of_sustained_bf16_peak": round(value / world * flop / 1e12 / pk["tf_sust"], 4),
+           "loss_first_last": [round(float(losses[0]), 4), round(float(losses[-1]), 4)],
+           "workspace_mb": round(model._tplan.workspace_bytes / 1e6)}
+    model._tplan.close()
+    del model, batch
+    torch.cuda.empty_cache()
+    return res
+
+
 def config_dict(args, total_B):
     return {"workload": "%s-%d sampling, %s, pred 31x5 (rows=%d), obs 10x(96x96x3 + pos/vel/act), random-init weights" % (
                 args.sampler.upper(), args.ddim_steps, "UNet_Film (attention)" if args.variant == "attn" else "UNet_Film_noAttention", args.rows) + ("" if args.dim == 5 else ", prediction_dim=%d" % args.dim),
@@ -249,6 +326,17 @@ def main():
         for i in range(2):
             step_device(i)
         torch.cuda.synchronize()
+        return
+    if args.workload == "train":
+        res = bench_train(args, dev, world, rank, args.steps, args.warmup)
+        res.update({"n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "higher_is_better": True, "scaling": "weak",
+                    "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                    "config": {"workload": res.pop("workload"), "global_batch": res["global_batch"], "per_gpu_batch": res["per_gpu_batch"],
+                               "parallelism": "data-parallel x%d, one gradient all-reduce per step" % world}})
+        if rank == 0:
+            print(json.dumps(res), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
         return
 
     def barrier():
@@ -378,6 +466,11 @@ def main():
                                   "per_denoise_step": round(ms_loop / args.steps / K, 4)},
             "pipelined": pipelined}
 
+    if not args.no_train:
+        try:
+            line["train"] = bench_train(args, dev, world, rank, max(args.steps, 5), 3)
+        except Exception as e:  # the sampling line is the headline; a training failure must not hide it
+            line["train"] = {"error": str(e)[:300]}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         rate, cores, sample = cpu_oracle_rate(model.noise_estimator.state_dict(), model.vision_encoder.state_dict(), args,
                                               budget_s=12.0, b_cpu=32)

@@ -3,6 +3,7 @@
 // bilinear-upsample backward, LayerNorm and attention-core backward, the MSE loss + outc backward, the fp32 weight-
 // gradient GEMM of the parity path, the vision-encoder backward and fused clip + Adam.
 // Reference lines are cited per kernel (paths relative to the reference repo root).
+#include <cooperative_groups.h>
 #include <math.h>
 
 #include "train.cuh"
@@ -161,8 +162,218 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(GnBwdArgs a) {
     store8(dx + ((size_t)b * a.HW + row) * a.ld_dx + c8, x);
   }
 }
+
+// Register-cached variant (every shape of the U-Net): a cluster of CS CTAs owns one sample (CS = 1 up to 2048 8-channel
+// vectors, else 2/4/8), each thread keeps its <= 4 vectors of (g = d out/d gn * gamma, xhat) in registers between the
+// reduction pass and the dx pass, so dy / raw are read once and gelu' is evaluated once.  The two per-sample sums cross the
+// cluster through distributed shared memory; per-channel sums go out as atomics.
+template <typename T, int VPT>
+__global__ void __launch_bounds__(512) gn_bwd_cached_kernel(GnBwdArgs a, int CS) {
+  namespace cg = cooperative_groups;
+  extern __shared__ float red[];       // [threads][8]
+  __shared__ float wsum[2][16];
+  __shared__ float cta_part[2];
+  const int b = blockIdx.x / CS, part = blockIdx.x - b * CS;
+  const int tid = threadIdx.x, nthreads = blockDim.x;
+  double s = 0.0, q = 0.0;
+  for (int p = 0; p < a.P; ++p) {
+    const float2 sq = __ldg(reinterpret_cast<const float2*>(a.stats) + (size_t)b * a.P + p);
+    s += (double)sq.x;
+    q += (double)sq.y;
+  }
+  const double n = (double)a.HW * (double)a.C;
+  const double dmean = s / n;
+  double var = q / n - dmean * dmean;
+  if (var < 0.0) var = 0.0;
+  const float mean = (float)dmean;
+  const float rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+  const T* __restrict__ dy = reinterpret_cast<const T*>(a.dy);
+  const T* __restrict__ raw = reinterpret_cast<const T*>(a.raw);
+  T* __restrict__ dx = reinterpret_cast<T*>(a.dx);
+  const int vpr = a.C >> 3;            // divides nthreads
+  const int c8 = (tid % vpr) << 3;
+  const int row_step = nthreads / vpr;
+  const int row0 = part * (a.HW / CS) + tid / vpr;
+  float g[8], be[8], te[8], fs[8];
+  load8(a.gamma + c8, g);
+  load8(a.beta + c8, be);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { te[i] = 0.f; fs[i] = 1.f; }
+  const bool has_film = a.film != nullptr, has_temb = a.temb != nullptr;
+  if (has_temb) load8(a.temb + (size_t)b * SPDM_TEMB_WIDTH + a.temb_off + c8, te);
+  if (has_film) load8(a.film + (size_t)b * SPDM_FILM_WIDTH + a.film_off + c8, fs);
+  float gg[VPT][8], xh[VPT][8];
+  float acc_dg[8], acc_db[8], acc_fb[8], acc_fs[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { acc_dg[i] = 0.f; acc_db[i] = 0.f; acc_fb[i] = 0.f; acc_fs[i] = 0.f; }
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int row = row0 + k * row_step;
+    float d[8], x[8];
+    load8(dy + ((size_t)b * a.HW + row) * a.ld_dy + c8, d);
+    load8(raw + ((size_t)b * a.HW + row) * a.ld_raw + c8, x);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float xhv = (x[i] - mean) * rstd;
+      const float u = xhv * g[i] + be[i];
+      float go = d[i];
+      if (has_film) { acc_fb[i] += d[i]; acc_fs[i] = fmaf(d[i], u + te[i], acc_fs[i]); go = d[i] * fs[i]; }
+      else if (has_temb) acc_fb[i] += d[i];
+      if (a.act == ACT_GELU) go *= gelu_grad(u);
+      acc_dg[i] = fmaf(go, xhv, acc_dg[i]);
+      acc_db[i] += go;
+      const float gv = go * g[i];
+      s1 += gv;
+      s2 = fmaf(gv, xhv, s2);
+      gg[k][i] = gv;
+      xh[k][i] = xhv;
+    }
+  }
+  // per-sample sums: warp -> CTA -> cluster
+  s1 = warp_sum(s1);
+  s2 = warp_sum(s2);
+  if ((tid & 31) == 0) { wsum[0][tid >> 5] = s1; wsum[1][tid >> 5] = s2; }
+  __syncthreads();
+  float t1 = 0.f, t2 = 0.f;
+  for (int i = 0; i < (nthreads >> 5); ++i) { t1 += wsum[0][i]; t2 += wsum[1][i]; }
+  if (CS > 1) {
+    cg::cluster_group cluster = cg::this_cluster();
+    if (tid == 0) { cta_part[0] = t1; cta_part[1] = t2; }
+    cluster.sync();
+    t1 = 0.f; t2 = 0.f;
+    for (int r = 0; r < CS; ++r) {
+      const float* peer = cluster.map_shared_rank(cta_part, r);
+      t1 += peer[0];
+      t2 += peer[1];
+    }
+    cluster.sync();  // nobody leaves (or reuses cta_part) while a peer may still be reading it
+  }
+  const float inv_n = 1.0f / ((float)a.HW * (float)a.C);
+  const float m1 = t1 * inv_n, m2 = t2 * inv_n;
+#pragma unroll
+  for (int k = 0; k < VPT; ++k) {
+    const int row = row0 + k * row_step;
+    float o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i] = rstd * (gg[k][i] - m1 - xh[k][i] * m2);
+    store8(dx + ((size_t)b * a.HW + row) * a.ld_dx + c8, o);
+  }
+  // per-channel sums: tree over the row groups (threads tid and tid + stride share their channels when vpr | stride)
+  auto reduce_channels = [&](const float (&acc)[8], float (&out)[8]) {
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) red[tid * 8 + i] = acc[i];
+    __syncthreads();
+    for (int stride = nthreads >> 1; stride >= vpr; stride >>= 1) {
+      if (tid < stride) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) red[tid * 8 + i] += red[(tid + stride) * 8 + i];
+      }
+      __syncthreads();
+    }
+    if (tid < vpr) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) out[i] = red[tid * 8 + i];
+    }
+  };
+  float tot[8];
+  const bool use_part = a.part != nullptr && CS == 1;
+  reduce_channels(acc_dg, tot);
+  if (tid < vpr) {
+    if (use_part) store8(a.part + (size_t)b * 2 * a.C + c8, tot);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(a.dgamma + c8 + i, tot[i]);
+    }
+  }
+  reduce_channels(acc_db, tot);
+  if (tid < vpr) {
+    if (use_part) store8(a.part + (size_t)b * 2 * a.C + a.C + c8, tot);
+    else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) atomicAdd(a.dbeta + c8 + i, tot[i]);
+    }
+  }
+  if (has_film || has_temb) {   // per-sample outputs: accumulated too (the step zeroes d_film / d_temb), CS CTAs contribute
+    reduce_channels(acc_fb, tot);
+    if (tid < vpr) {
+      if (has_film) {
+        float* dst = a.d_film + (size_t)b * SPDM_FILM_WIDTH + a.film_off + a.C + c8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(dst + i, tot[i]);
+      }
+      if (has_temb) {
+        float* dst = a.d_temb + (size_t)b * SPDM_TEMB_WIDTH + a.temb_off + c8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(dst + i, tot[i] * fs[i]);
+      }
+    }
+    if (has_film) {
+      reduce_channels(acc_fs, tot);
+      if (tid < vpr) {
+        float* dst = a.d_film + (size_t)b * SPDM_FILM_WIDTH + a.film_off + c8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) atomicAdd(dst + i, tot[i]);
+      }
+    }
+  }
+}
+
+template <typename T, int VPT> void launch_gn_cached(const GnBwdArgs& a, int B, int CS, int threads, cudaStream_t s) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(B * CS);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = (size_t)threads * 8 * sizeof(float);
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CS;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, gn_bwd_cached_kernel<T, VPT>, a, CS);
+}
+// d gamma[c] += sum_b part[b][c], d beta[c] += sum_b part[b][C + c]: 32 columns per block, 8 row groups
+__global__ void __launch_bounds__(256) gn_part_finalize_kernel(const float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                               int B, int C) {
+  __shared__ float sm[8][32];
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), rg = threadIdx.x >> 5;
+  float acc = 0.f;
+  if (col < 2 * C)
+    for (int b = rg; b < B; b += 8) acc += part[(size_t)b * 2 * C + col];
+  sm[rg][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (rg == 0 && col < 2 * C) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) t += sm[r][threadIdx.x];
+    if (col < C) atomicAdd(dgamma + col, t);
+    else atomicAdd(dbeta + col - C, t);
+  }
+}
 }  // namespace
+// NOTE: d_film / d_temb are ACCUMULATED by the cached kernel (zero them first) and overwritten by the fallback kernel.
 template <typename T> void launch_gn_bwd(const GnBwdArgs& a, int B, cudaStream_t s) {
+  const int nvec = a.HW * (a.C >> 3), vpr = a.C >> 3;
+  if ((nvec & (nvec - 1)) == 0 && nvec >= 64 && nvec <= 16384) {
+    const int CS = nvec > 2048 ? nvec / 2048 : 1;
+    const int nv = nvec / CS;
+    const int threads = nv < 512 ? nv : 512;
+    const int vpt = nv / threads;
+    if (threads % vpr == 0 && a.HW % CS == 0 && (a.HW / CS) * vpr == nv) {
+      if (vpt == 4) launch_gn_cached<T, 4>(a, B, CS, threads, s);
+      else if (vpt == 2) launch_gn_cached<T, 2>(a, B, CS, threads, s);
+      else launch_gn_cached<T, 1>(a, B, CS, threads, s);
+      COUNT_LAUNCH();
+      if (a.part && CS == 1) {
+        gn_part_finalize_kernel<<<cdiv(2 * a.C, 32), 256, 0, s>>>(a.part, a.dgamma, a.dbeta, B, a.C);
+        COUNT_LAUNCH();
+      }
+      return;
+    }
+  }
   gn_bwd_kernel<T><<<B, 256, 0, s>>>(a);
   COUNT_LAUNCH();
 }
@@ -400,60 +611,74 @@ template void launch_upsample_bwd<bf16>(const bf16*, int, bf16*, int, int, int, 
 // LayerNorm backward (models/Unet_FiLmLayer.py:51,53): one warp per token row, C <= 256.
 // =================================================================================================
 namespace {
-template <typename T>
+template <typename T, int LANES>  // LANES = C / 8 lanes per token row, 32 / LANES rows per warp (like layernorm_kernel)
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict__ dy, int ld_dy, const T* __restrict__ x, int ld_x,
                                                             const float* __restrict__ g, const T* __restrict__ add, int ld_add, T* __restrict__ dx,
-                                                            int ld_dx, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M, int C) {
-  __shared__ float sg[256], sb[256];
+                                                            int ld_dx, float* __restrict__ dgamma, float* __restrict__ dbeta, long long M) {
+  constexpr int C = LANES * 8, ROWS_PER_WARP = 32 / LANES;
+  __shared__ float sg[C], sb[C];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   for (int i = tid; i < C; i += 256) { sg[i] = 0.f; sb[i] = 0.f; }
   __syncthreads();
-  const int c0 = lane * 8;
-  const bool act = c0 < C;
-  float gg[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (act) load8(g + c0, gg);
+  const int sub = lane / LANES, l = lane % LANES;
+  const int c0 = l * 8;
+  float gg[8];
+  load8(g + c0, gg);
   float adg[8], adb[8];
 #pragma unroll
   for (int i = 0; i < 8; ++i) { adg[i] = 0.f; adb[i] = 0.f; }
-  const float inv_c = 1.0f / (float)C;
-  for (long long row = (long long)blockIdx.x * 8 + warp; row < M; row += (long long)gridDim.x * 8) {
+  constexpr float inv_c = 1.0f / (float)C;
+  const long long rows_per_block_iter = 8LL * ROWS_PER_WARP;
+  for (long long base = (long long)blockIdx.x * rows_per_block_iter; base < M; base += (long long)gridDim.x * rows_per_block_iter) {
+    const long long row = base + warp * ROWS_PER_WARP + sub;
+    const bool ok = row < M;
     float xv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (act) { load8(x + row * ld_x + c0, xv); load8(dy + row * ld_dy + c0, d); }
+    if (ok) { load8(x + row * ld_x + c0, xv); load8(dy + row * ld_dy + c0, d); }
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < 8; ++i) sum += xv[i];
-    const float mean = warp_sum(sum) * inv_c;
-    float qq = 0.f;
-    if (act) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { const float t = xv[i] - mean; qq = fmaf(t, t, qq); }
-    }
-    const float rstd = rsqrtf(warp_sum(qq) * inv_c + 1e-5f);
+    for (int o = LANES / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * inv_c;
+    float qq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { const float t = xv[i] - mean; qq = fmaf(t, t, qq); }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) qq += __shfl_xor_sync(0xffffffffu, qq, o);
+    const float rstd = rsqrtf(qq * inv_c + 1e-5f);
     float a1 = 0.f, a2 = 0.f, xh[8], dh[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      xh[i] = act ? (xv[i] - mean) * rstd : 0.f;
+      xh[i] = (xv[i] - mean) * rstd;
       dh[i] = d[i] * gg[i];
       a1 += dh[i];
       a2 = fmaf(dh[i], xh[i], a2);
-      adg[i] = fmaf(d[i], xh[i], adg[i]);
+      adg[i] = fmaf(d[i], xh[i], adg[i]);   // d == 0 for rows past M
       adb[i] += d[i];
     }
-    a1 = warp_sum(a1) * inv_c;
-    a2 = warp_sum(a2) * inv_c;
-    if (act) {
-      float o[8];
-      if (add) load8(add + row * ld_add + c0, o);
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) { a1 += __shfl_xor_sync(0xffffffffu, a1, o); a2 += __shfl_xor_sync(0xffffffffu, a2, o); }
+    a1 *= inv_c;
+    a2 *= inv_c;
+    if (ok) {
+      float o8[8];
+      if (add) load8(add + row * ld_add + c0, o8);
       else {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) o[i] = 0.f;
+        for (int i = 0; i < 8; ++i) o8[i] = 0.f;
       }
 #pragma unroll
-      for (int i = 0; i < 8; ++i) o[i] += rstd * (dh[i] - a1 - xh[i] * a2);
-      store8(dx + row * ld_dx + c0, o);
+      for (int i = 0; i < 8; ++i) o8[i] += rstd * (dh[i] - a1 - xh[i] * a2);
+      store8(dx + row * ld_dx + c0, o8);
     }
   }
-  if (act) {
+  // lanes with the same l inside a warp hold the same channels: fold them before touching shared memory
+#pragma unroll
+  for (int o = LANES; o < 32; o <<= 1) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { adg[i] += __shfl_xor_sync(0xffffffffu, adg[i], o); adb[i] += __shfl_xor_sync(0xffffffffu, adb[i], o); }
+  }
+  if (sub == 0) {
 #pragma unroll
     for (int i = 0; i < 8; ++i) { atomicAdd(&sg[c0 + i], adg[i]); atomicAdd(&sb[c0 + i], adb[i]); }
   }
@@ -464,9 +689,12 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const T* __restrict_
 template <typename T>
 void launch_layernorm_bwd(const T* dy, int ld_dy, const T* x, int ld_x, const float* g, const T* add, int ld_add, T* dx, int ld_dx,
                           float* dgamma, float* dbeta, long long M, int C, cudaStream_t s) {
-  int grid = cdiv(M, 8);
+  const int rows_per_iter = 8 * (256 / C);
+  int grid = cdiv(M, rows_per_iter);
   if (grid > 148 * 4) grid = 148 * 4;
-  layernorm_bwd_kernel<T><<<grid, 256, 0, s>>>(dy, ld_dy, x, ld_x, g, add, ld_add, dx, ld_dx, dgamma, dbeta, M, C);
+  if (C == 64) layernorm_bwd_kernel<T, 8><<<grid, 256, 0, s>>>(dy, ld_dy, x, ld_x, g, add, ld_add, dx, ld_dx, dgamma, dbeta, M);
+  else if (C == 128) layernorm_bwd_kernel<T, 16><<<grid, 256, 0, s>>>(dy, ld_dy, x, ld_x, g, add, ld_add, dx, ld_dx, dgamma, dbeta, M);
+  else layernorm_bwd_kernel<T, 32><<<grid, 256, 0, s>>>(dy, ld_dy, x, ld_x, g, add, ld_add, dx, ld_dx, dgamma, dbeta, M);
   COUNT_LAUNCH();
 }
 template void launch_layernorm_bwd<float>(const float*, int, const float*, int, const float*, const float*, int, float*, int, float*, float*,
@@ -1126,30 +1354,36 @@ void launch_adam(float* p, float* g, float* m, float* v, long long n, float lr, 
 // cores: conv1 (3 -> 16, K = 12), its weight gradient, the ReLU masks and the tiny weight (un)packs.
 // =================================================================================================
 namespace {
+// Stage the 8-row input strip of conv3 row r3 into shared memory as [3*8 rows][100]: image column j sits at index 4 + j
+// (16-byte aligned float4 copies), index 3 is the zero padding column -1, row 0 of strip 0 is the zero padding row -1.
+__device__ __forceinline__ void enc_stage_strip(const float* __restrict__ im, int r3, float* s_in, int tid) {
+  for (int i = tid; i < 24 * 24; i += 192) {
+    const int row = i / 24, q4 = i - row * 24;
+    const int c = row >> 3, r8 = row & 7;
+    const int gr = 8 * r3 - 1 + r8;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gr >= 0) v = __ldg(reinterpret_cast<const float4*>(im + ((size_t)c * 96 + gr) * 96) + q4);
+    *reinterpret_cast<float4*>(s_in + row * 100 + 4 + 4 * q4) = v;
+  }
+  if (tid < 24) s_in[tid * 100 + 3] = 0.f;
+}
+
 // one block per (frame, conv3 row r3): 192 conv1 pixels, one thread each, 16 channels per thread
 __global__ void __launch_bounds__(192) enc_conv1_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w1, const float* __restrict__ b1,
                                                             bf16* __restrict__ c1p) {
-  __shared__ float s_in[3 * 8 * 97];
+  __shared__ __align__(16) float s_in[24 * 100];
   __shared__ __align__(16) float w1s[12 * 16];
   __shared__ __align__(16) float b1s[16];
   const int tid = threadIdx.x;
   const int frame = blockIdx.x / 12, r3 = blockIdx.x % 12;
   const float* im = img + (size_t)frame * 3 * 96 * 96;
-  for (int e = tid; e < 12 * 16; e += 192) w1s[e] = __ldg(w1 + (e % 16) * 12 + e / 16);
+  w1s[tid] = __ldg(w1 + (tid & 15) * 12 + (tid >> 4));
   if (tid < 16) b1s[tid] = __ldg(b1 + tid);
-  for (int e = tid; e < 3 * 8 * 97; e += 192) {
-    const int col = e % 97 - 1;
-    const int r = (e / 97) % 8;
-    const int c = e / (97 * 8);
-    const int gr = 8 * r3 - 1 + r;
-    float v = 0.f;
-    if (gr >= 0 && gr < 96 && col >= 0 && col < 96) v = im[((size_t)c * 96 + gr) * 96 + col];
-    s_in[e] = v;
-  }
+  enc_stage_strip(im, r3, s_in, tid);
   __syncthreads();
   // tid = (c3*4 + kk3)*4 + kk2 : consecutive threads write consecutive 32-byte pixel slots of c1p
   const int kk2 = tid & 3, kk3 = (tid >> 2) & 3, c3 = tid >> 4;
-  const int yl = 2 * (kk3 >> 1) + (kk2 >> 1);        // conv1 row inside the strip (0..3)
+  const int yl = 2 * (kk3 >> 1) + (kk2 >> 1);          // conv1 row inside the strip (0..3)
   const int x = 2 * (2 * c3 + (kk3 & 1)) + (kk2 & 1);  // conv1 column (0..47)
   float acc[16];
 #pragma unroll
@@ -1158,7 +1392,7 @@ __global__ void __launch_bounds__(192) enc_conv1_fwd_kernel(const float* __restr
   for (int c = 0; c < 3; ++c)
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
-      const float xv = s_in[(c * 8 + 2 * yl + (kk >> 1)) * 97 + 2 * x + (kk & 1)];
+      const float xv = s_in[(c * 8 + 2 * yl + (kk >> 1)) * 100 + 3 + 2 * x + (kk & 1)];
       const float4* wp = reinterpret_cast<const float4*>(w1s + (c * 4 + kk) * 16);
 #pragma unroll
       for (int o4 = 0; o4 < 4; ++o4) {
@@ -1177,62 +1411,73 @@ __global__ void __launch_bounds__(192) enc_conv1_fwd_kernel(const float* __restr
 }
 
 // dW1 (16,3,2,2) and db1 from d1 [M2][64] (gradient of the pre-ReLU conv1 output, same layout as c1p).
-// Thread (o, ck) owns one weight; a block walks (frame, r3) strips; the strip's 192 pixels come from shared memory.
+// Thread (o, ck) owns one weight; a block walks (frame, r3) strips; the strip's 192 pixel gradients are re-ordered into
+// raster order in shared memory so that the inner loop is two LDS + one FMA with unit-stride addressing.
 __global__ void __launch_bounds__(192) enc_conv1_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ d1, float* __restrict__ dw1,
                                                               float* __restrict__ db1, int n_strips) {
-  __shared__ float s_in[3 * 8 * 97];
-  __shared__ float s_d[192 * 16];
+  __shared__ __align__(16) float s_in[24 * 100];
+  __shared__ float s_d[192 * 16];   // [yl][x][16]
   const int tid = threadIdx.x;
   const int o = tid & 15, ck = tid >> 4, c = ck >> 2, kk = ck & 3;
+  const int kk2 = tid & 3, kk3 = (tid >> 2) & 3, c3 = tid >> 4;
+  const int my_yl = 2 * (kk3 >> 1) + (kk2 >> 1), my_x = 2 * (2 * c3 + (kk3 & 1)) + (kk2 & 1);
   float acc = 0.f, accb = 0.f;
   for (int strip = blockIdx.x; strip < n_strips; strip += gridDim.x) {
     const int frame = strip / 12, r3 = strip % 12;
-    const float* im = img + (size_t)frame * 3 * 96 * 96;
     __syncthreads();
-    for (int e = tid; e < 3 * 8 * 97; e += 192) {
-      const int col = e % 97 - 1;
-      const int r = (e / 97) % 8;
-      const int cc = e / (97 * 8);
-      const int gr = 8 * r3 - 1 + r;
-      float v = 0.f;
-      if (gr >= 0 && gr < 96 && col >= 0 && col < 96) v = im[((size_t)cc * 96 + gr) * 96 + col];
-      s_in[e] = v;
-    }
+    enc_stage_strip(img + (size_t)frame * 3 * 96 * 96, r3, s_in, tid);
     {
       float t8[8];
       const bf16* src = d1 + ((size_t)strip * 192 + tid) * 16;
+      float* dst = s_d + (my_yl * 48 + my_x) * 16;
       load8(src, t8);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s_d[tid * 16 + i] = t8[i];
+      for (int i = 0; i < 8; ++i) dst[i] = t8[i];
       load8(src + 8, t8);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) s_d[tid * 16 + 8 + i] = t8[i];
+      for (int i = 0; i < 8; ++i) dst[8 + i] = t8[i];
     }
     __syncthreads();
-#pragma unroll 4
-    for (int px = 0; px < 192; ++px) {
-      const int kk2 = px & 3, kk3 = (px >> 2) & 3, c3 = px >> 4;
-      const int yl = 2 * (kk3 >> 1) + (kk2 >> 1);
-      const int x = 2 * (2 * c3 + (kk3 & 1)) + (kk2 & 1);
-      const float d = s_d[px * 16 + o];
-      acc = fmaf(d, s_in[(c * 8 + 2 * yl + (kk >> 1)) * 97 + 2 * x + (kk & 1)], acc);
-      if (ck == 0) accb += d;
+#pragma unroll
+    for (int yl = 0; yl < 4; ++yl) {
+      const float* xin = s_in + (c * 8 + 2 * yl + (kk >> 1)) * 100 + 3 + (kk & 1);
+      const float* dd = s_d + yl * 48 * 16 + o;
+#pragma unroll 8
+      for (int x = 0; x < 48; ++x) {
+        const float d = dd[x * 16];
+        acc = fmaf(d, xin[2 * x], acc);
+        accb += d;
+      }
     }
   }
   atomicAdd(dw1 + o * 12 + ck, acc);
   if (ck == 0) atomicAdd(db1 + o, accb);
 }
 
-// out = act > 0 ? d : 0   (ReLU backward), 8 bf16 per thread; in place allowed
-__global__ void relu_mask_kernel(const bf16* __restrict__ d, const bf16* __restrict__ act, bf16* __restrict__ out, long long nvec) {
-  const long long v = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (v >= nvec) return;
-  float a[8], g[8];
-  load8(act + v * 8, a);
-  load8(d + v * 8, g);
+// out = act > 0 ? d : 0   (ReLU backward) over [rows][64] bf16, in place allowed; optionally colsum[64] += column sums of the
+// masked gradient (the conv bias gradient).  Grid-stride with a stride that keeps every thread on the same 8 columns.
+__global__ void __launch_bounds__(256) relu_mask_kernel(const bf16* __restrict__ d, const bf16* __restrict__ act, bf16* __restrict__ out,
+                                                        long long nvec, float* __restrict__ colsum) {
+  __shared__ float red[256 * 8];
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (long long v = (long long)blockIdx.x * 256 + threadIdx.x; v < nvec; v += (long long)gridDim.x * 256) {
+    float a[8], g[8];
+    load8(act + v * 8, a);
+    load8(d + v * 8, g);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) g[i] = a[i] > 0.f ? g[i] : 0.f;
-  store8(out + v * 8, g);
+    for (int i = 0; i < 8; ++i) { g[i] = a[i] > 0.f ? g[i] : 0.f; acc[i] += g[i]; }
+    store8(out + v * 8, g);
+  }
+  if (!colsum) return;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64) {  // column = (thread % 8) * 8 + i
+    const int cg8 = threadIdx.x >> 3, i = threadIdx.x & 7;
+    float t = 0.f;
+    for (int r = 0; r < 32; ++r) t += red[(r * 8 + cg8) * 8 + i];
+    atomicAdd(colsum + cg8 * 8 + i, t);
+  }
 }
 
 // weight packs of the patch-GEMM encoder (see header of this section)
@@ -1289,8 +1534,11 @@ void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float*
   enc_conv1_wgrad_kernel<<<grid, 192, 0, s>>>(img, d1, dw1, db1, n * 12);
   COUNT_LAUNCH();
 }
-void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, cudaStream_t s) {
-  relu_mask_kernel<<<cdiv(n / 8, 256), 256, 0, s>>>(d, act, out, n / 8);
+void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, float* colsum64, cudaStream_t s) {
+  int grid = cdiv(n / 8, 256 * 4);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid < 1) grid = 1;
+  relu_mask_kernel<<<grid, 256, 0, s>>>(d, act, out, n / 8, colsum64);
   COUNT_LAUNCH();
 }
 void launch_enc_pack_tc(const float* w2, const float* b2, const float* w3, bf16* w2p, bf16* w2pT, bf16* w3p, bf16* w3pT, float* b2p, cudaStream_t s) {

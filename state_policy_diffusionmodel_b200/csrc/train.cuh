@@ -15,6 +15,8 @@ struct GnBwdArgs {
   const float* stats; int P;     // forward partial (sum, sumsq) [B][P][2]
   const float* gamma; const float* beta;
   float* dgamma; float* dbeta;   // [C], atomically accumulated
+  float* part;                   // optional scratch [B][2C]: per-sample (d gamma | d beta) rows, summed over B by a finalize kernel
+                                 // (512 blocks hammering the same C addresses with atomics cost 50 us per launch)
   int act;                       // ACT_GELU: out = gelu(gn(raw));  ACT_NONE: out = gn(raw) (+temb) (*film)
   const float* temb; int temb_off;  // [B][SPDM_TEMB_WIDTH] rows (per sample) or null
   const float* film; int film_off;  // [B][SPDM_FILM_WIDTH] or null
@@ -84,7 +86,8 @@ void launch_pack_enc_linear_t(const float* w, float* out, cudaStream_t s);
 // ---- vision encoder as patch GEMMs on the tensor cores (bf16 training path; layouts in bwd_kernels.cu) ----------
 void launch_enc_conv1_fwd(const float* img, const float* w1, const float* b1, bf16* c1p, int n, cudaStream_t s);
 void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float* db1, int n, cudaStream_t s);
-void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, cudaStream_t s);
+// over [rows][64] bf16; colsum64 (or null) += column sums of the masked gradient
+void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, float* colsum64, cudaStream_t s);
 void launch_enc_pack_tc(const float* w2, const float* b2, const float* w3, bf16* w2p, bf16* w2pT, bf16* w3p, bf16* w3pT, float* b2p, cudaStream_t s);
 void launch_enc_pack_linear_T16(const float* w, bf16* out, cudaStream_t s);
 void launch_enc_unpack_grads(const float* g2, const float* g3, const float* gb2, float* dw2, float* db2, float* dw3, cudaStream_t s);

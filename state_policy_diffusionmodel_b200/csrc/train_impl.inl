@@ -25,6 +25,12 @@ struct TrainState {
   bf16 *enc_w2p = nullptr, *enc_w2pT = nullptr, *enc_w3p = nullptr, *enc_w3pT = nullptr, *enc_wlT16 = nullptr;
   float* enc_b2p = nullptr;
   bool enc_simt = false;      // SPDM_ENC_SIMT=1: CUDA-core encoder on the bf16 path too (A/B switch)
+  // weight / bias gradients are off the critical path (nothing in the step reads them): they run on a side stream, forked
+  // from the main stream after the gradient they consume exists and joined at the end of the step
+  cudaStream_t side = nullptr;
+  std::vector<cudaEvent_t> evs; size_t ev_cur = 0;
+  cudaEvent_t ev_join = nullptr;
+  bool use_side = true;       // SPDM_TRAIN_SIDE=0 switches it off (A/B)
   bool wgrad_simt = false;    // SPDM_WGRAD_SIMT=1: CUDA-core weight gradients on the bf16 path too (A/B switch)
 };
 
@@ -34,6 +40,9 @@ float* train_enc_wlT(spdm_plan* p) { return p->tr ? p->tr->enc_wlT : nullptr; }
 void train_destroy(spdm_plan* p) {
   if (!p->tr) return;
   for (void* q : p->tr->bufs) cudaFree(q);
+  for (cudaEvent_t e : p->tr->evs) cudaEventDestroy(e);
+  if (p->tr->ev_join) cudaEventDestroy(p->tr->ev_join);
+  if (p->tr->side) cudaStreamDestroy(p->tr->side);
   delete p->tr;
   p->tr = nullptr;
 }
@@ -89,8 +98,23 @@ template <typename T> struct Train {
     return tr->grads + it->second.off;
   }
 
+  // stream for work nothing downstream in the step depends on (ordered after everything enqueued on the main stream so far)
+  cudaStream_t fork_side() {
+    if (!tr->use_side) return s;
+    if (tr->ev_cur == tr->evs.size()) {
+      cudaEvent_t e;
+      CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      tr->evs.push_back(e);
+    }
+    cudaEvent_t e = tr->evs[tr->ev_cur++];
+    CUDA_OK(cudaEventRecord(e, s));
+    CUDA_OK(cudaStreamWaitEvent(tr->side, e, 0));
+    return tr->side;
+  }
+
   // ---- weight / bias gradients ----
   void wgrad(const std::string& wname, const T* x, int ld_x, const T* dy, int ld_dy, int level) {
+    cudaStream_t s = fork_side();
     GemmW& g = p->gemms[wname];
     const int H = p->levelH(level), W = p->levelW(level);
     const long long m = M(level);
@@ -109,7 +133,9 @@ template <typename T> struct Train {
     a.dw = G(pname);
     launch_wgrad_simt<T, T>(a, s);
   }
-  void bias_grad(const std::string& bname, const T* dy, int ld, int level, int N) { launch_colsum<T>(dy, ld, M(level), N, G(bname), s); }
+  void bias_grad(const std::string& bname, const T* dy, int ld, int level, int N) {
+    launch_colsum<T>(dy, ld, M(level), N, G(bname), tr->use_side ? tr->side : s);  // always right after the wgrad of the same dy
+  }
 
   // ---- DoubleConvolution (models/Unet_FiLmLayer.py:85-115) ----
   DC dc_fwd(const std::string& name, const T* in, int ld_in, int Cin, int Cout, int level, T* out, int ld_out, const StageInfo* st,
@@ -147,6 +173,7 @@ template <typename T> struct Train {
       if (f.c.film) { a.film = f.c.film; a.film_off = d.st->film_off; a.d_film = d_film; }
     }
     a.HW = p->levelH(d.level) * p->levelW(d.level); a.C = d.Cout; a.eps = 1e-5f;
+    a.part = Fbuf((size_t)f.Bpad * 2 * d.Cout);
     launch_gn_bwd<T>(a, B, s);
   }
 
@@ -235,6 +262,8 @@ template <typename T> struct Train {
     const int rows = p->cfg.rows, dim = p->cfg.dim;
     d_temb = Fbuf((size_t)f.Bpad * SPDM_TEMB_WIDTH);
     d_film = Fbuf((size_t)f.Bpad * SPDM_FILM_WIDTH);
+    CUDA_OK(cudaMemsetAsync(d_temb, 0, (size_t)f.Bpad * SPDM_TEMB_WIDTH * sizeof(float), s));  // accumulated by gn_bwd
+    CUDA_OK(cudaMemsetAsync(d_film, 0, (size_t)f.Bpad * SPDM_FILM_WIDTH * sizeof(float), s));
     T* cat3 = A(0, 128); T* cat2 = A(1, 256); T* cat1 = A(2, 512);
 
     // ================= forward =================
@@ -341,6 +370,7 @@ template <typename T> struct Train {
     dc_bwd(inc, d_cur, 64, nullptr, 0, x_noisy);
 
     // ---- time-embedding Linears (Unet_FiLmLayer.py:136-142,165-168) ----
+    cudaStream_t s = fork_side();
     for (const StageInfo& st : kStages) {
       WgradArgs a{};
       a.x = silu_pe; a.ld_x = p->cfg.time_dim; a.dy = d_temb + st.temb_off; a.ld_dy = SPDM_TEMB_WIDTH; a.M = B; a.Cin = p->cfg.time_dim;
@@ -378,6 +408,9 @@ extern "C" int spdm_train_enable(spdm_plan* p) {
   tr->enc_wlT = p->alloc<float>((size_t)128 * 9216);
   tr->loss_dev = p->alloc<float>(1);
   if (const char* e = getenv("SPDM_ENC_SIMT")) tr->enc_simt = atoi(e) != 0;
+  if (const char* e = getenv("SPDM_TRAIN_SIDE")) tr->use_side = atoi(e) != 0;
+  CUDA_OK(cudaStreamCreateWithFlags(&tr->side, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&tr->ev_join, cudaEventDisableTiming));
   if (p->bf16_mode && !tr->enc_simt) {
     tr->enc_w2p = p->alloc<bf16>(64 * 64); tr->enc_w2pT = p->alloc<bf16>(64 * 64);
     tr->enc_w3p = p->alloc<bf16>(64 * 256); tr->enc_w3pT = p->alloc<bf16>(256 * 64);
@@ -456,6 +489,7 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
   cudaStream_t s = (cudaStream_t)stream;
   const long long before = total_launches();
   arena_reset(p, B);
+  tr->ev_cur = 0;
   CUDA_OK(cudaMemsetAsync(tr->grads, 0, (size_t)tr->total * sizeof(float), s));
   CUDA_OK(cudaMemsetAsync(tr->loss_dev, 0, sizeof(float), s));
   if (tr->packed) CUDA_OK(cudaMemsetAsync(tr->packed, 0, tr->packed_elems * sizeof(float), s));
@@ -522,12 +556,6 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     REQUIRE(it != tr->bind.end(), "training: parameter '%s' is not bound (spdm_train_bind)", name.c_str());
     return tr->grads + it->second.off;
   };
-  // ---- conv weight gradients of the bf16 path: [tap][Cout][Cin] -> PyTorch layout ----
-  if (tr->packed && !tr->wgrad_simt)
-    for (auto& kv : tr->packed_off) {
-      GemmW& g = p->gemms[kv.first];
-      launch_unpack_conv_grad(tr->packed + kv.second, G(kv.first + ".weight"), g.Cout, g.Cin, s);
-    }
   // ---- FiLM Linears, d obs_cond, vision encoder ----
   for (const StageInfo& st : kStages) {
     WgradArgs a{};
@@ -562,17 +590,15 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     launch_colsum<float>(d_enc_out, 128, n_frames, 128, G("vision_encoder.7.bias"), s);
     bf16* d3 = H16((size_t)n_pad * 9216);   // d feat, then masked in place = gradient of the pre-ReLU conv3 output [M3][64]
     tc_flat("d_feat", d_eo16, 128, tr->enc_wlT16, 128, 9216, n_pad, d3, 9216, nullptr, 0);
-    launch_relu_mask(d3, feat16, d3, M3 * 64, s);
+    launch_relu_mask(d3, feat16, d3, M3 * 64, G("vision_encoder.4.bias"), s);
     wg(c2, 256, d3, 64, M3, 256, 64, g3);
-    launch_colsum<bf16>(d3, 64, M3, 64, G("vision_encoder.4.bias"), s);
     bf16* d2 = H16((size_t)M2 * 64);        // [M3][256] == [M2][64]
     tc_flat("d_c2", d3, 64, tr->enc_w3pT, 64, 256, M3, d2, 256, nullptr, 0);
-    launch_relu_mask(d2, c2, d2, M2 * 64, s);
+    launch_relu_mask(d2, c2, d2, M2 * 64, gb2, s);
     wg(c1p, 64, d2, 64, M2, 64, 64, g2);
-    launch_colsum<bf16>(d2, 64, M2, 64, gb2, s);
     bf16* d1 = H16((size_t)M2 * 64);
     tc_flat("d_c1", d2, 64, tr->enc_w2pT, 64, 64, M2, d1, 64, nullptr, 0);
-    launch_relu_mask(d1, c1p, d1, M2 * 64, s);
+    launch_relu_mask(d1, c1p, d1, M2 * 64, nullptr, s);
     launch_enc_conv1_wgrad(images, d1, G("vision_encoder.0.weight"), G("vision_encoder.0.bias"), n_frames, s);
     launch_enc_unpack_grads(g2, g3, gb2, G("vision_encoder.2.weight"), G("vision_encoder.2.bias"), G("vision_encoder.4.weight"), s);
   } else {
@@ -596,6 +622,16 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
                        G("vision_encoder.0.bias"), G("vision_encoder.2.weight"), G("vision_encoder.2.bias"), G("vision_encoder.4.weight"),
                        G("vision_encoder.4.bias"), n_frames, s);
   }
+  if (tr->use_side) {  // join: every weight gradient is in place from here on
+    CUDA_OK(cudaEventRecord(tr->ev_join, tr->side));
+    CUDA_OK(cudaStreamWaitEvent(s, tr->ev_join, 0));
+  }
+  // ---- conv weight gradients of the bf16 path: [tap][Cout][Cin] -> PyTorch layout ----
+  if (tr->packed && !tr->wgrad_simt)
+    for (auto& kv : tr->packed_off) {
+      GemmW& g = p->gemms[kv.first];
+      launch_unpack_conv_grad(tr->packed + kv.second, G(kv.first + ".weight"), g.Cout, g.Cin, s);
+    }
   CUDA_OK(cudaMemcpyAsync(loss_out, tr->loss_dev, sizeof(float), cudaMemcpyDeviceToDevice, s));
   p->launches += total_launches() - before;
   check_async("train_fwd_bwd");
