@@ -248,7 +248,10 @@ int wgrad_tc_launch(const bf16* x, int ld_x, const bf16* dy, int ld_dy, long lon
     p.nty = (taps == 9 && H > 1) ? 3 : 1;
     p.kblocks = (int)(M / WG_KB);
     const int units = p.ntx * p.nty * p.ci_tiles * p.co_tiles;
-    int ksplit = (148 + units - 1) / units;
+    // one CTA per SM (192 KB of pipeline stages): keep the grid within one wave, every CTA does the same amount of work
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); }
+    int ksplit = sms / units;
     if (ksplit > p.kblocks / 4) ksplit = p.kblocks / 4;   // at least four 64-pixel blocks per unit
     if (ksplit < 1) ksplit = 1;
     p.ksplit = ksplit;
