@@ -5,6 +5,7 @@
 // Reference lines are cited per kernel (paths relative to the reference repo root).
 #include <cooperative_groups.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "train.cuh"
 
@@ -833,8 +834,281 @@ template <typename T> __global__ void gelu_bwd_kernel(const T* __restrict__ dy, 
   store8(dx + v * 8, d);
 }
 }  // namespace
+
+// -------------------------------------------------------------------------------------------------
+// Tensor-core version of the same backward for bf16 (warp-level mma.sync.m16n8k16, fp32 accumulate):
+//   phase 1, a warp per 16-query tile: S = Q K^T twice (once for the log-sum-exp, once to form P), dP = dO V^T,
+//            dS = P o (dP - D), dQ = scale * dS K      (the S / dS accumulator tiles become A fragments directly)
+//   phase 2, a warp per 16-key tile:   S^T = K Q^T, dP^T = V dO^T, dV = P^T dO, dK = scale * dS^T Q
+// Q, K, V, dO of a (sample, head) group sit in shared memory as bf16 rows padded by 16 bytes (conflict-free ldmatrix);
+// groups with L <= 16 are packed four to a block (one warp each).  Rows / keys past L are zero-filled and masked.
+// -------------------------------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const bf16* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void ldsm_x2_trans(uint32_t (&r)[2], const bf16* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x2.trans.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
+}
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  const __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+
+template <int HD>
+__global__ void __launch_bounds__(128) sdpa_bwd_mma_kernel(const bf16* __restrict__ qkv, const bf16* __restrict__ o, const bf16* __restrict__ d_o,
+                                                           bf16* __restrict__ d_qkv, int n_groups, int L, int Lp, int C, int heads, int gpb) {
+  constexpr int STR = HD + 8;      // padded row stride (elements)
+  constexpr int KS = HD / 16;      // k-steps over the head dimension
+  constexpr int DN = HD / 8;       // 8-wide output tiles over the head dimension
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t region = (size_t)4 * Lp * STR * sizeof(bf16) + (size_t)2 * Lp * sizeof(float);
+  const int ld = 3 * C;
+  const float scale = rsqrtf((float)HD);
+  constexpr int VPR = HD / 8;
+  // ---- stage Q, K, V, dO (zero rows past L) and D = rowsum(dO o O), lse = +inf (until phase 1 fills it) ----
+  for (int idx = tid; idx < gpb * 4 * Lp * VPR; idx += 128) {
+    const int v = idx % VPR;
+    int r = idx / VPR;
+    const int row = r % Lp; r /= Lp;
+    const int arr = r & 3, gl = r >> 2;
+    const int grp = blockIdx.x * gpb + gl;
+    bf16* dst = reinterpret_cast<bf16*>(smraw + gl * region) + ((size_t)arr * Lp + row) * STR + v * 8;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (grp < n_groups && row < L) {
+      const int b = grp / heads, h = grp - b * heads;
+      const bf16* src = arr < 3 ? qkv + ((size_t)b * L + row) * ld + arr * C + h * HD + v * 8
+                                : d_o + ((size_t)b * L + row) * C + h * HD + v * 8;
+      val = *reinterpret_cast<const uint4*>(src);
+    }
+    *reinterpret_cast<uint4*>(dst) = val;
+  }
+  for (int idx = tid; idx < gpb * Lp; idx += 128) {
+    const int row = idx % Lp, gl = idx / Lp;
+    const int grp = blockIdx.x * gpb + gl;
+    float* lse = reinterpret_cast<float*>(smraw + gl * region + (size_t)4 * Lp * STR * sizeof(bf16));
+    float* Dd = lse + Lp;
+    float dsum = 0.f;
+    if (grp < n_groups && row < L) {
+      const int b = grp / heads, h = grp - b * heads;
+      const bf16* po = o + ((size_t)b * L + row) * C + h * HD;
+      const bf16* pg = d_o + ((size_t)b * L + row) * C + h * HD;
+#pragma unroll
+      for (int d = 0; d < HD; d += 8) {
+        float a8[8], b8[8];
+        load8(po + d, a8);
+        load8(pg + d, b8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) dsum = fmaf(a8[e], b8[e], dsum);
+      }
+    }
+    Dd[row] = dsum;
+    lse[row] = INFINITY;
+  }
+  __syncthreads();
+  const int wpg = 4 / gpb;                         // warps per group
+  const int gl = warp / wpg, wl = warp - gl * wpg;  // group inside the block, warp inside the group
+  const int grp = blockIdx.x * gpb + gl;
+  const bool active = grp < n_groups;
+  bf16* Qs = reinterpret_cast<bf16*>(smraw + gl * region);
+  bf16* Ks = Qs + (size_t)Lp * STR;
+  bf16* Vs = Ks + (size_t)Lp * STR;
+  bf16* Gs = Vs + (size_t)Lp * STR;
+  float* lse = reinterpret_cast<float*>(Gs + (size_t)Lp * STR);
+  float* Dd = lse + Lp;
+  const int b = active ? grp / heads : 0, h = active ? grp - b * heads : 0;
+  const int ntiles = Lp / 16;
+
+  // ================= phase 1: queries =================
+  for (int it = wl; it < ntiles && active; it += wpg) {
+    const int r0 = it * 16;
+    uint32_t qa[KS][4], ga[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      ldsm_x4(qa[ks], Qs + (size_t)(r0 + (lane & 15)) * STR + ks * 16 + (lane >> 4) * 8);
+      ldsm_x4(ga[ks], Gs + (size_t)(r0 + (lane & 15)) * STR + ks * 16 + (lane >> 4) * 8);
+    }
+    float m0 = -INFINITY, l0 = 0.f, m1 = -INFINITY, l1 = 0.f;
+    for (int nt = 0; nt < Lp / 8; ++nt) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t kb[2];
+        ldsm_x2(kb, Ks + (size_t)(nt * 8 + (lane & 7)) * STR + ks * 16 + ((lane >> 3) & 1) * 8);
+        mma16816(c, qa[ks], kb);
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = nt * 8 + 2 * t + e < L;
+        const float s0 = ok ? c[e] * scale : -INFINITY, s1 = ok ? c[2 + e] * scale : -INFINITY;
+        if (s0 > m0) { l0 = l0 * __expf(m0 - s0) + 1.f; m0 = s0; } else if (ok) l0 += __expf(s0 - m0);
+        if (s1 > m1) { l1 = l1 * __expf(m1 - s1) + 1.f; m1 = s1; } else if (ok) l1 += __expf(s1 - m1);
+      }
+    }
+#pragma unroll
+    for (int off = 1; off <= 2; off <<= 1) {  // merge the 4 lanes that share a row
+      const float om0 = __shfl_xor_sync(0xffffffffu, m0, off), ol0 = __shfl_xor_sync(0xffffffffu, l0, off);
+      const float om1 = __shfl_xor_sync(0xffffffffu, m1, off), ol1 = __shfl_xor_sync(0xffffffffu, l1, off);
+      const float nm0 = fmaxf(m0, om0), nm1 = fmaxf(m1, om1);
+      l0 = (m0 == -INFINITY ? 0.f : l0 * __expf(m0 - nm0)) + (om0 == -INFINITY ? 0.f : ol0 * __expf(om0 - nm0));
+      l1 = (m1 == -INFINITY ? 0.f : l1 * __expf(m1 - nm1)) + (om1 == -INFINITY ? 0.f : ol1 * __expf(om1 - nm1));
+      m0 = nm0; m1 = nm1;
+    }
+    const float lse0 = m0 + __logf(l0), lse1 = m1 + __logf(l1);
+    const float D0 = Dd[r0 + g], D1 = Dd[r0 + g + 8];
+    float dq[DN][4];
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn) { dq[dn][0] = 0.f; dq[dn][1] = 0.f; dq[dn][2] = 0.f; dq[dn][3] = 0.f; }
+    for (int np = 0; np < ntiles; ++np) {
+      float ds[2][4];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int nt = np * 2 + hh;
+        float c[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          uint32_t kb[2], vb[2];
+          ldsm_x2(kb, Ks + (size_t)(nt * 8 + (lane & 7)) * STR + ks * 16 + ((lane >> 3) & 1) * 8);
+          ldsm_x2(vb, Vs + (size_t)(nt * 8 + (lane & 7)) * STR + ks * 16 + ((lane >> 3) & 1) * 8);
+          mma16816(c, qa[ks], kb);
+          mma16816(dp, ga[ks], vb);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool ok = nt * 8 + 2 * t + e < L;
+          const float p0 = ok ? __expf(c[e] * scale - lse0) : 0.f, p1 = ok ? __expf(c[2 + e] * scale - lse1) : 0.f;
+          ds[hh][e] = p0 * (dp[e] - D0);
+          ds[hh][2 + e] = p1 * (dp[2 + e] - D1);
+        }
+      }
+      uint32_t dsa[4] = {pack_bf16x2(ds[0][0], ds[0][1]), pack_bf16x2(ds[0][2], ds[0][3]), pack_bf16x2(ds[1][0], ds[1][1]),
+                         pack_bf16x2(ds[1][2], ds[1][3])};
+#pragma unroll
+      for (int dn = 0; dn < DN; ++dn) {
+        uint32_t kb2[2];
+        ldsm_x2_trans(kb2, Ks + (size_t)(np * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * STR + dn * 8);
+        mma16816(dq[dn], dsa, kb2);
+      }
+    }
+    const int row_a = r0 + g, row_b = r0 + g + 8;
+    if (t == 0) {
+      if (row_a < L) lse[row_a] = lse0;
+      if (row_b < L) lse[row_b] = lse1;
+    }
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn) {
+      const int col = h * HD + dn * 8 + 2 * t;
+      if (row_a < L) *reinterpret_cast<uint32_t*>(d_qkv + ((size_t)b * L + row_a) * ld + col) = pack_bf16x2(dq[dn][0] * scale, dq[dn][1] * scale);
+      if (row_b < L) *reinterpret_cast<uint32_t*>(d_qkv + ((size_t)b * L + row_b) * ld + col) = pack_bf16x2(dq[dn][2] * scale, dq[dn][3] * scale);
+    }
+  }
+  __syncthreads();
+  // ================= phase 2: keys =================
+  for (int jt = wl; jt < ntiles && active; jt += wpg) {
+    const int k0 = jt * 16;
+    uint32_t ka[KS][4], va[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      ldsm_x4(ka[ks], Ks + (size_t)(k0 + (lane & 15)) * STR + ks * 16 + (lane >> 4) * 8);
+      ldsm_x4(va[ks], Vs + (size_t)(k0 + (lane & 15)) * STR + ks * 16 + (lane >> 4) * 8);
+    }
+    float dk[DN][4], dv[DN][4];
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { dk[dn][e] = 0.f; dv[dn][e] = 0.f; }
+    }
+    for (int np = 0; np < ntiles; ++np) {
+      float pt[2][4], dst[2][4];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int nt = np * 2 + hh;
+        float c[4] = {0.f, 0.f, 0.f, 0.f}, dp[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          uint32_t qb[2], gb[2];
+          ldsm_x2(qb, Qs + (size_t)(nt * 8 + (lane & 7)) * STR + ks * 16 + ((lane >> 3) & 1) * 8);
+          ldsm_x2(gb, Gs + (size_t)(nt * 8 + (lane & 7)) * STR + ks * 16 + ((lane >> 3) & 1) * 8);
+          mma16816(c, ka[ks], qb);
+          mma16816(dp, va[ks], gb);
+        }
+        const float2 ls = *reinterpret_cast<const float2*>(lse + nt * 8 + 2 * t);   // +inf for queries past L -> p = 0
+        const float2 dd = *reinterpret_cast<const float2*>(Dd + nt * 8 + 2 * t);
+        pt[hh][0] = __expf(c[0] * scale - ls.x); pt[hh][1] = __expf(c[1] * scale - ls.y);
+        pt[hh][2] = __expf(c[2] * scale - ls.x); pt[hh][3] = __expf(c[3] * scale - ls.y);
+        dst[hh][0] = pt[hh][0] * (dp[0] - dd.x); dst[hh][1] = pt[hh][1] * (dp[1] - dd.y);
+        dst[hh][2] = pt[hh][2] * (dp[2] - dd.x); dst[hh][3] = pt[hh][3] * (dp[3] - dd.y);
+      }
+      uint32_t pa[4] = {pack_bf16x2(pt[0][0], pt[0][1]), pack_bf16x2(pt[0][2], pt[0][3]), pack_bf16x2(pt[1][0], pt[1][1]),
+                        pack_bf16x2(pt[1][2], pt[1][3])};
+      uint32_t dsa[4] = {pack_bf16x2(dst[0][0], dst[0][1]), pack_bf16x2(dst[0][2], dst[0][3]), pack_bf16x2(dst[1][0], dst[1][1]),
+                         pack_bf16x2(dst[1][2], dst[1][3])};
+#pragma unroll
+      for (int dn = 0; dn < DN; ++dn) {
+        uint32_t gb2[2], qb2[2];
+        ldsm_x2_trans(gb2, Gs + (size_t)(np * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * STR + dn * 8);
+        ldsm_x2_trans(qb2, Qs + (size_t)(np * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * STR + dn * 8);
+        mma16816(dv[dn], pa, gb2);
+        mma16816(dk[dn], dsa, qb2);
+      }
+    }
+    const int row_a = k0 + g, row_b = k0 + g + 8;
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn) {
+      const int col = h * HD + dn * 8 + 2 * t;
+      if (row_a < L) {
+        bf16* base = d_qkv + ((size_t)b * L + row_a) * ld + col;
+        *reinterpret_cast<uint32_t*>(base + C) = pack_bf16x2(dk[dn][0] * scale, dk[dn][1] * scale);
+        *reinterpret_cast<uint32_t*>(base + 2 * C) = pack_bf16x2(dv[dn][0], dv[dn][1]);
+      }
+      if (row_b < L) {
+        bf16* base = d_qkv + ((size_t)b * L + row_b) * ld + col;
+        *reinterpret_cast<uint32_t*>(base + C) = pack_bf16x2(dk[dn][2] * scale, dk[dn][3] * scale);
+        *reinterpret_cast<uint32_t*>(base + 2 * C) = pack_bf16x2(dv[dn][2], dv[dn][3]);
+      }
+    }
+  }
+}
+
+template <int HD> bool launch_sdpa_bwd_mma(const bf16* qkv, const bf16* o, const bf16* d_o, bf16* d_qkv, int B, int L, int C, int heads, cudaStream_t s) {
+  const int Lp = (L + 15) / 16 * 16;
+  const int gpb = Lp <= 16 ? 4 : 1;
+  const size_t region = (size_t)4 * Lp * (HD + 8) * sizeof(bf16) + (size_t)2 * Lp * sizeof(float);
+  const size_t smem = region * gpb;
+  if (smem > 200 * 1024 || region % 16) return false;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(sdpa_bwd_mma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+  const int n_groups = B * heads;
+  sdpa_bwd_mma_kernel<HD><<<(n_groups + gpb - 1) / gpb, 128, smem, s>>>(qkv, o, d_o, d_qkv, n_groups, L, Lp, C, heads, gpb);
+  return true;
+}
+}  // namespace
 template <typename T> void launch_sdpa_bwd(const T* qkv, const T* o, const T* d_o, T* d_qkv, int B, int L, int C, int heads, cudaStream_t s) {
   const int hd = C / heads;
+  if constexpr (sizeof(T) == 2) {
+    static int simt = -1;  // SPDM_SDPA_BWD_SIMT=1: CUDA-core kernel on the bf16 path too (A/B switch)
+    if (simt < 0) { const char* e = getenv("SPDM_SDPA_BWD_SIMT"); simt = e ? atoi(e) : 0; }
+    if (!simt) {
+      bool done = false;
+      if (hd == 16) done = launch_sdpa_bwd_mma<16>(qkv, o, d_o, d_qkv, B, L, C, heads, s);
+      else if (hd == 32) done = launch_sdpa_bwd_mma<32>(qkv, o, d_o, d_qkv, B, L, C, heads, s);
+      else if (hd == 64) done = launch_sdpa_bwd_mma<64>(qkv, o, d_o, d_qkv, B, L, C, heads, s);
+      if (done) { COUNT_LAUNCH(); return; }
+    }
+  }
   const size_t smem = ((size_t)4 * L * hd + 2 * L) * sizeof(float);
 #define SDPA_BWD_CASE(HD)                                                                                       \
   {                                                                                                             \
