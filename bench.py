@@ -164,6 +164,22 @@ def run_reference(args):
         return
     import torch
     from oracle import fixtures
+    if args.workload == "train":
+        rates = []
+        for i in range(args.warmup + args.steps):
+            r, cores, sample = cpu_train_rate(args, reps=1)
+            if i >= args.warmup:
+                rates.append(r)
+        value = sum(rates) / len(rates)
+        print(json.dumps({"impl": "reference", "metric": "train samples/s", "value": round(value, 2), "unit": "samples/s", "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(1000.0 * args.train_batch * args.gpus / value, 1),
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "training step: %s + vision encoder, fwd + bwd + clip + Adam" % (
+                              "UNet_Film (attention)" if args.variant == "attn" else "UNet_Film_noAttention"),
+                              "global_batch": args.train_batch * args.gpus, "per_gpu_batch": args.train_batch},
+                          "cpu_baseline": {"value": round(value, 2), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": round(value, 2), "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}), flush=True)
+        return
     attention = args.variant == "attn"
     sd = fixtures.make_unet_weights(attention=attention, seed=0)
     esd = fixtures.make_encoder_weights()
@@ -185,6 +201,43 @@ def run_reference(args):
 
 # nominal FLOPs of one training step per sample: U-Net fwd+bwd + 3 x the conditioning encode
 FLOP_TRAIN_ATTN, FLOP_TRAIN_NOATTN = 2464.6e6 + 240e6, 2262.1e6 + 240e6
+
+
+def cpu_train_rate(args, b_cpu=32, reps=2):
+    """The reference's CPU training step (oracle port: fp32 eager torch autograd over the restated process_single_batch,
+    models/diffusion_ddpm.py:128-173, + clip + Adam restatement) on the host cores: samples/s on a bounded sample."""
+    import torch
+    from oracle import fixtures, train_ref
+    from oracle.schedulers import RefDDPMScheduler
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    attention = args.variant == "attn"
+    sd = fixtures.make_unet_weights(attention=attention, seed=0)
+    esd = fixtures.make_encoder_weights()
+    g = torch.Generator().manual_seed(3)
+    T = 10 + args.rows - 1
+    full = {"image": torch.rand((b_cpu, T, 3, 96, 96), generator=g), "position": 0.3 * torch.randn((b_cpu, T, 2), generator=g),
+            "velocity": 2 * torch.rand((b_cpu, T, 2), generator=g) - 1, "action": 2 * torch.rand((b_cpu, T, 3), generator=g) - 1}
+    sched = RefDDPMScheduler(num_train_timesteps=1000, beta_schedule="linear", clip_sample=False)
+    params = dict(sd)
+    params.update({train_ref.ENC_PREFIX + k: v for k, v in esd.items()})
+    m = {k: torch.zeros_like(v) for k, v in params.items()}
+    v = {k: torch.zeros_like(v) for k, v in params.items()}
+    times = []
+    for i in range(reps + 1):
+        t = torch.randint(0, 1000, (b_cpu,), generator=g)
+        noise = torch.randn((b_cpu, 1, args.rows, 5), generator=g)
+        t0 = time.perf_counter()
+        _, grads = train_ref.loss_and_grads(sd, esd, sched, full, 10, 1, t, noise, attention=attention)
+        _, grads = train_ref.clip_grad_norm(grads, 0.5)
+        params, m, v = train_ref.adam_step(params, grads, m, v, i + 1)
+        sd = {k: params[k] for k in sd}
+        esd = {k: params[train_ref.ENC_PREFIX + k] for k in esd}
+        if i > 0:
+            times.append(time.perf_counter() - t0)
+    per = sum(times) / len(times)
+    return b_cpu / per, cores, "%d samples per step, %d timed steps of fwd + autograd bwd + clip + Adam (%.2fs each), 1 warm-up" % (
+        b_cpu, len(times), per)
 
 
 def bench_train(args, dev, world, rank, steps, warmup):
@@ -253,6 +306,9 @@ def bench_train(args, dev, world, rank, steps, warmup):
     model._tplan.close()
     del model, batch
     torch.cuda.empty_cache()
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.dim == 5:
+        rate, cores, sample = cpu_train_rate(args)
+        res["cpu_baseline"] = {"value": round(rate, 2), "unit": "samples/s", "cores": cores, "kind": "port", "sample": sample}
     return res
 
 

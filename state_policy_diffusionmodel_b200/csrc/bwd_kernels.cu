@@ -336,20 +336,23 @@ template <typename T, int VPT> void launch_gn_cached(const GnBwdArgs& a, int B, 
   cfg.numAttrs = 1;
   cudaLaunchKernelEx(&cfg, gn_bwd_cached_kernel<T, VPT>, a, CS);
 }
-// d gamma[c] += sum_b part[b][c], d beta[c] += sum_b part[b][C + c]: 32 columns per block, 8 row groups
-__global__ void __launch_bounds__(256) gn_part_finalize_kernel(const float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta,
-                                                               int B, int C) {
-  __shared__ float sm[8][32];
-  const int col = blockIdx.x * 32 + (threadIdx.x & 31), rg = threadIdx.x >> 5;
+// d gamma[c] += sum_b part[b][c], d beta[c] += sum_b part[b][C + c]: 32 columns x 32 row groups per block
+__global__ void __launch_bounds__(1024) gn_part_finalize_kernel(const float* __restrict__ part, float* __restrict__ dgamma, float* __restrict__ dbeta,
+                                                                int B, int C) {
+  __shared__ float sm[32][33];
+  const int lane = threadIdx.x & 31, rg = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
   float acc = 0.f;
-  if (col < 2 * C)
-    for (int b = rg; b < B; b += 8) acc += part[(size_t)b * 2 * C + col];
-  sm[rg][threadIdx.x & 31] = acc;
+  if (col < 2 * C) {
+#pragma unroll 8
+    for (int b = rg; b < B; b += 32) acc += __ldg(part + (size_t)b * 2 * C + col);
+  }
+  sm[rg][lane] = acc;
   __syncthreads();
   if (rg == 0 && col < 2 * C) {
     float t = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) t += sm[r][threadIdx.x];
+    for (int r = 0; r < 32; ++r) t += sm[r][lane];
     if (col < C) atomicAdd(dgamma + col, t);
     else atomicAdd(dbeta + col - C, t);
   }
@@ -369,7 +372,7 @@ template <typename T> void launch_gn_bwd(const GnBwdArgs& a, int B, cudaStream_t
       else launch_gn_cached<T, 1>(a, B, CS, threads, s);
       COUNT_LAUNCH();
       if (a.part && CS == 1) {
-        gn_part_finalize_kernel<<<cdiv(2 * a.C, 32), 256, 0, s>>>(a.part, a.dgamma, a.dbeta, B, a.C);
+        gn_part_finalize_kernel<<<cdiv(2 * a.C, 32), 1024, 0, s>>>(a.part, a.dgamma, a.dbeta, B, a.C);
         COUNT_LAUNCH();
       }
       return;
@@ -1685,17 +1688,19 @@ __global__ void __launch_bounds__(192) enc_conv1_fwd_kernel(const float* __restr
 }
 
 // dW1 (16,3,2,2) and db1 from d1 [M2][64] (gradient of the pre-ReLU conv1 output, same layout as c1p).
-// Thread (o, ck) owns one weight; a block walks (frame, r3) strips; the strip's 192 pixel gradients are re-ordered into
-// raster order in shared memory so that the inner loop is two LDS + one FMA with unit-stride addressing.
+// A block walks (frame, r3) strips.  The kernel is bound by shared-memory reads, so every thread owns a 2 (o) x 4 (kh,kw)
+// register tile of one input channel and one eighth of the strip's pixels: 1 LDS.64 + 4 LDS per 8 FMAs.
+// thread = pixel group pg (8) x input channel c (3) x output pair op (8); partial tiles are folded through shared memory once,
+// at the end of the kernel, then one atomicAdd per weight per block.
 __global__ void __launch_bounds__(192) enc_conv1_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ d1, float* __restrict__ dw1,
                                                               float* __restrict__ db1, int n_strips) {
   __shared__ __align__(16) float s_in[24 * 100];
-  __shared__ float s_d[192 * 16];   // [yl][x][16]
+  __shared__ __align__(16) float s_d[192 * 16];   // [yl][x][16]
   const int tid = threadIdx.x;
-  const int o = tid & 15, ck = tid >> 4, c = ck >> 2, kk = ck & 3;
+  const int op = tid & 7, c = (tid >> 3) % 3, pg = tid / 24;   // outputs 2*op, 2*op+1; channel c; pixels pg, pg+8, ...
   const int kk2 = tid & 3, kk3 = (tid >> 2) & 3, c3 = tid >> 4;
   const int my_yl = 2 * (kk3 >> 1) + (kk2 >> 1), my_x = 2 * (2 * c3 + (kk3 & 1)) + (kk2 & 1);
-  float acc = 0.f, accb = 0.f;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}}, accb[2] = {0.f, 0.f};
   for (int strip = blockIdx.x; strip < n_strips; strip += gridDim.x) {
     const int frame = strip / 12, r3 = strip % 12;
     __syncthreads();
@@ -1714,18 +1719,44 @@ __global__ void __launch_bounds__(192) enc_conv1_wgrad_kernel(const float* __res
     __syncthreads();
 #pragma unroll
     for (int yl = 0; yl < 4; ++yl) {
-      const float* xin = s_in + (c * 8 + 2 * yl + (kk >> 1)) * 100 + 3 + (kk & 1);
-      const float* dd = s_d + yl * 48 * 16 + o;
-#pragma unroll 8
-      for (int x = 0; x < 48; ++x) {
-        const float d = dd[x * 16];
-        acc = fmaf(d, xin[2 * x], acc);
-        accb += d;
+      const float* r0 = s_in + (c * 8 + 2 * yl) * 100 + 3;
+      const float* r1 = r0 + 100;
+      const float* dd = s_d + yl * 48 * 16 + 2 * op;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        const int x = pg + 8 * j;
+        const float2 d = *reinterpret_cast<const float2*>(dd + x * 16);
+        const float i00 = r0[2 * x], i01 = r0[2 * x + 1], i10 = r1[2 * x], i11 = r1[2 * x + 1];
+        acc[0][0] = fmaf(d.x, i00, acc[0][0]); acc[0][1] = fmaf(d.x, i01, acc[0][1]);
+        acc[0][2] = fmaf(d.x, i10, acc[0][2]); acc[0][3] = fmaf(d.x, i11, acc[0][3]);
+        acc[1][0] = fmaf(d.y, i00, acc[1][0]); acc[1][1] = fmaf(d.y, i01, acc[1][1]);
+        acc[1][2] = fmaf(d.y, i10, acc[1][2]); acc[1][3] = fmaf(d.y, i11, acc[1][3]);
+        accb[0] += d.x;
+        accb[1] += d.y;
       }
     }
   }
-  atomicAdd(dw1 + o * 12 + ck, acc);
-  if (ck == 0) atomicAdd(db1 + o, accb);
+  // fold the 8 pixel groups: s_d is free now
+  __syncthreads();
+  float* red = s_d;                       // [pg][16 o][12 ck] then [pg][16] bias partials at 8*192
+#pragma unroll
+  for (int e = 0; e < 2; ++e)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) red[pg * 192 + (2 * op + e) * 12 + c * 4 + kk] = acc[e][kk];
+  if (c == 0) { red[8 * 192 + pg * 16 + 2 * op] = accb[0]; red[8 * 192 + pg * 16 + 2 * op + 1] = accb[1]; }
+  __syncthreads();
+  {
+    float t = 0.f;
+#pragma unroll
+    for (int g8 = 0; g8 < 8; ++g8) t += red[g8 * 192 + tid];
+    atomicAdd(dw1 + tid, t);              // (16,3,2,2) is [o][c*4+kk]
+    if (tid < 16) {
+      float tb = 0.f;
+#pragma unroll
+      for (int g8 = 0; g8 < 8; ++g8) tb += red[8 * 192 + g8 * 16 + tid];
+      atomicAdd(db1 + tid, tb);
+    }
+  }
 }
 
 // out = act > 0 ? d : 0   (ReLU backward) over [rows][64] bf16, in place allowed; optionally colsum[64] += column sums of the

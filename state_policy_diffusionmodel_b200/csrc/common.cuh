@@ -17,7 +17,7 @@ typedef __nv_bfloat16 bf16;
 
 enum : int { ACT_NONE = 0, ACT_GELU = 1, ACT_RELU = 2 };
 enum : int { TEMB_NONE = 0, TEMB_ROW0 = 1, TEMB_PER_SAMPLE = 2, TEMB_STEP = 3 };
-enum : int { EPI_STATS = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RESID = 8, EPI_VT = 16, EPI_APPLY = 32, EPI_RELU = 64 };
+enum : int { EPI_STATS = 1, EPI_BIAS = 2, EPI_GELU = 4, EPI_RESID = 8, EPI_VT = 16, EPI_APPLY = 32, EPI_RELU = 64, EPI_MASK = 128 /* out = resid > 0 ? acc : 0 (ReLU backward) */ };
 
 #define SPDM_FILM_WIDTH 1792 /* sum over the 6 stages of 2*C_out */
 #define SPDM_TEMB_WIDTH 896  /* sum over the 6 stages of C_out   */

@@ -209,7 +209,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       const long long row0 = ((long long)t.b0 * p.H + t.h0) * p.W;  // tile rows are contiguous in the [M, C] map
       const long long row = row0 + r_t;
       bf16* orow = p.out + row * p.ld_out + t.n0;
-      const bf16* rrow = (p.flags & EPI_RESID) ? p.resid + row * p.ld_res + t.n0 : nullptr;
+      const bf16* rrow = (p.flags & (EPI_RESID | EPI_MASK)) ? p.resid + row * p.ld_res + t.n0 : nullptr;
       float rs = 0.f, rq = 0.f;
       mbar_wait(&tmem_full_bar[acc], aph);
       tc_fence_after();
@@ -343,12 +343,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.f);
         }
         if (rrow) {
+          const bool mask = (p.flags & EPI_MASK) != 0;
 #pragma unroll
           for (int i = 0; i < 32; i += 8) {
             float t8[8];
             load8(rrow + c + i, t8);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) f[i + e] += t8[e];
+            for (int e = 0; e < 8; ++e) f[i + e] = mask ? (t8[e] > 0.f ? f[i + e] : 0.f) : f[i + e] + t8[e];
           }
         }
         if (p.flags & EPI_STATS) {

@@ -742,8 +742,10 @@ void run_forward(spdm_plan* p, const FwdCtx& c) {
   else { Fwd<float> f(p, c); f.run(); }
 }
 
-void check_ready(spdm_plan* p) {
+void train_wait_packs(spdm_plan* p);  // train_impl.inl: block until weight repacks still running on the side stream are done
+void check_ready(spdm_plan* p, bool training_step = false) {
   if (p->sched_only) throw SpdmError{"this plan was created scheduler-only (SPDM_FLAG_SCHEDULER_ONLY)"};
+  if (p->tr && !training_step) train_wait_packs(p);
   if (!p->missing_unet.empty()) throw SpdmError{"U-Net weights missing, first: " + *p->missing_unet.begin()};
 }
 

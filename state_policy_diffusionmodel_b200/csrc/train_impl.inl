@@ -30,6 +30,8 @@ struct TrainState {
   cudaStream_t side = nullptr;
   std::vector<cudaEvent_t> evs; size_t ev_cur = 0;
   cudaEvent_t ev_join = nullptr;
+  cudaEvent_t ev_packs = nullptr, ev_packs_fork = nullptr;  // U-Net weight repacks run on the side stream, under the encoder forward
+  bool packs_pending = false;
   bool use_side = true;       // SPDM_TRAIN_SIDE=0 switches it off (A/B)
   bool wgrad_simt = false;    // SPDM_WGRAD_SIMT=1: CUDA-core weight gradients on the bf16 path too (A/B switch)
 };
@@ -42,9 +44,18 @@ void train_destroy(spdm_plan* p) {
   for (void* q : p->tr->bufs) cudaFree(q);
   for (cudaEvent_t e : p->tr->evs) cudaEventDestroy(e);
   if (p->tr->ev_join) cudaEventDestroy(p->tr->ev_join);
+  if (p->tr->ev_packs) cudaEventDestroy(p->tr->ev_packs);
+  if (p->tr->ev_packs_fork) cudaEventDestroy(p->tr->ev_packs_fork);
   if (p->tr->side) cudaStreamDestroy(p->tr->side);
   delete p->tr;
   p->tr = nullptr;
+}
+
+void train_wait_packs(spdm_plan* p) {
+  if (p->tr && p->tr->packs_pending) {
+    CUDA_OK(cudaEventSynchronize(p->tr->ev_packs));
+    p->tr->packs_pending = false;
+  }
 }
 
 void arena_reset(spdm_plan* p, int B) {
@@ -125,6 +136,7 @@ template <typename T> struct Train {
         const int rc = wgrad_tc_launch(reinterpret_cast<const bf16*>(x), ld_x, reinterpret_cast<const bf16*>(dy), ld_dy, m, g.Cin, g.Cout, H, W,
                                        g.taps, dst, s);
         REQUIRE(rc == 0, "%s: %s", wname.c_str(), wgrad_tc_last_error());
+        if (g.taps == 9) launch_unpack_conv_grad(dst, G(pname), g.Cout, g.Cin, s);  // [tap][Cout][Cin] -> PyTorch layout, same stream
         return;
       }
     }
@@ -411,6 +423,8 @@ extern "C" int spdm_train_enable(spdm_plan* p) {
   if (const char* e = getenv("SPDM_TRAIN_SIDE")) tr->use_side = atoi(e) != 0;
   CUDA_OK(cudaStreamCreateWithFlags(&tr->side, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&tr->ev_join, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&tr->ev_packs, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&tr->ev_packs_fork, cudaEventDisableTiming));
   if (p->bf16_mode && !tr->enc_simt) {
     tr->enc_w2p = p->alloc<bf16>(64 * 64); tr->enc_w2pT = p->alloc<bf16>(64 * 64);
     tr->enc_w3p = p->alloc<bf16>(64 * 256); tr->enc_w3pT = p->alloc<bf16>(256 * 64);
@@ -450,11 +464,25 @@ extern "C" int spdm_train_set_buffers(spdm_plan* p, float* params, float* grads,
 extern "C" int spdm_train_sync_weights(spdm_plan* p, void* stream) {
   API_BEGIN
   REQUIRE(p && p->tr && p->tr->params, "training buffers not set");
+  // The encoder's (few, small) tensors are repacked on the caller's stream; the U-Net's ~150 repack launches go to the side
+  // stream, ordered after everything enqueued so far (the optimizer step), and the next training step only waits for them
+  // after its encoder forward.  Any other consumer (sampling, unet_forward) waits at once, below.
+  cudaStream_t main_s = (cudaStream_t)stream;
+  cudaStream_t pack_s = p->tr->use_side ? p->tr->side : main_s;
+  if (p->tr->use_side) {
+    CUDA_OK(cudaEventRecord(p->tr->ev_packs_fork, main_s));
+    CUDA_OK(cudaStreamWaitEvent(pack_s, p->tr->ev_packs_fork, 0));
+  }
   for (auto& kv : p->tr->bind) {
     const TrainBind& b = kv.second;
-    p->loaders[kv.first](p->tr->params + b.off, b.shape.data(), (int)b.shape.size(), (cudaStream_t)stream);
+    const bool enc = kv.first.rfind("vision_encoder.", 0) == 0;
+    p->loaders[kv.first](p->tr->params + b.off, b.shape.data(), (int)b.shape.size(), enc ? main_s : pack_s);
     p->missing_unet.erase(kv.first);
     p->missing_enc.erase(kv.first);
+  }
+  if (p->tr->use_side) {
+    CUDA_OK(cudaEventRecord(p->tr->ev_packs, pack_s));
+    p->tr->packs_pending = true;
   }
   if (p->tr->enc_w2p) {
     auto P = [&](const char* n) {
@@ -483,7 +511,7 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
   REQUIRE(p->cfg.cond_dim == 135 && p->G > 0, "training needs the conditional model (cond_dim == 135)");
   REQUIRE(B % p->bm == 0, "bf16 training: the batch (%d) must be a multiple of %d (pixel tiles of the weight-gradient GEMM hold whole samples)",
           B, p->bm);
-  check_ready(p);
+  check_ready(p, true);
   if (!p->missing_enc.empty()) throw SpdmError{"vision encoder weights missing, first: " + *p->missing_enc.begin()};
   TrainState* tr = p->tr;
   cudaStream_t s = (cudaStream_t)stream;
@@ -506,7 +534,7 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
   auto H16 = [&](size_t n) { return reinterpret_cast<bf16*>(arena_alloc(p, n * sizeof(bf16))); };
   // flat tensor-core GEMM (taps = 1) on `rows` rows: out = epi(in @ w^T)
   auto tc_flat = [&](const char* tag, const bf16* in, int ld_in, const bf16* w, int Cin, int Cout, long long rows, bf16* out, int ld_out,
-                     const float* bias, int flags) {
+                     const float* bias, int flags, const bf16* mask_act = nullptr, int ld_mask = 0) {
     char key[96];
     snprintf(key, sizeof key, "enc|%s|%p|%lld", tag, (const void*)in, rows);
     TcGemm*& g = p->tc_cache[key];
@@ -514,7 +542,7 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
       g = tc_gemm_create(in, ld_in, w, Cin, Cout, 1, 1, 1, (int)rows);
       REQUIRE(g != nullptr, "encoder GEMM %s: %s", tag, tc_last_error());
     }
-    tc_gemm_launch(g, out, ld_out, nullptr, bias, nullptr, 0, flags, (int)rows, s);
+    tc_gemm_launch(g, out, ld_out, nullptr, bias, mask_act, ld_mask, flags, (int)rows, s);
   };
   float* feat = nullptr;
   float* enc_out = F((size_t)n_frames * 128);
@@ -539,6 +567,10 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     launch_gemm_simt<float, float>(a, s);
   }
   launch_build_cond(position, action, velocity, enc_out, p->cond, B, T, p->cfg.cond_dim, s);
+  if (tr->packs_pending) {  // the U-Net weights repacked on the side stream (spdm_train_sync_weights) are needed from here on
+    CUDA_OK(cudaStreamWaitEvent(s, tr->ev_packs, 0));
+    tr->packs_pending = false;
+  }
   compute_film(p, B, s);
   // ---- time embedding rows (per sample) ----
   launch_temb(reinterpret_cast<const long long*>(t), B, p->inv_freq, p->temb_w, p->temb_b, p->temb_call, p->cfg.time_dim, s);
@@ -576,8 +608,20 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
   float* d_enc_out = F((size_t)n_frames * 128);
   launch_gather_feat_grad(d_cond, d_enc_out, B, T, p->cfg.cond_dim, s);
   if (enc_tc) {
+    auto fork = [&]() -> cudaStream_t {  // same contract as Train::fork_side
+      if (!tr->use_side) return s;
+      if (tr->ev_cur == tr->evs.size()) {
+        cudaEvent_t e;
+        CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        tr->evs.push_back(e);
+      }
+      cudaEvent_t e = tr->evs[tr->ev_cur++];
+      CUDA_OK(cudaEventRecord(e, s));
+      CUDA_OK(cudaStreamWaitEvent(tr->side, e, 0));
+      return tr->side;
+    };
     auto wg = [&](const bf16* x, int ld_x, const bf16* dy, int ld_dy, long long M, int Cin, int Cout, float* dst) {
-      const int rc = wgrad_tc_launch(x, ld_x, dy, ld_dy, M, Cin, Cout, 1, 1, 1, dst, s);
+      const int rc = wgrad_tc_launch(x, ld_x, dy, ld_dy, M, Cin, Cout, 1, 1, 1, dst, fork());
       REQUIRE(rc == 0, "encoder wgrad: %s", wgrad_tc_last_error());
     };
     bf16* d_eo16 = H16((size_t)n_pad * 128);
@@ -586,8 +630,8 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     float *g3 = tmp + (size_t)128 * 9216, *g2 = g3 + 64 * 256, *gb2 = g2 + 64 * 64;
     CUDA_OK(cudaMemsetAsync(tmp, 0, ((size_t)128 * 9216 + 64 * 256 + 64 * 64 + 64) * sizeof(float), s));
     wg(feat16, 9216, d_eo16, 128, n_pad, 9216, 128, tmp);
-    launch_enc_linear_grad_permute(tmp, G("vision_encoder.7.weight"), s);
-    launch_colsum<float>(d_enc_out, 128, n_frames, 128, G("vision_encoder.7.bias"), s);
+    launch_enc_linear_grad_permute(tmp, G("vision_encoder.7.weight"), tr->use_side ? tr->side : s);
+    launch_colsum<float>(d_enc_out, 128, n_frames, 128, G("vision_encoder.7.bias"), tr->use_side ? tr->side : s);
     bf16* d3 = H16((size_t)n_pad * 9216);   // d feat, then masked in place = gradient of the pre-ReLU conv3 output [M3][64]
     tc_flat("d_feat", d_eo16, 128, tr->enc_wlT16, 128, 9216, n_pad, d3, 9216, nullptr, 0);
     launch_relu_mask(d3, feat16, d3, M3 * 64, G("vision_encoder.4.bias"), s);
@@ -597,10 +641,12 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     launch_relu_mask(d2, c2, d2, M2 * 64, gb2, s);
     wg(c1p, 64, d2, 64, M2, 64, 64, g2);
     bf16* d1 = H16((size_t)M2 * 64);
-    tc_flat("d_c1", d2, 64, tr->enc_w2pT, 64, 64, M2, d1, 64, nullptr, 0);
-    launch_relu_mask(d1, c1p, d1, M2 * 64, nullptr, s);
+    tc_flat("d_c1", d2, 64, tr->enc_w2pT, 64, 64, M2, d1, 64, nullptr, EPI_MASK, c1p, 64);  // ReLU' of conv1 in the epilogue
     launch_enc_conv1_wgrad(images, d1, G("vision_encoder.0.weight"), G("vision_encoder.0.bias"), n_frames, s);
-    launch_enc_unpack_grads(g2, g3, gb2, G("vision_encoder.2.weight"), G("vision_encoder.2.bias"), G("vision_encoder.4.weight"), s);
+    {  // gb2 was accumulated on the main stream (relu mask), g2 / g3 on the side stream: unpack there, after this point of main
+      cudaStream_t us = fork();
+      launch_enc_unpack_grads(g2, g3, gb2, G("vision_encoder.2.weight"), G("vision_encoder.2.bias"), G("vision_encoder.4.weight"), us);
+    }
   } else {
   {  // Linear(9216 -> 128): weight gradient in the kernel's hwc column order first, then permuted into (128, 9216 chw)
     float* tmp = F((size_t)128 * 9216);
@@ -626,12 +672,6 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     CUDA_OK(cudaEventRecord(tr->ev_join, tr->side));
     CUDA_OK(cudaStreamWaitEvent(s, tr->ev_join, 0));
   }
-  // ---- conv weight gradients of the bf16 path: [tap][Cout][Cin] -> PyTorch layout ----
-  if (tr->packed && !tr->wgrad_simt)
-    for (auto& kv : tr->packed_off) {
-      GemmW& g = p->gemms[kv.first];
-      launch_unpack_conv_grad(tr->packed + kv.second, G(kv.first + ".weight"), g.Cout, g.Cin, s);
-    }
   CUDA_OK(cudaMemcpyAsync(loss_out, tr->loss_dev, sizeof(float), cudaMemcpyDeviceToDevice, s));
   p->launches += total_launches() - before;
   check_async("train_fwd_bwd");
