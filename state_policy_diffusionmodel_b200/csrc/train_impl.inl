@@ -33,6 +33,7 @@ struct TrainState {
   cudaEvent_t ev_packs = nullptr, ev_packs_fork = nullptr;  // U-Net weight repacks run on the side stream, under the encoder forward
   bool packs_pending = false;
   bool use_side = true;       // SPDM_TRAIN_SIDE=0 switches it off (A/B)
+  bool dgrad_swap = true;     // SPDM_DGRAD_SWAP=0: plain N = Cout tiles for the narrow data gradients (A/B)
   bool wgrad_simt = false;    // SPDM_WGRAD_SIMT=1: CUDA-core weight gradients on the bf16 path too (A/B switch)
 };
 
@@ -90,6 +91,7 @@ template <typename T> struct Train {
   cudaStream_t s;
   float* d_temb = nullptr;  // [B][896]
   float* d_film = nullptr;  // [B][1792]
+  float* dgrad_stats = nullptr;  // scratch GroupNorm partial sums written (and ignored) by swapped-operand dgrad launches
 
   struct DC {
     std::string name; const T* in; int ld_in, Cin, Cout, level;
@@ -189,20 +191,35 @@ template <typename T> struct Train {
     launch_gn_bwd<T>(a, B, s);
   }
 
+  // Data gradient of a 3x3 conv.  The swapped-operand kernel (N = 256 pixels per MMA instead of N = Cout <= 128) only exists
+  // with the GroupNorm-statistics epilogue, so narrow dgrads ask for statistics into a scratch slot and ignore them.
+  void dgrad3(const std::string& wname, const T* dy, int ld_dy, int level, T* dx, int ld_dx) {
+    int flags = 0;
+    if constexpr (sizeof(T) == 2) {
+      if (tr->dgrad_swap && p->gemms[wname].Cout <= 128) {
+        if (!dgrad_stats) dgrad_stats = S();
+        f.stats_ov = dgrad_stats;
+        flags = EPI_STATS;
+      }
+    }
+    f.gemm(wname, dy, ld_dy, level, dx, ld_dx, flags);
+    f.stats_ov = nullptr;
+  }
+
   // d_in: [M, Cin] (ld_din) or null when the block's input needs no gradient (inc)
   void dc_bwd(const DC& d, const T* d_out, int ld_dout, T* d_in, int ld_din, const float* x_noisy = nullptr) {
     T* d_raw2 = A(d.level, d.Cout);
     gn_bwd(d, true, d_out, ld_dout, d_raw2);
     wgrad(d.name + ".second", d.h, d.Cout, d_raw2, d.Cout, d.level);
     T* d_h = A(d.level, d.Cout);
-    f.gemm(d.name + ".second#d", d_raw2, d.Cout, d.level, d_h, d.Cout, 0);
+    dgrad3(d.name + ".second#d", d_raw2, d.Cout, d.level, d_h, d.Cout);
     T* d_raw1 = A(d.level, d.Cout);
     gn_bwd(d, false, d_h, d.Cout, d_raw1);
     if (d.first_is_in) {
       launch_conv_in_wgrad<T>(x_noisy, d_raw1, G("inc.first.weight"), B, p->H0, p->W0, p->cfg.rows, p->cfg.dim, p->lh, p->lw, s);
     } else {
       wgrad(d.name + ".first", d.in, d.ld_in, d_raw1, d.Cout, d.level);
-      if (d_in) f.gemm(d.name + ".first#d", d_raw1, d.Cout, d.level, d_in, ld_din, 0);
+      if (d_in) dgrad3(d.name + ".first#d", d_raw1, d.Cout, d.level, d_in, ld_din);
     }
   }
 
@@ -421,6 +438,7 @@ extern "C" int spdm_train_enable(spdm_plan* p) {
   tr->loss_dev = p->alloc<float>(1);
   if (const char* e = getenv("SPDM_ENC_SIMT")) tr->enc_simt = atoi(e) != 0;
   if (const char* e = getenv("SPDM_TRAIN_SIDE")) tr->use_side = atoi(e) != 0;
+  if (const char* e = getenv("SPDM_DGRAD_SWAP")) tr->dgrad_swap = atoi(e) != 0;
   CUDA_OK(cudaStreamCreateWithFlags(&tr->side, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&tr->ev_join, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&tr->ev_packs, cudaEventDisableTiming));
