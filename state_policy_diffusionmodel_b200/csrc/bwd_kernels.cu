@@ -1086,6 +1086,128 @@ __global__ void __launch_bounds__(128) sdpa_bwd_mma_kernel(const bf16* __restric
   }
 }
 
+// Forward attention core with the same building blocks (the training forward keeps Q|K|V row-major, which the tcgen05 core of
+// inference -- V^T produced by the in_proj epilogue -- does not): a warp per 16-query tile, pass 1 = log-sum-exp of S = Q K^T,
+// pass 2 = O = P V with P = exp(scale S - lse) formed straight from the accumulator tiles.
+template <int HD>
+__global__ void __launch_bounds__(128) sdpa_fwd_mma_kernel(const bf16* __restrict__ qkv, bf16* __restrict__ out, int n_groups, int L, int Lp, int C,
+                                                           int heads, int gpb) {
+  constexpr int STR = HD + 8, KS = HD / 16, DN = HD / 8, VPR = HD / 8;
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const size_t region = (size_t)3 * Lp * STR * sizeof(bf16);
+  const int ld = 3 * C;
+  const float scale = rsqrtf((float)HD);
+  for (int idx = tid; idx < gpb * 3 * Lp * VPR; idx += 128) {
+    const int v = idx % VPR;
+    int r = idx / VPR;
+    const int row = r % Lp; r /= Lp;
+    const int arr = r % 3, gl = r / 3;
+    const int grp = blockIdx.x * gpb + gl;
+    bf16* dst = reinterpret_cast<bf16*>(smraw + gl * region) + ((size_t)arr * Lp + row) * STR + v * 8;
+    uint4 val = make_uint4(0u, 0u, 0u, 0u);
+    if (grp < n_groups && row < L) {
+      const int b = grp / heads, h = grp - b * heads;
+      val = *reinterpret_cast<const uint4*>(qkv + ((size_t)b * L + row) * ld + arr * C + h * HD + v * 8);
+    }
+    *reinterpret_cast<uint4*>(dst) = val;
+  }
+  __syncthreads();
+  const int wpg = 4 / gpb;
+  const int gl = warp / wpg, wl = warp - gl * wpg;
+  const int grp = blockIdx.x * gpb + gl;
+  if (grp >= n_groups) return;
+  const bf16* Qs = reinterpret_cast<const bf16*>(smraw + gl * region);
+  const bf16* Ks = Qs + (size_t)Lp * STR;
+  const bf16* Vs = Ks + (size_t)Lp * STR;
+  const int b = grp / heads, h = grp - b * heads;
+  const int ntiles = Lp / 16;
+  for (int it = wl; it < ntiles; it += wpg) {
+    const int r0 = it * 16;
+    uint32_t qa[KS][4];
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) ldsm_x4(qa[ks], Qs + (size_t)(r0 + (lane & 15)) * STR + ks * 16 + (lane >> 4) * 8);
+    float m0 = -INFINITY, l0 = 0.f, m1 = -INFINITY, l1 = 0.f;
+    for (int nt = 0; nt < Lp / 8; ++nt) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t kb[2];
+        ldsm_x2(kb, Ks + (size_t)(nt * 8 + (lane & 7)) * STR + ks * 16 + ((lane >> 3) & 1) * 8);
+        mma16816(c, qa[ks], kb);
+      }
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool ok = nt * 8 + 2 * t + e < L;
+        const float s0 = ok ? c[e] * scale : -INFINITY, s1 = ok ? c[2 + e] * scale : -INFINITY;
+        if (s0 > m0) { l0 = l0 * __expf(m0 - s0) + 1.f; m0 = s0; } else if (ok) l0 += __expf(s0 - m0);
+        if (s1 > m1) { l1 = l1 * __expf(m1 - s1) + 1.f; m1 = s1; } else if (ok) l1 += __expf(s1 - m1);
+      }
+    }
+#pragma unroll
+    for (int off = 1; off <= 2; off <<= 1) {
+      const float om0 = __shfl_xor_sync(0xffffffffu, m0, off), ol0 = __shfl_xor_sync(0xffffffffu, l0, off);
+      const float om1 = __shfl_xor_sync(0xffffffffu, m1, off), ol1 = __shfl_xor_sync(0xffffffffu, l1, off);
+      const float nm0 = fmaxf(m0, om0), nm1 = fmaxf(m1, om1);
+      l0 = (m0 == -INFINITY ? 0.f : l0 * __expf(m0 - nm0)) + (om0 == -INFINITY ? 0.f : ol0 * __expf(om0 - nm0));
+      l1 = (m1 == -INFINITY ? 0.f : l1 * __expf(m1 - nm1)) + (om1 == -INFINITY ? 0.f : ol1 * __expf(om1 - nm1));
+      m0 = nm0; m1 = nm1;
+    }
+    const float lse0 = m0 + __logf(l0), lse1 = m1 + __logf(l1);
+    float oacc[DN][4];
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn) { oacc[dn][0] = 0.f; oacc[dn][1] = 0.f; oacc[dn][2] = 0.f; oacc[dn][3] = 0.f; }
+    for (int np = 0; np < ntiles; ++np) {
+      float pp[2][4];
+#pragma unroll
+      for (int hh = 0; hh < 2; ++hh) {
+        const int nt = np * 2 + hh;
+        float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < KS; ++ks) {
+          uint32_t kb[2];
+          ldsm_x2(kb, Ks + (size_t)(nt * 8 + (lane & 7)) * STR + ks * 16 + ((lane >> 3) & 1) * 8);
+          mma16816(c, qa[ks], kb);
+        }
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const bool ok = nt * 8 + 2 * t + e < L;
+          pp[hh][e] = ok ? __expf(c[e] * scale - lse0) : 0.f;
+          pp[hh][2 + e] = ok ? __expf(c[2 + e] * scale - lse1) : 0.f;
+        }
+      }
+      uint32_t pa[4] = {pack_bf16x2(pp[0][0], pp[0][1]), pack_bf16x2(pp[0][2], pp[0][3]), pack_bf16x2(pp[1][0], pp[1][1]),
+                        pack_bf16x2(pp[1][2], pp[1][3])};
+#pragma unroll
+      for (int dn = 0; dn < DN; ++dn) {
+        uint32_t vb[2];
+        ldsm_x2_trans(vb, Vs + (size_t)(np * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * STR + dn * 8);
+        mma16816(oacc[dn], pa, vb);
+      }
+    }
+    const int row_a = r0 + g, row_b = r0 + g + 8;
+#pragma unroll
+    for (int dn = 0; dn < DN; ++dn) {
+      const int col = h * HD + dn * 8 + 2 * t;
+      if (row_a < L) *reinterpret_cast<uint32_t*>(out + ((size_t)b * L + row_a) * C + col) = pack_bf16x2(oacc[dn][0], oacc[dn][1]);
+      if (row_b < L) *reinterpret_cast<uint32_t*>(out + ((size_t)b * L + row_b) * C + col) = pack_bf16x2(oacc[dn][2], oacc[dn][3]);
+    }
+  }
+}
+template <int HD> bool launch_sdpa_fwd_mma_t(const bf16* qkv, bf16* out, int B, int L, int C, int heads, cudaStream_t s) {
+  const int Lp = (L + 15) / 16 * 16;
+  const int gpb = Lp <= 16 ? 4 : 1;
+  const size_t region = (size_t)3 * Lp * (HD + 8) * sizeof(bf16);
+  const size_t smem = region * gpb;
+  if (smem > 200 * 1024) return false;
+  static bool attr_set = false;
+  if (!attr_set) { cudaFuncSetAttribute(sdpa_fwd_mma_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024); attr_set = true; }
+  const int n_groups = B * heads;
+  sdpa_fwd_mma_kernel<HD><<<(n_groups + gpb - 1) / gpb, 128, smem, s>>>(qkv, out, n_groups, L, Lp, C, heads, gpb);
+  return true;
+}
+
 template <int HD> bool launch_sdpa_bwd_mma(const bf16* qkv, const bf16* o, const bf16* d_o, bf16* d_qkv, int B, int L, int C, int heads, cudaStream_t s) {
   const int Lp = (L + 15) / 16 * 16;
   const int gpb = Lp <= 16 ? 4 : 1;
@@ -1695,7 +1817,8 @@ __global__ void __launch_bounds__(192) enc_conv1_fwd_kernel(const float* __restr
 __global__ void __launch_bounds__(192) enc_conv1_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ d1, float* __restrict__ dw1,
                                                               float* __restrict__ db1, int n_strips) {
   __shared__ __align__(16) float s_in[24 * 100];
-  __shared__ __align__(16) float s_d[192 * 16];   // [yl][x][16]
+  constexpr int SDS = 193;                        // padded row stride of s_d: [16 channels][192 raster pixels]
+  __shared__ __align__(16) float s_d[16 * SDS];
   const int tid = threadIdx.x;
   const int op = tid & 7, c = (tid >> 3) % 3, pg = tid / 24;   // outputs 2*op, 2*op+1; channel c; pixels pg, pg+8, ...
   const int kk2 = tid & 3, kk3 = (tid >> 2) & 3, c3 = tid >> 4;
@@ -1708,24 +1831,24 @@ __global__ void __launch_bounds__(192) enc_conv1_wgrad_kernel(const float* __res
     {
       float t8[8];
       const bf16* src = d1 + ((size_t)strip * 192 + tid) * 16;
-      float* dst = s_d + (my_yl * 48 + my_x) * 16;
+      float* dst = s_d + my_yl * 48 + my_x;   // channel-major: a warp's stores of one channel hit (nearly) distinct banks
       load8(src, t8);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dst[i] = t8[i];
+      for (int i = 0; i < 8; ++i) dst[i * SDS] = t8[i];
       load8(src + 8, t8);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) dst[8 + i] = t8[i];
+      for (int i = 0; i < 8; ++i) dst[(8 + i) * SDS] = t8[i];
     }
     __syncthreads();
 #pragma unroll
     for (int yl = 0; yl < 4; ++yl) {
       const float* r0 = s_in + (c * 8 + 2 * yl) * 100 + 3;
       const float* r1 = r0 + 100;
-      const float* dd = s_d + yl * 48 * 16 + 2 * op;
+      const float* dd = s_d + (2 * op) * SDS + yl * 48;
 #pragma unroll
       for (int j = 0; j < 6; ++j) {
         const int x = pg + 8 * j;
-        const float2 d = *reinterpret_cast<const float2*>(dd + x * 16);
+        const float2 d = make_float2(dd[x], dd[SDS + x]);
         const float i00 = r0[2 * x], i01 = r0[2 * x + 1], i10 = r1[2 * x], i11 = r1[2 * x + 1];
         acc[0][0] = fmaf(d.x, i00, acc[0][0]); acc[0][1] = fmaf(d.x, i01, acc[0][1]);
         acc[0][2] = fmaf(d.x, i10, acc[0][2]); acc[0][3] = fmaf(d.x, i11, acc[0][3]);
@@ -1855,4 +1978,15 @@ void launch_enc_pack_linear_T16(const float* w, bf16* out, cudaStream_t s) {
 void launch_enc_unpack_grads(const float* g2, const float* g3, const float* gb2, float* dw2, float* db2, float* dw3, cudaStream_t s) {
   enc_unpack_grads_kernel<<<cdiv(64 * 128, 256), 256, 0, s>>>(g2, g3, gb2, dw2, db2, dw3);
   COUNT_LAUNCH();
+}
+
+// bf16 attention core forward on mma.sync (training forward); returns false when the shape does not fit shared memory
+bool launch_sdpa_fwd_mma(const bf16* qkv, bf16* out, int B, int L, int C, int heads, cudaStream_t s) {
+  const int hd = C / heads;
+  bool done = false;
+  if (hd == 16) done = launch_sdpa_fwd_mma_t<16>(qkv, out, B, L, C, heads, s);
+  else if (hd == 32) done = launch_sdpa_fwd_mma_t<32>(qkv, out, B, L, C, heads, s);
+  else if (hd == 64) done = launch_sdpa_fwd_mma_t<64>(qkv, out, B, L, C, heads, s);
+  if (done) COUNT_LAUNCH();
+  return done;
 }

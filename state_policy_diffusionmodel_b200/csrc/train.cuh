@@ -54,6 +54,7 @@ void launch_layernorm_bwd(const T* dy, int ld_dy, const T* x, int ld_x, const fl
                           float* dgamma, float* dbeta, long long M, int C, cudaStream_t s);
 // attention core backward: qkv [B*L][3C], o = forward output [B*L][C], d_o [B*L][C] -> d_qkv [B*L][3C]
 template <typename T> void launch_sdpa_bwd(const T* qkv, const T* o, const T* d_o, T* d_qkv, int B, int L, int C, int heads, cudaStream_t s);
+bool launch_sdpa_fwd_mma(const bf16* qkv, bf16* out, int B, int L, int C, int heads, cudaStream_t s);  // bf16, mma.sync; false = shape too large
 template <typename T> void launch_gelu_fwd(const T* x, T* y, long long n, cudaStream_t s);              // y = gelu(x)
 template <typename T> void launch_gelu_bwd(const T* dy, const T* pre, T* dx, long long n, cudaStream_t s);  // dx = dy * gelu'(pre)
 

@@ -235,7 +235,13 @@ template <typename T> struct Train {
     a.qkv = A(level, 3 * C);
     f.gemm(name + ".attention.in_proj_weight", a.h1, C, level, a.qkv, 3 * C, EPI_BIAS);
     a.attn = A(level, C);
-    launch_sdpa<T>(a.qkv, a.attn, B, L, C, 4, s);
+    bool mma_done = false;
+    if constexpr (sizeof(T) == 2) {
+      static int simt = -1;  // SPDM_SDPA_FWD_SIMT=1: CUDA-core forward core (A/B switch)
+      if (simt < 0) { const char* e = getenv("SPDM_SDPA_FWD_SIMT"); simt = e ? atoi(e) : 0; }
+      if (!simt) mma_done = launch_sdpa_fwd_mma(reinterpret_cast<const bf16*>(a.qkv), reinterpret_cast<bf16*>(a.attn), B, L, C, 4, s);
+    }
+    if (!mma_done) launch_sdpa<T>(a.qkv, a.attn, B, L, C, 4, s);
     a.a = A(level, C);
     f.gemm(name + ".attention.out_proj.weight", a.attn, C, level, a.a, C, EPI_BIAS | EPI_RESID, x, ld_x);
     a.f0 = A(level, C);
@@ -659,7 +665,9 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     launch_relu_mask(d2, c2, d2, M2 * 64, gb2, s);
     wg(c1p, 64, d2, 64, M2, 64, 64, g2);
     bf16* d1 = H16((size_t)M2 * 64);
-    tc_flat("d_c1", d2, 64, tr->enc_w2pT, 64, 64, M2, d1, 64, nullptr, EPI_MASK, c1p, 64);  // ReLU' of conv1 in the epilogue
+    tc_flat("d_c1", d2, 64, tr->enc_w2pT, 64, 64, M2, d1, 64, nullptr, 0);
+    // (ReLU' in the GEMM epilogue -- EPI_MASK -- was measured slower: 457 us vs 182 + 130 us for GEMM + this streaming kernel)
+    launch_relu_mask(d1, c1p, d1, M2 * 64, nullptr, s);
     launch_enc_conv1_wgrad(images, d1, G("vision_encoder.0.weight"), G("vision_encoder.0.bias"), n_frames, s);
     {  // gb2 was accumulated on the main stream (relu mask), g2 / g3 on the side stream: unpack there, after this point of main
       cudaStream_t us = fork();
