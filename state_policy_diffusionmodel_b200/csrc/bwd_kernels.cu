@@ -260,60 +260,77 @@ __global__ void __launch_bounds__(512) gn_bwd_cached_kernel(GnBwdArgs a, int CS)
     for (int i = 0; i < 8; ++i) o[i] = rstd * (gg[k][i] - m1 - xh[k][i] * m2);
     store8(dx + ((size_t)b * a.HW + row) * a.ld_dx + c8, o);
   }
-  // per-channel sums: tree over the row groups (threads tid and tid + stride share their channels when vpr | stride)
-  auto reduce_channels = [&](const float (&acc)[8], float (&out)[8]) {
-    __syncthreads();
+  // per-channel sums of the four quantities in one pass: fold lanes that share channels inside each warp with shuffles, park
+  // one row per warp (or per warp segment when vpr < 32) in shared memory, then vpr threads per quantity add the rows up.
+  //   red layout: [quantity q][row r][vpr][8]
+  const int seg = vpr < 32 ? vpr : 32;          // lanes l and l + seg (+ 2 seg ...) of a warp hold the same channels
 #pragma unroll
-    for (int i = 0; i < 8; ++i) red[tid * 8 + i] = acc[i];
-    __syncthreads();
-    for (int stride = nthreads >> 1; stride >= vpr; stride >>= 1) {
-      if (tid < stride) {
+  for (int off = 16; off >= 1; off >>= 1) {
+    if (off >= seg) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) red[tid * 8 + i] += red[(tid + stride) * 8 + i];
+      for (int i = 0; i < 8; ++i) {
+        acc_dg[i] += __shfl_xor_sync(0xffffffffu, acc_dg[i], off);
+        acc_db[i] += __shfl_xor_sync(0xffffffffu, acc_db[i], off);
+        acc_fb[i] += __shfl_xor_sync(0xffffffffu, acc_fb[i], off);
+        acc_fs[i] += __shfl_xor_sync(0xffffffffu, acc_fs[i], off);
       }
-      __syncthreads();
     }
-    if (tid < vpr) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) out[i] = red[tid * 8 + i];
-    }
-  };
-  float tot[8];
+  }
+  // after the fold, lanes 0..seg-1 of every warp hold the warp's sums for channel group (tid % vpr)
+  const int lane = tid & 31, warp = tid >> 5;
+  const int rows_per_q = (nthreads * seg / 32) / vpr;   // partial rows per quantity
+  const size_t qstride = (size_t)rows_per_q * vpr * 8;
   const bool use_part = a.part != nullptr && CS == 1;
-  reduce_channels(acc_dg, tot);
-  if (tid < vpr) {
-    if (use_part) store8(a.part + (size_t)b * 2 * a.C + c8, tot);
-    else {
+  const int n_pass = (has_film || has_temb) ? 2 : 1;    // pass 0: (d gamma, d beta); pass 1: (sum dy, sum dy*(gn+temb))
+  for (int pass = 0; pass < n_pass; ++pass) {
+    __syncthreads();
+    if (lane < seg) {
+      const int cgp = (warp * 32 + lane) % vpr;
+      const int r = (warp * seg) / vpr;
+      float* dst = red + ((size_t)r * vpr + cgp) * 8;
 #pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(a.dgamma + c8 + i, tot[i]);
-    }
-  }
-  reduce_channels(acc_db, tot);
-  if (tid < vpr) {
-    if (use_part) store8(a.part + (size_t)b * 2 * a.C + a.C + c8, tot);
-    else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) atomicAdd(a.dbeta + c8 + i, tot[i]);
-    }
-  }
-  if (has_film || has_temb) {   // per-sample outputs: accumulated too (the step zeroes d_film / d_temb), CS CTAs contribute
-    reduce_channels(acc_fb, tot);
-    if (tid < vpr) {
-      if (has_film) {
-        float* dst = a.d_film + (size_t)b * SPDM_FILM_WIDTH + a.film_off + a.C + c8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(dst + i, tot[i]);
-      }
-      if (has_temb) {
-        float* dst = a.d_temb + (size_t)b * SPDM_TEMB_WIDTH + a.temb_off + c8;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) atomicAdd(dst + i, tot[i] * fs[i]);
+      for (int i = 0; i < 8; ++i) {
+        dst[i] = pass == 0 ? acc_dg[i] : acc_fb[i];
+        dst[qstride + i] = pass == 0 ? acc_db[i] : acc_fs[i];
       }
     }
-    if (has_film) {
-      reduce_channels(acc_fs, tot);
-      if (tid < vpr) {
-        float* dst = a.d_film + (size_t)b * SPDM_FILM_WIDTH + a.film_off + c8;
+    __syncthreads();
+    if (tid < 2 * vpr) {
+      const int qi = 2 * pass + tid / vpr, cgp = tid % vpr;
+      float tot[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      for (int r = 0; r < rows_per_q; ++r) {
+        const float* src = red + (qi & 1) * qstride + ((size_t)r * vpr + cgp) * 8;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tot[i] += src[i];
+      }
+      const int cc = cgp << 3;
+      if (qi == 0) {
+        if (use_part) store8(a.part + (size_t)b * 2 * a.C + cc, tot);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(a.dgamma + cc + i, tot[i]);
+        }
+      } else if (qi == 1) {
+        if (use_part) store8(a.part + (size_t)b * 2 * a.C + a.C + cc, tot);
+        else {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(a.dbeta + cc + i, tot[i]);
+        }
+      } else if (qi == 2) {   // sum_hw dy: FiLM bias gradient and (times the FiLM scale) the time-embedding gradient
+        if (has_film) {
+          float* dst = a.d_film + (size_t)b * SPDM_FILM_WIDTH + a.film_off + a.C + cc;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(dst + i, tot[i]);
+        }
+        if (has_temb) {
+          float fsc[8] = {1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f, 1.f};
+          if (has_film) load8(a.film + (size_t)b * SPDM_FILM_WIDTH + a.film_off + cc, fsc);
+          float* dst = a.d_temb + (size_t)b * SPDM_TEMB_WIDTH + a.temb_off + cc;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) atomicAdd(dst + i, tot[i] * fsc[i]);
+        }
+      } else if (has_film) {  // sum_hw dy * (gn + temb): FiLM scale gradient
+        float* dst = a.d_film + (size_t)b * SPDM_FILM_WIDTH + a.film_off + cc;
 #pragma unroll
         for (int i = 0; i < 8; ++i) atomicAdd(dst + i, tot[i]);
       }
@@ -325,7 +342,7 @@ template <typename T, int VPT> void launch_gn_cached(const GnBwdArgs& a, int B, 
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(B * CS);
   cfg.blockDim = dim3(threads);
-  cfg.dynamicSmemBytes = (size_t)threads * 8 * sizeof(float);
+  cfg.dynamicSmemBytes = (size_t)2 * threads * 8 * sizeof(float);  // two quantities per pass, <= one row per warp segment
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
