@@ -122,6 +122,10 @@ int spdm_train_fwd_bwd(spdm_plan* plan, const float* images, const float* positi
                        const float* velocity, const float* x0, const float* noise, const int64_t* t,
                        const float* sqrt_ab, const float* sqrt_1mab, const float* inpaint, float* loss_out,
                        int32_t B, void* stream);
+/* Data-parallel overlap: make `stream` wait until every gradient of completion phase `phase` of the latest
+ * spdm_train_fwd_bwd is final.  Phase 0: outc, sa4-sa6, up1-up3 (convs, norms, attention); phase 1: the rest of the U-Net
+ * except the emb_layer / cond_encoder Linears; phase 2: everything (those Linears and the vision encoder). */
+int spdm_train_wait_phase(spdm_plan* plan, int32_t phase, void* stream);
 /* torch.nn.utils.clip_grad_norm_(max_norm) (Lightning gradient_clip_val=0.5, train.py:107; max_norm <= 0: off) followed
  * by torch.optim.Adam.step() (ddpm:115-125) over n floats; `step` counts from 1; grad_scale multiplies the gradient first
  * (1/world_size after a summing all-reduce); scratch = one device float. */

@@ -32,6 +32,9 @@ struct TrainState {
   cudaEvent_t ev_join = nullptr;
   cudaEvent_t ev_packs = nullptr, ev_packs_fork = nullptr;  // U-Net weight repacks run on the side stream, under the encoder forward
   bool packs_pending = false;
+  // gradient-completion phases for overlapped data-parallel all-reduces: 0 = up path + outc + sa4-6 done, 1 = everything of the
+  // U-Net except the time-embedding / FiLM Linears done, 2 = all gradients done (same point as the end of the step)
+  cudaEvent_t ev_phase[3] = {nullptr, nullptr, nullptr};
   bool use_side = true;       // SPDM_TRAIN_SIDE=0 switches it off (A/B)
   bool dgrad_swap = true;     // SPDM_DGRAD_SWAP=0: plain N = Cout tiles for the narrow data gradients (A/B)
   bool wgrad_simt = false;    // SPDM_WGRAD_SIMT=1: CUDA-core weight gradients on the bf16 path too (A/B switch)
@@ -45,6 +48,7 @@ void train_destroy(spdm_plan* p) {
   for (void* q : p->tr->bufs) cudaFree(q);
   for (cudaEvent_t e : p->tr->evs) cudaEventDestroy(e);
   if (p->tr->ev_join) cudaEventDestroy(p->tr->ev_join);
+  for (cudaEvent_t e : p->tr->ev_phase) if (e) cudaEventDestroy(e);
   if (p->tr->ev_packs) cudaEventDestroy(p->tr->ev_packs);
   if (p->tr->ev_packs_fork) cudaEventDestroy(p->tr->ev_packs_fork);
   if (p->tr->side) cudaStreamDestroy(p->tr->side);
@@ -123,6 +127,12 @@ template <typename T> struct Train {
     CUDA_OK(cudaEventRecord(e, s));
     CUDA_OK(cudaStreamWaitEvent(tr->side, e, 0));
     return tr->side;
+  }
+
+  // every gradient of phase `ph` has been enqueued (main or side stream): record the event a communication stream can wait on
+  void mark_phase(int ph) {
+    cudaStream_t sd = fork_side();  // the side stream now also waits for the main stream's work up to here
+    CUDA_OK(cudaEventRecord(tr->ev_phase[ph], sd));
   }
 
   // ---- weight / bias gradients ----
@@ -378,6 +388,7 @@ template <typename T> struct Train {
       launch_upsample_bwd<T>(d_cats[i], st.cin, d_low, c_lows[i], B, p->levelH(l + 1), p->levelW(l + 1), c_lows[i], s);
       d_cur = d_low;
     }
+    mark_phase(0);
     // d_cur = d x5
     T* d_b2o = A(3, 512); T* d_b1o = A(3, 512); T* d_x4 = A(3, 256);
     dc_bwd(bot3, d_cur, 256, d_b2o, 512);
@@ -403,6 +414,7 @@ template <typename T> struct Train {
       d_cur = d_in;
     }
     dc_bwd(inc, d_cur, 64, nullptr, 0, x_noisy);
+    mark_phase(1);
 
     // ---- time-embedding Linears (Unet_FiLmLayer.py:136-142,165-168) ----
     cudaStream_t s = fork_side();
@@ -448,6 +460,7 @@ extern "C" int spdm_train_enable(spdm_plan* p) {
   CUDA_OK(cudaStreamCreateWithFlags(&tr->side, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&tr->ev_join, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&tr->ev_packs, cudaEventDisableTiming));
+  for (int i = 0; i < 3; ++i) CUDA_OK(cudaEventCreateWithFlags(&tr->ev_phase[i], cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&tr->ev_packs_fork, cudaEventDisableTiming));
   if (p->bf16_mode && !tr->enc_simt) {
     tr->enc_w2p = p->alloc<bf16>(64 * 64); tr->enc_w2pT = p->alloc<bf16>(64 * 64);
@@ -698,6 +711,7 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     CUDA_OK(cudaEventRecord(tr->ev_join, tr->side));
     CUDA_OK(cudaStreamWaitEvent(s, tr->ev_join, 0));
   }
+  CUDA_OK(cudaEventRecord(tr->ev_phase[2], s));
   CUDA_OK(cudaMemcpyAsync(loss_out, tr->loss_dev, sizeof(float), cudaMemcpyDeviceToDevice, s));
   p->launches += total_launches() - before;
   check_async("train_fwd_bwd");
@@ -720,6 +734,17 @@ extern "C" int spdm_adam_step(float* params, float* grads, float* m, float* v, i
   }
   launch_adam(params, grads, m, v, n, lr, beta1, beta2, eps, step, sumsq, max_norm, grad_scale, s);
   check_async("adam_step");
+  return 0;
+  API_END
+}
+
+// Makes `stream` wait for gradient-completion phase `phase` (0, 1, 2) of the most recent spdm_train_fwd_bwd: a communication
+// stream calls this before all-reducing the matching slice of the flat gradient buffer, so the all-reduce of the up-path
+// gradients runs under the rest of the backward pass.  Phase membership of a tensor: see engine.py::_grad_phase.
+extern "C" int spdm_train_wait_phase(spdm_plan* p, int32_t phase, void* stream) {
+  API_BEGIN
+  REQUIRE(p && p->tr && phase >= 0 && phase < 3, "bad argument");
+  CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, p->tr->ev_phase[phase], 0));
   return 0;
   API_END
 }

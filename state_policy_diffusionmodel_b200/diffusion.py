@@ -264,10 +264,9 @@ class Diffusion_DDPM(_Base):
         self._enc_tag = None
 
     def allreduce_gradients(self, group=None):
-        """Data-parallel training: one NCCL all-reduce (sum) over the flat gradient buffer.  Returns the factor
-        (1 / world_size) that `optimizer_step` folds into the update."""
-        from .distributed import allreduce_sum_
-        return allreduce_sum_(self._tplan.grads_flat, group=group)
+        """Data-parallel training: NCCL all-reduce (sum) of the flat gradient buffer in three completion-phase buckets that
+        overlap the backward pass.  Returns the factor (1 / world_size) that `optimizer_step` folds into the update."""
+        return self._tplan.allreduce_gradients(group=group)
 
     def optimizer_step(self, lr=None, betas=(0.9, 0.999), eps=1e-8, gradient_clip_val=0.5, grad_scale=1.0):
         """Fused clip_grad_norm_(gradient_clip_val) + Adam over all parameters (one kernel pair on the flat buffers);

@@ -28,6 +28,15 @@ def _f32c(t, device):
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+def _grad_phase(name):
+    """When, inside the backward pass, the gradient of parameter `name` is final (spdm_train_wait_phase): 0 = up path
+    (outc, sa4-6, up1-3), 1 = bottleneck + down path, 2 = time-embedding / FiLM Linears and the vision encoder (they need the
+    gradients of every stage)."""
+    if name.startswith("vision_encoder.") or ".emb_layer." in name or ".cond_encoder." in name:
+        return 2
+    return 0 if name.split(".")[0] in ("outc", "sa4", "sa5", "sa6", "up1", "up2", "up3") else 1
+
+
 class DenoisePlan:
     def __init__(self, attention=True, precision="bf16", batch_max=1, rows=31, dim=5, obs_horizon=10, cond_dim=135,
                  inpaint_rows=1, time_dim=256, device=None, graph_steps=1, scheduler_only=False, split=1):
@@ -211,10 +220,16 @@ class DenoisePlan:
         returns {name: (offset, shape)}."""
         with torch.cuda.device(self.device):
             _lib.check(self.lib.spdm_train_enable(self._h))
+            # flat layout in gradient-completion order, so that each phase is one contiguous slice (bucket) of the buffer
             self.train_offsets, off = {}, 0
-            for name, t in named_tensors.items():
-                self.train_offsets[name] = (off, tuple(t.shape))
-                off += (t.numel() + 3) // 4 * 4
+            self.train_buckets = []
+            for phase in (0, 1, 2):
+                lo = off
+                for name, t in named_tensors.items():
+                    if _grad_phase(name) == phase:
+                        self.train_offsets[name] = (off, tuple(t.shape))
+                        off += (t.numel() + 3) // 4 * 4
+                self.train_buckets.append((lo, off))
             self.train_total = off
             self.params_flat = torch.zeros(off, device=self.device, dtype=torch.float32)
             self.grads_flat = torch.zeros_like(self.params_flat)
@@ -242,6 +257,26 @@ class DenoisePlan:
 
     def grad_view(self, name):
         return self.param_view(name, self.grads_flat)
+
+    def allreduce_gradients(self, group=None, comm_stream=None):
+        """Data-parallel step: summing all-reduce of the flat gradient buffer in its three completion-phase buckets, each
+        enqueued on `comm_stream` behind the event that marks its gradients final, so the first two run under the rest of the
+        backward pass.  Returns 1 / world_size (fold it into `adam_step(grad_scale=...)`)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return 1.0
+        if comm_stream is None:
+            if getattr(self, "_comm_stream", None) is None:
+                self._comm_stream = torch.cuda.Stream(device=self.device)
+            comm_stream = self._comm_stream
+        cur = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device), torch.cuda.stream(comm_stream):
+            for phase, (lo, hi) in enumerate(self.train_buckets):
+                if hi > lo:
+                    _lib.check(self.lib.spdm_train_wait_phase(self._h, phase, ctypes.c_void_p(comm_stream.cuda_stream)))
+                    dist.all_reduce(self.grads_flat[lo:hi], op=dist.ReduceOp.SUM, group=group)
+        cur.wait_stream(comm_stream)
+        return 1.0 / dist.get_world_size(group)
 
     def sync_weights(self):
         """Repack the flat fp32 parameters into the kernel layouts (forward operands and data-gradient twins)."""
