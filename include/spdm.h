@@ -122,6 +122,9 @@ int spdm_train_fwd_bwd(spdm_plan* plan, const float* images, const float* positi
                        const float* velocity, const float* x0, const float* noise, const int64_t* t,
                        const float* sqrt_ab, const float* sqrt_1mab, const float* inpaint, float* loss_out,
                        int32_t B, void* stream);
+/* `images` of the next spdm_train_fwd_bwd calls is a strided view: frame (b, t) at images + b*stride + t*3*96*96 floats
+ * (0 = contiguous).  The reference slices the observation window out of the full recording (ddpm:283-298). bf16 plans only. */
+int spdm_train_set_image_stride(spdm_plan* plan, int64_t stride);
 /* Data-parallel overlap: make `stream` wait until every gradient of completion phase `phase` of the latest
  * spdm_train_fwd_bwd is final.  Phase 0: outc, sa4-sa6, up1-up3 (convs, norms, attention); phase 1: the rest of the U-Net
  * except the emb_layer / cond_encoder Linears; phase 2: everything (those Linears and the vision encoder). */

@@ -47,6 +47,7 @@ _PROTOTYPES = {
     "spdm_train_set_buffers": (_c.c_int, [_P, _P, _P, _c.c_int64]),
     "spdm_train_sync_weights": (_c.c_int, [_P, _P]),
     "spdm_train_fwd_bwd": (_c.c_int, [_P] + [_P] * 11 + [_c.c_int32, _P]),
+    "spdm_train_set_image_stride": (_c.c_int, [_P, _c.c_int64]),
     "spdm_train_wait_phase": (_c.c_int, [_P, _c.c_int32, _P]),
     "spdm_adam_step": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_int32,
                                   _c.c_float, _c.c_float, _P, _P]),

@@ -1786,13 +1786,13 @@ __device__ __forceinline__ void enc_stage_strip(const float* __restrict__ im, in
 
 // one block per (frame, conv3 row r3): 192 conv1 pixels, one thread each, 16 channels per thread
 __global__ void __launch_bounds__(192) enc_conv1_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w1, const float* __restrict__ b1,
-                                                            bf16* __restrict__ c1p) {
+                                                            bf16* __restrict__ c1p, int T, long long bstride) {
   __shared__ __align__(16) float s_in[24 * 100];
   __shared__ __align__(16) float w1s[12 * 16];
   __shared__ __align__(16) float b1s[16];
   const int tid = threadIdx.x;
   const int frame = blockIdx.x / 12, r3 = blockIdx.x % 12;
-  const float* im = img + (size_t)frame * 3 * 96 * 96;
+  const float* im = img + (size_t)(frame / T) * bstride + (size_t)(frame % T) * 3 * 96 * 96;  // frame = b*T + t; samples bstride apart
   w1s[tid] = __ldg(w1 + (tid & 15) * 12 + (tid >> 4));
   if (tid < 16) b1s[tid] = __ldg(b1 + tid);
   enc_stage_strip(im, r3, s_in, tid);
@@ -1832,7 +1832,7 @@ __global__ void __launch_bounds__(192) enc_conv1_fwd_kernel(const float* __restr
 // thread = pixel group pg (8) x input channel c (3) x output pair op (8); partial tiles are folded through shared memory once,
 // at the end of the kernel, then one atomicAdd per weight per block.
 __global__ void __launch_bounds__(192) enc_conv1_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ d1, float* __restrict__ dw1,
-                                                              float* __restrict__ db1, int n_strips) {
+                                                              float* __restrict__ db1, int n_strips, int T, long long bstride) {
   __shared__ __align__(16) float s_in[24 * 100];
   constexpr int SDS = 193;                        // padded row stride of s_d: [16 channels][192 raster pixels]
   __shared__ __align__(16) float s_d[16 * SDS];
@@ -1844,7 +1844,7 @@ __global__ void __launch_bounds__(192) enc_conv1_wgrad_kernel(const float* __res
   for (int strip = blockIdx.x; strip < n_strips; strip += gridDim.x) {
     const int frame = strip / 12, r3 = strip % 12;
     __syncthreads();
-    enc_stage_strip(img + (size_t)frame * 3 * 96 * 96, r3, s_in, tid);
+    enc_stage_strip(img + (size_t)(frame / T) * bstride + (size_t)(frame % T) * 3 * 96 * 96, r3, s_in, tid);
     {
       float t8[8];
       const bf16* src = d1 + ((size_t)strip * 192 + tid) * 16;
@@ -1969,14 +1969,14 @@ __global__ void enc_unpack_grads_kernel(const float* __restrict__ g2 /*[64][64]*
   if (i < 32) db2[i] += gb2[i];
 }
 }  // namespace
-void launch_enc_conv1_fwd(const float* img, const float* w1, const float* b1, bf16* c1p, int n, cudaStream_t s) {
-  enc_conv1_fwd_kernel<<<n * 12, 192, 0, s>>>(img, w1, b1, c1p);
+void launch_enc_conv1_fwd(const float* img, const float* w1, const float* b1, bf16* c1p, int n, int T, long long bstride, cudaStream_t s) {
+  enc_conv1_fwd_kernel<<<n * 12, 192, 0, s>>>(img, w1, b1, c1p, T, bstride);
   COUNT_LAUNCH();
 }
-void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float* db1, int n, cudaStream_t s) {
+void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float* db1, int n, int T, long long bstride, cudaStream_t s) {
   int grid = n * 12;
   if (grid > 148 * 8) grid = 148 * 8;
-  enc_conv1_wgrad_kernel<<<grid, 192, 0, s>>>(img, d1, dw1, db1, n * 12);
+  enc_conv1_wgrad_kernel<<<grid, 192, 0, s>>>(img, d1, dw1, db1, n * 12, T, bstride);
   COUNT_LAUNCH();
 }
 void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, float* colsum64, cudaStream_t s) {

@@ -85,8 +85,9 @@ void launch_enc_linear_grad_permute(const float* tmp_hwc, float* dwl, cudaStream
 void launch_pack_enc_linear_t(const float* w, float* out, cudaStream_t s);
 
 // ---- vision encoder as patch GEMMs on the tensor cores (bf16 training path; layouts in bwd_kernels.cu) ----------
-void launch_enc_conv1_fwd(const float* img, const float* w1, const float* b1, bf16* c1p, int n, cudaStream_t s);
-void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float* db1, int n, cudaStream_t s);
+// img: frame (b, t) at img + b * bstride + t * 3*96*96 (bstride = T*3*96*96 for a contiguous observation window)
+void launch_enc_conv1_fwd(const float* img, const float* w1, const float* b1, bf16* c1p, int n, int T, long long bstride, cudaStream_t s);
+void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float* db1, int n, int T, long long bstride, cudaStream_t s);
 // over [rows][64] bf16; colsum64 (or null) += column sums of the masked gradient
 void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, float* colsum64, cudaStream_t s);
 void launch_enc_pack_tc(const float* w2, const float* b2, const float* w3, bf16* w2p, bf16* w2pT, bf16* w3p, bf16* w3pT, float* b2p, cudaStream_t s);

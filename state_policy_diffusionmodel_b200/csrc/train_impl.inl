@@ -32,6 +32,7 @@ struct TrainState {
   cudaEvent_t ev_join = nullptr;
   cudaEvent_t ev_packs = nullptr, ev_packs_fork = nullptr;  // U-Net weight repacks run on the side stream, under the encoder forward
   bool packs_pending = false;
+  long long image_bstride = 0;  // elements between samples of `images` (0 = contiguous); spdm_train_set_image_stride
   // gradient-completion phases for overlapped data-parallel all-reduces: 0 = up path + outc + sa4-6 done, 1 = everything of the
   // U-Net except the time-embedding / FiLM Linears done, 2 = all gradients done (same point as the end of the step)
   cudaEvent_t ev_phase[3] = {nullptr, nullptr, nullptr};
@@ -567,6 +568,8 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
                    p->n_elems(), p->cfg.inpaint_rows * p->cfg.dim, B, s);
   // ---- conditioning: encoder -> obs_cond -> Mish -> the six FiLM Linears (ddpm:317-330, Unet_FiLmLayer.py:149-154) ----
   const bool enc_tc = tr->enc_w2p != nullptr;
+  const long long img_bstride = tr->image_bstride > 0 ? tr->image_bstride : (long long)T * 3 * 96 * 96;
+  REQUIRE(enc_tc || img_bstride == (long long)T * 3 * 96 * 96, "a strided observation window needs the bf16 (tensor-core) encoder path");
   const long long n_pad = ((long long)n_frames + 127) / 128 * 128, M2 = (long long)n_frames * 576, M3 = (long long)n_frames * 144;
   auto H16 = [&](size_t n) { return reinterpret_cast<bf16*>(arena_alloc(p, n * sizeof(bf16))); };
   // flat tensor-core GEMM (taps = 1) on `rows` rows: out = epi(in @ w^T)
@@ -590,7 +593,7 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     c2 = H16((size_t)M2 * 64);
     feat16 = H16((size_t)n_pad * 9216);
     bf16* enc_out16 = H16((size_t)n_pad * 128);
-    launch_enc_conv1_fwd(images, p->enc_w1, p->enc_b1, c1p, n_frames, s);
+    launch_enc_conv1_fwd(images, p->enc_w1, p->enc_b1, c1p, n_frames, T, img_bstride, s);
     tc_flat("conv2", c1p, 64, tr->enc_w2p, 64, 64, M2, c2, 64, tr->enc_b2p, EPI_BIAS | EPI_RELU);
     tc_flat("conv3", c2, 256, tr->enc_w3p, 256, 64, M3, feat16, 64, p->enc_b3, EPI_BIAS | EPI_RELU);
     tc_flat("linear", feat16, 9216, p->enc_wl16, 9216, 128, n_pad, enc_out16, 128, p->enc_bl, EPI_BIAS);
@@ -681,7 +684,7 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     tc_flat("d_c1", d2, 64, tr->enc_w2pT, 64, 64, M2, d1, 64, nullptr, 0);
     // (ReLU' in the GEMM epilogue -- EPI_MASK -- was measured slower: 457 us vs 182 + 130 us for GEMM + this streaming kernel)
     launch_relu_mask(d1, c1p, d1, M2 * 64, nullptr, s);
-    launch_enc_conv1_wgrad(images, d1, G("vision_encoder.0.weight"), G("vision_encoder.0.bias"), n_frames, s);
+    launch_enc_conv1_wgrad(images, d1, G("vision_encoder.0.weight"), G("vision_encoder.0.bias"), n_frames, T, img_bstride, s);
     {  // gb2 was accumulated on the main stream (relu mask), g2 / g3 on the side stream: unpack there, after this point of main
       cudaStream_t us = fork();
       launch_enc_unpack_grads(g2, g3, gb2, G("vision_encoder.2.weight"), G("vision_encoder.2.bias"), G("vision_encoder.4.weight"), us);
@@ -745,6 +748,17 @@ extern "C" int spdm_train_wait_phase(spdm_plan* p, int32_t phase, void* stream) 
   API_BEGIN
   REQUIRE(p && p->tr && phase >= 0 && phase < 3, "bad argument");
   CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, p->tr->ev_phase[phase], 0));
+  return 0;
+  API_END
+}
+
+// The observation window handed to spdm_train_fwd_bwd may be a view of a longer recording: frame (b, t) then sits at
+// images + b * stride + t * 3*96*96 (stride in floats; 0 = contiguous (B, T, 3, 96, 96)).  Saves the 566 MB slice copy per step
+// that `batch['image'][:, :obs_horizon]` (models/diffusion_ddpm.py:283-298) otherwise costs.  bf16 path only.
+extern "C" int spdm_train_set_image_stride(spdm_plan* p, int64_t stride) {
+  API_BEGIN
+  REQUIRE(p && p->tr && stride >= 0, "bad argument");
+  p->tr->image_bstride = stride;
   return 0;
   API_END
 }

@@ -352,6 +352,7 @@ class Diffusion_DDPM(_Base):
     # batch-prep helpers (ddpm:283-348)
     # ------------------------------------------------------------------------------------------
     def _slice(self, batch, sl):
+        # .to()/.float() are no-ops for fp32 tensors already on the device: the slices stay views of the caller's batch
         return {k: batch[k][:, sl].to(self.device).float() for k in ('image', 'position', 'action', 'velocity')}
 
     def prepare_observation_batch(self, batch):

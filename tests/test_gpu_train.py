@@ -261,3 +261,31 @@ def test_training_gradients_other_geometries(attention, rows, dim, B, precision)
         den += float((b ** 2).sum())
     assert (num / den) ** 0.5 <= (1e-4 if precision == "fp32" else 1e-2)
     plan.close()
+
+
+def test_strided_observation_window_matches_contiguous():
+    """bf16 path: the observation window passed as a strided view of the full recording (what `batch['image'][:, :10]` is)
+    gives the same gradients as a contiguous copy of it."""
+    import state_policy_diffusionmodel_b200 as spdm
+    sd = fixtures.make_unet_weights(attention=False, seed=0)
+    esd = fixtures.make_encoder_weights()
+    B = 32
+    full, t, noise = _case(B, seed=17)
+    plan = spdm.DenoisePlan(attention=False, precision="bf16", batch_max=B, inpaint_rows=1)
+    plan.enable_training(_named(sd, esd))
+    ac = RefDDPMScheduler(num_train_timesteps=1000, beta_schedule="linear", clip_sample=False).alphas_cumprod
+    dev = {k: v.cuda() for k, v in full.items()}
+    obs = {k: v[:, :10] for k, v in dev.items()}
+    inp = torch.cat([obs["position"][:, -1:], obs["action"][:, -1:]], dim=-1)
+    vec = torch.cat([inp.unsqueeze(1), torch.cat([dev["position"][:, 10:], dev["action"][:, 10:]], dim=-1).unsqueeze(1)], dim=2)
+    outs = []
+    for image in (obs["image"], obs["image"].contiguous()):
+        assert image.is_contiguous() == (len(outs) == 1)
+        loss = plan.train_fwd_bwd(image, obs["position"], obs["action"], obs["velocity"], vec, noise, t, ac ** 0.5, (1 - ac) ** 0.5,
+                                  inpaint=inp.reshape(B, -1))
+        torch.cuda.synchronize()
+        outs.append((float(loss), plan.grads_flat.clone()))
+    assert abs(outs[0][0] - outs[1][0]) <= 1e-6 * abs(outs[1][0])
+    rel = float((outs[0][1] - outs[1][1]).norm() / outs[1][1].norm())
+    assert rel <= 1e-4, rel   # fp32 atomics only
+    plan.close()
