@@ -1763,9 +1763,10 @@ void launch_adam(float* p, float* g, float* m, float* v, long long n, float lr, 
 // Vision encoder on the tensor cores (bf16 training path; models/encoder/autoencoder.py:11-20).
 // k == stride == 2 makes conv2 / conv3 plain GEMMs once the activations are stored patch-major:
 //   c1p [M2 = n*576][64]  : row = ((frame*144 + p3)*4 + kk3) = one 2x2 patch of conv1 pixels, col = kk2*16 + ch
-//   c2  [M2][64] (ch >= 32 are zero padding)  ==  [M3 = n*144][256] : row = conv3 patch p3, col = kk3*64 + ch
+//   c2  [M2/2][64] : row = a PAIR of conv1 patches (kk3 = 2j, 2j+1), col = (kk3 % 2)*32 + ch  ==  [M3 = n*144][128] : row = conv3
+//                    patch p3, col = kk3*32 + ch   (conv2 runs two patches per GEMM row against a block-diagonal weight)
 //   feat [M3][64] == [n][9216] in (pixel, channel) order
-// so conv2 = c1p @ W2p^T (64 -> 64, half of it padding), conv3 = c2 @ W3p^T (256 -> 64), both through conv_tc.cu with a
+// so conv2 = [M2/2][128] c1p @ W2bd^T (128 -> 64), conv3 = c2 @ W3p^T (128 -> 64), both through conv_tc.cu with a
 // bias + ReLU epilogue, and their backward is wgrad_tc.cu + the same GEMM with transposed weights.  What stays on CUDA
 // cores: conv1 (3 -> 16, K = 12), its weight gradient, the ReLU masks and the tiny weight (un)packs.
 // =================================================================================================
@@ -1925,24 +1926,30 @@ __global__ void __launch_bounds__(256) relu_mask_kernel(const bf16* __restrict__
   }
 }
 
-// weight packs of the patch-GEMM encoder (see header of this section)
+// weight packs of the patch-GEMM encoder (see header of this section).  conv2 handles TWO conv1 patches per GEMM row with a
+// block-diagonal weight, so that its 32 output channels fill the 64-wide tile without zero padding:
+//   W2bd[pp*32 + o2][pp'*64 + kk2*16 + c1] = (pp == pp') * W2[o2][c1][kk2]     (64 x 128)
+//   W3p[o][kk3*32 + c2] = W3[o][c2][kk3]                                         (64 x 128)
 __global__ void enc_pack_tc_kernel(const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
                                    bf16* __restrict__ w2p, bf16* __restrict__ w2pT, bf16* __restrict__ w3p, bf16* __restrict__ w3pT,
                                    float* __restrict__ b2p) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 64 * 64) {   // W2p[o][k], k = kk2*16 + c1 ; PyTorch (32,16,2,2): o*64 + c1*4 + kk2
-    const int o = i / 64, k = i % 64, kk2 = k / 16, c1 = k % 16;
-    const float v = o < 32 ? w2[o * 64 + c1 * 4 + kk2] : 0.f;
-    w2p[i] = __float2bfloat16_rn(v);
-    w2pT[k * 64 + o] = __float2bfloat16_rn(v);
+  if (i < 64 * 128) {
+    const int ob = i / 128, kb = i % 128;
+    {
+      const int pp = ob / 32, o2 = ob % 32, pq = kb / 64, k = kb % 64, kk2 = k / 16, c1 = k % 16;
+      const float v = pp == pq ? w2[o2 * 64 + c1 * 4 + kk2] : 0.f;
+      w2p[i] = __float2bfloat16_rn(v);
+      w2pT[kb * 64 + ob] = __float2bfloat16_rn(v);
+    }
+    {
+      const int o = ob, kk3 = kb / 32, c2 = kb % 32;
+      const float v = w3[o * 128 + c2 * 4 + kk3];
+      w3p[i] = __float2bfloat16_rn(v);
+      w3pT[kb * 64 + o] = __float2bfloat16_rn(v);
+    }
   }
-  if (i < 64 * 256) {  // W3p[o][k], k = kk3*64 + c2 (c2 < 32 real) ; PyTorch (64,32,2,2): o*128 + c2*4 + kk3
-    const int o = i / 256, k = i % 256, kk3 = k / 64, c2 = k % 64;
-    const float v = c2 < 32 ? w3[o * 128 + c2 * 4 + kk3] : 0.f;
-    w3p[i] = __float2bfloat16_rn(v);
-    w3pT[k * 64 + o] = __float2bfloat16_rn(v);
-  }
-  if (i < 64) b2p[i] = i < 32 ? b2[i] : 0.f;
+  if (i < 64) b2p[i] = b2[i % 32];
 }
 // (128, 9216 chw) fp32 -> bf16 [9216 hwc][128]  (B operand of d feat = d enc_out @ Wl)
 __global__ void enc_pack_linear_T16_kernel(const float* __restrict__ w, bf16* __restrict__ out) {
@@ -1953,20 +1960,20 @@ __global__ void enc_pack_linear_T16_kernel(const float* __restrict__ w, bf16* __
   const int c = k2 % 64, p = k2 / 64;
   out[i] = __float2bfloat16_rn(w[(size_t)nrow * 9216 + c * 144 + p]);
 }
-// padded patch-GEMM weight gradients -> PyTorch layouts (accumulating)
-__global__ void enc_unpack_grads_kernel(const float* __restrict__ g2 /*[64][64]*/, const float* __restrict__ g3 /*[64][256]*/,
-                                        const float* __restrict__ gb2 /*[64]*/, float* __restrict__ dw2, float* __restrict__ db2,
-                                        float* __restrict__ dw3) {
+// patch-GEMM weight gradients -> PyTorch layouts (accumulating): g2 = d W2bd (64 x 128, the two diagonal blocks are summed,
+// the off-diagonal blocks are cross terms between neighbouring patches and are dropped), g3 = d W3p (64 x 128)
+__global__ void enc_unpack_grads_kernel(const float* __restrict__ g2, const float* __restrict__ g3, const float* __restrict__ gb2 /*[64]*/,
+                                        float* __restrict__ dw2, float* __restrict__ db2, float* __restrict__ dw3) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 32 * 64) {   // dw2 (32,16,2,2): o*64 + c1*4 + kk2
-    const int o = i / 64, r = i % 64, c1 = r / 4, kk2 = r % 4;
-    dw2[i] += g2[o * 64 + kk2 * 16 + c1];
+  if (i < 32 * 64) {   // dw2 (32,16,2,2): o2*64 + c1*4 + kk2
+    const int o2 = i / 64, r = i % 64, c1 = r / 4, kk2 = r % 4;
+    dw2[i] += g2[o2 * 128 + kk2 * 16 + c1] + g2[(32 + o2) * 128 + 64 + kk2 * 16 + c1];
   }
   if (i < 64 * 128) {  // dw3 (64,32,2,2): o*128 + c2*4 + kk3
     const int o = i / 128, r = i % 128, c2 = r / 4, kk3 = r % 4;
-    dw3[i] += g3[o * 256 + kk3 * 64 + c2];
+    dw3[i] += g3[o * 128 + kk3 * 32 + c2];
   }
-  if (i < 32) db2[i] += gb2[i];
+  if (i < 32) db2[i] += gb2[i] + gb2[32 + i];
 }
 }  // namespace
 void launch_enc_conv1_fwd(const float* img, const float* w1, const float* b1, bf16* c1p, int n, int T, long long bstride, cudaStream_t s) {
@@ -1987,7 +1994,7 @@ void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, fl
   COUNT_LAUNCH();
 }
 void launch_enc_pack_tc(const float* w2, const float* b2, const float* w3, bf16* w2p, bf16* w2pT, bf16* w3p, bf16* w3pT, float* b2p, cudaStream_t s) {
-  enc_pack_tc_kernel<<<cdiv(64 * 256, 256), 256, 0, s>>>(w2, b2, w3, w2p, w2pT, w3p, w3pT, b2p);
+  enc_pack_tc_kernel<<<cdiv(64 * 128, 256), 256, 0, s>>>(w2, b2, w3, w2p, w2pT, w3p, w3pT, b2p);
 }
 void launch_enc_pack_linear_T16(const float* w, bf16* out, cudaStream_t s) {
   enc_pack_linear_T16_kernel<<<cdiv(128LL * 9216, 256), 256, 0, s>>>(w, out);

@@ -464,8 +464,8 @@ extern "C" int spdm_train_enable(spdm_plan* p) {
   for (int i = 0; i < 3; ++i) CUDA_OK(cudaEventCreateWithFlags(&tr->ev_phase[i], cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&tr->ev_packs_fork, cudaEventDisableTiming));
   if (p->bf16_mode && !tr->enc_simt) {
-    tr->enc_w2p = p->alloc<bf16>(64 * 64); tr->enc_w2pT = p->alloc<bf16>(64 * 64);
-    tr->enc_w3p = p->alloc<bf16>(64 * 256); tr->enc_w3pT = p->alloc<bf16>(256 * 64);
+    tr->enc_w2p = p->alloc<bf16>(64 * 128); tr->enc_w2pT = p->alloc<bf16>(128 * 64);   // block-diagonal conv2 (two patches per row)
+    tr->enc_w3p = p->alloc<bf16>(64 * 128); tr->enc_w3pT = p->alloc<bf16>(128 * 64);
     tr->enc_wlT16 = p->alloc<bf16>((size_t)9216 * 128);
     tr->enc_b2p = p->alloc<float>(64);
   }
@@ -590,12 +590,12 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
   if (enc_tc) {
     REQUIRE(n_frames % 8 == 0, "bf16 training: B * obs_horizon (%d) must be a multiple of 8", n_frames);
     c1p = H16((size_t)M2 * 64);
-    c2 = H16((size_t)M2 * 64);
+    c2 = H16((size_t)M2 * 32);           // [M2/2][64] == [M3][128]
     feat16 = H16((size_t)n_pad * 9216);
     bf16* enc_out16 = H16((size_t)n_pad * 128);
     launch_enc_conv1_fwd(images, p->enc_w1, p->enc_b1, c1p, n_frames, T, img_bstride, s);
-    tc_flat("conv2", c1p, 64, tr->enc_w2p, 64, 64, M2, c2, 64, tr->enc_b2p, EPI_BIAS | EPI_RELU);
-    tc_flat("conv3", c2, 256, tr->enc_w3p, 256, 64, M3, feat16, 64, p->enc_b3, EPI_BIAS | EPI_RELU);
+    tc_flat("conv2", c1p, 128, tr->enc_w2p, 128, 64, M2 / 2, c2, 64, tr->enc_b2p, EPI_BIAS | EPI_RELU);
+    tc_flat("conv3", c2, 128, tr->enc_w3p, 128, 64, M3, feat16, 64, p->enc_b3, EPI_BIAS | EPI_RELU);
     tc_flat("linear", feat16, 9216, p->enc_wl16, 9216, 128, n_pad, enc_out16, 128, p->enc_bl, EPI_BIAS);
     launch_cast_f32(enc_out16, enc_out, (long long)n_frames * 128, s);
   } else {
@@ -666,22 +666,22 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     };
     bf16* d_eo16 = H16((size_t)n_pad * 128);
     launch_cast_bf16(d_enc_out, d_eo16, (long long)n_frames * 128, s);
-    float* tmp = F((size_t)128 * 9216 + 64 * 256 + 64 * 64 + 64);  // hwc-ordered Linear grad | padded conv3 | padded conv2 | padded b2
-    float *g3 = tmp + (size_t)128 * 9216, *g2 = g3 + 64 * 256, *gb2 = g2 + 64 * 64;
-    CUDA_OK(cudaMemsetAsync(tmp, 0, ((size_t)128 * 9216 + 64 * 256 + 64 * 64 + 64) * sizeof(float), s));
+    float* tmp = F((size_t)128 * 9216 + 64 * 128 + 64 * 128 + 64);  // hwc-ordered Linear grad | conv3 | block-diagonal conv2 | paired b2
+    float *g3 = tmp + (size_t)128 * 9216, *g2 = g3 + 64 * 128, *gb2 = g2 + 64 * 128;
+    CUDA_OK(cudaMemsetAsync(tmp, 0, ((size_t)128 * 9216 + 64 * 128 + 64 * 128 + 64) * sizeof(float), s));
     wg(feat16, 9216, d_eo16, 128, n_pad, 9216, 128, tmp);
     launch_enc_linear_grad_permute(tmp, G("vision_encoder.7.weight"), tr->use_side ? tr->side : s);
     launch_colsum<float>(d_enc_out, 128, n_frames, 128, G("vision_encoder.7.bias"), tr->use_side ? tr->side : s);
     bf16* d3 = H16((size_t)n_pad * 9216);   // d feat, then masked in place = gradient of the pre-ReLU conv3 output [M3][64]
     tc_flat("d_feat", d_eo16, 128, tr->enc_wlT16, 128, 9216, n_pad, d3, 9216, nullptr, 0);
     launch_relu_mask(d3, feat16, d3, M3 * 64, G("vision_encoder.4.bias"), s);
-    wg(c2, 256, d3, 64, M3, 256, 64, g3);
-    bf16* d2 = H16((size_t)M2 * 64);        // [M3][256] == [M2][64]
-    tc_flat("d_c2", d3, 64, tr->enc_w3pT, 64, 256, M3, d2, 256, nullptr, 0);
-    launch_relu_mask(d2, c2, d2, M2 * 64, gb2, s);
-    wg(c1p, 64, d2, 64, M2, 64, 64, g2);
+    wg(c2, 128, d3, 64, M3, 128, 64, g3);
+    bf16* d2 = H16((size_t)M2 * 32);        // [M3][128] == [M2/2][64]
+    tc_flat("d_c2", d3, 64, tr->enc_w3pT, 64, 128, M3, d2, 128, nullptr, 0);
+    launch_relu_mask(d2, c2, d2, M2 * 32, gb2, s);
+    wg(c1p, 128, d2, 64, M2 / 2, 128, 64, g2);
     bf16* d1 = H16((size_t)M2 * 64);
-    tc_flat("d_c1", d2, 64, tr->enc_w2pT, 64, 64, M2, d1, 64, nullptr, 0);
+    tc_flat("d_c1", d2, 64, tr->enc_w2pT, 64, 128, M2 / 2, d1, 128, nullptr, 0);
     // (ReLU' in the GEMM epilogue -- EPI_MASK -- was measured slower: 457 us vs 182 + 130 us for GEMM + this streaming kernel)
     launch_relu_mask(d1, c1p, d1, M2 * 64, nullptr, s);
     launch_enc_conv1_wgrad(images, d1, G("vision_encoder.0.weight"), G("vision_encoder.0.bias"), n_frames, T, img_bstride, s);
