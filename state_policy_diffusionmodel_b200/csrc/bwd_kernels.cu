@@ -1930,26 +1930,25 @@ __global__ void __launch_bounds__(256) relu_mask_kernel(const bf16* __restrict__
 // block-diagonal weight, so that its 32 output channels fill the 64-wide tile without zero padding:
 //   W2bd[pp*32 + o2][pp'*64 + kk2*16 + c1] = (pp == pp') * W2[o2][c1][kk2]     (64 x 128)
 //   W3p[o][kk3*32 + c2] = W3[o][c2][kk3]                                         (64 x 128)
-__global__ void enc_pack_tc_kernel(const float* __restrict__ w2, const float* __restrict__ b2, const float* __restrict__ w3,
-                                   bf16* __restrict__ w2p, bf16* __restrict__ w2pT, bf16* __restrict__ w3p, bf16* __restrict__ w3pT,
-                                   float* __restrict__ b2p) {
+__global__ void enc_pack_w2_kernel(const float* __restrict__ w2, bf16* __restrict__ w2p, bf16* __restrict__ w2pT) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < 64 * 128) {
-    const int ob = i / 128, kb = i % 128;
-    {
-      const int pp = ob / 32, o2 = ob % 32, pq = kb / 64, k = kb % 64, kk2 = k / 16, c1 = k % 16;
-      const float v = pp == pq ? w2[o2 * 64 + c1 * 4 + kk2] : 0.f;
-      w2p[i] = __float2bfloat16_rn(v);
-      w2pT[kb * 64 + ob] = __float2bfloat16_rn(v);
-    }
-    {
-      const int o = ob, kk3 = kb / 32, c2 = kb % 32;
-      const float v = w3[o * 128 + c2 * 4 + kk3];
-      w3p[i] = __float2bfloat16_rn(v);
-      w3pT[kb * 64 + o] = __float2bfloat16_rn(v);
-    }
-  }
-  if (i < 64) b2p[i] = b2[i % 32];
+  if (i >= 64 * 128) return;
+  const int ob = i / 128, kb = i % 128;
+  const int pp = ob / 32, o2 = ob % 32, pq = kb / 64, k = kb % 64, kk2 = k / 16, c1 = k % 16;
+  const float v = pp == pq ? w2[o2 * 64 + c1 * 4 + kk2] : 0.f;
+  w2p[i] = __float2bfloat16_rn(v);
+  w2pT[kb * 64 + ob] = __float2bfloat16_rn(v);
+}
+__global__ void enc_pack_w3_kernel(const float* __restrict__ w3, bf16* __restrict__ w3p, bf16* __restrict__ w3pT) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 64 * 128) return;
+  const int o = i / 128, kb = i % 128, kk3 = kb / 32, c2 = kb % 32;
+  const float v = w3[o * 128 + c2 * 4 + kk3];
+  w3p[i] = __float2bfloat16_rn(v);
+  w3pT[kb * 64 + o] = __float2bfloat16_rn(v);
+}
+__global__ void enc_pack_b2_kernel(const float* __restrict__ b2, float* __restrict__ b2p) {
+  if (threadIdx.x < 64) b2p[threadIdx.x] = b2[threadIdx.x % 32];
 }
 // (128, 9216 chw) fp32 -> bf16 [9216 hwc][128]  (B operand of d feat = d enc_out @ Wl)
 __global__ void enc_pack_linear_T16_kernel(const float* __restrict__ w, bf16* __restrict__ out) {
@@ -1993,9 +1992,9 @@ void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, fl
   relu_mask_kernel<<<grid, 256, 0, s>>>(d, act, out, n / 8, colsum64);
   COUNT_LAUNCH();
 }
-void launch_enc_pack_tc(const float* w2, const float* b2, const float* w3, bf16* w2p, bf16* w2pT, bf16* w3p, bf16* w3pT, float* b2p, cudaStream_t s) {
-  enc_pack_tc_kernel<<<cdiv(64 * 128, 256), 256, 0, s>>>(w2, b2, w3, w2p, w2pT, w3p, w3pT, b2p);
-}
+void launch_enc_pack_w2(const float* w2, bf16* w2p, bf16* w2pT, cudaStream_t s) { enc_pack_w2_kernel<<<cdiv(64 * 128, 256), 256, 0, s>>>(w2, w2p, w2pT); }
+void launch_enc_pack_w3(const float* w3, bf16* w3p, bf16* w3pT, cudaStream_t s) { enc_pack_w3_kernel<<<cdiv(64 * 128, 256), 256, 0, s>>>(w3, w3p, w3pT); }
+void launch_enc_pack_b2(const float* b2, float* b2p, cudaStream_t s) { enc_pack_b2_kernel<<<1, 64, 0, s>>>(b2, b2p); }
 void launch_enc_pack_linear_T16(const float* w, bf16* out, cudaStream_t s) {
   enc_pack_linear_T16_kernel<<<cdiv(128LL * 9216, 256), 256, 0, s>>>(w, out);
 }

@@ -95,6 +95,11 @@ struct spdm_plan {
   float *enc_wl = nullptr, *enc_bl = nullptr;  // [9216][128], [128]
   bf16* enc_wl16 = nullptr;                    // bf16 plan: [128][9216] K-major for the tcgen05 GEMM
   bf16* enc_feat16 = nullptr; bf16* enc_out16 = nullptr; TcGemm* enc_tc = nullptr;
+  // bf16 plan: conv2 / conv3 of the encoder as patch GEMMs (layouts: bwd_kernels.cu, "Vision encoder on the tensor cores")
+  bf16 *enc_w2p = nullptr, *enc_w2pT = nullptr, *enc_w3p = nullptr, *enc_w3pT = nullptr;
+  float* enc_b2p = nullptr;
+  bf16 *enc_c1p = nullptr, *enc_c2 = nullptr; TcGemm *enc_tc2 = nullptr, *enc_tc3 = nullptr;
+  bool enc_simt_infer = false;  // SPDM_ENC_SIMT_INFER=1: fused CUDA-core conv stack for inference (A/B switch)
   std::map<std::string, std::function<void(const float*, const int64_t*, int, cudaStream_t)>> loaders;
   std::set<std::string> missing_unet, missing_enc;
 
@@ -336,21 +341,36 @@ void register_weights(spdm_plan* p) {
   p->enc_wl = p->alloc<float>((size_t)9216 * 128);  p->enc_bl = p->alloc<float>(128);
   reg_vec(p, "vision_encoder.0.weight", p->enc_w1, 16 * 3 * 4, p->missing_enc);
   reg_vec(p, "vision_encoder.0.bias", p->enc_b1, 16, p->missing_enc);
+  if (p->bf16_mode) {
+    p->enc_w2p = p->alloc<bf16>(64 * 128); p->enc_w2pT = p->alloc<bf16>(128 * 64);
+    p->enc_w3p = p->alloc<bf16>(64 * 128); p->enc_w3pT = p->alloc<bf16>(128 * 64);
+    p->enc_b2p = p->alloc<float>(64);
+  }
   p->missing_enc.insert("vision_encoder.2.weight");
   {
     float* dst = p->enc_w2;  // stored transposed: [16*4][32]
     p->loaders["vision_encoder.2.weight"] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
       check_shape("vision_encoder.2.weight", shape, ndim, {32, 16, 2, 2});
       launch_pack_linear_f32(src, dst, 32, 64, 32, 0, s);
+      if (p->enc_w2p) launch_enc_pack_w2(src, p->enc_w2p, p->enc_w2pT, s);
     };
   }
-  reg_vec(p, "vision_encoder.2.bias", p->enc_b2, 32, p->missing_enc);
+  p->missing_enc.insert("vision_encoder.2.bias");
+  {
+    float* dst = p->enc_b2;
+    p->loaders["vision_encoder.2.bias"] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
+      check_shape("vision_encoder.2.bias", shape, ndim, {32});
+      CUDA_OK(cudaMemcpyAsync(dst, src, 32 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      if (p->enc_b2p) launch_enc_pack_b2(src, p->enc_b2p, s);
+    };
+  }
   p->missing_enc.insert("vision_encoder.4.weight");
   {
     float* dst = p->enc_w3;  // stored transposed: [32*4][64]
     p->loaders["vision_encoder.4.weight"] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
       check_shape("vision_encoder.4.weight", shape, ndim, {64, 32, 2, 2});
       launch_pack_linear_f32(src, dst, 64, 128, 64, 0, s);
+      if (p->enc_w3p) launch_enc_pack_w3(src, p->enc_w3p, p->enc_w3pT, s);
     };
   }
   reg_vec(p, "vision_encoder.4.bias", p->enc_b3, 64, p->missing_enc);
@@ -879,6 +899,7 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
     if (const char* e = getenv("SPDM_NO_FUSE_APPLY")) p->no_fuse = atoi(e) != 0;
     if (const char* e = getenv("SPDM_FUSE_MODE")) p->fuse_mode = atoi(e);
     if (const char* e = getenv("SPDM_NO_SPLITK")) p->no_splitk = atoi(e) != 0;
+    if (const char* e = getenv("SPDM_ENC_SIMT_INFER")) p->enc_simt_infer = atoi(e) != 0;
     if (p->split < 1) p->split = 1;
     if (p->split > 8) p->split = 8;
     CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
@@ -905,6 +926,8 @@ extern "C" int spdm_plan_destroy(spdm_plan* p) {
   }
   for (auto& kv : p->tc_cache) tc_gemm_destroy(kv.second);
   if (p->enc_tc) tc_gemm_destroy(p->enc_tc);
+  if (p->enc_tc2) tc_gemm_destroy(p->enc_tc2);
+  if (p->enc_tc3) tc_gemm_destroy(p->enc_tc3);
   for (auto& kv : p->sdpa_cache) sdpa_tc_destroy(kv.second);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   for (auto& kv : p->tail_cache) attn_tail_destroy(kv.second);
@@ -983,10 +1006,25 @@ extern "C" int spdm_encode_images(spdm_plan* p, const float* images, float* out,
       p->enc_tc = tc_gemm_create(p->enc_feat16, 9216, p->enc_wl16, 9216, 128, 1, 1, 1, p->enc_chunk);
       REQUIRE(p->enc_tc != nullptr, "encoder GEMM: %s", tc_last_error());
     }
+    if (!p->enc_simt_infer && !p->enc_c1p) {  // conv2 / conv3 as flat tcgen05 GEMMs over patch-major rows
+      const long long rows2 = (long long)p->enc_chunk * 288, rows3 = (long long)p->enc_chunk * 144;
+      p->enc_c1p = p->alloc<bf16>((size_t)p->enc_chunk * 576 * 64);
+      p->enc_c2 = p->alloc<bf16>((size_t)rows2 * 64);
+      p->enc_tc2 = tc_gemm_create(p->enc_c1p, 128, p->enc_w2p, 128, 64, 1, 1, 1, (int)rows2);
+      p->enc_tc3 = tc_gemm_create(p->enc_c2, 128, p->enc_w3p, 128, 64, 1, 1, 1, (int)rows3);
+      REQUIRE(p->enc_tc2 && p->enc_tc3, "encoder conv GEMMs: %s", tc_last_error());
+    }
     for (int f0 = 0; f0 < n; f0 += p->enc_chunk) {
       const int m = n - f0 < p->enc_chunk ? n - f0 : p->enc_chunk;
-      launch_enc_convs<bf16>(images + (size_t)f0 * 3 * 96 * 96, p->enc_w1, p->enc_b1, p->enc_w2, p->enc_b2, p->enc_w3, p->enc_b3,
-                             p->enc_feat16, m, s);
+      if (p->enc_simt_infer) {
+        launch_enc_convs<bf16>(images + (size_t)f0 * 3 * 96 * 96, p->enc_w1, p->enc_b1, p->enc_w2, p->enc_b2, p->enc_w3, p->enc_b3,
+                               p->enc_feat16, m, s);
+      } else {
+        const int m8 = (m + 7) / 8 * 8;  // whole 128-row tiles: 288 * 8 and 144 * 8 rows; rows past m are scratch nobody reads
+        launch_enc_conv1_fwd(images + (size_t)f0 * 3 * 96 * 96, p->enc_w1, p->enc_b1, p->enc_c1p, m, 1, 3 * 96 * 96, s);
+        tc_gemm_launch(p->enc_tc2, p->enc_c2, 64, nullptr, p->enc_b2p, nullptr, 0, EPI_BIAS | EPI_RELU, m8 * 288, s);
+        tc_gemm_launch(p->enc_tc3, p->enc_feat16, 64, nullptr, p->enc_b3, nullptr, 0, EPI_BIAS | EPI_RELU, m8 * 144, s);
+      }
       tc_gemm_launch(p->enc_tc, p->enc_out16, 128, nullptr, p->enc_bl, nullptr, 0, EPI_BIAS, ((m + 127) / 128) * 128, s);
       launch_cast_f32(p->enc_out16, out + (size_t)f0 * 128, (long long)m * 128, s);
     }

@@ -90,7 +90,9 @@ void launch_enc_conv1_fwd(const float* img, const float* w1, const float* b1, bf
 void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float* db1, int n, int T, long long bstride, cudaStream_t s);
 // over [rows][64] bf16; colsum64 (or null) += column sums of the masked gradient
 void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, float* colsum64, cudaStream_t s);
-void launch_enc_pack_tc(const float* w2, const float* b2, const float* w3, bf16* w2p, bf16* w2pT, bf16* w3p, bf16* w3pT, float* b2p, cudaStream_t s);
+void launch_enc_pack_w2(const float* w2, bf16* w2p, bf16* w2pT, cudaStream_t s);  // (32,16,2,2) -> block-diagonal [64][128] and its transpose
+void launch_enc_pack_w3(const float* w3, bf16* w3p, bf16* w3pT, cudaStream_t s);  // (64,32,2,2) -> [64][128] and its transpose
+void launch_enc_pack_b2(const float* b2, float* b2p, cudaStream_t s);             // (32,) -> [64] (one copy per patch of the pair)
 void launch_enc_pack_linear_T16(const float* w, bf16* out, cudaStream_t s);
 void launch_enc_unpack_grads(const float* g2, const float* g3, const float* gb2, float* dw2, float* db2, float* dw3, cudaStream_t s);
 

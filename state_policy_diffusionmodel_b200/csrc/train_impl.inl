@@ -22,8 +22,7 @@ struct TrainState {
   std::map<std::string, size_t> packed_off;
   float* loss_dev = nullptr;
   // bf16 path: vision encoder as patch GEMMs (layouts: bwd_kernels.cu, "Vision encoder on the tensor cores")
-  bf16 *enc_w2p = nullptr, *enc_w2pT = nullptr, *enc_w3p = nullptr, *enc_w3pT = nullptr, *enc_wlT16 = nullptr;
-  float* enc_b2p = nullptr;
+  bf16* enc_wlT16 = nullptr;  // conv2 / conv3 packs live in the plan (inference uses them too)
   bool enc_simt = false;      // SPDM_ENC_SIMT=1: CUDA-core encoder on the bf16 path too (A/B switch)
   // weight / bias gradients are off the critical path (nothing in the step reads them): they run on a side stream, forked
   // from the main stream after the gradient they consume exists and joined at the end of the step
@@ -464,10 +463,7 @@ extern "C" int spdm_train_enable(spdm_plan* p) {
   for (int i = 0; i < 3; ++i) CUDA_OK(cudaEventCreateWithFlags(&tr->ev_phase[i], cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&tr->ev_packs_fork, cudaEventDisableTiming));
   if (p->bf16_mode && !tr->enc_simt) {
-    tr->enc_w2p = p->alloc<bf16>(64 * 128); tr->enc_w2pT = p->alloc<bf16>(128 * 64);   // block-diagonal conv2 (two patches per row)
-    tr->enc_w3p = p->alloc<bf16>(64 * 128); tr->enc_w3pT = p->alloc<bf16>(128 * 64);
     tr->enc_wlT16 = p->alloc<bf16>((size_t)9216 * 128);
-    tr->enc_b2p = p->alloc<float>(64);
   }
   // every weight has to be uploaded again so that the twins are filled
   for (auto& kv : p->loaders) {
@@ -522,16 +518,10 @@ extern "C" int spdm_train_sync_weights(spdm_plan* p, void* stream) {
     CUDA_OK(cudaEventRecord(p->tr->ev_packs, pack_s));
     p->tr->packs_pending = true;
   }
-  if (p->tr->enc_w2p) {
-    auto P = [&](const char* n) {
-      auto it = p->tr->bind.find(n);
-      REQUIRE(it != p->tr->bind.end(), "training: parameter '%s' is not bound", n);
-      return p->tr->params + it->second.off;
-    };
-    TrainState* tr = p->tr;
-    launch_enc_pack_tc(P("vision_encoder.2.weight"), P("vision_encoder.2.bias"), P("vision_encoder.4.weight"), tr->enc_w2p, tr->enc_w2pT,
-                       tr->enc_w3p, tr->enc_w3pT, tr->enc_b2p, (cudaStream_t)stream);
-    launch_enc_pack_linear_T16(P("vision_encoder.7.weight"), tr->enc_wlT16, (cudaStream_t)stream);
+  if (p->tr->enc_wlT16) {
+    auto it = p->tr->bind.find("vision_encoder.7.weight");
+    REQUIRE(it != p->tr->bind.end(), "training: parameter 'vision_encoder.7.weight' is not bound");
+    launch_enc_pack_linear_T16(p->tr->params + it->second.off, p->tr->enc_wlT16, (cudaStream_t)stream);
   }
   p->temb_table_dirty = true;
   check_async("train_sync_weights");
@@ -567,7 +557,7 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
   launch_add_noise(x0, noise, reinterpret_cast<const long long*>(t), sqrt_ab, sqrt_1mab, p->cfg.inpaint_rows > 0 ? inpaint : nullptr, x_noisy,
                    p->n_elems(), p->cfg.inpaint_rows * p->cfg.dim, B, s);
   // ---- conditioning: encoder -> obs_cond -> Mish -> the six FiLM Linears (ddpm:317-330, Unet_FiLmLayer.py:149-154) ----
-  const bool enc_tc = tr->enc_w2p != nullptr;
+  const bool enc_tc = tr->enc_wlT16 != nullptr;
   const long long img_bstride = tr->image_bstride > 0 ? tr->image_bstride : (long long)T * 3 * 96 * 96;
   REQUIRE(enc_tc || img_bstride == (long long)T * 3 * 96 * 96, "a strided observation window needs the bf16 (tensor-core) encoder path");
   const long long n_pad = ((long long)n_frames + 127) / 128 * 128, M2 = (long long)n_frames * 576, M3 = (long long)n_frames * 144;
@@ -594,8 +584,8 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     feat16 = H16((size_t)n_pad * 9216);
     bf16* enc_out16 = H16((size_t)n_pad * 128);
     launch_enc_conv1_fwd(images, p->enc_w1, p->enc_b1, c1p, n_frames, T, img_bstride, s);
-    tc_flat("conv2", c1p, 128, tr->enc_w2p, 128, 64, M2 / 2, c2, 64, tr->enc_b2p, EPI_BIAS | EPI_RELU);
-    tc_flat("conv3", c2, 128, tr->enc_w3p, 128, 64, M3, feat16, 64, p->enc_b3, EPI_BIAS | EPI_RELU);
+    tc_flat("conv2", c1p, 128, p->enc_w2p, 128, 64, M2 / 2, c2, 64, p->enc_b2p, EPI_BIAS | EPI_RELU);
+    tc_flat("conv3", c2, 128, p->enc_w3p, 128, 64, M3, feat16, 64, p->enc_b3, EPI_BIAS | EPI_RELU);
     tc_flat("linear", feat16, 9216, p->enc_wl16, 9216, 128, n_pad, enc_out16, 128, p->enc_bl, EPI_BIAS);
     launch_cast_f32(enc_out16, enc_out, (long long)n_frames * 128, s);
   } else {
@@ -677,11 +667,11 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     launch_relu_mask(d3, feat16, d3, M3 * 64, G("vision_encoder.4.bias"), s);
     wg(c2, 128, d3, 64, M3, 128, 64, g3);
     bf16* d2 = H16((size_t)M2 * 32);        // [M3][128] == [M2/2][64]
-    tc_flat("d_c2", d3, 64, tr->enc_w3pT, 64, 128, M3, d2, 128, nullptr, 0);
+    tc_flat("d_c2", d3, 64, p->enc_w3pT, 64, 128, M3, d2, 128, nullptr, 0);
     launch_relu_mask(d2, c2, d2, M2 * 32, gb2, s);
     wg(c1p, 128, d2, 64, M2 / 2, 128, 64, g2);
     bf16* d1 = H16((size_t)M2 * 64);
-    tc_flat("d_c1", d2, 64, tr->enc_w2pT, 64, 128, M2 / 2, d1, 128, nullptr, 0);
+    tc_flat("d_c1", d2, 64, p->enc_w2pT, 64, 128, M2 / 2, d1, 128, nullptr, 0);
     // (ReLU' in the GEMM epilogue -- EPI_MASK -- was measured slower: 457 us vs 182 + 130 us for GEMM + this streaming kernel)
     launch_relu_mask(d1, c1p, d1, M2 * 64, nullptr, s);
     launch_enc_conv1_wgrad(images, d1, G("vision_encoder.0.weight"), G("vision_encoder.0.bias"), n_frames, T, img_bstride, s);
