@@ -203,6 +203,17 @@ __device__ __forceinline__ float erf_fast(float x) {
   return copysignf(1.0f - poly * __expf(-ax * ax), x);
 }
 
+// GELU for the bf16 path: y * Phi(y) with Phi through the hardware tanh (one MUFU + 5 FMA-class instructions per element instead
+// of the ~18 of the erf polynomial: the GELU launches of apply_kernel were issue-bound, ncu smsp__issue_active 59-69 %, twice the
+// time of the GELU-free launches on the same bytes).  |gelu_tanh - gelu_erf| <= 5e-4 absolute, an eighth of the bf16 rounding step
+// of the stored result; the fp32 parity path (EXACT) keeps erff.
+__device__ __forceinline__ float gelu_tanh_fast(float y) {
+  const float u = 0.7978845608028654f * fmaf(0.044715f * y * y, y, y);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
+  return fmaf(0.5f * y, th, 0.5f * y);
+}
+
 template <typename TI, typename TO, bool EXACT, int APPLY_VEC_PER_THREAD>
 __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(ApplyArgs a) {
   pdl_wait();
@@ -263,7 +274,7 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(ApplyArgs a) {
       else y = fmaf(x[i], g[i], be[i]);
       if (a.act == ACT_GELU) {
         if (EXACT) y = gelu_exact(y);
-        else y = 0.5f * y * (1.0f + erf_fast(y * 0.70710678118654752440f));
+        else y = gelu_tanh_fast(y);
       }
       if (has_temb) y += te[i];
       if (has_film) y = fs[i] * y + fb[i];
@@ -331,7 +342,7 @@ __global__ void __launch_bounds__(256) apply_partial_kernel(ApplyArgs a, const f
                   (x[k].z - mean) * rstd * g.z + be.z, (x[k].w - mean) * rstd * g.w + be.w};
     if (a.act == ACT_GELU) {
 #pragma unroll
-      for (int i = 0; i < 4; ++i) y[i] = 0.5f * y[i] * (1.0f + erf_fast(y[i] * 0.70710678118654752440f));
+      for (int i = 0; i < 4; ++i) y[i] = gelu_tanh_fast(y[i]);
     }
     if (temb) {
       const float4 t4 = __ldg(reinterpret_cast<const float4*>(temb + c));
