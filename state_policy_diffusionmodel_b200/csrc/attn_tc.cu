@@ -29,6 +29,14 @@ __device__ __forceinline__ float erf_fast_(float x) {
   return copysignf(1.0f - poly * __expf(-ax * ax), x);
 }
 
+// GELU through the hardware tanh (see kernels.cu::gelu_tanh_fast): the epilogue runs on 4 warps and is issue-bound
+__device__ __forceinline__ float gelu_tanh_fast_(float y) {
+  const float u = 0.7978845608028654f * fmaf(0.044715f * y * y, y, y);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
+  return fmaf(0.5f * y, th, 0.5f * y);
+}
+
 // 32 fp32 values of row r, columns [c, c+32) -> bf16 -> K-major 128B-swizzled A tile (k-block c/64)
 __device__ __forceinline__ void store_a_chunk(uint8_t* sA, int r, int c, const float f[32]) {
   uint8_t* rowp = sA + (c >> 6) * 16384 + r * 128;
@@ -207,7 +215,7 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float y = __uint_as_float(v[i + e]) + bb[e];
-        f[i + e] = 0.5f * y * (1.0f + erf_fast_(y * 0.70710678118654752440f));
+        f[i + e] = gelu_tanh_fast_(y);
       }
     }
     store_a_chunk(sA, r, c, f);
