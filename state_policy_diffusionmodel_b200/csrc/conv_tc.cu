@@ -71,7 +71,13 @@ __device__ __forceinline__ float erf_fast_tc(float x) {  // Abramowitz-Stegun 7.
   const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
   return copysignf(1.0f - poly * __expf(-ax * ax), x);
 }
-__device__ __forceinline__ float gelu_fast_tc(float y) { return 0.5f * y * (1.0f + erf_fast_tc(y * 0.70710678118654752440f)); }
+// GELU through the hardware tanh (kernels.cu::gelu_tanh_fast): the fused GroupNorm-apply epilogue is issue-bound on 4 warps
+__device__ __forceinline__ float gelu_fast_tc(float y) {
+  const float u = 0.7978845608028654f * fmaf(0.044715f * y * y, y, y);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
+  return fmaf(0.5f * y, th, 0.5f * y);
+}
 
 // row of the time-embedding table used by this launch (or null)
 __device__ __forceinline__ const float* temb_row(const ApplyArgs& ap, int b) {
