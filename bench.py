@@ -52,6 +52,9 @@ def parse():
                     help="sample: BASELINE configs[1] (headline); train: configs[2], training step of the attention U-Net + encoder")
     ap.add_argument("--train-batch", type=int, default=512, help="training samples per GPU (configs[2])")
     ap.add_argument("--no-train", action="store_true", help="skip the short training-step measurement appended to the sampling line")
+    ap.add_argument("--large-batch", type=int, default=4096,
+                    help="N=1 only: also measure the same workload at this per-GPU batch (north_star's >= 4096 regime, where the "
+                         "kernels are throughput- rather than launch-bound) and report it as `large_batch`; 0 disables")
     ap.add_argument("--pipeline-depth", type=int, default=2,
                     help="extra measurement: independent batches kept in flight on separate streams/plans (reported separately)")
     return ap.parse_args()
@@ -312,6 +315,64 @@ def bench_train(args, dev, world, rank, steps, warmup):
     return res
 
 
+def bench_large_batch(args, dev, model, BL, pk):
+    """Same sampler / U-Net / horizon at per-GPU batch BL (one GPU): trajectories/s with device-resident inputs (encode + graphed
+    loop, CUDA events) and the per-class table of one eager, event-timed denoising step against the measured peaks."""
+    import torch
+    import state_policy_diffusionmodel_b200 as spdm
+    attention = args.variant == "attn"
+    K, rows = args.ddim_steps, args.rows
+    m2 = spdm.Diffusion_DDIM(noise_steps=1000, obs_horizon=10, pred_horizon=rows - 1, observation_dim=135, prediction_dim=args.dim,
+                             model="UNet_Film" if attention else "UNet_FilmnoAttention", inpaint_horizon=1).to(dev).eval()
+    m2.load_state_dict(model.state_dict())
+    m2.configure(precision=args.precision, graph_steps=args.graph_steps, batch_max=BL, split=1)
+    if args.sampler == "ddim":
+        m2.use_ddim(K)
+    else:
+        m2.noise_steps = K
+        m2.noise_scheduler = spdm.DDPMScheduler(num_train_timesteps=K, beta_schedule="linear", clip_sample=False, prediction_type="epsilon")
+    devb = {k: v.to(dev) for k, v in synth_batch(BL, 10, 4321).items()}
+    x_T = torch.rand((BL, 1, rows, args.dim), device=dev)
+    plan = m2._plan(BL)
+    m2._bind_schedule(plan)
+    inpaint = m2.prepare_inpaint_vectors(devb).reshape(BL, -1).contiguous()
+
+    def step(i):
+        plan.encode_cond(devb["image"], devb["position"], devb["action"], devb["velocity"])
+        plan.sample(x_T, inpaint=inpaint, seed=2000 + i)
+
+    for i in range(3):
+        step(i)
+    torch.cuda.synchronize()
+    n = 3
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(n):
+        step(i)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    value = BL / (ms / 1000.0)
+    prof = plan.profile_step(BL, reps=3)
+    conv, app = prof["conv3x3"], prof["gn_apply"]
+    tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
+    gbs = app["bytes"] / (app["ms"] * 1e-3) / 1e9 if app["ms"] > 0 else 0.0
+    tot = sum(v["ms"] for v in prof.values())
+    flop_unet = (FLOP_UNET_ATTN if attention else FLOP_UNET_NOATTN).get(rows)
+    whole = value * (K * flop_unet + FLOP_COND) / 1e12 if flop_unet else None
+    res = {"per_gpu_batch": BL, "value": round(value, 1), "unit": UNIT, "ms_per_step": round(ms, 2), "ms_per_denoise_step": round(ms / K, 4),
+           "timed_steps": n, "cache": "inputs_larger_than_l2",
+           "conv3x3": {"tflops": round(tf, 1), "frac_of_burst_bf16_peak": round(tf / pk["tf_burst"], 4), "ms": round(conv["ms"], 4)},
+           "gn_apply": {"gbs": round(gbs, 1), "frac_of_hbm_peak": round(gbs / pk["hbm"], 4), "ms": round(app["ms"], 4)},
+           "whole_job_tflops": round(whole, 1) if whole else None,
+           "whole_job_frac_of_sustained": round(whole / pk["tf_sust"], 4) if whole else None,
+           "kernel_classes_ms": {k: round(v["ms"], 4) for k, v in prof.items()}, "eager_step_ms": round(tot, 4)}
+    plan.close() if hasattr(plan, "close") else None
+    del m2, devb
+    torch.cuda.empty_cache()
+    return res
+
+
 def config_dict(args, total_B):
     return {"workload": "%s-%d sampling, %s, pred 31x5 (rows=%d), obs 10x(96x96x3 + pos/vel/act), random-init weights" % (
                 args.sampler.upper(), args.ddim_steps, "UNet_Film (attention)" if args.variant == "attn" else "UNet_Film_noAttention", args.rows) + ("" if args.dim == 5 else ", prediction_dim=%d" % args.dim),
@@ -522,6 +583,12 @@ def main():
                                   "per_denoise_step": round(ms_loop / args.steps / K, 4)},
             "pipelined": pipelined}
 
+    # ---- the same workload at a batch where the kernels are throughput-bound (north_star: batch >= 4096) --------------
+    if args.large_batch > B and world == 1:
+        try:
+            line["large_batch"] = bench_large_batch(args, dev, model, args.large_batch, pk)
+        except Exception as e:
+            line["large_batch"] = {"error": str(e)[:300]}
     if not args.no_train:
         try:
             line["train"] = bench_train(args, dev, world, rank, max(args.steps, 5), 3)

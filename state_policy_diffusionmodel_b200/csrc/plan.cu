@@ -128,6 +128,8 @@ struct spdm_plan {
   std::map<int, size_t> partial_cap;
   bool no_splitk = false;              // SPDM_NO_SPLITK=1 (A/B switch)
   bool no_fuse = false;                // SPDM_NO_FUSE_APPLY=1: keep GroupNorm apply as a separate kernel (A/B switch)
+  std::vector<char> skip;              // SPDM_SKIP_IDX=i,j,...: launches of one forward (in timed() order) that are NOT issued --
+  int timed_idx = 0;                   // timing ablation only (tools/ablate.py), results are garbage
   int fuse_mode = 0;                   // SPDM_FUSE_MODE: 0 none (default: measured faster, the 4-warp epilogue is the bottleneck), 1 GELU-free convs, 2 all
   cudaStream_t lane_stream[7] = {};
   cudaEvent_t ev_fork = nullptr, ev_lane[7] = {};
@@ -429,6 +431,10 @@ struct FwdCtx {
 enum : int { PC_CONV3 = 0, PC_GEMM1, PC_APPLY, PC_STATS, PC_RESAMPLE, PC_LN, PC_SDPA, PC_IO, PC_STEP, PC_N };
 
 template <typename F> void timed(spdm_plan* p, cudaStream_t s, int cat, double flops, double bytes, F&& f) {
+  if (!p->skip.empty()) {
+    const int idx = p->timed_idx++;
+    if (idx < (int)p->skip.size() && p->skip[idx]) return;
+  }
   if (!p->prof_on) { f(); return; }
   spdm_plan::ProfRec r{cat, nullptr, nullptr, flops, bytes};
   while (p->ev_pool.size() < p->ev_used + 2) {  // events are pooled: creation is far slower than a small kernel
@@ -674,6 +680,7 @@ template <typename T> struct Fwd {
 
   // UNet_Film.forward (models/Unet_FiLmLayer.py:277-312) / UNet_Film_noAttention.forward
   void run() {
+    p->timed_idx = 0;
     const int rows = p->cfg.rows, dim = p->cfg.dim;
     T* cat3 = act(p->cat[0], 0); T* cat2 = act(p->cat[1], 1); T* cat1 = act(p->cat[2], 2);
     // ---- inc ----
@@ -899,6 +906,16 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
     if (const char* e = getenv("SPDM_NO_FUSE_APPLY")) p->no_fuse = atoi(e) != 0;
     if (const char* e = getenv("SPDM_FUSE_MODE")) p->fuse_mode = atoi(e);
     if (const char* e = getenv("SPDM_NO_SPLITK")) p->no_splitk = atoi(e) != 0;
+    if (const char* e = getenv("SPDM_SKIP_IDX")) {
+      p->skip.assign(256, 0);
+      for (const char* q = e; *q;) {
+        char* end = nullptr;
+        const long v = strtol(q, &end, 10);
+        if (end == q) break;
+        if (v >= 0 && v < 256) p->skip[v] = 1;
+        q = (*end == ',') ? end + 1 : end;
+      }
+    }
     if (const char* e = getenv("SPDM_ENC_SIMT_INFER")) p->enc_simt_infer = atoi(e) != 0;
     if (p->split < 1) p->split = 1;
     if (p->split > 8) p->split = 8;

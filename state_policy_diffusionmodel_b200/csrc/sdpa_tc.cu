@@ -13,6 +13,7 @@
 //   O = P V    : tcgen05.mma M=128, N=hd, K=LK; V^T tiles ([C][LK], K-major) are written by the in_proj GEMM
 //                epilogue (EPI_VT), so both operands of both GEMMs are K-major
 //   epilogue   : O row / rowsum -> bf16 -> att[token][C]
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -204,6 +205,188 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();  // S, P, O and s_red are reused by the next head
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem);
+  }
+}
+
+// Second generation of the same tile: P never goes through shared memory.  The softmax threads write P (bf16 pairs) back
+// into tensor memory, over the S columns they have already consumed, and O = P V is issued in the TS form of
+// tcgen05.mma (A operand from TMEM).  In the SS form every K=16 step of the P V product costs the ~128-cycle shared-memory
+// read of a 128-row A operand although N = hd is only 16..64 (16 steps per head at LK = 256: ~2 000 cycles, as long as
+// the softmax itself); from TMEM the step costs ~N/2 cycles.  Without the 64 KB P buffer a CTA needs 48-80 KB of shared
+// memory and 256 TMEM columns, so two CTAs share an SM and one's softmax runs under the other's MMA / barrier latencies.
+//   TMEM columns, LK = 256: S [0,256); P keys 0..127 -> [0,64), keys 128..255 -> [128,192); O_h -> [64, 64+hd)
+//                 LK = 128: S [0,128); P keys 0..63  -> [0,32), keys 64..127  -> [64,96);   O_h -> [128, 128+hd)
+//   (a thread owns one row and one half of its key columns: its P columns lie inside its own, already-read S columns)
+template <int LK, bool MASKED>
+__global__ void __launch_bounds__(256, 2)
+sdpa_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constant__ CUtensorMap map_vt, const SdpaParams p) {
+  constexpr int KB = LK / 64;
+  constexpr int SQ = 16384, SK = LK * 128, SVT = KB * 8192;
+  constexpr int TMEM_COLS = 256;
+  constexpr int HALF = LK / 2;
+  constexpr uint32_t O_COL = (LK == 256) ? 64 : 128;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + SQ;
+  uint8_t* sVt = sK + SK;
+  __shared__ __align__(8) uint64_t bar_load;
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ float s_max[2][128];   // per-row partial maximum of the two column halves
+  __shared__ float s_sum[2][128];   // per-row partial sum
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;
+  const int r = (warp & 3) * 32 + lane;   // query row inside the tile == TMEM lane
+  const int q_row0 = blockIdx.x * 128;
+  const int cb = blockIdx.y;
+  const int kv_tile = q_row0 / LK;
+  const int key_row0 = kv_tile * LK;
+
+  if (tid == 0) {
+    tma_prefetch_desc(&map_qkv);
+    tma_prefetch_desc(&map_vt);
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+  pdl_wait();
+  pdl_trigger();
+
+  if (tid == 0) {
+    mbar_expect_tx(&bar_load, SQ + SK + SVT);
+    tma_load_2d(sQ, &map_qkv, &bar_load, cb * 64, q_row0);
+#pragma unroll
+    for (int i = 0; i < LK / 128; ++i) tma_load_2d(sK + i * 16384, &map_qkv, &bar_load, p.C + cb * 64, key_row0 + i * 128);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) tma_load_2d(sVt + kb * 8192, &map_vt, &bar_load, kb * 64, kv_tile * p.C + cb * 64);
+  }
+  mbar_wait(&bar_load, 0);
+
+  int k_lo = 0, k_hi = LK;
+  if (MASKED) {
+    const int pos = (q_row0 - key_row0) + r;
+    k_lo = (pos / p.L) * p.L;
+    k_hi = k_lo + p.L;
+  }
+  const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t idesc_s = make_idesc(LK), idesc_o = make_idesc(p.hd);
+  uint32_t mma_phase = 0;
+  const int c_begin = half * HALF, c_end = c_begin + HALF;
+  const uint32_t pair_bar = 1 + (warp & 3);   // named barrier shared by the two warps that own the same 32 rows
+
+  for (int h = 0; h < p.heads_per_blk; ++h) {
+    // ---------------- S = Q_h K_h^T ----------------
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t head_off = (uint64_t)((h * p.hd * 2) >> 4);
+      const uint64_t dq = make_smem_desc(smem_u32(sQ)) + head_off;
+      const uint64_t dk = make_smem_desc(smem_u32(sK)) + head_off;
+      for (int kk = 0; kk < p.hd / 16; ++kk) umma_bf16(tmem, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc_s, kk > 0 ? 1u : 0u);
+      umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+
+    // ---------------- pass 1: row maximum over this thread's columns ----------------
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + (uint32_t)c, v);
+      tmem_ld_wait();
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float x = __uint_as_float(v[i]);
+        if (!MASKED || (c + i >= k_lo && c + i < k_hi)) m4[i & 3] = fmaxf(m4[i & 3], x);
+      }
+      m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+    }
+    s_max[half][r] = m;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    m = fmaxf(s_max[0][r], s_max[1][r]);
+    // a fully masked half (MASKED, L < HALF) leaves -inf in one slot; the row maximum itself is always finite
+    const float mscaled = m * p.scale_log2;
+
+    // ---------------- pass 2: P = exp2(S - max) -> bf16 pairs -> TMEM (behind the read pointer) ----------------
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + (uint32_t)c, v);
+      tmem_ld_wait();
+      uint32_t packed[16];
+      float s2[2] = {0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -mscaled));
+        float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mscaled));
+        if (MASKED) {
+          if (!(c + i >= k_lo && c + i < k_hi)) p0 = 0.f;
+          if (!(c + i + 1 >= k_lo && c + i + 1 < k_hi)) p1 = 0.f;
+        }
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);   // .x (low half) = the even key
+        s2[0] += __low2float(b2);
+        s2[1] += __high2float(b2);
+        packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+      }
+      sum += s2[0] + s2[1];
+      tmem_st_32x16(t_lane + (uint32_t)(c_begin + ((c - c_begin) >> 1)), packed);
+    }
+    tmem_st_wait();
+    s_sum[half][r] = sum;
+    tc_fence_before();
+    __syncthreads();   // every row of P is in tensor memory; S is dead
+
+    // ---------------- O = P V_h (A = P from TMEM) ----------------
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll 1
+      for (int k16 = 0; k16 < LK / 16; ++k16) {
+        const int kb = k16 >> 2, kk = k16 & 3;
+        const uint32_t a_col = (uint32_t)((k16 >= LK / 32 ? HALF : 0) + 8 * (k16 % (LK / 32)));
+        const uint64_t dv = make_smem_desc(smem_u32(sVt + kb * 8192 + h * p.hd * 128)) + (uint64_t)(2 * kk);
+        umma_bf16_ts(tmem + O_COL, tmem + a_col, dv, idesc_o, k16 > 0 ? 1u : 0u);
+      }
+      umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+
+    if (half == 0) {
+      const float inv = 1.f / (s_sum[0][r] + s_sum[1][r]);
+      bf16* orow = p.out + (size_t)(q_row0 + r) * p.C + cb * 64 + h * p.hd;
+#pragma unroll 1
+      for (int c = 0; c < p.hd; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + O_COL + (uint32_t)c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          if (c + i < p.hd) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i + e]) * inv;
+            store8(orow + c + i, f);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();  // S / P / O columns and the exchange arrays are reused by the next head
   }
   if (warp == 0) {
     tc_fence_after();
@@ -483,10 +666,26 @@ static void sdpa_launch_cfg(const SdpaTc* g, const SdpaParams& p, dim3 grid, cud
   launch_pdl(sdpa_tc_kernel<LK, MASKED>, grid, dim3(256), smem, s, g->map_qkv, g->map_vt, p);
 }
 
+template <int LK, bool MASKED>
+static void sdpa2_launch_cfg(const SdpaTc* g, const SdpaParams& p, dim3 grid, cudaStream_t s) {
+  constexpr int smem = 16384 + LK * 128 + (LK / 64) * 8192 + 1024;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(sdpa_tc2_kernel<LK, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  launch_pdl(sdpa_tc2_kernel<LK, MASKED>, grid, dim3(256), smem, s, g->map_qkv, g->map_vt, p);
+}
+
 void sdpa_tc_launch(const SdpaTc* g, bf16* out, long long M, cudaStream_t s) {
   SdpaParams p = g->p;
   p.out = out;
   dim3 grid((unsigned)(M / 128), (unsigned)(p.C / 64));
+  static int v1 = -1;  // SPDM_SDPA_V1=1: the first-generation kernel (P through shared memory), kept for A/B runs
+  if (v1 < 0) { const char* e = getenv("SPDM_SDPA_V1"); v1 = e ? atoi(e) : 0; }
+  if (p.L <= 256 && !v1) {
+    if (g->LK == 256) sdpa2_launch_cfg<256, false>(g, p, grid, s);
+    else if (p.L == 128) sdpa2_launch_cfg<128, false>(g, p, grid, s);
+    else sdpa2_launch_cfg<128, true>(g, p, grid, s);
+    return;
+  }
   if (p.L > 256) {
     constexpr int smem = 16384 + 256 * 128 + 4 * 8192 + 4 * 16384 + 1024;
     static bool attr = false;

@@ -126,4 +126,23 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t v[3
         "r"(v[30]), "r"(v[31])
       : "memory");
 }
+// registers -> 32 lanes x 16 columns of TMEM
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T : the A operand (128 rows x 16 bf16, K-major) is read from tensor memory -- lane = row,
+// 32-bit column j of the operand = elements (2j, 2j+1) -- so a small-N MMA is not paced by the shared-memory read of A.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
