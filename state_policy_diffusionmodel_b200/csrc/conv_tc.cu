@@ -53,6 +53,7 @@ struct TcParams {
   const bf16* resid;
   int ksplit;             // > 1: the K loop of every tile is cut into ksplit pieces run by different CTAs (split-K)
   float* partial;         // ksplit > 1: fp32 partial tiles [ksplit][m_tiles*128][Cout], summed by apply_partial_kernel
+  int cl_ks;              // conv_tc_cluster_kernel: K slices per output tile inside a cluster (cluster size = n_tiles * cl_ks)
   ApplyArgs ap;           // EPI_APPLY: GroupNorm apply (+GELU, +temb, +FiLM) fused behind the accumulator (raw/out/stats unused)
   bf16* vt;               // EPI_VT: columns >= vt_c0 go, transposed, to vt[row / vt_lk][col - vt_c0][row % vt_lk]
   int vt_c0, vt_C, vt_lk;
@@ -400,6 +401,301 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     }
     tc_fence_before();
   }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem_base);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Cluster split-K with the GroupNorm apply fused behind it (the 8x2 / 4x1 levels at small batch).
+//
+// At batch 256 a deep-level conv has 8-32 output tiles and a K loop of up to 72 serial ~0.27 us steps, so it is cut along K
+// to occupy the machine.  The first version of that wrote fp32 partial tiles to global memory and a second kernel
+// (apply_partial_kernel) summed them and applied GroupNorm: two launches (~10-15 us + ~5.5 us on the critical path of
+// the step, measured by leaving them out of the graph: tools/ablate.py).  Here the K slices of one tile -- and, for
+// Cout = 512, both of its N tiles -- form ONE thread-block cluster:
+//   1. every CTA runs its K slice (same TMA / tcgen05 pipeline as conv_tc_kernel) into its own TMEM accumulator,
+//   2. dumps the fp32 accumulator into its shared memory (over the now idle operand ring), column-slice major,
+//   3. cluster barrier; CTA j sums column slice j of all K slices through distributed shared memory (fixed order),
+//      keeps the result in its own shared memory and pushes its per-sample (sum, sumsq) to every CTA of the cluster,
+//   4. cluster barrier; GroupNorm(1, C) statistics of the tile's whole samples are now local: normalise (+GELU, +time
+//      embedding, +FiLM) and store the bf16 activation.  Neither the raw conv output nor a partial tile touches HBM.
+// Requires whole samples per 128-row tile (H == Hb) with 4..32 rows per sample; cluster size n_tiles * cl_ks <= 8.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t laddr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(laddr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ float4 ld_dsmem_v4(uint32_t addr) {
+  float4 v;
+  // volatile keeps it ordered against the (volatile) cluster barriers; no "memory" clobber so a batch of loads stays in flight
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void st_dsmem_v2(uint32_t addr, float a, float b) {
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
+}
+
+template <int BLOCK_N, int STAGES>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
+  constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int TMEM_COLS = BLOCK_N <= 128 ? 128 : 256;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + STAGES * A_STAGE_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(8) float s_stat[32][8][2];   // [sample of the tile][source CTA rank] (sum, sumsq), filled by remote stores
+  __shared__ float s_part[128][2];                   // (sum, sumsq) of every warp-sized run of the reduced slice
+  __shared__ float s_mr[32][2];                      // per sample: rstd, -mean * rstd
+  __shared__ __align__(16) float s_par[3][128];      // gamma, beta, time embedding of this CTA's channel slice
+  __shared__ __align__(16) float s_film[4096];       // FiLM (scale | bias) of the tile's samples for the slice: [sample][2][Wd]
+  long long tstamp[7];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int CS = p.n_tiles * p.cl_ks;
+  const int m_tile = blockIdx.x / CS;
+  const int nt = (int)rank % p.n_tiles, ks = (int)rank / p.n_tiles;
+  const int b0 = m_tile * p.Bt;                  // whole samples per tile: h0 == 0
+  const int n0 = nt * BLOCK_N;
+
+  const bool skip_dx = (p.W == 1), skip_dy = (p.H == 1);
+  const int ntx = skip_dx ? 1 : 3, nty = skip_dy ? 1 : 3;
+  const int k_iters = ntx * nty * p.kb_per_tap;
+  const int it_begin = ks * k_iters / p.cl_ks, it_end = (ks + 1) * k_iters / p.cl_ks;   // host guarantees cl_ks <= k_iters
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&map_a);
+    tma_prefetch_desc(&map_b);
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+  pdl_trigger();
+
+  const int Wd = BLOCK_N / p.cl_ks;              // columns of the tile this CTA reduces and finishes
+  const int RS = Wd + 4;                         // padded row stride (floats): 16-byte row-per-lane accesses stay conflict-free
+  float* red = reinterpret_cast<float*>(smem);   // [cl_ks slices][128 rows][RS], over the operand ring once every MMA has retired
+  const int r_t = (warp & 3) * 32 + lane;        // epilogue threads: tile row == TMEM lane
+
+  if (warp == 0) {
+    if (lane == 0) {
+      uint32_t kit = 0;
+      for (int it = it_begin; it < it_end; ++it, ++kit) {
+        const int s = kit % STAGES;
+        const uint32_t ph = (kit / STAGES) & 1u;
+        mbar_wait(&empty_bar[s], ph ^ 1u);
+        const int tap_i = it / p.kb_per_tap, kb = it - tap_i * p.kb_per_tap;
+        const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
+        const int dy = skip_dy ? 0 : ty - 1, dx = skip_dx ? 0 : tx - 1;
+        const int tap = (dy + 1) * 3 + (dx + 1);
+        mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
+        tma_load_4d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, dy, b0);
+        tma_load_2d(smem_b + s * B_STAGE_BYTES, &map_b, &full_bar[s], tap * p.Cin + kb * BLOCK_K, n0);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+      uint32_t kit = 0;
+      for (int it = it_begin; it < it_end; ++it, ++kit) {
+        const int s = kit % STAGES;
+        const uint32_t ph = (kit / STAGES) & 1u;
+        mbar_wait(&full_bar[s], ph);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
+        const uint64_t db = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+          umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > it_begin || k > 0) ? 1u : 0u);
+        umma_commit(&empty_bar[s]);
+      }
+      umma_commit(&tmem_full_bar);
+    }
+    __syncwarp();
+  } else {
+    // ---- while the K slice runs: per-channel constants of this CTA's output slice -> shared memory ----
+    tstamp[0] = clock64();
+    {
+      const int ch0 = n0 + ks * Wd;
+      const bool te_cta = p.ap.temb_mode == TEMB_ROW0 || p.ap.temb_mode == TEMB_STEP;
+      const float* te = te_cta ? temb_row(p.ap, 0) : nullptr;
+      if (r_t < Wd) {
+        s_par[0][r_t] = __ldg(p.ap.gamma + ch0 + r_t);
+        s_par[1][r_t] = __ldg(p.ap.beta + ch0 + r_t);
+        s_par[2][r_t] = te ? __ldg(te + ch0 + r_t) : 0.f;
+      }
+      const int ns = BLOCK_M / (p.Hb * p.W);
+      if (p.ap.film && ns * 2 * Wd <= 4096) {
+        for (int i = r_t; i < ns * 2 * Wd; i += 128) {
+          const int sm = i / (2 * Wd), rem = i - sm * 2 * Wd, hf = rem / Wd, cc = rem - hf * Wd;
+          s_film[i] = __ldg(p.ap.film + (size_t)(b0 + sm) * SPDM_FILM_WIDTH + p.ap.film_off + hf * p.Cout + ch0 + cc);
+        }
+      }
+    }
+    // ---- accumulator -> own shared memory, column-slice major ----
+    mbar_wait(&tmem_full_bar, 0);
+    tc_fence_after();
+    tstamp[1] = clock64();
+    const uint32_t t_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+    for (int c = 0; c < BLOCK_N; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_addr + (uint32_t)c, v);
+      tmem_ld_wait();
+      const int j = c / Wd, col = c - j * Wd;      // Wd >= 32: a 32-column chunk lies inside one slice
+      float* dst = red + ((size_t)j * BLOCK_M + r_t) * RS + col;
+#pragma unroll
+      for (int i = 0; i < 32; i += 4)
+        *reinterpret_cast<uint4*>(dst + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+    }
+    tc_fence_before();
+    tstamp[2] = clock64();
+  }
+  cluster_sync_all();   // every partial tile of the cluster is in shared memory
+  tstamp[3] = clock64();
+
+  // ---- the slice block [128 rows][Wd] is walked as a flat list of float4 by all 192 threads: thread t takes float4
+  //      t + 192 k, so a warp reads contiguous 512-byte runs of the remote tiles (the SM-to-SM network is the bound of this
+  //      phase: ~12 B/clk/SM measured) and later writes contiguous bf16 runs of the output ----
+  const int rps = p.Hb * p.W;                    // rows per sample (4..32, power of two)
+  const int ns = BLOCK_M / rps;                  // samples of the tile
+  const int W4 = Wd >> 2;                        // float4 per row of the slice (8, 16 or 32)
+  const int lw4 = __ffs(W4) - 1, lrps = __ffs(rps) - 1;
+  const int n4 = BLOCK_M * W4;                   // float4 of the slice
+  const int tid = (int)threadIdx.x;
+  float* blk = red + (size_t)ks * BLOCK_M * RS;  // this CTA's own partial of slice `ks`, then the reduced slice
+  {
+    // sum column slice `ks` over the K slices of this N tile (ranks sp * n_tiles + nt), fixed order
+    const uint32_t blk_addr = smem_u32(blk);
+    uint32_t src[8];
+#pragma unroll
+    for (int sp = 0; sp < 8; ++sp) src[sp] = sp < p.cl_ks ? mapa_u32(blk_addr, (uint32_t)(sp * p.n_tiles + nt)) : 0u;
+#pragma unroll 1
+    for (int i0 = tid; i0 < n4; i0 += 2 * NUM_THREADS) {   // 2 * cl_ks remote 16-byte loads in flight per thread
+      float4 v[8][2];
+      int off[2];
+      bool ok[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int i = i0 + u * NUM_THREADS;
+        ok[u] = i < n4;
+        const int row = i >> lw4, c4 = i & (W4 - 1);
+        off[u] = ok[u] ? row * RS + c4 * 4 : 0;
+      }
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp)
+        if (sp < p.cl_ks) {
+          v[sp][0] = ld_dsmem_v4(src[sp] + (uint32_t)off[0] * 4u);
+          v[sp][1] = ld_dsmem_v4(src[sp] + (uint32_t)off[1] * 4u);
+        }
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        float4 acc = v[0][u];
+#pragma unroll
+        for (int sp = 1; sp < 8; ++sp)
+          if (sp < p.cl_ks) { acc.x += v[sp][u].x; acc.y += v[sp][u].y; acc.z += v[sp][u].z; acc.w += v[sp][u].w; }
+        if (ok[u]) *reinterpret_cast<float4*>(blk + off[u]) = acc;   // n4 is a multiple of 32: ok[u] is warp-uniform
+        float ps = (acc.x + acc.y) + (acc.z + acc.w);
+        float pq = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, acc.w * acc.w)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { ps += __shfl_xor_sync(0xffffffffu, ps, o); pq += __shfl_xor_sync(0xffffffffu, pq, o); }
+        // the 32 float4 of a warp are 128 / Wd whole rows of ONE sample (rps >= 4 rows, aligned): slot = first index / 32
+        if (lane == 0 && ok[u]) { const int q = (i0 + u * NUM_THREADS) >> 5; s_part[q][0] = ps; s_part[q][1] = pq; }
+      }
+    }
+    __syncthreads();
+    if (tid < ns) {   // sample tid: slots [tid * sps, (tid + 1) * sps), summed in a fixed order, pushed to every CTA of the cluster
+      const int sps = (rps * W4) >> 5;
+      float ts = 0.f, tq = 0.f;
+      for (int q = tid * sps; q < (tid + 1) * sps; ++q) { ts += s_part[q][0]; tq += s_part[q][1]; }
+      const uint32_t slot = smem_u32(&s_stat[tid][rank][0]);
+      for (int d = 0; d < CS; ++d) st_dsmem_v2(mapa_u32(slot, (uint32_t)d), ts, tq);
+    }
+    tstamp[4] = clock64();
+  }
+  cluster_sync_all();   // all statistics partials have arrived; nothing remote is touched below
+  tstamp[5] = clock64();
+
+  {
+    if (tid < ns) {
+      float ts = 0.f, tq = 0.f;
+      for (int d = 0; d < CS; ++d) { ts += s_stat[tid][d][0]; tq += s_stat[tid][d][1]; }
+      const float inv_n = 1.0f / ((float)rps * (float)p.Cout);
+      const float mean = ts * inv_n;
+      const float rstd = rsqrtf(fmaxf(tq * inv_n - mean * mean, 0.f) + p.ap.eps);
+      s_mr[tid][0] = rstd;
+      s_mr[tid][1] = -mean * rstd;
+    }
+    __syncthreads();
+    const int ch0 = n0 + ks * Wd;
+    const bool film_smem = p.ap.film && ns * 2 * Wd <= 4096;
+#pragma unroll 4
+    for (int i = tid; i < n4; i += NUM_THREADS) {
+      const int row = i >> lw4, c = (i & (W4 - 1)) * 4;
+      const int sm = row >> lrps;
+      const float A = s_mr[sm][0], Bm = s_mr[sm][1];
+      const float4 x = *reinterpret_cast<const float4*>(blk + row * RS + c);
+      const float4 g = *reinterpret_cast<const float4*>(&s_par[0][c]);
+      const float4 e = *reinterpret_cast<const float4*>(&s_par[1][c]);
+      float4 t = *reinterpret_cast<const float4*>(&s_par[2][c]);
+      if (p.ap.temb_mode == TEMB_PER_SAMPLE) t = __ldg(reinterpret_cast<const float4*>(temb_row(p.ap, b0 + sm) + ch0 + c));
+      float f[4] = {fmaf(fmaf(x.x, A, Bm), g.x, e.x), fmaf(fmaf(x.y, A, Bm), g.y, e.y), fmaf(fmaf(x.z, A, Bm), g.z, e.z),
+                    fmaf(fmaf(x.w, A, Bm), g.w, e.w)};
+      if (p.ap.act == ACT_GELU) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) f[j] = gelu_fast_tc(f[j]);
+      }
+      f[0] += t.x; f[1] += t.y; f[2] += t.z; f[3] += t.w;
+      if (p.ap.film) {
+        float4 fs, fb;
+        if (film_smem) {
+          fs = *reinterpret_cast<const float4*>(&s_film[sm * 2 * Wd + c]);
+          fb = *reinterpret_cast<const float4*>(&s_film[sm * 2 * Wd + Wd + c]);
+        } else {
+          const float* fi = p.ap.film + (size_t)(b0 + sm) * SPDM_FILM_WIDTH + p.ap.film_off + ch0 + c;
+          fs = __ldg(reinterpret_cast<const float4*>(fi));
+          fb = __ldg(reinterpret_cast<const float4*>(fi + p.Cout));
+        }
+        f[0] = fmaf(fs.x, f[0], fb.x); f[1] = fmaf(fs.y, f[1], fb.y); f[2] = fmaf(fs.z, f[2], fb.z); f[3] = fmaf(fs.w, f[3], fb.w);
+      }
+      uint2 o;
+      __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+      ho[0] = __floats2bfloat162_rn(f[0], f[1]);
+      ho[1] = __floats2bfloat162_rn(f[2], f[3]);
+      *reinterpret_cast<uint2*>(p.out + ((long long)m_tile * BLOCK_M + row) * p.ld_out + ch0 + c) = o;
+    }
+  }
+  tstamp[6] = clock64();
+  if ((p.dbg & 2048) && blockIdx.x == 0 && threadIdx.x == 64)
+    printf("spdm cluster timing H%d Cin%d Cout%d ks%d nt%d: mainloop %lld dump %lld sync1 %lld reduce %lld sync2 %lld apply %lld total %lld cycles\n", p.H, p.Cin,
+           p.Cout, p.cl_ks, p.n_tiles, tstamp[1] - tstamp[0], tstamp[2] - tstamp[1], tstamp[3] - tstamp[2], tstamp[4] - tstamp[3],
+           tstamp[5] - tstamp[4], tstamp[6] - tstamp[5], tstamp[6] - tstamp[0]);
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
@@ -850,6 +1146,96 @@ int tc_gemm_split(const TcGemm* g, int B) {
   if (s > k_iters / 4) s = k_iters / 4;
   if (s > 8) s = 8;
   return s < 2 ? 1 : s;
+}
+
+// ---- cluster split-K + fused GroupNorm apply (conv_tc_cluster_kernel) ----
+template <int BLOCK_N, int STAGES>
+static cudaError_t launch_cluster_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p, int cs, cudaStream_t s, int* max_clusters) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(conv_tc_cluster_kernel<BLOCK_N, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes<BLOCK_N, STAGES>());
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)(p.m_tiles * cs));
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem_bytes<BLOCK_N, STAGES>();
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_spdm_pdl ? 2 : 1;
+  if (max_clusters) {  // occupancy query only
+    cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(max_clusters, conv_tc_cluster_kernel<BLOCK_N, STAGES>, &cfg);
+  }
+  return cudaLaunchKernelEx(&cfg, conv_tc_cluster_kernel<BLOCK_N, STAGES>, ma, mb, p);
+}
+
+// Clusters of `cs` CTAs (one CTA per SM: ~193 KB of shared memory each) that can be resident at once; cached per (N, cs).
+static int max_active_clusters(const TcGemm* g, int bn, int cs) {
+  static int cache[2][9] = {};
+  int& c = cache[bn == 256][cs];
+  if (c == 0) {
+    TcParams p = g->p;
+    p.m_tiles = 1;
+    int n = 0;
+    cudaError_t e = bn == 256 ? launch_cluster_cfg<256, 4>(g->map_a, g->map_b256, p, cs, nullptr, &n)
+                              : launch_cluster_cfg<128, 6>(g->map_a, g->map_b, p, cs, nullptr, &n);
+    if (e != cudaSuccess) { cudaGetLastError(); n = 0; }
+    c = n > 0 ? n : -1;
+  }
+  return c > 0 ? c : 0;
+}
+
+int tc_gemm_cluster_split(const TcGemm* g, int B) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("SPDM_NO_CLUSTER"); off = e ? atoi(e) : 0; }
+  if (off || tc_gemm_split(g, B) <= 1) return 0;   // only where the global-memory split-K path would be taken
+  const TcParams& p = g->p;
+  if (p.taps != 9 || p.H != p.Hb) return 0;
+  const int rps = p.Hb * p.W;
+  if (rps < 4 || rps > 32) return 0;
+  const int bn = g->has256 ? 256 : g->block_n;
+  if (bn != 128 && bn != 256) return 0;
+  const int n_tiles = p.Cout / bn;
+  if (n_tiles > 2) return 0;
+  const int m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
+  const int k_iters = (p.W == 1 ? 1 : 3) * (p.H == 1 ? 1 : 3) * p.kb_per_tap;
+  static int verbose = -1;
+  if (verbose < 0) { const char* e = getenv("SPDM_VERBOSE"); verbose = e ? atoi(e) : 0; }
+  for (int ks = 8 / n_tiles; ks >= 2; ks >>= 1) {
+    if (ks * 2 > k_iters || bn / ks < 32) continue;
+    const int mac = max_active_clusters(g, bn, ks * n_tiles);
+    if (verbose) fprintf(stderr, "spdm cluster conv %dx%d %d->%d B=%d: m_tiles %d n_tiles %d k_iters %d ks %d: max active clusters %d\n", p.H, p.W, p.Cin, p.Cout, B, m_tiles, n_tiles, k_iters, ks, mac);
+    if (m_tiles > mac) continue;   // one wave of co-scheduled clusters
+    return ks;
+  }
+  return 0;
+}
+
+int tc_gemm_launch_cluster(const TcGemm* g, bf16* out, int ld_out, const ApplyArgs* ap, int B, int ks, cudaStream_t s) {
+  TcParams p = g->p;
+  p.ap = *ap;
+  p.flags = EPI_APPLY;
+  static int timing = -1;  // SPDM_CL_TIMING=1: block 0 prints its per-phase cycle counts (diagnostics)
+  if (timing < 0) { const char* e = getenv("SPDM_CL_TIMING"); timing = e ? atoi(e) : 0; }
+  p.dbg = timing ? 2048 : 0;
+  p.out = out; p.ld_out = ld_out;
+  p.m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
+  const int bn = g->has256 ? 256 : g->block_n;
+  p.n_tiles = p.Cout / bn;
+  p.cl_ks = ks;
+  p.total_tiles = p.m_tiles * p.n_tiles * ks;
+  const int cs = p.n_tiles * ks;
+  cudaError_t e = bn == 256 ? launch_cluster_cfg<256, 4>(g->map_a, g->map_b256, p, cs, s, nullptr)
+                            : launch_cluster_cfg<128, 6>(g->map_a, g->map_b, p, cs, s, nullptr);
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "cluster conv launch failed: %s", cudaGetErrorString(e)); return -1; }
+  ++g_tc_launches;
+  return 0;
 }
 
 bool tc_gemm_can_fuse_apply(const TcGemm* g, int B) {

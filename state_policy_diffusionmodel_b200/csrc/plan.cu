@@ -510,6 +510,27 @@ template <typename T> struct Fwd {
     return 1;
   }
 
+  // Deep-level conv at small batch: K slices of a tile as one thread-block cluster, reduced through distributed shared
+  // memory with GroupNorm apply behind it (conv_tc_cluster_kernel).  Returns false when not applicable here.
+  bool gemm_cluster(const std::string& wname, const T* in, int ld_in, int level, T* out, int ld_out, const ApplyArgs& a) {
+    if constexpr (sizeof(T) == 2) {
+      if (p->no_splitk) return false;
+      GemmW& g = p->gemms[wname];
+      TcGemm* tc = get_tc(wname, g, in, ld_in, level);
+      const int ks = tc_gemm_cluster_split(tc, Bpad);
+      if (ks < 2) return false;
+      const int H = p->levelH(level), W = p->levelW(level);
+      const double flops = 2.0 * g.Cin * g.Cout * (3.0 * H - 2) * (3.0 * W - 2) * c.B;
+      const double bytes = ((double)c.B * H * W * (g.Cin + g.Cout) + (double)g.taps * g.Cin * g.Cout) * 2.0;
+      timed(p, c.s, PC_CONV3, flops, bytes, [&] {
+        const int rc = tc_gemm_launch_cluster(tc, reinterpret_cast<bf16*>(out), ld_out, &a, Bpad, ks, c.s);
+        REQUIRE(rc == 0, "%s: %s", wname.c_str(), tc_last_error());
+      });
+      return true;
+    }
+    return false;
+  }
+
   // can GroupNorm apply run inside this conv's epilogue (whole samples and all channels in one tile)?
   bool can_fuse(const std::string& wname, const T* in, int ld_in, int level) {
     if constexpr (sizeof(T) == 2) {
@@ -587,7 +608,9 @@ template <typename T> struct Fwd {
     const long long Mpad = (long long)Bpad * p->levelH(level) * p->levelW(level);
     if (!first_done) {
       const int S = tap1 ? 1 : split_for(name + ".first", in, ld_in, level, Cout);
-      if (S > 1) {
+      if (S > 1 && gemm_cluster(name + ".first", in, ld_in, level, h, Cout, make_apply(name + ".norm", Cout, level, ACT_GELU, nullptr))) {
+        fused = true;
+      } else if (S > 1) {
         gemm(name + ".first", in, ld_in, level, raw, Cout, EPI_STATS, nullptr, 0, nullptr, S, p->partial[c.b0]);
         ApplyArgs a = make_apply(name + ".norm", Cout, level, ACT_GELU, nullptr);
         a.out = h; a.ld_out = Cout;
@@ -606,7 +629,8 @@ template <typename T> struct Fwd {
       apply(name + ".norm", raw, Cout, Cout, level, h, Cout, ACT_GELU, nullptr);
     }
     const int S2 = tap2 ? 1 : split_for(name + ".second", h, Cout, level, Cout);
-    if (S2 > 1) {
+    if (S2 > 1 && gemm_cluster(name + ".second", h, Cout, level, out, ld_out, make_apply(name + ".norm", Cout, level, ACT_NONE, st))) {
+    } else if (S2 > 1) {
       gemm(name + ".second", h, Cout, level, raw, Cout, EPI_STATS, nullptr, 0, nullptr, S2, p->partial[c.b0]);
       ApplyArgs a = make_apply(name + ".norm", Cout, level, ACT_NONE, st);
       a.out = out; a.ld_out = ld_out;
