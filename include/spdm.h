@@ -138,9 +138,9 @@ int spdm_adam_step(float* params, float* grads, float* m, float* v, int64_t n, f
 /* Kernel-class profile of one denoising step (U-Net forward + posterior update) run EAGERLY with CUDA
  * events around every launch, averaged over `reps` steps: out[c*4 + {0,1,2,3}] = {ms, launches,
  * algorithmic FLOPs, algorithmic bytes} for class c.  Needs a schedule and (if conditional) cached cond. */
-#define SPDM_PROFILE_CLASSES 9
+#define SPDM_PROFILE_CLASSES 10
 enum { SPDM_PC_CONV3 = 0, SPDM_PC_GEMM1, SPDM_PC_APPLY, SPDM_PC_STATS, SPDM_PC_RESAMPLE, SPDM_PC_LN,
-       SPDM_PC_SDPA, SPDM_PC_IO, SPDM_PC_STEP };
+       SPDM_PC_SDPA, SPDM_PC_IO, SPDM_PC_STEP, SPDM_PC_CONV3_GN /* cluster split-K conv + fused GroupNorm apply */ };
 int spdm_profile_step(spdm_plan* plan, int32_t B, int32_t reps, double* out, void* stream);
 
 /* Microbenchmark of one tcgen05 implicit-GEMM launch (3x3 conv when taps == 9, Linear when taps == 1) on

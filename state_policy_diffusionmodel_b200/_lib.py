@@ -22,7 +22,7 @@ VARIANT_ATTENTION, VARIANT_NO_ATTENTION = 0, 1
 PRECISION_FP32, PRECISION_BF16 = 0, 1
 SCHED_DDPM, SCHED_DDIM = 0, 1
 FLAG_SCHEDULER_ONLY = 1
-PROFILE_CLASSES = ("conv3x3", "gemm1x1", "gn_apply", "gn_stats", "resample", "layernorm", "sdpa", "io_conv", "step")
+PROFILE_CLASSES = ("conv3x3", "gemm1x1", "gn_apply", "gn_stats", "resample", "layernorm", "sdpa", "io_conv", "step", "conv3x3_gn")
 
 _P = _c.c_void_p
 _PROTOTYPES = {

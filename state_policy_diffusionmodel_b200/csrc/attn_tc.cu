@@ -86,13 +86,18 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_smem;
-  pdl_wait();
-  pdl_trigger();
-
   auto load_w = [&](const CUtensorMap* m) {
 #pragma unroll
     for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * WBLK, m, &bar_load, kb * 64, 0);
   };
+  // the weights do not depend on the previous kernel: Wo is put in flight before the programmatic-dependency wait
+  if (tid == 0) {
+    mbar_expect_tx(&bar_load, SA + SW);
+    load_w(&map_wo);
+  }
+  pdl_wait();
+  pdl_trigger();
+
   auto issue_gemm = [&]() {  // D[128][C] = A[128][C] * W[C][C]^T
     const uint32_t idesc = make_idesc(C);
 #pragma unroll
@@ -112,10 +117,8 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
 
   // ---------------- GEMM 1: att @ Wo^T ----------------
   if (tid == 0) {
-    mbar_expect_tx(&bar_load, SA + SW);
 #pragma unroll
     for (int kb = 0; kb < KB; ++kb) tma_load_2d(sA + kb * 16384, &map_att, &bar_load, kb * 64, row0);
-    load_w(&map_wo);
     mbar_wait(&bar_load, load_phase);
     tc_fence_after();
     issue_gemm();

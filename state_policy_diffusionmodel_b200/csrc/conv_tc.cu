@@ -141,33 +141,59 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  pdl_wait();     // everything above overlapped with the previous kernel's tail; global memory is touched only below
-  pdl_trigger();
+  // Programmatic dependent launch: everything above overlapped with the previous kernel's tail.  The weights do not depend
+  // on the previous kernel either, so the producer also puts the B tiles of its first STAGES k-steps in flight BEFORE the
+  // dependency wait; activations (A tiles) and every global write come after it.
+  if (!(warp == 0 && lane == 0)) { pdl_wait(); pdl_trigger(); }
 
   if (warp == 0) {
     // ================= TMA producer =================
-    if (lane == 0 && !(p.dbg & 16)) {
-      uint32_t kit = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-        const TileCoord t = decode_tile(p, tile, BLOCK_N);
+    if (lane == 0) {
+      auto tap_of = [&](int it, int& dy, int& dx, int& tap, int& kb) {
+        const int tap_i = it / p.kb_per_tap;
+        kb = it - tap_i * p.kb_per_tap;
+        dy = 0; dx = 0; tap = 0;
+        if (p.taps == 9) {
+          const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
+          dy = skip_dy ? 0 : ty - 1;
+          dx = skip_dx ? 0 : tx - 1;
+          tap = (dy + 1) * 3 + (dx + 1);
+        }
+      };
+      const uint32_t stage_tx = ((p.dbg & 2) ? 0 : A_STAGE_BYTES) + ((p.dbg & 1) ? 0 : B_STAGE_BYTES);
+      uint32_t n_pre = 0;   // k-steps of the first tile whose expect_tx + weight load were issued before the wait
+      if (!(p.dbg & 16) && (int)blockIdx.x < p.total_tiles) {
+        const TileCoord t = decode_tile(p, blockIdx.x, BLOCK_N);
         const int it_begin = p.ksplit > 1 ? t.ks * k_iters / p.ksplit : 0;
         const int it_end = p.ksplit > 1 ? (t.ks + 1) * k_iters / p.ksplit : k_iters;
-        for (int it = it_begin; it < it_end; ++it, ++kit) {
-          const int s = kit % STAGES;
-          const uint32_t ph = (kit / STAGES) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
-          const int tap_i = it / p.kb_per_tap, kb = it - tap_i * p.kb_per_tap;
-          int dy = 0, dx = 0, tap = 0;
-          if (p.taps == 9) {
-            const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
-            dy = skip_dy ? 0 : ty - 1;
-            dx = skip_dx ? 0 : tx - 1;
-            tap = (dy + 1) * 3 + (dx + 1);
+        for (int it = it_begin; it < it_end && n_pre < (uint32_t)STAGES; ++it, ++n_pre) {
+          int dy, dx, tap, kb;
+          tap_of(it, dy, dx, tap, kb);
+          mbar_expect_tx(&full_bar[n_pre], stage_tx);
+          if (!(p.dbg & 1)) tma_load_2d(smem_b + n_pre * B_STAGE_BYTES, &map_b, &full_bar[n_pre], tap * p.Cin + kb * BLOCK_K, t.n0);
+        }
+      }
+      pdl_wait();
+      pdl_trigger();
+      if (!(p.dbg & 16)) {
+        uint32_t kit = 0;
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+          const TileCoord t = decode_tile(p, tile, BLOCK_N);
+          const int it_begin = p.ksplit > 1 ? t.ks * k_iters / p.ksplit : 0;
+          const int it_end = p.ksplit > 1 ? (t.ks + 1) * k_iters / p.ksplit : k_iters;
+          for (int it = it_begin; it < it_end; ++it, ++kit) {
+            const int s = kit % STAGES;
+            const uint32_t ph = (kit / STAGES) & 1u;
+            int dy, dx, tap, kb;
+            tap_of(it, dy, dx, tap, kb);
+            if (p.dbg & 8) { dx = 0; dy = 0; }
+            if (kit >= n_pre) {
+              mbar_wait(&empty_bar[s], ph ^ 1u);
+              mbar_expect_tx(&full_bar[s], stage_tx);
+              if (!(p.dbg & 1)) tma_load_2d(smem_b + s * B_STAGE_BYTES, &map_b, &full_bar[s], tap * p.Cin + kb * BLOCK_K, t.n0);
+            }
+            if (!(p.dbg & 2)) tma_load_4d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t.h0 + dy, t.b0);
           }
-          if (p.dbg & 8) { dx = 0; dy = 0; }
-          mbar_expect_tx(&full_bar[s], ((p.dbg & 2) ? 0 : A_STAGE_BYTES) + ((p.dbg & 1) ? 0 : B_STAGE_BYTES));
-          if (!(p.dbg & 2)) tma_load_4d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t.h0 + dy, t.b0);
-          if (!(p.dbg & 1)) tma_load_2d(smem_b + s * B_STAGE_BYTES, &map_b, &full_bar[s], tap * p.Cin + kb * BLOCK_K, t.n0);
         }
       }
     }
@@ -494,8 +520,7 @@ conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  pdl_wait();
-  pdl_trigger();
+  if (!(warp == 0 && lane == 0)) { pdl_wait(); pdl_trigger(); }   // the producer first puts its weight tiles in flight (below)
 
   const int Wd = BLOCK_N / p.cl_ks;              // columns of the tile this CTA reduces and finishes
   const int RS = Wd + 4;                         // padded row stride (floats): 16-byte row-per-lane accesses stay conflict-free
@@ -504,18 +529,31 @@ conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 
   if (warp == 0) {
     if (lane == 0) {
-      uint32_t kit = 0;
-      for (int it = it_begin; it < it_end; ++it, ++kit) {
-        const int s = kit % STAGES;
-        const uint32_t ph = (kit / STAGES) & 1u;
-        mbar_wait(&empty_bar[s], ph ^ 1u);
+      uint32_t n_pre = 0;
+      for (int it = it_begin; it < it_end && n_pre < (uint32_t)STAGES; ++it, ++n_pre) {   // weights only: before the dependency wait
         const int tap_i = it / p.kb_per_tap, kb = it - tap_i * p.kb_per_tap;
         const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
         const int dy = skip_dy ? 0 : ty - 1, dx = skip_dx ? 0 : tx - 1;
         const int tap = (dy + 1) * 3 + (dx + 1);
-        mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
+        mbar_expect_tx(&full_bar[n_pre], A_STAGE_BYTES + B_STAGE_BYTES);
+        tma_load_2d(smem_b + n_pre * B_STAGE_BYTES, &map_b, &full_bar[n_pre], tap * p.Cin + kb * BLOCK_K, n0);
+      }
+      pdl_wait();
+      pdl_trigger();
+      uint32_t kit = 0;
+      for (int it = it_begin; it < it_end; ++it, ++kit) {
+        const int s = kit % STAGES;
+        const uint32_t ph = (kit / STAGES) & 1u;
+        const int tap_i = it / p.kb_per_tap, kb = it - tap_i * p.kb_per_tap;
+        const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
+        const int dy = skip_dy ? 0 : ty - 1, dx = skip_dx ? 0 : tx - 1;
+        const int tap = (dy + 1) * 3 + (dx + 1);
+        if (kit >= n_pre) {
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], A_STAGE_BYTES + B_STAGE_BYTES);
+          tma_load_2d(smem_b + s * B_STAGE_BYTES, &map_b, &full_bar[s], tap * p.Cin + kb * BLOCK_K, n0);
+        }
         tma_load_4d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, dy, b0);
-        tma_load_2d(smem_b + s * B_STAGE_BYTES, &map_b, &full_bar[s], tap * p.Cin + kb * BLOCK_K, n0);
       }
     }
     __syncwarp();
@@ -756,13 +794,27 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
-  pdl_wait();     // everything above overlapped with the previous kernel's tail; global memory is touched only below
-  pdl_trigger();
+  // as in conv_tc_kernel: the producer puts the weight tiles of its first STAGES k-steps in flight before the dependency wait
+  if (!(warp == 0 && lane == 0)) { pdl_wait(); pdl_trigger(); }
   TcParams pm = p;       // decode_tile works on 128-row tiles with n_tiles == 1
   pm.n_tiles = 1;
 
   if (warp == 0) {
     if (lane == 0) {
+      uint32_t n_pre = 0;
+      if ((int)blockIdx.x < total) {
+        const int c_tile = (int)blockIdx.x % c_tiles;
+        for (int it = 0; it < k_iters && n_pre < (uint32_t)STAGES; ++it, ++n_pre) {
+          const int tap_i = it / p.kb_per_tap, kb = it - tap_i * p.kb_per_tap;
+          const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
+          const int dy = skip_dy ? 0 : ty - 1, dx = skip_dx ? 0 : tx - 1;
+          const int tap = (dy + 1) * 3 + (dx + 1);
+          mbar_expect_tx(&full_bar[n_pre], PIX_BYTES + W_BYTES);
+          tma_load_2d(smem_w + n_pre * W_BYTES, &map_w, &full_bar[n_pre], tap * p.Cin + kb * BLOCK_K, c_tile * WM);
+        }
+      }
+      pdl_wait();
+      pdl_trigger();
       uint32_t kit = 0;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
         const int c_tile = tile % c_tiles, pt = tile / c_tiles;
@@ -770,15 +822,17 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int it = 0; it < k_iters; ++it, ++kit) {
           const int s = kit % STAGES;
           const uint32_t ph = (kit / STAGES) & 1u;
-          mbar_wait(&empty_bar[s], ph ^ 1u);
           const int tap_i = it / p.kb_per_tap, kb = it - tap_i * p.kb_per_tap;
           const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
           const int dy = skip_dy ? 0 : ty - 1, dx = skip_dx ? 0 : tx - 1;
           const int tap = (dy + 1) * 3 + (dx + 1);
-          mbar_expect_tx(&full_bar[s], PIX_BYTES + W_BYTES);
+          if (kit >= n_pre) {
+            mbar_wait(&empty_bar[s], ph ^ 1u);
+            mbar_expect_tx(&full_bar[s], PIX_BYTES + W_BYTES);
+            tma_load_2d(smem_w + s * W_BYTES, &map_w, &full_bar[s], tap * p.Cin + kb * BLOCK_K, c_tile * WM);
+          }
           tma_load_4d(smem_pix + s * PIX_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t0.h0 + dy, t0.b0);
           tma_load_4d(smem_pix + s * PIX_BYTES + A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t1.h0 + dy, t1.b0);
-          tma_load_2d(smem_w + s * W_BYTES, &map_w, &full_bar[s], tap * p.Cin + kb * BLOCK_K, c_tile * WM);
         }
       }
     }

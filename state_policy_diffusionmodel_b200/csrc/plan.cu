@@ -428,7 +428,7 @@ struct FwdCtx {
   cudaStream_t s;
 };
 
-enum : int { PC_CONV3 = 0, PC_GEMM1, PC_APPLY, PC_STATS, PC_RESAMPLE, PC_LN, PC_SDPA, PC_IO, PC_STEP, PC_N };
+enum : int { PC_CONV3 = 0, PC_GEMM1, PC_APPLY, PC_STATS, PC_RESAMPLE, PC_LN, PC_SDPA, PC_IO, PC_STEP, PC_CONV3_GN, PC_N };
 
 template <typename F> void timed(spdm_plan* p, cudaStream_t s, int cat, double flops, double bytes, F&& f) {
   if (!p->skip.empty()) {
@@ -522,7 +522,7 @@ template <typename T> struct Fwd {
       const int H = p->levelH(level), W = p->levelW(level);
       const double flops = 2.0 * g.Cin * g.Cout * (3.0 * H - 2) * (3.0 * W - 2) * c.B;
       const double bytes = ((double)c.B * H * W * (g.Cin + g.Cout) + (double)g.taps * g.Cin * g.Cout) * 2.0;
-      timed(p, c.s, PC_CONV3, flops, bytes, [&] {
+      timed(p, c.s, PC_CONV3_GN, flops, bytes, [&] {
         const int rc = tc_gemm_launch_cluster(tc, reinterpret_cast<bf16*>(out), ld_out, &a, Bpad, ks, c.s);
         REQUIRE(rc == 0, "%s: %s", wname.c_str(), tc_last_error());
       });

@@ -14,7 +14,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import state_policy_diffusionmodel_b200 as spdm  # noqa: E402
-from bench import peaks, synth_batch  # noqa: E402
+from bench import merge_conv, peaks, synth_batch  # noqa: E402
 
 
 def run_point(model, K, B, rows, reps):
@@ -69,7 +69,7 @@ def main():
                 if K != 50 and B not in (256, 4096):
                     continue
                 ms, prof = run_point(model, K, B, rows, args.reps)
-                conv, app = prof["conv3x3"], prof["gn_apply"]
+                conv, app = merge_conv(prof), prof["gn_apply"]
                 tf = conv["flops"] / (conv["ms"] * 1e-3) / 1e12 if conv["ms"] > 0 else 0.0
                 gbs = app["bytes"] / (app["ms"] * 1e-3) / 1e9 if app["ms"] > 0 else 0.0
                 launches = sum(v["launches"] for v in prof.values())
