@@ -159,6 +159,33 @@ int64_t spdm_debug_forward(spdm_plan* plan, const float* x, const int64_t* t, in
                            const float* y, int32_t use_cached_cond, float* out, int32_t B,
                            const char* tap_name, float* tap_out, void* stream);
 
+/* ---- dataset -> batch on the device (utils/load_data.py:11-144, utils/data_utils.py:18-62) ------------
+ * The dataset arrays stay resident in device memory; one call gathers a batch of B strided windows, exactly as
+ * CarRacingDataset.__getitem__ + the DataLoader's default collate build it on the host:
+ *   images      uint8 (N, H, W, 3) as the simulator wrote them (decoded x / 255 in flight), or float (N, 3, H, W)
+ *   starts      int64 [B], first frame of every window (create_sample_indices_sparse, data_utils.py:46-56)
+ *   out_image   (B, T_img, 3, H, W): frames start + t*step, t < T_img <= T (T_img = T is the reference's item; obs_horizon is
+ *               all the model reads, models/diffusion_ddpm.py:283-298; 0 = no images)
+ *   out_position (B, T, 2): min-max normalised with the scalar position statistics, centred on the window's first point,
+ *               halved (load_data.py:128-133); out_translation (B, 2) = that first point
+ *   out_velocity (B, T, 2), out_action (B, T, 3): min-max normalised per dimension (load_data.py:78-81)
+ * Arithmetic is fp32, one IEEE rounding per operation in the reference's order: bit-identical to the numpy float32 path. */
+enum { SPDM_IMAGES_U8_HWC = 0, SPDM_IMAGES_F32_CHW = 1 };
+typedef struct spdm_data_stats {
+  float pos_min, pos_max;          /* scalars: mean of the per-window minima / maxima (load_data.py:58-71) */
+  float vel_min[2], vel_max[2];    /* get_data_stats(velocity)  (data_utils.py:10-16)                       */
+  float act_min[3], act_max[3];    /* get_data_stats(action)                                                */
+} spdm_data_stats;
+int spdm_gather_windows(const void* images, int32_t image_kind, int32_t H, int32_t W, const float* position,
+                        const float* velocity, const float* action, const int64_t* starts, int32_t B, int32_t T,
+                        int32_t T_img, int32_t step, const spdm_data_stats* stats /* host */, float* out_image,
+                        float* out_position, float* out_velocity, float* out_action, float* out_translation, void* stream);
+/* utils/data_utils.py:35-40 unnormalize_position on (n_samples, rows_per_sample, 2) device positions with the per-sample
+ * translation (n_samples, 2): sampled trajectories / whole sample_history stacks without a host round trip. */
+int spdm_unnormalize_position(const float* npos, const float* translation, float pos_min, float pos_max, int64_t n_samples,
+                              int32_t rows_per_sample, float* out, void* stream);
+int64_t spdm_data_launch_count(void);
+
 const char* spdm_last_error(void);
 const char* spdm_version(void);
 

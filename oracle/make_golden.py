@@ -180,6 +180,55 @@ def golden_train_grads(seed=0):
         print(name, "loss", float(loss), "total_norm", float(total), "tensors", len(named))
 
 
+def golden_dataset(seed=0):
+    """the reference's own CarRacingDataset (utils/load_data.py:11-144) on the synthetic dataset of
+    oracle/data_ref.py -- only its zarr reader is replaced -- and utils/data_utils.unnormalize_position."""
+    from . import data_ref
+    shim.install()
+    import utils.load_data as ld
+    from utils.data_utils import unnormalize_position
+    raw = data_ref.make_synthetic_dataset(seed)
+    img = data_ref.image_chw_float(raw["img_u8"])
+
+    def _load(self, dataset_path):
+        return img, {"position": raw["position"], "velocity": raw["velocity"], "action": raw["action"]}, raw["episode_ends"]
+
+    class DS(ld.CarRacingDataset):           # training dataset: computes the statistics, items are dicts
+        _load_data = _load
+
+    class DSI(ld.CarRacingDatasetForInference):   # inference dataset: given statistics, items carry translation / start / end
+        _load_data = _load
+
+    out = {"seed": seed}
+    for tag, (obs_h, pred_h, step) in {"a": (3, 4, 2), "b": (2, 3, 1)}.items():
+        ds = DS("unused", pred_h, obs_h, None, step_size=step)
+        dsi = DSI("unused", pred_h, obs_h, ds.stats, step_size=step)
+        assert dsi.indices == ds.indices
+        idxs = list(range(0, len(ds), max(1, len(ds) // 5)))[:6]
+        train_items = [ds[i] for i in idxs]
+        items = [dsi[i] for i in idxs]
+        for ti, it in zip(train_items, items):   # both classes normalise a window identically
+            for k in ("position", "velocity", "action", "image"):
+                assert np.array_equal(np.asarray(ti[k]), np.asarray(it[0][k])), k
+        out[tag + "_cfg"] = np.asarray([obs_h, pred_h, step])
+        out[tag + "_indices"] = np.asarray(ds.indices)
+        out[tag + "_idxs"] = np.asarray(idxs)
+        out[tag + "_pos_stats"] = np.asarray([ds.stats["position"]["min"], ds.stats["position"]["max"]])
+        out[tag + "_vel_stats"] = np.stack([ds.stats["velocity"]["min"], ds.stats["velocity"]["max"]])
+        out[tag + "_act_stats"] = np.stack([ds.stats["action"]["min"], ds.stats["action"]["max"]])
+        out[tag + "_position"] = np.stack([it[0]["position"] for it in items])
+        out[tag + "_velocity"] = np.stack([it[0]["velocity"] for it in items])
+        out[tag + "_action"] = np.stack([it[0]["action"] for it in items])
+        out[tag + "_translation"] = np.stack([it[1] for it in items])
+        out[tag + "_start_end"] = np.asarray([[it[2], it[3]] for it in items])
+        im = np.stack([it[0]["image"] for it in items]).astype(np.float64)      # (n, T, 3, H, W): fingerprints only
+        out[tag + "_image_fp"] = np.stack([im.sum(axis=(2, 3, 4)), im[:, :, 0, 0, 0], im[:, :, 1, 5, 7], im[:, :, 2, -1, -1],
+                                          (im * np.arange(im.shape[-1])).sum(axis=(2, 3, 4))], axis=-1)
+        out[tag + "_unnorm"] = np.stack([unnormalize_position(it[0]["position"], it[1], ds.stats["position"]) for it in items])
+        print("dataset", tag, len(ds), "windows", out[tag + "_position"].shape)
+    np.savez_compressed(os.path.join(OUT, "dataset.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     shim.install()
@@ -193,6 +242,7 @@ def main():
     golden_sample("ddpm", "UNet_FilmnoAttention", False, 20, 2, "sample_ddpm20_noattn_pos2", seed=3)
     golden_validate_and_train()
     golden_train_grads()
+    golden_dataset()
 
 
 if __name__ == "__main__":

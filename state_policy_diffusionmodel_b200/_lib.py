@@ -25,6 +25,16 @@ FLAG_SCHEDULER_ONLY = 1
 PROFILE_CLASSES = ("conv3x3", "gemm1x1", "gn_apply", "gn_stats", "resample", "layernorm", "sdpa", "io_conv", "step", "conv3x3_gn")
 
 _P = _c.c_void_p
+
+
+IMAGES_U8_HWC, IMAGES_F32_CHW = 0, 1
+
+
+class SpdmDataStats(_c.Structure):  # include/spdm.h: spdm_data_stats
+    _fields_ = [("pos_min", _c.c_float), ("pos_max", _c.c_float), ("vel_min", _c.c_float * 2), ("vel_max", _c.c_float * 2),
+                ("act_min", _c.c_float * 3), ("act_max", _c.c_float * 3)]
+
+
 _PROTOTYPES = {
     "spdm_plan_create": (_c.c_int, [_c.POINTER(_P), _c.POINTER(SpdmConfig)]),
     "spdm_plan_destroy": (_c.c_int, [_P]),
@@ -51,6 +61,10 @@ _PROTOTYPES = {
     "spdm_train_wait_phase": (_c.c_int, [_P, _c.c_int32, _P]),
     "spdm_adam_step": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_int32,
                                   _c.c_float, _c.c_float, _P, _P]),
+    "spdm_gather_windows": (_c.c_int, [_P, _c.c_int32, _c.c_int32, _c.c_int32, _P, _P, _P, _P, _c.c_int32, _c.c_int32, _c.c_int32,
+                                       _c.c_int32, _P, _P, _P, _P, _P, _P, _P]),
+    "spdm_unnormalize_position": (_c.c_int, [_P, _P, _c.c_float, _c.c_float, _c.c_int64, _c.c_int32, _P, _P]),
+    "spdm_data_launch_count": (_c.c_int64, []),
     "spdm_plan_launch_count": (_c.c_int64, [_P]),
     "spdm_plan_workspace_bytes": (_c.c_int64, [_P]),
     "spdm_last_error": (_c.c_char_p, []),

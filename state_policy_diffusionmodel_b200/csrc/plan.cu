@@ -50,6 +50,11 @@ struct SpdmError { std::string msg; };
   } while (0)
 
 extern "C" const char* spdm_last_error(void) { return g_err; }
+// data_kernels.cu (plan-free entry points) reports through the same thread-local message
+int spdm_data_fail(const char* msg) { return fail("%s", msg); }
+static long long g_data_launches = 0;
+void spdm_count_data_launch() { ++g_data_launches; }
+extern "C" int64_t spdm_data_launch_count(void) { return g_data_launches; }
 extern "C" const char* spdm_version(void) { return "spdm-b200 0.1 (sm_100a)"; }
 
 // -------------------------------------------------------------------------------------------------

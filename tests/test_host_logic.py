@@ -206,3 +206,23 @@ def _gloo_train_worker(rank, world, port):
 def test_data_parallel_training_world2_gloo():
     port = 31500 + os.getpid() % 2000
     mp.spawn(_gloo_train_worker, args=(2, port), nprocs=2, join=True)
+
+
+def test_dataset_host_logic_matches_oracle():
+    """Window indices and normalisation statistics of DeviceWindowDataset are host preprocessing (as in the reference,
+    utils/data_utils.py:46-56, utils/load_data.py:58-76): the package's restatement must equal the oracle's, which is pinned to
+    the reference classes by tests/golden/dataset.npz."""
+    import numpy as np
+    from oracle import data_ref
+    from state_policy_diffusionmodel_b200 import data as pdata
+    raw = data_ref.make_synthetic_dataset(0)
+    for seq, step in ((7, 2), (5, 1), (40, 1), (3, 9)):
+        assert pdata.create_sample_indices_sparse(raw["episode_ends"], seq, step) == data_ref.create_sample_indices_sparse(
+            raw["episode_ends"], seq, step)
+    idx = data_ref.create_sample_indices_sparse(raw["episode_ends"], 7, 2)
+    a = pdata.compute_stats(raw["position"], raw["velocity"], raw["action"], idx, 2)
+    b = data_ref.compute_stats(raw, idx, 2)
+    assert a["position"]["min"] == b["position"]["min"] and a["position"]["max"] == b["position"]["max"]
+    for k in ("velocity", "action"):
+        assert np.array_equal(a[k]["min"], b[k]["min"]) and np.array_equal(a[k]["max"], b[k]["max"])
+    assert pdata.create_sample_indices_sparse([5], 7, 1) == []      # an episode shorter than the window yields nothing

@@ -126,3 +126,37 @@ def test_training_gradients_and_adam_oracle(golden_dir, name):
     got_p = torch.stack([train_ref.summary(new_p[n]) for n in names])
     want_p = torch.from_numpy(raw["param_fp_after"])
     assert float(((got_p - want_p).abs() / want_p[:, 2:3].clamp_min(1e-12)).max()) < 1e-4
+
+
+def test_dataset_oracle_vs_reference_golden(golden_dir):
+    """oracle/data_ref.py against tests/golden/dataset.npz, which the reference's own CarRacingDataset /
+    CarRacingDatasetForInference (utils/load_data.py) and unnormalize_position (utils/data_utils.py:35-40) produced."""
+    import numpy as np
+    from oracle import data_ref
+    g = np.load(os.path.join(golden_dir, "dataset.npz"))
+    raw = data_ref.make_synthetic_dataset(int(g["seed"]))
+    data = {"image": data_ref.image_chw_float(raw["img_u8"]), "position": raw["position"], "velocity": raw["velocity"],
+            "action": raw["action"]}
+    for tag in ("a", "b"):
+        obs_h, pred_h, step = (int(v) for v in g[tag + "_cfg"])
+        ds = data_ref.RefWindowDataset(data, raw["episode_ends"], pred_h, obs_h, None, step)
+        assert np.array_equal(np.asarray(ds.indices), g[tag + "_indices"])
+        assert np.array_equal(np.asarray([ds.stats["position"]["min"], ds.stats["position"]["max"]]), g[tag + "_pos_stats"])
+        assert np.array_equal(np.stack([ds.stats["velocity"]["min"], ds.stats["velocity"]["max"]]), g[tag + "_vel_stats"])
+        assert np.array_equal(np.stack([ds.stats["action"]["min"], ds.stats["action"]["max"]]), g[tag + "_act_stats"])
+        batch, tr, start, end = ds.collate(list(g[tag + "_idxs"]))
+        for k in ("position", "velocity", "action"):
+            assert batch[k].dtype == np.float32
+            assert np.array_equal(batch[k], g[tag + "_" + k]), k          # bit-exact: same float32 operations
+        assert np.array_equal(tr, g[tag + "_translation"])
+        assert np.array_equal(np.stack([start, end], axis=1), g[tag + "_start_end"])
+        im = batch["image"].astype(np.float64)
+        fp = np.stack([im.sum(axis=(2, 3, 4)), im[:, :, 0, 0, 0], im[:, :, 1, 5, 7], im[:, :, 2, -1, -1],
+                       (im * np.arange(im.shape[-1])).sum(axis=(2, 3, 4))], axis=-1)
+        assert np.allclose(fp, g[tag + "_image_fp"], rtol=1e-12, atol=0)
+        un = np.stack([data_ref.unnormalize_position(batch["position"][i], tr[i], ds.stats["position"]) for i in range(len(tr))])
+        assert np.array_equal(un, g[tag + "_unnorm"])
+        # round trip: un-normalising a window gives back the raw positions of its frames
+        for i, s0 in enumerate(start):
+            rawpos = raw["position"][s0:end[i]:step]
+            assert np.allclose(un[i], rawpos, rtol=0, atol=2e-4 * float(np.abs(rawpos).max()))

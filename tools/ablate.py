@@ -14,25 +14,25 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# launch indices of one UNet_Film forward, bf16 path, in issue order (profiles/r01_launches_ddim50_b256_final.csv)
-APPLY = [1, 3, 6, 8, 10, 12, 19, 21, 23, 25, 32, 34, 36, 38, 44, 46, 48, 50, 52, 54, 57, 59, 61, 63, 70, 72, 74, 76, 83, 85, 87, 89]
+# launch indices of one UNet_Film forward at batch 256, bf16 path, in issue order (profiles/r01_launches_ddim50_b256_v3.csv):
+# 77 launches -- the 18 deep-level convs are cluster split-K launches with the GroupNorm apply fused behind them
+APPLY = [1, 3, 6, 8, 10, 12, 52, 54, 56, 58, 65, 67, 69, 71]
 GROUPS = {
     "none": [],
-    "gn_apply (32)": APPLY,
-    "layernorm (6)": [13, 26, 39, 64, 77, 90],
-    "in_proj (6)": [14, 27, 40, 65, 78, 91],
-    "sdpa (6)": [15, 28, 41, 66, 79, 92],
-    "sdpa sa6 (1)": [92],
-    "attn tail (6)": [16, 29, 42, 67, 80, 93],
-    "sa6 whole (4)": [90, 91, 92, 93],
-    "attention whole (24)": [13, 14, 15, 16, 26, 27, 28, 29, 39, 40, 41, 42, 64, 65, 66, 67, 77, 78, 79, 80, 90, 91, 92, 93],
-    "pool+upsample (6)": [4, 17, 30, 55, 68, 81],
-    "conv 32x8 (5)": [2, 82, 84, 86, 88],
-    "conv 16x4 (8)": [5, 7, 9, 11, 69, 71, 73, 75],
-    "conv 8x2 (8)": [18, 20, 22, 24, 56, 58, 60, 62],
-    "conv 4x1 (10)": [31, 33, 35, 37, 43, 45, 47, 49, 51, 53],
-    "level 4x1 convs+applies (20)": list(range(31, 39)) + list(range(43, 55)),
-    "everything but conv_in/outc (93)": list(range(1, 94)),
+    "gn_apply, separate kernels, 32x8 + 16x4 levels (14)": APPLY,
+    "layernorm (6)": [13, 22, 31, 46, 59, 72],
+    "in_proj (6)": [14, 23, 32, 47, 60, 73],
+    "sdpa (6)": [15, 24, 33, 48, 61, 74],
+    "sdpa sa6 (1)": [74],
+    "attn tail (6)": [16, 25, 34, 49, 62, 75],
+    "sa6 whole (4)": [72, 73, 74, 75],
+    "attention whole (24)": [13, 14, 15, 16, 22, 23, 24, 25, 31, 32, 33, 34, 46, 47, 48, 49, 59, 60, 61, 62, 72, 73, 74, 75],
+    "pool+upsample (6)": [4, 17, 26, 41, 50, 63],
+    "conv 32x8 (5)": [2, 64, 66, 68, 70],
+    "conv 16x4 (8)": [5, 7, 9, 11, 51, 53, 55, 57],
+    "cluster conv+GN 8x2 (8)": [18, 19, 20, 21, 42, 43, 44, 45],
+    "cluster conv+GN 4x1 (10)": [27, 28, 29, 30, 35, 36, 37, 38, 39, 40],
+    "everything but conv_in/outc (75)": list(range(1, 76)),
 }
 
 
