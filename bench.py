@@ -315,6 +315,58 @@ def bench_train(args, dev, world, rank, steps, warmup):
     return res
 
 
+def bench_data_pipeline(args, dev, pk, B=512, n_frames=8192):
+    """one training batch (B windows, obs_horizon frames of 96x96x3 each) gathered from an HBM-resident
+    uint8 dataset by spdm_gather_windows -- HBM-bound: 1 byte read + 4 bytes written per pixel-channel -- next to the
+    reference's host path (oracle restatement of CarRacingDataset.__getitem__ + collate) on a bounded sample."""
+    import numpy as np
+    import torch
+    import state_policy_diffusionmodel_b200 as spdm
+    from oracle import data_ref
+    obs_h, pred_h = 10, args.rows - 1
+    rs = np.random.RandomState(5)
+    img = torch.randint(0, 256, (n_frames, 96, 96, 3), dtype=torch.uint8, device=dev)     # 226 MB: larger than L2
+    pos = np.cumsum(rs.normal(0, 0.7, (n_frames, 2)), axis=0).astype(np.float32)
+    vel = rs.uniform(-30, 60, (n_frames, 2)).astype(np.float32)
+    act = rs.uniform(-1, 1, (n_frames, 3)).astype(np.float32)
+    ends = np.arange(1024, n_frames + 1, 1024)
+    ds = spdm.DeviceWindowDataset(img, pos, vel, act, ends, pred_h, obs_h, None, 1, device=dev, image_frames=obs_h)
+    g = torch.Generator().manual_seed(3)
+    idx_sets = [torch.randint(0, len(ds), (B,), generator=g).to(dev) for _ in range(8)]
+    for i in range(3):
+        ds.batch(idx_sets[i])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n = 8
+    e0.record()
+    for i in range(n):
+        ds.batch(idx_sets[i])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / n
+    bytes_alg = B * obs_h * 96 * 96 * 3 * (1 + 4) + B * (obs_h + pred_h) * 7 * 8
+    gbs = bytes_alg / (ms * 1e-3) / 1e9
+    res = {"workload": "%d windows x %d frames of 96x96x3 uint8 -> fp32 CHW + normalised state, dataset resident in HBM (%d frames)" % (
+               B, obs_h, n_frames), "ms_per_batch": round(ms, 4), "samples_per_s": round(B / (ms * 1e-3), 1),
+           "roofline": {"bound": "hbm", "achieved": round(gbs, 1), "peak": pk["hbm"], "unit": "GB/s", "frac": round(gbs / pk["hbm"], 4),
+                        "algorithmic_bytes_per_batch": bytes_alg}, "includes": "index gather + allocation of the output tensors (torch)"}
+    if not args.no_cpu_baseline:
+        sub = 2048
+        img_f = data_ref.image_chw_float(img[:sub].cpu().numpy())
+        ref = data_ref.RefWindowDataset({"image": img_f, "position": pos[:sub], "velocity": vel[:sub], "action": act[:sub]},
+                                        ends[ends <= sub], pred_h, obs_h, None, 1)
+        ii = list(range(0, len(ref), max(1, len(ref) // 64)))[:64]
+        t0 = time.perf_counter()
+        ref.collate(ii)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"value": round(len(ii) / dt, 1), "unit": "samples/s", "cores": 1, "kind": "port",
+                               "sample": "%d windows (full %d-frame items, as the reference's __getitem__ + collate build them), %.3fs" % (
+                                   len(ii), obs_h + pred_h, dt)}
+    del ds, img
+    torch.cuda.empty_cache()
+    return res
+
+
 def merge_conv(prof):
     """All 3x3 implicit-GEMM launches of a step: the plain tcgen05 convs plus the cluster split-K convs (whose time also
     contains the GroupNorm apply fused behind them)."""
@@ -598,6 +650,11 @@ def main():
             line["large_batch"] = bench_large_batch(args, dev, model, args.large_batch, pk)
         except Exception as e:
             line["large_batch"] = {"error": str(e)[:300]}
+    if world == 1 and args.dim == 5:
+        try:
+            line["data_pipeline"] = bench_data_pipeline(args, dev, pk)
+        except Exception as e:
+            line["data_pipeline"] = {"error": str(e)[:300]}
     if not args.no_train:
         try:
             line["train"] = bench_train(args, dev, world, rank, max(args.steps, 5), 3)
