@@ -1245,6 +1245,17 @@ static int max_active_clusters(const TcGemm* g, int bn, int cs) {
   return c > 0 ? c : 0;
 }
 
+// Tile width of the cluster path: 256 where Cout allows, except that a 256-channel layer with few M tiles (the 4x1 level at
+// batch <= 480) is cut into two 128-wide N tiles so that a cluster of 8 (2 N tiles x 4 K slices) shares the work: the
+// DSMEM reduction -- the longest phase, bound by the SM-to-SM network at ~12 B/clk/SM -- then moves half the bytes per CTA.
+static int cluster_bn(const TcGemm* g, int m_tiles) {
+  const int bn = g->has256 ? 256 : g->block_n;
+  static int wide = -1;   // SPDM_CL_BN256=1: always 256-wide tiles (A/B switch)
+  if (wide < 0) { const char* e = getenv("SPDM_CL_BN256"); wide = e ? atoi(e) : 0; }
+  if (bn == 256 && g->p.Cout == 256 && !wide && m_tiles <= max_active_clusters(g, 128, 8)) return 128;
+  return bn;
+}
+
 int tc_gemm_cluster_split(const TcGemm* g, int B) {
   static int off = -1;
   if (off < 0) { const char* e = getenv("SPDM_NO_CLUSTER"); off = e ? atoi(e) : 0; }
@@ -1253,18 +1264,18 @@ int tc_gemm_cluster_split(const TcGemm* g, int B) {
   if (p.taps != 9 || p.H != p.Hb) return 0;
   const int rps = p.Hb * p.W;
   if (rps < 4 || rps > 32) return 0;
-  const int bn = g->has256 ? 256 : g->block_n;
-  if (bn != 128 && bn != 256) return 0;
+  const int m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
+  if ((g->has256 ? 256 : g->block_n) != 128 && !g->has256) return 0;
+  const int bn = cluster_bn(g, m_tiles);
   const int n_tiles = p.Cout / bn;
   if (n_tiles > 2) return 0;
-  const int m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
   const int k_iters = (p.W == 1 ? 1 : 3) * (p.H == 1 ? 1 : 3) * p.kb_per_tap;
   static int verbose = -1;
   if (verbose < 0) { const char* e = getenv("SPDM_VERBOSE"); verbose = e ? atoi(e) : 0; }
   for (int ks = 8 / n_tiles; ks >= 2; ks >>= 1) {
     if (ks * 2 > k_iters || bn / ks < 32) continue;
     const int mac = max_active_clusters(g, bn, ks * n_tiles);
-    if (verbose) fprintf(stderr, "spdm cluster conv %dx%d %d->%d B=%d: m_tiles %d n_tiles %d k_iters %d ks %d: max active clusters %d\n", p.H, p.W, p.Cin, p.Cout, B, m_tiles, n_tiles, k_iters, ks, mac);
+    if (verbose) fprintf(stderr, "spdm cluster conv %dx%d %d->%d B=%d: m_tiles %d bn %d n_tiles %d k_iters %d ks %d: max active clusters %d\n", p.H, p.W, p.Cin, p.Cout, B, m_tiles, bn, n_tiles, k_iters, ks, mac);
     if (m_tiles > mac) continue;   // one wave of co-scheduled clusters
     return ks;
   }
@@ -1280,7 +1291,7 @@ int tc_gemm_launch_cluster(const TcGemm* g, bf16* out, int ld_out, const ApplyAr
   p.dbg = timing ? 2048 : 0;
   p.out = out; p.ld_out = ld_out;
   p.m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
-  const int bn = g->has256 ? 256 : g->block_n;
+  const int bn = cluster_bn(g, p.m_tiles);
   p.n_tiles = p.Cout / bn;
   p.cl_ks = ks;
   p.total_tiles = p.m_tiles * p.n_tiles * ks;

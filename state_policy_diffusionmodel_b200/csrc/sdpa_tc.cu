@@ -274,10 +274,14 @@ sdpa_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
   mbar_wait(&bar_load, 0);
 
   int k_lo = 0, k_hi = LK;
-  if (MASKED) {
+  int wk_lo = 0, wk_hi = LK;   // union of the key ranges of this warp's 32 rows (warp-uniform): chunks outside it hold no key of
+  if (MASKED) {                // any of them -- no TMEM read, no exp, P = 0 (at L = 16 that is 7 of every 8 columns)
     const int pos = (q_row0 - key_row0) + r;
     k_lo = (pos / p.L) * p.L;
     k_hi = k_lo + p.L;
+    const int pos_w = (q_row0 - key_row0) + (warp & 3) * 32;
+    wk_lo = (pos_w / p.L) * p.L;
+    wk_hi = ((pos_w + 31) / p.L + 1) * p.L;
   }
   const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t idesc_s = make_idesc(LK), idesc_o = make_idesc(p.hd);
@@ -303,6 +307,7 @@ sdpa_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     float m = -INFINITY;
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
+      if (MASKED && (c + 32 <= wk_lo || c >= wk_hi)) continue;
       uint32_t v[32];
       tmem_ld_32x32(t_lane + (uint32_t)c, v);
       tmem_ld_wait();
@@ -324,10 +329,16 @@ sdpa_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
     float sum = 0.f;
 #pragma unroll 1
     for (int c = c_begin; c < c_end; c += 32) {
+      uint32_t packed[16];
+      if (MASKED && (c + 32 <= wk_lo || c >= wk_hi)) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) packed[i] = 0u;
+        tmem_st_32x16(t_lane + (uint32_t)(c_begin + ((c - c_begin) >> 1)), packed);
+        continue;
+      }
       uint32_t v[32];
       tmem_ld_32x32(t_lane + (uint32_t)c, v);
       tmem_ld_wait();
-      uint32_t packed[16];
       float s2[2] = {0.f, 0.f};
 #pragma unroll
       for (int i = 0; i < 32; i += 2) {
