@@ -198,7 +198,7 @@ int tc_gemm_split(const TcGemm* g, int B);
 // (+GELU, +temb, +FiLM) can run in the conv epilogue (pass `fuse`; `out` then receives the activated map).
 bool tc_gemm_can_fuse_apply(const TcGemm* g, int B);
 // Cluster split-K with GroupNorm apply fused behind it (deep levels at small batch): K slices per tile (0 = not
-// applicable at this geometry / batch) and the launch; `out` receives the activated bf16 map, no partial tiles.
+// applicable at this geometry / batch; 1 = the cluster only shares the GroupNorm statistics of a tile's N tiles) and the launch; `out` receives the activated bf16 map, no partial tiles.
 int tc_gemm_cluster_split(const TcGemm* g, int B);
 int tc_gemm_launch_cluster(const TcGemm* g, bf16* out, int ld_out, const ApplyArgs* ap, int B, int ks, cudaStream_t s);
 const char* tc_last_error();

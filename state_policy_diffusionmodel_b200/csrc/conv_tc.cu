@@ -634,6 +634,8 @@ conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     uint32_t src[8];
 #pragma unroll
     for (int sp = 0; sp < 8; ++sp) src[sp] = sp < p.cl_ks ? mapa_u32(blk_addr, (uint32_t)(sp * p.n_tiles + nt)) : 0u;
+    // (tried: keeping the per-run sums in registers and doing all warp reductions after a fully unrolled loop -- 198 registers,
+    //  reduce phase 6.7-10 K cycles instead of 4.6-8 K: the phase is bound by the remote loads, not by the shuffle chains)
 #pragma unroll 1
     for (int i0 = tid; i0 < n4; i0 += 2 * NUM_THREADS) {   // 2 * cl_ks remote 16-byte loads in flight per thread
       float4 v[8][2];
@@ -649,8 +651,13 @@ conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 #pragma unroll
       for (int sp = 0; sp < 8; ++sp)
         if (sp < p.cl_ks) {
-          v[sp][0] = ld_dsmem_v4(src[sp] + (uint32_t)off[0] * 4u);
-          v[sp][1] = ld_dsmem_v4(src[sp] + (uint32_t)off[1] * 4u);
+          if (sp == ks) {   // this CTA's own partial: a plain shared-memory load (ld.shared::cluster is slow even to oneself)
+            v[sp][0] = *reinterpret_cast<const float4*>(blk + off[0]);
+            v[sp][1] = *reinterpret_cast<const float4*>(blk + off[1]);
+          } else {
+            v[sp][0] = ld_dsmem_v4(src[sp] + (uint32_t)off[0] * 4u);
+            v[sp][1] = ld_dsmem_v4(src[sp] + (uint32_t)off[1] * 4u);
+          }
         }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
@@ -1245,15 +1252,40 @@ static int max_active_clusters(const TcGemm* g, int bn, int cs) {
   return c > 0 ? c : 0;
 }
 
-// Tile width of the cluster path: 256 where Cout allows, except that a 256-channel layer with few M tiles (the 4x1 level at
-// batch <= 480) is cut into two 128-wide N tiles so that a cluster of 8 (2 N tiles x 4 K slices) shares the work: the
-// DSMEM reduction -- the longest phase, bound by the SM-to-SM network at ~12 B/clk/SM -- then moves half the bytes per CTA.
-static int cluster_bn(const TcGemm* g, int m_tiles) {
-  const int bn = g->has256 ? 256 : g->block_n;
-  static int wide = -1;   // SPDM_CL_BN256=1: always 256-wide tiles (A/B switch)
-  if (wide < 0) { const char* e = getenv("SPDM_CL_BN256"); wide = e ? atoi(e) : 0; }
-  if (bn == 256 && g->p.Cout == 256 && !wide && m_tiles <= max_active_clusters(g, 128, 8)) return 128;
-  return bn;
+// Shape of the cluster launch for a deep-level conv of m_tiles M tiles: tile width bn, K slices ks (0 = not applicable).
+//   * SPDM_CL_NOSPLIT_MAX = n (default 0 = off): K loops of <= n k-steps are NOT cut -- 128-wide N tiles, the cluster = the
+//     Cout / 128 N tiles of an M tile and only exchanges the GroupNorm statistics.  Measured slower (0.926 vs 0.820 ms per step
+//     with n = 24): a k-step costs ~830 cycles in this kernel, not the 512 of its four MMAs, so the longer chain outweighs the
+//     saved reduction; kept as an A/B switch;
+//   * otherwise 256-wide tiles where Cout allows and ks = 2..8 K slices, except that a 256-channel layer with few M tiles is
+//     cut into two 128-wide N tiles so that a cluster of 8 shares the work (half the DSMEM bytes per CTA).
+static void cluster_config(const TcGemm* g, int m_tiles, int* bn_out, int* ks_out) {
+  *bn_out = 0; *ks_out = 0;
+  const TcParams& p = g->p;
+  const int bn0 = g->has256 ? 256 : g->block_n;
+  if (bn0 != 128 && bn0 != 256) return;
+  const int k_iters = (p.W == 1 ? 1 : 3) * (p.H == 1 ? 1 : 3) * p.kb_per_tap;
+  static int wide = -1, nosplit_max = -1, verbose = -1;
+  if (wide < 0) { const char* e = getenv("SPDM_CL_BN256"); wide = e ? atoi(e) : 0; }   // 1: always 256-wide tiles (A/B switch)
+  if (nosplit_max < 0) { const char* e = getenv("SPDM_CL_NOSPLIT_MAX"); nosplit_max = e ? atoi(e) : 0; }
+  if (verbose < 0) { const char* e = getenv("SPDM_VERBOSE"); verbose = e ? atoi(e) : 0; }
+  if (k_iters <= nosplit_max && p.Cout % 128 == 0 && p.Cout / 128 <= 4 && m_tiles <= max_active_clusters(g, 128, p.Cout / 128)) {
+    *bn_out = 128; *ks_out = 1;
+    if (verbose) fprintf(stderr, "spdm cluster conv %dx%d %d->%d: m_tiles %d k_iters %d -> bn 128, no K split, cluster %d\n", p.H, p.W, p.Cin, p.Cout, m_tiles, k_iters, p.Cout / 128);
+    return;
+  }
+  int bn = bn0;
+  if (bn == 256 && p.Cout == 256 && !wide && m_tiles <= max_active_clusters(g, 128, 8)) bn = 128;
+  const int n_tiles = p.Cout / bn;
+  if (n_tiles > 2) return;
+  for (int ks = 8 / n_tiles; ks >= 2; ks >>= 1) {
+    if (ks * 2 > k_iters || bn / ks < 32) continue;
+    const int mac = max_active_clusters(g, bn, ks * n_tiles);
+    if (verbose) fprintf(stderr, "spdm cluster conv %dx%d %d->%d: m_tiles %d bn %d n_tiles %d k_iters %d ks %d: max active clusters %d\n", p.H, p.W, p.Cin, p.Cout, m_tiles, bn, n_tiles, k_iters, ks, mac);
+    if (m_tiles > mac) continue;   // one wave of co-scheduled clusters
+    *bn_out = bn; *ks_out = ks;
+    return;
+  }
 }
 
 int tc_gemm_cluster_split(const TcGemm* g, int B) {
@@ -1264,22 +1296,9 @@ int tc_gemm_cluster_split(const TcGemm* g, int B) {
   if (p.taps != 9 || p.H != p.Hb) return 0;
   const int rps = p.Hb * p.W;
   if (rps < 4 || rps > 32) return 0;
-  const int m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
-  if ((g->has256 ? 256 : g->block_n) != 128 && !g->has256) return 0;
-  const int bn = cluster_bn(g, m_tiles);
-  const int n_tiles = p.Cout / bn;
-  if (n_tiles > 2) return 0;
-  const int k_iters = (p.W == 1 ? 1 : 3) * (p.H == 1 ? 1 : 3) * p.kb_per_tap;
-  static int verbose = -1;
-  if (verbose < 0) { const char* e = getenv("SPDM_VERBOSE"); verbose = e ? atoi(e) : 0; }
-  for (int ks = 8 / n_tiles; ks >= 2; ks >>= 1) {
-    if (ks * 2 > k_iters || bn / ks < 32) continue;
-    const int mac = max_active_clusters(g, bn, ks * n_tiles);
-    if (verbose) fprintf(stderr, "spdm cluster conv %dx%d %d->%d B=%d: m_tiles %d bn %d n_tiles %d k_iters %d ks %d: max active clusters %d\n", p.H, p.W, p.Cin, p.Cout, B, m_tiles, bn, n_tiles, k_iters, ks, mac);
-    if (m_tiles > mac) continue;   // one wave of co-scheduled clusters
-    return ks;
-  }
-  return 0;
+  int bn, ks;
+  cluster_config(g, (int)(((long long)B * p.H * p.W) / BLOCK_M), &bn, &ks);
+  return ks;
 }
 
 int tc_gemm_launch_cluster(const TcGemm* g, bf16* out, int ld_out, const ApplyArgs* ap, int B, int ks, cudaStream_t s) {
@@ -1291,7 +1310,9 @@ int tc_gemm_launch_cluster(const TcGemm* g, bf16* out, int ld_out, const ApplyAr
   p.dbg = timing ? 2048 : 0;
   p.out = out; p.ld_out = ld_out;
   p.m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
-  const int bn = cluster_bn(g, p.m_tiles);
+  int bn, ks_cfg;
+  cluster_config(g, p.m_tiles, &bn, &ks_cfg);
+  if (bn == 0 || ks_cfg != ks) { snprintf(g_tc_err, sizeof g_tc_err, "cluster conv: inconsistent configuration"); return -1; }
   p.n_tiles = p.Cout / bn;
   p.cl_ks = ks;
   p.total_tiles = p.m_tiles * p.n_tiles * ks;

@@ -523,7 +523,7 @@ template <typename T> struct Fwd {
       GemmW& g = p->gemms[wname];
       TcGemm* tc = get_tc(wname, g, in, ld_in, level);
       const int ks = tc_gemm_cluster_split(tc, Bpad);
-      if (ks < 2) return false;
+      if (ks < 1) return false;
       const int H = p->levelH(level), W = p->levelW(level);
       const double flops = 2.0 * g.Cin * g.Cout * (3.0 * H - 2) * (3.0 * W - 2) * c.B;
       const double bytes = ((double)c.B * H * W * (g.Cin + g.Cout) + (double)g.taps * g.Cin * g.Cout) * 2.0;
