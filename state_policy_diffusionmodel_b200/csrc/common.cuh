@@ -173,6 +173,7 @@ void launch_add_noise(const float* x0, const float* noise, const long long* t, c
 // weight repack (fp32 PyTorch layout -> kernel layout)
 void launch_pack_conv_f32(const float* oihw, float* out, int Cout, int Cin, int k, cudaStream_t s);  // -> [tap][Cin][Cout]
 void launch_pack_conv_bf16(const float* oihw, bf16* out, int Cout, int Cin, int k, cudaStream_t s); // -> [Cout][tap][Cin]
+void launch_pack_conv_fold2_bf16(const float* oihw, bf16* out, int Cout, int Cin, cudaStream_t s);    // W = 2 fold: [2 Cout][9][2 Cin]
 void launch_pack_linear_f32(const float* nk, float* out, int N, int K, int ld_out, int col_off, cudaStream_t s);  // -> [K][ld_out] at col_off
 void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
 void launch_pack_enc_linear(const float* w, float* out, cudaStream_t s);  // (128, 64*12*12 chw) -> [9216 hwc][128]

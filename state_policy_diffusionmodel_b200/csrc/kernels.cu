@@ -1153,6 +1153,24 @@ __global__ void pack_conv_bf16_kernel(const float* __restrict__ oihw, bf16* __re
   const int o = (int)(t / kk);
   out[i] = __float2bfloat16_rn(oihw[((size_t)o * Cin + c) * kk + tap]);
 }
+// 3x3 weights of a conv on a W = 2 map, folded so that the two pixels of an image row become extra input / output channels:
+//   out[(wo*Cout + co)][tap (dy, dx = 0)][wi*Cin + ci] = w[co][ci][dy][(wi - wo) + 1]
+// in the ordinary [Cout'][9][Cin'] layout with Cout' = 2 Cout, Cin' = 2 Cin (the dx != 0 taps of the folded conv stay zero and
+// are never read: a W = 1 geometry skips them).  The folded conv is dense -- no zero-padding taps along W.
+__global__ void pack_conv_fold2_bf16_kernel(const float* __restrict__ oihw, bf16* __restrict__ out, int Cout, int Cin) {
+  pdl_wait();
+  pdl_trigger();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = 2LL * Cout * 3 * 2 * Cin;
+  if (i >= total) return;
+  const int cin2 = (int)(i % (2 * Cin));
+  const long long t = i / (2 * Cin);
+  const int ty = (int)(t % 3);
+  const int co2 = (int)(t / 3);
+  const int wi = cin2 / Cin, ci = cin2 - wi * Cin, wo = co2 / Cout, co = co2 - wo * Cout;
+  const int tx = wi - wo + 1;
+  out[((size_t)co2 * 9 + ty * 3 + 1) * (2 * Cin) + cin2] = __float2bfloat16_rn(oihw[((size_t)co * Cin + ci) * 9 + ty * 3 + tx]);
+}
 __global__ void pack_linear_f32_kernel(const float* __restrict__ nk, float* __restrict__ out, int N, int K, int ld_out, int col_off) {
   pdl_wait();
   pdl_trigger();
@@ -1187,6 +1205,10 @@ void launch_pack_conv_f32(const float* oihw, float* out, int Cout, int Cin, int 
 void launch_pack_conv_bf16(const float* oihw, bf16* out, int Cout, int Cin, int k, cudaStream_t s) {
   const long long total = (long long)Cout * Cin * k * k;
   launch_pdl(pack_conv_bf16_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, oihw, out, Cout, Cin, k * k);
+}
+void launch_pack_conv_fold2_bf16(const float* oihw, bf16* out, int Cout, int Cin, cudaStream_t s) {
+  const long long total = 2LL * Cout * 3 * 2 * Cin;
+  launch_pdl(pack_conv_fold2_bf16_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, oihw, out, Cout, Cin);
 }
 void launch_pack_linear_f32(const float* nk, float* out, int N, int K, int ld_out, int col_off, cudaStream_t s) {
   launch_pdl(pack_linear_f32_kernel, dim3(cdiv((long long)N * K, 256)), dim3(256), 0, s, nk, out, N, K, ld_out, col_off);

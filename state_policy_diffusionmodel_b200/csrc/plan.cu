@@ -66,6 +66,7 @@ struct GemmW {  // a 3x3 convolution or a Linear layer
   int Cin = 0, Cout = 0, taps = 1;
   float* w32 = nullptr;  // [taps][Cin][Cout]   (fp32 path)
   bf16* w16 = nullptr;   // [Cout][taps*Cin]    (bf16 tcgen05 path)
+  bf16* w16_fold = nullptr;  // 3x3 convs of the W = 2 level, inference: [2 Cout][9][2 Cin], the two pixels of a row folded into channels
   float* bias = nullptr; // [Cout] or null
   GemmW* twin = nullptr; // training: the data-gradient GEMM (Cin/Cout exchanged, transposed / tap-flipped weights)
 };
@@ -132,6 +133,7 @@ struct spdm_plan {
   std::map<int, float*> partial;       // split-K fp32 partial tiles, one buffer per concurrent lane (keyed by b0)
   std::map<int, size_t> partial_cap;
   bool no_splitk = false;              // SPDM_NO_SPLITK=1 (A/B switch)
+  bool no_fold = false;                // SPDM_NO_FOLD=1: W = 2 convs as ordinary 9-tap implicit GEMMs (A/B switch)
   bool no_fuse = false;                // SPDM_NO_FUSE_APPLY=1: keep GroupNorm apply as a separate kernel (A/B switch)
   std::vector<char> skip;              // SPDM_SKIP_IDX=i,j,...: launches of one forward (in timed() order) that are NOT issued --
   int timed_idx = 0;                   // timing ablation only (tools/ablate.py), results are garbage
@@ -207,6 +209,11 @@ GemmW& reg_conv3(spdm_plan* p, const std::string& name, int Cin, int Cout) {
   g.Cin = Cin; g.Cout = Cout; g.taps = 9;
   if (p->bf16_mode) g.w16 = p->alloc<bf16>((size_t)9 * Cin * Cout);
   else g.w32 = p->alloc<float>((size_t)9 * Cin * Cout);
+  // the third level of the U-Net is H/4 x 2: a third of the MMAs of a tile-wise 9-tap implicit GEMM there multiply the zero
+  // padding left and right of the two columns.  Folding the column into the channels (K = 3 x 2 Cin, N = 2 Cout over (b, h) rows)
+  // makes the conv dense along W (Fwd::fold_ok)
+  const bool level2 = name.rfind("down2.", 0) == 0 || name.rfind("up1.", 0) == 0;
+  if (p->bf16_mode && level2 && p->W0 == 8 && Cin % 32 == 0 && Cout % 32 == 0) g.w16_fold = p->alloc<bf16>((size_t)2 * Cout * 9 * 2 * Cin);
   p->missing_unet.insert(name + ".weight");
   GemmW* gp = &g;
   bool bfm = p->bf16_mode;
@@ -214,6 +221,7 @@ GemmW& reg_conv3(spdm_plan* p, const std::string& name, int Cin, int Cout) {
     check_shape(name + ".weight", shape, ndim, {Cout, Cin, 3, 3});
     if (bfm) launch_pack_conv_bf16(src, gp->w16, Cout, Cin, 3, s);
     else launch_pack_conv_f32(src, gp->w32, Cout, Cin, 3, s);
+    if (gp->w16_fold && !p->tr) launch_pack_conv_fold2_bf16(src, gp->w16_fold, Cout, Cin, s);  // inference only (Fwd::fold_ok)
     if (gp->twin) {
       if (bfm) launch_pack_conv_dgrad_bf16(src, gp->twin->w16, Cout, Cin, s);
       else launch_pack_conv_dgrad_f32(src, gp->twin->w32, Cout, Cin, s);
@@ -496,6 +504,29 @@ template <typename T> struct Fwd {
     return tc;
   }
 
+  // W = 2 level, inference: run the conv in its folded form (GemmW::w16_fold) -- same memory for input and output, viewed as
+  // [B*H rows][2*C]; needs both to be dense in the channel dimension
+  // Only at batches where the conv's tiles fill the machine anyway: folding halves the number of M tiles, so where the K loop is
+  // split to occupy the SMs (small batch: split-K / cluster path) it would trade parallelism for work.
+  bool fold_ok(const std::string& wname, GemmW& g, const T* in, int ld_in, int level, int ld_out) {
+    if constexpr (sizeof(T) == 2) {
+      if (!(g.taps == 9 && g.w16_fold && !p->tr && !p->no_fold && p->fuse_mode == 0 && p->levelW(level) == 2 && ld_in == g.Cin &&
+            ld_out == g.Cout)) return false;
+      return p->no_splitk || tc_gemm_split(get_tc(wname, g, in, ld_in, level), Bpad) <= 1;
+    }
+    return false;
+  }
+  TcGemm* get_tc_fold(const std::string& wname, GemmW& g, const T* in, int level) {
+    char key[160];
+    snprintf(key, sizeof key, "%s#fold|%p", wname.c_str(), (const void*)in);
+    TcGemm*& tc = p->tc_cache[key];
+    if (!tc) {
+      tc = tc_gemm_create(reinterpret_cast<const bf16*>(in), 2 * g.Cin, g.w16_fold, 2 * g.Cin, 2 * g.Cout, 9, p->levelH(level), 1, p->Bcap);
+      REQUIRE(tc != nullptr, "%s (folded): %s", wname.c_str(), tc_last_error());
+    }
+    return tc;
+  }
+
   // split-K factor for this conv at the current batch (1 = none); sizes the lane's partial buffer on first use
   int split_for(const std::string& wname, const T* in, int ld_in, int level, int Cout) {
     if constexpr (sizeof(T) == 2) {
@@ -503,7 +534,7 @@ template <typename T> struct Fwd {
       const int n = p->levelH(level) * p->levelW(level) * Cout;
       if (n > 16384 || n % 1024) return 1;
       GemmW& g = p->gemms[wname];
-      const int S = tc_gemm_split(get_tc(wname, g, in, ld_in, level), Bpad);
+      const int S = tc_gemm_split(get_tc(wname, g, in, ld_in, level), Bpad);   // (a folded conv is only used where this is 1)
       if (S > 1) {
         const size_t need = (size_t)S * Bpad * n;
         float*& buf = p->partial[c.b0];
@@ -554,7 +585,9 @@ template <typename T> struct Fwd {
     GemmW& g = it->second;
     const int H = p->levelH(level), W = p->levelW(level);
     if constexpr (sizeof(T) == 2) {
-      TcGemm* tc = get_tc(wname, g, in, ld_in, level);
+      const bool fold = !fuse && !resid && ksplit <= 1 && (flags & ~EPI_STATS) == 0 && fold_ok(wname, g, in, ld_in, level, ld_out);
+      TcGemm* tc = fold ? get_tc_fold(wname, g, in, level) : get_tc(wname, g, in, ld_in, level);
+      if (fold) ld_out *= 2;
       // algorithmic work: taps that fall inside the image only, real batch rows only
       const double flops = g.taps == 9 ? 2.0 * g.Cin * g.Cout * (3.0 * H - 2) * (3.0 * W - 2) * c.B
                                        : 2.0 * g.Cin * g.Cout * (double)H * W * c.B;
@@ -935,6 +968,7 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
     if (const char* e = getenv("SPDM_NO_FUSE_APPLY")) p->no_fuse = atoi(e) != 0;
     if (const char* e = getenv("SPDM_FUSE_MODE")) p->fuse_mode = atoi(e);
     if (const char* e = getenv("SPDM_NO_SPLITK")) p->no_splitk = atoi(e) != 0;
+    if (const char* e = getenv("SPDM_NO_FOLD")) p->no_fold = atoi(e) != 0;
     if (const char* e = getenv("SPDM_SKIP_IDX")) {
       p->skip.assign(256, 0);
       for (const char* q = e; *q;) {

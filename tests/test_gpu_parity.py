@@ -431,3 +431,30 @@ def test_bf16_forward_cluster_splitk_geometries(spdm, B):
     # per-sample check: a wrong sample <-> statistics association would hide in a global max-norm
     per = (outs["bf16"] - outs["fp32"]).abs().flatten(1).max(dim=1).values / outs["fp32"].abs().flatten(1).max(dim=1).values
     assert float(per.max()) < 2 * BF16_FWD_TOL
+
+
+def test_bf16_forward_folded_w2_convs(spdm, monkeypatch):
+    """At batches whose tiles fill the machine the 3x3 convs of the H/4 x 2 level run folded (the two pixels of a row become
+    channels: K = 3 x 2 Cin, N = 2 Cout, no zero-padding MMAs along W).  Same maths, other summation order: the folded bf16
+    forward must agree with the unfolded bf16 forward (SPDM_NO_FOLD=1) and with the fp32 CUDA path."""
+    B = 1024
+    sd = fixtures.make_unet_weights(attention=True, seed=0)
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand((B, 1, 31, 5), generator=g)
+    y = torch.randn((B, 1, 10, 135), generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    outs = {}
+    for tag, precision, nofold in (("fp32", "fp32", "0"), ("fold", "bf16", "0"), ("plain", "bf16", "1")):
+        monkeypatch.setenv("SPDM_NO_FOLD", nofold)
+        plan = spdm.DenoisePlan(attention=True, precision=precision, batch_max=B, graph_steps=0)
+        plan.load_unet_state_dict(sd)
+        outs[tag] = plan.unet_forward(x, t, y).float().cpu()
+        if tag != "fp32":
+            # the tap of a folded layer reads the same memory through the natural (B, C, H, W) view
+            _, outs[tag + "_tap"] = plan.debug_forward(x, t, y, "up1", (B, 128, 8, 2))
+        plan.close()
+    assert torch.isfinite(outs["fold"]).all()
+    assert rel(outs["fold"], outs["fp32"]) < BF16_FWD_TOL
+    assert rel(outs["fold"], outs["plain"]) < BF16_FWD_TOL
+    assert rel(outs["fold_tap"], outs["plain_tap"]) < BF16_FWD_TOL
+    assert not torch.equal(outs["fold"], outs["plain"]), "the folded path was not taken"
