@@ -1,0 +1,394 @@
+// attn_head.cu — the head of a SelfAttention block as ONE tcgen05 kernel (sm_100a), for maps of L <= 128 tokens.
+//
+//   x_ln = LayerNorm(x)                                            reference models/Unet_FiLmLayer.py:75
+//   q, k, v = in_proj(x_ln)                                        :76 (nn.MultiheadAttention, 4 heads, batch_first)
+//   att[b, i, h] = softmax_j(q_i . k_j / sqrt(hd)) v_j             :76
+//
+// A 128-token tile holds 128 / L whole samples, so everything up to the attention output is local to it.  CTA = one
+// 128-token tile x one 64-channel block (64 / hd heads):
+//   1. every thread pair normalises one row of x in registers and writes LN(x) as the bf16, K-major, 128B-swizzled A operand;
+//   2. [Q | K | V](128 x 192) = LN(x) · [Wq; Wk; Wv](cb)^T: one tcgen05 chain, N = 192, K = C; the three 64-row weight blocks
+//      arrive by TMA (issued before the programmatic-dependency wait: weights do not depend on the previous kernel);
+//   3. the epilogue adds the bias and writes Q and K as K-major operand tiles and V transposed ([channel][key]) into the shared
+//      memory the A / weight tiles occupied;
+//   4. the attention core is sdpa_tc2's (sdpa_tc.cu): S = Q_h K_h^T into TMEM, two-pass softmax with the block-diagonal sample
+//      mask, P written back to TMEM as bf16 pairs, O_h = P V_h in the TS form of tcgen05.mma, O / rowsum -> att.
+// Replaces three launches of the latency-bound batch-256 step (LayerNorm, in_proj GEMM with its V^T scatter, attention core)
+// and the HBM round trips of x_ln, qkv and V^T.  LayerNorm is recomputed by the C / 64 CTAs of a tile (cheap).
+#include <stdlib.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace {
+
+struct HeadParams {
+  const bf16* x;       // block input [M][ld_x]
+  int ld_x;
+  bf16* out;           // att [M][C]
+  int L, hd, heads_per_blk;
+  float scale_log2;    // log2(e) / sqrt(hd)
+  const float *ln_g, *ln_b;
+  const float* bias;   // in_proj bias [3C]
+};
+
+__device__ __forceinline__ float ex2_approx_h(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int C, bool MASKED>
+__global__ void __launch_bounds__(256, (C <= 128 ? 2 : 1))
+attn_head_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams p) {
+  constexpr int KB = C / 64;
+  constexpr int SA = KB * 16384;       // LN(x): KB blocks of [128 rows][64 ch]
+  constexpr int WBLK = 3 * 8192;       // per k-block: [Wq 64 rows | Wk 64 rows | Wv 64 rows] x 64 k
+  constexpr int SW = KB * WBLK;
+  constexpr int TMEM_COLS = 256;
+  constexpr int LK = 128, HALF = 64;
+  constexpr uint32_t O_COL = 128;
+  constexpr int NCH = C / 16;          // 8-channel chunks per thread: a thread pair shares a row
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + SA;
+  uint8_t* sQ = smem;                  // after the projection GEMM has retired: Q, K, V^T over the A / weight tiles
+  uint8_t* sK = smem + 16384;
+  uint8_t* sVt = smem + 32768;
+  __shared__ __align__(8) uint64_t bar_w;
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_g[C], s_b[C], s_bias[192];
+  __shared__ float s_x0[2][128], s_x1[2][128];   // pair exchange: LayerNorm sums, softmax maximum / sum
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;
+  const int r = (warp & 3) * 32 + lane;          // row of the tile == TMEM lane
+  const int q_row0 = blockIdx.x * 128;
+  const int cb = blockIdx.y;
+  const uint32_t pair_bar = 1 + (warp & 3);      // named barrier of the two warps that own the same 32 rows
+
+  for (int i = tid; i < C; i += 256) { s_g[i] = __ldg(p.ln_g + i); s_b[i] = __ldg(p.ln_b + i); }
+  for (int i = tid; i < 192; i += 256) s_bias[i] = __ldg(p.bias + (i >> 6) * C + cb * 64 + (i & 63));
+  if (tid == 0) {
+    tma_prefetch_desc(&map_w);
+    mbar_init(&bar_w, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+  if (tid == 0) {   // weights: in flight before the dependency wait
+    mbar_expect_tx(&bar_w, SW);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+      for (int j = 0; j < 3; ++j) tma_load_2d(sW + kb * WBLK + j * 8192, &map_w, &bar_w, kb * 64, j * C + cb * 64);
+  }
+  pdl_wait();
+  pdl_trigger();
+
+  // ---------------- 1. LayerNorm of row r (this thread: channels [half*C/2, (half+1)*C/2)) -> A operand ----------------
+  {
+    const bf16* xrow = p.x + (size_t)(q_row0 + r) * p.ld_x + half * (C / 2);
+    uint4 xr[NCH];
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) xr[i] = *reinterpret_cast<const uint4*>(xrow + 8 * i);
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xr[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) s += __low2float(h2[e]) + __high2float(h2[e]);
+    }
+    s_x0[half][r] = s;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    const float mean = (s_x0[0][r] + s_x0[1][r]) * (1.0f / (float)C);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xr[i]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float d0 = __low2float(h2[e]) - mean, d1 = __high2float(h2[e]) - mean;
+        q = fmaf(d0, d0, fmaf(d1, d1, q));
+      }
+    }
+    s_x1[half][r] = q;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    const float rstd = rsqrtf((s_x1[0][r] + s_x1[1][r]) * (1.0f / (float)C) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < NCH; ++i) {
+      const int c = half * (C / 2) + 8 * i;
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xr[i]);
+      uint4 val;
+      __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float y0 = (__low2float(h2[e]) - mean) * rstd * s_g[c + 2 * e] + s_b[c + 2 * e];
+        const float y1 = (__high2float(h2[e]) - mean) * rstd * s_g[c + 2 * e + 1] + s_b[c + 2 * e + 1];
+        o2[e] = __floats2bfloat162_rn(y0, y1);
+      }
+      // k-block c/64, row r, 16-byte chunk (c%64)/8 at (chunk ^ (r & 7)): the canonical 128B swizzle of a K-major tile
+      *reinterpret_cast<uint4*>(sA + (c >> 6) * 16384 + r * 128 + ((((c & 63) >> 3) ^ (r & 7)) << 4)) = val;
+    }
+  }
+  fence_proxy_async_smem();
+  __syncthreads();
+
+  // ---------------- 2. [Q | K | V] = LN(x) · W^T ----------------
+  uint32_t mma_phase = 0;
+  if (tid == 0) {
+    mbar_wait(&bar_w, 0);
+    tc_fence_after();
+    constexpr uint32_t idesc_p = make_idesc(192);
+#pragma unroll
+    for (int kb = 0; kb < KB; ++kb) {
+      const uint64_t da = make_smem_desc(smem_u32(sA + kb * 16384));
+      const uint64_t dw = make_smem_desc(smem_u32(sW + kb * WBLK));
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem, da + (uint64_t)(2 * kk), dw + (uint64_t)(2 * kk), idesc_p, (kb > 0 || kk > 0) ? 1u : 0u);
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, mma_phase);
+  mma_phase ^= 1u;
+  tc_fence_after();
+
+  // ---------------- 3. + bias -> Q, K (K-major tiles) and V^T ([channel][key]) in shared memory ----------------
+  const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+#pragma unroll 1
+  for (int ci = 0; ci < 3; ++ci) {
+    const int c = half * 96 + ci * 32;             // accumulator columns [c, c+32): Q = [0,64), K = [64,128), V = [128,192)
+    uint32_t v[32];
+    tmem_ld_32x32(t_lane + (uint32_t)c, v);
+    tmem_ld_wait();
+    float f[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + s_bias[c + i];
+    if (c < 128) {
+      uint8_t* rowp = (c < 64 ? sQ : sK) + r * 128;
+      const int j0 = (c & 63) >> 3;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint4 val;
+        __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
+        *reinterpret_cast<uint4*>(rowp + (((j0 + j) ^ (r & 7)) << 4)) = val;
+      }
+    } else {
+      // V^T: key block r/64 of [64 channel rows][64 keys]; element (ch, key) at row ch, chunk (key%64)/8 ^ (ch & 7)
+      uint8_t* blk = sVt + (r >> 6) * 8192;
+      const int key = r & 63;
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const int ch = c - 128 + i;
+        *reinterpret_cast<bf16*>(blk + ch * 128 + (((key >> 3) ^ (ch & 7)) << 4) + (key & 7) * 2) = __float2bfloat16_rn(f[i]);
+      }
+    }
+  }
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+
+  // ---------------- 4. attention core (sdpa_tc2 with LK = 128; the key tile is the query tile) ----------------
+  int k_lo = 0, k_hi = LK, wk_lo = 0, wk_hi = LK;
+  if (MASKED) {
+    k_lo = (r / p.L) * p.L;
+    k_hi = k_lo + p.L;
+    const int pos_w = (warp & 3) * 32;
+    wk_lo = (pos_w / p.L) * p.L;
+    wk_hi = ((pos_w + 31) / p.L + 1) * p.L;
+  }
+  const uint32_t idesc_s = make_idesc(LK), idesc_o = make_idesc(p.hd);
+  const int c_begin = half * HALF, c_end = c_begin + HALF;
+
+  for (int h = 0; h < p.heads_per_blk; ++h) {
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t head_off = (uint64_t)((h * p.hd * 2) >> 4);
+      const uint64_t dq = make_smem_desc(smem_u32(sQ)) + head_off;
+      const uint64_t dk = make_smem_desc(smem_u32(sK)) + head_off;
+      for (int kk = 0; kk < p.hd / 16; ++kk) umma_bf16(tmem, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc_s, kk > 0 ? 1u : 0u);
+      umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      if (MASKED && (c + 32 <= wk_lo || c >= wk_hi)) continue;
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + (uint32_t)c, v);
+      tmem_ld_wait();
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) {
+        const float x = __uint_as_float(v[i]);
+        if (!MASKED || (c + i >= k_lo && c + i < k_hi)) m4[i & 3] = fmaxf(m4[i & 3], x);
+      }
+      m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+    }
+    s_x0[half][r] = m;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    m = fmaxf(s_x0[0][r], s_x0[1][r]);
+    const float mscaled = m * p.scale_log2;
+
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      uint32_t packed[16];
+      if (MASKED && (c + 32 <= wk_lo || c >= wk_hi)) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) packed[i] = 0u;
+        tmem_st_32x16(t_lane + (uint32_t)(c_begin + ((c - c_begin) >> 1)), packed);
+        continue;
+      }
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + (uint32_t)c, v);
+      tmem_ld_wait();
+      float s2[2] = {0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        float p0 = ex2_approx_h(fmaf(__uint_as_float(v[i]), p.scale_log2, -mscaled));
+        float p1 = ex2_approx_h(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mscaled));
+        if (MASKED) {
+          if (!(c + i >= k_lo && c + i < k_hi)) p0 = 0.f;
+          if (!(c + i + 1 >= k_lo && c + i + 1 < k_hi)) p1 = 0.f;
+        }
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+        s2[0] += __low2float(b2);
+        s2[1] += __high2float(b2);
+        packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+      }
+      sum += s2[0] + s2[1];
+      tmem_st_32x16(t_lane + (uint32_t)(c_begin + ((c - c_begin) >> 1)), packed);
+    }
+    tmem_st_wait();
+    s_x1[half][r] = sum;
+    tc_fence_before();
+    __syncthreads();
+
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll 1
+      for (int k16 = 0; k16 < LK / 16; ++k16) {
+        const int kb = k16 >> 2, kk = k16 & 3;
+        const uint32_t a_col = (uint32_t)((k16 >= LK / 32 ? HALF : 0) + 8 * (k16 % (LK / 32)));
+        const uint64_t dv = make_smem_desc(smem_u32(sVt + kb * 8192 + h * p.hd * 128)) + (uint64_t)(2 * kk);
+        umma_bf16_ts(tmem + O_COL, tmem + a_col, dv, idesc_o, k16 > 0 ? 1u : 0u);
+      }
+      umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+
+    if (half == 0) {
+      const float inv = 1.f / (s_x1[0][r] + s_x1[1][r]);
+      bf16* orow = p.out + (size_t)(q_row0 + r) * C + cb * 64 + h * p.hd;
+#pragma unroll 1
+      for (int c = 0; c < p.hd; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_lane + O_COL + (uint32_t)c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          if (c + i < p.hd) {
+            float f[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i + e]) * inv;
+            store8(orow + c + i, f);
+          }
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode_h() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess || !p) return nullptr;
+    fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+}  // namespace
+
+struct AttnHead {
+  CUtensorMap map_w;
+  HeadParams p;
+  int C;
+  bool masked;
+};
+
+bool attn_head_supported(int L, int C, int heads) {
+  if (heads <= 0 || C % heads || (C != 64 && C != 128 && C != 256)) return false;
+  const int hd = C / heads;
+  if (hd != 16 && hd != 32 && hd != 64) return false;
+  return L >= 1 && L <= 128 && 128 % L == 0;
+}
+
+AttnHead* attn_head_create(const bf16* w_in_proj, const float* bias, const float* ln_g, const float* ln_b, int C, int L, int heads) {
+  EncodeTiledFn enc = get_encode_h();
+  if (!enc || !attn_head_supported(L, C, heads)) return nullptr;
+  AttnHead* g = new AttnHead();
+  memset(g, 0, sizeof(*g));
+  g->C = C;
+  g->masked = L < 128;
+  const int hd = C / heads;
+  g->p.L = L; g->p.hd = hd; g->p.heads_per_blk = 64 / hd;
+  g->p.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
+  g->p.ln_g = ln_g; g->p.ln_b = ln_b; g->p.bias = bias;
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)3 * C};     // in_proj_weight [3C][C], K-major
+  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  if (enc(&g->map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_in_proj, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+    delete g;
+    return nullptr;
+  }
+  return g;
+}
+void attn_head_destroy(AttnHead* g) { delete g; }
+
+namespace {
+template <int C, bool MASKED>
+void launch_head(const AttnHead* g, const HeadParams& p, long long M, cudaStream_t s) {
+  constexpr int need = (C / 64) * (16384 + 3 * 8192);
+  constexpr int smem = (need < 49152 ? 49152 : need) + 1024;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(attn_head_kernel<C, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  launch_pdl(attn_head_kernel<C, MASKED>, dim3((unsigned)(M / 128), (unsigned)(C / 64)), dim3(256), smem, s, g->map_w, p);
+}
+}  // namespace
+
+void attn_head_launch(const AttnHead* g, const bf16* x, int ld_x, bf16* out, long long M, cudaStream_t s) {
+  HeadParams p = g->p;
+  p.x = x; p.ld_x = ld_x; p.out = out;
+  if (g->C == 64) { if (g->masked) launch_head<64, true>(g, p, M, s); else launch_head<64, false>(g, p, M, s); }
+  else if (g->C == 128) { if (g->masked) launch_head<128, true>(g, p, M, s); else launch_head<128, false>(g, p, M, s); }
+  else { if (g->masked) launch_head<256, true>(g, p, M, s); else launch_head<256, false>(g, p, M, s); }
+}

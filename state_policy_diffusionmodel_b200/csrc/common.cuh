@@ -216,6 +216,14 @@ SdpaTc* sdpa_tc_create(const bf16* qkv, const bf16* vt, int C, int L, int heads,
 void sdpa_tc_destroy(SdpaTc* g);
 void sdpa_tc_launch(const SdpaTc* g, bf16* out, long long M, cudaStream_t s);  // out bf16 [M][C], M % 128 == 0
 
+// fused SelfAttention head (attn_head.cu): att = SDPA(in_proj(LayerNorm(x))) for maps of L <= 128 tokens, one launch --------
+struct AttnHead;
+bool attn_head_supported(int L, int C, int heads);
+// w_in_proj: bf16 [3C][C] (K-major), bias fp32 [3C], ln_g / ln_b fp32 [C]
+AttnHead* attn_head_create(const bf16* w_in_proj, const float* bias, const float* ln_g, const float* ln_b, int C, int L, int heads);
+void attn_head_destroy(AttnHead* g);
+void attn_head_launch(const AttnHead* g, const bf16* x, int ld_x, bf16* out, long long M, cudaStream_t s);  // M % 128 == 0
+
 // fused SelfAttention tail (attn_tc.cu): out = FF(LN(out_proj(att) + x)) + (out_proj(att) + x) ------------------
 struct AttnTail;
 bool attn_tail_supported(int C);

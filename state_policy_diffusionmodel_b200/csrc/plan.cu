@@ -114,6 +114,8 @@ struct spdm_plan {
   void *a_ln[4] = {}, *a_qkv[4] = {}, *a_att[4] = {}, *a_res[4] = {}, *a_ff[4] = {}, *a_vt[4] = {};
   std::map<std::string, SdpaTc*> sdpa_cache;
   std::map<std::string, AttnTail*> tail_cache;
+  std::map<std::string, AttnHead*> head_cache;
+  bool no_head = false;                // SPDM_NO_ATTN_HEAD=1: LayerNorm, in_proj and the attention core as three launches (A/B switch)
   float* stats = nullptr;   // [Bcap][SPDM_MAX_PARTIALS][2]
   float* film = nullptr;    // [Bcap][1792]
   float* cond = nullptr;    // [Bcap][G]
@@ -692,10 +694,28 @@ template <typename T> struct Fwd {
     NormW& n1 = p->norms[name + ".ln"];
     NormW& n2 = p->norms[name + ".ff_self.0"];
     const double ln_bytes = 2.0 * M * C * sizeof(T);
-    timed(p, c.s, PC_LN, 0, ln_bytes, [&] { launch_layernorm<T>(x, ld_x, ln, C, n1.g, n1.b, M, C, c.s); });
+    bool head_done = false;
+    if constexpr (sizeof(T) == 2) {
+      // L <= 128: LayerNorm + in_proj + attention core in one launch (attn_head.cu); the tail kernel follows
+      if (!p->tr && !p->no_head && attn_head_supported(L, C, 4) && attn_tail_supported(C) && !getenv("SPDM_NO_ATTN_TAIL")) {
+        AttnHead*& hk = p->head_cache[name];
+        if (!hk) {
+          GemmW& wi = p->gemms[name + ".attention.in_proj_weight"];
+          hk = attn_head_create(wi.w16, wi.bias, n1.g, n1.b, C, L, 4);
+          REQUIRE(hk != nullptr, "%s: attn_head_create failed", name.c_str());
+        }
+        const long long Mpad = (long long)Bpad * L;
+        timed(p, c.s, PC_SDPA, 6.0 * M * C * C + 4.0 * M * L * C, (2.0 * M * C + 3.0 * C * C) * sizeof(T), [&] {
+          attn_head_launch(hk, reinterpret_cast<const bf16*>(x), ld_x, reinterpret_cast<bf16*>(attn), Mpad, c.s);
+        });
+        head_done = true;
+      }
+    }
+    if (!head_done) timed(p, c.s, PC_LN, 0, ln_bytes, [&] { launch_layernorm<T>(x, ld_x, ln, C, n1.g, n1.b, M, C, c.s); });
     bool tc_sdpa = false;
     if constexpr (sizeof(T) == 2) tc_sdpa = sdpa_tc_supported(L, C, 4);
-    if (tc_sdpa) {
+    if (head_done) {
+    } else if (tc_sdpa) {
       if constexpr (sizeof(T) == 2) {
         SdpaTc*& sd = p->sdpa_cache[name + "|" + std::to_string(c.b0)];
         if (!sd) {
@@ -969,6 +989,7 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
     if (const char* e = getenv("SPDM_FUSE_MODE")) p->fuse_mode = atoi(e);
     if (const char* e = getenv("SPDM_NO_SPLITK")) p->no_splitk = atoi(e) != 0;
     if (const char* e = getenv("SPDM_NO_FOLD")) p->no_fold = atoi(e) != 0;
+    if (const char* e = getenv("SPDM_NO_ATTN_HEAD")) p->no_head = atoi(e) != 0;
     if (const char* e = getenv("SPDM_SKIP_IDX")) {
       p->skip.assign(256, 0);
       for (const char* q = e; *q;) {
@@ -1009,6 +1030,7 @@ extern "C" int spdm_plan_destroy(spdm_plan* p) {
   if (p->enc_tc2) tc_gemm_destroy(p->enc_tc2);
   if (p->enc_tc3) tc_gemm_destroy(p->enc_tc3);
   for (auto& kv : p->sdpa_cache) sdpa_tc_destroy(kv.second);
+  for (auto& kv : p->head_cache) attn_head_destroy(kv.second);
   for (cudaEvent_t e : p->ev_pool) cudaEventDestroy(e);
   for (auto& kv : p->tail_cache) attn_tail_destroy(kv.second);
   for (void* q : p->allocs) cudaFree(q);
