@@ -320,6 +320,257 @@ attn_head_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams p) 
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// L = 256 tokens per sample, C = 64 (sa6 of the default horizon: the 32x8 map, the largest attention block).
+// CTA = one sample: its two 128-token tiles are normalised and projected one after the other (the same 192-column TMEM
+// accumulator and the same A tile are reused), the keys / values of all 256 tokens end up in shared memory, then every
+// (query tile, head) runs sdpa_tc2's LK = 256 core.  256 TMEM columns and 104 KB of shared memory per CTA -> two CTAs per SM.
+// Shared-memory map (R = 1024-aligned base): Q tile 0 [R, +16K) | A tile, later Q tile 1 [R+16K, +16K) | K rows 0..255
+// [R+32K, +32K) | V^T key blocks 0..3 [R+64K, +32K) | weights [R+80K, +24K) -- the weights overlap V^T blocks 2, 3, which are
+// only written by the epilogue of the second tile, after the last projection MMA has retired.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
+attn_head256_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams p) {
+  constexpr int C = 64, LK = 256, HALF = 128;
+  constexpr int TMEM_COLS = 256;
+  constexpr uint32_t O_COL = 64;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = smem + 16384;
+  uint8_t* sK = smem + 32768;
+  uint8_t* sVt = smem + 65536;
+  uint8_t* sW = smem + 81920;
+  __shared__ __align__(8) uint64_t bar_w;
+  __shared__ __align__(8) uint64_t bar_mma;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(16) float s_g[C], s_b[C], s_bias[192];
+  __shared__ float s_x0[2][128], s_x1[2][128];
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int half = warp >> 2;
+  const int r = (warp & 3) * 32 + lane;
+  const long long row0 = (long long)blockIdx.x * 256;   // first token of the sample
+  const uint32_t pair_bar = 1 + (warp & 3);
+
+  for (int i = tid; i < C; i += 256) { s_g[i] = __ldg(p.ln_g + i); s_b[i] = __ldg(p.ln_b + i); }
+  for (int i = tid; i < 192; i += 256) s_bias[i] = __ldg(p.bias + i);   // C = 64: [q | k | v] bias is contiguous
+  if (tid == 0) {
+    tma_prefetch_desc(&map_w);
+    mbar_init(&bar_w, 1);
+    mbar_init(&bar_mma, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_smem;
+  if (tid == 0) {
+    mbar_expect_tx(&bar_w, 3 * 8192);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) tma_load_2d(sW + j * 8192, &map_w, &bar_w, 0, j * C);
+  }
+  pdl_wait();
+  pdl_trigger();
+
+  const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  uint32_t mma_phase = 0;
+#pragma unroll 1
+  for (int t = 0; t < 2; ++t) {
+    // ---- LayerNorm of row t*128 + r (this thread: 32 of its 64 channels) -> A tile ----
+    {
+      const bf16* xrow = p.x + (size_t)(row0 + t * 128 + r) * p.ld_x + half * 32;
+      uint4 xr[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) xr[i] = *reinterpret_cast<const uint4*>(xrow + 8 * i);
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xr[i]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) s += __low2float(h2[e]) + __high2float(h2[e]);
+      }
+      s_x0[half][r] = s;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float mean = (s_x0[0][r] + s_x0[1][r]) * (1.0f / (float)C);
+      float q = 0.f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xr[i]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float d0 = __low2float(h2[e]) - mean, d1 = __high2float(h2[e]) - mean;
+          q = fmaf(d0, d0, fmaf(d1, d1, q));
+        }
+      }
+      s_x1[half][r] = q;
+      asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+      const float rstd = rsqrtf((s_x1[0][r] + s_x1[1][r]) * (1.0f / (float)C) + 1e-5f);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int c = half * 32 + 8 * i;
+        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xr[i]);
+        uint4 val;
+        __nv_bfloat162* o2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float y0 = (__low2float(h2[e]) - mean) * rstd * s_g[c + 2 * e] + s_b[c + 2 * e];
+          const float y1 = (__high2float(h2[e]) - mean) * rstd * s_g[c + 2 * e + 1] + s_b[c + 2 * e + 1];
+          o2[e] = __floats2bfloat162_rn(y0, y1);
+        }
+        *reinterpret_cast<uint4*>(sA + r * 128 + (((c >> 3) ^ (r & 7)) << 4)) = val;
+      }
+    }
+    fence_proxy_async_smem();
+    __syncthreads();
+    // ---- [Q | K | V] of the tile ----
+    if (tid == 0) {
+      if (t == 0) mbar_wait(&bar_w, 0);
+      tc_fence_after();
+      constexpr uint32_t idesc_p = make_idesc(192);
+      const uint64_t da = make_smem_desc(smem_u32(sA)), dw = make_smem_desc(smem_u32(sW));
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem, da + (uint64_t)(2 * kk), dw + (uint64_t)(2 * kk), idesc_p, kk > 0 ? 1u : 0u);
+      umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+    // ---- + bias -> Q tile t, K rows t*128.., V^T key blocks 2t, 2t+1 ----
+#pragma unroll 1
+    for (int ci = 0; ci < 3; ++ci) {
+      const int c = half * 96 + ci * 32;
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + (uint32_t)c, v);
+      tmem_ld_wait();
+      float f[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + s_bias[c + i];
+      if (c < 128) {
+        uint8_t* rowp = (c < 64 ? smem + t * 16384 : sK + t * 16384) + r * 128;
+        const int j0 = (c & 63) >> 3;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint4 val;
+          __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
+          *reinterpret_cast<uint4*>(rowp + (((j0 + j) ^ (r & 7)) << 4)) = val;
+        }
+      } else {
+        uint8_t* blk = sVt + (2 * t + (r >> 6)) * 8192;
+        const int key = r & 63;
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int ch = c - 128 + i;
+          *reinterpret_cast<bf16*>(blk + ch * 128 + (((key >> 3) ^ (ch & 7)) << 4) + (key & 7) * 2) = __float2bfloat16_rn(f[i]);
+        }
+      }
+    }
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+  }
+
+  // ---------------- attention core: 2 query tiles x 4 heads, keys = the 256 tokens of the sample ----------------
+  const uint32_t idesc_s = make_idesc(LK), idesc_o = make_idesc(p.hd);
+  const int c_begin = half * HALF, c_end = c_begin + HALF;
+#pragma unroll 1
+  for (int th = 0; th < 2 * p.heads_per_blk; ++th) {
+    const int t = th / p.heads_per_blk, h = th - t * p.heads_per_blk;
+    if (tid == 0) {
+      tc_fence_after();
+      const uint64_t head_off = (uint64_t)((h * p.hd * 2) >> 4);
+      const uint64_t dq = make_smem_desc(smem_u32(smem + t * 16384)) + head_off;
+      const uint64_t dk = make_smem_desc(smem_u32(sK)) + head_off;
+      for (int kk = 0; kk < p.hd / 16; ++kk) umma_bf16(tmem, dq + (uint64_t)(2 * kk), dk + (uint64_t)(2 * kk), idesc_s, kk > 0 ? 1u : 0u);
+      umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+
+    float m = -INFINITY;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + (uint32_t)c, v);
+      tmem_ld_wait();
+      float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+      m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
+    }
+    s_x0[half][r] = m;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    m = fmaxf(s_x0[0][r], s_x0[1][r]);
+    const float mscaled = m * p.scale_log2;
+
+    float sum = 0.f;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; c += 32) {
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + (uint32_t)c, v);
+      tmem_ld_wait();
+      uint32_t packed[16];
+      float s2[2] = {0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 32; i += 2) {
+        const float p0 = ex2_approx_h(fmaf(__uint_as_float(v[i]), p.scale_log2, -mscaled));
+        const float p1 = ex2_approx_h(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mscaled));
+        const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
+        s2[0] += __low2float(b2);
+        s2[1] += __high2float(b2);
+        packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
+      }
+      sum += s2[0] + s2[1];
+      tmem_st_32x16(t_lane + (uint32_t)(c_begin + ((c - c_begin) >> 1)), packed);
+    }
+    tmem_st_wait();
+    s_x1[half][r] = sum;
+    tc_fence_before();
+    __syncthreads();
+
+    if (tid == 0) {
+      tc_fence_after();
+#pragma unroll 1
+      for (int k16 = 0; k16 < LK / 16; ++k16) {
+        const int kb = k16 >> 2, kk = k16 & 3;
+        const uint32_t a_col = (uint32_t)((k16 >= LK / 32 ? HALF : 0) + 8 * (k16 % (LK / 32)));
+        const uint64_t dv = make_smem_desc(smem_u32(sVt + kb * 8192 + h * p.hd * 128)) + (uint64_t)(2 * kk);
+        umma_bf16_ts(tmem + O_COL, tmem + a_col, dv, idesc_o, k16 > 0 ? 1u : 0u);
+      }
+      umma_commit(&bar_mma);
+    }
+    mbar_wait(&bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+
+    if (half == 0) {
+      const float inv = 1.f / (s_x1[0][r] + s_x1[1][r]);
+      bf16* orow = p.out + (size_t)(row0 + t * 128 + r) * C + h * p.hd;
+      uint32_t v[32];
+      tmem_ld_32x32(t_lane + O_COL, v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 32; i += 8) {
+        if (i < p.hd) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i + e]) * inv;
+          store8(orow + i, f);
+        }
+      }
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+  if (warp == 0) {
+    tc_fence_after();
+    tmem_dealloc<TMEM_COLS>(tmem);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -347,7 +598,7 @@ bool attn_head_supported(int L, int C, int heads) {
   if (heads <= 0 || C % heads || (C != 64 && C != 128 && C != 256)) return false;
   const int hd = C / heads;
   if (hd != 16 && hd != 32 && hd != 64) return false;
-  return L >= 1 && L <= 128 && 128 % L == 0;
+  return (L >= 1 && L <= 128 && 128 % L == 0) || (L == 256 && C == 64);
 }
 
 AttnHead* attn_head_create(const bf16* w_in_proj, const float* bias, const float* ln_g, const float* ln_b, int C, int L, int heads) {
@@ -388,6 +639,13 @@ void launch_head(const AttnHead* g, const HeadParams& p, long long M, cudaStream
 void attn_head_launch(const AttnHead* g, const bf16* x, int ld_x, bf16* out, long long M, cudaStream_t s) {
   HeadParams p = g->p;
   p.x = x; p.ld_x = ld_x; p.out = out;
+  if (p.L == 256) {   // one CTA per sample (C = 64)
+    constexpr int smem = 81920 + 3 * 8192 + 1024;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(attn_head256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+    launch_pdl(attn_head256_kernel, dim3((unsigned)(M / 256)), dim3(256), smem, s, g->map_w, p);
+    return;
+  }
   if (g->C == 64) { if (g->masked) launch_head<64, true>(g, p, M, s); else launch_head<64, false>(g, p, M, s); }
   else if (g->C == 128) { if (g->masked) launch_head<128, true>(g, p, M, s); else launch_head<128, false>(g, p, M, s); }
   else { if (g->masked) launch_head<256, true>(g, p, M, s); else launch_head<256, false>(g, p, M, s); }

@@ -14,25 +14,22 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# launch indices of one UNet_Film forward at batch 256, bf16 path, in issue order (profiles/r01_launches_ddim50_b256_v3.csv):
-# 77 launches -- the 18 deep-level convs are cluster split-K launches with the GroupNorm apply fused behind them
-APPLY = [1, 3, 6, 8, 10, 12, 52, 54, 56, 58, 65, 67, 69, 71]
+# launch indices of one UNet_Film forward at batch 256, bf16 path, in issue order: 67 launches -- the 18 deep-level convs are
+# cluster split-K launches with the GroupNorm apply fused behind them, sa1..sa5 are two launches each (fused head + fused tail)
+APPLY = [1, 3, 6, 8, 10, 12, 44, 46, 48, 50, 55, 57, 59, 61]
 GROUPS = {
     "none": [],
     "gn_apply, separate kernels, 32x8 + 16x4 levels (14)": APPLY,
-    "layernorm (6)": [13, 22, 31, 46, 59, 72],
-    "in_proj (6)": [14, 23, 32, 47, 60, 73],
-    "sdpa (6)": [15, 24, 33, 48, 61, 74],
-    "sdpa sa6 (1)": [74],
-    "attn tail (6)": [16, 25, 34, 49, 62, 75],
-    "sa6 whole (4)": [72, 73, 74, 75],
-    "attention whole (24)": [13, 14, 15, 16, 22, 23, 24, 25, 31, 32, 33, 34, 46, 47, 48, 49, 59, 60, 61, 62, 72, 73, 74, 75],
-    "pool+upsample (6)": [4, 17, 26, 41, 50, 63],
-    "conv 32x8 (5)": [2, 64, 66, 68, 70],
-    "conv 16x4 (8)": [5, 7, 9, 11, 51, 53, 55, 57],
-    "cluster conv+GN 8x2 (8)": [18, 19, 20, 21, 42, 43, 44, 45],
-    "cluster conv+GN 4x1 (10)": [27, 28, 29, 30, 35, 36, 37, 38, 39, 40],
-    "everything but conv_in/outc (75)": list(range(1, 76)),
+    "attention heads sa1-sa5: LN + in_proj + core (5)": [13, 20, 27, 40, 51],
+    "attention tails (6)": [14, 21, 28, 41, 52, 65],
+    "sa6: LN, in_proj, core, tail (4)": [62, 63, 64, 65],
+    "attention whole (14)": [13, 14, 20, 21, 27, 28, 40, 41, 51, 52, 62, 63, 64, 65],
+    "pool+upsample (6)": [4, 15, 22, 35, 42, 53],
+    "conv 32x8 (5)": [2, 54, 56, 58, 60],
+    "conv 16x4 (8)": [5, 7, 9, 11, 43, 45, 47, 49],
+    "cluster conv+GN 8x2 (8)": [16, 17, 18, 19, 36, 37, 38, 39],
+    "cluster conv+GN 4x1 (10)": [23, 24, 25, 26, 29, 30, 31, 32, 33, 34],
+    "everything but conv_in/outc (65)": list(range(1, 66)),
 }
 
 
