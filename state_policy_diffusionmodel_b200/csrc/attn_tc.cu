@@ -51,8 +51,11 @@ __device__ __forceinline__ void store_a_chunk(uint8_t* sA, int r, int c, const f
   }
 }
 
+// 256 threads: two threads per token row, each owns half of the row's C columns in every epilogue (the epilogues -- 128 threads x C
+// columns each -- were the longest part of the C = 256 instances: ~20 us per launch on 8..32 CTAs); the LayerNorm statistics of a
+// row are combined through shared memory and a 64-thread named barrier.
 template <int C>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_constant__ CUtensorMap map_wo,
                  const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const TailParams p) {
   constexpr int KB = C / 64;
@@ -68,10 +71,11 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
   __shared__ __align__(8) uint64_t bar_mma;
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_bo[C], s_b1[C], s_b2[C], s_g[C], s_b[C];  // per-column constants (weights: no dependency)
+  __shared__ float s_ls[2][128], s_lq[2][128];                                // LayerNorm partial sums of the two column halves
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row0 = blockIdx.x * 128;
-  for (int i = tid; i < C; i += 128) {
+  for (int i = tid; i < C; i += 256) {
     s_bo[i] = __ldg(p.bo + i); s_b1[i] = __ldg(p.b1 + i); s_b2[i] = __ldg(p.b2 + i);
     s_g[i] = __ldg(p.ln_g + i); s_b[i] = __ldg(p.ln_b + i);
   }
@@ -111,9 +115,12 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
   };
 
   uint32_t load_phase = 0, mma_phase = 0;
-  const int r = tid;
+  const int half = warp >> 2;
+  const int r = (warp & 3) * 32 + (tid & 31);
+  const int c_lo = half * (C / 2), c_hi = c_lo + C / 2;   // this thread's columns
+  const uint32_t pair_bar = 1 + (warp & 3);
   const long long row = (long long)row0 + r;
-  const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+  const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
 
   // ---------------- GEMM 1: att @ Wo^T ----------------
   if (tid == 0) {
@@ -127,7 +134,7 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
   const bf16* xrow = p.x + row * p.ld_x;
   uint4 xn[4];   // residual row, prefetched one 32-column chunk ahead of the accumulator reads
 #pragma unroll
-  for (int j = 0; j < 4; ++j) xn[j] = *reinterpret_cast<const uint4*>(xrow + 8 * j);
+  for (int j = 0; j < 4; ++j) xn[j] = *reinterpret_cast<const uint4*>(xrow + c_lo + 8 * j);
   mbar_wait(&bar_mma, mma_phase);
   mma_phase ^= 1u;
   tc_fence_after();
@@ -138,11 +145,11 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
   // epilogue 1: a = acc + bo + x  (kept fp32 in TMEM region R), LayerNorm statistics
   float s = 0.f, q = 0.f;
 #pragma unroll 1
-  for (int c = 0; c < C; c += 32) {
+  for (int c = c_lo; c < c_hi; c += 32) {
     uint4 xc[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) xc[j] = xn[j];
-    if (c + 32 < C) {
+    if (c + 32 < c_hi) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) xn[j] = *reinterpret_cast<const uint4*>(xrow + c + 32 + 8 * j);
     }
@@ -167,10 +174,15 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
     tmem_st_32x32(t_lane + (uint32_t)(C + c), v);
   }
   tmem_st_wait();
+  s_ls[half][r] = s;
+  s_lq[half][r] = q;
+  asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+  s = s_ls[0][r] + s_ls[1][r];
+  q = s_lq[0][r] + s_lq[1][r];
   const float mean = s * (1.0f / C);
   const float rstd = rsqrtf(fmaxf(q * (1.0f / C) - mean * mean, 0.f) + 1e-5f);
 #pragma unroll 1
-  for (int c = 0; c < C; c += 32) {
+  for (int c = c_lo; c < c_hi; c += 32) {
     uint32_t v[32];
     tmem_ld_32x32(t_lane + (uint32_t)(C + c), v);
     tmem_ld_wait();
@@ -206,7 +218,7 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
   }
   // epilogue 2: GELU(acc + b1) -> A operand of GEMM 3
 #pragma unroll 1
-  for (int c = 0; c < C; c += 32) {
+  for (int c = c_lo; c < c_hi; c += 32) {
     uint32_t v[32];
     tmem_ld_32x32(t_lane + (uint32_t)c, v);
     tmem_ld_wait();
@@ -240,7 +252,7 @@ attn_tail_kernel(const __grid_constant__ CUtensorMap map_att, const __grid_const
   // epilogue 3: out = acc + b2 + a
   bf16* orow = p.out + row * p.ld_out;
 #pragma unroll 1
-  for (int c = 0; c < C; c += 32) {
+  for (int c = c_lo; c < c_hi; c += 32) {
     uint32_t v[32], a[32];
     tmem_ld_32x32(t_lane + (uint32_t)c, v);
     tmem_ld_32x32(t_lane + (uint32_t)(C + c), a);
@@ -302,7 +314,7 @@ template <int C> void launch_tail(const AttnTail* g, const TailParams& p, long l
   constexpr int smem = (C / 64) * 16384 + C * C * 2 + 1024;
   static bool attr = false;
   if (!attr) { cudaFuncSetAttribute(attn_tail_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-  launch_pdl(attn_tail_kernel<C>, dim3((unsigned)(M / 128)), dim3(128), smem, s, g->map_att, g->map_wo, g->map_w1, g->map_w2, p);
+  launch_pdl(attn_tail_kernel<C>, dim3((unsigned)(M / 128)), dim3(256), smem, s, g->map_att, g->map_wo, g->map_w1, g->map_w2, p);
 }
 }  // namespace
 
