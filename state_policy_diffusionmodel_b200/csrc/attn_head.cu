@@ -31,6 +31,10 @@ struct HeadParams {
   float scale_log2;    // log2(e) / sqrt(hd)
   const float *ln_g, *ln_b;
   const float* bias;   // in_proj bias [3C]
+  // C = 64 with the tail merged in (TAIL kernels): out_proj / ff_self constants and the block output
+  const float *bo, *b1, *b2, *ln2_g, *ln2_b;
+  bf16* y;             // block output [M][ld_y]
+  int ld_y;
 };
 
 __device__ __forceinline__ float ex2_approx_h(float x) {
@@ -39,9 +43,116 @@ __device__ __forceinline__ float ex2_approx_h(float x) {
   return y;
 }
 
-template <int C, bool MASKED>
+__device__ __forceinline__ float gelu_tanh_fast_h(float y) {
+  const float u = 0.7978845608028654f * fmaf(0.044715f * y * y, y, y);
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(u));
+  return fmaf(0.5f * y, th, 0.5f * y);
+}
+// 32 fp32 values of row r, columns [c, c+32) of a 64-column tile -> bf16 -> K-major 128B-swizzled operand tile
+__device__ __forceinline__ void store_tile_chunk(uint8_t* tile, int r, int c, const float f[32]) {
+  uint8_t* rowp = tile + r * 128;
+  const int j0 = c >> 3;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 val;
+    __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) h[e] = __floats2bfloat162_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
+    *reinterpret_cast<uint4*>(rowp + (((j0 + j) ^ (r & 7)) << 4)) = val;
+  }
+}
+
+// The tail of a C = 64 SelfAttention block on one 128-token tile (attn_tc.cu's maths: a = out_proj(att) + x,
+// out = Linear2(GELU(Linear1(LN(a)))) + a), run by the 256 threads of a head kernel that owns all 64 channels of the tile:
+// tile = att as a K-major operand tile (written by the attention epilogue, made visible by the caller), wts = [Wo | W1 | W2]
+// (3 x 8 KB, K-major, TMA), accumulator = TMEM columns [0, 64).  Thread (r, half) owns columns [32 half, 32 half + 32) of row r in
+// every epilogue; the residual a stays in its registers.
+struct Tail64Consts { const float *bo, *b1, *b2, *g, *b; };
+__device__ __forceinline__ void tail64(uint8_t* tile, const uint8_t* wts, uint32_t tmem, uint32_t t_lane, int tid, int r, int half,
+                                       uint32_t pair_bar, const bf16* xrow, bf16* yrow, const Tail64Consts& k, float (*s_x0)[128],
+                                       float (*s_x1)[128], uint64_t* bar_mma, uint32_t& mma_phase) {
+  const int c = half * 32;
+  auto gemm = [&](int w) {
+    if (tid == 0) {
+      tc_fence_after();
+      constexpr uint32_t idesc = make_idesc(64);
+      const uint64_t da = make_smem_desc(smem_u32(tile)), dw = make_smem_desc(smem_u32(wts + w * 8192));
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) umma_bf16(tmem, da + (uint64_t)(2 * kk), dw + (uint64_t)(2 * kk), idesc, kk > 0 ? 1u : 0u);
+      umma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    tc_fence_after();
+  };
+  uint4 xc[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) xc[j] = *reinterpret_cast<const uint4*>(xrow + c + 8 * j);
+  gemm(0);
+  float a[32], f[32];
+  {
+    uint32_t v[32];
+    tmem_ld_32x32(t_lane + (uint32_t)c, v);
+    tmem_ld_wait();
+    float s = 0.f, q = 0.f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&xc[j]);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int i = 8 * j + 2 * e;
+        a[i] = __uint_as_float(v[i]) + k.bo[c + i] + __low2float(h2[e]);
+        a[i + 1] = __uint_as_float(v[i + 1]) + k.bo[c + i + 1] + __high2float(h2[e]);
+        s += a[i] + a[i + 1];
+        q = fmaf(a[i], a[i], fmaf(a[i + 1], a[i + 1], q));
+      }
+    }
+    s_x0[half][r] = s;
+    s_x1[half][r] = q;
+    asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+    s = s_x0[0][r] + s_x0[1][r];
+    q = s_x1[0][r] + s_x1[1][r];
+    const float mean = s * (1.0f / 64.0f);
+    const float rstd = rsqrtf(fmaxf(q * (1.0f / 64.0f) - mean * mean, 0.f) + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = (a[i] - mean) * rstd * k.g[c + i] + k.b[c + i];
+  }
+  store_tile_chunk(tile, r, c, f);       // the MMAs that read att have retired
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  gemm(1);
+  {
+    uint32_t v[32];
+    tmem_ld_32x32(t_lane + (uint32_t)c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = gelu_tanh_fast_h(__uint_as_float(v[i]) + k.b1[c + i]);
+  }
+  store_tile_chunk(tile, r, c, f);
+  fence_proxy_async_smem();
+  tc_fence_before();
+  __syncthreads();
+  gemm(2);
+  {
+    uint32_t v[32];
+    tmem_ld_32x32(t_lane + (uint32_t)c, v);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]) + k.b2[c + i] + a[i];
+#pragma unroll
+    for (int i = 0; i < 32; i += 8) store8(yrow + c + i, f + i);
+  }
+  tc_fence_before();
+  __syncthreads();
+}
+
+template <int C, bool MASKED, bool TAIL>
 __global__ void __launch_bounds__(256, (C <= 128 ? 2 : 1))
-attn_head_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams p) {
+attn_head_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wo,
+                 const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const HeadParams p) {
+  static_assert(!TAIL || C == 64, "the merged tail needs one CTA to own all channels of the tile");
   constexpr int KB = C / 64;
   constexpr int SA = KB * 16384;       // LN(x): KB blocks of [128 rows][64 ch]
   constexpr int WBLK = 3 * 8192;       // per k-block: [Wq 64 rows | Wk 64 rows | Wv 64 rows] x 64 k
@@ -57,6 +168,9 @@ attn_head_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams p) 
   uint8_t* sQ = smem;                  // after the projection GEMM has retired: Q, K, V^T over the A / weight tiles
   uint8_t* sK = smem + 16384;
   uint8_t* sVt = smem + 32768;
+  uint8_t* sWt = smem + 49152;         // TAIL: [Wo | W1 | W2], 3 x 8 KB (own region: prefetched before the dependency wait)
+  __shared__ __align__(8) uint64_t bar_t;
+  __shared__ __align__(16) float s_bo[TAIL ? 64 : 4], s_b1[TAIL ? 64 : 4], s_b2[TAIL ? 64 : 4], s_g2[TAIL ? 64 : 4], s_be2[TAIL ? 64 : 4];
   __shared__ __align__(8) uint64_t bar_w;
   __shared__ __align__(8) uint64_t bar_mma;
   __shared__ uint32_t tmem_base_smem;
@@ -72,8 +186,15 @@ attn_head_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams p) 
 
   for (int i = tid; i < C; i += 256) { s_g[i] = __ldg(p.ln_g + i); s_b[i] = __ldg(p.ln_b + i); }
   for (int i = tid; i < 192; i += 256) s_bias[i] = __ldg(p.bias + (i >> 6) * C + cb * 64 + (i & 63));
+  if (TAIL) {
+    for (int i = tid; i < 64; i += 256) {
+      s_bo[i] = __ldg(p.bo + i); s_b1[i] = __ldg(p.b1 + i); s_b2[i] = __ldg(p.b2 + i);
+      s_g2[i] = __ldg(p.ln2_g + i); s_be2[i] = __ldg(p.ln2_b + i);
+    }
+  }
   if (tid == 0) {
     tma_prefetch_desc(&map_w);
+    if (TAIL) { tma_prefetch_desc(&map_wo); tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_w2); mbar_init(&bar_t, 1); }
     mbar_init(&bar_w, 1);
     mbar_init(&bar_mma, 1);
     fence_barrier_init();
@@ -89,6 +210,12 @@ attn_head_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams p) 
     for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
       for (int j = 0; j < 3; ++j) tma_load_2d(sW + kb * WBLK + j * 8192, &map_w, &bar_w, kb * 64, j * C + cb * 64);
+    if (TAIL) {
+      mbar_expect_tx(&bar_t, 3 * 8192);
+      tma_load_2d(sWt, &map_wo, &bar_t, 0, 0);
+      tma_load_2d(sWt + 8192, &map_w1, &bar_t, 0, 0);
+      tma_load_2d(sWt + 16384, &map_w2, &bar_t, 0, 0);
+    }
   }
   pdl_wait();
   pdl_trigger();
@@ -306,13 +433,28 @@ attn_head_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams p) 
             float f[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i + e]) * inv;
-            store8(orow + c + i, f);
+            if (TAIL) {   // att stays on chip: it overwrites the (consumed) Q columns of this head in the operand tile
+              uint4 val;
+              __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+              *reinterpret_cast<uint4*>(sQ + r * 128 + ((((h * p.hd + c + i) >> 3) ^ (r & 7)) << 4)) = val;
+            } else {
+              store8(orow + c + i, f);
+            }
           }
         }
       }
     }
+    if (TAIL) fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+  }
+  if (TAIL) {
+    if (tid == 0) mbar_wait(&bar_t, 0);
+    const Tail64Consts k{s_bo, s_b1, s_b2, s_g2, s_be2};
+    tail64(sQ, sWt, tmem, t_lane, tid, r, half, pair_bar, p.x + (size_t)(q_row0 + r) * p.ld_x, p.y + (size_t)(q_row0 + r) * p.ld_y, k,
+           s_x0, s_x1, &bar_mma, mma_phase);
   }
   if (warp == 0) {
     tc_fence_after();
@@ -329,8 +471,10 @@ attn_head_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams p) 
 // [R+32K, +32K) | V^T key blocks 0..3 [R+64K, +32K) | weights [R+80K, +24K) -- the weights overlap V^T blocks 2, 3, which are
 // only written by the epilogue of the second tile, after the last projection MMA has retired.
 // ---------------------------------------------------------------------------------------------
+template <bool TAIL>
 __global__ void __launch_bounds__(256, 2)
-attn_head256_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams p) {
+attn_head256_kernel(const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_wo,
+                    const __grid_constant__ CUtensorMap map_w1, const __grid_constant__ CUtensorMap map_w2, const HeadParams p) {
   constexpr int C = 64, LK = 256, HALF = 128;
   constexpr int TMEM_COLS = 256;
   constexpr uint32_t O_COL = 64;
@@ -345,6 +489,9 @@ attn_head256_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams 
   __shared__ uint32_t tmem_base_smem;
   __shared__ __align__(16) float s_g[C], s_b[C], s_bias[192];
   __shared__ float s_x0[2][128], s_x1[2][128];
+  // TAIL: the three tail weight tiles go over the key tiles once the last S MMA has retired
+  __shared__ __align__(8) uint64_t bar_t;
+  __shared__ __align__(16) float s_bo[TAIL ? 64 : 4], s_b1[TAIL ? 64 : 4], s_b2[TAIL ? 64 : 4], s_g2[TAIL ? 64 : 4], s_be2[TAIL ? 64 : 4];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int half = warp >> 2;
@@ -354,8 +501,15 @@ attn_head256_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams 
 
   for (int i = tid; i < C; i += 256) { s_g[i] = __ldg(p.ln_g + i); s_b[i] = __ldg(p.ln_b + i); }
   for (int i = tid; i < 192; i += 256) s_bias[i] = __ldg(p.bias + i);   // C = 64: [q | k | v] bias is contiguous
+  if (TAIL) {
+    for (int i = tid; i < 64; i += 256) {
+      s_bo[i] = __ldg(p.bo + i); s_b1[i] = __ldg(p.b1 + i); s_b2[i] = __ldg(p.b2 + i);
+      s_g2[i] = __ldg(p.ln2_g + i); s_be2[i] = __ldg(p.ln2_b + i);
+    }
+  }
   if (tid == 0) {
     tma_prefetch_desc(&map_w);
+    if (TAIL) { tma_prefetch_desc(&map_wo); tma_prefetch_desc(&map_w1); tma_prefetch_desc(&map_w2); mbar_init(&bar_t, 1); }
     mbar_init(&bar_w, 1);
     mbar_init(&bar_mma, 1);
     fence_barrier_init();
@@ -489,6 +643,12 @@ attn_head256_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams 
     mbar_wait(&bar_mma, mma_phase);
     mma_phase ^= 1u;
     tc_fence_after();
+    if (TAIL && th == 2 * p.heads_per_blk - 1 && tid == 0) {   // the key tiles are dead: tail weights stream in under the last head
+      mbar_expect_tx(&bar_t, 3 * 8192);
+      tma_load_2d(sK, &map_wo, &bar_t, 0, 0);
+      tma_load_2d(sK + 8192, &map_w1, &bar_t, 0, 0);
+      tma_load_2d(sK + 16384, &map_w2, &bar_t, 0, 0);
+    }
 
     float m = -INFINITY;
 #pragma unroll 1
@@ -558,12 +718,29 @@ attn_head256_kernel(const __grid_constant__ CUtensorMap map_w, const HeadParams 
           float f[8];
 #pragma unroll
           for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(v[i + e]) * inv;
-          store8(orow + i, f);
+          if (TAIL) {   // att over the consumed Q columns of this (tile, head)
+            uint4 val;
+            __nv_bfloat162* h2 = reinterpret_cast<__nv_bfloat162*>(&val);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) h2[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+            *reinterpret_cast<uint4*>(smem + t * 16384 + r * 128 + ((((h * p.hd + i) >> 3) ^ (r & 7)) << 4)) = val;
+          } else {
+            store8(orow + i, f);
+          }
         }
       }
     }
+    if (TAIL) fence_proxy_async_smem();
     tc_fence_before();
     __syncthreads();
+  }
+  if (TAIL) {
+    if (tid == 0) mbar_wait(&bar_t, 0);
+    const Tail64Consts k{s_bo, s_b1, s_b2, s_g2, s_be2};
+#pragma unroll 1
+    for (int t = 0; t < 2; ++t)
+      tail64(smem + t * 16384, sK, tmem, t_lane, tid, r, half, pair_bar, p.x + (size_t)(row0 + t * 128 + r) * p.ld_x,
+             p.y + (size_t)(row0 + t * 128 + r) * p.ld_y, k, s_x0, s_x1, &bar_mma, mma_phase);
   }
   if (warp == 0) {
     tc_fence_after();
@@ -588,10 +765,11 @@ EncodeTiledFn get_encode_h() {
 }  // namespace
 
 struct AttnHead {
-  CUtensorMap map_w;
+  CUtensorMap map_w, map_wo, map_w1, map_w2;
   HeadParams p;
   int C;
   bool masked;
+  bool tail;   // C = 64: the whole block (head + tail) in one launch
 };
 
 bool attn_head_supported(int L, int C, int heads) {
@@ -600,8 +778,21 @@ bool attn_head_supported(int L, int C, int heads) {
   if (hd != 16 && hd != 32 && hd != 64) return false;
   return (L >= 1 && L <= 128 && 128 % L == 0) || (L == 256 && C == 64);
 }
+bool attn_head_merges_tail(const AttnHead* g) { return g && g->tail; }
 
-AttnHead* attn_head_create(const bf16* w_in_proj, const float* bias, const float* ln_g, const float* ln_b, int C, int L, int heads) {
+namespace {
+bool encode_w(EncodeTiledFn enc, CUtensorMap* m, const bf16* w, int C, int rows) {
+  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
+  cuuint32_t box[2] = {64, 64};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+}  // namespace
+
+AttnHead* attn_head_create(const bf16* w_in_proj, const float* bias, const float* ln_g, const float* ln_b, int C, int L, int heads,
+                           const AttnHeadTail* tail) {
   EncodeTiledFn enc = get_encode_h();
   if (!enc || !attn_head_supported(L, C, heads)) return nullptr;
   AttnHead* g = new AttnHead();
@@ -612,41 +803,49 @@ AttnHead* attn_head_create(const bf16* w_in_proj, const float* bias, const float
   g->p.L = L; g->p.hd = hd; g->p.heads_per_blk = 64 / hd;
   g->p.scale_log2 = 1.4426950408889634f / sqrtf((float)hd);
   g->p.ln_g = ln_g; g->p.ln_b = ln_b; g->p.bias = bias;
-  cuuint64_t dims[2] = {(cuuint64_t)C, (cuuint64_t)3 * C};     // in_proj_weight [3C][C], K-major
-  cuuint64_t strides[1] = {(cuuint64_t)C * 2};
-  cuuint32_t box[2] = {64, 64};
-  cuuint32_t estr[2] = {1, 1};
-  if (enc(&g->map_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_in_proj, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
-    delete g;
-    return nullptr;
+  bool ok = encode_w(enc, &g->map_w, w_in_proj, C, 3 * C);     // in_proj_weight [3C][C], K-major
+  g->tail = tail != nullptr && C == 64;
+  if (g->tail) {
+    g->p.bo = tail->bo; g->p.b1 = tail->b1; g->p.b2 = tail->b2; g->p.ln2_g = tail->ln_g; g->p.ln2_b = tail->ln_b;
+    ok = ok && encode_w(enc, &g->map_wo, tail->wo, C, C) && encode_w(enc, &g->map_w1, tail->w1, C, C) && encode_w(enc, &g->map_w2, tail->w2, C, C);
+  } else {
+    g->map_wo = g->map_w; g->map_w1 = g->map_w; g->map_w2 = g->map_w;
   }
+  if (!ok) { delete g; return nullptr; }
   return g;
 }
 void attn_head_destroy(AttnHead* g) { delete g; }
 
 namespace {
-template <int C, bool MASKED>
+template <int C, bool MASKED, bool TAIL>
 void launch_head(const AttnHead* g, const HeadParams& p, long long M, cudaStream_t s) {
-  constexpr int need = (C / 64) * (16384 + 3 * 8192);
+  constexpr int need = TAIL ? 49152 + 3 * 8192 : (C / 64) * (16384 + 3 * 8192);
   constexpr int smem = (need < 49152 ? 49152 : need) + 1024;
   static bool attr = false;
-  if (!attr) { cudaFuncSetAttribute(attn_head_kernel<C, MASKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-  launch_pdl(attn_head_kernel<C, MASKED>, dim3((unsigned)(M / 128), (unsigned)(C / 64)), dim3(256), smem, s, g->map_w, p);
+  if (!attr) { cudaFuncSetAttribute(attn_head_kernel<C, MASKED, TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  launch_pdl(attn_head_kernel<C, MASKED, TAIL>, dim3((unsigned)(M / 128), (unsigned)(C / 64)), dim3(256), smem, s, g->map_w, g->map_wo,
+             g->map_w1, g->map_w2, p);
+}
+template <bool TAIL>
+void launch_head256(const AttnHead* g, const HeadParams& p, long long M, cudaStream_t s) {
+  constexpr int smem = 81920 + 3 * 8192 + 1024;
+  static bool attr = false;
+  if (!attr) { cudaFuncSetAttribute(attn_head256_kernel<TAIL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
+  launch_pdl(attn_head256_kernel<TAIL>, dim3((unsigned)(M / 256)), dim3(256), smem, s, g->map_w, g->map_wo, g->map_w1, g->map_w2, p);
 }
 }  // namespace
 
-void attn_head_launch(const AttnHead* g, const bf16* x, int ld_x, bf16* out, long long M, cudaStream_t s) {
+// out: att [M][C] (head only) -- unused when the tail is merged, then x -> y [M][ld_y] is the whole block
+void attn_head_launch(const AttnHead* g, const bf16* x, int ld_x, bf16* out, long long M, cudaStream_t s, bf16* y, int ld_y) {
   HeadParams p = g->p;
-  p.x = x; p.ld_x = ld_x; p.out = out;
+  p.x = x; p.ld_x = ld_x; p.out = out; p.y = y; p.ld_y = ld_y;
   if (p.L == 256) {   // one CTA per sample (C = 64)
-    constexpr int smem = 81920 + 3 * 8192 + 1024;
-    static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(attn_head256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    launch_pdl(attn_head256_kernel, dim3((unsigned)(M / 256)), dim3(256), smem, s, g->map_w, p);
+    if (g->tail) launch_head256<true>(g, p, M, s); else launch_head256<false>(g, p, M, s);
     return;
   }
-  if (g->C == 64) { if (g->masked) launch_head<64, true>(g, p, M, s); else launch_head<64, false>(g, p, M, s); }
-  else if (g->C == 128) { if (g->masked) launch_head<128, true>(g, p, M, s); else launch_head<128, false>(g, p, M, s); }
-  else { if (g->masked) launch_head<256, true>(g, p, M, s); else launch_head<256, false>(g, p, M, s); }
+  if (g->C == 64) {
+    if (g->tail) { if (g->masked) launch_head<64, true, true>(g, p, M, s); else launch_head<64, false, true>(g, p, M, s); }
+    else { if (g->masked) launch_head<64, true, false>(g, p, M, s); else launch_head<64, false, false>(g, p, M, s); }
+  } else if (g->C == 128) { if (g->masked) launch_head<128, true, false>(g, p, M, s); else launch_head<128, false, false>(g, p, M, s); }
+  else { if (g->masked) launch_head<256, true, false>(g, p, M, s); else launch_head<256, false, false>(g, p, M, s); }
 }

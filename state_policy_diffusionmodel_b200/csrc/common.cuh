@@ -219,10 +219,16 @@ void sdpa_tc_launch(const SdpaTc* g, bf16* out, long long M, cudaStream_t s);  /
 // fused SelfAttention head (attn_head.cu): att = SDPA(in_proj(LayerNorm(x))) for maps of L <= 128 tokens, one launch --------
 struct AttnHead;
 bool attn_head_supported(int L, int C, int heads);
+// out_proj / ff_self weights (bf16 [C][C], K-major) and constants: with them and C == 64 (one CTA owns all channels of a tile) the
+// kernel runs the WHOLE SelfAttention block -- attn_head_merges_tail() -- and writes the block output instead of att
+struct AttnHeadTail { const bf16 *wo, *w1, *w2; const float *bo, *b1, *b2, *ln_g, *ln_b; };
 // w_in_proj: bf16 [3C][C] (K-major), bias fp32 [3C], ln_g / ln_b fp32 [C]
-AttnHead* attn_head_create(const bf16* w_in_proj, const float* bias, const float* ln_g, const float* ln_b, int C, int L, int heads);
+AttnHead* attn_head_create(const bf16* w_in_proj, const float* bias, const float* ln_g, const float* ln_b, int C, int L, int heads,
+                           const AttnHeadTail* tail = nullptr);
+bool attn_head_merges_tail(const AttnHead* g);
 void attn_head_destroy(AttnHead* g);
-void attn_head_launch(const AttnHead* g, const bf16* x, int ld_x, bf16* out, long long M, cudaStream_t s);  // M % 128 == 0
+// M % 128 == 0 (256 when L == 256); out = att [M][C], or with a merged tail y = block output [M][ld_y]
+void attn_head_launch(const AttnHead* g, const bf16* x, int ld_x, bf16* out, long long M, cudaStream_t s, bf16* y = nullptr, int ld_y = 0);
 
 // fused SelfAttention tail (attn_tc.cu): out = FF(LN(out_proj(att) + x)) + (out_proj(att) + x) ------------------
 struct AttnTail;

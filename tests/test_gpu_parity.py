@@ -410,11 +410,13 @@ def test_sampling_pipeline_matches_sequential(spdm):
         assert torch.equal(g, w)
 
 
-@pytest.mark.parametrize("B", [24, 256, 512])
+@pytest.mark.parametrize("B", [24, 256, 512, 1536])
 def test_bf16_forward_cluster_splitk_geometries(spdm, B):
     """The deep-level convs change kernel with the batch (cluster split-K + fused GroupNorm for few tiles: cluster sizes
     8 / 4 / 2 at these batches; plain tiles beyond): the bf16 forward must agree with the fp32 CUDA path (itself pinned to
-    the golden vectors at rel 1e-4) at every one of them, including a batch that needs padding to the tile granularity."""
+    the golden vectors at rel 1e-4) at every one of them, including a batch that needs padding to the tile granularity.  The
+    attention blocks change too: fused head + separate tail below ~300 (sa6) / ~1200 (sa5) trajectories, the whole C = 64 block in
+    one launch above (B = 1536 covers both)."""
     sd = fixtures.make_unet_weights(attention=True, seed=0)
     g = torch.Generator().manual_seed(21 + B)
     x = torch.rand((B, 1, 31, 5), generator=g)
