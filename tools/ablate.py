@@ -14,22 +14,23 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# launch indices of one UNet_Film forward at batch 256, bf16 path, in issue order: 67 launches -- the 18 deep-level convs are
-# cluster split-K launches with the GroupNorm apply fused behind them, sa1..sa5 are two launches each (fused head + fused tail)
+# launch indices of one UNet_Film forward at batch 256, bf16 path, in issue order: 65 launches -- the 18 deep-level convs are
+# cluster split-K launches with the GroupNorm apply fused behind them, every attention block is two launches (fused head + tail)
 APPLY = [1, 3, 6, 8, 10, 12, 44, 46, 48, 50, 55, 57, 59, 61]
 GROUPS = {
     "none": [],
     "gn_apply, separate kernels, 32x8 + 16x4 levels (14)": APPLY,
     "attention heads sa1-sa5: LN + in_proj + core (5)": [13, 20, 27, 40, 51],
-    "attention tails (6)": [14, 21, 28, 41, 52, 65],
-    "sa6: LN, in_proj, core, tail (4)": [62, 63, 64, 65],
-    "attention whole (14)": [13, 14, 20, 21, 27, 28, 40, 41, 51, 52, 62, 63, 64, 65],
+    "attention tails (6)": [14, 21, 28, 41, 52, 63],
+    "attention heads: LN + in_proj + core (6)": [13, 20, 27, 40, 51, 62],
+    "sa6: head, tail (2)": [62, 63],
+    "attention whole (12)": [13, 14, 20, 21, 27, 28, 40, 41, 51, 52, 62, 63],
     "pool+upsample (6)": [4, 15, 22, 35, 42, 53],
     "conv 32x8 (5)": [2, 54, 56, 58, 60],
     "conv 16x4 (8)": [5, 7, 9, 11, 43, 45, 47, 49],
     "cluster conv+GN 8x2 (8)": [16, 17, 18, 19, 36, 37, 38, 39],
     "cluster conv+GN 4x1 (10)": [23, 24, 25, 26, 29, 30, 31, 32, 33, 34],
-    "everything but conv_in/outc (65)": list(range(1, 66)),
+    "everything but conv_in/outc (63)": list(range(1, 64)),
 }
 
 
