@@ -760,8 +760,12 @@ conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 // ---------------------------------------------------------------------------------------------
 // WM = weight rows per tile = M of the MMA: 128 (rows >= Cout are TMA zero fill) or 64 for the 64-channel layers, whose
 // accumulator then sits in 16 lanes of each TMEM lane quarter (row i -> lane 32*(i/16) + i%16).
+// 320 threads: warp 0 TMA, warp 1 MMA, warps 2..9 epilogue -- two warps per TMEM lane quarter (warp % 4), each owns half of the
+// tile's 256 pixel columns.  The epilogue (one 2-byte store per channel lane and pixel, half the lanes idle when WM = 64) is what
+// the narrow layers are bound by once the tile's MMAs take only a few microseconds.
+constexpr int SWAP_THREADS = 320;
 template <int STAGES, int WM>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(SWAP_THREADS, 1)
 conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
   constexpr int PIX_BYTES = 2 * A_STAGE_BYTES;           // 256 pixels x 64 ch
   constexpr int W_BYTES = WM * BLOCK_K * 2;              // WM weight rows x 64 k
@@ -793,7 +797,8 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full_bar[0], 1); mbar_init(&tmem_full_bar[1], 1);
-    mbar_init(&tmem_empty_bar[0], 4); mbar_init(&tmem_empty_bar[1], 4);
+    const uint32_t n_epi_w = (blockDim.x >> 5) - 2;   // 4 or 8 epilogue warps (chosen at launch)
+    mbar_init(&tmem_empty_bar[0], n_epi_w); mbar_init(&tmem_empty_bar[1], n_epi_w);   // one arrival per epilogue warp
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
@@ -871,6 +876,12 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     }
   } else {
     const int q = warp & 3;
+    // 8 epilogue warps (launched where a CTA has a single tile and the epilogue is exposed): two warps per lane quarter, each owns
+    // half of the tile's pixel columns.  4 warps (persistent multi-tile launches, where the epilogue hides under the next tile's
+    // MMAs and extra warps only compete for issue slots: measured -1.3 % at batch 4096): every warp walks all 256 columns.
+    const bool split = (blockDim.x >> 5) == 10;
+    const int eh = split ? (warp - 2) >> 2 : 0;
+    const int c_lo = split ? eh * (NPIX / 2) : 0, c_hi = split ? c_lo + NPIX / 2 : NPIX;
     // TMEM lane -> output channel inside the tile
     const bool layout_b = (p.dbg & 1024) != 0;          // M = 64 alternative hypothesis: rows 0..63 in lanes 0..63
     const int ch_local = (WM == 128 || layout_b) ? q * 32 + lane : q * 16 + lane;
@@ -890,6 +901,12 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int ch = c_tile * WM + ch_local;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NPIX);
       float rs = 0.f, rq = 0.f;
+      if ((p.flags & EPI_APPLY) && eh == 1) {   // the fused-apply epilogue keeps its 4-warp form (warps 2..5 walk all columns)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        continue;
+      }
       if (p.flags & EPI_APPLY) {
         // The 256-pixel tile holds NPIX/pps whole samples and every channel (host guarantees Cout <= 128, pps | 256):
         // GroupNorm is tile-local.  Pass 1 over TMEM: per-sample statistics; pass 2: normalise (+GELU/temb/FiLM) and store.
@@ -996,11 +1013,11 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       }
       if (active) {
 #pragma unroll 1
-        for (int c = 0; c < NPIX; c += 32) {
+        for (int c = c_lo; c < c_hi; c += 32) {
           uint32_t v[32];
           tmem_ld_32x32(t_addr + (uint32_t)c, v);
           tmem_ld_wait();
-          if (c + 32 == NPIX) {
+          if (c + 32 == c_hi) {
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
@@ -1016,14 +1033,17 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
             rs += (s4[0] + s4[1]) + (s4[2] + s4[3]);
             rq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
-            const int span = pps < NPIX ? pps : NPIX;   // columns per (sample, tile)
+            // columns of one sample inside this warp's half of the tile; a sample of >= 256 pixels spans both halves and gets one
+            // partial slot per half
+            const bool both = split && pps >= NPIX;
+            const int span = both ? NPIX / 2 : (pps < NPIX ? pps : NPIX);
             if ((c + 32) % span == 0) {                 // end of a sample's columns: publish this warp's partial
 #pragma unroll
               for (int o = 16; o > 0; o >>= 1) { rs += __shfl_xor_sync(0xffffffffu, rs, o); rq += __shfl_xor_sync(0xffffffffu, rq, o); }
               if (lane == 0) {
                 const long long b = (row0 + c) / pps;
                 const int tile_in_sample = (int)(pt % tiles_per_sample);
-                const int slot = (tile_in_sample * c_tiles + c_tile) * nw + q;
+                const int slot = both ? ((tile_in_sample * c_tiles + c_tile) * nw + q) * 2 + eh : (tile_in_sample * c_tiles + c_tile) * nw + q;
                 float* dst = p.stats + ((size_t)b * p.P + slot) * 2;
                 dst[0] = rs; dst[1] = rq;
               }
@@ -1350,7 +1370,9 @@ int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const f
     p.total_tiles = (p.m_tiles / 2) * p.n_tiles;
     const int pps = p.H * p.W;
     const int nw = p.Cout >= BLOCK_M ? 4 : p.Cout / 32;
-    p.P = (pps > 256 ? pps / 256 : 1) * p.n_tiles * nw;
+    const int threads = p.total_tiles <= 2 * num_sms() ? SWAP_THREADS : NUM_THREADS;   // 8 epilogue warps only where the epilogue is exposed (<= 2 tiles per CTA)
+    const int halves = (threads == SWAP_THREADS && pps >= 256) ? 2 : 1;   // then a sample of >= 256 pixels gets one partial per column half
+    p.P = (pps > 256 ? pps / 256 : 1) * p.n_tiles * nw * halves;
     constexpr int STG = 4;
     constexpr int smem = STG * (2 * A_STAGE_BYTES + BLOCK_M * BLOCK_K * 2) + 1024;
     static int m64_mode = -1;  // SPDM_M64: 0 = off, 1 = on (TMEM layout A), 2 = on (layout B)
@@ -1358,17 +1380,17 @@ int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const f
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
     if (p.Cout == 64 && !fuse && m64_mode > 0) {  // 64-row MMA: no zero rows, half the operand-read time per instruction
       const int nw64 = m64_mode == 2 ? 2 : 4;
-      p.P = (pps > 256 ? pps / 256 : 1) * p.n_tiles * nw64;
+      p.P = (pps > 256 ? pps / 256 : 1) * p.n_tiles * nw64 * halves;
       if (m64_mode == 2) p.dbg |= 1024;
       static bool attr64 = false;
       if (!attr64) { cudaFuncSetAttribute(conv_tc_swap_kernel<STG, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr64 = true; }
-      launch_pdl(conv_tc_swap_kernel<STG, 64>, dim3(grid), dim3(NUM_THREADS), smem, s, g->map_a, g->map_b, p);
+      launch_pdl(conv_tc_swap_kernel<STG, 64>, dim3(grid), dim3(threads), smem, s, g->map_a, g->map_b, p);
       ++g_tc_launches;
       return p.P;
     }
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(conv_tc_swap_kernel<STG, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    launch_pdl(conv_tc_swap_kernel<STG, 128>, dim3(grid), dim3(NUM_THREADS), smem, s, g->map_a, g->map_wswap, p);
+    launch_pdl(conv_tc_swap_kernel<STG, 128>, dim3(grid), dim3(threads), smem, s, g->map_a, g->map_wswap, p);
     ++g_tc_launches;
     return p.P;
   }
