@@ -473,8 +473,11 @@ __device__ __forceinline__ void st_dsmem_v2(uint32_t addr, float a, float b) {
   asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(a), "f"(b) : "memory");
 }
 
+// 320 threads: warp 0 TMA, warp 1 MMA, warps 2..9 dump the accumulator (two warps per TMEM lane quarter, half of the columns each);
+// the reduction and the apply phase are walked by all 320 threads.
+constexpr int CL_THREADS = 320;
 template <int BLOCK_N, int STAGES>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+__global__ void __launch_bounds__(CL_THREADS, 1)
 conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
   constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
   constexpr int TMEM_COLS = BLOCK_N <= 128 ? 128 : 256;
@@ -601,8 +604,9 @@ conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     tc_fence_after();
     tstamp[1] = clock64();
     const uint32_t t_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+    const int eh = (warp - 2) >> 2;
 #pragma unroll 1
-    for (int c = 0; c < BLOCK_N; c += 32) {
+    for (int c = eh * (BLOCK_N / 2); c < (eh + 1) * (BLOCK_N / 2); c += 32) {
       uint32_t v[32];
       tmem_ld_32x32(t_addr + (uint32_t)c, v);
       tmem_ld_wait();
@@ -618,8 +622,8 @@ conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   cluster_sync_all();   // every partial tile of the cluster is in shared memory
   tstamp[3] = clock64();
 
-  // ---- the slice block [128 rows][Wd] is walked as a flat list of float4 by all 192 threads: thread t takes float4
-  //      t + 192 k, so a warp reads contiguous 512-byte runs of the remote tiles (the SM-to-SM network is the bound of this
+  // ---- the slice block [128 rows][Wd] is walked as a flat list of float4 by all 320 threads: thread t takes float4
+  //      t + 320 k, so a warp reads contiguous 512-byte runs of the remote tiles (the SM-to-SM network is the bound of this
   //      phase: ~12 B/clk/SM measured) and later writes contiguous bf16 runs of the output ----
   const int rps = p.Hb * p.W;                    // rows per sample (4..32, power of two)
   const int ns = BLOCK_M / rps;                  // samples of the tile
@@ -637,13 +641,13 @@ conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     // (tried: keeping the per-run sums in registers and doing all warp reductions after a fully unrolled loop -- 198 registers,
     //  reduce phase 6.7-10 K cycles instead of 4.6-8 K: the phase is bound by the remote loads, not by the shuffle chains)
 #pragma unroll 1
-    for (int i0 = tid; i0 < n4; i0 += 2 * NUM_THREADS) {   // 2 * cl_ks remote 16-byte loads in flight per thread
+    for (int i0 = tid; i0 < n4; i0 += 2 * CL_THREADS) {   // 2 * cl_ks remote 16-byte loads in flight per thread
       float4 v[8][2];
       int off[2];
       bool ok[2];
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
-        const int i = i0 + u * NUM_THREADS;
+        const int i = i0 + u * CL_THREADS;
         ok[u] = i < n4;
         const int row = i >> lw4, c4 = i & (W4 - 1);
         off[u] = ok[u] ? row * RS + c4 * 4 : 0;
@@ -671,7 +675,7 @@ conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) { ps += __shfl_xor_sync(0xffffffffu, ps, o); pq += __shfl_xor_sync(0xffffffffu, pq, o); }
         // the 32 float4 of a warp are 128 / Wd whole rows of ONE sample (rps >= 4 rows, aligned): slot = first index / 32
-        if (lane == 0 && ok[u]) { const int q = (i0 + u * NUM_THREADS) >> 5; s_part[q][0] = ps; s_part[q][1] = pq; }
+        if (lane == 0 && ok[u]) { const int q = (i0 + u * CL_THREADS) >> 5; s_part[q][0] = ps; s_part[q][1] = pq; }
       }
     }
     __syncthreads();
@@ -701,7 +705,7 @@ conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     const int ch0 = n0 + ks * Wd;
     const bool film_smem = p.ap.film && ns * 2 * Wd <= 4096;
 #pragma unroll 4
-    for (int i = tid; i < n4; i += NUM_THREADS) {
+    for (int i = tid; i < n4; i += CL_THREADS) {
       const int row = i >> lw4, c = (i & (W4 - 1)) * 4;
       const int sm = row >> lrps;
       const float A = s_mr[sm][0], Bm = s_mr[sm][1];
@@ -1239,7 +1243,7 @@ static cudaError_t launch_cluster_cfg(const CUtensorMap& ma, const CUtensorMap& 
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)(p.m_tiles * cs));
-  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.blockDim = dim3(CL_THREADS);
   cfg.dynamicSmemBytes = smem_bytes<BLOCK_N, STAGES>();
   cfg.stream = s;
   cudaLaunchAttribute at[2];
