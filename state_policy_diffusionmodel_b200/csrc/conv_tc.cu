@@ -784,7 +784,7 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_part[2][16][4][2];  // EPI_APPLY: per-sample, per-warp (sum, sumsq); double-buffered like TMEM
+  __shared__ float s_part[2][16][4][2][2];  // EPI_APPLY: per-sample, per-warp (lane quarter, column half) (sum, sumsq); double-buffered like TMEM
   __shared__ float s_mr[2][16][2];       // per-sample (mean, rstd)
 
   const int warp = threadIdx.x >> 5;
@@ -905,19 +905,15 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const int ch = c_tile * WM + ch_local;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NPIX);
       float rs = 0.f, rq = 0.f;
-      if ((p.flags & EPI_APPLY) && eh == 1) {   // the fused-apply epilogue keeps its 4-warp form (warps 2..5 walk all columns)
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
-        continue;
-      }
       if (p.flags & EPI_APPLY) {
         // The 256-pixel tile holds NPIX/pps whole samples and every channel (host guarantees Cout <= 128, pps | 256):
         // GroupNorm is tile-local.  Pass 1 over TMEM: per-sample statistics; pass 2: normalise (+GELU/temb/FiLM) and store.
         const int n_s = NPIX / pps;
+        const int span2 = pps < c_hi - c_lo ? pps : c_hi - c_lo;   // columns of one sample inside this warp's column range
+        const int n_epi_thr = split ? 256 : 128;
         if (active) {
 #pragma unroll 1
-          for (int c = 0; c < NPIX; c += 32) {
+          for (int c = c_lo; c < c_hi; c += 32) {
             uint32_t v[32];
             tmem_ld_32x32(t_addr + (uint32_t)c, v);
             tmem_ld_wait();
@@ -927,10 +923,10 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
               for (int i = 0; i < 32; ++i) { const float f = __uint_as_float(v[i]); s4[i & 3] += f; q4[i & 3] = fmaf(f, f, q4[i & 3]); }
               rs += (s4[0] + s4[1]) + (s4[2] + s4[3]);
               rq += (q4[0] + q4[1]) + (q4[2] + q4[3]);
-              if ((c + 32) % pps == 0) {
+              if ((c + 32) % span2 == 0) {
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) { rs += __shfl_xor_sync(0xffffffffu, rs, o); rq += __shfl_xor_sync(0xffffffffu, rq, o); }
-                if (lane == 0) { s_part[acc][c / pps][q][0] = rs; s_part[acc][c / pps][q][1] = rq; }
+                if (lane == 0) { s_part[acc][c / pps][q][eh][0] = rs; s_part[acc][c / pps][q][eh][1] = rq; }
                 rs = 0.f; rq = 0.f;
               }
             } else {  // pps == 16
@@ -946,25 +942,28 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
                 sb += __shfl_xor_sync(0xffffffffu, sb, o); qb += __shfl_xor_sync(0xffffffffu, qb, o);
               }
               if (lane == 0) {
-                s_part[acc][c / 16][q][0] = sa; s_part[acc][c / 16][q][1] = qa;
-                s_part[acc][c / 16 + 1][q][0] = sb; s_part[acc][c / 16 + 1][q][1] = qb;
+                s_part[acc][c / 16][q][eh][0] = sa; s_part[acc][c / 16][q][eh][1] = qa;
+                s_part[acc][c / 16 + 1][q][eh][0] = sb; s_part[acc][c / 16 + 1][q][eh][1] = qb;
               }
             }
           }
         }
-        epi_bar_sync();
+        asm volatile("bar.sync 1, %0;" ::"r"(n_epi_thr) : "memory");
         {
-          const int et = (int)threadIdx.x - 64;  // 0..127 over the epilogue warps
+          const int et = (int)threadIdx.x - 64;  // 0..127 (255) over the epilogue warps
           if (et >= 0 && et < n_s) {
+            // column halves that hold pixels of sample et (one, or both when the sample spans the whole tile)
+            const int h_lo = split ? (et * pps) / (NPIX / 2) : 0, h_hi = split ? ((et + 1) * pps - 1) / (NPIX / 2) : 0;
             float ts = 0.f, tq = 0.f;
-            for (int j = 0; j < nw; ++j) { ts += s_part[acc][et][j][0]; tq += s_part[acc][et][j][1]; }
+            for (int j = 0; j < nw; ++j)
+              for (int hh = h_lo; hh <= h_hi; ++hh) { ts += s_part[acc][et][j][hh][0]; tq += s_part[acc][et][j][hh][1]; }
             const float inv_n = 1.0f / ((float)pps * (float)p.Cout);
             const float mean = ts * inv_n;
             s_mr[acc][et][0] = mean;
             s_mr[acc][et][1] = rsqrtf(fmaxf(tq * inv_n - mean * mean, 0.f) + p.ap.eps);
           }
         }
-        epi_bar_sync();
+        asm volatile("bar.sync 1, %0;" ::"r"(n_epi_thr) : "memory");
         if (active) {
           const float g = __ldg(p.ap.gamma + ch), be = __ldg(p.ap.beta + ch);
           const long long b_first = row0 / pps;
@@ -987,11 +986,11 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             }
           };
 #pragma unroll 1
-          for (int c = 0; c < NPIX; c += 32) {
+          for (int c = c_lo; c < c_hi; c += 32) {
             uint32_t v[32];
             tmem_ld_32x32(t_addr + (uint32_t)c, v);
             tmem_ld_wait();
-            if (c + 32 == NPIX) {
+            if (c + 32 == c_hi) {
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
