@@ -155,6 +155,9 @@ template <typename T> void launch_layernorm(const T* in, int ld_in, T* out, int 
 template <typename T> void launch_sdpa(const T* qkv, T* out, int B, int L, int C, int heads, cudaStream_t s);
 // inc.first + the sample's GroupNorm partial sums (P = 1) in one launch
 template <typename T> void launch_conv_in(const float* x, const float* w, T* out, float* stats, int B, int H, int W, int rows, int dim, int lh, int lw, cudaStream_t s);
+// bf16 path, H*W == 256: inc.first + GroupNorm + GELU in one launch, out = activated map [B*256][64]
+void launch_conv_in_gn(const float* x, const float* w, const float* gamma, const float* beta, bf16* out, int B, int H, int W, int rows,
+                       int dim, int lh, int lw, cudaStream_t s);
 // outc fused with the posterior update of the graphed loop (a.dyn != null); act = last activation [B*H*W][ld]
 template <typename T> void launch_outc_step(const StepArgs& a, const T* act, int ld, const float* w, const float* bias, int H, int W, int C, int rows, int dim, int lh, int lw, cudaStream_t s);
 template <typename T> void launch_outc(const T* x, int ld, const float* w, const float* bias, float* eps, int B, int H, int W, int C, int rows, int dim, int lh, int lw, cudaStream_t s);

@@ -694,6 +694,67 @@ __global__ void __launch_bounds__(256) conv_in_kernel(const float* __restrict__ 
   }
 }
 
+// inc.first + GroupNorm(1, 64) + GELU of the default 32x8 map in ONE kernel (bf16 path): the block already owns the whole sample,
+// so its 256 x 64 outputs stay in registers (8 pixels x 8 channels per thread) between the statistics and the apply --
+// conv_in_kernel + apply_kernel without the raw round trip (at batch 4096: 104 + 140 us of the step).
+__global__ void __launch_bounds__(256) conv_in_gn_kernel(const float* __restrict__ x, const float* __restrict__ w /*[9][64]*/,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                         bf16* __restrict__ out, int H, int W, int rows, int dim, int lh, int lw, float eps) {
+  extern __shared__ float csm[];  // [9*64] weights, then [rows*dim] sample
+  float* sw = csm;
+  float* sx = csm + 9 * 64;
+  const int tid = threadIdx.x, b = blockIdx.x;
+  for (int i = tid; i < 9 * 64; i += 256) sw[i] = __ldg(w + i);
+  const int c8 = (tid & 7) << 3;
+  float g[8], be[8];
+  load8(gamma + c8, g);
+  load8(beta + c8, be);
+  pdl_wait();
+  pdl_trigger();
+  for (int i = tid; i < rows * dim; i += 256) sx[i] = x[(size_t)b * rows * dim + i];
+  __syncthreads();
+  float acc[8][8];
+  float s = 0.f, q = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {                 // H * W == 256 pixels: 8 per thread
+    const int px = (tid >> 3) + 32 * j;
+    const int hh = px / W, ww = px - hh * W;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) acc[j][i] = 0.f;
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+      const int sh = hh + tap / 3 - 1 - lh, sw_ = ww + tap % 3 - 1 - lw;
+      if (sh < 0 || sh >= rows || sw_ < 0 || sw_ >= dim) continue;
+      const float xv = sx[sh * dim + sw_];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[j][i] = fmaf(xv, sw[tap * 64 + c8 + i], acc[j][i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { s += acc[j][i]; q = fmaf(acc[j][i], acc[j][i], q); }
+  }
+  __shared__ float ss[8], sq[8];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if ((tid & 31) == 0) { ss[tid >> 5] = s; sq[tid >> 5] = q; }
+  __syncthreads();
+  float ts = 0.f, tq = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { ts += ss[i]; tq += sq[i]; }
+  const float inv_n = 1.0f / (256.0f * 64.0f);
+  const float mean = ts * inv_n;
+  const float rstd = rsqrtf(fmaxf(tq * inv_n - mean * mean, 0.f) + eps);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { const float ga = rstd * g[i]; be[i] = fmaf(-mean, ga, be[i]); g[i] = ga; }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int px = (tid >> 3) + 32 * j;
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = gelu_tanh_fast(fmaf(acc[j][i], g[i], be[i]));
+    store8(out + ((size_t)b * 256 + px) * 64 + c8, y);
+  }
+}
+
 template <typename T>
 __global__ void outc_kernel(const T* __restrict__ x, int ld, const float* __restrict__ w, const float* __restrict__ bias, float* __restrict__ eps,
                             long long total, int H, int W, int C, int rows, int dim, int lh, int lw) {
@@ -732,6 +793,12 @@ __global__ void to_nchw_kernel(const T* __restrict__ in, int ld, float* __restri
 template <typename T> void launch_conv_in(const float* x, const float* w, T* out, float* stats, int B, int H, int W, int rows, int dim, int lh, int lw, cudaStream_t s) {
   const size_t smem = (size_t)(9 * 64 + rows * dim) * sizeof(float);
   launch_pdl(conv_in_kernel<T>, dim3(B), dim3(256), smem, s, x, w, out, stats, H, W, rows, dim, lh, lw);
+  COUNT_LAUNCH();
+}
+void launch_conv_in_gn(const float* x, const float* w, const float* gamma, const float* beta, bf16* out, int B, int H, int W, int rows,
+                       int dim, int lh, int lw, cudaStream_t s) {
+  const size_t smem = (size_t)(9 * 64 + rows * dim) * sizeof(float);
+  launch_pdl(conv_in_gn_kernel, dim3(B), dim3(256), smem, s, x, w, gamma, beta, out, H, W, rows, dim, lh, lw, 1e-5f);
   COUNT_LAUNCH();
 }
 template <typename T> void launch_outc(const T* x, int ld, const float* w, const float* bias, float* eps, int B, int H, int W, int C, int rows, int dim, int lh, int lw, cudaStream_t s) {

@@ -640,12 +640,13 @@ template <typename T> struct Fwd {
 
   // DoubleConvolution (models/Unet_FiLmLayer.py:85-115); `first_done`: raw already holds conv1's output.
   // On the tensor-core path GroupNorm apply runs inside the conv epilogue whenever a tile holds whole samples.
+  // first_done: 1 = raw already holds conv1's output (+ statistics), 2 = h already holds GELU(GN(conv1))
   void double_conv(const std::string& name, const T* in, int ld_in, int Cout, int level, T* out, int ld_out, const StageInfo* st,
-                   bool first_done = false) {
+                   int first_done = 0) {
     T* raw = act(p->raw[level], level);
     T* h = act(p->hbuf[level], level);
     const bool tap1 = p->tap_out && p->tap_name == name + ".first", tap2 = p->tap_out && p->tap_name == name + ".second";
-    bool fused = false;
+    bool fused = first_done == 2;
     const long long Mpad = (long long)Bpad * p->levelH(level) * p->levelW(level);
     if (!first_done) {
       const int S = tap1 ? 1 : split_for(name + ".first", in, ld_in, level, Cout);
@@ -778,11 +779,24 @@ template <typename T> struct Fwd {
     T* cat3 = act(p->cat[0], 0); T* cat2 = act(p->cat[1], 1); T* cat1 = act(p->cat[2], 2);
     // ---- inc ----
     const double hw0 = (double)p->H0 * p->W0;
-    timed(p, c.s, PC_IO, 2.0 * 9 * 64 * hw0 * c.B, c.B * hw0 * 64 * sizeof(T), [&] {
-      launch_conv_in<T>(c.x, p->w_in, act(p->raw[0], 0), stats(), c.B, p->H0, p->W0, rows, dim, p->lh, p->lw, c.s);
-    });
+    bool inc_applied = false;
+    if constexpr (sizeof(T) == 2) {
+      // default horizon: the first conv, its GroupNorm and the GELU in one launch (the block owns the whole 32x8 sample)
+      if (p->H0 * p->W0 == 256 && !p->tr && !(p->tap_out && p->tap_name == "inc.first") && !getenv("SPDM_NO_CONV_IN_GN")) {
+        NormW& n0 = p->norms["inc.norm"];
+        timed(p, c.s, PC_IO, 2.0 * 9 * 64 * hw0 * c.B, c.B * hw0 * 64 * sizeof(T), [&] {
+          launch_conv_in_gn(c.x, p->w_in, n0.g, n0.b, reinterpret_cast<bf16*>(act(p->hbuf[0], 0)), c.B, p->H0, p->W0, rows, dim, p->lh, p->lw, c.s);
+        });
+        inc_applied = true;
+      }
+    }
+    if (!inc_applied) {
+      timed(p, c.s, PC_IO, 2.0 * 9 * 64 * hw0 * c.B, c.B * hw0 * 64 * sizeof(T), [&] {
+        launch_conv_in<T>(c.x, p->w_in, act(p->raw[0], 0), stats(), c.B, p->H0, p->W0, rows, dim, p->lh, p->lw, c.s);
+      });
+    }
     curP = 1;
-    double_conv("inc", nullptr, 0, 64, 0, cat3 + 64, 128, nullptr, true);  // x1 -> skip slot of up3
+    double_conv("inc", nullptr, 0, 64, 0, cat3 + 64, 128, nullptr, inc_applied ? 2 : 1);  // x1 -> skip slot of up3
     tap("x1", cat3 + 64, 128, 64, 0);
     tap("inc", cat3 + 64, 128, 64, 0);
 

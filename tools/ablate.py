@@ -14,23 +14,23 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
-# launch indices of one UNet_Film forward at batch 256, bf16 path, in issue order: 65 launches -- the 18 deep-level convs are
+# launch indices of one UNet_Film forward at batch 256, bf16 path, in issue order: 64 launches (conv_in carries its GroupNorm + GELU) -- the 18 deep-level convs are
 # cluster split-K launches with the GroupNorm apply fused behind them, every attention block is two launches (fused head + tail)
-APPLY = [1, 3, 6, 8, 10, 12, 44, 46, 48, 50, 55, 57, 59, 61]
+APPLY = [2, 5, 7, 9, 11, 43, 45, 47, 49, 54, 56, 58, 60]
 GROUPS = {
     "none": [],
-    "gn_apply, separate kernels, 32x8 + 16x4 levels (14)": APPLY,
-    "attention heads sa1-sa5: LN + in_proj + core (5)": [13, 20, 27, 40, 51],
-    "attention tails (6)": [14, 21, 28, 41, 52, 63],
-    "attention heads: LN + in_proj + core (6)": [13, 20, 27, 40, 51, 62],
-    "sa6: head, tail (2)": [62, 63],
-    "attention whole (12)": [13, 14, 20, 21, 27, 28, 40, 41, 51, 52, 62, 63],
-    "pool+upsample (6)": [4, 15, 22, 35, 42, 53],
-    "conv 32x8 (5)": [2, 54, 56, 58, 60],
-    "conv 16x4 (8)": [5, 7, 9, 11, 43, 45, 47, 49],
-    "cluster conv+GN 8x2 (8)": [16, 17, 18, 19, 36, 37, 38, 39],
-    "cluster conv+GN 4x1 (10)": [23, 24, 25, 26, 29, 30, 31, 32, 33, 34],
-    "everything but conv_in/outc (63)": list(range(1, 64)),
+    "gn_apply, separate kernels, 32x8 + 16x4 levels (13)": APPLY,
+    "attention heads sa1-sa5: LN + in_proj + core (5)": [12, 19, 26, 39, 50],
+    "attention tails (6)": [13, 20, 27, 40, 51, 62],
+    "attention heads: LN + in_proj + core (6)": [12, 19, 26, 39, 50, 61],
+    "sa6: head, tail (2)": [61, 62],
+    "attention whole (12)": [12, 13, 19, 20, 26, 27, 39, 40, 50, 51, 61, 62],
+    "pool+upsample (6)": [3, 14, 21, 34, 41, 52],
+    "conv 32x8 (5)": [1, 53, 55, 57, 59],
+    "conv 16x4 (8)": [4, 6, 8, 10, 42, 44, 46, 48],
+    "cluster conv+GN 8x2 (8)": [15, 16, 17, 18, 35, 36, 37, 38],
+    "cluster conv+GN 4x1 (10)": [22, 23, 24, 25, 28, 29, 30, 31, 32, 33],
+    "everything but conv_in/outc (62)": list(range(1, 63)),
 }
 
 
