@@ -201,6 +201,7 @@ int tc_gemm_split(const TcGemm* g, int B);
 // True when a launch for B samples keeps whole samples and all channels inside one tile, so that GroupNorm apply
 // (+GELU, +temb, +FiLM) can run in the conv epilogue (pass `fuse`; `out` then receives the activated map).
 bool tc_gemm_can_fuse_apply(const TcGemm* g, int B);
+bool tc_gemm_fuse_apply_pays(const TcGemm* g, int B);   // ... and it is measured faster than the separate apply kernel
 // Cluster split-K with GroupNorm apply fused behind it (deep levels at small batch): K slices per tile (0 = not
 // applicable at this geometry / batch; 1 = the cluster only shares the GroupNorm statistics of a tile's N tiles) and the launch; `out` receives the activated bf16 map, no partial tiles.
 int tc_gemm_cluster_split(const TcGemm* g, int B);

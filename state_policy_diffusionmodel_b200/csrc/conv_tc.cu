@@ -1358,6 +1358,18 @@ bool tc_gemm_can_fuse_apply(const TcGemm* g, int B) {
   return p.Cout == bn && p.H == p.Hb;  // one N tile, whole samples per M tile
 }
 
+// Does fusing the GroupNorm apply into this conv's epilogue pay?  Measured: only on the swapped-operand kernel and only where its
+// 8-warp epilogue is used, i.e. the launch has at most two tiles per CTA (batch 256: -1 % of the step; batch 4096: +3.5 %, the
+// tile's CTAs then do elementwise work that a separate kernel spreads over all SMs while hiding under the next tile's MMAs).
+bool tc_gemm_fuse_apply_pays(const TcGemm* g, int B) {
+  if (!tc_gemm_can_fuse_apply(g, B)) return false;
+  const TcParams& p = g->p;
+  const int m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
+  if (!swap_taken(g, m_tiles, EPI_STATS)) return false;
+  const int total = (m_tiles / 2) * ((p.Cout + BLOCK_M - 1) / BLOCK_M);
+  return total <= 2 * num_sms();
+}
+
 int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const float* bias, const bf16* resid, int ld_res, int flags,
                    int B, cudaStream_t s, bf16* vt, int vt_lk, const ApplyArgs* fuse, int ksplit, float* partial) {
   TcParams p = g->p;

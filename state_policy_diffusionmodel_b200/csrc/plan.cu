@@ -140,7 +140,8 @@ struct spdm_plan {
   bool no_fuse = false;                // SPDM_NO_FUSE_APPLY=1: keep GroupNorm apply as a separate kernel (A/B switch)
   std::vector<char> skip;              // SPDM_SKIP_IDX=i,j,...: launches of one forward (in timed() order) that are NOT issued --
   int timed_idx = 0;                   // timing ablation only (tools/ablate.py), results are garbage
-  int fuse_mode = 0;                   // SPDM_FUSE_MODE: 0 none (default: measured faster, the 4-warp epilogue is the bottleneck), 1 GELU-free convs, 2 all
+  int fuse_mode = -1;                  // SPDM_FUSE_MODE: -1 auto (default: GroupNorm apply inside the swapped conv's 8-warp epilogue where the launch
+                                       // has at most two tiles per CTA), 0 never, 1 GELU-free convs wherever possible, 2 all convs wherever possible
   cudaStream_t lane_stream[7] = {};
   cudaEvent_t ev_fork = nullptr, ev_lane[7] = {};
   float* enc_feat = nullptr; int enc_chunk = 0;  // [enc_chunk][9216]
@@ -513,7 +514,7 @@ template <typename T> struct Fwd {
   // split to occupy the SMs (small batch: split-K / cluster path) it would trade parallelism for work.
   bool fold_ok(const std::string& wname, GemmW& g, const T* in, int ld_in, int level, int ld_out) {
     if constexpr (sizeof(T) == 2) {
-      if (!(g.taps == 9 && g.w16_fold && !p->tr && !p->no_fold && p->fuse_mode == 0 && p->levelW(level) == 2 && ld_in == g.Cin &&
+      if (!(g.taps == 9 && g.w16_fold && !p->tr && !p->no_fold && p->fuse_mode <= 0 && p->levelW(level) == 2 && ld_in == g.Cin &&
             ld_out == g.Cout)) return false;
       return p->no_splitk || tc_gemm_split(get_tc(wname, g, in, ld_in, level), Bpad) <= 1;
     }
@@ -571,11 +572,14 @@ template <typename T> struct Fwd {
   }
 
   // can GroupNorm apply run inside this conv's epilogue (whole samples and all channels in one tile)?
-  bool can_fuse(const std::string& wname, const T* in, int ld_in, int level) {
+  // `min_mode`: the SPDM_FUSE_MODE value from which this conv is fused unconditionally (1: GELU-free second conv, 2: first conv)
+  bool can_fuse(const std::string& wname, const T* in, int ld_in, int level, int min_mode) {
     if constexpr (sizeof(T) == 2) {
-      if (p->no_fuse) return false;
+      if (p->no_fuse || p->fuse_mode == 0 || p->tr) return false;
       GemmW& g = p->gemms[wname];
-      return tc_gemm_can_fuse_apply(get_tc(wname, g, in, ld_in, level), Bpad);
+      TcGemm* tc = get_tc(wname, g, in, ld_in, level);
+      if (p->fuse_mode < 0) return tc_gemm_fuse_apply_pays(tc, Bpad);
+      return p->fuse_mode >= min_mode && tc_gemm_can_fuse_apply(tc, Bpad);
     }
     return false;
   }
@@ -658,7 +662,7 @@ template <typename T> struct Fwd {
         a.out = h; a.ld_out = Cout;
         timed(p, c.s, PC_APPLY, 0, (4.0 * S + 2.0) * c.B * a.HW * Cout, [&] { launch_apply_partial(a, p->partial[c.b0], S, Mpad, c.B, c.s); });
         fused = true;
-      } else if (!tap1 && p->fuse_mode >= 2 && can_fuse(name + ".first", in, ld_in, level)) {
+      } else if (!tap1 && can_fuse(name + ".first", in, ld_in, level, 2)) {
         const ApplyArgs a = make_apply(name + ".norm", Cout, level, ACT_GELU, nullptr);
         gemm(name + ".first", in, ld_in, level, h, Cout, EPI_STATS, nullptr, 0, &a);
         fused = true;
@@ -677,7 +681,7 @@ template <typename T> struct Fwd {
       ApplyArgs a = make_apply(name + ".norm", Cout, level, ACT_NONE, st);
       a.out = out; a.ld_out = ld_out;
       timed(p, c.s, PC_APPLY, 0, (4.0 * S2 + 2.0) * c.B * a.HW * Cout, [&] { launch_apply_partial(a, p->partial[c.b0], S2, Mpad, c.B, c.s); });
-    } else if (!tap2 && p->fuse_mode >= 1 && can_fuse(name + ".second", h, Cout, level)) {
+    } else if (!tap2 && can_fuse(name + ".second", h, Cout, level, 1)) {
       const ApplyArgs a = make_apply(name + ".norm", Cout, level, ACT_NONE, st);
       gemm(name + ".second", h, Cout, level, out, ld_out, EPI_STATS, nullptr, 0, &a);
     } else {
