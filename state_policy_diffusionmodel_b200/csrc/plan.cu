@@ -140,8 +140,8 @@ struct spdm_plan {
   bool no_fuse = false;                // SPDM_NO_FUSE_APPLY=1: keep GroupNorm apply as a separate kernel (A/B switch)
   std::vector<char> skip;              // SPDM_SKIP_IDX=i,j,...: launches of one forward (in timed() order) that are NOT issued --
   int timed_idx = 0;                   // timing ablation only (tools/ablate.py), results are garbage
-  int fuse_mode = 0;                   // SPDM_FUSE_MODE: 0 never (default), -1 auto (GroupNorm apply inside the swapped conv's 8-warp epilogue where the
-                                       // launch has at most two tiles per CTA), 1 GELU-free convs wherever possible, 2 all convs wherever possible
+  int fuse_mode = -1;                  // SPDM_FUSE_MODE: -1 auto (default: GroupNorm apply inside the swapped conv's 8-warp epilogue where the launch has
+                                       // at most two tiles per CTA; batch 256: 0.7256 -> 0.7201 ms per step), 0 never, 1 / 2 wherever possible (slower)
   cudaStream_t lane_stream[7] = {};
   cudaEvent_t ev_fork = nullptr, ev_lane[7] = {};
   float* enc_feat = nullptr; int enc_chunk = 0;  // [enc_chunk][9216]
