@@ -837,6 +837,7 @@ void launch_head256(const AttnHead* g, const HeadParams& p, long long M, cudaStr
 
 // out: att [M][C] (head only) -- unused when the tail is merged, then x -> y [M][ld_y] is the whole block
 void attn_head_launch(const AttnHead* g, const bf16* x, int ld_x, bf16* out, long long M, cudaStream_t s, bf16* y, int ld_y) {
+  kernels_count_launch();
   HeadParams p = g->p;
   p.x = x; p.ld_x = ld_x; p.out = out; p.y = y; p.ld_y = ld_y;
   if (p.L == 256) {   // one CTA per sample (C = 64)

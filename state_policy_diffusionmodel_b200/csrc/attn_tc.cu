@@ -338,6 +338,7 @@ AttnTail* attn_tail_create(const bf16* att, long long Mcap, int C, const bf16* w
 void attn_tail_destroy(AttnTail* g) { delete g; }
 
 void attn_tail_launch(const AttnTail* g, const bf16* x, int ld_x, bf16* out, int ld_out, long long M, cudaStream_t s) {
+  kernels_count_launch();
   TailParams p = g->p;
   p.x = x; p.ld_x = ld_x; p.out = out; p.ld_out = ld_out;
   if (g->C == 64) launch_tail<64>(g, p, M, s);

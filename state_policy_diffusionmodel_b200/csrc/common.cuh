@@ -181,6 +181,7 @@ void launch_pack_linear_f32(const float* nk, float* out, int N, int K, int ld_ou
 void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
 void launch_pack_enc_linear(const float* w, float* out, cudaStream_t s);  // (128, 64*12*12 chw) -> [9216 hwc][128]
 long long kernels_launch_count();
+void kernels_count_launch();  // one more launch (kernels that live in other translation units)
 
 // tcgen05 path (conv_tc.cu) -----------------------------------------------------------------------
 struct TcGemm;  // opaque: tensor maps + geometry for one implicit-GEMM launch

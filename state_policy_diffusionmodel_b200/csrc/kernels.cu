@@ -10,6 +10,7 @@
 static long long g_launches = 0;
 int g_spdm_pdl = 1;
 long long kernels_launch_count() { return g_launches; }
+void kernels_count_launch() { ++g_launches; }  // launches issued by sdpa_tc.cu / attn_tc.cu / attn_head.cu
 #define COUNT_LAUNCH() (++g_launches)
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }

@@ -686,6 +686,7 @@ static void sdpa2_launch_cfg(const SdpaTc* g, const SdpaParams& p, dim3 grid, cu
 }
 
 void sdpa_tc_launch(const SdpaTc* g, bf16* out, long long M, cudaStream_t s) {
+  kernels_count_launch();
   SdpaParams p = g->p;
   p.out = out;
   dim3 grid((unsigned)(M / 128), (unsigned)(p.C / 64));
