@@ -59,8 +59,9 @@ int spdm_plan_missing_weights(spdm_plan* plan);
 
 /* DDPMScheduler/DDIMScheduler.set_timesteps (call sites models/diffusion_ddpm.py:204,257;
  * diffusion_ddim.py:57,67).  coef is HOST memory, K rows of 8 floats:
- *   {sqrt(1-abar_t), sqrt(abar_t), k_x0, k_x, k_eps, k_noise, 0, 0}
- *   x0 = (x - c0*eps)/c1 ;  x_prev = k_x0*x0 + k_x*x + k_eps*eps + k_noise*z
+ *   {sqrt(1-abar_t), sqrt(abar_t), k_x0, k_x, k_eps, k_noise, clip, 0}
+ *   x0 = (x - c0*eps)/c1 ;  clip > 0: x0 = clamp(x0, -clip, clip)  (clip_sample=True, clip_sample_range; the
+ *   reference passes clip_sample=False, models/diffusion_ddpm.py:68) ;  x_prev = k_x0*x0 + k_x*x + k_eps*eps + k_noise*z
  * timesteps is HOST int64[K] (descending), the value fed to the U-Net time embedding. */
 int spdm_plan_set_schedule(spdm_plan* plan, int32_t kind, int32_t K, const float* coef,
                            const int64_t* timesteps, void* stream);
@@ -73,6 +74,11 @@ int spdm_encode_images(spdm_plan* plan, const float* images, float* out, int32_t
  * velocity (B,T,2).  Leaves the conditioning cached in the plan for spdm_sample. */
 int spdm_encode_cond(spdm_plan* plan, const float* images, const float* position,
                      const float* action, const float* velocity, int32_t B, void* stream);
+/* Same with the frames as the simulator / dataset stores them (generateData/trajectory_control_utils.py:170 divides by 255 on
+ * the way into the zarr file): uint8 (B,T,96,96,3) HWC, decoded x / 255 inside the encoder's first conv -- a quarter of the
+ * bytes of the fp32 frames over PCIe and out of HBM. */
+int spdm_encode_cond_u8(spdm_plan* plan, const uint8_t* images_hwc, const float* position, const float* action,
+                        const float* velocity, int32_t B, void* stream);
 /* Same, from an already built obs_cond (B, T*cond_dim). */
 int spdm_set_cond(spdm_plan* plan, const float* obs_cond, int32_t B, void* stream);
 /* Copy of the cached obs_cond (B, T*cond_dim) for inspection / parity tests. */
@@ -125,6 +131,10 @@ int spdm_train_fwd_bwd(spdm_plan* plan, const float* images, const float* positi
 /* `images` of the next spdm_train_fwd_bwd calls is a strided view: frame (b, t) at images + b*stride + t*3*96*96 floats
  * (0 = contiguous).  The reference slices the observation window out of the full recording (ddpm:283-298). bf16 plans only. */
 int spdm_train_set_image_stride(spdm_plan* plan, int64_t stride);
+/* Ragged batches (the reference's DataLoader has no drop_last, utils/load_data.py:174): the bf16 path needs B to be a multiple of
+ * spdm_plan_batch_multiple(); the caller pads the batch with any valid samples and declares how many at the head are real.
+ * The loss is then the mean over the real samples and the padding samples contribute no gradient.  0 = all real (default). */
+int spdm_train_set_valid(spdm_plan* plan, int32_t valid);
 /* Data-parallel overlap: make `stream` wait until every gradient of completion phase `phase` of the latest
  * spdm_train_fwd_bwd is final.  Phase 0: outc, sa4-sa6, up1-up3 (convs, norms, attention); phase 1: the rest of the U-Net
  * except the emb_layer / cond_encoder Linears; phase 2: everything (those Linears and the vision encoder). */
@@ -152,6 +162,7 @@ int spdm_microbench_conv(int32_t H, int32_t W, int32_t B, int32_t Cin, int32_t C
 /* Introspection used by bench.py / tests. */
 int64_t spdm_plan_launch_count(spdm_plan* plan);     /* kernels enqueued so far by this plan  */
 int64_t spdm_plan_workspace_bytes(spdm_plan* plan);
+int32_t spdm_plan_batch_multiple(spdm_plan* plan);  /* granularity of B on the tensor-core path (1 on the fp32 path) */
 /* Debug tap (tests only): spdm_unet_forward that additionally copies the internal activation `tap_name`
  * ("inc", "down1", "sa1", "x2", "bot3", "up1", "u3", "<block>.first", ... ) to tap_out as fp32
  * (B, C, H, W).  Returns the element count written, or negative. */

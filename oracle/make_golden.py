@@ -229,6 +229,25 @@ def golden_dataset(seed=0):
     np.savez_compressed(os.path.join(OUT, "dataset.npz"), **out)
 
 
+def golden_beta_schedules():
+    """utils/schedulers.py:6-40 of the reference, imported as is (the functions are unbound "methods" reading self.device)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_ref_utils_schedulers", os.path.join(shim.REFERENCE_ROOT, "utils", "schedulers.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+
+    class Dev:
+        device = torch.device("cpu")
+    out = {}
+    for steps in (10, 50, 100, 1000):
+        out["linear_%d" % steps] = mod.linear_beta_schedule(Dev(), steps)
+        out["linear_v2_%d" % steps] = mod.linear_beta_schedule_v2(Dev(), steps)
+        out["cosine_%d" % steps] = mod.cosine_beta_schedule(Dev(), steps)
+    out["cosine_100_s02_f64"] = mod.cosine_beta_schedule(Dev(), 100, s=0.02, dtype=torch.float64)
+    np.savez_compressed(os.path.join(OUT, "beta_schedules.npz"), **_np(out))
+    print("beta_schedules", sorted(out))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     shim.install()
@@ -243,6 +262,7 @@ def main():
     golden_validate_and_train()
     golden_train_grads()
     golden_dataset()
+    golden_beta_schedules()
 
 
 if __name__ == "__main__":

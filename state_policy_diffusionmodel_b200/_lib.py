@@ -43,6 +43,7 @@ _PROTOTYPES = {
     "spdm_plan_set_schedule": (_c.c_int, [_P, _c.c_int32, _c.c_int32, _P, _P, _P]),
     "spdm_encode_images": (_c.c_int, [_P, _P, _P, _c.c_int32, _P]),
     "spdm_encode_cond": (_c.c_int, [_P, _P, _P, _P, _P, _c.c_int32, _P]),
+    "spdm_encode_cond_u8": (_c.c_int, [_P, _P, _P, _P, _P, _c.c_int32, _P]),
     "spdm_set_cond": (_c.c_int, [_P, _P, _c.c_int32, _P]),
     "spdm_get_cond": (_c.c_int, [_P, _P, _c.c_int32, _P]),
     "spdm_unet_forward": (_c.c_int, [_P, _P, _P, _c.c_int32, _P, _c.c_int32, _P, _c.c_int32, _P]),
@@ -58,6 +59,7 @@ _PROTOTYPES = {
     "spdm_train_sync_weights": (_c.c_int, [_P, _P]),
     "spdm_train_fwd_bwd": (_c.c_int, [_P] + [_P] * 11 + [_c.c_int32, _P]),
     "spdm_train_set_image_stride": (_c.c_int, [_P, _c.c_int64]),
+    "spdm_train_set_valid": (_c.c_int, [_P, _c.c_int32]),
     "spdm_train_wait_phase": (_c.c_int, [_P, _c.c_int32, _P]),
     "spdm_adam_step": (_c.c_int, [_P, _P, _P, _P, _c.c_int64, _c.c_float, _c.c_float, _c.c_float, _c.c_float, _c.c_int32,
                                   _c.c_float, _c.c_float, _P, _P]),
@@ -67,6 +69,7 @@ _PROTOTYPES = {
     "spdm_data_launch_count": (_c.c_int64, []),
     "spdm_plan_launch_count": (_c.c_int64, [_P]),
     "spdm_plan_workspace_bytes": (_c.c_int64, [_P]),
+    "spdm_plan_batch_multiple": (_c.c_int32, [_P]),
     "spdm_last_error": (_c.c_char_p, []),
     "spdm_version": (_c.c_char_p, []),
 }

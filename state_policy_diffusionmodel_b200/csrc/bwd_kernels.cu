@@ -1293,7 +1293,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) mse_outc_bwd_kernel(const float* __restrict__ eps_hat, const float* __restrict__ noise, const T* __restrict__ act,
                                                            int ld, const float* __restrict__ w, T* __restrict__ d_act, float* __restrict__ d_w,
                                                            float* __restrict__ d_b, float* __restrict__ loss, float inv_n, int H, int W, int C,
-                                                           int rows, int dim, int lh, int lw) {
+                                                           int rows, int dim, int lh, int lw, int B_valid) {
   extern __shared__ float se[];  // [H*W] e per padded pixel, then [256*8] reduction scratch
   float* red = se + H * W;
   __shared__ float scratch[8];
@@ -1302,7 +1302,7 @@ __global__ void __launch_bounds__(256) mse_outc_bwd_kernel(const float* __restri
   for (int px = tid; px < H * W; px += 256) {
     const int hh = px / W - lh, ww = px % W - lw;
     float e = 0.f;
-    if (hh >= 0 && hh < rows && ww >= 0 && ww < dim) {
+    if (b < B_valid && hh >= 0 && hh < rows && ww >= 0 && ww < dim) {  // samples past B_valid pad a ragged batch: no loss, no gradient
       const size_t i = ((size_t)b * rows + hh) * dim + ww;
       const float d = eps_hat[i] - noise[i];
       lsum = fmaf(d, d, lsum);
@@ -1379,10 +1379,11 @@ __global__ void __launch_bounds__(256) conv_in_wgrad_kernel(const float* __restr
 }  // namespace
 template <typename T>
 void launch_mse_outc_bwd(const float* eps_hat, const float* noise, const T* act, int ld, const float* w, T* d_act, float* d_w, float* d_b,
-                         float* loss, int B, int H, int W, int C, int rows, int dim, int lh, int lw, cudaStream_t s) {
+                         float* loss, int B, int H, int W, int C, int rows, int dim, int lh, int lw, cudaStream_t s, int B_valid) {
   const size_t smem = ((size_t)H * W + 256 * 8) * sizeof(float);
-  const float inv_n = 1.0f / ((float)B * rows * dim);
-  mse_outc_bwd_kernel<T><<<B, 256, smem, s>>>(eps_hat, noise, act, ld, w, d_act, d_w, d_b, loss, inv_n, H, W, C, rows, dim, lh, lw);
+  if (B_valid <= 0 || B_valid > B) B_valid = B;
+  const float inv_n = 1.0f / ((float)B_valid * rows * dim);   // MSELoss 'mean' over the real samples (ddpm:171)
+  mse_outc_bwd_kernel<T><<<B, 256, smem, s>>>(eps_hat, noise, act, ld, w, d_act, d_w, d_b, loss, inv_n, H, W, C, rows, dim, lh, lw, B_valid);
   COUNT_LAUNCH();
 }
 template <typename T>
@@ -1392,9 +1393,9 @@ void launch_conv_in_wgrad(const float* x, const T* d_raw, float* dw, int B, int 
   COUNT_LAUNCH();
 }
 template void launch_mse_outc_bwd<float>(const float*, const float*, const float*, int, const float*, float*, float*, float*, float*, int, int, int,
-                                         int, int, int, int, int, cudaStream_t);
+                                         int, int, int, int, int, cudaStream_t, int);
 template void launch_mse_outc_bwd<bf16>(const float*, const float*, const bf16*, int, const float*, bf16*, float*, float*, float*, int, int, int,
-                                        int, int, int, int, int, cudaStream_t);
+                                        int, int, int, int, int, cudaStream_t, int);
 template void launch_conv_in_wgrad<float>(const float*, const float*, float*, int, int, int, int, int, int, int, cudaStream_t);
 template void launch_conv_in_wgrad<bf16>(const float*, const bf16*, float*, int, int, int, int, int, int, int, cudaStream_t);
 
@@ -1785,18 +1786,40 @@ __device__ __forceinline__ void enc_stage_strip(const float* __restrict__ im, in
   if (tid < 24) s_in[tid * 100 + 3] = 0.f;
 }
 
+// The same strip from a uint8 HWC frame (what the simulator / dataset stores): 8 rows x 288 bytes, decoded x / 255 (one IEEE
+// division, the reference's `/ 255.0`) while staging; a thread handles 3 of the 576 32-bit words.
+__device__ __forceinline__ void enc_stage_strip_u8(const uint8_t* __restrict__ im, int r3, float* s_in, int tid) {
+  for (int i = tid; i < 8 * 72; i += 192) {
+    const int r8 = i / 72, wq = i - r8 * 72;
+    const int gr = 8 * r3 - 1 + r8;
+    uint32_t w = 0;
+    if (gr >= 0) w = __ldg(reinterpret_cast<const uint32_t*>(im + (size_t)gr * 288) + wq);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = 4 * wq + j, x = k / 3, c = k - 3 * x;
+      s_in[(c * 8 + r8) * 100 + 4 + x] = gr >= 0 ? __fdiv_rn((float)((w >> (8 * j)) & 255u), 255.0f) : 0.f;
+    }
+  }
+  if (tid < 24) s_in[tid * 100 + 3] = 0.f;
+}
+
 // one block per (frame, conv3 row r3): 192 conv1 pixels, one thread each, 16 channels per thread
-__global__ void __launch_bounds__(192) enc_conv1_fwd_kernel(const float* __restrict__ img, const float* __restrict__ w1, const float* __restrict__ b1,
+template <bool U8>
+__global__ void __launch_bounds__(192) enc_conv1_fwd_kernel(const void* __restrict__ img, const float* __restrict__ w1, const float* __restrict__ b1,
                                                             bf16* __restrict__ c1p, int T, long long bstride) {
   __shared__ __align__(16) float s_in[24 * 100];
   __shared__ __align__(16) float w1s[12 * 16];
   __shared__ __align__(16) float b1s[16];
   const int tid = threadIdx.x;
   const int frame = blockIdx.x / 12, r3 = blockIdx.x % 12;
-  const float* im = img + (size_t)(frame / T) * bstride + (size_t)(frame % T) * 3 * 96 * 96;  // frame = b*T + t; samples bstride apart
   w1s[tid] = __ldg(w1 + (tid & 15) * 12 + (tid >> 4));
   if (tid < 16) b1s[tid] = __ldg(b1 + tid);
-  enc_stage_strip(im, r3, s_in, tid);
+  if constexpr (U8) {
+    enc_stage_strip_u8(reinterpret_cast<const uint8_t*>(img) + (size_t)frame * 96 * 96 * 3, r3, s_in, tid);   // contiguous (B*T, 96, 96, 3)
+  } else {
+    // frame = b*T + t; samples bstride apart
+    enc_stage_strip(reinterpret_cast<const float*>(img) + (size_t)(frame / T) * bstride + (size_t)(frame % T) * 3 * 96 * 96, r3, s_in, tid);
+  }
   __syncthreads();
   // tid = (c3*4 + kk3)*4 + kk2 : consecutive threads write consecutive 32-byte pixel slots of c1p
   const int kk2 = tid & 3, kk3 = (tid >> 2) & 3, c3 = tid >> 4;
@@ -1976,7 +1999,11 @@ __global__ void enc_unpack_grads_kernel(const float* __restrict__ g2, const floa
 }
 }  // namespace
 void launch_enc_conv1_fwd(const float* img, const float* w1, const float* b1, bf16* c1p, int n, int T, long long bstride, cudaStream_t s) {
-  enc_conv1_fwd_kernel<<<n * 12, 192, 0, s>>>(img, w1, b1, c1p, T, bstride);
+  enc_conv1_fwd_kernel<false><<<n * 12, 192, 0, s>>>(img, w1, b1, c1p, T, bstride);
+  COUNT_LAUNCH();
+}
+void launch_enc_conv1_fwd_u8(const uint8_t* img_hwc, const float* w1, const float* b1, bf16* c1p, int n, cudaStream_t s) {
+  enc_conv1_fwd_kernel<true><<<n * 12, 192, 0, s>>>(img_hwc, w1, b1, c1p, 1, 0);
   COUNT_LAUNCH();
 }
 void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float* db1, int n, int T, long long bstride, cudaStream_t s) {

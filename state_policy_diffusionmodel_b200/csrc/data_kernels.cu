@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) gather_images_u8_kernel(const uint8_t* __
   const int y = rem / w4, x = (rem - y * w4) * 4;
   const long long b = f / T_img;
   const int t = (int)(f - b * T_img);
-  const long long src_frame = starts[b] + (long long)t * step;
+  const long long src_frame = starts ? starts[b] + (long long)t * step : f;   // starts == null: plain decode, frame f -> frame f
   const uint32_t* src = reinterpret_cast<const uint32_t*>(img + ((src_frame * H + y) * W + x) * 3);   // 12 bytes, 4-byte aligned
   const uint32_t w0 = __ldg(src), w1 = __ldg(src + 1), w2 = __ldg(src + 2);
   const uint32_t bytes[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24, w1 & 255u, (w1 >> 8) & 255u,
@@ -104,6 +104,14 @@ __global__ void unnormalize_position_kernel(const float* __restrict__ npos, cons
 }
 
 }  // namespace
+
+// uint8 HWC frames -> fp32 CHW (x / 255), frame by frame: the decode half of gather_images_u8_kernel without the window gather
+// (spdm_encode_cond_u8 on an fp32 plan)
+void launch_decode_u8_hwc(const uint8_t* img, float* out, long long frames, int H, int W, cudaStream_t s) {
+  const long long n = frames * H * (W / 4);
+  gather_images_u8_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(img, nullptr, 1, 1, H, W, frames, out);
+  spdm_count_data_launch();
+}
 
 extern "C" int spdm_gather_windows(const void* images, int32_t image_kind, int32_t H, int32_t W, const float* position,
                                    const float* velocity, const float* action, const int64_t* starts, int32_t B, int32_t T, int32_t T_img,

@@ -823,7 +823,8 @@ template void launch_to_nchw<bf16>(const bf16*, int, float*, int, int, int, cuda
 //   x0     = (x - c0*eps) / c1                       DDPMScheduler/DDIMScheduler.step (diffusers 0.17.1;
 //   x_prev = k_x0*x0 + k_x*x + k_eps*eps + k_n*z      call sites models/diffusion_ddpm.py:211,274, ddim.py:61,72)
 //   x_prev[:, :inpaint] = inpaint                     models/diffusion_ddpm.py:216-219
-// coef row = {c0, c1, k_x0, k_x, k_eps, k_n, 0, 0}; the row index comes from a device counter so the
+// coef row = {c0, c1, k_x0, k_x, k_eps, k_n, clip, 0} (clip > 0: x0 is clamped to [-clip, clip] first -- the schedulers'
+// clip_sample=True / clip_sample_range, diffusers' default); the row index comes from a device counter so the
 // launch is CUDA-graph replayable.  z is injected (parity) or Philox4x32-10 + Box-Muller (throughput).
 // =================================================================================================
 namespace {
@@ -875,7 +876,7 @@ __global__ void step_kernel(StepArgs a) {
     use_philox = a.dyn->use_philox;
   }
   const float* cf = a.coef + (size_t)step * 8;
-  const float c0 = cf[0], c1 = cf[1], kx0 = cf[2], kx = cf[3], keps = cf[4], kn = cf[5];
+  const float c0 = cf[0], c1 = cf[1], kx0 = cf[2], kx = cf[3], keps = cf[4], kn = cf[5], clip = cf[6];
   const long long b = i / a.n;
   const int e = (int)(i - b * a.n);
   float r;
@@ -883,7 +884,8 @@ __global__ void step_kernel(StepArgs a) {
     r = inpaint[b * a.inpaint_elems + e];
   } else {
     const float x = a.x[i], ep = a.eps[i];
-    const float x0 = (x - c0 * ep) / c1;
+    float x0 = (x - c0 * ep) / c1;
+    if (clip > 0.f) x0 = fminf(fmaxf(x0, -clip), clip);  // clip_sample=True: x0.clamp(-range, range)
     r = kx0 * x0 + kx * x;
     if (keps != 0.f) r += keps * ep;
     if (kn != 0.f) {
@@ -912,7 +914,7 @@ __global__ void outc_step_kernel(StepArgs a, const T* __restrict__ act, int ld, 
   const float* inpaint = a.dyn->inpaint;
   float* history = a.dyn->history;
   const float* cf = a.coef + (size_t)step * 8;
-  const float c0 = cf[0], c1 = cf[1], kx0 = cf[2], kx = cf[3], keps = cf[4], kn = cf[5];
+  const float c0 = cf[0], c1 = cf[1], kx0 = cf[2], kx = cf[3], keps = cf[4], kn = cf[5], clip = cf[6];
   const long long b = i / a.n;
   const int e = (int)(i - b * a.n);
   float r;
@@ -931,7 +933,8 @@ __global__ void outc_step_kernel(StepArgs a, const T* __restrict__ act, int ld, 
     }
     ep += __ldg(bias);
     const float x = a.x[i];
-    const float x0 = (x - c0 * ep) / c1;
+    float x0 = (x - c0 * ep) / c1;
+    if (clip > 0.f) x0 = fminf(fmaxf(x0, -clip), clip);  // clip_sample=True: x0.clamp(-range, range)
     r = kx0 * x0 + kx * x;
     if (keps != 0.f) r += keps * ep;
     if (kn != 0.f) {

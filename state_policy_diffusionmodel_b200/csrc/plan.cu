@@ -129,7 +129,19 @@ struct spdm_plan {
   bool temb_table_dirty = true;
   bool have_cond = false;
   float* xt = nullptr; float* eps = nullptr;  // [Bcap][n]
-  StepDyn* dyn = nullptr; StepDyn* dyn_host = nullptr;
+  StepDyn* dyn = nullptr;
+  // pinned staging of the per-call parameter block: a small ring, so that a call never has to wait for the previous call's
+  // upload (a slot is reused DYN_SLOTS calls later; its event has long completed by then)
+  enum { DYN_SLOTS = 8 };
+  StepDyn* dyn_host = nullptr; cudaEvent_t dyn_ev[DYN_SLOTS] = {}; bool dyn_used[DYN_SLOTS] = {}; unsigned dyn_next = 0;
+  StepDyn* dyn_slot() {
+    const unsigned j = dyn_next++ % DYN_SLOTS;
+    if (dyn_used[j]) cudaEventSynchronize(dyn_ev[j]);
+    dyn_used[j] = true;
+    dyn_cur = j;
+    return dyn_host + j;
+  }
+  unsigned dyn_cur = 0;
   cudaStream_t own_stream = nullptr;  // graphs are captured and replayed here (the caller's stream may be the legacy stream)
   cudaEvent_t ev_in = nullptr, ev_out = nullptr;
   int split = 1;                       // sub-batches run concurrently per denoising step
@@ -146,6 +158,7 @@ struct spdm_plan {
   cudaEvent_t ev_fork = nullptr, ev_lane[7] = {};
   float* enc_feat = nullptr; int enc_chunk = 0;  // [enc_chunk][9216]
   float* enc_out = nullptr;                       // [Bcap*T][128]
+  float* enc_u8_stage = nullptr; int enc_u8_cap = 0;  // decoded frames of spdm_encode_cond_u8 on plans whose encoder reads fp32
 
   std::map<std::string, TcGemm*> tc_cache;
   // graphs keyed by batch: [0] = graph_steps-step body, [1] = 1-step body
@@ -1008,7 +1021,8 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
     p->xt = p->alloc<float>((size_t)p->Bcap * p->n_elems());
     p->eps = p->alloc<float>((size_t)p->Bcap * p->n_elems());
     p->dyn = p->alloc<StepDyn>(1);
-    CUDA_OK(cudaMallocHost((void**)&p->dyn_host, sizeof(StepDyn)));
+    CUDA_OK(cudaMallocHost((void**)&p->dyn_host, sizeof(StepDyn) * spdm_plan::DYN_SLOTS));
+    for (int i = 0; i < spdm_plan::DYN_SLOTS; ++i) CUDA_OK(cudaEventCreateWithFlags(&p->dyn_ev[i], cudaEventDisableTiming));
     CUDA_OK(cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking));
     CUDA_OK(cudaEventCreateWithFlags(&p->ev_in, cudaEventDisableTiming));
     CUDA_OK(cudaEventCreateWithFlags(&p->ev_out, cudaEventDisableTiming));
@@ -1066,6 +1080,7 @@ extern "C" int spdm_plan_destroy(spdm_plan* p) {
   for (void* q : p->allocs) cudaFree(q);
   train_destroy(p);
   if (p->dyn_host) cudaFreeHost(p->dyn_host);
+  for (int i = 0; i < spdm_plan::DYN_SLOTS; ++i) if (p->dyn_ev[i]) cudaEventDestroy(p->dyn_ev[i]);
   if (p->own_stream) cudaStreamDestroy(p->own_stream);
   if (p->ev_in) cudaEventDestroy(p->ev_in);
   if (p->ev_out) cudaEventDestroy(p->ev_out);
@@ -1124,11 +1139,17 @@ extern "C" int spdm_plan_set_schedule(spdm_plan* p, int32_t kind, int32_t K, con
   API_END
 }
 
-extern "C" int spdm_encode_images(spdm_plan* p, const float* images, float* out, int32_t n, void* stream) {
-  API_BEGIN
-  REQUIRE(p && images && out && n > 0, "bad argument");
+// Autoencoder.encoder on n frames: `images` fp32 (n,3,96,96), or -- images_u8 non-null -- uint8 HWC (n,96,96,3) decoded x / 255 in flight
+static void encode_images_impl(spdm_plan* p, const float* images, const uint8_t* images_u8, float* out, int32_t n, cudaStream_t s) {
+  REQUIRE(p && (images || images_u8) && out && n > 0, "bad argument");
   if (!p->missing_enc.empty()) throw SpdmError{"vision encoder weights missing, first: " + *p->missing_enc.begin()};
-  cudaStream_t s = (cudaStream_t)stream;
+  if (images_u8 && !(p->bf16_mode && !p->enc_simt_infer)) {
+    // fp32 (parity) plans and the A/B CUDA-core conv stack read fp32 frames: decode into a plan-owned staging buffer first
+    if (p->enc_u8_cap < n) { p->enc_u8_stage = p->alloc<float>((size_t)n * 3 * 96 * 96); p->enc_u8_cap = n; }
+    launch_decode_u8_hwc(images_u8, p->enc_u8_stage, n, 96, 96, s);
+    images = p->enc_u8_stage;
+    images_u8 = nullptr;
+  }
   if (p->bf16_mode) {
     // bf16 plan: conv stack writes bf16 features, Linear(9216 -> 128) runs on the tcgen05 GEMM (one 128-frame tile per CTA)
     if (!p->enc_feat16) {
@@ -1153,7 +1174,8 @@ extern "C" int spdm_encode_images(spdm_plan* p, const float* images, float* out,
                                p->enc_feat16, m, s);
       } else {
         const int m8 = (m + 7) / 8 * 8;  // whole 128-row tiles: 288 * 8 and 144 * 8 rows; rows past m are scratch nobody reads
-        launch_enc_conv1_fwd(images + (size_t)f0 * 3 * 96 * 96, p->enc_w1, p->enc_b1, p->enc_c1p, m, 1, 3 * 96 * 96, s);
+        if (images_u8) launch_enc_conv1_fwd_u8(images_u8 + (size_t)f0 * 3 * 96 * 96, p->enc_w1, p->enc_b1, p->enc_c1p, m, s);
+        else launch_enc_conv1_fwd(images + (size_t)f0 * 3 * 96 * 96, p->enc_w1, p->enc_b1, p->enc_c1p, m, 1, 3 * 96 * 96, s);
         tc_gemm_launch(p->enc_tc2, p->enc_c2, 64, nullptr, p->enc_b2p, nullptr, 0, EPI_BIAS | EPI_RELU, m8 * 288, s);
         tc_gemm_launch(p->enc_tc3, p->enc_feat16, 64, nullptr, p->enc_b3, nullptr, 0, EPI_BIAS | EPI_RELU, m8 * 144, s);
       }
@@ -1172,6 +1194,11 @@ extern "C" int spdm_encode_images(spdm_plan* p, const float* images, float* out,
   }
   }
   check_async("encode_images");
+}
+
+extern "C" int spdm_encode_images(spdm_plan* p, const float* images, float* out, int32_t n, void* stream) {
+  API_BEGIN
+  encode_images_impl(p, images, nullptr, out, n, (cudaStream_t)stream);
   return 0;
   API_END
 }
@@ -1189,20 +1216,33 @@ extern "C" int spdm_set_cond(spdm_plan* p, const float* obs_cond, int32_t B, voi
   API_END
 }
 
-extern "C" int spdm_encode_cond(spdm_plan* p, const float* images, const float* position, const float* action, const float* velocity,
-                                int32_t B, void* stream) {
-  API_BEGIN
-  REQUIRE(p && images && position && action && velocity && B > 0 && B <= p->cfg.batch_max, "bad argument");
+static void encode_cond_impl(spdm_plan* p, const float* images, const uint8_t* images_u8, const float* position, const float* action,
+                             const float* velocity, int32_t B, cudaStream_t s) {
+  REQUIRE(p && (images || images_u8) && position && action && velocity && B > 0 && B <= p->cfg.batch_max, "bad argument");
   REQUIRE(p->cfg.cond_dim == 135, "encode_cond needs cond_dim == 135 (2 pos + 3 act + 2 vel + 128 image features)");
   check_ready(p);
-  cudaStream_t s = (cudaStream_t)stream;
   const int T = p->cfg.obs_horizon;
   if (!p->enc_out) p->enc_out = p->alloc<float>((size_t)p->Bcap * T * 128);
-  int rc = spdm_encode_images(p, images, p->enc_out, B * T, stream);
-  if (rc) return rc;
+  encode_images_impl(p, images, images_u8, p->enc_out, B * T, s);
   launch_build_cond(position, action, velocity, p->enc_out, p->cond, B, T, p->cfg.cond_dim, s);
   compute_film(p, B, s);
   check_async("encode_cond");
+}
+
+extern "C" int spdm_encode_cond(spdm_plan* p, const float* images, const float* position, const float* action, const float* velocity,
+                                int32_t B, void* stream) {
+  API_BEGIN
+  REQUIRE(images, "bad argument");
+  encode_cond_impl(p, images, nullptr, position, action, velocity, B, (cudaStream_t)stream);
+  return 0;
+  API_END
+}
+
+extern "C" int spdm_encode_cond_u8(spdm_plan* p, const uint8_t* images_hwc, const float* position, const float* action, const float* velocity,
+                                   int32_t B, void* stream) {
+  API_BEGIN
+  REQUIRE(images_hwc, "bad argument");
+  encode_cond_impl(p, nullptr, images_hwc, position, action, velocity, B, (cudaStream_t)stream);
   return 0;
   API_END
 }
@@ -1297,13 +1337,14 @@ extern "C" int spdm_sample(spdm_plan* p, const float* x_T, const float* noise, c
   }
   ensure_temb_table(p, s);
   const size_t nb = (size_t)B * p->n_elems() * sizeof(float);
-  // per-call dynamic parameters live in device memory so that the captured graphs are call-independent
-  CUDA_OK(cudaStreamSynchronize(s));  // dyn_host is reused across calls
+  // per-call dynamic parameters live in device memory so that the captured graphs are call-independent; the call itself only
+  // enqueues (no host synchronisation: the pinned staging block comes from a ring)
   StepDyn d{};
   d.step = 0; d.seed = seed; d.noise = noise; d.inpaint = p->cfg.inpaint_rows > 0 ? inpaint : nullptr; d.history = history;
   d.use_philox = noise ? 0 : 1;
-  *p->dyn_host = d;
-  CUDA_OK(cudaMemcpyAsync(p->dyn, p->dyn_host, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
+  StepDyn* dh = p->dyn_slot();
+  *dh = d;
+  CUDA_OK(cudaMemcpyAsync(p->dyn, dh, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
 
   const long long key = ((long long)B << 1) | (use_film ? 1 : 0);
   const int n_multi = gs > 0 ? p->K / gs : 0, n_single = gs > 0 ? p->K % gs : 0;
@@ -1314,7 +1355,7 @@ extern "C" int spdm_sample(spdm_plan* p, const float* x_T, const float* noise, c
       const long long before = total_launches();
       one_step(p, B, use_film, s);
       p->launches += total_launches() - before;
-      CUDA_OK(cudaMemcpyAsync(p->dyn, p->dyn_host, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
+      CUDA_OK(cudaMemcpyAsync(p->dyn, dh, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
       auto capture = [&](int steps, cudaGraphExec_t* exec, long long* count) {
         cudaGraph_t graph;
         const long long c0 = total_launches();
@@ -1347,6 +1388,7 @@ extern "C" int spdm_sample(spdm_plan* p, const float* x_T, const float* noise, c
     p->launches += n_multi * g.n_multi + n_single * g.n_single;
   }
   CUDA_OK(cudaMemcpyAsync(out, p->xt, nb, cudaMemcpyDeviceToDevice, s));
+  CUDA_OK(cudaEventRecord(p->dyn_ev[p->dyn_cur], s));
   if (s != user) {  // join back
     CUDA_OK(cudaEventRecord(p->ev_out, s));
     CUDA_OK(cudaStreamWaitEvent(user, p->ev_out, 0));
@@ -1380,8 +1422,9 @@ extern "C" int spdm_profile_step(spdm_plan* p, int32_t B, int32_t reps, double* 
   CUDA_OK(cudaStreamSynchronize(s));
   StepDyn d{};
   d.use_philox = 1;
-  *p->dyn_host = d;
-  CUDA_OK(cudaMemcpyAsync(p->dyn, p->dyn_host, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
+  StepDyn* dh = p->dyn_slot();
+  *dh = d;
+  CUDA_OK(cudaMemcpyAsync(p->dyn, dh, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
   one_step(p, B, use_film, s);  // warm-up (tensor maps, attributes)
   for (int i = 0; i < SPDM_PROFILE_CLASSES * 4; ++i) out[i] = 0.0;
   {  // size the event pool before timing
@@ -1391,7 +1434,7 @@ extern "C" int spdm_profile_step(spdm_plan* p, int32_t B, int32_t reps, double* 
     CUDA_OK(cudaStreamSynchronize(s));
   }
   for (int r = 0; r < reps; ++r) {
-    CUDA_OK(cudaMemcpyAsync(p->dyn, p->dyn_host, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
+    CUDA_OK(cudaMemcpyAsync(p->dyn, dh, sizeof(StepDyn), cudaMemcpyHostToDevice, s));
     // a ~3 ms spin kernel lets the host enqueue the whole step ahead of the GPU, so the event intervals are
     // back-to-back kernel durations and not host launch latency
     launch_delay(6000000LL, s);
@@ -1411,6 +1454,7 @@ extern "C" int spdm_profile_step(spdm_plan* p, int32_t B, int32_t reps, double* 
     }
     p->prof.clear();
   }
+  CUDA_OK(cudaEventRecord(p->dyn_ev[p->dyn_cur], s));
   check_async("profile_step");
   return 0;
   API_END
@@ -1455,6 +1499,7 @@ extern "C" int spdm_microbench_conv(int32_t H, int32_t W, int32_t B, int32_t Cin
 }
 
 extern "C" int64_t spdm_plan_launch_count(spdm_plan* p) { return p ? p->launches : 0; }
+extern "C" int32_t spdm_plan_batch_multiple(spdm_plan* p) { return p ? p->bm : 0; }
 extern "C" int64_t spdm_plan_workspace_bytes(spdm_plan* p) { return p ? (int64_t)p->bytes : 0; }
 
 #include "train_impl.inl"

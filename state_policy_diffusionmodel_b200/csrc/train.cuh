@@ -61,9 +61,11 @@ template <typename T> void launch_gelu_bwd(const T* dy, const T* pre, T* dx, lon
 // ---- ends of the network ------------------------------------------------------------------------------
 // MSELoss(noise, eps_hat) (mean over B*rows*dim) + its gradient through outc (1x1 conv 64 -> 1, + unpad):
 //   loss += sum (eps_hat - noise)^2 / N ;  d_act[M0, C] ; d_w[C], d_b accumulated.   (ddpm:171, Unet_FiLmLayer.py:264,310)
+// B_valid > 0: only the first B_valid samples are real (the rest pad a ragged batch to the tile granularity): N = B_valid*rows*dim
+// and the padding samples get a zero gradient, so nothing downstream of them reaches a parameter gradient.
 template <typename T>
 void launch_mse_outc_bwd(const float* eps_hat, const float* noise, const T* act, int ld, const float* w, T* d_act, float* d_w, float* d_b,
-                         float* loss, int B, int H, int W, int C, int rows, int dim, int lh, int lw, cudaStream_t s);
+                         float* loss, int B, int H, int W, int C, int rows, int dim, int lh, int lw, cudaStream_t s, int B_valid = 0);
 // inc.first weight gradient: dw[64][1][3][3] += sum x_pad[shift] * d_raw     (Unet_FiLmLayer.py:101, pad_to folded in)
 template <typename T>
 void launch_conv_in_wgrad(const float* x, const T* d_raw, float* dw, int B, int H, int W, int rows, int dim, int lh, int lw, cudaStream_t s);
@@ -87,6 +89,9 @@ void launch_pack_enc_linear_t(const float* w, float* out, cudaStream_t s);
 // ---- vision encoder as patch GEMMs on the tensor cores (bf16 training path; layouts in bwd_kernels.cu) ----------
 // img: frame (b, t) at img + b * bstride + t * 3*96*96 (bstride = T*3*96*96 for a contiguous observation window)
 void launch_enc_conv1_fwd(const float* img, const float* w1, const float* b1, bf16* c1p, int n, int T, long long bstride, cudaStream_t s);
+// the same from uint8 HWC frames (n, 96, 96, 3), decoded x / 255 while the input strip is staged
+void launch_enc_conv1_fwd_u8(const uint8_t* img_hwc, const float* w1, const float* b1, bf16* c1p, int n, cudaStream_t s);
+void launch_decode_u8_hwc(const uint8_t* img, float* out, long long frames, int H, int W, cudaStream_t s);  // data_kernels.cu
 void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float* db1, int n, int T, long long bstride, cudaStream_t s);
 // over [rows][64] bf16; colsum64 (or null) += column sums of the masked gradient
 void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, float* colsum64, cudaStream_t s);

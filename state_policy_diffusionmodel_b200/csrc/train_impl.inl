@@ -32,6 +32,7 @@ struct TrainState {
   cudaEvent_t ev_packs = nullptr, ev_packs_fork = nullptr;  // U-Net weight repacks run on the side stream, under the encoder forward
   bool packs_pending = false;
   long long image_bstride = 0;  // elements between samples of `images` (0 = contiguous); spdm_train_set_image_stride
+  int valid = 0;                // spdm_train_set_valid: real samples at the head of the batch (0 = all of them)
   // gradient-completion phases for overlapped data-parallel all-reduces: 0 = up path + outc + sa4-6 done, 1 = everything of the
   // U-Net except the time-embedding / FiLM Linears done, 2 = all gradients done (same point as the end of the step)
   cudaEvent_t ev_phase[3] = {nullptr, nullptr, nullptr};
@@ -372,7 +373,7 @@ template <typename T> struct Train {
     // ================= loss + backward =================
     T* d_u = A(0, 64);
     launch_mse_outc_bwd<T>(p->eps, noise, u3, 64, p->w_outc, d_u, G("outc.weight"), G("outc.bias"), tr->loss_dev, B, p->H0, p->W0, 64, rows,
-                           dim, p->lh, p->lw, s);
+                           dim, p->lh, p->lw, s, tr->valid);
     T* d_cats[3] = {nullptr, nullptr, nullptr};  // indexed like cats: cat1, cat2, cat3
     const T* d_cur = d_u;
     for (int i = 2; i >= 0; --i) {
@@ -537,8 +538,9 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
   REQUIRE(B > 0 && B <= p->cfg.batch_max, "B=%d outside 1..batch_max=%d", B, p->cfg.batch_max);
   REQUIRE(p->tr->grads, "training buffers not set (spdm_train_set_buffers)");
   REQUIRE(p->cfg.cond_dim == 135 && p->G > 0, "training needs the conditional model (cond_dim == 135)");
-  REQUIRE(B % p->bm == 0, "bf16 training: the batch (%d) must be a multiple of %d (pixel tiles of the weight-gradient GEMM hold whole samples)",
-          B, p->bm);
+  REQUIRE(B % p->bm == 0, "bf16 training: the batch (%d) must be a multiple of %d (pixel tiles of the weight-gradient GEMM hold whole samples); "
+          "pad it and declare the real count with spdm_train_set_valid", B, p->bm);
+  REQUIRE(p->tr->valid <= B, "spdm_train_set_valid(%d) exceeds the batch (%d)", p->tr->valid, B);
   check_ready(p, true);
   if (!p->missing_enc.empty()) throw SpdmError{"vision encoder weights missing, first: " + *p->missing_enc.begin()};
   TrainState* tr = p->tr;
@@ -738,6 +740,17 @@ extern "C" int spdm_train_wait_phase(spdm_plan* p, int32_t phase, void* stream) 
   API_BEGIN
   REQUIRE(p && p->tr && phase >= 0 && phase < 3, "bad argument");
   CUDA_OK(cudaStreamWaitEvent((cudaStream_t)stream, p->tr->ev_phase[phase], 0));
+  return 0;
+  API_END
+}
+
+// A ragged batch (the last one of an epoch: the reference's DataLoader has no drop_last, utils/load_data.py:174) is padded by the
+// caller to the tile granularity (spdm_plan_batch_multiple); only the first `valid` samples of the following spdm_train_fwd_bwd
+// calls then count: the loss is the mean over them and the padding samples contribute no gradient.  0 = every sample is real.
+extern "C" int spdm_train_set_valid(spdm_plan* p, int32_t valid) {
+  API_BEGIN
+  REQUIRE(p && p->tr && valid >= 0, "bad argument");
+  p->tr->valid = valid;
   return 0;
   API_END
 }

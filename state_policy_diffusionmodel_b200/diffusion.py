@@ -65,16 +65,21 @@ except Exception:  # pragma: no cover - depends on the environment
 
 
 class _NativeLoss(torch.autograd.Function):
-    """The loss returned by a native training step: its gradients already sit in the parameters' `.grad` (written by
-    spdm_train_fwd_bwd), so `loss.backward()` — which Lightning / user loops call — has nothing left to do."""
+    """The loss returned by a native training step.  spdm_train_fwd_bwd has already left d loss / d parameter in the plan's
+    private flat gradient buffer; `loss.backward()` -- which Lightning's automatic optimization and plain user loops call
+    AFTER `optimizer.zero_grad()` (training_step -> zero_grad -> backward -> step) -- publishes them into the parameters'
+    `.grad` with autograd's semantics: `.grad = g * dL/dp` where it is None (zero_grad(set_to_none=True)), `.grad += g * dL/dp`
+    otherwise (zero_grad(set_to_none=False), gradient accumulation)."""
 
     @staticmethod
-    def forward(ctx, loss, anchor):
+    def forward(ctx, loss, anchor, owner):
+        ctx.owner = owner
         return loss.clone()
 
     @staticmethod
     def backward(ctx, g):
-        return None, None
+        ctx.owner()._publish_gradients(g)
+        return None, None, None
 
 
 class VisionEncoder(nn.Sequential):
@@ -136,7 +141,7 @@ class Diffusion_DDPM(_Base):
         self.vision_encoder.eval()
         # B200 execution options
         self.precision = "bf16"
-        self.graph_steps = 1
+        self.graph_steps = 10   # denoising steps per captured CUDA graph (the K % graph_steps remainder runs as 1-step graphs)
         self.batch_max = 0
         self._enc_tag = None
 
@@ -182,15 +187,57 @@ class Diffusion_DDPM(_Base):
     # ------------------------------------------------------------------------------------------
     # training / validation hooks (ddpm:92-125)
     # ------------------------------------------------------------------------------------------
+    def _current_lr(self):
+        """ddpm:95 logs `self.optimizers().param_groups[0]['lr']` (train.py's EarlyStopping monitors it); outside a Lightning
+        trainer there is no attached optimizer and the configured rate is logged instead."""
+        try:
+            opt = self.optimizers()
+            if isinstance(opt, (list, tuple)):
+                opt = opt[0]
+            return opt.param_groups[0]['lr']
+        except Exception:
+            return self.lr
+
     def training_step(self, batch, batch_idx):
         loss = self.process_single_batch(batch)
         self.log("train_loss", loss)
+        self.log('lr', self._current_lr())
         return loss
 
     def validation_step(self, batch, batch_idx):
+        if batch_idx == 0:  # ddpm:100-109: one sampled trajectory per validation run, handed to the plotting hook
+            x_0_predicted, observation_batch, inpaint_vector = self.validate(batch)
+            self.plt2tensorboard(batch=batch, prediction=x_0_predicted, inpaint_vector=inpaint_vector,
+                                 observation_batch=observation_batch)
         loss = self.process_single_batch(batch)
         self.log("val_loss", loss, sync_dist=True)
         return loss
+
+    def plt2tensorboard(self, batch, prediction, inpaint_vector, observation_batch):
+        """ddpm:350-367 draws the sampled trajectory into the tensorboard logger.  Plotting is outside the hot path: the
+        sampled trajectory is kept in `last_validation` (device tensors) and, when a Lightning logger and matplotlib are
+        present, the predicted and ground-truth positions are added as a figure."""
+        self.last_validation = {"prediction": prediction, "inpaint_vector": inpaint_vector, "observation_batch": observation_batch}
+        logger = getattr(self, "logger", None)
+        exp = getattr(logger, "experiment", None) if logger is not None else None
+        if exp is None or not hasattr(exp, "add_figure"):
+            return
+        try:
+            import matplotlib
+            matplotlib.use("Agg")
+            import matplotlib.pyplot as plt
+        except Exception:
+            return
+        pred = prediction[0, 0, :, :2].detach().float().cpu().numpy()
+        truth = batch['position'][0, self.obs_horizon:, :].detach().float().cpu().numpy()
+        obs = observation_batch['position'][0].detach().float().cpu().numpy()
+        fig = plt.figure()
+        plt.plot(obs[:, 0], obs[:, 1], 'o', label='observation')
+        plt.plot(truth[:, 0], truth[:, 1], 'o', label='ground truth')
+        plt.plot(pred[:, 0], pred[:, 1], 'x', label='prediction')
+        plt.legend()
+        exp.add_figure("plot", fig, global_step=int(getattr(self, "global_step", 0)))
+        plt.close(fig)
 
     def configure_optimizers(self):
         optimizer = torch.optim.Adam(self.parameters(), lr=self.lr)
@@ -213,18 +260,30 @@ class Diffusion_DDPM(_Base):
                self.inpaint_horizon, str(self.device))
         if plan is None or self._tplan_key != key or plan.batch_max < B:
             named = self.named_trainable()
-            if plan is not None:  # keep the current values: they live in the old plan's flat buffer
+            carry = None
+            if plan is not None:  # keep the current values (and the optimizer moments): they live in the old plan's flat buffers
                 named = {k: p.detach().clone() for k, p in named.items()}
+                carry = plan.optimizer_state_dict()
                 plan.close()
             ne = self.noise_estimator
-            plan = DenoisePlan(attention=ne._attention, precision=self.precision, batch_max=max(int(B), self.batch_max),
+            cap = max(int(B), self.batch_max)
+            if self.precision == "bf16":  # room to pad a ragged (last-of-epoch) batch to the tile granularity (engine.train_fwd_bwd)
+                up8 = lambda v: (v + 7) // 8 * 8
+                hw3 = (up8(self.pred_horizon + self.inpaint_horizon) // 8) * (up8(self.prediction_dim) // 8)
+                bm = max(1, 128 // hw3)
+                cap = (cap + bm - 1) // bm * bm
+            plan = DenoisePlan(attention=ne._attention, precision=self.precision, batch_max=cap,
                                rows=self.pred_horizon + self.inpaint_horizon, dim=self.prediction_dim, obs_horizon=self.obs_horizon,
                                cond_dim=self.observation_dim, inpaint_rows=self.inpaint_horizon, time_dim=ne.time_dim, device=self.device)
             plan.enable_training(named)
-            # nn.Parameters now alias the plan's flat fp32 buffers: any torch optimizer / all-reduce works on them unchanged
+            if carry is not None:
+                plan.load_optimizer_state_dict(carry)
+            # nn.Parameters now alias the plan's flat fp32 parameter buffer: any torch optimizer works on them unchanged.  Their
+            # `.grad` is filled by `loss.backward()` (_publish_gradients) from the plan's private gradient buffer.
             for k, p in self.named_trainable().items():
                 p.data = plan.param_view(k)
-                p.grad = plan.grad_view(k)
+                p.grad = None
+            self._grads_pub = None
             self._tplan, self._tplan_key = plan, key
             self._tplan_versions = None
         return plan
@@ -251,13 +310,36 @@ class Diffusion_DDPM(_Base):
         loss = plan.train_fwd_bwd(observation_batch['image'], observation_batch['position'], observation_batch['action'],
                                   observation_batch['velocity'], prediction_vector, noise, t, ac ** 0.5, (1 - ac) ** 0.5,
                                   inpaint=x_0_inpaint.reshape(B, -1) if self.inpaint_horizon > 0 else None)
-        anchor = None
-        for k, p in self.named_trainable().items():  # optimizer.zero_grad(set_to_none=True) drops the aliases: restore them
-            if p.grad is None or p.grad.data_ptr() != plan.grad_view(k).data_ptr():
-                p.grad = plan.grad_view(k)
-            anchor = p
+        anchor = next(iter(self.noise_estimator.parameters()))
         self._tplan_versions = self._param_versions()
-        return _NativeLoss.apply(loss.reshape(()), anchor)
+        import weakref
+        return _NativeLoss.apply(loss.reshape(()), anchor, weakref.ref(self))
+
+    def _publish_gradients(self, g):
+        """`loss.backward()` of a native step: .grad (+)= g * (the plan's gradient buffer), for every trainable parameter.
+        The published gradients live in one flat buffer of their own (`.grad` tensors are views of it), so whatever the
+        optimizer / `zero_grad` / `clip_grad_norm_` do to `.grad` in place never touches the buffer the kernels write."""
+        plan = self._tplan
+        named = self.named_trainable()
+        if getattr(self, "_grads_pub", None) is None or self._grads_pub.data_ptr() == 0 or self._grads_pub.numel() != plan.grads_flat.numel():
+            self._grads_pub = torch.empty_like(plan.grads_flat)
+        pub = self._grads_pub
+        views = {k: plan.param_view(k, pub) for k in named}
+        state = [None if p.grad is None else p.grad.data_ptr() == views[k].data_ptr() for k, p in named.items()]
+        g = g.to(pub.dtype)
+        if all(st is None for st in state):          # zero_grad(set_to_none=True) (torch / Lightning default), or the first step
+            torch.mul(plan.grads_flat, g, out=pub)
+            for k, p in named.items():
+                p.grad = views[k]
+        elif all(st is True for st in state):        # zero_grad(set_to_none=False) or gradient accumulation: accumulate, flat
+            pub.addcmul_(plan.grads_flat, g)
+        else:                                        # mixed / foreign .grad tensors: per parameter, autograd's rule
+            for k, p in named.items():
+                inc = plan.grad_view(k) * g
+                if p.grad is None:
+                    p.grad = inc
+                else:
+                    p.grad.add_(inc)
 
     def _weights_changed(self):
         self.noise_estimator._weights_epoch += 1
@@ -318,7 +400,7 @@ class Diffusion_DDPM(_Base):
         plan = self._plan(B)
         self._bind_schedule(plan)
         plan.encode_cond(observation_batch['image'], observation_batch['position'], observation_batch['action'],
-                         observation_batch['velocity'])
+                         observation_batch['velocity'], return_cond=False)
         inpaint = self.prepare_inpaint_vectors(observation_batch).unsqueeze(1)
         rows = self.pred_horizon + self.inpaint_horizon
         if x_T is None:
@@ -340,8 +422,9 @@ class Diffusion_DDPM(_Base):
             return self.validate(batch)
         for key, tensor in batch.items():
             if torch.is_tensor(tensor):
-                batch[key] = tensor.to(self.device)
-        observation_batch = {k: batch[k].float() for k in ('image', 'position', 'action', 'velocity')}
+                batch[key] = tensor.to(self.device, non_blocking=True)
+        # frames may also arrive as the uint8 (B, T, 96, 96, 3) HWC the simulator stores: decoded on the device (a quarter of the H2D bytes)
+        observation_batch = {k: batch[k] if batch[k].dtype == torch.uint8 else batch[k].float() for k in ('image', 'position', 'action', 'velocity')}
         res, _ = self._run_loop(observation_batch, not batched, option == 'sample_history', x_T=x_T, noise=noise, seed=seed)
         if option == 'sample_history':
             _, hist = res
@@ -370,6 +453,9 @@ class Diffusion_DDPM(_Base):
         return cond.reshape(B, T, -1)
 
     def prepare_prediction_vectors(self, prediction_batch):
+        """ddpm:332-338; position only when prediction_dim == 2 (mirrors prepare_inpaint_vectors)."""
+        if self.prediction_dim == prediction_batch['position'].shape[-1]:
+            return prediction_batch['position']
         return torch.cat([prediction_batch['position'], prediction_batch['action']], dim=-1)
 
     def prepare_inpaint_vectors(self, observation_batch):
@@ -432,9 +518,10 @@ class SamplingPipeline:
         self._next += 1
         stream.wait_stream(torch.cuda.current_stream(plan.device))
         with torch.cuda.stream(stream):
-            obs = {k: batch[k].to(m.device, non_blocking=True).float() for k in ('image', 'position', 'action', 'velocity')}
+            obs = {k: batch[k].to(m.device, non_blocking=True) for k in ('image', 'position', 'action', 'velocity')}
+            obs = {k: v if v.dtype == torch.uint8 else v.float() for k, v in obs.items()}
             B = obs['position'].shape[0]
-            plan.encode_cond(obs['image'], obs['position'], obs['action'], obs['velocity'])
+            plan.encode_cond(obs['image'], obs['position'], obs['action'], obs['velocity'], return_cond=False)
             inpaint = m.prepare_inpaint_vectors(obs).unsqueeze(1)
             if x_T is None:
                 x_T = torch.rand(B, 1, m.pred_horizon + m.inpaint_horizon, m.prediction_dim, device=m.device)
@@ -449,4 +536,5 @@ class SamplingPipeline:
     def result(self, ticket):
         out, done, _ = self._pending.pop(ticket)
         done.synchronize()
+        out.record_stream(torch.cuda.current_stream(out.device))  # allocated on the lane stream, consumed on the caller's
         return out

@@ -124,13 +124,22 @@ class DenoisePlan:
             _lib.check(self.lib.spdm_encode_images(self._h, _ptr(img), _ptr(out), img.shape[0], _stream()))
         return out
 
-    def encode_cond(self, image, position, action, velocity):
+    def encode_cond(self, image, position, action, velocity, return_cond=True):
+        """Vision encoder + obs_cond + the six FiLM Linears, cached in the plan.  `image`: float (B,T,3,96,96) in [0,1] as the
+        reference's batches carry it, or uint8 (B,T,96,96,3) HWC as the simulator stores it (decoded x / 255 on the device)."""
         B = image.shape[0]
-        img, pos, act, vel = (_f32c(t, self.device) for t in (image, position, action, velocity))
+        pos, act, vel = (_f32c(t, self.device) for t in (position, action, velocity))
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.spdm_encode_cond(self._h, _ptr(img), _ptr(pos), _ptr(act), _ptr(vel), B, _stream()))
-        self._keep = [img, pos, act, vel]
-        return self.get_cond(B)
+            if image.dtype == torch.uint8:
+                if image.dim() != 5 or tuple(image.shape[2:]) != (96, 96, 3):
+                    raise ValueError("uint8 frames must be (B, T, 96, 96, 3) HWC")
+                img = image.detach().to(self.device, non_blocking=True).contiguous()
+                _lib.check(self.lib.spdm_encode_cond_u8(self._h, _ptr(img), _ptr(pos), _ptr(act), _ptr(vel), B, _stream()))
+            else:
+                img = _f32c(image, self.device)
+                _lib.check(self.lib.spdm_encode_cond(self._h, _ptr(img), _ptr(pos), _ptr(act), _ptr(vel), B, _stream()))
+        self._keep_cond = [img, pos, act, vel]
+        return self.get_cond(B) if return_cond else None
 
     def set_cond(self, obs_cond):
         c = _f32c(obs_cond, self.device).reshape(obs_cond.shape[0], -1)
@@ -283,10 +292,34 @@ class DenoisePlan:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.spdm_train_sync_weights(self._h, _stream()))
 
+    @property
+    def batch_multiple(self):
+        """Granularity of the batch on the tensor-core path (whole samples per 128-row tile at the deepest level); 1 on fp32."""
+        return int(self.lib.spdm_plan_batch_multiple(self._h))
+
     def train_fwd_bwd(self, image, position, action, velocity, x0, noise, t, sqrt_ab, sqrt_1mab, inpaint=None):
         """q-sample + inpaint + encoder + U-Net forward, MSE loss, full backward.  Gradients (fp32, PyTorch layout) are left
-        in `grads_flat`; returns the loss as a 1-element device tensor."""
+        in `grads_flat`; returns the loss as a 1-element device tensor.
+
+        A batch that is not a multiple of `batch_multiple` (the last batch of an epoch: the reference's DataLoader has no
+        drop_last, utils/load_data.py:174) is padded with copies of its first sample and the real count is declared to the
+        library (spdm_train_set_valid): loss and gradients are those of the real samples only."""
         B = x0.shape[0]
+        bm = self.batch_multiple
+        valid = 0
+        if B % bm:
+            Bp = (B + bm - 1) // bm * bm
+            if Bp > self.batch_max:
+                raise _lib.SpdmError("ragged batch of %d needs %d slots (batch_multiple %d) but the plan holds %d" % (B, Bp, bm, self.batch_max))
+            idx = torch.cat([torch.arange(B), torch.zeros(Bp - B, dtype=torch.long)])
+
+            def pad(v):
+                return None if v is None else v.to(self.device).index_select(0, idx.to(self.device))
+            image, position, action, velocity, x0, noise, t, inpaint = (pad(v) for v in (image, position, action, velocity, x0, noise, t, inpaint))
+            valid, B = B, Bp
+        if valid != getattr(self, "_valid", 0):
+            _lib.check(self.lib.spdm_train_set_valid(self._h, valid))
+            self._valid = valid
         pos, act, vel = (_f32c(v, self.device) for v in (position, action, velocity))
         # the observation window is usually a slice [:, :obs_horizon] of the full recording: pass it as a strided view
         # (bf16 path) instead of copying 566 MB per step
@@ -321,6 +354,19 @@ class DenoisePlan:
                                                _ptr(self._adam_scratch), _stream()))
             if sync:
                 self.sync_weights()
+
+    def optimizer_state_dict(self):
+        """The fused optimizer's state (Adam moments per parameter name + step count), for checkpoints and plan rebuilds."""
+        return {"step": int(self.adam_steps),
+                "exp_avg": {k: self.param_view(k, self.adam_m).detach().clone() for k in self.train_offsets},
+                "exp_avg_sq": {k: self.param_view(k, self.adam_v).detach().clone() for k in self.train_offsets}}
+
+    def load_optimizer_state_dict(self, state):
+        self.adam_steps = int(state["step"])
+        for k in self.train_offsets:
+            if k in state["exp_avg"]:
+                self.param_view(k, self.adam_m).copy_(state["exp_avg"][k].to(self.device))
+                self.param_view(k, self.adam_v).copy_(state["exp_avg_sq"][k].to(self.device))
 
     def profile_step(self, B, reps=3):
         """Eager, CUDA-event-timed denoising step: {class: dict(ms, launches, flops, bytes)} averaged over `reps`."""

@@ -56,11 +56,14 @@ class _SchedulerBase:
     kind = None
 
     def __init__(self, num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
-                 trained_betas=None, clip_sample=True, prediction_type="epsilon", **unused):
+                 trained_betas=None, clip_sample=True, prediction_type="epsilon", clip_sample_range=1.0, thresholding=False,
+                 **unused):
         if prediction_type != "epsilon":
             raise NotImplementedError("only prediction_type='epsilon' (the reference's setting) is implemented")
-        if clip_sample:
-            raise NotImplementedError("clip_sample=True is not on the reference's path (it passes clip_sample=False)")
+        if thresholding:
+            raise NotImplementedError("dynamic thresholding is not on the reference's path")
+        if clip_sample and not float(clip_sample_range) > 0:
+            raise ValueError("clip_sample_range must be positive")
         if trained_betas is not None:
             self.betas = torch.as_tensor(trained_betas, dtype=torch.float32).cpu()
         elif beta_schedule == "linear":
@@ -70,7 +73,8 @@ class _SchedulerBase:
         else:
             raise NotImplementedError(beta_schedule)
         self.num_train_timesteps = int(self.betas.numel())
-        self.clip_sample = clip_sample
+        self.clip_sample = bool(clip_sample)
+        self.clip_sample_range = float(clip_sample_range)
         self.prediction_type = prediction_type
         self.alphas = 1.0 - self.betas
         self.alphas_cumprod = torch.cumprod(self.alphas, dim=0)
@@ -99,9 +103,13 @@ class _SchedulerBase:
         raise NotImplementedError
 
     def coef_table(self):
-        """(K, 8) fp32 rows {c0, c1, k_x0, k_x, k_eps, k_noise, 0, 0} for the current `timesteps`:
-           x0 = (x - c0*eps)/c1 ;  x_prev = k_x0*x0 + k_x*x + k_eps*eps + k_noise*z."""
+        """(K, 8) fp32 rows {c0, c1, k_x0, k_x, k_eps, k_noise, clip, 0} for the current `timesteps`:
+           x0 = (x - c0*eps)/c1 ;  clip > 0 (clip_sample=True): x0 = x0.clamp(-clip, clip) ;
+           x_prev = k_x0*x0 + k_x*x + k_eps*eps + k_noise*z."""
         return torch.stack([self.coef_row(int(t)) for t in self.timesteps])
+
+    def _clip(self):
+        return torch.tensor(self.clip_sample_range if self.clip_sample else 0.0)
 
     # -- tensor math: fused CUDA kernels ---------------------------------------------------------
     def _borrow_plan(self, sample):
@@ -156,7 +164,8 @@ class _SchedulerBase:
 
 
 class DDPMScheduler(_SchedulerBase):
-    """diffusers 0.17.1 DDPMScheduler(variance_type='fixed_small'), epsilon prediction, no clipping."""
+    """diffusers 0.17.1 DDPMScheduler(variance_type='fixed_small'), epsilon prediction; clip_sample as in the library
+    (default True, range 1.0; the reference passes False)."""
     kind = "ddpm"
 
     def coef_row(self, t):
@@ -175,7 +184,7 @@ class DDPMScheduler(_SchedulerBase):
         else:
             sigma = torch.tensor(0.0)
         z = torch.tensor(0.0)
-        return torch.stack([beta_prod_t ** 0.5, a_t ** 0.5, k_x0, k_x, z, sigma, z, z]).to(torch.float32)
+        return torch.stack([beta_prod_t ** 0.5, a_t ** 0.5, k_x0, k_x, z, sigma, self._clip(), z]).to(torch.float32)
 
 
 class DDIMScheduler(_SchedulerBase):
@@ -197,4 +206,5 @@ class DDIMScheduler(_SchedulerBase):
         a_prev = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
         beta_prod_t = 1 - a_t
         z = torch.tensor(0.0)
-        return torch.stack([beta_prod_t ** 0.5, a_t ** 0.5, a_prev ** 0.5, z, (1 - a_prev - 0.0) ** 0.5, z, z, z]).to(torch.float32)
+        # (use_clipped_model_output=False, diffusers' default: the direction term keeps the unclipped model output)
+        return torch.stack([beta_prod_t ** 0.5, a_t ** 0.5, a_prev ** 0.5, z, (1 - a_prev - 0.0) ** 0.5, z, self._clip(), z]).to(torch.float32)

@@ -388,7 +388,7 @@ def test_error_paths_are_loud(spdm):
         plan.unet_forward(x, torch.tensor([1, 2, 3]), None)
     plan.close()
     with pytest.raises(NotImplementedError):
-        spdm.DDPMScheduler(num_train_timesteps=10, clip_sample=True)
+        spdm.DDPMScheduler(num_train_timesteps=10, thresholding=True)
     with pytest.raises(NotImplementedError):
         spdm.Diffusion_DDPM(model="UNet")
 
@@ -460,3 +460,47 @@ def test_bf16_forward_folded_w2_convs(spdm, monkeypatch):
     assert rel(outs["fold"], outs["plain"]) < BF16_FWD_TOL
     assert rel(outs["fold_tap"], outs["plain_tap"]) < BF16_FWD_TOL
     assert not torch.equal(outs["fold"], outs["plain"]), "the folded path was not taken"
+
+
+def test_load_from_checkpoint_like_generate_py(spdm, tmp_path):
+    """generate.py:23-36 `load_model`: Diffusion_DDIM.load_from_checkpoint(ckpt, hparams_file=...) on a Lightning-format
+    checkpoint (state_dict with the `noise_estimator.` / `vision_encoder.` prefixes, hyper-parameters in hparams.yaml), then the
+    scheduler swap; the loaded model must sample what a directly-constructed model with the same weights samples."""
+    import yaml
+    sd = fixtures.make_unet_weights(attention=True, seed=0)
+    esd = fixtures.make_encoder_weights()
+    hp = dict(noise_steps=1000, obs_horizon=10, pred_horizon=30, observation_dim=135, prediction_dim=5, learning_rate=1e-4,
+              model="UNet_Film", vision_encoder=None, noise_scheduler_type="linear", inpaint_horizon=1, step_size=5)
+    state = {"noise_estimator." + k: v for k, v in sd.items()}
+    state.update({"vision_encoder." + k: v for k, v in esd.items()})
+    ckpt = tmp_path / "epoch=4.ckpt"
+    torch.save({"state_dict": state, "epoch": 4, "global_step": 100}, ckpt)
+    hparams = tmp_path / "hparams.yaml"
+    hparams.write_text(yaml.safe_dump(hp))
+    # ---- generate.py:23-36 ----
+    num_of_ddim_steps = 10
+    model = spdm.Diffusion_DDIM.load_from_checkpoint(str(ckpt), hparams_file=str(hparams))
+    noise_scheduler = spdm.DDIMScheduler(num_train_timesteps=num_of_ddim_steps, beta_schedule='linear', clip_sample=False,
+                                         prediction_type='epsilon')
+    model.noise_scheduler = noise_scheduler
+    model.noise_steps = num_of_ddim_steps
+    model.eval()
+    # ----
+    model = model.cuda()
+    model.configure(precision="fp32")
+    assert model.hparams["step_size"] == 5 and model.pred_horizon == 30
+    batch = fixtures.make_batch(2, seed=4321)
+    x_T = fixtures.make_xT(1)
+    got = model.sample({k: v.clone() for k, v in batch.items()}, x_T=x_T.cuda())
+    with torch.no_grad():
+        cond = unet_ref.obs_cond(esd, batch)[:1].unsqueeze(1)
+        inp = unet_ref.inpaint_vector(batch, 1)[:1].unsqueeze(1)
+        want = sampler_ref.sample_ref(sd, sampler_ref.make_scheduler("ddim", 10), 10, x_T, cond, inp, 1, attention=True)
+    assert rel(got, want) < 5e-4
+    # uint8 HWC frames through the same public call (batched extension)
+    u8 = (batch["image"] * 255).round().clamp(0, 255).to(torch.uint8).permute(0, 1, 3, 4, 2).contiguous()
+    fl = (u8.float() / 255.0).permute(0, 1, 4, 2, 3).contiguous()
+    xT2 = fixtures.make_xT(2).cuda()
+    a = model.sample(dict(batch, image=fl), batched=True, x_T=xT2)
+    b = model.sample(dict(batch, image=u8), batched=True, x_T=xT2)
+    assert torch.equal(a, b)

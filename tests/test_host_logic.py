@@ -22,7 +22,7 @@ def test_library_builds_and_exports_the_c_abi():
     path = _build.build()
     lib = ctypes.CDLL(path)
     header = open(os.path.join(ROOT, "include", "spdm.h")).read()
-    declared = set(re.findall(r"\b(spdm_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(spdm_[a-z0-9_]+)\s*\(", header))
     assert declared, "no declarations parsed from include/spdm.h"
     for name in declared:
         assert hasattr(lib, name), "libspdm.so does not export %s" % name
@@ -141,6 +141,67 @@ def test_reference_aliases():
         for k in list(sys.modules):
             if k.split(".")[0] in ("models", "utils", "diffusers") and k not in saved:
                 del sys.modules[k]
+
+
+_SCRIPT_PROLOGUE = """
+import sys
+sys.path.insert(0, {root!r})
+import state_policy_diffusionmodel_b200 as spdm
+spdm.install_reference_aliases()
+# ---- generate.py:1-8 ----
+import os
+from models.diffusion_ddpm import *
+from models.diffusion_ddim import *
+from utils.load_data import *
+import pickle
+import time
+import argparse
+assert Diffusion_DDIM.__module__.startswith("state_policy_diffusionmodel_b200") and DDIMScheduler is spdm.DDIMScheduler
+assert LOAD_DATA_MARKER == "real utils.load_data" and torch is not None and np is not None
+# ---- train.py:1-11 ----
+import pytorch_lightning as pl
+from pytorch_lightning import loggers as pl_loggers
+from pytorch_lightning.callbacks.early_stopping import EarlyStopping
+from pytorch_lightning.callbacks import ModelCheckpoint
+from models.diffusion_ddpm import *
+from utils.load_data import *
+from utils.print_utils import *
+assert PRINT_UTILS_MARKER == "real utils.print_utils" and Diffusion_DDPM is spdm.Diffusion_DDPM
+# sub-modules the aliases do not replace keep resolving from the checkout (models/diffusion_ddpm.py:19)
+from models.encoder.autoencoder import *
+assert AUTOENCODER_MARKER == "real models.encoder.autoencoder"
+from utils.schedulers import *
+assert linear_beta_schedule is spdm.linear_beta_schedule
+import models, utils
+assert not getattr(models, "_spdm_standin", False) and not getattr(utils, "_spdm_standin", False)
+print("PROLOGUE_OK")
+"""
+
+
+def test_reference_aliases_do_not_shadow_the_checkout(tmp_path):
+    """VERDICT r1 row b: with the aliases installed, the import prologues of the reference's generate.py:1-8 and train.py:1-11
+    must still find `utils.load_data`, `utils.print_utils` and `models.encoder.autoencoder` in the checkout the script runs
+    from.  The checkout is a temporary tree with the reference's layout (namespace packages, no __init__.py); the absent
+    pytorch_lightning dependency is a test-only stub next to it."""
+    import subprocess
+    ck = tmp_path / "checkout"
+    (ck / "utils").mkdir(parents=True)
+    (ck / "models" / "encoder").mkdir(parents=True)
+    (ck / "utils" / "load_data.py").write_text("import numpy as np\nimport pickle\nLOAD_DATA_MARKER = 'real utils.load_data'\n")
+    (ck / "utils" / "print_utils.py").write_text("PRINT_UTILS_MARKER = 'real utils.print_utils'\n")
+    (ck / "utils" / "schedulers.py").write_text("raise ImportError('the reference file must be shadowed by the alias')\n")
+    (ck / "models" / "diffusion_ddpm.py").write_text("raise ImportError('the reference file must be shadowed by the alias')\n")
+    (ck / "models" / "encoder" / "autoencoder.py").write_text("AUTOENCODER_MARKER = 'real models.encoder.autoencoder'\n")
+    stub = tmp_path / "stubs" / "pytorch_lightning"
+    (stub / "callbacks").mkdir(parents=True)
+    (stub / "__init__.py").write_text("import torch.nn as nn\nclass LightningModule(nn.Module):\n    pass\nclass Trainer: pass\n")
+    (stub / "loggers.py").write_text("class TensorBoardLogger: pass\n")
+    (stub / "callbacks" / "__init__.py").write_text("class ModelCheckpoint: pass\n")
+    (stub / "callbacks" / "early_stopping.py").write_text("class EarlyStopping: pass\n")
+    env = dict(os.environ, PYTHONPATH=str(tmp_path / "stubs"))
+    res = subprocess.run([sys.executable, "-c", _SCRIPT_PROLOGUE.format(root=ROOT)], cwd=str(ck), env=env, capture_output=True,
+                         text=True, timeout=600)
+    assert res.returncode == 0 and "PROLOGUE_OK" in res.stdout, res.stdout + res.stderr
 
 
 def test_shard_range():

@@ -74,3 +74,27 @@ def test_utils_schedulers_known_answers():
     close(b[0], 4.9999999e-05); close(b[999], 9.9999998e-03); close(torch.cumprod(1 - b, 0)[999], 6.4618289e-03, 1e-4)
     b = ref_cosine_beta_schedule(1000)
     close(b[0], 4.1284224e-05, 1e-5); close(b[500], 3.1556915e-03, 1e-5); close(b[999], 0.9990000129)
+
+
+def test_beta_schedules_vs_reference_golden():
+    """utils/schedulers.py:6-40: the oracle restatement AND the product's drop-in functions are bit-identical to what the
+    reference's own file returns (tests/golden/beta_schedules.npz, written by oracle/make_golden.py::golden_beta_schedules from
+    the unmodified /root/reference/utils/schedulers.py)."""
+    import os
+    import numpy as np
+    import state_policy_diffusionmodel_b200 as spdm
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "beta_schedules.npz"))
+
+    class Dev:
+        device = torch.device("cpu")
+    for steps in (10, 50, 100, 1000):
+        for tag, ref, mine in (("linear", ref_linear_beta_schedule, spdm.linear_beta_schedule),
+                               ("linear_v2", ref_linear_beta_schedule_v2, spdm.linear_beta_schedule_v2),
+                               ("cosine", ref_cosine_beta_schedule, spdm.cosine_beta_schedule)):
+            want = torch.from_numpy(g["%s_%d" % (tag, steps)])
+            assert torch.equal(ref(steps), want), (tag, steps)
+            assert torch.equal(mine(Dev(), steps), want), (tag, steps)
+    want = torch.from_numpy(g["cosine_100_s02_f64"])
+    assert want.dtype == torch.float64
+    assert torch.equal(ref_cosine_beta_schedule(100, s=0.02, dtype=torch.float64), want)
+    assert torch.equal(spdm.cosine_beta_schedule(None, 100, s=0.02, dtype=torch.float64), want)
