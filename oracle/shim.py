@@ -4,7 +4,8 @@ Lets the reference's Lightning wrappers (models/diffusion_ddpm.py, models/diffus
 in an environment without pytorch_lightning / diffusers / matplotlib / zarr by injecting minimal
 stand-ins into sys.modules.  The diffusers scheduler classes resolve to oracle/schedulers.py (the
 restated 0.17.1 arithmetic — the package itself is not installable here: parity unpinned).
-Only oracle/make_golden.py uses this.
+Used by oracle/make_golden.py (on /root/reference) and oracle/ref_runner.py (on the copy in oracle/_ref, for bench.py's
+CPU arm).
 """
 import sys
 import types
@@ -47,7 +48,9 @@ class _LightningModule(nn.Module):
         return cls()
 
 
-def install():
+def install(root=None):
+    """`root`: directory holding the reference's `models/` and `utils/` (default: the read-only checkout)."""
+    root = root or REFERENCE_ROOT
     if "pytorch_lightning" not in sys.modules:
         pl = types.ModuleType("pytorch_lightning")
         pl.LightningModule = _LightningModule
@@ -82,5 +85,5 @@ def install():
         pil.Image = types.ModuleType("PIL.Image")
         sys.modules["PIL"] = pil
         sys.modules["PIL.Image"] = pil.Image
-    if REFERENCE_ROOT not in sys.path:
-        sys.path.insert(0, REFERENCE_ROOT)
+    if root not in sys.path:
+        sys.path.insert(0, root)
