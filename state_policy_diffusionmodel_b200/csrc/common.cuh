@@ -107,7 +107,8 @@ struct ApplyArgs {
   const float* beta;
   const float* temb;   // [rows][SPDM_TEMB_WIDTH] or null
   int temb_mode, temb_off;
-  const int* step_ptr; // device int: schedule index (TEMB_STEP)
+  const int* step_ptr; // device int: schedule index (TEMB_STEP); the row used is *step_ptr + step_off
+  int step_off;        // position of this launch's denoising step inside a captured multi-step graph (the counter advances once per graph)
   const float* film;   // [B][SPDM_FILM_WIDTH] or null; scale at film_off, bias at film_off + C
   int film_off;
   int HW, C, ld_in, ld_out;
@@ -140,6 +141,7 @@ struct StepArgs {
   int inpaint_elems;     // inpaint_rows*dim
   int B;                 // samples handled by this launch: [b0, b0 + B) of a batch of B_total
   int b0, B_total;
+  int step_off;          // dyn != null: schedule index = dyn->step + step_off (see ApplyArgs::step_off)
 };
 
 // launchers implemented in kernels.cu ------------------------------------------------------------
@@ -177,6 +179,7 @@ void launch_add_noise(const float* x0, const float* noise, const long long* t, c
 void launch_pack_conv_f32(const float* oihw, float* out, int Cout, int Cin, int k, cudaStream_t s);  // -> [tap][Cin][Cout]
 void launch_pack_conv_bf16(const float* oihw, bf16* out, int Cout, int Cin, int k, cudaStream_t s); // -> [Cout][tap][Cin]
 void launch_pack_conv_fold2_bf16(const float* oihw, bf16* out, int Cout, int Cin, cudaStream_t s);    // W = 2 fold: [2 Cout][9][2 Cin]
+void launch_pack_conv_pfold_bf16(const float* oihw, bf16* out, int Cin, cudaStream_t s);               // pair fold, Cout = 64: [128][3][4][Cin]
 void launch_pack_linear_f32(const float* nk, float* out, int N, int K, int ld_out, int col_off, cudaStream_t s);  // -> [K][ld_out] at col_off
 void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
 void launch_pack_enc_linear(const float* w, float* out, cudaStream_t s);  // (128, 64*12*12 chw) -> [9216 hwc][128]
@@ -188,6 +191,11 @@ struct TcGemm;  // opaque: tensor maps + geometry for one implicit-GEMM launch
 // in: bf16 [Bcap*H*W, Cin] (ld_in); w_packed: bf16 [Cout][taps*Cin]; taps 1 or 9
 TcGemm* tc_gemm_create(const bf16* in, int ld_in, const bf16* w_packed, int Cin, int Cout, int taps, int H, int W,
                        int Bcap);
+// Pair-folded 3x3 conv with 64 output channels (weights from launch_pack_conv_pfold_bf16): same `in` / geometry arguments as
+// tc_gemm_create; runs on the swapped-operand kernel only (EPI_STATS, optionally with the fused GroupNorm apply), B*H*W/2 must
+// be a multiple of 256.  tc_gemm_launch takes the real output pointer / leading dimension.  Null if the geometry does not fit.
+TcGemm* tc_gemm_create_pfold(const bf16* in, int ld_in, const bf16* w_pfold, int Cin, int H, int W, int Bcap);
+bool tc_gemm_is_pfold(const TcGemm* g);
 void tc_gemm_destroy(TcGemm* g);
 // out bf16 [M, Cout] ld_out; stats partials [B][P][2] with EPI_STATS.  B must be a multiple of tc_batch_multiple.
 // returns P, the number of GroupNorm partial slots per sample that EPI_STATS wrote
@@ -207,6 +215,16 @@ bool tc_gemm_fuse_apply_pays(const TcGemm* g, int B);   // ... and it is measure
 // applicable at this geometry / batch; 1 = the cluster only shares the GroupNorm statistics of a tile's N tiles) and the launch; `out` receives the activated bf16 map, no partial tiles.
 int tc_gemm_cluster_split(const TcGemm* g, int B);
 int tc_gemm_launch_cluster(const TcGemm* g, bf16* out, int ld_out, const ApplyArgs* ap, int B, int ks, cudaStream_t s);
+// Chain of cluster convs (conv_chain_kernel): a run of [3x3 conv + GroupNorm (+GELU / time embedding / FiLM)] layers of one deep
+// level (whole samples per 128-row tile) in one launch, optionally with the MaxPool2d(2) (pre_kind 1) / bilinear x2 upsample
+// (pre_kind 2) that feeds the first layer; pre_out is the first layer's input buffer (a channel slice of it for the upsample +
+// concat).  Returns null when the run is not a small-batch cluster case (the caller then issues the layers one by one).
+struct TcChain;
+struct TcChainLayerDesc { const TcGemm* g; bf16* out; int ld_out; ApplyArgs ap; };
+TcChain* tc_chain_create(const TcChainLayerDesc* layers, int n, int B, int pre_kind, const bf16* pre_in, int pre_ld_in, bf16* pre_out,
+                         int pre_ld_out, int pre_C);
+void tc_chain_destroy(TcChain* c);
+int tc_chain_launch(const TcChain* c, cudaStream_t s, int step_off);   // step_off: ApplyArgs::step_off for every layer of this launch
 const char* tc_last_error();
 void tc_set_debug(int v);  // microbenchmark switches, see TcParams::dbg
 int tc_batch_multiple(int H, int W);  // granularity of B required by the 128-row M tiling at geometry HxW

@@ -21,6 +21,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -57,6 +59,10 @@ struct TcParams {
   ApplyArgs ap;           // EPI_APPLY: GroupNorm apply (+GELU, +temb, +FiLM) fused behind the accumulator (raw/out/stats unused)
   bf16* vt;               // EPI_VT: columns >= vt_c0 go, transposed, to vt[row / vt_lk][col - vt_c0][row % vt_lk]
   int vt_c0, vt_C, vt_lk;
+  // pair fold (conv_tc_swap_kernel, 64 real output channels): W is the number of PAIRS per image row, Cout = 128 = (wo, co), the
+  // K loop walks 3 dy x 4 blocks (kernels.cu::pack_conv_pfold_bf16_kernel); fold_c1 = channel offset of a pair's second pixel
+  // in the pair-row view of the input (= ld_in), fold_ldo = real leading dimension of the output (ld_out is the pair-row stride)
+  int fold, fold_c1, fold_ldo;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -85,7 +91,15 @@ __device__ __forceinline__ const float* temb_row(const ApplyArgs& ap, int b) {
   if (ap.temb_mode == TEMB_NONE) return nullptr;
   int trow = 0;
   if (ap.temb_mode == TEMB_PER_SAMPLE) trow = b;
-  else if (ap.temb_mode == TEMB_STEP) trow = *ap.step_ptr;
+  else if (ap.temb_mode == TEMB_STEP) trow = *ap.step_ptr + ap.step_off;
+  return ap.temb + (size_t)trow * SPDM_TEMB_WIDTH + ap.temb_off;
+}
+
+__device__ __forceinline__ const float* temb_row_off(const ApplyArgs& ap, int b, int step_off) {
+  if (ap.temb_mode == TEMB_NONE) return nullptr;
+  int trow = 0;
+  if (ap.temb_mode == TEMB_PER_SAMPLE) trow = b;
+  else if (ap.temb_mode == TEMB_STEP) trow = *ap.step_ptr + step_off;
   return ap.temb + (size_t)trow * SPDM_TEMB_WIDTH + ap.temb_off;
 }
 
@@ -752,6 +766,362 @@ conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Chain of cluster convs: a whole run of [3x3 conv + GroupNorm (+GELU / time embedding / FiLM)] layers of one U-Net level in
+// ONE launch (the 8x2 / 4x1 levels at small batch: down2/down3, the bottleneck, up1 -- 18 of the 54 launches of a batch-256
+// step, each ~13 us of which only ~7 are work).
+//
+// At these levels a 128-row M tile holds whole samples (H == Hb), every layer of the run has the same geometry and GroupNorm is
+// per sample, so M tile m of layer l+1 depends on M tile m of layer l only.  The cluster that owns tile m therefore walks the
+// layers by itself: per layer the phases of conv_tc_cluster_kernel (K slice -> TMEM, dump to shared memory, DSMEM
+// reduce-scatter, statistics exchange, normalise + activate + store), then a cluster barrier instead of a kernel boundary --
+// the activations it wrote (generic proxy, other CTAs of the cluster) become the next layer's TMA operand after
+// fence.proxy.async + barrier.cluster (release / acquire).  No grid-wide synchronisation, so clusters need not be co-resident.
+// The MaxPool2d(2) / bilinear x2 upsample (+ channel concat) in front of the run is done by the cluster for its own samples
+// before the first layer.  Tensor maps and per-layer constants live in a device array (ChainLayer).
+// ---------------------------------------------------------------------------------------------
+struct alignas(128) ChainLayer {
+  CUtensorMap map_a, map_b;
+  int Cin, Cout, kb_per_tap;
+  int bn, n_tiles, ks;        // N tile width, N tiles per M tile, K slices per tile: n_tiles * ks == cluster size
+  int ld_out, pad;
+  bf16* out;
+  ApplyArgs ap;
+};
+struct ChainParams {
+  int H, W, Bt;               // geometry of the level; Bt whole samples per 128-row tile (H * W * Bt == 128)
+  int n_layers;
+  const ChainLayer* layers;   // device memory
+  int pre_kind;               // 0 none, 1 MaxPool2d(2) from a (2H x 2W) map, 2 bilinear x2 upsample (align_corners) from (H/2 x W/2)
+  const bf16* pre_in; int pre_ld_in; bf16* pre_out; int pre_ld_out; int pre_C;
+  int dbg;                    // 2048: thread 64 of block 0 prints per-phase cycle counts of every layer (SPDM_CL_TIMING=1)
+  int step_off;               // replaces ApplyArgs::step_off of every layer (one chain object serves every step of a captured graph)
+};
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+constexpr int CH_STAGES = 4;
+constexpr int CH_B_SLOT = 256 * BLOCK_K * 2;                       // 32 KB: a 256-wide weight tile (128-wide layers use half)
+constexpr int CH_SMEM = CH_STAGES * (A_STAGE_BYTES + CH_B_SLOT) + 1024;
+
+__global__ void __launch_bounds__(CL_THREADS, 1) conv_chain_kernel(const ChainParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + CH_STAGES * A_STAGE_BYTES;
+  __shared__ __align__(8) uint64_t full_bar[CH_STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[CH_STAGES];
+  __shared__ __align__(8) uint64_t tmem_full_bar;
+  __shared__ uint32_t tmem_base_smem;
+  __shared__ __align__(8) float s_stat[32][8][2];   // [sample of the tile][source CTA rank] (sum, sumsq), filled by remote stores
+  __shared__ float s_part[128][2];
+  __shared__ float s_mr[32][2];
+  __shared__ __align__(16) float s_par[3][128];
+  __shared__ __align__(16) float s_film[4096];
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int tid = (int)threadIdx.x;
+  const uint32_t rank = cluster_ctarank();
+  uint32_t CS;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(CS));
+  const int m_tile = blockIdx.x / (int)CS;
+  const int b0 = m_tile * p.Bt;
+  const bool skip_dx = (p.W == 1), skip_dy = (p.H == 1);
+  const int ntx = skip_dx ? 1 : 3, nty = skip_dy ? 1 : 3;
+  const int rps = p.H * p.W;                     // rows per sample (4..32, power of two)
+  const int ns = BLOCK_M / rps;                  // samples of the tile
+  const int lrps = __ffs(rps) - 1;
+
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < CH_STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    mbar_init(&tmem_full_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc<256>(&tmem_base_smem);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = tmem_base_smem;
+  pdl_wait();
+  pdl_trigger();
+
+  // ---- resample in front of the run: this cluster's samples only ----
+  if (p.pre_kind) {
+    const int vpr = p.pre_C >> 3;
+    const int total = p.Bt * rps * vpr;
+    for (int v = (int)rank * CL_THREADS + tid; v < total; v += (int)CS * CL_THREADS) {
+      const int orow_l = v / vpr, c8 = (v - orow_l * vpr) << 3;
+      const int wo = orow_l % p.W, t2 = orow_l / p.W, ho = t2 % p.H, bl = t2 / p.H;
+      const long long b = b0 + bl;
+      float y[8];
+      if (p.pre_kind == 1) {
+        const int Wi = p.W * 2, Hi = p.H * 2;
+        const long long r00 = (b * Hi + 2 * ho) * Wi + 2 * wo;
+        float x[8];
+        load8(p.pre_in + r00 * p.pre_ld_in + c8, y);
+        load8(p.pre_in + (r00 + 1) * p.pre_ld_in + c8, x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], x[i]);
+        load8(p.pre_in + (r00 + Wi) * p.pre_ld_in + c8, x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], x[i]);
+        load8(p.pre_in + (r00 + Wi + 1) * p.pre_ld_in + c8, x);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = fmaxf(y[i], x[i]);
+      } else {   // same arithmetic as upsample_kernel (kernels.cu)
+        const int Hi = p.H / 2, Wi = p.W / 2;
+        const float sh = (p.H > 1) ? (float)(Hi - 1) / (float)(p.H - 1) : 0.f;
+        const float sw = (p.W > 1) ? (float)(Wi - 1) / (float)(p.W - 1) : 0.f;
+        const float fh = sh * ho, fw = sw * wo;
+        const int h0 = (int)fh, w0 = (int)fw;
+        const int h1 = h0 + ((h0 < Hi - 1) ? 1 : 0), w1 = w0 + ((w0 < Wi - 1) ? 1 : 0);
+        const float lh1 = fh - h0, lh0 = 1.f - lh1, lw1 = fw - w0, lw0 = 1.f - lw1;
+        float a00[8], a01[8], a10[8], a11[8];
+        const long long base = b * Hi;
+        load8(p.pre_in + ((base + h0) * Wi + w0) * p.pre_ld_in + c8, a00);
+        load8(p.pre_in + ((base + h0) * Wi + w1) * p.pre_ld_in + c8, a01);
+        load8(p.pre_in + ((base + h1) * Wi + w0) * p.pre_ld_in + c8, a10);
+        load8(p.pre_in + ((base + h1) * Wi + w1) * p.pre_ld_in + c8, a11);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) y[i] = lh0 * (lw0 * a00[i] + lw1 * a01[i]) + lh1 * (lw0 * a10[i] + lw1 * a11[i]);
+      }
+      store8(p.pre_out + ((long long)b0 * rps + orow_l) * p.pre_ld_out + c8, y);
+    }
+    fence_proxy_async_all();
+    cluster_sync_all();
+  }
+
+  uint32_t kit = 0;                              // k-steps issued so far (producer and MMA warp count the same sequence)
+  const int r_t = (warp & 3) * 32 + lane;        // epilogue threads: tile row == TMEM lane
+  long long ts[8];
+#pragma unroll 1
+  for (int l = 0; l < p.n_layers; ++l) {
+    ts[0] = clock64();
+    const ChainLayer* L = p.layers + l;
+    const int bn = L->bn, n_tiles = L->n_tiles, cl_ks = L->ks, kb_per_tap = L->kb_per_tap, Cin = L->Cin, Cout = L->Cout;
+    const int nt = (int)rank % n_tiles, ks = (int)rank / n_tiles;
+    const int n0 = nt * bn;
+    const int k_iters = ntx * nty * kb_per_tap;
+    const int it_begin = ks * k_iters / cl_ks, it_end = (ks + 1) * k_iters / cl_ks;
+    const int Wd = bn / cl_ks;                   // columns of the tile this CTA reduces and finishes (>= 32)
+    const int RS = Wd + 4;
+    float* red = reinterpret_cast<float*>(smem);
+    const uint32_t stage_tx = (uint32_t)(A_STAGE_BYTES + bn * BLOCK_K * 2);
+
+    if (warp == 0) {
+      if (lane == 0) {
+        fence_proxy_async_all();                 // the ring was last touched through the generic proxy (reduction scratch)
+        tma_prefetch_desc(&L->map_a);
+        tma_prefetch_desc(&L->map_b);
+        for (int it = it_begin; it < it_end; ++it, ++kit) {
+          const int s = kit % CH_STAGES;
+          const uint32_t ph = (kit / CH_STAGES) & 1u;
+          const int tap_i = it / kb_per_tap, kb = it - tap_i * kb_per_tap;
+          const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
+          const int dy = skip_dy ? 0 : ty - 1, dx = skip_dx ? 0 : tx - 1;
+          const int tap = (dy + 1) * 3 + (dx + 1);
+          mbar_wait(&empty_bar[s], ph ^ 1u);
+          mbar_expect_tx(&full_bar[s], stage_tx);
+          tma_load_2d(smem_b + s * CH_B_SLOT, &L->map_b, &full_bar[s], tap * Cin + kb * BLOCK_K, n0);
+          tma_load_4d(smem_a + s * A_STAGE_BYTES, &L->map_a, &full_bar[s], kb * BLOCK_K, dx, dy, b0);
+        }
+      }
+      __syncwarp();
+    } else if (warp == 1) {
+      if (lane == 0) {
+        const uint32_t idesc = make_idesc(bn);
+        tc_fence_after();
+        for (int it = it_begin; it < it_end; ++it, ++kit) {
+          const int s = kit % CH_STAGES;
+          const uint32_t ph = (kit / CH_STAGES) & 1u;
+          mbar_wait(&full_bar[s], ph);
+          tc_fence_after();
+          const uint64_t da = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
+          const uint64_t db = make_smem_desc(smem_u32(smem_b + s * CH_B_SLOT));
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+            umma_bf16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > it_begin || k > 0) ? 1u : 0u);
+          umma_commit(&empty_bar[s]);
+        }
+        umma_commit(&tmem_full_bar);
+      }
+      __syncwarp();
+    } else {
+      // ---- while the K slice runs: per-channel constants of this CTA's output slice -> shared memory ----
+      {
+        const int ch0 = n0 + ks * Wd;
+        const bool te_cta = L->ap.temb_mode == TEMB_ROW0 || L->ap.temb_mode == TEMB_STEP;
+        const float* te = te_cta ? temb_row_off(L->ap, 0, p.step_off) : nullptr;
+        const int et = tid - 64;                 // 0..255 over the epilogue warps
+        if (et < Wd) {
+          s_par[0][et] = __ldg(L->ap.gamma + ch0 + et);
+          s_par[1][et] = __ldg(L->ap.beta + ch0 + et);
+          s_par[2][et] = te ? __ldg(te + ch0 + et) : 0.f;
+        }
+        if (L->ap.film && ns * 2 * Wd <= 4096) {
+          for (int i = et; i < ns * 2 * Wd; i += 256) {
+            const int sm = i / (2 * Wd), rem = i - sm * 2 * Wd, hf = rem / Wd, cc = rem - hf * Wd;
+            s_film[i] = __ldg(L->ap.film + (size_t)(b0 + sm) * SPDM_FILM_WIDTH + L->ap.film_off + hf * Cout + ch0 + cc);
+          }
+        }
+      }
+      // ---- accumulator -> own shared memory, column-slice major ----
+      ts[1] = clock64();
+      mbar_wait(&tmem_full_bar, (uint32_t)l & 1u);
+      tc_fence_after();
+      ts[2] = clock64();
+      const uint32_t t_addr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16);
+      const int eh = (warp - 2) >> 2;
+#pragma unroll 1
+      for (int c = eh * (bn / 2); c < (eh + 1) * (bn / 2); c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_addr + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int j = c / Wd, col = c - j * Wd;    // Wd >= 32: a 32-column chunk lies inside one slice
+        float* dst = red + ((size_t)j * BLOCK_M + r_t) * RS + col;
+#pragma unroll
+        for (int i = 0; i < 32; i += 4)
+          *reinterpret_cast<uint4*>(dst + i) = make_uint4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+      }
+      tc_fence_before();
+    }
+    ts[3] = clock64();
+    cluster_sync_all();   // every partial tile of the cluster is in shared memory
+    ts[4] = clock64();
+
+    const int W4 = Wd >> 2;
+    const int lw4 = __ffs(W4) - 1;
+    const int n4 = BLOCK_M * W4;
+    float* blk = red + (size_t)ks * BLOCK_M * RS;
+    {
+      const uint32_t blk_addr = smem_u32(blk);
+      uint32_t src[8];
+#pragma unroll
+      for (int sp = 0; sp < 8; ++sp) src[sp] = sp < cl_ks ? mapa_u32(blk_addr, (uint32_t)(sp * n_tiles + nt)) : 0u;
+#pragma unroll 1
+      for (int i0 = tid; i0 < n4; i0 += 2 * CL_THREADS) {
+        float4 v[8][2];
+        int off[2];
+        bool ok[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int i = i0 + u * CL_THREADS;
+          ok[u] = i < n4;
+          const int row = i >> lw4, c4 = i & (W4 - 1);
+          off[u] = ok[u] ? row * RS + c4 * 4 : 0;
+        }
+#pragma unroll
+        for (int sp = 0; sp < 8; ++sp)
+          if (sp < cl_ks) {
+            if (sp == ks) {
+              v[sp][0] = *reinterpret_cast<const float4*>(blk + off[0]);
+              v[sp][1] = *reinterpret_cast<const float4*>(blk + off[1]);
+            } else {
+              v[sp][0] = ld_dsmem_v4(src[sp] + (uint32_t)off[0] * 4u);
+              v[sp][1] = ld_dsmem_v4(src[sp] + (uint32_t)off[1] * 4u);
+            }
+          }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          float4 acc = v[0][u];
+#pragma unroll
+          for (int sp = 1; sp < 8; ++sp)
+            if (sp < cl_ks) { acc.x += v[sp][u].x; acc.y += v[sp][u].y; acc.z += v[sp][u].z; acc.w += v[sp][u].w; }
+          if (ok[u]) *reinterpret_cast<float4*>(blk + off[u]) = acc;
+          float ps = (acc.x + acc.y) + (acc.z + acc.w);
+          float pq = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, acc.w * acc.w)));
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) { ps += __shfl_xor_sync(0xffffffffu, ps, o); pq += __shfl_xor_sync(0xffffffffu, pq, o); }
+          if (lane == 0 && ok[u]) { const int q = (i0 + u * CL_THREADS) >> 5; s_part[q][0] = ps; s_part[q][1] = pq; }
+        }
+      }
+      __syncthreads();
+      if (tid < ns) {
+        const int sps = (rps * W4) >> 5;
+        float tsum = 0.f, tq = 0.f;
+        for (int q = tid * sps; q < (tid + 1) * sps; ++q) { tsum += s_part[q][0]; tq += s_part[q][1]; }
+        const uint32_t slot = smem_u32(&s_stat[tid][rank][0]);
+        for (int d = 0; d < (int)CS; ++d) st_dsmem_v2(mapa_u32(slot, (uint32_t)d), tsum, tq);
+      }
+    }
+    ts[5] = clock64();
+    cluster_sync_all();   // all statistics partials have arrived; nothing remote is touched below
+    ts[6] = clock64();
+
+    {
+      if (tid < ns) {
+        float tsum = 0.f, tq = 0.f;
+        for (int d = 0; d < (int)CS; ++d) { tsum += s_stat[tid][d][0]; tq += s_stat[tid][d][1]; }
+        const float inv_n = 1.0f / ((float)rps * (float)Cout);
+        const float mean = tsum * inv_n;
+        const float rstd = rsqrtf(fmaxf(tq * inv_n - mean * mean, 0.f) + L->ap.eps);
+        s_mr[tid][0] = rstd;
+        s_mr[tid][1] = -mean * rstd;
+      }
+      __syncthreads();
+      const int ch0 = n0 + ks * Wd;
+      const bool has_film = L->ap.film != nullptr;
+      const bool film_smem = has_film && ns * 2 * Wd <= 4096;
+      const int act = L->ap.act, temb_mode = L->ap.temb_mode;
+      bf16* outp = L->out;
+      const int ld_out = L->ld_out;
+#pragma unroll 4
+      for (int i = tid; i < n4; i += CL_THREADS) {
+        const int row = i >> lw4, c = (i & (W4 - 1)) * 4;
+        const int sm = row >> lrps;
+        const float A = s_mr[sm][0], Bm = s_mr[sm][1];
+        const float4 x = *reinterpret_cast<const float4*>(blk + row * RS + c);
+        const float4 g = *reinterpret_cast<const float4*>(&s_par[0][c]);
+        const float4 e = *reinterpret_cast<const float4*>(&s_par[1][c]);
+        float4 t = *reinterpret_cast<const float4*>(&s_par[2][c]);
+        if (temb_mode == TEMB_PER_SAMPLE) t = __ldg(reinterpret_cast<const float4*>(temb_row_off(L->ap, b0 + sm, p.step_off) + ch0 + c));
+        float f[4] = {fmaf(fmaf(x.x, A, Bm), g.x, e.x), fmaf(fmaf(x.y, A, Bm), g.y, e.y), fmaf(fmaf(x.z, A, Bm), g.z, e.z),
+                      fmaf(fmaf(x.w, A, Bm), g.w, e.w)};
+        if (act == ACT_GELU) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) f[j] = gelu_fast_tc(f[j]);
+        }
+        f[0] += t.x; f[1] += t.y; f[2] += t.z; f[3] += t.w;
+        if (has_film) {
+          float4 fs, fb;
+          if (film_smem) {
+            fs = *reinterpret_cast<const float4*>(&s_film[sm * 2 * Wd + c]);
+            fb = *reinterpret_cast<const float4*>(&s_film[sm * 2 * Wd + Wd + c]);
+          } else {
+            const float* fi = L->ap.film + (size_t)(b0 + sm) * SPDM_FILM_WIDTH + L->ap.film_off + ch0 + c;
+            fs = __ldg(reinterpret_cast<const float4*>(fi));
+            fb = __ldg(reinterpret_cast<const float4*>(fi + Cout));
+          }
+          f[0] = fmaf(fs.x, f[0], fb.x); f[1] = fmaf(fs.y, f[1], fb.y); f[2] = fmaf(fs.z, f[2], fb.z); f[3] = fmaf(fs.w, f[3], fb.w);
+        }
+        uint2 o;
+        __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+        ho[0] = __floats2bfloat162_rn(f[0], f[1]);
+        ho[1] = __floats2bfloat162_rn(f[2], f[3]);
+        *reinterpret_cast<uint2*>(outp + ((long long)m_tile * BLOCK_M + row) * ld_out + ch0 + c) = o;
+      }
+    }
+    ts[7] = clock64();
+    if (l + 1 < p.n_layers) {
+      // this layer's activations (written by every CTA of the cluster through the generic proxy) are the next layer's TMA
+      // operand; the reduction scratch is about to be overwritten by TMA as well
+      fence_proxy_async_all();
+      cluster_sync_all();
+    }
+    if ((p.dbg & 2048) && blockIdx.x == 0 && threadIdx.x == 64)
+      printf("spdm chain timing layer %d (%d->%d bn %d ks %d, %d k-steps): const %lld mainloop-wait %lld dump %lld sync1 %lld reduce %lld sync2 %lld apply %lld endsync %lld total %lld\n",
+             l, Cin, Cout, bn, cl_ks, it_end - it_begin, ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], ts[5] - ts[4], ts[6] - ts[5],
+             ts[7] - ts[6], clock64() - ts[7], clock64() - ts[0]);
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Swapped-operand variant for narrow outputs (Cout = 64 or 128).
 //
@@ -791,7 +1161,7 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   const int lane = threadIdx.x & 31;
   const bool skip_dx = (p.W == 1), skip_dy = (p.H == 1);
   const int ntx = skip_dx ? 1 : 3, nty = skip_dy ? 1 : 3;
-  const int k_iters = ntx * nty * p.kb_per_tap;
+  const int k_iters = p.fold ? 12 * p.kb_per_tap : ntx * nty * p.kb_per_tap;
   const int c_tiles = p.n_tiles;             // tiles of 128 output channels
   const int total = p.total_tiles;           // (m_tiles / 2) * c_tiles
 
@@ -817,16 +1187,32 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
 
   if (warp == 0) {
     if (lane == 0) {
+      // k-step -> weight column, channel offset of the pixel box, (dx, dy) shift
+      auto decode = [&](int it, int& wcol, int& c0, int& dx, int& dy) {
+        if (p.fold) {
+          const int per_dy = 4 * p.kb_per_tap;
+          const int dyi = it / per_dy, r = it - dyi * per_dy, blk = r / p.kb_per_tap, kb = r - blk * p.kb_per_tap;
+          dy = dyi - 1;
+          dx = blk == 0 ? -1 : (blk == 3 ? 1 : 0);
+          c0 = ((blk == 0 || blk == 2) ? p.fold_c1 : 0) + kb * BLOCK_K;
+          wcol = (dyi * 4 + blk) * p.Cin + kb * BLOCK_K;
+        } else {
+          const int tap_i = it / p.kb_per_tap, kb = it - tap_i * p.kb_per_tap;
+          const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
+          dy = skip_dy ? 0 : ty - 1;
+          dx = skip_dx ? 0 : tx - 1;
+          c0 = kb * BLOCK_K;
+          wcol = ((dy + 1) * 3 + (dx + 1)) * p.Cin + kb * BLOCK_K;
+        }
+      };
       uint32_t n_pre = 0;
       if ((int)blockIdx.x < total) {
         const int c_tile = (int)blockIdx.x % c_tiles;
         for (int it = 0; it < k_iters && n_pre < (uint32_t)STAGES; ++it, ++n_pre) {
-          const int tap_i = it / p.kb_per_tap, kb = it - tap_i * p.kb_per_tap;
-          const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
-          const int dy = skip_dy ? 0 : ty - 1, dx = skip_dx ? 0 : tx - 1;
-          const int tap = (dy + 1) * 3 + (dx + 1);
+          int wcol, c0, dx, dy;
+          decode(it, wcol, c0, dx, dy);
           mbar_expect_tx(&full_bar[n_pre], PIX_BYTES + W_BYTES);
-          tma_load_2d(smem_w + n_pre * W_BYTES, &map_w, &full_bar[n_pre], tap * p.Cin + kb * BLOCK_K, c_tile * WM);
+          tma_load_2d(smem_w + n_pre * W_BYTES, &map_w, &full_bar[n_pre], wcol, c_tile * WM);
         }
       }
       pdl_wait();
@@ -838,17 +1224,15 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int it = 0; it < k_iters; ++it, ++kit) {
           const int s = kit % STAGES;
           const uint32_t ph = (kit / STAGES) & 1u;
-          const int tap_i = it / p.kb_per_tap, kb = it - tap_i * p.kb_per_tap;
-          const int ty = tap_i / ntx, tx = tap_i - ty * ntx;
-          const int dy = skip_dy ? 0 : ty - 1, dx = skip_dx ? 0 : tx - 1;
-          const int tap = (dy + 1) * 3 + (dx + 1);
+          int wcol, c0, dx, dy;
+          decode(it, wcol, c0, dx, dy);
           if (kit >= n_pre) {
             mbar_wait(&empty_bar[s], ph ^ 1u);
             mbar_expect_tx(&full_bar[s], PIX_BYTES + W_BYTES);
-            tma_load_2d(smem_w + s * W_BYTES, &map_w, &full_bar[s], tap * p.Cin + kb * BLOCK_K, c_tile * WM);
+            tma_load_2d(smem_w + s * W_BYTES, &map_w, &full_bar[s], wcol, c_tile * WM);
           }
-          tma_load_4d(smem_pix + s * PIX_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t0.h0 + dy, t0.b0);
-          tma_load_4d(smem_pix + s * PIX_BYTES + A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t1.h0 + dy, t1.b0);
+          tma_load_4d(smem_pix + s * PIX_BYTES, &map_a, &full_bar[s], c0, dx, t0.h0 + dy, t0.b0);
+          tma_load_4d(smem_pix + s * PIX_BYTES + A_STAGE_BYTES, &map_a, &full_bar[s], c0, dx, t1.h0 + dy, t1.b0);
         }
       }
     }
@@ -902,7 +1286,10 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       mbar_wait(&tmem_full_bar[acc], aph);
       tc_fence_after();
       const bool active = q < nw;
-      const int ch = c_tile * WM + ch_local;
+      // `ch`: element offset of this lane's channel inside an output row (pair fold: the (wo, co) row of the accumulator is pixel
+      // wo of the pair, channel co); `chp`: the channel whose GroupNorm / time-embedding / FiLM parameters apply
+      const int ch = p.fold ? (ch_local >> 6) * p.fold_ldo + (ch_local & 63) : c_tile * WM + ch_local;
+      const int chp = p.fold ? (ch_local & 63) : c_tile * WM + ch_local;
       const uint32_t t_addr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * NPIX);
       float rs = 0.f, rq = 0.f;
       if (p.flags & EPI_APPLY) {
@@ -965,7 +1352,7 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         }
         asm volatile("bar.sync 1, %0;" ::"r"(n_epi_thr) : "memory");
         if (active) {
-          const float g = __ldg(p.ap.gamma + ch), be = __ldg(p.ap.beta + ch);
+          const float g = __ldg(p.ap.gamma + chp), be = __ldg(p.ap.beta + chp);
           const long long b_first = row0 / pps;
           float te = 0.f;
           const bool has_film = p.ap.film != nullptr;
@@ -978,11 +1365,11 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             A = rstd * g;
             Bc = fmaf(-mean, A, be);
             const float* tr = temb_row(p.ap, (int)(b_first + sl));
-            te = tr ? __ldg(tr + ch) : 0.f;
+            te = tr ? __ldg(tr + chp) : 0.f;
             if (has_film) {
               const float* fi = p.ap.film + (size_t)(b_first + sl) * SPDM_FILM_WIDTH + p.ap.film_off;
-              fs = __ldg(fi + ch);
-              fb = __ldg(fi + p.Cout + ch);
+              fs = __ldg(fi + chp);
+              fb = __ldg(fi + p.ap.C + chp);
             }
           };
 #pragma unroll 1
@@ -1208,6 +1595,55 @@ TcGemm* tc_gemm_create(const bf16* in, int ld_in, const bf16* w_packed, int Cin,
   return g;
 }
 
+// Pair-folded conv (TcParams::fold): geometry of the PAIR grid (W / 2 columns), 128 = (wo, co) output rows, swapped kernel only.
+TcGemm* tc_gemm_create_pfold(const bf16* in, int ld_in, const bf16* w_pfold, int Cin, int H, int W, int Bcap) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled entry point not available"); return nullptr; }
+  if (Cin % BLOCK_K || ld_in % 8 || W % 2) { snprintf(g_tc_err, sizeof g_tc_err, "tc_gemm_create_pfold: unsupported shape Cin=%d ld=%d W=%d", Cin, ld_in, W); return nullptr; }
+  const int Wp = W / 2;
+  if (BLOCK_M % Wp) { snprintf(g_tc_err, sizeof g_tc_err, "tc_gemm_create_pfold: W/2=%d does not divide 128", Wp); return nullptr; }
+  int Hb = BLOCK_M / Wp;
+  if (Hb > H) Hb = H;
+  if (H % Hb || BLOCK_M % (Hb * Wp)) { snprintf(g_tc_err, sizeof g_tc_err, "tc_gemm_create_pfold: H=%d W/2=%d not tileable", H, Wp); return nullptr; }
+  const int Bt = BLOCK_M / (Hb * Wp);
+  const int pps = H * Wp;
+  if (Bcap % Bt || !(pps == 16 || (pps >= 32 && pps % 32 == 0 && (pps >= 256 ? pps % 256 == 0 : 256 % pps == 0)))) {
+    snprintf(g_tc_err, sizeof g_tc_err, "tc_gemm_create_pfold: geometry %dx%d / Bcap %d does not fit 256-pair tiles", H, W, Bcap);
+    return nullptr;
+  }
+  TcGemm* g = new TcGemm();
+  memset(g, 0, sizeof(*g));
+  g->Bcap = Bcap;
+  g->block_n = 128;
+  g->has256 = false;
+  g->can_swap = true;
+  TcParams& p = g->p;
+  p.H = H; p.W = Wp; p.Hb = Hb; p.Bt = Bt; p.Cin = Cin; p.Cout = 128; p.taps = 9;
+  p.kb_per_tap = Cin / BLOCK_K;
+  p.fold = 1; p.fold_c1 = ld_in;
+  {  // pair-row view of the channels-last activation: (2 pixels x channels, W / 2, H, B); the second pixel's channels start at ld_in
+    cuuint64_t dims[4] = {(cuuint64_t)(ld_in + Cin), (cuuint64_t)Wp, (cuuint64_t)H, (cuuint64_t)Bcap};
+    cuuint64_t strides[3] = {(cuuint64_t)2 * ld_in * 2, (cuuint64_t)W * ld_in * 2, (cuuint64_t)H * W * ld_in * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)Wp, (cuuint32_t)Hb, (cuuint32_t)Bt};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&g->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(A, pair fold) failed: %d", (int)r); delete g; return nullptr; }
+  }
+  {
+    const cuuint64_t Ktot = (cuuint64_t)12 * Cin;
+    cuuint64_t dims[2] = {Ktot, 128};
+    cuuint64_t strides[1] = {Ktot * 2};
+    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)BLOCK_M};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(&g->map_wswap, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)w_pfold, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(W, pair fold) failed: %d", (int)r); delete g; return nullptr; }
+  }
+  return g;
+}
+bool tc_gemm_is_pfold(const TcGemm* g) { return g && g->p.fold != 0; }
+
 void tc_gemm_destroy(TcGemm* g) { delete g; }
 
 static bool swap_taken(const TcGemm* g, int m_tiles, int flags) {
@@ -1347,6 +1783,138 @@ int tc_gemm_launch_cluster(const TcGemm* g, bf16* out, int ld_out, const ApplyAr
   return 0;
 }
 
+
+// ---- chain of cluster convs (conv_chain_kernel) ----
+struct TcChain {
+  ChainParams p;
+  ChainLayer* dev_layers;
+  int cs, m_tiles, n_layers;
+};
+
+static cudaError_t chain_launch_cfg(const ChainParams& p, int grid, int cs, cudaStream_t s, int* max_clusters) {
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(conv_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, CH_SMEM);
+    attr = true;
+  }
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(CL_THREADS);
+  cfg.dynamicSmemBytes = CH_SMEM;
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = (unsigned)cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_spdm_pdl ? 2 : 1;
+  if (max_clusters) {
+    cfg.numAttrs = 1;
+    return cudaOccupancyMaxActiveClusters(max_clusters, conv_chain_kernel, &cfg);
+  }
+  return cudaLaunchKernelEx(&cfg, conv_chain_kernel, p);
+}
+
+// Per-layer tile shape for a chain run by clusters of `cs`: N tile width bn and K slices ks with (Cout / bn) * ks == cs.
+static bool chain_layer_shape(const TcGemm* g, int cs, int* bn_out, int* ks_out) {
+  const TcParams& p = g->p;
+  const int k_iters = (p.W == 1 ? 1 : 3) * (p.H == 1 ? 1 : 3) * p.kb_per_tap;
+  // prefer the shape that moves the fewest bytes through DSMEM per CTA: (ks - 1) / ks * 128 * bn * 4
+  int best_bn = 0, best_ks = 0;
+  long long best_cost = 0;
+  for (int bn = 128; bn <= 256; bn += 128) {
+    if (p.Cout % bn) continue;
+    const int n_tiles = p.Cout / bn;
+    if (cs % n_tiles) continue;
+    const int ks = cs / n_tiles;
+    if (ks < 1 || ks > 8 || ks > k_iters || bn / ks < 32 || (bn / ks) % 32) continue;
+    const long long cost = (long long)(ks - 1) * 128 * bn * 4 / ks + (long long)((k_iters + ks - 1) / ks) * 9000;   // DSMEM bytes + the ~9 KB a k-step (~530 cycles) is worth at ~17 B/clk
+    if (!best_bn || cost < best_cost) { best_bn = bn; best_ks = ks; best_cost = cost; }
+  }
+  *bn_out = best_bn; *ks_out = best_ks;
+  return best_bn != 0;
+}
+
+TcChain* tc_chain_create(const TcChainLayerDesc* layers, int n, int B, int pre_kind, const bf16* pre_in, int pre_ld_in, bf16* pre_out,
+                         int pre_ld_out, int pre_C) {
+  static int off = -1;
+  if (off < 0) { const char* e = getenv("SPDM_NO_CHAIN"); off = e ? atoi(e) : 0; }
+  if (off || n < 1 || n > 16) return nullptr;
+  const TcParams& p0 = layers[0].g->p;
+  const int rps = p0.Hb * p0.W;
+  if (p0.taps != 9 || p0.H != p0.Hb || rps < 4 || rps > 32) return nullptr;
+  const int m_tiles = (int)(((long long)B * p0.H * p0.W) / BLOCK_M);
+  if (m_tiles < 1 || (long long)m_tiles * BLOCK_M != (long long)B * p0.H * p0.W) return nullptr;
+  for (int i = 0; i < n; ++i) {
+    const TcParams& q = layers[i].g->p;
+    if (q.taps != 9 || q.H != p0.H || q.W != p0.W || q.Hb != p0.Hb) return nullptr;
+    if (tc_gemm_split(layers[i].g, B) <= 1) return nullptr;   // only where the tiles alone would leave most SMs idle
+  }
+  // largest cluster size whose clusters all run in one wave and that every layer can be cut for
+  int cs = 0;
+  ChainParams probe{};
+  for (int c = 8; c >= 2; c >>= 1) {
+    static int mac_cache[9] = {};
+    if (mac_cache[c] == 0) {
+      int nmax = 0;
+      if (chain_launch_cfg(probe, c, c, nullptr, &nmax) != cudaSuccess) { cudaGetLastError(); nmax = 0; }
+      mac_cache[c] = nmax > 0 ? nmax : -1;
+    }
+    if (mac_cache[c] < m_tiles) continue;
+    bool ok = true;
+    for (int i = 0; i < n && ok; ++i) { int bn, ks; ok = chain_layer_shape(layers[i].g, c, &bn, &ks); }
+    if (ok) { cs = c; break; }
+  }
+  if (!cs) return nullptr;
+  std::vector<ChainLayer> host((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const TcGemm* g = layers[i].g;
+    ChainLayer& L = host[i];
+    memset(&L, 0, sizeof L);
+    int bn, ks;
+    chain_layer_shape(g, cs, &bn, &ks);
+    L.map_a = g->map_a;
+    if (bn == 256) L.map_b = g->map_b256;
+    else if (g->block_n == 128) L.map_b = g->map_b;
+    else return nullptr;
+    L.Cin = g->p.Cin; L.Cout = g->p.Cout; L.kb_per_tap = g->p.kb_per_tap;
+    L.bn = bn; L.n_tiles = g->p.Cout / bn; L.ks = ks;
+    L.out = layers[i].out; L.ld_out = layers[i].ld_out; L.ap = layers[i].ap;
+    static int verbose = -1;
+    if (verbose < 0) { const char* e = getenv("SPDM_VERBOSE"); verbose = e ? atoi(e) : 0; }
+    if (verbose) fprintf(stderr, "spdm chain layer %d: %dx%d %d->%d m_tiles %d cluster %d: bn %d n_tiles %d ks %d\n", i, g->p.H, g->p.W, L.Cin, L.Cout, m_tiles, cs, bn, L.n_tiles, ks);
+  }
+  TcChain* c = new TcChain();
+  memset(c, 0, sizeof *c);
+  if (cudaMalloc(&c->dev_layers, sizeof(ChainLayer) * n) != cudaSuccess) { delete c; return nullptr; }
+  if (cudaMemcpy(c->dev_layers, host.data(), sizeof(ChainLayer) * n, cudaMemcpyHostToDevice) != cudaSuccess) { cudaFree(c->dev_layers); delete c; return nullptr; }
+  c->cs = cs; c->m_tiles = m_tiles; c->n_layers = n;
+  c->p.H = p0.H; c->p.W = p0.W; c->p.Bt = p0.Bt; c->p.n_layers = n; c->p.layers = c->dev_layers;
+  {
+    static int timing = -1;
+    if (timing < 0) { const char* e = getenv("SPDM_CL_TIMING"); timing = e ? atoi(e) : 0; }
+    c->p.dbg = timing ? 2048 : 0;
+  }
+  c->p.pre_kind = pre_kind; c->p.pre_in = pre_in; c->p.pre_ld_in = pre_ld_in; c->p.pre_out = pre_out; c->p.pre_ld_out = pre_ld_out; c->p.pre_C = pre_C;
+  return c;
+}
+
+void tc_chain_destroy(TcChain* c) {
+  if (!c) return;
+  cudaFree(c->dev_layers);
+  delete c;
+}
+
+int tc_chain_launch(const TcChain* c, cudaStream_t s, int step_off) {
+  ChainParams p = c->p;
+  p.step_off = step_off;
+  cudaError_t e = chain_launch_cfg(p, c->m_tiles * c->cs, c->cs, s, nullptr);
+  if (e != cudaSuccess) { snprintf(g_tc_err, sizeof g_tc_err, "chain launch failed: %s", cudaGetErrorString(e)); return -1; }
+  ++g_tc_launches;
+  return 0;
+}
+
 bool tc_gemm_can_fuse_apply(const TcGemm* g, int B) {
   if (g_tc_dbg & 256) return false;
   const TcParams& p = g->p;
@@ -1358,16 +1926,29 @@ bool tc_gemm_can_fuse_apply(const TcGemm* g, int B) {
   return p.Cout == bn && p.H == p.Hb;  // one N tile, whole samples per M tile
 }
 
-// Does fusing the GroupNorm apply into this conv's epilogue pay?  Measured: only on the swapped-operand kernel and only where its
-// 8-warp epilogue is used, i.e. the launch has at most two tiles per CTA (batch 256: -1 % of the step; batch 4096: +3.5 %, the
-// tile's CTAs then do elementwise work that a separate kernel spreads over all SMs while hiding under the next tile's MMAs).
+// Does fusing the GroupNorm apply into this conv's epilogue pay?  Measured per layer at batch 256 and 4096 (event-timed eager
+// steps, profiles/r02_fused_apply_per_layer.md):
+//   * swapped-operand kernel, launch of at most two tiles per CTA: its 8-warp epilogue is exposed anyway (batch 256: -1 % of the step);
+//   * swapped-operand kernel, persistent launch: the epilogue hides under the next tile's MMAs when the tile's K loop is long
+//     enough (>= 18 k-steps) or the map is large (>= 256 pixels per sample, where the separate apply kernel is the expensive one):
+//     batch 4096: 128->128 32x8 second conv 279 + 127 us -> 301 us, 256->256 16x4 254 + 80 -> 271; short K loops at 16x4 lose
+//     (64->64: 41 + 23 -> 76 us) and stay unfused;
+//   * plain kernel (Cout = 256 in one N tile): the 4x1 level gains (19 + 15 -> 25 us) and so do the long K loops of the 16x4 level
+//     (256->256: 254 + 80 -> 271 us); the 8x2 level does not (56 + 23 -> 90 us).
 bool tc_gemm_fuse_apply_pays(const TcGemm* g, int B) {
   if (!tc_gemm_can_fuse_apply(g, B)) return false;
   const TcParams& p = g->p;
   const int m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
-  if (!swap_taken(g, m_tiles, EPI_STATS)) return false;
+  static int big = -1;   // SPDM_FUSE_BIG=0: never fuse in persistent (multi-tile) launches (A/B switch: round-1 behaviour)
+  if (big < 0) { const char* e = getenv("SPDM_FUSE_BIG"); big = e ? atoi(e) : 1; }
+  const int k_iters0 = (p.W == 1 ? 1 : 3) * (p.H == 1 ? 1 : 3) * p.kb_per_tap;
+  if (!swap_taken(g, m_tiles, EPI_STATS)) return big && (p.H * p.W <= 8 || (p.H * p.W >= 64 && k_iters0 >= 36));
   const int total = (m_tiles / 2) * ((p.Cout + BLOCK_M - 1) / BLOCK_M);
-  return total <= 2 * num_sms();
+  if (total <= 2 * num_sms()) return true;
+  if (!big) return false;
+  const int k_iters = p.fold ? 12 * p.kb_per_tap : (p.W == 1 ? 1 : 3) * (p.H == 1 ? 1 : 3) * p.kb_per_tap;
+  const int pps_real = p.H * p.W * (p.fold ? 2 : 1);
+  return k_iters >= 18 || pps_real >= 256;
 }
 
 int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const float* bias, const bf16* resid, int ld_res, int flags,
@@ -1380,12 +1961,25 @@ int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const f
   p.vt = vt; p.vt_lk = vt_lk; p.vt_C = p.Cout / 3; p.vt_c0 = 2 * (p.Cout / 3);
   p.out = out; p.ld_out = ld_out; p.stats = stats; p.bias = bias; p.resid = resid; p.ld_res = ld_res; p.flags = flags;
   p.m_tiles = (int)(((long long)B * p.H * p.W) / BLOCK_M);
+  if (p.fold) {   // pair fold: swapped kernel only; the output row of a pair is two real rows
+    if (p.ksplit != 1 || !swap_taken(g, p.m_tiles, flags)) {
+      snprintf(g_tc_err, sizeof g_tc_err, "pair-folded conv: only EPI_STATS launches over an even number of 128-pair tiles (B=%d)", B);
+      return -1;
+    }
+    p.fold_ldo = ld_out;
+    p.ld_out = 2 * ld_out;
+  }
   if (p.ksplit == 1 && swap_taken(g, p.m_tiles, flags)) {
     p.n_tiles = (p.Cout + BLOCK_M - 1) / BLOCK_M;
     p.total_tiles = (p.m_tiles / 2) * p.n_tiles;
     const int pps = p.H * p.W;
     const int nw = p.Cout >= BLOCK_M ? 4 : p.Cout / 32;
-    const int threads = p.total_tiles <= 2 * num_sms() ? SWAP_THREADS : NUM_THREADS;   // 8 epilogue warps only where the epilogue is exposed (<= 2 tiles per CTA)
+    // 8 epilogue warps also for persistent launches that carry the fused GroupNorm apply: its two passes over the accumulator
+    // (statistics, then normalise + GELU + store) are twice the plain epilogue's work; batch 4096: 15 550 -> 16 170 trajectories/s
+    // (SPDM_FUSE_EPI8=0: A/B switch)
+    static int epi8 = -1;
+    if (epi8 < 0) { const char* e = getenv("SPDM_FUSE_EPI8"); epi8 = e ? atoi(e) : 1; }
+    const int threads = (p.total_tiles <= 2 * num_sms() || (epi8 && fuse)) ? SWAP_THREADS : NUM_THREADS;   // 8 epilogue warps only where the epilogue is exposed (<= 2 tiles per CTA)
     const int halves = (threads == SWAP_THREADS && pps >= 256) ? 2 : 1;   // then a sample of >= 256 pixels gets one partial per column half
     p.P = (pps > 256 ? pps / 256 : 1) * p.n_tiles * nw * halves;
     constexpr int STG = 4;

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(APPLY_THREADS) apply_kernel(ApplyArgs a) {
   if (has_temb) {
     int trow = 0;
     if (a.temb_mode == TEMB_PER_SAMPLE) trow = b;
-    else if (a.temb_mode == TEMB_STEP) trow = *a.step_ptr;
+    else if (a.temb_mode == TEMB_STEP) trow = *a.step_ptr + a.step_off;
     load8(a.temb + (size_t)trow * SPDM_TEMB_WIDTH + a.temb_off + c8, te);
   }
   if (has_film) {
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(256) apply_partial_kernel(ApplyArgs a, const f
   if (a.temb_mode != TEMB_NONE) {
     int trow = 0;
     if (a.temb_mode == TEMB_PER_SAMPLE) trow = b;
-    else if (a.temb_mode == TEMB_STEP) trow = *a.step_ptr;
+    else if (a.temb_mode == TEMB_STEP) trow = *a.step_ptr + a.step_off;
     temb = a.temb + (size_t)trow * SPDM_TEMB_WIDTH + a.temb_off;
   }
   const float* film = a.film ? a.film + (size_t)b * SPDM_FILM_WIDTH + a.film_off : nullptr;
@@ -868,7 +868,7 @@ __global__ void step_kernel(StepArgs a) {
   float* history = nullptr;
   unsigned long long seed = 0;
   if (a.dyn) {
-    step = a.dyn->step;
+    step = a.dyn->step + a.step_off;
     noise = a.dyn->noise ? a.dyn->noise + (size_t)step * total : nullptr;
     inpaint = a.dyn->inpaint;
     history = a.dyn->history;
@@ -909,7 +909,7 @@ __global__ void outc_step_kernel(StepArgs a, const T* __restrict__ act, int ld, 
   const long long li = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (li >= (long long)a.B * a.n) return;
   const long long i = (long long)a.b0 * a.n + li;
-  const int step = a.dyn->step;
+  const int step = a.dyn->step + a.step_off;
   const float* noise = a.dyn->noise ? a.dyn->noise + (size_t)step * total : nullptr;
   const float* inpaint = a.dyn->inpaint;
   float* history = a.dyn->history;
@@ -1242,6 +1242,29 @@ __global__ void pack_conv_fold2_bf16_kernel(const float* __restrict__ oihw, bf16
   const int tx = wi - wo + 1;
   out[((size_t)co2 * 9 + ty * 3 + 1) * (2 * Cin) + cin2] = __float2bfloat16_rn(oihw[((size_t)co * Cin + ci) * 9 + ty * 3 + tx]);
 }
+// Pair fold of a 64-output-channel 3x3 conv (conv_tc_swap_kernel, TcParams::fold): two horizontally adjacent pixels (a "pair",
+// wp = w / 2) become one GEMM row, so that the swapped-operand MMA gets M = 128 real rows (wo, co) instead of 64 -- a 64-row
+// tcgen05.mma takes as long as a 128-row one.  Per dy the K dimension is four Cin-wide blocks:
+//   blk 0: pair wp - 1, its pixel wi = 1 (w = 2 wp - 1)     blk 1: pair wp, wi = 0 (w = 2 wp)
+//   blk 2: pair wp, wi = 1 (w = 2 wp + 1)                   blk 3: pair wp + 1, its pixel wi = 0 (w = 2 wp + 2)
+//   out[(wo*64 + co)][(dy*4 + blk)*Cin + ci] = w[co][ci][dy][dx + 1] with dx = w_in - (2 wp + wo), zero where |dx| > 1
+// i.e. 8 of the 16 (wo, blk) sub-blocks per dy are dense, 6 of them... the two corner ones (blk 0 / wo 1, blk 3 / wo 0) are zero.
+__global__ void pack_conv_pfold_bf16_kernel(const float* __restrict__ oihw, bf16* __restrict__ out, int Cin) {
+  pdl_wait();
+  pdl_trigger();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long total = 128LL * 12 * Cin;
+  if (i >= total) return;
+  const int r = (int)(i % (12 * Cin));
+  const int m = (int)(i / (12 * Cin));
+  const int ci = r % Cin, blk = (r / Cin) & 3, dyi = r / (4 * Cin);
+  const int wo = m >> 6, co = m & 63;
+  const int w_in = blk == 0 ? -1 : (blk == 1 ? 0 : (blk == 2 ? 1 : 2));
+  const int dx = w_in - wo;
+  float v = 0.f;
+  if (dx >= -1 && dx <= 1) v = oihw[((size_t)co * Cin + ci) * 9 + dyi * 3 + dx + 1];
+  out[i] = __float2bfloat16_rn(v);
+}
 __global__ void pack_linear_f32_kernel(const float* __restrict__ nk, float* __restrict__ out, int N, int K, int ld_out, int col_off) {
   pdl_wait();
   pdl_trigger();
@@ -1280,6 +1303,10 @@ void launch_pack_conv_bf16(const float* oihw, bf16* out, int Cout, int Cin, int 
 void launch_pack_conv_fold2_bf16(const float* oihw, bf16* out, int Cout, int Cin, cudaStream_t s) {
   const long long total = 2LL * Cout * 3 * 2 * Cin;
   launch_pdl(pack_conv_fold2_bf16_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, oihw, out, Cout, Cin);
+}
+void launch_pack_conv_pfold_bf16(const float* oihw, bf16* out, int Cin, cudaStream_t s) {
+  const long long total = 128LL * 12 * Cin;
+  launch_pdl(pack_conv_pfold_bf16_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, oihw, out, Cin);
 }
 void launch_pack_linear_f32(const float* nk, float* out, int N, int K, int ld_out, int col_off, cudaStream_t s) {
   launch_pdl(pack_linear_f32_kernel, dim3(cdiv((long long)N * K, 256)), dim3(256), 0, s, nk, out, N, K, ld_out, col_off);

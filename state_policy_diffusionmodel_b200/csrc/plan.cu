@@ -67,6 +67,7 @@ struct GemmW {  // a 3x3 convolution or a Linear layer
   float* w32 = nullptr;  // [taps][Cin][Cout]   (fp32 path)
   bf16* w16 = nullptr;   // [Cout][taps*Cin]    (bf16 tcgen05 path)
   bf16* w16_fold = nullptr;  // 3x3 convs of the W = 2 level, inference: [2 Cout][9][2 Cin], the two pixels of a row folded into channels
+  bf16* w16_pfold = nullptr; // 3x3 convs with 64 output channels, inference: pair fold [128][3][4][Cin] (kernels.cu::pack_conv_pfold_bf16_kernel)
   float* bias = nullptr; // [Cout] or null
   GemmW* twin = nullptr; // training: the data-gradient GEMM (Cin/Cout exchanged, transposed / tap-flipped weights)
 };
@@ -149,6 +150,7 @@ struct spdm_plan {
   std::map<int, size_t> partial_cap;
   bool no_splitk = false;              // SPDM_NO_SPLITK=1 (A/B switch)
   bool no_fold = false;                // SPDM_NO_FOLD=1: W = 2 convs as ordinary 9-tap implicit GEMMs (A/B switch)
+  bool no_pfold = false;               // SPDM_NO_PFOLD=1: 64-channel convs on 64-row MMAs instead of the pair fold (A/B switch)
   bool no_fuse = false;                // SPDM_NO_FUSE_APPLY=1: keep GroupNorm apply as a separate kernel (A/B switch)
   std::vector<char> skip;              // SPDM_SKIP_IDX=i,j,...: launches of one forward (in timed() order) that are NOT issued --
   int timed_idx = 0;                   // timing ablation only (tools/ablate.py), results are garbage
@@ -161,6 +163,7 @@ struct spdm_plan {
   float* enc_u8_stage = nullptr; int enc_u8_cap = 0;  // decoded frames of spdm_encode_cond_u8 on plans whose encoder reads fp32
 
   std::map<std::string, TcGemm*> tc_cache;
+  std::map<std::string, TcChain*> chain_cache;   // runs of deep-level convs as one launch (null = tried, not applicable)
   // graphs keyed by batch: [0] = graph_steps-step body, [1] = 1-step body
   struct GraphSet { cudaGraphExec_t multi = nullptr, single = nullptr; long long n_multi = 0, n_single = 0; };
   std::map<long long, GraphSet> graphs;
@@ -231,6 +234,8 @@ GemmW& reg_conv3(spdm_plan* p, const std::string& name, int Cin, int Cout) {
   // makes the conv dense along W (Fwd::fold_ok)
   const bool level2 = name.rfind("down2.", 0) == 0 || name.rfind("up1.", 0) == 0;
   if (p->bf16_mode && level2 && p->W0 == 8 && Cin % 32 == 0 && Cout % 32 == 0) g.w16_fold = p->alloc<bf16>((size_t)2 * Cout * 9 * 2 * Cin);
+  // 64 output channels: a 64-row tcgen05.mma costs what a 128-row one does, so pairs of pixels are folded into the rows (Fwd::pfold_tc)
+  if (p->bf16_mode && Cout == 64 && Cin % 64 == 0 && !p->no_pfold) g.w16_pfold = p->alloc<bf16>((size_t)128 * 12 * Cin);
   p->missing_unet.insert(name + ".weight");
   GemmW* gp = &g;
   bool bfm = p->bf16_mode;
@@ -239,6 +244,7 @@ GemmW& reg_conv3(spdm_plan* p, const std::string& name, int Cin, int Cout) {
     if (bfm) launch_pack_conv_bf16(src, gp->w16, Cout, Cin, 3, s);
     else launch_pack_conv_f32(src, gp->w32, Cout, Cin, 3, s);
     if (gp->w16_fold && !p->tr) launch_pack_conv_fold2_bf16(src, gp->w16_fold, Cout, Cin, s);  // inference only (Fwd::fold_ok)
+    if (gp->w16_pfold && !p->tr) launch_pack_conv_pfold_bf16(src, gp->w16_pfold, Cin, s);        // inference only (Fwd::pfold_tc)
     if (gp->twin) {
       if (bfm) launch_pack_conv_dgrad_bf16(src, gp->twin->w16, Cout, Cin, s);
       else launch_pack_conv_dgrad_f32(src, gp->twin->w32, Cout, Cin, s);
@@ -451,6 +457,7 @@ struct FwdCtx {
   const float* temb;     // rows of SPDM_TEMB_WIDTH
   int temb_mode;
   const int* step_ptr;
+  int step_off;          // this step's position inside a captured multi-step graph (ApplyArgs::step_off)
   const float* film;     // [B][1792] or null
   int B;
   const StepArgs* fuse_step;  // non-null: replace outc by outc + posterior update (the sampling loop)
@@ -544,6 +551,22 @@ template <typename T> struct Fwd {
     return tc;
   }
 
+  // 64 output channels, inference: the pair-folded form of the conv (null where it does not apply at this geometry / batch)
+  TcGemm* pfold_tc(const std::string& wname, GemmW& g, const T* in, int ld_in, int level) {
+    if constexpr (sizeof(T) == 2) {
+      if (!g.w16_pfold || p->tr || g.taps != 9) return nullptr;
+      const int H = p->levelH(level), W = p->levelW(level);
+      if (W % 2 || ((long long)Bpad * H * (W / 2)) % 256) return nullptr;
+      char key[160];
+      snprintf(key, sizeof key, "%s#pfold|%p|%d", wname.c_str(), (const void*)in, ld_in);
+      auto it = p->tc_cache.find(key);
+      if (it == p->tc_cache.end())
+        it = p->tc_cache.emplace(key, tc_gemm_create_pfold(reinterpret_cast<const bf16*>(in), ld_in, g.w16_pfold, g.Cin, H, W, p->Bcap)).first;
+      return it->second;
+    }
+    return nullptr;
+  }
+
   // split-K factor for this conv at the current batch (1 = none); sizes the lane's partial buffer on first use
   int split_for(const std::string& wname, const T* in, int ld_in, int level, int Cout) {
     if constexpr (sizeof(T) == 2) {
@@ -590,7 +613,8 @@ template <typename T> struct Fwd {
     if constexpr (sizeof(T) == 2) {
       if (p->no_fuse || p->fuse_mode == 0 || p->tr) return false;
       GemmW& g = p->gemms[wname];
-      TcGemm* tc = get_tc(wname, g, in, ld_in, level);
+      TcGemm* pf = pfold_tc(wname, g, in, ld_in, level);
+      TcGemm* tc = pf ? pf : get_tc(wname, g, in, ld_in, level);
       if (p->fuse_mode < 0) return tc_gemm_fuse_apply_pays(tc, Bpad);
       return p->fuse_mode >= min_mode && tc_gemm_can_fuse_apply(tc, Bpad);
     }
@@ -606,7 +630,8 @@ template <typename T> struct Fwd {
     const int H = p->levelH(level), W = p->levelW(level);
     if constexpr (sizeof(T) == 2) {
       const bool fold = !fuse && !resid && ksplit <= 1 && (flags & ~EPI_STATS) == 0 && fold_ok(wname, g, in, ld_in, level, ld_out);
-      TcGemm* tc = fold ? get_tc_fold(wname, g, in, level) : get_tc(wname, g, in, ld_in, level);
+      TcGemm* pf = (!resid && ksplit <= 1 && (flags & ~EPI_STATS) == 0 && (flags & EPI_STATS)) ? pfold_tc(wname, g, in, ld_in, level) : nullptr;
+      TcGemm* tc = pf ? pf : (fold ? get_tc_fold(wname, g, in, level) : get_tc(wname, g, in, ld_in, level));
       if (fold) ld_out *= 2;
       // algorithmic work: taps that fall inside the image only, real batch rows only
       const double flops = g.taps == 9 ? 2.0 * g.Cin * g.Cout * (3.0 * H - 2) * (3.0 * W - 2) * c.B
@@ -616,6 +641,7 @@ template <typename T> struct Fwd {
       timed(p, c.s, g.taps == 9 ? PC_CONV3 : PC_GEMM1, flops, bytes, [&] {
         P = tc_gemm_launch(tc, reinterpret_cast<bf16*>(out), ld_out, stats(), (flags & EPI_BIAS) ? g.bias : nullptr,
                            reinterpret_cast<const bf16*>(resid), ld_res, flags, Bpad, c.s, vt, vt_lk, fuse, ksplit, partial);
+        REQUIRE(P >= 0, "%s: %s", wname.c_str(), tc_last_error());
       });
       REQUIRE(fuse || !(flags & EPI_STATS) || P <= SPDM_MAX_PARTIALS, "%s: too many GroupNorm partials (%d)", wname.c_str(), P);
       curP = P;
@@ -642,7 +668,7 @@ template <typename T> struct Fwd {
     a.stats = stats(); a.P = curP; a.gamma = n.g; a.beta = n.b;
     a.temb = nullptr; a.temb_mode = TEMB_NONE; a.film = nullptr;
     if (st) {
-      a.temb = c.temb; a.temb_mode = c.temb_mode; a.temb_off = st->temb_off; a.step_ptr = c.step_ptr;
+      a.temb = c.temb; a.temb_mode = c.temb_mode; a.temb_off = st->temb_off; a.step_ptr = c.step_ptr; a.step_off = c.step_off;
       if (c.film) { a.film = c.film; a.film_off = st->film_off; }
     }
     a.HW = p->levelH(level) * p->levelW(level); a.C = C; a.act = act; a.eps = 1e-5f;
@@ -702,6 +728,60 @@ template <typename T> struct Fwd {
       tap(name + ".second", raw, Cout, Cout, level);
       apply(name + ".norm", raw, Cout, Cout, level, out, ld_out, ACT_NONE, st);
     }
+  }
+
+  // A run of DoubleConvolutions of one deep level as ONE launch (conv_chain_kernel): `dcs` = {name, Cin, Cout, stage-or-null, out} in
+  // order; the first conv reads `in` (ld_in), the map between the two convs of a DoubleConvolution lives in hbuf, every
+  // DoubleConvolution writes its own `out`.  pre_kind 1 / 2: the MaxPool2d(2) / bilinear upsample that produces `in` (channels
+  // [0, pre_C)) from pre_src.  Returns false when the run is not a small-batch cluster case: the caller then issues the layers
+  // one by one.
+  struct ChainDC { std::string name; int Cin, Cout; const StageInfo* st; T* out; int ld_out; };
+  bool chain(const std::string& key0, const std::vector<ChainDC>& dcs, const T* in, int ld_in, int level, int pre_kind, const T* pre_src,
+             int pre_ld_src, int pre_C) {
+    if constexpr (sizeof(T) == 2) {
+      if (p->no_splitk || p->tr || p->tap_out || !p->skip.empty()) return false;
+      char key[256];
+      snprintf(key, sizeof key, "%s|%d|%d|%p|%d|%p|%p", key0.c_str(), c.b0, Bpad, (const void*)c.temb, c.temb_mode, (const void*)c.film,
+               (const void*)c.step_ptr);
+      auto it = p->chain_cache.find(key);
+      const int H = p->levelH(level), W = p->levelW(level);
+      double flops = 0.0, bytes = 0.0;
+      if (it == p->chain_cache.end()) {
+        std::vector<TcChainLayerDesc> descs;
+        T* h = act(p->hbuf[level], level);
+        const T* cur = in;
+        int cur_ld = ld_in;
+        for (const ChainDC& d : dcs) {
+          GemmW& g1 = p->gemms[d.name + ".first"];
+          GemmW& g2 = p->gemms[d.name + ".second"];
+          TcChainLayerDesc a{}, b{};
+          a.g = get_tc(d.name + ".first", g1, cur, cur_ld, level);
+          a.out = reinterpret_cast<bf16*>(h); a.ld_out = d.Cout;
+          curP = 1;
+          a.ap = make_apply(d.name + ".norm", d.Cout, level, ACT_GELU, nullptr);
+          b.g = get_tc(d.name + ".second", g2, h, d.Cout, level);
+          b.out = reinterpret_cast<bf16*>(d.out); b.ld_out = d.ld_out;
+          b.ap = make_apply(d.name + ".norm", d.Cout, level, ACT_NONE, d.st);
+          descs.push_back(a);
+          descs.push_back(b);
+          cur = d.out; cur_ld = d.ld_out;
+        }
+        TcChain* ch = tc_chain_create(descs.data(), (int)descs.size(), Bpad, pre_kind, reinterpret_cast<const bf16*>(pre_src), pre_ld_src,
+                                      reinterpret_cast<bf16*>(const_cast<T*>(in)), ld_in, pre_C);
+        it = p->chain_cache.emplace(key, ch).first;
+      }
+      if (!it->second) return false;
+      for (const ChainDC& d : dcs) {
+        flops += 2.0 * (d.Cin + d.Cout) * d.Cout * (3.0 * H - 2) * (3.0 * W - 2) * c.B;
+        bytes += ((double)c.B * H * W * (d.Cin + 3.0 * d.Cout) + 9.0 * (d.Cin + d.Cout) * d.Cout) * 2.0;
+      }
+      timed(p, c.s, PC_CONV3_GN, flops, bytes, [&] {
+        const int rc = tc_chain_launch(it->second, c.s, c.step_off);
+        REQUIRE(rc == 0, "%s: %s", key0.c_str(), tc_last_error());
+      });
+      return true;
+    }
+    return false;
   }
 
   // SelfAttention (models/Unet_FiLmLayer.py:44-82)
@@ -827,6 +907,16 @@ template <typename T> struct Fwd {
       const StageInfo& st = kStages[d.stage];
       const int l = d.level;
       T* a = act(p->abuf[l], l); T* b = act(p->bbuf[l], l);
+      {  // deep levels at small batch: pool + the four convs of the stage in one launch
+        T* last = p->attention ? a : d.dest;
+        const int ld_last = p->attention ? st.cout : d.ld_dest;
+        if (l >= 2 && chain(st.name, {{std::string(st.name) + ".doubleConv1", st.cin, st.cin, nullptr, b, st.cin},
+                                       {std::string(st.name) + ".doubleConv2", st.cin, st.cout, &st, last, ld_last}},
+                            a, st.cin, l, 1, d.in, d.ld_in, st.cin)) {
+          if (p->attention) self_attention(d.sa, a, st.cout, st.cout, l, d.dest, d.ld_dest);
+          continue;
+        }
+      }
       timed(p, c.s, PC_RESAMPLE, 0, 5.0 * c.B * p->levelH(l) * p->levelW(l) * st.cin * sizeof(T),
             [&] { launch_pool<T>(d.in, d.ld_in, a, st.cin, c.B, p->levelH(l), p->levelW(l), st.cin, c.s); });
       double_conv(std::string(st.name) + ".doubleConv1", a, st.cin, st.cin, l, b, st.cin, nullptr);
@@ -843,12 +933,15 @@ template <typename T> struct Fwd {
     }
     // ---- bottleneck ----
     T* a3 = act(p->abuf[3], 3); T* b3 = act(p->bbuf[3], 3);
+    if (!chain("bot", {{"bot1", 256, 512, nullptr, a3, 512}, {"bot2", 512, 512, nullptr, b3, 512}, {"bot3", 512, 256, nullptr, a3, 256}}, b3, 256, 3, 0,
+               nullptr, 0, 0)) {
     double_conv("bot1", b3, 256, 512, 3, a3, 512, nullptr);
     tap("bot1", a3, 512, 512, 3);
     double_conv("bot2", a3, 512, 512, 3, b3, 512, nullptr);
     tap("bot2", b3, 512, 512, 3);
     double_conv("bot3", b3, 512, 256, 3, a3, 256, nullptr);
     tap("bot3", a3, 256, 256, 3);
+    }
     tap("x5", a3, 256, 256, 3);
 
     // ---- up path ----
@@ -859,6 +952,15 @@ template <typename T> struct Fwd {
       const StageInfo& st = kStages[u.stage];
       const int l = u.level;
       T* a = act(p->abuf[l], l); T* b = act(p->bbuf[l], l);
+      {  // deep level at small batch: upsample (+ concat) + the four convs of the stage in one launch
+        T* last = p->attention ? a : b;
+        if (l >= 2 && chain(st.name, {{std::string(st.name) + ".doubleConv1", st.cin, st.cin, nullptr, a, st.cin},
+                                       {std::string(st.name) + ".doubleConv2", st.cin, st.cout, &st, last, st.cout}},
+                            u.catbuf, st.cin, l, 2, u.low, u.c_low, u.c_low)) {
+          if (p->attention) self_attention(u.sa, a, st.cout, st.cout, l, b, st.cout);
+          continue;
+        }
+      }
       timed(p, c.s, PC_RESAMPLE, 0, 1.25 * c.B * p->levelH(l) * p->levelW(l) * u.c_low * sizeof(T), [&] {
         launch_upsample<T>(u.low, u.c_low, u.catbuf, st.cin, c.B, p->levelH(l + 1), p->levelW(l + 1), u.c_low, c.s);
       });
@@ -916,15 +1018,15 @@ void compute_film(spdm_plan* p, int B, cudaStream_t s) {
   p->have_cond = true;
 }
 
-void one_lane(spdm_plan* p, int b0, int Bsub, int B, bool use_film, cudaStream_t s) {
+void one_lane(spdm_plan* p, int b0, int Bsub, int B, bool use_film, cudaStream_t s, int step_off) {
   const size_t n = p->n_elems();
   FwdCtx c{};
   c.x = p->xt + (size_t)b0 * n; c.out = p->eps + (size_t)b0 * n; c.temb = p->temb_table; c.temb_mode = TEMB_STEP;
-  c.step_ptr = &p->dyn->step;
+  c.step_ptr = &p->dyn->step; c.step_off = step_off;
   c.film = use_film ? p->film + (size_t)b0 * SPDM_FILM_WIDTH : nullptr; c.B = Bsub; c.b0 = b0; c.s = s;
   StepArgs a{};
   a.x = p->xt; a.eps = p->eps; a.x_out = p->xt; a.coef = p->coef; a.dyn = p->dyn; a.n = p->n_elems();
-  a.inpaint_elems = p->cfg.inpaint_rows * p->cfg.dim; a.B = Bsub; a.b0 = b0; a.B_total = B;
+  a.inpaint_elems = p->cfg.inpaint_rows * p->cfg.dim; a.B = Bsub; a.b0 = b0; a.B_total = B; a.step_off = step_off;
   c.fuse_step = &a;
   run_forward(p, c);
 }
@@ -933,12 +1035,14 @@ void one_lane(spdm_plan* p, int b0, int Bsub, int B, bool use_film, cudaStream_t
 // whole U-Net concurrently on separate streams (forked from and joined back into `s`, also under stream capture, where
 // they become parallel graph branches): the many small-grid kernels of the deep levels then overlap instead of
 // leaving most SMs idle.
-void one_step(spdm_plan* p, int B, bool use_film, cudaStream_t s) {
+// `step_off` / `advance`: inside a captured graph of several steps every launch carries its step's offset from the device counter,
+// which then advances once per graph launch instead of once per step (one launch fewer per denoising step).
+void one_step(spdm_plan* p, int B, bool use_film, cudaStream_t s, int step_off = 0, int advance = 1) {
   int split = p->split;
   int chunk = (B + split - 1) / split;
   chunk = ((chunk + p->bm - 1) / p->bm) * p->bm;
   if (split <= 1 || chunk >= B) {
-    one_lane(p, 0, B, B, use_film, s);
+    one_lane(p, 0, B, B, use_film, s, step_off);
   } else {
     CUDA_OK(cudaEventRecord(p->ev_fork, s));
     int lane = 0;
@@ -946,14 +1050,14 @@ void one_step(spdm_plan* p, int B, bool use_film, cudaStream_t s) {
       const int Bsub = B - b0 < chunk ? B - b0 : chunk;
       cudaStream_t ls = lane == 0 ? s : p->lane_stream[lane - 1];
       if (lane > 0) CUDA_OK(cudaStreamWaitEvent(ls, p->ev_fork, 0));
-      one_lane(p, b0, Bsub, B, use_film, ls);
+      one_lane(p, b0, Bsub, B, use_film, ls, step_off);
       if (lane > 0) {
         CUDA_OK(cudaEventRecord(p->ev_lane[lane - 1], ls));
         CUDA_OK(cudaStreamWaitEvent(s, p->ev_lane[lane - 1], 0));
       }
     }
   }
-  launch_advance(&p->dyn->step, 1, s);
+  if (advance > 0) launch_advance(&p->dyn->step, advance, s);
 }
 
 }  // namespace
@@ -991,6 +1095,7 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
   p->cfg = *cfg;
   p->attention = cfg->variant == SPDM_VARIANT_ATTENTION;
   p->bf16_mode = cfg->precision == SPDM_PRECISION_BF16;
+  if (const char* e = getenv("SPDM_NO_PFOLD")) p->no_pfold = atoi(e) != 0;
   // pad_to(x, 8): models/Unet_FiLmLayer.py:15-34
   auto up8 = [](int v) { return v % 8 ? v + 8 - v % 8 : v; };
   p->H0 = up8(cfg->rows); p->W0 = up8(cfg->dim);
@@ -1070,6 +1175,7 @@ extern "C" int spdm_plan_destroy(spdm_plan* p) {
     if (kv.second.single) cudaGraphExecDestroy(kv.second.single);
   }
   for (auto& kv : p->tc_cache) tc_gemm_destroy(kv.second);
+  for (auto& kv : p->chain_cache) tc_chain_destroy(kv.second);
   if (p->enc_tc) tc_gemm_destroy(p->enc_tc);
   if (p->enc_tc2) tc_gemm_destroy(p->enc_tc2);
   if (p->enc_tc3) tc_gemm_destroy(p->enc_tc3);
@@ -1361,7 +1467,7 @@ extern "C" int spdm_sample(spdm_plan* p, const float* x_T, const float* noise, c
         const long long c0 = total_launches();
         CUDA_OK(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
         try {
-          for (int k = 0; k < steps; ++k) one_step(p, B, use_film, s);
+          for (int k = 0; k < steps; ++k) one_step(p, B, use_film, s, k, k + 1 == steps ? steps : 0);
         } catch (...) {
           cudaStreamEndCapture(s, &graph);
           throw;
@@ -1444,9 +1550,13 @@ extern "C" int spdm_profile_step(spdm_plan* p, int32_t B, int32_t reps, double* 
     try { one_step(p, B, use_film, s); } catch (...) { p->prof_on = false; throw; }
     p->prof_on = false;
     CUDA_OK(cudaStreamSynchronize(s));
+    int rec_i = 0;
     for (auto& rec : p->prof) {
       float ms = 0.f;
       CUDA_OK(cudaEventElapsedTime(&ms, rec.e0, rec.e1));
+      if (r == reps - 1 && getenv("SPDM_PROF_DUMP"))   // per-launch list of the last repetition (diagnostics)
+        fprintf(stderr, "spdm prof %3d class %d  %9.2f us  %8.1f GFLOP  %8.1f MB\n", rec_i, rec.cat, ms * 1e3, rec.flops / 1e9, rec.bytes / 1e6);
+      ++rec_i;
       out[rec.cat * 4 + 0] += ms / reps;
       out[rec.cat * 4 + 1] += 1.0 / reps;
       out[rec.cat * 4 + 2] += rec.flops / reps;
