@@ -63,7 +63,8 @@ def parse():
                          "kernels are throughput- rather than launch-bound) and report it as `large_batch`; 0 disables")
     ap.add_argument("--ddpm-batch", type=int, default=512, help="per-GPU batch of the DDPM-1000 leg (BASELINE configs[3]); 0 disables")
     ap.add_argument("--ddpm-steps", type=int, default=1000)
-    ap.add_argument("--pipeline-depth", type=int, default=2,
+    ap.add_argument("--e2e-depth", type=int, default=3, help="lanes of the SamplingPipeline the e2e measurement runs through")
+    ap.add_argument("--pipeline-depth", type=int, default=3,
                     help="extra measurement: independent batches kept in flight on separate streams/plans (reported separately)")
     return ap.parse_args()
 
@@ -700,7 +701,7 @@ def main():
     # the timed region.
     host_u8 = dict(host)
     host_u8["image"] = (host["image"] * 255.0).round().clamp_(0, 255).to(torch.uint8).permute(0, 1, 3, 4, 2).contiguous().pin_memory()
-    pipe = spdm.SamplingPipeline(model, depth=2, batch_max=B)
+    pipe = spdm.SamplingPipeline(model, depth=args.e2e_depth, batch_max=B)
     pinned_out = [torch.empty((B, 1, rows, args.dim)).pin_memory() for _ in range(2)]
 
     def run_e2e(n):
@@ -714,7 +715,7 @@ def main():
             pinned_out[j % 2].copy_(out)           # D2H of this step's trajectories (blocking: the result is on the host)
         for i in range(n):
             tickets.append((i, pipe.submit(host_u8, x_T=x_T, seed=1000 + i)))   # H2D of this step's inputs (async, pinned)
-            if len(tickets) > 1:
+            if len(tickets) >= args.e2e_depth:
                 drain_one()
         while tickets:
             drain_one()
@@ -778,7 +779,7 @@ def main():
             "dtype": args.precision, "data": "synthetic", "config": config_dict(args, total_B),
             "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": round(ms_e2e / args.steps, 3), "host_wall_ms_per_step": round(t_wall / args.steps, 3),
-                    "api": "SamplingPipeline(Diffusion_DDIM, depth=2).submit(host batch) / .result(): uint8 HWC frames from pinned host "
+                    "api": "SamplingPipeline(Diffusion_DDIM, depth=%d).submit(host batch) / .result(): uint8 HWC frames from pinned host " % args.e2e_depth +
                            "memory, trajectories read back to pinned host memory, per step",
                     "sync_f32": {"value": round(total_B * args.steps / (ms_e2e_sync / 1000.0), 2), "unit": UNIT,
                                  "h2d_bytes_per_step": h2d_f32, "d2h_bytes_per_step": d2h, "ms_per_step": round(ms_e2e_sync / args.steps, 3),

@@ -87,6 +87,36 @@ def make_unet_weights(attention=True, cond_dim=1350, seed=0):
     return _draw(_unet_shapes(attention, cond_dim), seed)
 
 
+def _simple_unet_shapes(cond_dim=1350, time_dim=256):
+    s = {}
+
+    def dc(p, ci, co):
+        s[p + ".first.weight"] = (co, ci, 3, 3)
+        s[p + ".second.weight"] = (co, co, 3, 3)
+        s[p + ".norm.weight"] = (co,)
+        s[p + ".norm.bias"] = (co,)
+
+    dc("input_conv", 1, 16)
+    for name, ci, co in (("down1", 16, 32), ("down2", 64, 128), ("down3", 160, 256), ("up1", 448, 128), ("up2", 224, 64), ("up3", 112, 32)):
+        dc(name + ".doubleConv1", ci, ci)
+        dc(name + ".doubleConv2", ci, co)
+        s[name + ".emb_layer.1.weight"] = (co, time_dim)
+        s[name + ".emb_layer.1.bias"] = (co,)
+        s[name + ".cond_emb_layer.1.weight"] = (32, cond_dim)
+        s[name + ".cond_emb_layer.1.bias"] = (32,)
+    s["outc.weight"] = (1, 64, 1, 1)
+    s["outc.bias"] = (1,)
+    return s
+
+
+def make_simple_unet_weights(cond_dim=1350, seed=0, noise_steps=1000):
+    """State dict of the legacy simple U-Net (models/simple_Unet.py:260-339) incl. its PositionalEncoding buffer."""
+    from .simple_unet_ref import pos_table
+    sd = _draw(_simple_unet_shapes(cond_dim), seed)
+    sd["pos_encoding.pos_encoding"] = pos_table(noise_steps + 1)
+    return sd
+
+
 def make_encoder_weights(seed=1):
     shapes = {"0.weight": (16, 3, 2, 2), "0.bias": (16,), "2.weight": (32, 16, 2, 2), "2.bias": (32,),
               "4.weight": (64, 32, 2, 2), "4.bias": (64,), "7.weight": (128, 9216), "7.bias": (128,)}

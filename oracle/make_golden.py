@@ -229,6 +229,33 @@ def golden_dataset(seed=0):
     np.savez_compressed(os.path.join(OUT, "dataset.npz"), **out)
 
 
+def golden_simple_unet(seed=7):
+    """The reference's legacy UNet (models/simple_Unet.py:260-339) in eval mode on the fixture weights: output + three skip taps."""
+    from models.simple_Unet import UNet
+    sd = fixtures.make_simple_unet_weights(seed=seed)
+    net = UNet(in_channels=1, out_channels=1, noise_steps=1000, global_cond_dim=1350, time_dim=256).eval()
+    ref_table = net.pos_encoding.pos_encoding.clone()
+    net.load_state_dict(sd, strict=True)     # pins key names, shapes and the buffer
+    assert torch.equal(ref_table, sd["pos_encoding.pos_encoding"]), "PositionalEncoding table restatement differs from the reference buffer"
+    g = torch.Generator().manual_seed(seed + 100)
+    B = 3
+    x = torch.rand((B, 1, 31, 5), generator=g)
+    y = torch.randn((B, 1, 10, 135), generator=g)
+    t = torch.tensor([999, 500, 3], dtype=torch.long)
+    taps = {}
+    hooks = [getattr(net, m).register_forward_hook(lambda mod, i, o, n=m: taps.__setitem__(n, o.detach().clone())) for m in ("input_conv", "down3", "up1", "up3")]
+    with torch.no_grad():
+        out = net(x, t, y)
+        out_t1 = net(x, torch.tensor([17]), y)    # a single timestep broadcast over the batch (models/diffusion_ddpm.py:209)
+    for h in hooks:
+        h.remove()
+    d = {"x": x, "y": y, "t": t, "out": out, "out_t1": out_t1, "seed": seed}
+    for k, v in taps.items():
+        d["tap_" + k] = _tap_summary(v)
+    np.savez_compressed(os.path.join(OUT, "simple_unet.npz"), **_np(d))
+    print("simple_unet out", tuple(out.shape), float(out.abs().mean()))
+
+
 def golden_beta_schedules():
     """utils/schedulers.py:6-40 of the reference, imported as is (the functions are unbound "methods" reading self.device)."""
     import importlib.util
@@ -263,6 +290,7 @@ def main():
     golden_train_grads()
     golden_dataset()
     golden_beta_schedules()
+    golden_simple_unet()
 
 
 if __name__ == "__main__":

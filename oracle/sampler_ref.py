@@ -26,7 +26,7 @@ def add_constraints(x_t, x_inpaint, inpaint_horizon):
 
 @torch.no_grad()
 def sample_ref(sd, scheduler, n_steps, x_T, obs_cond, inpaint, inpaint_horizon, attention=True, noise=None,
-               history=False, max_steps=None):
+               history=False, max_steps=None, forward=None):
     """Loop of models/diffusion_ddpm.py:268-276 / diffusion_ddim.py:67-73.
 
     obs_cond (B,1,T,cond_dim); inpaint (B,1,ih,dim); noise (K,B,1,rows,dim) injected per step index
@@ -37,7 +37,10 @@ def sample_ref(sd, scheduler, n_steps, x_T, obs_cond, inpaint, inpaint_horizon, 
     for i, t in enumerate(scheduler.timesteps):
         if max_steps is not None and i >= max_steps:
             break
-        est = unet_ref.unet_forward(sd, x_t, torch.tensor([int(t)]), obs_cond, attention=attention)
+        if forward is not None:   # another noise estimator (oracle/simple_unet_ref.unet_forward)
+            est = forward(sd, x_t, torch.tensor([int(t)]), obs_cond)
+        else:
+            est = unet_ref.unet_forward(sd, x_t, torch.tensor([int(t)]), obs_cond, attention=attention)
         if isinstance(scheduler, RefDDPMScheduler):
             x_t = scheduler.step(est, t, x_t, noise=None if noise is None else noise[i]).prev_sample
         else:

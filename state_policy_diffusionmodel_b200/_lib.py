@@ -18,7 +18,7 @@ class SpdmConfig(_c.Structure):
         "time_dim", "device", "graph_steps", "flags")]
 
 
-VARIANT_ATTENTION, VARIANT_NO_ATTENTION = 0, 1
+VARIANT_ATTENTION, VARIANT_NO_ATTENTION, VARIANT_SIMPLE_UNET = 0, 1, 2
 PRECISION_FP32, PRECISION_BF16 = 0, 1
 SCHED_DDPM, SCHED_DDIM = 0, 1
 FLAG_SCHEDULER_ONLY = 1

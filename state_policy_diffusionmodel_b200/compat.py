@@ -68,11 +68,12 @@ def install_reference_aliases(override_diffusers=True):
 
     from . import diffusion, schedulers, unet
     models = _package("models")
-    common = dict(torch=torch, nn=nn, np=np, UNet_Film=unet.UNet_Film, UNet_Film_noAttention=unet.UNet_Film_noAttention,
+    common = dict(torch=torch, nn=nn, np=np, UNet=unet.UNet, UNet_Film=unet.UNet_Film, UNet_Film_noAttention=unet.UNet_Film_noAttention,
                   DoubleConvolution=unet.DoubleConvolution, DownSample=unet.DownSample, UpSample=unet.UpSample,
                   SelfAttention=unet.SelfAttention)
     _leaf(models, "Unet_FiLmLayer", **common)
     _leaf(models, "Unet_FiLmLayer_noAttention", **common)
+    _leaf(models, "simple_Unet", UNet=unet.UNet, torch=torch, nn=nn)
     # models/diffusion_ddpm.py:6-19 also star-exports pl / plt / datetime (scripts only rely on torch, np, nn and the classes)
     extra = dict(pl=diffusion.pl, datetime=diffusion.datetime)
     _leaf(models, "diffusion_ddpm", Diffusion_DDPM=diffusion.Diffusion_DDPM, DDPMScheduler=schedulers.DDPMScheduler, **extra, **common)

@@ -183,6 +183,15 @@ void launch_pack_conv_pfold_bf16(const float* oihw, bf16* out, int Cin, cudaStre
 void launch_pack_linear_f32(const float* nk, float* out, int N, int K, int ld_out, int col_off, cudaStream_t s);  // -> [K][ld_out] at col_off
 void launch_cast_bf16(const float* in, bf16* out, long long n, cudaStream_t s);
 void launch_pack_enc_linear(const float* w, float* out, cudaStream_t s);  // (128, 64*12*12 chw) -> [9216 hwc][128]
+// legacy simple U-Net (models/simple_Unet.py), fp32 (simple_kernels.cu)
+void launch_su_conv_in(const float* x, const float* w, float* out, int B, int H, int W, int rows, int dim, int lh, int lw, cudaStream_t s);
+void launch_su_apply(const float* raw, int ld_in, float* out, int ld_out, const float* stats, const float* gamma, const float* beta,
+                     const float* resid, int ld_res, const float* temb, int temb_stride, int temb_mode, const int* step_ptr, int step_off,
+                     int B, int HW, int C, cudaStream_t s);
+void launch_su_temb(const long long* t_dev, int n_t, const float* table, int max_len, const float* w_cat, const float* b_cat, float* out,
+                    int time_dim, int width, cudaStream_t s);
+void launch_su_silu(const float* in, float* out, long long n, cudaStream_t s);
+void launch_su_bcast(const float* emb, int emb_stride, float* out, int ld_out, int B, int HW, cudaStream_t s);
 long long kernels_launch_count();
 void kernels_count_launch();  // one more launch (kernels that live in other translation units)
 

@@ -83,6 +83,8 @@ static const StageInfo kStages[6] = {
 struct spdm_plan {
   spdm_config cfg;
   bool attention = true, bf16_mode = false, sched_only = false;
+  bool simple = false;                 // SPDM_VARIANT_SIMPLE_UNET: models/simple_Unet.py UNet on the fp32 path (simple_unet.inl)
+  float* su_table = nullptr; int su_table_rows = 0;   // its PositionalEncoding buffer [max_len][time_dim]
   int H0 = 0, W0 = 0, lh = 0, lw = 0;  // padded geometry (pad_to 8) and low-side pads
   int Bcap = 0, bm = 1;
   int G = 0;  // global_cond_dim
@@ -990,7 +992,12 @@ template <typename T> struct Fwd {
   }
 };
 
+}  // namespace
+#include "simple_unet.inl"
+namespace {
+
 void run_forward(spdm_plan* p, const FwdCtx& c) {
+  if (p->simple) { SimpleFwd f(p, c); f.run(); return; }
   if (p->bf16_mode) { Fwd<bf16> f(p, c); f.run(); }
   else { Fwd<float> f(p, c); f.run(); }
 }
@@ -1005,11 +1012,18 @@ void check_ready(spdm_plan* p, bool training_step = false) {
 void ensure_temb_table(spdm_plan* p, cudaStream_t s) {
   REQUIRE(p->K > 0, "no schedule set (spdm_plan_set_schedule)");
   if (!p->temb_table_dirty) return;
+  if (p->simple) {
+    REQUIRE(p->su_table != nullptr, "weight pos_encoding.pos_encoding missing");
+    launch_su_temb(p->timesteps, p->K, p->su_table, p->su_table_rows, p->temb_w, p->temb_b, p->temb_table, p->cfg.time_dim, SU_TEMB_WIDTH, s);
+    p->temb_table_dirty = false;
+    return;
+  }
   launch_temb(p->timesteps, p->K, p->inv_freq, p->temb_w, p->temb_b, p->temb_table, p->cfg.time_dim, s);
   p->temb_table_dirty = false;
 }
 
 void compute_film(spdm_plan* p, int B, cudaStream_t s) {
+  if (p->simple) { compute_cond_emb_simple(p, B, s); return; }
   launch_mish(p->cond, p->cond_mish, (long long)B * p->G, s);
   GemmSimtArgs a{};
   a.in = p->cond_mish; a.w = p->film_w; a.bias = p->film_b; a.out = p->film; a.M = B; a.Cin = p->G; a.Cout = SPDM_FILM_WIDTH;
@@ -1093,8 +1107,16 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
   REQUIRE(prop.major == 10, "libspdm is built for sm_100a only (device is sm_%d%d)", prop.major, prop.minor);
   spdm_plan* p = new spdm_plan();
   p->cfg = *cfg;
+  REQUIRE(cfg->variant == SPDM_VARIANT_ATTENTION || cfg->variant == SPDM_VARIANT_NO_ATTENTION || cfg->variant == SPDM_VARIANT_SIMPLE_UNET,
+          "bad variant");
   p->attention = cfg->variant == SPDM_VARIANT_ATTENTION;
+  p->simple = cfg->variant == SPDM_VARIANT_SIMPLE_UNET;
   p->bf16_mode = cfg->precision == SPDM_PRECISION_BF16;
+  if (p->simple && !(cfg->flags & SPDM_FLAG_SCHEDULER_ONLY)) {
+    // its channel counts (16, 160, 288, 448, 224, 96, 112) are not multiples of the 64-wide tcgen05 operand tiles
+    if (p->bf16_mode) { delete p; throw SpdmError{"the simple U-Net (models/simple_Unet.py) runs on the fp32 path only: create the plan with SPDM_PRECISION_FP32"}; }
+    if (cfg->obs_horizon * cfg->cond_dim <= 0) { delete p; throw SpdmError{"the simple U-Net needs conditioning (cond_dim > 0): its stages concatenate a 32-channel cond_emb"}; }
+  }
   if (const char* e = getenv("SPDM_NO_PFOLD")) p->no_pfold = atoi(e) != 0;
   // pad_to(x, 8): models/Unet_FiLmLayer.py:15-34
   auto up8 = [](int v) { return v % 8 ? v + 8 - v % 8 : v; };
@@ -1114,7 +1136,7 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
     p->Bcap = ((cfg->batch_max + p->bm - 1) / p->bm) * p->bm;
     p->sched_only = (cfg->flags & SPDM_FLAG_SCHEDULER_ONLY) != 0;  // scheduler-only plan: spdm_step / spdm_add_noise, no U-Net
     if (p->sched_only) { *out = p; return 0; }
-    register_weights(p);
+    if (p->simple) register_weights_simple(p); else register_weights(p);
     if (p->bf16_mode) alloc_workspace<bf16>(p); else alloc_workspace<float>(p);
     p->stats = p->alloc<float>((size_t)p->Bcap * SPDM_MAX_PARTIALS * 2);
     p->temb_call = p->alloc<float>((size_t)p->Bcap * SPDM_TEMB_WIDTH);
@@ -1378,7 +1400,13 @@ static int unet_forward_impl(spdm_plan* p, const float* x, const int64_t* t, int
     REQUIRE(p->have_cond, "no cached conditioning (call spdm_set_cond / spdm_encode_cond)");
     film = p->film;
   }
-  launch_temb(reinterpret_cast<const long long*>(t), t_count, p->inv_freq, p->temb_w, p->temb_b, p->temb_call, p->cfg.time_dim, s);
+  if (p->simple) {
+    REQUIRE(p->su_table != nullptr, "weight pos_encoding.pos_encoding missing");
+    launch_su_temb(reinterpret_cast<const long long*>(t), t_count, p->su_table, p->su_table_rows, p->temb_w, p->temb_b, p->temb_call,
+                   p->cfg.time_dim, SU_TEMB_WIDTH, s);
+  } else {
+    launch_temb(reinterpret_cast<const long long*>(t), t_count, p->inv_freq, p->temb_w, p->temb_b, p->temb_call, p->cfg.time_dim, s);
+  }
   FwdCtx c{};
   c.x = x; c.out = out; c.temb = p->temb_call; c.temb_mode = t_count == 1 ? TEMB_ROW0 : TEMB_PER_SAMPLE; c.step_ptr = nullptr;
   c.film = film; c.B = B; c.s = s;

@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from .schedulers import DDIMScheduler, DDPMScheduler
-from .unet import UNet_Film, UNet_Film_noAttention
+from .unet import UNet, UNet_Film, UNet_Film_noAttention
 
 try:  # Lightning is optional: the reference subclasses pl.LightningModule, which is absent on the B200 image
     import pytorch_lightning as pl
@@ -121,9 +121,8 @@ class Diffusion_DDPM(_Base):
             self.model = UNet_Film
         elif model == 'UNet_FilmnoAttention':
             self.model = UNet_Film_noAttention
-        else:
-            raise NotImplementedError("model=%r: the legacy simple U-Net (models/simple_Unet.py) is outside the B200 hot path; "
-                                      "use 'UNet_Film' or 'UNet_FilmnoAttention'" % (model,))
+        else:  # ddpm:60-62: anything else is the legacy simple U-Net (fp32 path, inference only here)
+            self.model = UNet
         self.noise_scheduler = DDPMScheduler(num_train_timesteps=self.noise_steps, beta_schedule='linear', clip_sample=False,
                                              prediction_type='epsilon')
         self.lr = learning_rate
@@ -140,7 +139,7 @@ class Diffusion_DDPM(_Base):
             self.vision_encoder.load_state_dict(enc, strict=True)
         self.vision_encoder.eval()
         # B200 execution options
-        self.precision = "bf16"
+        self.precision = "fp32" if self.model is UNet else "bf16"
         self.graph_steps = 10   # denoising steps per captured CUDA graph (the K % graph_steps remainder runs as 1-step graphs)
         self.batch_max = 0
         self._enc_tag = None
@@ -150,6 +149,8 @@ class Diffusion_DDPM(_Base):
     # ------------------------------------------------------------------------------------------
     def configure(self, precision=None, graph_steps=None, batch_max=None, split=None):
         if precision is not None:
+            if self.model is UNet and precision != "fp32":
+                raise ValueError("the simple U-Net (model='UNet') runs on the fp32 path only")
             self.precision = precision
         if graph_steps is not None:
             self.graph_steps = int(graph_steps)
@@ -255,6 +256,9 @@ class Diffusion_DDPM(_Base):
 
     def _training_plan(self, B):
         from .engine import DenoisePlan
+        if self.model is UNet:
+            raise NotImplementedError("spdm: the native training step covers model='UNet_Film' / 'UNet_FilmnoAttention'; the legacy simple "
+                                      "U-Net (model='UNet') is inference-only on the B200 path")
         plan = getattr(self, "_tplan", None)
         key = (self.precision, self.pred_horizon + self.inpaint_horizon, self.prediction_dim, self.obs_horizon, self.observation_dim,
                self.inpaint_horizon, str(self.device))
@@ -503,7 +507,7 @@ class SamplingPipeline:
             else:
                 plan = DenoisePlan(attention=ne._attention, precision=base.precision, batch_max=base.batch_max, rows=base.rows,
                                    dim=base.dim, obs_horizon=base.obs_horizon, cond_dim=base.cond_dim, inpaint_rows=base.inpaint_rows,
-                                   time_dim=ne.time_dim, device=base.device, graph_steps=base.cfg.graph_steps, split=ne.split)
+                                   time_dim=ne.time_dim, device=base.device, graph_steps=base.cfg.graph_steps, split=ne.split, simple=ne._simple)
                 plan.load_unet_state_dict(ne.state_dict())
                 plan.load_encoder_state_dict(model.vision_encoder.state_dict())
                 plan.set_schedule(sch.kind, sch.coef_table(), sch.timesteps)

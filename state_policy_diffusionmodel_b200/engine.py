@@ -39,7 +39,9 @@ def _grad_phase(name):
 
 class DenoisePlan:
     def __init__(self, attention=True, precision="bf16", batch_max=1, rows=31, dim=5, obs_horizon=10, cond_dim=135,
-                 inpaint_rows=1, time_dim=256, device=None, graph_steps=1, scheduler_only=False, split=1):
+                 inpaint_rows=1, time_dim=256, device=None, graph_steps=1, scheduler_only=False, split=1, simple=False):
+        """`attention`: UNet_Film (True) or UNet_Film_noAttention (False); `simple=True`: the legacy `UNet` of
+        models/simple_Unet.py (the reference's model='UNet' default) -- fp32 path, inference only."""
         if not torch.cuda.is_available():
             raise RuntimeError("spdm: no CUDA device — the B200 denoising path has no CPU fallback")
         self.lib = _lib.load()
@@ -47,14 +49,14 @@ class DenoisePlan:
         if precision not in ("fp32", "bf16"):
             raise ValueError("precision must be 'fp32' or 'bf16'")
         cfg = _lib.SpdmConfig(
-            variant=_lib.VARIANT_ATTENTION if attention else _lib.VARIANT_NO_ATTENTION,
+            variant=_lib.VARIANT_SIMPLE_UNET if simple else (_lib.VARIANT_ATTENTION if attention else _lib.VARIANT_NO_ATTENTION),
             precision=_lib.PRECISION_BF16 if precision == "bf16" else _lib.PRECISION_FP32,
             batch_max=int(batch_max), rows=int(rows), dim=int(dim), obs_horizon=int(obs_horizon),
             cond_dim=int(cond_dim or 0), inpaint_rows=int(inpaint_rows), time_dim=int(time_dim),
             device=self.device.index or 0, graph_steps=int(graph_steps),
             flags=(_lib.FLAG_SCHEDULER_ONLY if scheduler_only else 0) | ((int(split) & 0xF) << 8))
         self.cfg = cfg
-        self.attention, self.precision = attention, precision
+        self.attention, self.precision, self.simple = attention and not simple, precision, bool(simple)
         self.batch_max, self.rows, self.dim = int(batch_max), int(rows), int(dim)
         self.obs_horizon, self.cond_dim, self.inpaint_rows = int(obs_horizon), int(cond_dim or 0), int(inpaint_rows)
         self.K = 0
@@ -90,6 +92,8 @@ class DenoisePlan:
             if prefix and not k.startswith(prefix):
                 continue
             self.load_weight(k[len(prefix):], v)
+        if self.simple:   # its positional encoding is a buffer of the state_dict (pos_encoding.pos_encoding), loaded above
+            return
         # exact torch value of the sinusoidal frequencies (models/Unet_FiLmLayer.py:267-270)
         td = self.cfg.time_dim
         inv_freq = 1.0 / (10000 ** (torch.arange(0, td, 2) / td))

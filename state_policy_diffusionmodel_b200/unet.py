@@ -59,6 +59,7 @@ class SelfAttention(nn.Module):
 
 class _UNetBase(nn.Module):
     _attention = True
+    _simple = False
 
     def __init__(self, in_channels, out_channels, noise_steps, time_dim=256, global_cond_dim=None):
         super().__init__()
@@ -110,13 +111,6 @@ class _UNetBase(nn.Module):
             self.batch_max = int(batch_max)
         return self
 
-    def pos_encoding(self, t, channels):
-        """models/Unet_FiLmLayer.py:266-274 (kept for API parity; the kernels compute it on the device)."""
-        inv_freq = 1.0 / (10000 ** (torch.arange(0, channels, 2, device=t.device) / channels))
-        a = torch.sin(t.repeat(1, channels // 2) * inv_freq)
-        b = torch.cos(t.repeat(1, channels // 2) * inv_freq)
-        return torch.cat([a, b], dim=-1)
-
     def _tag(self):
         return (self._weights_epoch,) + tuple((p.data_ptr(), p._version) for p in self.parameters())
 
@@ -152,7 +146,7 @@ class _UNetBase(nn.Module):
                 old.close()
             self._plan = DenoisePlan(attention=self._attention, precision=self.precision, batch_max=cap, rows=rows, dim=dim,
                                      obs_horizon=T, cond_dim=cd, inpaint_rows=inpaint_rows, time_dim=self.time_dim, device=dev,
-                                     graph_steps=graph_steps, split=self.split)
+                                     graph_steps=graph_steps, split=self.split, simple=self._simple)
             self._plan_key = key
             self._weights_tag = None
         tag = self._tag()
@@ -180,11 +174,113 @@ class _UNetBase(nn.Module):
         return out.to(x.dtype)
 
 
-class UNet_Film(_UNetBase):
+class _FilmPosEncoding:
+    def pos_encoding(self, t, channels):
+        """models/Unet_FiLmLayer.py:266-274 (kept for API parity; the kernels compute it on the device)."""
+        inv_freq = 1.0 / (10000 ** (torch.arange(0, channels, 2, device=t.device) / channels))
+        a = torch.sin(t.repeat(1, channels // 2) * inv_freq)
+        b = torch.cos(t.repeat(1, channels // 2) * inv_freq)
+        return torch.cat([a, b], dim=-1)
+
+
+class UNet_Film(_FilmPosEncoding, _UNetBase):
     """FiLM U-Net with six SelfAttention blocks (reference models/Unet_FiLmLayer.py:240)."""
     _attention = True
 
 
-class UNet_Film_noAttention(_UNetBase):
+class UNet_Film_noAttention(_FilmPosEncoding, _UNetBase):
     """FiLM U-Net without attention (reference models/Unet_FiLmLayer_noAttention.py:240)."""
     _attention = False
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the legacy simple U-Net: models/simple_Unet.py (the reference's `model='UNet'` default, models/diffusion_ddpm.py:60-62)
+# ---------------------------------------------------------------------------------------------------------------------
+class _SimpleDoubleConvolution(DoubleConvolution):
+    """Parameters of models/simple_Unet.py:82-125 (same two bias-free 3x3 convs + one GroupNorm; `residual` changes the forward only)."""
+
+    def __init__(self, in_channels, out_channels, residual=False):
+        super().__init__(in_channels, out_channels)
+        self.residual = residual
+
+
+class _SimpleStage(nn.Module):
+    """Parameters of the simple DownSample / UpSample (models/simple_Unet.py:128-211)."""
+
+    def __init__(self, in_channels, out_channels, embeddedTime_dim=256, cond_dim=None):
+        super().__init__()
+        self.cond_dim = cond_dim
+        self.doubleConv1 = _SimpleDoubleConvolution(in_channels, in_channels, residual=True)
+        self.doubleConv2 = _SimpleDoubleConvolution(in_channels, out_channels)
+        self.emb_layer = nn.Sequential(nn.SiLU(), nn.Linear(embeddedTime_dim, out_channels))
+        if cond_dim is not None:
+            self.cond_emb_layer = nn.Sequential(nn.SiLU(), nn.Linear(in_features=cond_dim, out_features=32))
+
+
+class PositionalEncoding(nn.Module):
+    """models/simple_Unet.py:214-242: the (max_len, embedding_dim) sin / cos table is a registered buffer (part of the state_dict);
+    dropout applies in training mode only -- the B200 path implements the eval-mode lookup."""
+
+    def __init__(self, embedding_dim, dropout=0.1, max_len=1000, apply_dropout=True):
+        super().__init__()
+        import math
+        self.dropout = nn.Dropout(p=dropout)
+        self.apply_dropout = apply_dropout
+        pos_encoding = torch.zeros(max_len, embedding_dim)
+        position = torch.arange(start=0, end=max_len).unsqueeze(1)
+        div_term = torch.exp(-math.log(10000.0) * torch.arange(0, embedding_dim, 2).float() / embedding_dim)
+        pos_encoding[:, 0::2] = torch.sin(position * div_term)
+        pos_encoding[:, 1::2] = torch.cos(position * div_term)
+        self.register_buffer(name='pos_encoding', tensor=pos_encoding)
+
+
+class UNet(_UNetBase):
+    """Legacy simple U-Net (reference models/simple_Unet.py:260-339): 16/32/128/256-channel DoubleConvolutions with a trailing GELU
+    (residual on the first of every stage), table positional encoding, a 32-channel conditioning map concatenated after every
+    stage, no attention, no FiLM.  Runs on the fp32 CUDA-core path of libspdm (its channel counts are not multiples of the
+    64-wide tensor-core operand tiles), inference only."""
+    _attention = False
+    _simple = True
+
+    def __init__(self, in_channels, out_channels, noise_steps=1000, time_dim=256, global_cond_dim=None):
+        nn.Module.__init__(self)
+        if in_channels != 1 or out_channels != 1:
+            raise NotImplementedError("the B200 path implements the reference's wiring in_channels = out_channels = 1")
+        self.in_channels, self.out_channels = in_channels, out_channels
+        self.noise_steps, self.time_dim, self.global_cond_dim = noise_steps, time_dim, global_cond_dim
+        self.pos_encoding = PositionalEncoding(embedding_dim=time_dim, max_len=self.noise_steps + 1)
+        self.input_conv = _SimpleDoubleConvolution(in_channels, 16)
+        self.down1 = _SimpleStage(16, 32, cond_dim=global_cond_dim)
+        self.down2 = _SimpleStage(64, 128, cond_dim=global_cond_dim)
+        self.down3 = _SimpleStage(160, 256, cond_dim=global_cond_dim)
+        self.up1 = _SimpleStage(288 + 160, 128, cond_dim=global_cond_dim)
+        self.up2 = _SimpleStage(160 + 64, 64, cond_dim=global_cond_dim)
+        self.up3 = _SimpleStage(96 + 16, 32, cond_dim=global_cond_dim)
+        self.outc = nn.Conv2d(in_channels=64, out_channels=out_channels, kernel_size=(1, 1))
+        self.precision = "fp32"
+        self.batch_max = 0
+        self.split = 1
+        self._plan = None
+        self._plan_key = None
+        self._weights_tag = None
+        self._weights_epoch = 0
+
+    def configure(self, precision=None, batch_max=None):
+        if precision not in (None, "fp32"):
+            raise ValueError("the simple U-Net runs on the fp32 path only")
+        if batch_max is not None:
+            self.batch_max = int(batch_max)
+        return self
+
+    def _tag(self):
+        return super()._tag() + ((self.pos_encoding.pos_encoding.data_ptr(), self.pos_encoding.pos_encoding._version),)
+
+    def forward(self, x, t, y=None):
+        if y is None:
+            raise ValueError("the simple U-Net needs the conditioning `y`: its stage widths include the 32-channel cond_emb "
+                             "(models/simple_Unet.py:268-276; the reference fails on a channel mismatch without it)")
+        if self.training and torch.is_grad_enabled():
+            raise NotImplementedError("spdm: the simple U-Net is inference-only on the B200 path (eval mode / torch.no_grad()); "
+                                      "train the FiLM U-Nets (model='UNet_Film' / 'UNet_FilmnoAttention') natively")
+        self.precision = "fp32"
+        return super().forward(x, t, y)

@@ -389,8 +389,8 @@ def test_error_paths_are_loud(spdm):
     plan.close()
     with pytest.raises(NotImplementedError):
         spdm.DDPMScheduler(num_train_timesteps=10, thresholding=True)
-    with pytest.raises(NotImplementedError):
-        spdm.Diffusion_DDPM(model="UNet")
+    with pytest.raises(SpdmError, match="fp32 path only"):
+        spdm.DenoisePlan(simple=True, precision="bf16", batch_max=1)
 
 
 def test_sampling_pipeline_matches_sequential(spdm):
@@ -504,3 +504,45 @@ def test_load_from_checkpoint_like_generate_py(spdm, tmp_path):
     a = model.sample(dict(batch, image=fl), batched=True, x_T=xT2)
     b = model.sample(dict(batch, image=u8), batched=True, x_T=xT2)
     assert torch.equal(a, b)
+
+
+def test_simple_unet_forward_and_sampling(spdm, golden_dir):
+    """The legacy `UNet` (models/simple_Unet.py:260-339; the model='UNet' DEFAULT of the reference's Diffusion_DDPM constructor) on the
+    fp32 path: forward against the reference's own output (golden) at rel 1e-4, per-sample and broadcast timesteps; then a DDPM
+    sampling loop through `Diffusion_DDPM()` built with the reference's default model argument against the oracle loop."""
+    from oracle import simple_unet_ref
+    g = _golden(golden_dir, "simple_unet")
+    sd = fixtures.make_simple_unet_weights(seed=int(g["seed"]))
+    net = spdm.UNet(in_channels=1, out_channels=1, noise_steps=1000, global_cond_dim=1350).cuda().eval()
+    assert set(net.state_dict()) == set(sd) and all(tuple(net.state_dict()[k].shape) == tuple(v.shape) for k, v in sd.items())
+    net.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out = net(g["x"].cuda(), g["t"].cuda(), g["y"].cuda())
+        out1 = net(g["x"].cuda(), torch.tensor([17]).cuda(), g["y"].cuda())
+    assert rel(out, g["out"]) < FP32_TOL and rel(out1, g["out_t1"]) < FP32_TOL
+    with pytest.raises(ValueError):
+        net(g["x"].cuda(), g["t"].cuda(), None)
+    # the wrapper with the reference's default `model` argument
+    K = 12
+    m = spdm.Diffusion_DDPM(noise_steps=K, obs_horizon=10, pred_horizon=30, observation_dim=135, prediction_dim=5, inpaint_horizon=1).cuda().eval()
+    assert isinstance(m.noise_estimator, spdm.UNet) and m.precision == "fp32"
+    sd12 = fixtures.make_simple_unet_weights(seed=11, noise_steps=K)
+    esd = fixtures.make_encoder_weights()
+    m.noise_estimator.load_state_dict(sd12, strict=True)
+    m.vision_encoder.load_state_dict(esd, strict=True)
+    B = 3
+    batch = fixtures.make_batch(B, seed=31)
+    x_T = fixtures.make_xT(B)
+    noise = fixtures.make_noise(K, B)
+    got = m.sample({k: v.clone() for k, v in batch.items()}, batched=True, x_T=x_T.cuda(), noise=noise.cuda())
+    with torch.no_grad():
+        cond = unet_ref.obs_cond(esd, batch).unsqueeze(1)
+        inp = unet_ref.inpaint_vector(batch, 1).unsqueeze(1)
+        want = sampler_ref.sample_ref(sd12, sampler_ref.make_scheduler("ddpm", K), K, x_T, cond, inp, 1, noise=noise,
+                                      forward=simple_unet_ref.unet_forward)
+    assert rel(got, want) < 5e-4
+    one = m.sample({k: v.clone() for k, v in batch.items()})           # reference default: batch element 0 only
+    assert tuple(one.shape) == (1, 1, 31, 5)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m.process_single_batch({k: torch.cat([v] * 4, dim=1).cuda() for k, v in batch.items()})

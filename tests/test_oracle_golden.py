@@ -160,3 +160,18 @@ def test_dataset_oracle_vs_reference_golden(golden_dir):
         for i, s0 in enumerate(start):
             rawpos = raw["position"][s0:end[i]:step]
             assert np.allclose(un[i], rawpos, rtol=0, atol=2e-4 * float(np.abs(rawpos).max()))
+
+
+def test_simple_unet_oracle_vs_reference_golden(golden_dir):
+    """oracle/simple_unet_ref.py against the reference's own legacy UNet (models/simple_Unet.py:260-339; golden written by
+    oracle/make_golden.py::golden_simple_unet, which also checks the PositionalEncoding buffer restatement bit for bit)."""
+    import os
+    import numpy as np
+    from oracle import simple_unet_ref
+    g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, "simple_unet.npz")).items()}
+    sd = fixtures.make_simple_unet_weights(seed=int(g["seed"]))
+    with torch.no_grad():
+        out = simple_unet_ref.unet_forward(sd, g["x"], g["t"], g["y"])
+        out1 = simple_unet_ref.unet_forward(sd, g["x"], torch.tensor([17]), g["y"])
+    assert float((out - g["out"]).abs().max()) <= 1e-6 * float(g["out"].abs().max())
+    assert float((out1 - g["out_t1"]).abs().max()) <= 1e-6 * float(g["out_t1"].abs().max())
