@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--sampler", default="ddim", choices=["ddim", "ddpm"])
     ap.add_argument("--variant", default="attn", choices=["attn", "noattn"])
-    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32", "tf32"])
     ap.add_argument("--rows", type=int, default=31)
     ap.add_argument("--dim", type=int, default=5, help="prediction_dim (5 = position+action, 2 = position only)")
     ap.add_argument("--graph-steps", type=int, default=10)

@@ -25,14 +25,15 @@ typedef struct spdm_plan spdm_plan;
 
 enum { SPDM_VARIANT_ATTENTION = 0, SPDM_VARIANT_NO_ATTENTION = 1,
        SPDM_VARIANT_SIMPLE_UNET = 2 /* models/simple_Unet.py:260-339, the model='UNet' default; fp32 path, inference only */ };
-enum { SPDM_PRECISION_FP32 = 0, SPDM_PRECISION_BF16 = 1 };
+enum { SPDM_PRECISION_FP32 = 0, SPDM_PRECISION_BF16 = 1,
+       SPDM_PRECISION_TF32 = 2 /* fp32 activations; the 3x3 convs on tcgen05.mma.kind::tf32 (sampling / forward only) */ };
 enum { SPDM_SCHED_DDPM = 0, SPDM_SCHED_DDIM = 1 };
 enum { SPDM_FLAG_SCHEDULER_ONLY = 1 }; /* plan without U-Net weights/workspace: spdm_step, spdm_add_noise only */
 #define SPDM_FLAG_SPLIT(n) (((n) & 0xF) << 8) /* run n sub-batches of every denoising step concurrently (spdm_sample) */
 
 typedef struct spdm_config {
   int32_t variant;       /* models/Unet_FiLmLayer.py:240 (0), Unet_FiLmLayer_noAttention.py:240 (1), simple_Unet.py:260 (2) */
-  int32_t precision;     /* SPDM_PRECISION_*: fp32 = CUDA-core path, bf16 = tcgen05 path            */
+  int32_t precision;     /* SPDM_PRECISION_*: fp32 = CUDA-core path, bf16 / tf32 = tcgen05 paths     */
   int32_t batch_max;     /* largest number of trajectories a call will carry                        */
   int32_t rows;          /* pred_horizon + inpaint_horizon   (models/diffusion_ddpm.py:252)         */
   int32_t dim;           /* prediction_dim                   (models/diffusion_ddpm.py:252)         */

@@ -19,7 +19,7 @@ class SpdmConfig(_c.Structure):
 
 
 VARIANT_ATTENTION, VARIANT_NO_ATTENTION, VARIANT_SIMPLE_UNET = 0, 1, 2
-PRECISION_FP32, PRECISION_BF16 = 0, 1
+PRECISION_FP32, PRECISION_BF16, PRECISION_TF32 = 0, 1, 2
 SCHED_DDPM, SCHED_DDIM = 0, 1
 FLAG_SCHEDULER_ONLY = 1
 PROFILE_CLASSES = ("conv3x3", "gemm1x1", "gn_apply", "gn_stats", "resample", "layernorm", "sdpa", "io_conv", "step", "conv3x3_gn")

@@ -239,6 +239,14 @@ void tc_set_debug(int v);  // microbenchmark switches, see TcParams::dbg
 int tc_batch_multiple(int H, int W);  // granularity of B required by the 128-row M tiling at geometry HxW
 long long tc_launch_count();
 
+// tcgen05 kind::tf32 3x3 convolution on fp32 activations (conv_tf32.cu): the TF32 precision mode ---------------------------
+struct TfGemm;
+TfGemm* tf32_conv_create(const float* in, int ld_in, const float* w_packed, int Cin, int Cout, int H, int W, int Bcap);
+void tf32_conv_destroy(TfGemm* g);
+void tf32_conv_launch(const TfGemm* g, float* out, int ld_out, int B, cudaStream_t s);   // raw fp32 conv output
+const char* tf32_last_error();
+void launch_pack_conv_tf32(const float* oihw, float* out, int Cout, int Cin, cudaStream_t s);   // -> [Cout][tap][Cin] fp32
+
 // tcgen05 attention core (sdpa_tc.cu) ------------------------------------------------------------------
 struct SdpaTc;
 bool sdpa_tc_supported(int L, int C, int heads);

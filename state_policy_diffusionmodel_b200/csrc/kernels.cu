@@ -1304,6 +1304,21 @@ void launch_pack_conv_fold2_bf16(const float* oihw, bf16* out, int Cout, int Cin
   const long long total = 2LL * Cout * 3 * 2 * Cin;
   launch_pdl(pack_conv_fold2_bf16_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, oihw, out, Cout, Cin);
 }
+namespace {
+__global__ void pack_conv_tf32_kernel(const float* __restrict__ oihw, float* __restrict__ out, int Cout, int Cin) {
+  pdl_wait();
+  pdl_trigger();
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Cout * Cin * 9) return;
+  const int ci = (int)(i % Cin);
+  const long long t = i / Cin;
+  const int tap = (int)(t % 9), co = (int)(t / 9);
+  out[i] = oihw[((size_t)co * Cin + ci) * 9 + tap];
+}
+}  // namespace
+void launch_pack_conv_tf32(const float* oihw, float* out, int Cout, int Cin, cudaStream_t s) {
+  launch_pdl(pack_conv_tf32_kernel, dim3(cdiv((long long)Cout * Cin * 9, 256)), dim3(256), 0, s, oihw, out, Cout, Cin);
+}
 void launch_pack_conv_pfold_bf16(const float* oihw, bf16* out, int Cin, cudaStream_t s) {
   const long long total = 128LL * 12 * Cin;
   launch_pdl(pack_conv_pfold_bf16_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, oihw, out, Cin);

@@ -67,6 +67,7 @@ struct GemmW {  // a 3x3 convolution or a Linear layer
   float* w32 = nullptr;  // [taps][Cin][Cout]   (fp32 path)
   bf16* w16 = nullptr;   // [Cout][taps*Cin]    (bf16 tcgen05 path)
   bf16* w16_fold = nullptr;  // 3x3 convs of the W = 2 level, inference: [2 Cout][9][2 Cin], the two pixels of a row folded into channels
+  float* wtf = nullptr;      // TF32 plan: 3x3 conv weights [Cout][9][Cin] fp32, K-major B operand of tcgen05.mma.kind::tf32
   bf16* w16_pfold = nullptr; // 3x3 convs with 64 output channels, inference: pair fold [128][3][4][Cin] (kernels.cu::pack_conv_pfold_bf16_kernel)
   float* bias = nullptr; // [Cout] or null
   GemmW* twin = nullptr; // training: the data-gradient GEMM (Cin/Cout exchanged, transposed / tap-flipped weights)
@@ -83,6 +84,8 @@ static const StageInfo kStages[6] = {
 struct spdm_plan {
   spdm_config cfg;
   bool attention = true, bf16_mode = false, sched_only = false;
+  bool tf32_mode = false;              // SPDM_PRECISION_TF32: fp32 activations, 3x3 convs on tcgen05.mma.kind::tf32 (conv_tf32.cu)
+  std::map<std::string, TfGemm*> tf_cache;
   bool simple = false;                 // SPDM_VARIANT_SIMPLE_UNET: models/simple_Unet.py UNet on the fp32 path (simple_unet.inl)
   float* su_table = nullptr; int su_table_rows = 0;   // its PositionalEncoding buffer [max_len][time_dim]
   int H0 = 0, W0 = 0, lh = 0, lw = 0;  // padded geometry (pad_to 8) and low-side pads
@@ -231,6 +234,7 @@ GemmW& reg_conv3(spdm_plan* p, const std::string& name, int Cin, int Cout) {
   g.Cin = Cin; g.Cout = Cout; g.taps = 9;
   if (p->bf16_mode) g.w16 = p->alloc<bf16>((size_t)9 * Cin * Cout);
   else g.w32 = p->alloc<float>((size_t)9 * Cin * Cout);
+  if (p->tf32_mode && Cin % 32 == 0 && Cout % 64 == 0) g.wtf = p->alloc<float>((size_t)9 * Cin * Cout);
   // the third level of the U-Net is H/4 x 2: a third of the MMAs of a tile-wise 9-tap implicit GEMM there multiply the zero
   // padding left and right of the two columns.  Folding the column into the channels (K = 3 x 2 Cin, N = 2 Cout over (b, h) rows)
   // makes the conv dense along W (Fwd::fold_ok)
@@ -245,6 +249,7 @@ GemmW& reg_conv3(spdm_plan* p, const std::string& name, int Cin, int Cout) {
     check_shape(name + ".weight", shape, ndim, {Cout, Cin, 3, 3});
     if (bfm) launch_pack_conv_bf16(src, gp->w16, Cout, Cin, 3, s);
     else launch_pack_conv_f32(src, gp->w32, Cout, Cin, 3, s);
+    if (gp->wtf) launch_pack_conv_tf32(src, gp->wtf, Cout, Cin, s);
     if (gp->w16_fold && !p->tr) launch_pack_conv_fold2_bf16(src, gp->w16_fold, Cout, Cin, s);  // inference only (Fwd::fold_ok)
     if (gp->w16_pfold && !p->tr) launch_pack_conv_pfold_bf16(src, gp->w16_pfold, Cin, s);        // inference only (Fwd::pfold_tc)
     if (gp->twin) {
@@ -648,6 +653,25 @@ template <typename T> struct Fwd {
       REQUIRE(fuse || !(flags & EPI_STATS) || P <= SPDM_MAX_PARTIALS, "%s: too many GroupNorm partials (%d)", wname.c_str(), P);
       curP = P;
     } else {
+      if (p->tf32_mode && g.taps == 9 && g.wtf && !resid && (flags & ~EPI_STATS) == 0) {
+        // TF32 precision mode: the 3x3 convs run on the tensor cores (tcgen05.mma.kind::tf32), fp32 in / fp32 out
+        char key[160];
+        snprintf(key, sizeof key, "%s|%p|%d", wname.c_str(), (const void*)in, ld_in);
+        TfGemm*& tf = p->tf_cache[key];
+        if (!tf) {
+          tf = tf32_conv_create(reinterpret_cast<const float*>(in), ld_in, g.wtf, g.Cin, g.Cout, H, W, p->Bcap);
+          REQUIRE(tf != nullptr, "%s: %s", wname.c_str(), tf32_last_error());
+        }
+        const double flops = 2.0 * g.Cin * g.Cout * (3.0 * H - 2) * (3.0 * W - 2) * c.B;
+        const double bytes = ((double)c.B * H * W * (g.Cin + g.Cout) + 9.0 * g.Cin * g.Cout) * 4.0;
+        timed(p, c.s, PC_CONV3, flops, bytes, [&] { tf32_conv_launch(tf, reinterpret_cast<float*>(out), ld_out, Bpad, c.s); });
+        if (flags & EPI_STATS) {
+          timed(p, c.s, PC_STATS, 0, (double)c.B * H * W * g.Cout * 4.0,
+                [&] { launch_stats<T>(out, stats(), c.B, H * W, g.Cout, ld_out, c.s); });
+          curP = 1;
+        }
+        return;
+      }
       GemmSimtArgs a{};
       a.in = in; a.w = g.w32; a.bias = (flags & EPI_BIAS) ? g.bias : nullptr; a.resid = (flags & EPI_RESID) ? resid : nullptr;
       a.out = out; a.M = c.B * H * W; a.Cin = g.Cin; a.Cout = g.Cout; a.ld_in = ld_in; a.ld_out = ld_out; a.ld_res = ld_res;
@@ -1096,7 +1120,7 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
   if (const char* e = getenv("SPDM_PDL")) g_spdm_pdl = atoi(e) != 0;  // A/B switch for programmatic dependent launch
   REQUIRE(cfg->rows > 0 && cfg->dim > 0 && cfg->batch_max > 0, "rows/dim/batch_max must be positive");
   REQUIRE(cfg->time_dim > 0 && cfg->time_dim % 2 == 0 && cfg->time_dim <= 4096, "bad time_dim");
-  REQUIRE(cfg->precision == SPDM_PRECISION_FP32 || cfg->precision == SPDM_PRECISION_BF16, "bad precision");
+  REQUIRE(cfg->precision == SPDM_PRECISION_FP32 || cfg->precision == SPDM_PRECISION_BF16 || cfg->precision == SPDM_PRECISION_TF32, "bad precision");
   REQUIRE(cfg->inpaint_rows >= 0 && cfg->inpaint_rows <= cfg->rows, "bad inpaint_rows");
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1112,9 +1136,10 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
   p->attention = cfg->variant == SPDM_VARIANT_ATTENTION;
   p->simple = cfg->variant == SPDM_VARIANT_SIMPLE_UNET;
   p->bf16_mode = cfg->precision == SPDM_PRECISION_BF16;
+  p->tf32_mode = cfg->precision == SPDM_PRECISION_TF32;
   if (p->simple && !(cfg->flags & SPDM_FLAG_SCHEDULER_ONLY)) {
     // its channel counts (16, 160, 288, 448, 224, 96, 112) are not multiples of the 64-wide tcgen05 operand tiles
-    if (p->bf16_mode) { delete p; throw SpdmError{"the simple U-Net (models/simple_Unet.py) runs on the fp32 path only: create the plan with SPDM_PRECISION_FP32"}; }
+    if (p->bf16_mode || p->tf32_mode) { delete p; throw SpdmError{"the simple U-Net (models/simple_Unet.py) runs on the fp32 path only: create the plan with SPDM_PRECISION_FP32"}; }
     if (cfg->obs_horizon * cfg->cond_dim <= 0) { delete p; throw SpdmError{"the simple U-Net needs conditioning (cond_dim > 0): its stages concatenate a 32-channel cond_emb"}; }
   }
   if (const char* e = getenv("SPDM_NO_PFOLD")) p->no_pfold = atoi(e) != 0;
@@ -1124,7 +1149,7 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
   p->lh = (p->H0 - cfg->rows) / 2; p->lw = (p->W0 - cfg->dim) / 2;
   p->G = cfg->obs_horizon * cfg->cond_dim;
   try {
-    if (p->bf16_mode) {
+    if (p->bf16_mode || p->tf32_mode) {
       REQUIRE(p->W0 <= 128 && 128 % p->W0 == 0, "bf16 path: padded width %d must divide 128", p->W0);
       p->bm = tc_batch_multiple(p->levelH(3), p->levelW(3));
       for (int l = 0; l < 4; ++l) {
@@ -1198,6 +1223,7 @@ extern "C" int spdm_plan_destroy(spdm_plan* p) {
   }
   for (auto& kv : p->tc_cache) tc_gemm_destroy(kv.second);
   for (auto& kv : p->chain_cache) tc_chain_destroy(kv.second);
+  for (auto& kv : p->tf_cache) tf32_conv_destroy(kv.second);
   if (p->enc_tc) tc_gemm_destroy(p->enc_tc);
   if (p->enc_tc2) tc_gemm_destroy(p->enc_tc2);
   if (p->enc_tc3) tc_gemm_destroy(p->enc_tc3);

@@ -46,11 +46,11 @@ class DenoisePlan:
             raise RuntimeError("spdm: no CUDA device — the B200 denoising path has no CPU fallback")
         self.lib = _lib.load()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        if precision not in ("fp32", "bf16"):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if precision not in ("fp32", "bf16", "tf32"):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'tf32'")
         cfg = _lib.SpdmConfig(
             variant=_lib.VARIANT_SIMPLE_UNET if simple else (_lib.VARIANT_ATTENTION if attention else _lib.VARIANT_NO_ATTENTION),
-            precision=_lib.PRECISION_BF16 if precision == "bf16" else _lib.PRECISION_FP32,
+            precision={"bf16": _lib.PRECISION_BF16, "tf32": _lib.PRECISION_TF32, "fp32": _lib.PRECISION_FP32}[precision],
             batch_max=int(batch_max), rows=int(rows), dim=int(dim), obs_horizon=int(obs_horizon),
             cond_dim=int(cond_dim or 0), inpaint_rows=int(inpaint_rows), time_dim=int(time_dim),
             device=self.device.index or 0, graph_steps=int(graph_steps),

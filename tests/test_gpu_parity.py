@@ -546,3 +546,44 @@ def test_simple_unet_forward_and_sampling(spdm, golden_dir):
     m.train()
     with pytest.raises(NotImplementedError):
         m.process_single_batch({k: torch.cat([v] * 4, dim=1).cuda() for k, v in batch.items()})
+
+
+@pytest.mark.parametrize("attention,B", [(True, 3), (True, 40), (False, 64)])
+def test_tf32_path_forward_and_final_trajectory(spdm, attention, B):
+    """precision='tf32' (north_star: "the bf16/TF32 path"): fp32 activations, the 3x3 convs on tcgen05.mma.kind::tf32.  A single
+    forward within 5e-3 of the fp32 oracle (TF32 keeps 10 mantissa bits), the final DDIM-20 trajectory within the contract's
+    rel 1e-2 -- and the convs really left the CUDA cores (the result differs from the fp32 path's)."""
+    sd = fixtures.make_unet_weights(attention=attention, seed=0)
+    esd = fixtures.make_encoder_weights()
+    g = torch.Generator().manual_seed(41 + B)
+    x = torch.rand((B, 1, 31, 5), generator=g)
+    y = torch.randn((B, 1, 10, 135), generator=g)
+    t = torch.randint(0, 1000, (B,), generator=g)
+    outs = {}
+    for precision in ("fp32", "tf32"):
+        plan = spdm.DenoisePlan(attention=attention, precision=precision, batch_max=B, graph_steps=0)
+        plan.load_unet_state_dict(sd)
+        outs[precision] = plan.unet_forward(x, t, y).cpu()
+        plan.close()
+    assert torch.isfinite(outs["tf32"]).all()
+    assert rel(outs["tf32"], outs["fp32"]) < 5e-3
+    assert not torch.equal(outs["tf32"], outs["fp32"]), "the TF32 plan computed on the fp32 CUDA-core path"
+    if B > 8:
+        return
+    K = 20
+    batch = fixtures.make_batch(B, seed=7)
+    x_T = fixtures.make_xT(B)
+    with torch.no_grad():
+        cond = unet_ref.obs_cond(esd, batch).unsqueeze(1)
+        inp = unet_ref.inpaint_vector(batch, 1).unsqueeze(1)
+        want = sampler_ref.sample_ref(sd, sampler_ref.make_scheduler("ddim", K), K, x_T, cond, inp, 1, attention=attention)
+    sch = spdm.DDIMScheduler(num_train_timesteps=K, beta_schedule="linear", clip_sample=False, prediction_type="epsilon")
+    sch.set_timesteps(K)
+    plan = spdm.DenoisePlan(attention=attention, precision="tf32", batch_max=B, inpaint_rows=1, graph_steps=5)
+    plan.load_unet_state_dict(sd)
+    plan.load_encoder_state_dict(esd)
+    plan.set_schedule("ddim", sch.coef_table(), sch.timesteps)
+    plan.encode_cond(batch["image"], batch["position"], batch["action"], batch["velocity"])
+    got = plan.sample(x_T, inpaint=inp.reshape(B, -1))
+    assert rel(got, want) < BF16_FINAL_TOL
+    plan.close()
