@@ -28,7 +28,10 @@ enum { SPDM_VARIANT_ATTENTION = 0, SPDM_VARIANT_NO_ATTENTION = 1,
 enum { SPDM_PRECISION_FP32 = 0, SPDM_PRECISION_BF16 = 1,
        SPDM_PRECISION_TF32 = 2 /* fp32 activations; the 3x3 convs on tcgen05.mma.kind::tf32 (sampling / forward only) */ };
 enum { SPDM_SCHED_DDPM = 0, SPDM_SCHED_DDIM = 1 };
-enum { SPDM_FLAG_SCHEDULER_ONLY = 1 }; /* plan without U-Net weights/workspace: spdm_step, spdm_add_noise only */
+enum { SPDM_FLAG_SCHEDULER_ONLY = 1,    /* plan without U-Net weights/workspace: spdm_step, spdm_add_noise only */
+       SPDM_FLAG_ENCODER_RESNET18 = 2   /* vision encoder = ResNet18 with GroupNorm(C/16) (models/Unet_FiLmLayer.py:316-386, `VisionEncoder()`):
+                                           weights "vision_encoder.<torchvision resnet18 key>", 512 features per frame => cond_dim = 519;
+                                           inference only */ };
 #define SPDM_FLAG_SPLIT(n) (((n) & 0xF) << 8) /* run n sub-batches of every denoising step concurrently (spdm_sample) */
 
 typedef struct spdm_config {
@@ -68,7 +71,8 @@ int spdm_plan_missing_weights(spdm_plan* plan);
 int spdm_plan_set_schedule(spdm_plan* plan, int32_t kind, int32_t K, const float* coef,
                            const int64_t* timesteps, void* stream);
 
-/* Autoencoder.encoder (models/encoder/autoencoder.py:11-20): images (n,3,96,96) -> (n,128). */
+/* Autoencoder.encoder (models/encoder/autoencoder.py:11-20): images (n,3,96,96) -> (n,128); with SPDM_FLAG_ENCODER_RESNET18 the
+ * ResNet18-GroupNorm encoder (models/Unet_FiLmLayer.py:316-386): -> (n,512). */
 int spdm_encode_images(spdm_plan* plan, const float* images, float* out, int32_t n, void* stream);
 
 /* prepare_obs_cond_vectors (models/diffusion_ddpm.py:317-330) + the six FiLM cond_encoder

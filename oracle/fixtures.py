@@ -117,6 +117,23 @@ def make_simple_unet_weights(cond_dim=1350, seed=0, noise_steps=1000):
     return sd
 
 
+def make_resnet_weights(seed=2):
+    """State dict of the ResNet18-GroupNorm vision encoder (models/Unet_FiLmLayer.py:316-386, torchvision key names): convs
+    kaiming-like (std sqrt(2 / fan_out), as torchvision initialises them), GroupNorm affine perturbed off 1 / 0."""
+    from .resnet_ref import shapes
+    g = torch.Generator().manual_seed(seed)
+    sd = {}
+    for k, shp in sorted(shapes().items()):
+        if len(shp) == 4:
+            fan_out = shp[0] * shp[2] * shp[3]
+            sd[k] = math.sqrt(2.0 / fan_out) * torch.randn(shp, generator=g)
+        elif k.endswith(".weight"):
+            sd[k] = 1.0 + 0.1 * (2 * torch.rand(shp, generator=g) - 1)
+        else:
+            sd[k] = 0.1 * (2 * torch.rand(shp, generator=g) - 1)
+    return sd
+
+
 def make_encoder_weights(seed=1):
     shapes = {"0.weight": (16, 3, 2, 2), "0.bias": (16,), "2.weight": (32, 16, 2, 2), "2.bias": (32,),
               "4.weight": (64, 32, 2, 2), "4.bias": (64,), "7.weight": (128, 9216), "7.bias": (128,)}

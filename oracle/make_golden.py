@@ -256,6 +256,28 @@ def golden_simple_unet(seed=7):
     print("simple_unet out", tuple(out.shape), float(out.abs().mean()))
 
 
+def golden_resnet18gn(seed=2):
+    """The reference's `VisionEncoder()` (models/Unet_FiLmLayer.py:383-386: torchvision resnet18, fc = Identity, BatchNorm ->
+    GroupNorm(C // 16)) on the fixture weights: 512 features of 5 frames + the activation after layer1 / layer3."""
+    from models.Unet_FiLmLayer import VisionEncoder
+    sd = fixtures.make_resnet_weights(seed=seed)
+    net = VisionEncoder().eval()
+    net.load_state_dict(sd, strict=True)
+    g = torch.Generator().manual_seed(seed + 100)
+    img = torch.rand((5, 3, 96, 96), generator=g)
+    taps = {}
+    hooks = [getattr(net, m).register_forward_hook(lambda mod, i, o, n=m: taps.__setitem__(n, o.detach().clone())) for m in ("layer1", "layer3")]
+    with torch.no_grad():
+        out = net(img)
+    for h in hooks:
+        h.remove()
+    # (the frames are torch.rand((5, 3, 96, 96)) under the CPU generator seeded seed + 100: regenerated by the tests, not stored)
+    d = {"img_fingerprint": _tap_summary(img), "out": out, "seed": seed, "tap_layer1": _tap_summary(taps["layer1"]),
+         "tap_layer3": _tap_summary(taps["layer3"])}
+    np.savez_compressed(os.path.join(OUT, "resnet18gn.npz"), **_np(d))
+    print("resnet18gn out", tuple(out.shape), float(out.abs().mean()))
+
+
 def golden_beta_schedules():
     """utils/schedulers.py:6-40 of the reference, imported as is (the functions are unbound "methods" reading self.device)."""
     import importlib.util
@@ -291,6 +313,7 @@ def main():
     golden_dataset()
     golden_beta_schedules()
     golden_simple_unet()
+    golden_resnet18gn()
 
 
 if __name__ == "__main__":

@@ -13,8 +13,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libspdm.so")
-SOURCES = ["kernels.cu", "simple_kernels.cu", "conv_tc.cu", "conv_tf32.cu", "sdpa_tc.cu", "attn_tc.cu", "attn_head.cu", "bwd_kernels.cu", "wgrad_tc.cu", "data_kernels.cu", "plan.cu"]
-HEADERS = [os.path.join(CSRC, h) for h in ("common.cuh", "tc_ptx.cuh", "train.cuh", "train_impl.inl", "simple_unet.inl")] + [
+SOURCES = ["kernels.cu", "simple_kernels.cu", "resnet.cu", "conv_tc.cu", "conv_tf32.cu", "sdpa_tc.cu", "attn_tc.cu", "attn_head.cu", "bwd_kernels.cu", "wgrad_tc.cu", "data_kernels.cu", "plan.cu"]
+HEADERS = [os.path.join(CSRC, h) for h in ("common.cuh", "tc_ptx.cuh", "train.cuh", "train_impl.inl", "simple_unet.inl", "resnet.inl")] + [
     os.path.join(os.path.dirname(HERE), "include", "spdm.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC"]

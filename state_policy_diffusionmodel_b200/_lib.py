@@ -22,6 +22,7 @@ VARIANT_ATTENTION, VARIANT_NO_ATTENTION, VARIANT_SIMPLE_UNET = 0, 1, 2
 PRECISION_FP32, PRECISION_BF16, PRECISION_TF32 = 0, 1, 2
 SCHED_DDPM, SCHED_DDIM = 0, 1
 FLAG_SCHEDULER_ONLY = 1
+FLAG_ENCODER_RESNET18 = 2
 PROFILE_CLASSES = ("conv3x3", "gemm1x1", "gn_apply", "gn_stats", "resample", "layernorm", "sdpa", "io_conv", "step", "conv3x3_gn")
 
 _P = _c.c_void_p

@@ -192,6 +192,14 @@ void launch_su_temb(const long long* t_dev, int n_t, const float* table, int max
                     int time_dim, int width, cudaStream_t s);
 void launch_su_silu(const float* in, float* out, long long n, cudaStream_t s);
 void launch_su_bcast(const float* emb, int emb_stride, float* out, int ld_out, int B, int HW, cudaStream_t s);
+// ResNet18-GroupNorm vision encoder (resnet.cu): channels-last activations, convs as GEMMs over explicit patch rows
+template <typename T> void launch_rn_im2col_img(const float* img, T* out, long long frames_pad, int n_real, cudaStream_t s);
+template <typename T> void launch_rn_im2col(const T* in, T* out, long long frames, int H, int W, int C, int k, int stride, int pad, cudaStream_t s);
+template <typename T> void launch_rn_gn(const T* x, T* out, float* stats, const float* gamma, const float* beta, const T* resid, int relu, long long frames,
+                                        int HW, int C, cudaStream_t s);   // GroupNorm(C / 16) (+ residual) (+ ReLU)
+template <typename T> void launch_rn_maxpool(const T* in, T* out, long long frames, int H, int W, int C, cudaStream_t s);
+template <typename T> void launch_rn_avgpool(const T* in, float* out, long long frames, int HW, int C, cudaStream_t s);
+void launch_rn_pack_conv1(const float* oihw, bf16* w16, float* w32, cudaStream_t s);
 long long kernels_launch_count();
 void kernels_count_launch();  // one more launch (kernels that live in other translation units)
 

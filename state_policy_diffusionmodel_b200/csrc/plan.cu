@@ -86,6 +86,11 @@ struct spdm_plan {
   bool attention = true, bf16_mode = false, sched_only = false;
   bool tf32_mode = false;              // SPDM_PRECISION_TF32: fp32 activations, 3x3 convs on tcgen05.mma.kind::tf32 (conv_tf32.cu)
   std::map<std::string, TfGemm*> tf_cache;
+  bool enc_resnet = false;             // SPDM_FLAG_ENCODER_RESNET18: ResNet18-GroupNorm vision encoder (resnet.inl), 512 features per frame
+  void *rn_col = nullptr, *rn_a0 = nullptr, *rn_buf[4] = {};
+  float* rn_stats = nullptr;
+  std::map<std::string, long long> rn_rows_cap;
+  int feat_dim() const { return enc_resnet ? 512 : 128; }
   bool simple = false;                 // SPDM_VARIANT_SIMPLE_UNET: models/simple_Unet.py UNet on the fp32 path (simple_unet.inl)
   float* su_table = nullptr; int su_table_rows = 0;   // its PositionalEncoding buffer [max_len][time_dim]
   int H0 = 0, W0 = 0, lh = 0, lw = 0;  // padded geometry (pad_to 8) and low-side pads
@@ -379,6 +384,7 @@ void register_weights(spdm_plan* p) {
     std::set<std::string> dummy;
     reg_vec(p, "pos_encoding.inv_freq", p->inv_freq, TD / 2, dummy);
   }
+  if (p->enc_resnet) return;   // its weights are registered by register_weights_resnet (resnet.inl)
   // vision encoder (models/encoder/autoencoder.py:11-20)
   p->enc_w1 = p->alloc<float>(16 * 3 * 4);   p->enc_b1 = p->alloc<float>(16);
   p->enc_w2 = p->alloc<float>(32 * 16 * 4);  p->enc_b2 = p->alloc<float>(32);
@@ -1018,6 +1024,7 @@ template <typename T> struct Fwd {
 
 }  // namespace
 #include "simple_unet.inl"
+#include "resnet.inl"
 namespace {
 
 void run_forward(spdm_plan* p, const FwdCtx& c) {
@@ -1161,7 +1168,10 @@ extern "C" int spdm_plan_create(spdm_plan** out, const spdm_config* cfg) {
     p->Bcap = ((cfg->batch_max + p->bm - 1) / p->bm) * p->bm;
     p->sched_only = (cfg->flags & SPDM_FLAG_SCHEDULER_ONLY) != 0;  // scheduler-only plan: spdm_step / spdm_add_noise, no U-Net
     if (p->sched_only) { *out = p; return 0; }
+    p->enc_resnet = (cfg->flags & SPDM_FLAG_ENCODER_RESNET18) != 0;
+    REQUIRE(!(p->enc_resnet && p->simple), "the ResNet18 encoder is wired to the FiLM U-Nets");
     if (p->simple) register_weights_simple(p); else register_weights(p);
+    if (p->enc_resnet) register_weights_resnet(p);
     if (p->bf16_mode) alloc_workspace<bf16>(p); else alloc_workspace<float>(p);
     p->stats = p->alloc<float>((size_t)p->Bcap * SPDM_MAX_PARTIALS * 2);
     p->temb_call = p->alloc<float>((size_t)p->Bcap * SPDM_TEMB_WIDTH);
@@ -1297,12 +1307,17 @@ extern "C" int spdm_plan_set_schedule(spdm_plan* p, int32_t kind, int32_t K, con
 static void encode_images_impl(spdm_plan* p, const float* images, const uint8_t* images_u8, float* out, int32_t n, cudaStream_t s) {
   REQUIRE(p && (images || images_u8) && out && n > 0, "bad argument");
   if (!p->missing_enc.empty()) throw SpdmError{"vision encoder weights missing, first: " + *p->missing_enc.begin()};
-  if (images_u8 && !(p->bf16_mode && !p->enc_simt_infer)) {
+  if (images_u8 && (p->enc_resnet || !(p->bf16_mode && !p->enc_simt_infer))) {
     // fp32 (parity) plans and the A/B CUDA-core conv stack read fp32 frames: decode into a plan-owned staging buffer first
     if (p->enc_u8_cap < n) { p->enc_u8_stage = p->alloc<float>((size_t)n * 3 * 96 * 96); p->enc_u8_cap = n; }
     launch_decode_u8_hwc(images_u8, p->enc_u8_stage, n, 96, 96, s);
     images = p->enc_u8_stage;
     images_u8 = nullptr;
+  }
+  if (p->enc_resnet) {   // ResNet18-GroupNorm: (n, 3, 96, 96) -> (n, 512)
+    if (p->bf16_mode) resnet_encode<bf16>(p, images, out, n, s); else resnet_encode<float>(p, images, out, n, s);
+    check_async("encode_images (resnet18)");
+    return;
   }
   if (p->bf16_mode) {
     // bf16 plan: conv stack writes bf16 features, Linear(9216 -> 128) runs on the tcgen05 GEMM (one 128-frame tile per CTA)
@@ -1373,10 +1388,11 @@ extern "C" int spdm_set_cond(spdm_plan* p, const float* obs_cond, int32_t B, voi
 static void encode_cond_impl(spdm_plan* p, const float* images, const uint8_t* images_u8, const float* position, const float* action,
                              const float* velocity, int32_t B, cudaStream_t s) {
   REQUIRE(p && (images || images_u8) && position && action && velocity && B > 0 && B <= p->cfg.batch_max, "bad argument");
-  REQUIRE(p->cfg.cond_dim == 135, "encode_cond needs cond_dim == 135 (2 pos + 3 act + 2 vel + 128 image features)");
+  REQUIRE(p->cfg.cond_dim == 7 + p->feat_dim(), "encode_cond needs cond_dim == %d (2 pos + 3 act + 2 vel + %d image features)", 7 + p->feat_dim(),
+          p->feat_dim());
   check_ready(p);
   const int T = p->cfg.obs_horizon;
-  if (!p->enc_out) p->enc_out = p->alloc<float>((size_t)p->Bcap * T * 128);
+  if (!p->enc_out) p->enc_out = p->alloc<float>((size_t)p->Bcap * T * p->feat_dim());
   encode_images_impl(p, images, images_u8, p->enc_out, B * T, s);
   launch_build_cond(position, action, velocity, p->enc_out, p->cond, B, T, p->cfg.cond_dim, s);
   compute_film(p, B, s);

@@ -436,6 +436,7 @@ template <typename T> struct Train {
 extern "C" int spdm_train_enable(spdm_plan* p) {
   API_BEGIN
   REQUIRE(p && !p->sched_only, "bad plan");
+  REQUIRE(!p->enc_resnet, "the native training step covers the autoencoder vision encoder; the ResNet18-GroupNorm encoder is inference-only here");
   REQUIRE(!p->tf32_mode, "the native training step runs in fp32 (CUDA cores) or bf16 (tensor cores); create the plan with one of them");
   REQUIRE(!p->simple, "the native training step covers the FiLM U-Nets; the simple U-Net (models/simple_Unet.py) is inference-only here");
   if (p->tr) return 0;

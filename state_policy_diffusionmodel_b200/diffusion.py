@@ -19,7 +19,7 @@ import torch
 import torch.nn as nn
 
 from .schedulers import DDIMScheduler, DDPMScheduler
-from .unet import UNet, UNet_Film, UNet_Film_noAttention
+from .unet import ResNet18GN, UNet, UNet_Film, UNet_Film_noAttention
 
 try:  # Lightning is optional: the reference subclasses pl.LightningModule, which is absent on the B200 image
     import pytorch_lightning as pl
@@ -129,10 +129,22 @@ class Diffusion_DDPM(_Base):
         self.loss = nn.MSELoss()
         self.noise_estimator = self.model(in_channels=1, out_channels=1, noise_steps=noise_steps,
                                           global_cond_dim=observation_dim * obs_horizon, time_dim=256)
-        self.vision_encoder = VisionEncoder()
         import os
         import weakref
+        if vision_encoder in ('resnet18', 'ResNet18', 'resnet'):
+            # `VisionEncoder()` of models/Unet_FiLmLayer.py:383-386 (ResNet18, GroupNorm instead of BatchNorm): 512 features per frame;
+            # the reference's comment at ddpm:79 ("512 is the output dim of Resnet18") is this wiring
+            if model not in ('UNet_Film', 'UNet_FilmnoAttention'):
+                raise ValueError("vision_encoder='resnet18' is wired to the FiLM U-Nets")
+            if observation_dim != 7 + ResNet18GN.feat_dim:
+                raise ValueError("vision_encoder='resnet18' produces 512 image features: observation_dim must be 2 + 3 + 2 + 512 = 519, got %d"
+                                 % observation_dim)
+            self.vision_encoder = ResNet18GN()
+            autoencoder_checkpoint = None
+        else:
+            self.vision_encoder = VisionEncoder()
         self.vision_encoder._owner = weakref.ref(self)
+        self.noise_estimator.encoder = "resnet18" if isinstance(self.vision_encoder, ResNet18GN) else "autoencoder"
         if autoencoder_checkpoint and os.path.exists(autoencoder_checkpoint):  # ddpm:84-88
             sd = torch.load(autoencoder_checkpoint, map_location="cpu", weights_only=False)["state_dict"]
             enc = {k.split("encoder.", 1)[1]: v for k, v in sd.items() if "encoder." in k and "decoder" not in k}
@@ -259,6 +271,9 @@ class Diffusion_DDPM(_Base):
         if self.model is UNet:
             raise NotImplementedError("spdm: the native training step covers model='UNet_Film' / 'UNet_FilmnoAttention'; the legacy simple "
                                       "U-Net (model='UNet') is inference-only on the B200 path")
+        if isinstance(self.vision_encoder, ResNet18GN):
+            raise NotImplementedError("spdm: the native training step covers the autoencoder vision encoder; vision_encoder='resnet18' is "
+                                      "inference-only on the B200 path")
         plan = getattr(self, "_tplan", None)
         key = (self.precision, self.pred_horizon + self.inpaint_horizon, self.prediction_dim, self.obs_horizon, self.observation_dim,
                self.inpaint_horizon, str(self.device))
@@ -507,7 +522,7 @@ class SamplingPipeline:
             else:
                 plan = DenoisePlan(attention=ne._attention, precision=base.precision, batch_max=base.batch_max, rows=base.rows,
                                    dim=base.dim, obs_horizon=base.obs_horizon, cond_dim=base.cond_dim, inpaint_rows=base.inpaint_rows,
-                                   time_dim=ne.time_dim, device=base.device, graph_steps=base.cfg.graph_steps, split=ne.split, simple=ne._simple)
+                                   time_dim=ne.time_dim, device=base.device, graph_steps=base.cfg.graph_steps, split=ne.split, simple=ne._simple, encoder=ne.encoder)
                 plan.load_unet_state_dict(ne.state_dict())
                 plan.load_encoder_state_dict(model.vision_encoder.state_dict())
                 plan.set_schedule(sch.kind, sch.coef_table(), sch.timesteps)

@@ -39,9 +39,16 @@ def _grad_phase(name):
 
 class DenoisePlan:
     def __init__(self, attention=True, precision="bf16", batch_max=1, rows=31, dim=5, obs_horizon=10, cond_dim=135,
-                 inpaint_rows=1, time_dim=256, device=None, graph_steps=1, scheduler_only=False, split=1, simple=False):
+                 inpaint_rows=1, time_dim=256, device=None, graph_steps=1, scheduler_only=False, split=1, simple=False,
+                 encoder="autoencoder"):
         """`attention`: UNet_Film (True) or UNet_Film_noAttention (False); `simple=True`: the legacy `UNet` of
-        models/simple_Unet.py (the reference's model='UNet' default) -- fp32 path, inference only."""
+        models/simple_Unet.py (the reference's model='UNet' default) -- fp32 path, inference only.  `encoder`: "autoencoder"
+        (models/encoder/autoencoder.py, 128 features per frame, cond_dim 135) or "resnet18" (the ResNet18-GroupNorm `VisionEncoder()`
+        of models/Unet_FiLmLayer.py:316-386, 512 features, cond_dim 519; inference only)."""
+        if encoder not in ("autoencoder", "resnet18"):
+            raise ValueError("encoder must be 'autoencoder' or 'resnet18'")
+        self.encoder = encoder
+        self.feat_dim = 512 if encoder == "resnet18" else 128
         if not torch.cuda.is_available():
             raise RuntimeError("spdm: no CUDA device — the B200 denoising path has no CPU fallback")
         self.lib = _lib.load()
@@ -54,7 +61,8 @@ class DenoisePlan:
             batch_max=int(batch_max), rows=int(rows), dim=int(dim), obs_horizon=int(obs_horizon),
             cond_dim=int(cond_dim or 0), inpaint_rows=int(inpaint_rows), time_dim=int(time_dim),
             device=self.device.index or 0, graph_steps=int(graph_steps),
-            flags=(_lib.FLAG_SCHEDULER_ONLY if scheduler_only else 0) | ((int(split) & 0xF) << 8))
+            flags=(_lib.FLAG_SCHEDULER_ONLY if scheduler_only else 0) | ((int(split) & 0xF) << 8)
+            | (_lib.FLAG_ENCODER_RESNET18 if encoder == "resnet18" else 0))
         self.cfg = cfg
         self.attention, self.precision, self.simple = attention and not simple, precision, bool(simple)
         self.batch_max, self.rows, self.dim = int(batch_max), int(rows), int(dim)
@@ -100,7 +108,13 @@ class DenoisePlan:
         self.load_weight("pos_encoding.inv_freq", inv_freq)
 
     def load_encoder_state_dict(self, esd, prefix=""):
-        """Autoencoder.encoder weights: keys `{prefix}{0,2,4,7}.{weight,bias}`."""
+        """Autoencoder.encoder weights: keys `{prefix}{0,2,4,7}.{weight,bias}`; ResNet18-GroupNorm: every floating-point entry of the
+        torchvision state_dict (`conv1.weight`, `bn1.weight`, `layer1.0.conv1.weight`, ...)."""
+        if self.encoder == "resnet18":
+            for k, v in esd.items():
+                if k.startswith(prefix) and torch.is_floating_point(v):
+                    self.load_weight("vision_encoder." + k[len(prefix):], v)
+            return
         for k in ("0.weight", "0.bias", "2.weight", "2.bias", "4.weight", "4.bias", "7.weight", "7.bias"):
             self.load_weight("vision_encoder." + k, esd[prefix + k])
 
@@ -123,7 +137,7 @@ class DenoisePlan:
     # ------------------------------------------------------------------ conditioning
     def encode_images(self, images):
         img = _f32c(images, self.device).reshape(-1, 3, 96, 96)
-        out = torch.empty((img.shape[0], 128), device=self.device, dtype=torch.float32)
+        out = torch.empty((img.shape[0], self.feat_dim), device=self.device, dtype=torch.float32)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.spdm_encode_images(self._h, _ptr(img), _ptr(out), img.shape[0], _stream()))
         return out

@@ -98,6 +98,7 @@ class _UNetBase(nn.Module):
         self.precision = "bf16"   # "bf16": tcgen05 implicit-GEMM path; "fp32": CUDA-core parity path
         self.batch_max = 0        # 0 = grow on demand
         self.split = 1            # sub-batches run concurrently inside the graphed sampling loop
+        self.encoder = "autoencoder"   # vision encoder the plan carries: "autoencoder" | "resnet18" (set by the Diffusion_DDPM owner)
         self._plan = None
         self._plan_key = None
         self._weights_tag = None
@@ -137,7 +138,7 @@ class _UNetBase(nn.Module):
                 T, cd = old.obs_horizon, old.cond_dim
         inpaint_rows = 0 if inpaint_rows is None else int(inpaint_rows)
         graph_steps = 1 if graph_steps is None else int(graph_steps)
-        key = (self.precision, rows, dim, T, cd, inpaint_rows, graph_steps, str(dev), self.split)
+        key = (self.precision, rows, dim, T, cd, inpaint_rows, graph_steps, str(dev), self.split, self.encoder)
         if old is None or self._plan_key != key or old.batch_max < B:
             cap = max(int(B), self.batch_max)
             if old is not None:
@@ -146,7 +147,7 @@ class _UNetBase(nn.Module):
                 old.close()
             self._plan = DenoisePlan(attention=self._attention, precision=self.precision, batch_max=cap, rows=rows, dim=dim,
                                      obs_horizon=T, cond_dim=cd, inpaint_rows=inpaint_rows, time_dim=self.time_dim, device=dev,
-                                     graph_steps=graph_steps, split=self.split, simple=self._simple)
+                                     graph_steps=graph_steps, split=self.split, simple=self._simple, encoder=self.encoder)
             self._plan_key = key
             self._weights_tag = None
         tag = self._tag()
@@ -260,6 +261,7 @@ class UNet(_UNetBase):
         self.precision = "fp32"
         self.batch_max = 0
         self.split = 1
+        self.encoder = "autoencoder"
         self._plan = None
         self._plan_key = None
         self._weights_tag = None
@@ -284,3 +286,53 @@ class UNet(_UNetBase):
                                       "train the FiLM U-Nets (model='UNet_Film' / 'UNet_FilmnoAttention') natively")
         self.precision = "fp32"
         return super().forward(x, t, y)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ResNet18 with GroupNorm: `VisionEncoder()` of the reference (models/Unet_FiLmLayer.py:316-386)
+# ---------------------------------------------------------------------------------------------------------------------
+class _GNBasicBlock(nn.Module):
+    """Parameters of torchvision's BasicBlock after replace_bn_with_gn (models/Unet_FiLmLayer.py:368-380): conv1 / bn1 / conv2 / bn2
+    (+ downsample.{0,1}); `bnX` are GroupNorm(C // 16, C) -- the attribute names stay those of the replaced BatchNorm2d."""
+
+    def __init__(self, inplanes, planes, stride=1):
+        super().__init__()
+        self.conv1 = nn.Conv2d(inplanes, planes, kernel_size=3, stride=stride, padding=1, bias=False)
+        self.bn1 = nn.GroupNorm(planes // 16, planes)
+        self.relu = nn.ReLU(inplace=True)
+        self.conv2 = nn.Conv2d(planes, planes, kernel_size=3, stride=1, padding=1, bias=False)
+        self.bn2 = nn.GroupNorm(planes // 16, planes)
+        self.downsample = None
+        if stride != 1 or inplanes != planes:
+            self.downsample = nn.Sequential(nn.Conv2d(inplanes, planes, kernel_size=1, stride=stride, bias=False),
+                                            nn.GroupNorm(planes // 16, planes))
+
+
+class ResNet18GN(nn.Module):
+    """`VisionEncoder()` = get_resnet('resnet18') + replace_bn_with_gn (models/Unet_FiLmLayer.py:316-386): same sub-module names,
+    parameter shapes and construction order as torchvision.models.resnet18 with fc = Identity, so its state_dict (and a checkpoint of
+    it) loads with strict=True.  A parameter container: `forward` runs the encoder in libspdm (convs as tcgen05 GEMMs over patch rows).
+    (N, 3, 96, 96) -> (N, 512); inference only."""
+    feat_dim = 512
+
+    def __init__(self):
+        super().__init__()
+        self.conv1 = nn.Conv2d(3, 64, kernel_size=7, stride=2, padding=3, bias=False)
+        self.bn1 = nn.GroupNorm(64 // 16, 64)
+        self.relu = nn.ReLU(inplace=True)
+        self.maxpool = nn.MaxPool2d(kernel_size=3, stride=2, padding=1)
+        self.layer1 = nn.Sequential(_GNBasicBlock(64, 64), _GNBasicBlock(64, 64))
+        self.layer2 = nn.Sequential(_GNBasicBlock(64, 128, 2), _GNBasicBlock(128, 128))
+        self.layer3 = nn.Sequential(_GNBasicBlock(128, 256, 2), _GNBasicBlock(256, 256))
+        self.layer4 = nn.Sequential(_GNBasicBlock(256, 512, 2), _GNBasicBlock(512, 512))
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.fc = nn.Identity()
+        for m in self.modules():   # torchvision's initialisation (resnet.py): kaiming_normal_ for the convs, GroupNorm 1 / 0
+            if isinstance(m, nn.Conv2d):
+                nn.init.kaiming_normal_(m.weight, mode="fan_out", nonlinearity="relu")
+        self._owner = None
+
+    def forward(self, img):
+        if self._owner is None:
+            raise RuntimeError("ResNet18GN is driven through its Diffusion_DDPM owner")
+        return self._owner()._plan().encode_images(img)

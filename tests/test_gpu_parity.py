@@ -587,3 +587,53 @@ def test_tf32_path_forward_and_final_trajectory(spdm, attention, B):
     got = plan.sample(x_T, inpaint=inp.reshape(B, -1))
     assert rel(got, want) < BF16_FINAL_TOL
     plan.close()
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 3e-2)])
+def test_resnet18gn_encoder(spdm, golden_dir, precision, tol):
+    """`vision_encoder='resnet18'`: the ResNet18-GroupNorm `VisionEncoder()` of models/Unet_FiLmLayer.py:316-386 --
+    features against the reference module's own output (golden), conditioning vector (cond_dim = 519) against the oracle, and a
+    sampling call through `Diffusion_DDIM(vision_encoder='resnet18', observation_dim=519)`."""
+    from oracle import resnet_ref
+    g = _golden(golden_dir, "resnet18gn")
+    seed = int(g["seed"])
+    img = torch.rand((5, 3, 96, 96), generator=torch.Generator().manual_seed(seed + 100))
+    rsd = fixtures.make_resnet_weights(seed=seed)
+    plan = spdm.DenoisePlan(attention=False, precision=precision, batch_max=4, cond_dim=519, encoder="resnet18", graph_steps=0)
+    plan.load_encoder_state_dict(rsd)
+    out = plan.encode_images(img)
+    assert tuple(out.shape) == (5, 512)
+    assert rel(out, g["out"]) < tol
+    # a frame count that is not a multiple of the 128-row tile and spans two chunks gives the same rows
+    out2 = plan.encode_images(img.repeat(58, 1, 1, 1))     # 290 frames = one full chunk of 256 + a ragged one
+    # (the GroupNorm statistics are accumulated with shared-memory atomics: the summation order, and with it a bf16 rounding here and
+    # there, depends on the launch -- hence not bit-identical on the bf16 path)
+    assert tuple(out2.shape) == (290, 512) and rel(out2, out.repeat(58, 1)) < (1e-5 if precision == "fp32" else 1e-2)
+    plan.close()
+    # wrapper: cond_dim 519, FiLM U-Net conditioned on ResNet features
+    torch.manual_seed(0)
+    with pytest.raises(ValueError):
+        spdm.Diffusion_DDIM(noise_steps=1000, obs_horizon=10, pred_horizon=30, observation_dim=135, prediction_dim=5, model="UNet_Film",
+                            vision_encoder="resnet18", inpaint_horizon=1)
+    m = spdm.Diffusion_DDIM(noise_steps=1000, obs_horizon=10, pred_horizon=30, observation_dim=519, prediction_dim=5,
+                            model="UNet_FilmnoAttention", vision_encoder="resnet18", inpaint_horizon=1).cuda().eval()
+    assert set(m.vision_encoder.state_dict()) == set(rsd)
+    m.vision_encoder.load_state_dict(rsd, strict=True)
+    sd = fixtures.make_unet_weights(attention=False, cond_dim=5190, seed=3)
+    m.noise_estimator.load_state_dict(sd, strict=True)
+    m.configure(precision=precision, graph_steps=2).use_ddim(4)
+    batch = fixtures.make_batch(2, seed=77)
+    cond = m.prepare_obs_cond_vectors({k: v.cuda() for k, v in batch.items()})
+    with torch.no_grad():
+        feat = resnet_ref.encode(rsd, batch["image"].flatten(end_dim=1)).reshape(2, 10, 512)
+        want_cond = torch.cat([batch["position"], batch["action"], batch["velocity"], feat], dim=-1)
+    assert tuple(cond.shape) == (2, 10, 519) and rel(cond, want_cond) < tol
+    x_T = fixtures.make_xT(2)
+    got = m.sample({k: v.clone() for k, v in batch.items()}, batched=True, x_T=x_T.cuda())
+    with torch.no_grad():
+        inp = unet_ref.inpaint_vector(batch, 1).unsqueeze(1)
+        want = sampler_ref.sample_ref(sd, sampler_ref.make_scheduler("ddim", 4), 4, x_T, want_cond.unsqueeze(1), inp, 1, attention=False)
+    assert rel(got, want) < (5e-4 if precision == "fp32" else BF16_FINAL_TOL)
+    m.train()
+    with pytest.raises(NotImplementedError):
+        m.process_single_batch({k: torch.cat([v] * 4, dim=1).cuda() for k, v in batch.items()})

@@ -175,3 +175,21 @@ def test_simple_unet_oracle_vs_reference_golden(golden_dir):
         out1 = simple_unet_ref.unet_forward(sd, g["x"], torch.tensor([17]), g["y"])
     assert float((out - g["out"]).abs().max()) <= 1e-6 * float(g["out"].abs().max())
     assert float((out1 - g["out_t1"]).abs().max()) <= 1e-6 * float(g["out_t1"].abs().max())
+
+
+def test_resnet18gn_oracle_vs_reference_golden(golden_dir):
+    """oracle/resnet_ref.py against the reference's own `VisionEncoder()` (models/Unet_FiLmLayer.py:316-386; golden written by
+    oracle/make_golden.py::golden_resnet18gn): 512 features of 5 frames."""
+    import os
+    import numpy as np
+    from oracle import resnet_ref
+    g = {k: torch.from_numpy(v) for k, v in np.load(os.path.join(golden_dir, "resnet18gn.npz")).items()}
+    seed = int(g["seed"])
+    img = torch.rand((5, 3, 96, 96), generator=torch.Generator().manual_seed(seed + 100))
+    f = img.flatten(1)
+    fp = torch.stack([f.mean(1), f.std(1), f.abs().max(1).values, f[:, 0], f[:, -1]], dim=1)
+    assert torch.allclose(fp, g["img_fingerprint"]), "the regenerated frames differ from the ones the golden was made with"
+    sd = fixtures.make_resnet_weights(seed=seed)
+    with torch.no_grad():
+        out = resnet_ref.encode(sd, img)
+    assert float((out - g["out"]).abs().max()) <= 1e-5 * float(g["out"].abs().max())
