@@ -1440,6 +1440,54 @@ void launch_mish_bwd(const float* dy, const float* x, float* dx, long long n, cu
   mish_bwd_kernel<<<cdiv(n, 256), 256, 0, s>>>(dy, x, dx, n);
   COUNT_LAUNCH();
 }
+namespace {
+// FiLM Linears on the tensor cores (bf16 training): operand packs and the Mish on either side of the GEMMs.
+//   wf16 [1792][GP]  = the six (2C, G) PyTorch weights stacked, columns padded with zeros to GP = ceil64(G): B operand of the forward GEMM
+//   wb16 [GP][1792]  = its transpose: B operand of the data-gradient GEMM
+__global__ void film_pack16_kernel(const float* __restrict__ src, bf16* __restrict__ wf, bf16* __restrict__ wb, int C2, int G, int GP, int off) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)C2 * G) return;
+  const int j = (int)(i / G), g = (int)(i - (long long)j * G);
+  const bf16 v = __float2bfloat16_rn(src[i]);
+  wf[(size_t)(off + j) * GP + g] = v;
+  wb[(size_t)g * SPDM_FILM_WIDTH + off + j] = v;
+}
+__global__ void mish_pad_bf16_kernel(const float* __restrict__ cond, bf16* __restrict__ out, int B, int G, int GP, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int b = (int)(i / GP), g = (int)(i - (long long)b * GP);
+  float y = 0.f;
+  if (b < B && g < G) {
+    const float x = cond[(size_t)b * G + g];
+    const float sp = x > 20.f ? x : log1pf(expf(x));
+    y = x * tanhf(sp);
+  }
+  out[i] = __float2bfloat16_rn(y);
+}
+__global__ void mish_bwd_bf16_kernel(const bf16* __restrict__ dy, int ld_dy, const float* __restrict__ x, float* __restrict__ dx, int G, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int b = (int)(i / G), g = (int)(i - (long long)b * G);
+  const float v = x[i];
+  const float sp = v > 20.f ? v : log1pf(expf(v));
+  const float th = tanhf(sp);
+  const float sig = 1.f / (1.f + expf(-v));
+  dx[i] = __bfloat162float(dy[(size_t)b * ld_dy + g]) * (th + v * (1.f - th * th) * sig);
+}
+}  // namespace
+void launch_film_pack16(const float* src, bf16* wf, bf16* wb, int C2, int G, int GP, int off, cudaStream_t s) {
+  film_pack16_kernel<<<cdiv((long long)C2 * G, 256), 256, 0, s>>>(src, wf, wb, C2, G, GP, off);
+}
+void launch_mish_pad_bf16(const float* cond, bf16* out, int B, int Bpad, int G, int GP, cudaStream_t s) {
+  const long long total = (long long)Bpad * GP;
+  mish_pad_bf16_kernel<<<cdiv(total, 256), 256, 0, s>>>(cond, out, B, G, GP, total);
+  COUNT_LAUNCH();
+}
+void launch_mish_bwd_bf16(const bf16* dy, int ld_dy, const float* x, float* dx, int B, int G, cudaStream_t s) {
+  const long long n = (long long)B * G;
+  mish_bwd_bf16_kernel<<<cdiv(n, 256), 256, 0, s>>>(dy, ld_dy, x, dx, G, n);
+  COUNT_LAUNCH();
+}
 void launch_gather_feat_grad(const float* d_cond, float* d_feat, int B, int T, int cond_dim, cudaStream_t s) {
   const long long total = (long long)B * T * (cond_dim - 7);
   gather_feat_grad_kernel<<<cdiv(total, 256), 256, 0, s>>>(d_cond, d_feat, total, cond_dim);
@@ -1855,8 +1903,10 @@ __global__ void __launch_bounds__(192) enc_conv1_fwd_kernel(const void* __restri
 // register tile of one input channel and one eighth of the strip's pixels: 1 LDS.64 + 4 LDS per 8 FMAs.
 // thread = pixel group pg (8) x input channel c (3) x output pair op (8); partial tiles are folded through shared memory once,
 // at the end of the kernel, then one atomicAdd per weight per block.
-__global__ void __launch_bounds__(192) enc_conv1_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ d1, float* __restrict__ dw1,
-                                                              float* __restrict__ db1, int n_strips, int T, long long bstride) {
+// `act` (optional): the conv1 output c1p; d1 is then the gradient of the POST-ReLU output and the ReLU mask (act > 0) is applied
+// on load -- saves the separate relu_mask pass over d1 (read d1 + read c1p + write d1, ~175 us at 5120 frames).
+__global__ void __launch_bounds__(192) enc_conv1_wgrad_kernel(const float* __restrict__ img, const bf16* __restrict__ d1, const bf16* __restrict__ act,
+                                                              float* __restrict__ dw1, float* __restrict__ db1, int n_strips, int T, long long bstride) {
   __shared__ __align__(16) float s_in[24 * 100];
   constexpr int SDS = 193;                        // padded row stride of s_d: [16 channels][192 raster pixels]
   __shared__ __align__(16) float s_d[16 * SDS];
@@ -1870,13 +1920,24 @@ __global__ void __launch_bounds__(192) enc_conv1_wgrad_kernel(const float* __res
     __syncthreads();
     enc_stage_strip(img + (size_t)(frame / T) * bstride + (size_t)(frame % T) * 3 * 96 * 96, r3, s_in, tid);
     {
-      float t8[8];
+      float t8[8], a8[8];
       const bf16* src = d1 + ((size_t)strip * 192 + tid) * 16;
+      const bf16* asrc = act ? act + ((size_t)strip * 192 + tid) * 16 : nullptr;
       float* dst = s_d + my_yl * 48 + my_x;   // channel-major: a warp's stores of one channel hit (nearly) distinct banks
       load8(src, t8);
+      if (asrc) {
+        load8(asrc, a8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t8[i] = a8[i] > 0.f ? t8[i] : 0.f;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) dst[i * SDS] = t8[i];
       load8(src + 8, t8);
+      if (asrc) {
+        load8(asrc + 8, a8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) t8[i] = a8[i] > 0.f ? t8[i] : 0.f;
+      }
 #pragma unroll
       for (int i = 0; i < 8; ++i) dst[(8 + i) * SDS] = t8[i];
     }
@@ -2006,10 +2067,10 @@ void launch_enc_conv1_fwd_u8(const uint8_t* img_hwc, const float* w1, const floa
   enc_conv1_fwd_kernel<true><<<n * 12, 192, 0, s>>>(img_hwc, w1, b1, c1p, 1, 0);
   COUNT_LAUNCH();
 }
-void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float* db1, int n, int T, long long bstride, cudaStream_t s) {
+void launch_enc_conv1_wgrad(const float* img, const bf16* d1, const bf16* act, float* dw1, float* db1, int n, int T, long long bstride, cudaStream_t s) {
   int grid = n * 12;
   if (grid > 148 * 8) grid = 148 * 8;
-  enc_conv1_wgrad_kernel<<<grid, 192, 0, s>>>(img, d1, dw1, db1, n * 12, T, bstride);
+  enc_conv1_wgrad_kernel<<<grid, 192, 0, s>>>(img, d1, act, dw1, db1, n * 12, T, bstride);
   COUNT_LAUNCH();
 }
 void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, float* colsum64, cudaStream_t s) {

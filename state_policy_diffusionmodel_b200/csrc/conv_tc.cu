@@ -490,6 +490,60 @@ __device__ __forceinline__ void st_dsmem_v2(uint32_t addr, float a, float b) {
 // 320 threads: warp 0 TMA, warp 1 MMA, warps 2..9 dump the accumulator (two warps per TMEM lane quarter, half of the columns each);
 // the reduction and the apply phase are walked by all 320 threads.
 constexpr int CL_THREADS = 320;
+
+// Sum column slice `ks` of the tile over its KS K-slice partials (the own one from local shared memory, the others over DSMEM),
+// leave the reduced slice in `blk`, and put per-warp-run (sum, sumsq) partials into s_part.  A remote load costs ~1000 cycles of
+// latency plus ~230 cycles per 16 bytes x 320 threads (profiles/r02_chain_phase_cycles.txt), so every thread keeps KS * U = 16
+// of them in flight whatever the split is (was 2 * KS: a 2-way split paid the latency three times per slice).
+template <int KS, int U>
+__device__ __forceinline__ void cl_reduce_slice(float* blk, const uint32_t* src, int ks, int n4, int lw4, int W4, int RS, int tid, int lane,
+                                                float (*s_part)[2]) {
+#pragma unroll 1
+  for (int i0 = tid; i0 < n4; i0 += U * CL_THREADS) {
+    float4 v[KS][U];
+    int off[U];
+    bool ok[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int i = i0 + u * CL_THREADS;
+      ok[u] = i < n4;                              // n4 is a multiple of 32: warp-uniform
+      const int row = i >> lw4, c4 = i & (W4 - 1);
+      off[u] = ok[u] ? row * RS + c4 * 4 : 0;
+    }
+#pragma unroll
+    for (int sp = 0; sp < KS; ++sp) {
+      if (sp == ks) {   // this CTA's own partial: a plain shared-memory load (ld.shared::cluster is slow even to oneself)
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[sp][u] = ok[u] ? *reinterpret_cast<const float4*>(blk + off[u]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      } else {
+#pragma unroll
+        for (int u = 0; u < U; ++u) v[sp][u] = ok[u] ? ld_dsmem_v4(src[sp] + (uint32_t)off[u] * 4u) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      float4 acc = v[0][u];
+#pragma unroll
+      for (int sp = 1; sp < KS; ++sp) { acc.x += v[sp][u].x; acc.y += v[sp][u].y; acc.z += v[sp][u].z; acc.w += v[sp][u].w; }
+      if (ok[u]) *reinterpret_cast<float4*>(blk + off[u]) = acc;
+      float ps = (acc.x + acc.y) + (acc.z + acc.w);
+      float pq = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, acc.w * acc.w)));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { ps += __shfl_xor_sync(0xffffffffu, ps, o); pq += __shfl_xor_sync(0xffffffffu, pq, o); }
+      // the 32 float4 of a warp are 128 / Wd whole rows of ONE sample (rps >= 4 rows, aligned): slot = first index / 32
+      if (lane == 0 && ok[u]) { const int q = (i0 + u * CL_THREADS) >> 5; s_part[q][0] = ps; s_part[q][1] = pq; }
+    }
+  }
+}
+__device__ __forceinline__ void cl_reduce_dispatch(int cl_ks, float* blk, const uint32_t* src, int ks, int n4, int lw4, int W4, int RS, int tid,
+                                                   int lane, float (*s_part)[2]) {
+  switch (cl_ks) {
+    case 1: cl_reduce_slice<1, 8>(blk, src, ks, n4, lw4, W4, RS, tid, lane, s_part); break;
+    case 2: cl_reduce_slice<2, 8>(blk, src, ks, n4, lw4, W4, RS, tid, lane, s_part); break;
+    case 4: cl_reduce_slice<4, 4>(blk, src, ks, n4, lw4, W4, RS, tid, lane, s_part); break;
+    default: cl_reduce_slice<8, 2>(blk, src, ks, n4, lw4, W4, RS, tid, lane, s_part); break;
+  }
+}
 template <int BLOCK_N, int STAGES>
 __global__ void __launch_bounds__(CL_THREADS, 1)
 conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
@@ -652,46 +706,7 @@ conv_tc_cluster_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_c
     uint32_t src[8];
 #pragma unroll
     for (int sp = 0; sp < 8; ++sp) src[sp] = sp < p.cl_ks ? mapa_u32(blk_addr, (uint32_t)(sp * p.n_tiles + nt)) : 0u;
-    // (tried: keeping the per-run sums in registers and doing all warp reductions after a fully unrolled loop -- 198 registers,
-    //  reduce phase 6.7-10 K cycles instead of 4.6-8 K: the phase is bound by the remote loads, not by the shuffle chains)
-#pragma unroll 1
-    for (int i0 = tid; i0 < n4; i0 += 2 * CL_THREADS) {   // 2 * cl_ks remote 16-byte loads in flight per thread
-      float4 v[8][2];
-      int off[2];
-      bool ok[2];
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int i = i0 + u * CL_THREADS;
-        ok[u] = i < n4;
-        const int row = i >> lw4, c4 = i & (W4 - 1);
-        off[u] = ok[u] ? row * RS + c4 * 4 : 0;
-      }
-#pragma unroll
-      for (int sp = 0; sp < 8; ++sp)
-        if (sp < p.cl_ks) {
-          if (sp == ks) {   // this CTA's own partial: a plain shared-memory load (ld.shared::cluster is slow even to oneself)
-            v[sp][0] = *reinterpret_cast<const float4*>(blk + off[0]);
-            v[sp][1] = *reinterpret_cast<const float4*>(blk + off[1]);
-          } else {
-            v[sp][0] = ld_dsmem_v4(src[sp] + (uint32_t)off[0] * 4u);
-            v[sp][1] = ld_dsmem_v4(src[sp] + (uint32_t)off[1] * 4u);
-          }
-        }
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        float4 acc = v[0][u];
-#pragma unroll
-        for (int sp = 1; sp < 8; ++sp)
-          if (sp < p.cl_ks) { acc.x += v[sp][u].x; acc.y += v[sp][u].y; acc.z += v[sp][u].z; acc.w += v[sp][u].w; }
-        if (ok[u]) *reinterpret_cast<float4*>(blk + off[u]) = acc;   // n4 is a multiple of 32: ok[u] is warp-uniform
-        float ps = (acc.x + acc.y) + (acc.z + acc.w);
-        float pq = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, acc.w * acc.w)));
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { ps += __shfl_xor_sync(0xffffffffu, ps, o); pq += __shfl_xor_sync(0xffffffffu, pq, o); }
-        // the 32 float4 of a warp are 128 / Wd whole rows of ONE sample (rps >= 4 rows, aligned): slot = first index / 32
-        if (lane == 0 && ok[u]) { const int q = (i0 + u * CL_THREADS) >> 5; s_part[q][0] = ps; s_part[q][1] = pq; }
-      }
-    }
+    cl_reduce_dispatch(p.cl_ks, blk, src, ks, n4, lw4, W4, RS, tid, lane, s_part);
     __syncthreads();
     if (tid < ns) {   // sample tid: slots [tid * sps, (tid + 1) * sps), summed in a fixed order, pushed to every CTA of the cluster
       const int sps = (rps * W4) >> 5;
@@ -818,6 +833,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_chain_kernel(const ChainPa
   __shared__ float s_mr[32][2];
   __shared__ __align__(16) float s_par[3][128];
   __shared__ __align__(16) float s_film[4096];
+  __shared__ long long ts_log[16][9];              // SPDM_CL_TIMING only
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -1000,43 +1016,7 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_chain_kernel(const ChainPa
       uint32_t src[8];
 #pragma unroll
       for (int sp = 0; sp < 8; ++sp) src[sp] = sp < cl_ks ? mapa_u32(blk_addr, (uint32_t)(sp * n_tiles + nt)) : 0u;
-#pragma unroll 1
-      for (int i0 = tid; i0 < n4; i0 += 2 * CL_THREADS) {
-        float4 v[8][2];
-        int off[2];
-        bool ok[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const int i = i0 + u * CL_THREADS;
-          ok[u] = i < n4;
-          const int row = i >> lw4, c4 = i & (W4 - 1);
-          off[u] = ok[u] ? row * RS + c4 * 4 : 0;
-        }
-#pragma unroll
-        for (int sp = 0; sp < 8; ++sp)
-          if (sp < cl_ks) {
-            if (sp == ks) {
-              v[sp][0] = *reinterpret_cast<const float4*>(blk + off[0]);
-              v[sp][1] = *reinterpret_cast<const float4*>(blk + off[1]);
-            } else {
-              v[sp][0] = ld_dsmem_v4(src[sp] + (uint32_t)off[0] * 4u);
-              v[sp][1] = ld_dsmem_v4(src[sp] + (uint32_t)off[1] * 4u);
-            }
-          }
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          float4 acc = v[0][u];
-#pragma unroll
-          for (int sp = 1; sp < 8; ++sp)
-            if (sp < cl_ks) { acc.x += v[sp][u].x; acc.y += v[sp][u].y; acc.z += v[sp][u].z; acc.w += v[sp][u].w; }
-          if (ok[u]) *reinterpret_cast<float4*>(blk + off[u]) = acc;
-          float ps = (acc.x + acc.y) + (acc.z + acc.w);
-          float pq = fmaf(acc.x, acc.x, fmaf(acc.y, acc.y, fmaf(acc.z, acc.z, acc.w * acc.w)));
-#pragma unroll
-          for (int o = 16; o > 0; o >>= 1) { ps += __shfl_xor_sync(0xffffffffu, ps, o); pq += __shfl_xor_sync(0xffffffffu, pq, o); }
-          if (lane == 0 && ok[u]) { const int q = (i0 + u * CL_THREADS) >> 5; s_part[q][0] = ps; s_part[q][1] = pq; }
-        }
-      }
+      cl_reduce_dispatch(cl_ks, blk, src, ks, n4, lw4, W4, RS, tid, lane, s_part);
       __syncthreads();
       if (tid < ns) {
         const int sps = (rps * W4) >> 5;
@@ -1110,11 +1090,19 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_chain_kernel(const ChainPa
       fence_proxy_async_all();
       cluster_sync_all();
     }
-    if ((p.dbg & 2048) && blockIdx.x == 0 && threadIdx.x == 64)
-      printf("spdm chain timing layer %d (%d->%d bn %d ks %d, %d k-steps): const %lld mainloop-wait %lld dump %lld sync1 %lld reduce %lld sync2 %lld apply %lld endsync %lld total %lld\n",
-             l, Cin, Cout, bn, cl_ks, it_end - it_begin, ts[1] - ts[0], ts[2] - ts[1], ts[3] - ts[2], ts[4] - ts[3], ts[5] - ts[4], ts[6] - ts[5],
-             ts[7] - ts[6], clock64() - ts[7], clock64() - ts[0]);
+    if ((p.dbg & 2048) && blockIdx.x == 0 && threadIdx.x == 64 && l < 16) {   // logged, printed after the last layer (a printf here would delay this warp into the next layer's phases)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) ts_log[l][i] = ts[i];
+      ts_log[l][8] = clock64();
+    }
   }
+  if ((p.dbg & 2048) && blockIdx.x == 0 && threadIdx.x == 64)
+    for (int l = 0; l < p.n_layers && l < 16; ++l) {
+      const ChainLayer* L = p.layers + l;
+      const long long* t = ts_log[l];
+      printf("spdm chain timing layer %d (%d->%d bn %d ks %d): const %lld mainloop-wait %lld dump %lld sync1 %lld reduce %lld sync2 %lld apply %lld endsync %lld total %lld\n",
+             l, L->Cin, L->Cout, L->bn, L->ks, t[1] - t[0], t[2] - t[1], t[3] - t[2], t[4] - t[3], t[5] - t[4], t[6] - t[5], t[7] - t[6], t[8] - t[7], t[8] - t[0]);
+    }
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();

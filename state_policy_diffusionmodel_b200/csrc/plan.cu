@@ -208,6 +208,7 @@ namespace {
 long long total_launches() { return kernels_launch_count() + tc_launch_count() + bwd_launch_count() + wgrad_tc_launch_count_value; }
 
 float* train_film_wT(spdm_plan* p);  // training-only transposed weight copies (null when training is not enabled)
+void train_film_weight_loaded(spdm_plan* p, const float* src, int off, int C2, cudaStream_t s);
 float* train_enc_wlT(spdm_plan* p);
 void train_destroy(spdm_plan* p);
 
@@ -345,8 +346,7 @@ void register_weights(spdm_plan* p) {
       p->loaders[wn] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
         check_shape(wn, shape, ndim, {C2, G});
         launch_pack_linear_f32(src, dst, C2, G, SPDM_FILM_WIDTH, off, s);
-        if (float* wt = train_film_wT(p))  // [1792][G]: rows off.. = this stage's (2C, G) weight as stored by PyTorch
-          CUDA_OK(cudaMemcpyAsync(wt + (size_t)off * G, src, (size_t)C2 * G * sizeof(float), cudaMemcpyDeviceToDevice, s));
+        train_film_weight_loaded(p, src, off, C2, s);  // training-only copies (transposed fp32 / bf16 tensor-core operands)
       };
       reg_vec(p, n + ".cond_encoder.2.bias", p->film_b + off, C2, p->missing_unet);
     }

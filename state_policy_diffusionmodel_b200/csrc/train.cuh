@@ -92,7 +92,7 @@ void launch_enc_conv1_fwd(const float* img, const float* w1, const float* b1, bf
 // the same from uint8 HWC frames (n, 96, 96, 3), decoded x / 255 while the input strip is staged
 void launch_enc_conv1_fwd_u8(const uint8_t* img_hwc, const float* w1, const float* b1, bf16* c1p, int n, cudaStream_t s);
 void launch_decode_u8_hwc(const uint8_t* img, float* out, long long frames, int H, int W, cudaStream_t s);  // data_kernels.cu
-void launch_enc_conv1_wgrad(const float* img, const bf16* d1, float* dw1, float* db1, int n, int T, long long bstride, cudaStream_t s);
+void launch_enc_conv1_wgrad(const float* img, const bf16* d1, const bf16* act, float* dw1, float* db1, int n, int T, long long bstride, cudaStream_t s);  // act != null: ReLU mask applied on load
 // over [rows][64] bf16; colsum64 (or null) += column sums of the masked gradient
 void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, float* colsum64, cudaStream_t s);
 void launch_enc_pack_w2(const float* w2, bf16* w2p, bf16* w2pT, cudaStream_t s);  // (32,16,2,2) -> block-diagonal [64][128] and its transpose
@@ -116,6 +116,10 @@ void launch_adam(float* p, float* g, float* m, float* v, long long n, float lr, 
 
 // packed conv gradient [tap][Cout][Cin] -> PyTorch (Cout, Cin, 3, 3)
 void launch_unpack_conv_grad(const float* packed, float* dst, int Cout, int Cin, cudaStream_t s);
+// FiLM Linears on the tensor cores (bf16 training)
+void launch_film_pack16(const float* src, bf16* wf, bf16* wb, int C2, int G, int GP, int off, cudaStream_t s);
+void launch_mish_pad_bf16(const float* cond, bf16* out, int B, int Bpad, int G, int GP, cudaStream_t s);       // [Bpad][GP], zero padded
+void launch_mish_bwd_bf16(const bf16* dy, int ld_dy, const float* x, float* dx, int B, int G, cudaStream_t s);
 long long bwd_launch_count();
 extern long long wgrad_tc_launch_count_value;
 

@@ -17,6 +17,9 @@ struct TrainState {
   // arena: buffers are handed out in the same order every step, so pointers (and the TMA maps built on them) are stable
   std::vector<void*> bufs; std::vector<size_t> buf_bytes; size_t cur = 0; int arena_B = -1;
   float* film_wT = nullptr;   // [1792][G]
+  bf16* film_wf16 = nullptr;  // bf16 path: [1792][GP] forward / [GP][1792] data-gradient operands of the six FiLM Linears as ONE GEMM each
+  bf16* film_wb16 = nullptr; int GP = 0;
+  bool film_simt = false;     // SPDM_FILM_SIMT=1: CUDA-core fp32 FiLM Linears on the bf16 path too (A/B switch)
   float* enc_wlT = nullptr;   // [128][9216 hwc]
   float* packed = nullptr; size_t packed_elems = 0;  // bf16 path: conv weight gradients as [tap][Cout][Cin]
   std::map<std::string, size_t> packed_off;
@@ -43,6 +46,13 @@ struct TrainState {
 
 namespace {
 float* train_film_wT(spdm_plan* p) { return p->tr ? p->tr->film_wT : nullptr; }
+void train_film_weight_loaded(spdm_plan* p, const float* src, int off, int C2, cudaStream_t s) {
+  if (!p->tr) return;
+  TrainState* tr = p->tr;
+  if (tr->film_wT)  // [1792][G]: rows off.. = this stage's (2C, G) weight as stored by PyTorch
+    CUDA_OK(cudaMemcpyAsync(tr->film_wT + (size_t)off * p->G, src, (size_t)C2 * p->G * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  if (tr->film_wf16) launch_film_pack16(src, tr->film_wf16, tr->film_wb16, C2, p->G, tr->GP, off, s);
+}
 float* train_enc_wlT(spdm_plan* p) { return p->tr ? p->tr->enc_wlT : nullptr; }
 void train_destroy(spdm_plan* p) {
   if (!p->tr) return;
@@ -456,6 +466,12 @@ extern "C" int spdm_train_enable(spdm_plan* p) {
   }
   if (p->bf16_mode) tr->packed = p->alloc<float>(tr->packed_elems);
   if (p->G > 0) tr->film_wT = p->alloc<float>((size_t)SPDM_FILM_WIDTH * p->G);
+  if (const char* e = getenv("SPDM_FILM_SIMT")) tr->film_simt = atoi(e) != 0;
+  if (p->G > 0 && p->bf16_mode && !tr->film_simt) {
+    tr->GP = ((p->G + 63) / 64) * 64;
+    tr->film_wf16 = p->alloc<bf16>((size_t)SPDM_FILM_WIDTH * tr->GP);   // zero-filled: the padding columns / rows stay zero
+    tr->film_wb16 = p->alloc<bf16>((size_t)tr->GP * SPDM_FILM_WIDTH);
+  }
   tr->enc_wlT = p->alloc<float>((size_t)128 * 9216);
   tr->loss_dev = p->alloc<float>(1);
   if (const char* e = getenv("SPDM_ENC_SIMT")) tr->enc_simt = atoi(e) != 0;
@@ -606,7 +622,22 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     CUDA_OK(cudaStreamWaitEvent(s, tr->ev_packs, 0));
     tr->packs_pending = false;
   }
-  compute_film(p, B, s);
+  const bool film_tc = tr->film_wf16 != nullptr;
+  const int GP = tr->GP;
+  const int Bp = ((B + 127) / 128) * 128;                    // rows of the FiLM GEMMs (whole 128-row tiles)
+  const int Bf = ((B + p->bm - 1) / p->bm) * p->bm;          // rows of d_film (Fwd::Bpad)
+  bf16* cond_mish16 = nullptr;
+  if (film_tc) {
+    // the six FiLM Linears as one tensor-core GEMM [Bp][GP] x [GP][1792] (fp32: 160 us on the CUDA cores at batch 512)
+    cond_mish16 = H16((size_t)Bp * GP);
+    bf16* film16 = H16((size_t)Bp * SPDM_FILM_WIDTH);
+    launch_mish_pad_bf16(p->cond, cond_mish16, B, Bp, p->G, GP, s);
+    tc_flat("film", cond_mish16, GP, tr->film_wf16, GP, SPDM_FILM_WIDTH, Bp, film16, SPDM_FILM_WIDTH, p->film_b, EPI_BIAS);
+    launch_cast_f32(film16, p->film, (long long)B * SPDM_FILM_WIDTH, s);
+    p->have_cond = true;
+  } else {
+    compute_film(p, B, s);
+  }
   // ---- time embedding rows (per sample) ----
   launch_temb(reinterpret_cast<const long long*>(t), B, p->inv_freq, p->temb_w, p->temb_b, p->temb_call, p->cfg.time_dim, s);
   float* silu_pe = F((size_t)B * p->cfg.time_dim);
@@ -624,22 +655,41 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     return tr->grads + it->second.off;
   };
   // ---- FiLM Linears, d obs_cond, vision encoder ----
-  for (const StageInfo& st : kStages) {
-    WgradArgs a{};
-    a.x = p->cond_mish; a.ld_x = p->G; a.dy = d_film + st.film_off; a.ld_dy = SPDM_FILM_WIDTH; a.M = B; a.Cin = p->G; a.Cout = 2 * st.cout;
-    a.H = 1; a.W = 1; a.taps = 1; a.dw = G(std::string(st.name) + ".cond_encoder.2.weight");
-    launch_wgrad_simt<float, float>(a, s);
-    launch_colsum<float>(d_film + st.film_off, SPDM_FILM_WIDTH, B, 2 * st.cout, G(std::string(st.name) + ".cond_encoder.2.bias"), s);
-  }
-  float* d_cond_mish = F((size_t)B * p->G);
-  {
-    GemmSimtArgs a{};
-    a.in = d_film; a.w = tr->film_wT; a.out = d_cond_mish; a.M = B; a.Cin = SPDM_FILM_WIDTH; a.Cout = p->G;
-    a.ld_in = SPDM_FILM_WIDTH; a.ld_out = p->G; a.H = 1; a.W = 1; a.taps = 1; a.act = ACT_NONE;
-    launch_gemm_simt<float, float>(a, s);
-  }
   float* d_cond = F((size_t)B * p->G);
-  launch_mish_bwd(d_cond_mish, p->cond, d_cond, (long long)B * p->G, s);
+  if (film_tc) {
+    bf16* d_film16 = H16((size_t)Bp * SPDM_FILM_WIDTH);
+    launch_cast_bf16(d_film, d_film16, (long long)Bf * SPDM_FILM_WIDTH, s);   // rows B..Bf are zero (memset, never written)
+    if (Bp > Bf) CUDA_OK(cudaMemsetAsync(d_film16 + (size_t)Bf * SPDM_FILM_WIDTH, 0, (size_t)(Bp - Bf) * SPDM_FILM_WIDTH * sizeof(bf16), s));
+    // weight gradients of all six Linears in one pixel-contraction GEMM: dW [1792][GP] = d_film^T cond_mish, then row blocks -> parameters
+    float* dw_all = F((size_t)SPDM_FILM_WIDTH * GP);
+    CUDA_OK(cudaMemsetAsync(dw_all, 0, (size_t)SPDM_FILM_WIDTH * GP * sizeof(float), s));
+    const int rc = wgrad_tc_launch(cond_mish16, GP, d_film16, SPDM_FILM_WIDTH, Bp, GP, SPDM_FILM_WIDTH, 1, 1, 1, dw_all, s);
+    REQUIRE(rc == 0, "FiLM wgrad: %s", wgrad_tc_last_error());
+    for (const StageInfo& st : kStages) {
+      CUDA_OK(cudaMemcpy2DAsync(G(std::string(st.name) + ".cond_encoder.2.weight"), (size_t)p->G * sizeof(float), dw_all + (size_t)st.film_off * GP,
+                                (size_t)GP * sizeof(float), (size_t)p->G * sizeof(float), (size_t)2 * st.cout, cudaMemcpyDeviceToDevice, s));
+      launch_colsum<float>(d_film + st.film_off, SPDM_FILM_WIDTH, B, 2 * st.cout, G(std::string(st.name) + ".cond_encoder.2.bias"), s);
+    }
+    bf16* d_cm16 = H16((size_t)Bp * GP);
+    tc_flat("d_film", d_film16, SPDM_FILM_WIDTH, tr->film_wb16, SPDM_FILM_WIDTH, GP, Bp, d_cm16, GP, nullptr, 0);
+    launch_mish_bwd_bf16(d_cm16, GP, p->cond, d_cond, B, p->G, s);
+  } else {
+    for (const StageInfo& st : kStages) {
+      WgradArgs a{};
+      a.x = p->cond_mish; a.ld_x = p->G; a.dy = d_film + st.film_off; a.ld_dy = SPDM_FILM_WIDTH; a.M = B; a.Cin = p->G; a.Cout = 2 * st.cout;
+      a.H = 1; a.W = 1; a.taps = 1; a.dw = G(std::string(st.name) + ".cond_encoder.2.weight");
+      launch_wgrad_simt<float, float>(a, s);
+      launch_colsum<float>(d_film + st.film_off, SPDM_FILM_WIDTH, B, 2 * st.cout, G(std::string(st.name) + ".cond_encoder.2.bias"), s);
+    }
+    float* d_cond_mish = F((size_t)B * p->G);
+    {
+      GemmSimtArgs a{};
+      a.in = d_film; a.w = tr->film_wT; a.out = d_cond_mish; a.M = B; a.Cin = SPDM_FILM_WIDTH; a.Cout = p->G;
+      a.ld_in = SPDM_FILM_WIDTH; a.ld_out = p->G; a.H = 1; a.W = 1; a.taps = 1; a.act = ACT_NONE;
+      launch_gemm_simt<float, float>(a, s);
+    }
+    launch_mish_bwd(d_cond_mish, p->cond, d_cond, (long long)B * p->G, s);
+  }
   float* d_enc_out = F((size_t)n_frames * 128);
   launch_gather_feat_grad(d_cond, d_enc_out, B, T, p->cfg.cond_dim, s);
   if (enc_tc) {
@@ -677,9 +727,9 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     wg(c1p, 128, d2, 64, M2 / 2, 128, 64, g2);
     bf16* d1 = H16((size_t)M2 * 64);
     tc_flat("d_c1", d2, 64, p->enc_w2pT, 64, 128, M2 / 2, d1, 128, nullptr, 0);
-    // (ReLU' in the GEMM epilogue -- EPI_MASK -- was measured slower: 457 us vs 182 + 130 us for GEMM + this streaming kernel)
-    launch_relu_mask(d1, c1p, d1, M2 * 64, nullptr, s);
-    launch_enc_conv1_wgrad(images, d1, G("vision_encoder.0.weight"), G("vision_encoder.0.bias"), n_frames, T, img_bstride, s);
+    // (ReLU' in the GEMM epilogue -- EPI_MASK -- was measured slower: 457 us vs 182 + 130 us for GEMM + a streaming mask kernel);
+    // d1 has a single consumer, the conv1 weight gradient, which applies the mask (c1p > 0) as it loads d1
+    launch_enc_conv1_wgrad(images, d1, c1p, G("vision_encoder.0.weight"), G("vision_encoder.0.bias"), n_frames, T, img_bstride, s);
     {  // gb2 was accumulated on the main stream (relu mask), g2 / g3 on the side stream: unpack there, after this point of main
       cudaStream_t us = fork();
       launch_enc_unpack_grads(g2, g3, gb2, G("vision_encoder.2.weight"), G("vision_encoder.2.bias"), G("vision_encoder.4.weight"), us);
