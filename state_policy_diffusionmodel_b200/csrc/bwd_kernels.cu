@@ -379,11 +379,15 @@ __global__ void __launch_bounds__(1024) gn_part_finalize_kernel(const float* __r
 template <typename T> void launch_gn_bwd(const GnBwdArgs& a, int B, cudaStream_t s) {
   const int nvec = a.HW * (a.C >> 3), vpr = a.C >> 3;
   if ((nvec & (nvec - 1)) == 0 && nvec >= 64 && nvec <= 16384) {
-    const int CS = nvec > 2048 ? nvec / 2048 : 1;
+    static int tmax = 0;   // SPDM_GN_BWD_T: threads per CTA (512 default; 256 = two CTAs per SM, twice the cluster size)
+    if (!tmax) { const char* e = getenv("SPDM_GN_BWD_T"); tmax = e ? atoi(e) : 512; if (tmax != 256 && tmax != 512) tmax = 512; }
+    const int cap = tmax * 4;
+    int CS = nvec > cap ? nvec / cap : 1;
+    if (CS > 8) CS = 8;
     const int nv = nvec / CS;
-    const int threads = nv < 512 ? nv : 512;
+    const int threads = nv < tmax ? nv : tmax;
     const int vpt = nv / threads;
-    if (threads % vpr == 0 && a.HW % CS == 0 && (a.HW / CS) * vpr == nv) {
+    if (threads % vpr == 0 && a.HW % CS == 0 && (a.HW / CS) * vpr == nv && (vpt == 1 || vpt == 2 || vpt == 4)) {
       if (vpt == 4) launch_gn_cached<T, 4>(a, B, CS, threads, s);
       else if (vpt == 2) launch_gn_cached<T, 2>(a, B, CS, threads, s);
       else launch_gn_cached<T, 1>(a, B, CS, threads, s);
@@ -1778,15 +1782,24 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, float*
     coef *= c;
   }
   const float step_size = lr / bc1;
-  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
-    const float gi = g[i] * coef;
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
+  auto upd = [&](float& pi, float& gi, float& mi, float& vi) {
+    gi *= coef;
+    mi = beta1 * mi + (1.f - beta1) * gi;
+    vi = beta2 * vi + (1.f - beta2) * gi * gi;
     const float denom = sqrtf(vi) / bc2_sqrt + eps;
-    p[i] -= step_size * (mi / denom);
-    m[i] = mi;
-    v[i] = vi;
-    g[i] = gi;
+    pi -= step_size * (mi / denom);
+  };
+  // the step streams 32 bytes per parameter (read and write p, g, m, v): 16-byte accesses, the tail element-wise
+  const long long n4 = ((reinterpret_cast<uintptr_t>(p) | reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(m) | reinterpret_cast<uintptr_t>(v)) & 15) ? 0 : n / 4;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n4; i += (long long)gridDim.x * 256) {
+    float4 P = reinterpret_cast<float4*>(p)[i], Gv = reinterpret_cast<float4*>(g)[i], Mv = reinterpret_cast<float4*>(m)[i], Vv = reinterpret_cast<float4*>(v)[i];
+    upd(P.x, Gv.x, Mv.x, Vv.x); upd(P.y, Gv.y, Mv.y, Vv.y); upd(P.z, Gv.z, Mv.z, Vv.z); upd(P.w, Gv.w, Mv.w, Vv.w);
+    reinterpret_cast<float4*>(p)[i] = P; reinterpret_cast<float4*>(g)[i] = Gv; reinterpret_cast<float4*>(m)[i] = Mv; reinterpret_cast<float4*>(v)[i] = Vv;
+  }
+  for (long long i = n4 * 4 + (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    float pi = p[i], gi = g[i], mi = m[i], vi = v[i];
+    upd(pi, gi, mi, vi);
+    p[i] = pi; g[i] = gi; m[i] = mi; v[i] = vi;
   }
 }
 }  // namespace

@@ -178,6 +178,9 @@ void launch_add_noise(const float* x0, const float* noise, const long long* t, c
 // weight repack (fp32 PyTorch layout -> kernel layout)
 void launch_pack_conv_f32(const float* oihw, float* out, int Cout, int Cin, int k, cudaStream_t s);  // -> [tap][Cin][Cout]
 void launch_pack_conv_bf16(const float* oihw, bf16* out, int Cout, int Cin, int k, cudaStream_t s); // -> [Cout][tap][Cin]
+// 3x3, Cout and Cin multiples of 32 (else false, nothing launched): one pass -> [Cout][tap][Cin] and/or [Cin][8 - tap][Cout] (either may be null)
+bool launch_pack_conv3_bf16(const float* oihw, bf16* out_fwd, bf16* out_dgrad, int Cout, int Cin, cudaStream_t s);
+bool launch_unpack_conv3_grad(const float* packed, float* dst, int Cout, int Cin, cudaStream_t s);   // [tap][Cout][Cin] fp32 -> OIHW
 void launch_pack_conv_fold2_bf16(const float* oihw, bf16* out, int Cout, int Cin, cudaStream_t s);    // W = 2 fold: [2 Cout][9][2 Cin]
 void launch_pack_conv_pfold_bf16(const float* oihw, bf16* out, int Cin, cudaStream_t s);               // pair fold, Cout = 64: [128][3][4][Cin]
 void launch_pack_linear_f32(const float* nk, float* out, int N, int K, int ld_out, int col_off, cudaStream_t s);  // -> [K][ld_out] at col_off

@@ -1296,9 +1296,77 @@ void launch_pack_conv_f32(const float* oihw, float* out, int Cout, int Cin, int 
   const long long total = (long long)Cout * Cin * k * k;
   launch_pdl(pack_conv_f32_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, oihw, out, Cout, Cin, k * k);
 }
+namespace {
+// 3x3 weights, tiled through shared memory (Cout, Cin multiples of 32): a block reads 32 output channels x 32 input channels x
+// 9 taps as 1152-byte runs of the OIHW tensor and writes 64-byte runs of the forward operand [Cout][tap][Cin] and (training) of
+// the dgrad operand [Cin][tap'][Cout] (tap' = 8 - tap) -- one pass over the fp32 weights for both.  The elementwise kernels
+// above read with a 36-byte stride; every index split below is by a compile-time constant.
+constexpr int PK_T = 32;
+constexpr int PK_ROW = PK_T * 9;          // 288 floats of one output channel's 32 input channels
+__global__ void __launch_bounds__(256) pack_conv3_tiled_kernel(const float* __restrict__ oihw, bf16* __restrict__ out_f, bf16* __restrict__ out_d,
+                                                               int Cout, int Cin) {
+  __shared__ float tile[PK_T][PK_ROW + 1];
+  pdl_wait();
+  pdl_trigger();
+  const int ci0 = blockIdx.x * PK_T, co0 = blockIdx.y * PK_T;
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;   // 8 warps
+#pragma unroll
+  for (int rr = 0; rr < PK_T / 8; ++rr) {
+    const int r = q + 8 * rr;
+    const float* src = oihw + ((size_t)(co0 + r) * Cin + ci0) * 9;
+#pragma unroll
+    for (int k = lane; k < PK_ROW; k += 32) tile[r][k] = src[k];
+  }
+  __syncthreads();
+  if (out_f) {   // lane = input channel: 32 x 2 B contiguous
+#pragma unroll 4
+    for (int idx = q; idx < PK_T * 9; idx += 8) {
+      const int r = idx / 9, tap = idx - r * 9;
+      out_f[((size_t)(co0 + r) * 9 + tap) * Cin + ci0 + lane] = __float2bfloat16_rn(tile[r][lane * 9 + tap]);
+    }
+  }
+  if (out_d) {   // lane = output channel
+#pragma unroll 4
+    for (int idx = q; idx < PK_T * 9; idx += 8) {
+      const int c = idx / 9, tp = idx - c * 9;
+      out_d[((size_t)(ci0 + c) * 9 + tp) * Cout + co0 + lane] = __float2bfloat16_rn(tile[lane][c * 9 + 8 - tp]);
+    }
+  }
+}
+__global__ void __launch_bounds__(256) unpack_conv3_tiled_kernel(const float* __restrict__ packed, float* __restrict__ dst, int Cout, int Cin) {
+  __shared__ float tile[PK_T][PK_ROW + 1];
+  const int ci0 = blockIdx.x * PK_T, co0 = blockIdx.y * PK_T;
+  const int lane = threadIdx.x & 31, q = threadIdx.x >> 5;
+#pragma unroll
+  for (int idx = q; idx < PK_T * 9; idx += 8) {   // packed [tap][Cout][Cin]: lane = input channel, 128 B contiguous (36 loads in flight)
+    const int tap = idx >> 5, r = idx & 31;
+    tile[r][lane * 9 + tap] = packed[((size_t)tap * Cout + co0 + r) * Cin + ci0 + lane];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int rr = 0; rr < PK_T / 8; ++rr) {
+    const int r = q + 8 * rr;
+    float* d = dst + ((size_t)(co0 + r) * Cin + ci0) * 9;
+#pragma unroll
+    for (int k = lane; k < PK_ROW; k += 32) d[k] = tile[r][k];
+  }
+}
+}  // namespace
 void launch_pack_conv_bf16(const float* oihw, bf16* out, int Cout, int Cin, int k, cudaStream_t s) {
+  if (k == 3 && Cout % PK_T == 0 && Cin % PK_T == 0) { launch_pack_conv3_bf16(oihw, out, nullptr, Cout, Cin, s); return; }
   const long long total = (long long)Cout * Cin * k * k;
   launch_pdl(pack_conv_bf16_kernel, dim3(cdiv(total, 256)), dim3(256), 0, s, oihw, out, Cout, Cin, k * k);
+}
+bool launch_pack_conv3_bf16(const float* oihw, bf16* out_fwd, bf16* out_dgrad, int Cout, int Cin, cudaStream_t s) {
+  if (Cout % PK_T || Cin % PK_T) return false;
+  launch_pdl(pack_conv3_tiled_kernel, dim3(Cin / PK_T, Cout / PK_T), dim3(256), 0, s, oihw, out_fwd, out_dgrad, Cout, Cin);
+  return true;
+}
+bool launch_unpack_conv3_grad(const float* packed, float* dst, int Cout, int Cin, cudaStream_t s) {
+  if (Cout % PK_T || Cin % PK_T) return false;
+  unpack_conv3_tiled_kernel<<<dim3(Cin / PK_T, Cout / PK_T), 256, 0, s>>>(packed, dst, Cout, Cin);
+  COUNT_LAUNCH();
+  return true;
 }
 void launch_pack_conv_fold2_bf16(const float* oihw, bf16* out, int Cout, int Cin, cudaStream_t s) {
   const long long total = 2LL * Cout * 3 * 2 * Cin;

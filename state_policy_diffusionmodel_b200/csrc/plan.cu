@@ -253,12 +253,17 @@ GemmW& reg_conv3(spdm_plan* p, const std::string& name, int Cin, int Cout) {
   bool bfm = p->bf16_mode;
   p->loaders[name + ".weight"] = [=](const float* src, const int64_t* shape, int ndim, cudaStream_t s) {
     check_shape(name + ".weight", shape, ndim, {Cout, Cin, 3, 3});
-    if (bfm) launch_pack_conv_bf16(src, gp->w16, Cout, Cin, 3, s);
-    else launch_pack_conv_f32(src, gp->w32, Cout, Cin, 3, s);
+    bool twin_done = false;
+    if (bfm) {
+      twin_done = gp->twin && launch_pack_conv3_bf16(src, gp->w16, gp->twin->w16, Cout, Cin, s);   // forward and dgrad operands in one pass
+      if (!twin_done) launch_pack_conv_bf16(src, gp->w16, Cout, Cin, 3, s);
+    } else {
+      launch_pack_conv_f32(src, gp->w32, Cout, Cin, 3, s);
+    }
     if (gp->wtf) launch_pack_conv_tf32(src, gp->wtf, Cout, Cin, s);
     if (gp->w16_fold && !p->tr) launch_pack_conv_fold2_bf16(src, gp->w16_fold, Cout, Cin, s);  // inference only (Fwd::fold_ok)
     if (gp->w16_pfold && !p->tr) launch_pack_conv_pfold_bf16(src, gp->w16_pfold, Cin, s);        // inference only (Fwd::pfold_tc)
-    if (gp->twin) {
+    if (gp->twin && !twin_done) {
       if (bfm) launch_pack_conv_dgrad_bf16(src, gp->twin->w16, Cout, Cin, s);
       else launch_pack_conv_dgrad_f32(src, gp->twin->w32, Cout, Cin, s);
     }

@@ -159,7 +159,7 @@ template <typename T> struct Train {
         const int rc = wgrad_tc_launch(reinterpret_cast<const bf16*>(x), ld_x, reinterpret_cast<const bf16*>(dy), ld_dy, m, g.Cin, g.Cout, H, W,
                                        g.taps, dst, s);
         REQUIRE(rc == 0, "%s: %s", wname.c_str(), wgrad_tc_last_error());
-        if (g.taps == 9) launch_unpack_conv_grad(dst, G(pname), g.Cout, g.Cin, s);  // [tap][Cout][Cin] -> PyTorch layout, same stream
+        if (g.taps == 9 && !launch_unpack_conv3_grad(dst, G(pname), g.Cout, g.Cin, s)) launch_unpack_conv_grad(dst, G(pname), g.Cout, g.Cin, s);  // [tap][Cout][Cin] -> PyTorch layout, same stream
         return;
       }
     }
