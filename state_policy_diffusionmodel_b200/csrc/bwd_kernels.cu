@@ -872,6 +872,10 @@ __device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const bf16* p) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
 }
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t (&r)[4], const bf16* p) {
+  const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(a));
+}
 __device__ __forceinline__ void ldsm_x2(uint32_t (&r)[2], const bf16* p) {
   const uint32_t a = (uint32_t)__cvta_generic_to_shared(p);
   asm volatile("ldmatrix.sync.aligned.m8n8.x2.shared.b16 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(a));
@@ -1997,6 +2001,88 @@ __global__ void __launch_bounds__(192) enc_conv1_wgrad_kernel(const float* __res
   }
 }
 
+// The same gradient on the tensor cores (mma.sync m16n8k16, bf16 operands, fp32 accumulate): per strip
+//   D[16 o][16 n] += A[16 o][192 pixels] * B[192 pixels][16 n],   n = c*4 + kh*2 + kw (12 columns), n = 12 a column of ones (the
+// bias gradient), 13..15 zero.  A is the (masked) d1 strip as it lies in memory ([pixel][16 o] bf16, read with ldmatrix.trans),
+// B is gathered from the fp32 input strip in shared memory (one scalar load per element, rounded to bf16).  The CUDA-core
+// kernel above issues 144 shared-memory loads per warp and strip, this one 36; it is then bound by the HBM reads of the
+// frames and of d1 / c1p.  A warp owns 2 of the 12 16-pixel blocks of every strip and keeps its accumulators for the whole
+// kernel; the 6 warps are folded through shared memory at the end, then one atomicAdd per weight per block.
+__global__ void __launch_bounds__(192) enc_conv1_wgrad_mma_kernel(const float* __restrict__ img, const bf16* __restrict__ d1, const bf16* __restrict__ act,
+                                                                  float* __restrict__ dw1, float* __restrict__ db1, int n_strips, int T, long long bstride) {
+  __shared__ __align__(16) float s_in[24 * 100];
+  constexpr int DS = 24;                          // padded row stride (bf16) of s_d: 48-byte rows, conflict-free ldmatrix
+  __shared__ __align__(16) bf16 s_d[192 * DS];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  // B columns of this thread: n = g (tile 0) and 8 + g (tile 1); n -> (c, kh, kw) -> offset of the tap inside the strip
+  const int n1 = 8 + g;
+  const int off0 = ((g >> 2) * 8 + ((g >> 1) & 1)) * 100 + 3 + (g & 1);
+  const int off1 = ((n1 >> 2) * 8 + ((n1 >> 1) & 1)) * 100 + 3 + (n1 & 1);   // used when n1 < 12
+  const float fill1 = g == 4 ? 1.f : 0.f;
+  for (int strip = blockIdx.x; strip < n_strips; strip += gridDim.x) {
+    const int frame = strip / 12, r3 = strip % 12;
+    __syncthreads();
+    enc_stage_strip(img + (size_t)(frame / T) * bstride + (size_t)(frame % T) * 3 * 96 * 96, r3, s_in, tid);
+    {
+      const uint4* src = reinterpret_cast<const uint4*>(d1 + ((size_t)strip * 192 + tid) * 16);
+      uint4 v[2] = {src[0], src[1]};
+      if (act) {
+        const uint4* as = reinterpret_cast<const uint4*>(act + ((size_t)strip * 192 + tid) * 16);
+        const uint4 a[2] = {as[0], as[1]};
+        const __nv_bfloat162 zero = __floats2bfloat162_rn(0.f, 0.f);
+        __nv_bfloat162* vv = reinterpret_cast<__nv_bfloat162*>(v);
+        const __nv_bfloat162* aa = reinterpret_cast<const __nv_bfloat162*>(a);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) vv[i] = __hmul2(vv[i], __hgt2(aa[i], zero));   // ReLU mask: x 1.0 or x 0.0
+      }
+      *reinterpret_cast<uint4*>(s_d + tid * DS) = v[0];
+      *reinterpret_cast<uint4*>(s_d + tid * DS + 8) = v[1];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+      const int k0 = (warp * 2 + kk) * 16;
+      uint32_t a[4];
+      const int mi = lane >> 3;
+      ldsm_x4_trans(a, s_d + (k0 + 8 * (mi >> 1) + (lane & 7)) * DS + 8 * (mi & 1));
+      float b0[4], b1[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = k0 + 2 * t + (e & 1) + 8 * (e >> 1);           // pixel of the strip, memory order of c1p / d1
+        const int kk2 = j & 3, kk3 = (j >> 2) & 3, c3 = j >> 4;
+        const int yl = 2 * (kk3 >> 1) + (kk2 >> 1), x = 2 * (2 * c3 + (kk3 & 1)) + (kk2 & 1);
+        const int base = 2 * yl * 100 + 2 * x;
+        b0[e] = s_in[off0 + base];
+        b1[e] = g < 4 ? s_in[off1 + base] : fill1;
+      }
+      const uint32_t f0[2] = {pack_bf16x2(b0[0], b0[1]), pack_bf16x2(b0[2], b0[3])};
+      const uint32_t f1[2] = {pack_bf16x2(b1[0], b1[1]), pack_bf16x2(b1[2], b1[3])};
+      mma16816(acc[0], a, f0);
+      mma16816(acc[1], a, f1);
+    }
+  }
+  __syncthreads();
+  float* red = s_in;                              // [6 warps][16 o][16 n]
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    red[(warp * 16 + g) * 16 + 8 * j + 2 * t] = acc[j][0];
+    red[(warp * 16 + g) * 16 + 8 * j + 2 * t + 1] = acc[j][1];
+    red[(warp * 16 + g + 8) * 16 + 8 * j + 2 * t] = acc[j][2];
+    red[(warp * 16 + g + 8) * 16 + 8 * j + 2 * t + 1] = acc[j][3];
+  }
+  __syncthreads();
+  for (int idx = tid; idx < 256; idx += 192) {
+    float tsum = 0.f;
+#pragma unroll
+    for (int w = 0; w < 6; ++w) tsum += red[w * 256 + idx];
+    const int o = idx >> 4, n = idx & 15;
+    if (n < 12) atomicAdd(dw1 + o * 12 + n, tsum);   // (16,3,2,2) is [o][c*4 + kh*2 + kw]
+    else if (n == 12) atomicAdd(db1 + o, tsum);
+  }
+}
+
 // out = act > 0 ? d : 0   (ReLU backward) over [rows][64] bf16, in place allowed; optionally colsum[64] += column sums of the
 // masked gradient (the conv bias gradient).  Grid-stride with a stride that keeps every thread on the same 8 columns.
 __global__ void __launch_bounds__(256) relu_mask_kernel(const bf16* __restrict__ d, const bf16* __restrict__ act, bf16* __restrict__ out,
@@ -2083,7 +2169,10 @@ void launch_enc_conv1_fwd_u8(const uint8_t* img_hwc, const float* w1, const floa
 void launch_enc_conv1_wgrad(const float* img, const bf16* d1, const bf16* act, float* dw1, float* db1, int n, int T, long long bstride, cudaStream_t s) {
   int grid = n * 12;
   if (grid > 148 * 8) grid = 148 * 8;
-  enc_conv1_wgrad_kernel<<<grid, 192, 0, s>>>(img, d1, act, dw1, db1, n * 12, T, bstride);
+  static int simt = -1;   // SPDM_ENC_W1_SIMT=1: the CUDA-core kernel (A/B switch)
+  if (simt < 0) { const char* e = getenv("SPDM_ENC_W1_SIMT"); simt = e ? atoi(e) : 0; }
+  if (simt) enc_conv1_wgrad_kernel<<<grid, 192, 0, s>>>(img, d1, act, dw1, db1, n * 12, T, bstride);
+  else enc_conv1_wgrad_mma_kernel<<<grid, 192, 0, s>>>(img, d1, act, dw1, db1, n * 12, T, bstride);
   COUNT_LAUNCH();
 }
 void launch_relu_mask(const bf16* d, const bf16* act, bf16* out, long long n, float* colsum64, cudaStream_t s) {
