@@ -376,7 +376,9 @@ __global__ void __launch_bounds__(1024) gn_part_finalize_kernel(const float* __r
 }
 }  // namespace
 // NOTE: d_film / d_temb are ACCUMULATED by the cached kernel (zero them first) and overwritten by the fallback kernel.
-template <typename T> void launch_gn_bwd(const GnBwdArgs& a, int B, cudaStream_t s) {
+// Returns true when the per-sample (d gamma, d beta) partials in a.part still have to be summed over the batch
+// (launch_gn_part_finalize -- nothing else of the step reads them, so the caller may put it on another stream).
+template <typename T> bool launch_gn_bwd(const GnBwdArgs& a, int B, cudaStream_t s) {
   const int nvec = a.HW * (a.C >> 3), vpr = a.C >> 3;
   if ((nvec & (nvec - 1)) == 0 && nvec >= 64 && nvec <= 16384) {
     static int tmax = 0;   // SPDM_GN_BWD_T: threads per CTA (512 default; 256 = two CTAs per SM, twice the cluster size)
@@ -392,18 +394,19 @@ template <typename T> void launch_gn_bwd(const GnBwdArgs& a, int B, cudaStream_t
       else if (vpt == 2) launch_gn_cached<T, 2>(a, B, CS, threads, s);
       else launch_gn_cached<T, 1>(a, B, CS, threads, s);
       COUNT_LAUNCH();
-      if (a.part && CS == 1) {
-        gn_part_finalize_kernel<<<cdiv(2 * a.C, 32), 1024, 0, s>>>(a.part, a.dgamma, a.dbeta, B, a.C);
-        COUNT_LAUNCH();
-      }
-      return;
+      return a.part && CS == 1;
     }
   }
   gn_bwd_kernel<T><<<B, 256, 0, s>>>(a);
   COUNT_LAUNCH();
+  return false;
 }
-template void launch_gn_bwd<float>(const GnBwdArgs&, int, cudaStream_t);
-template void launch_gn_bwd<bf16>(const GnBwdArgs&, int, cudaStream_t);
+template bool launch_gn_bwd<float>(const GnBwdArgs&, int, cudaStream_t);
+template bool launch_gn_bwd<bf16>(const GnBwdArgs&, int, cudaStream_t);
+void launch_gn_part_finalize(const float* part, float* dgamma, float* dbeta, int B, int C, cudaStream_t s) {
+  gn_part_finalize_kernel<<<cdiv(2 * C, 32), 1024, 0, s>>>(part, dgamma, dbeta, B, C);
+  COUNT_LAUNCH();
+}
 
 // =================================================================================================
 // Weight gradient on CUDA cores (fp32 accumulate): 64(ci) x 64(co) tile per block, split over the pixel
@@ -500,6 +503,45 @@ __global__ void __launch_bounds__(256) colsum_kernel(const T* __restrict__ dy, i
   __syncthreads();
   if (rg == 0 && c < N) atomicAdd(out + c, sm[0][threadIdx.x] + sm[1][threadIdx.x] + sm[2][threadIdx.x] + sm[3][threadIdx.x]);
 }
+// Column sums with 16-byte (bf16) / 32-byte (fp32) loads: a block covers 64 columns as 8 vectors x 32 row lanes, four independent
+// loads in flight per thread (the scalar kernel above spends ~11 us on any bias gradient of the step, 36 of them per step).
+template <typename T>
+__global__ void __launch_bounds__(256) colsum8_kernel(const T* __restrict__ dy, int ld, long long M, int N, float* __restrict__ out, long long rows_per_block) {
+  __shared__ float sm[32][65];
+  const int cv = threadIdx.x & 7, rl = threadIdx.x >> 3;
+  const int c = blockIdx.x * 64 + cv * 8;
+  const long long m0 = (long long)blockIdx.y * rows_per_block;
+  long long m1 = m0 + rows_per_block;
+  if (m1 > M) m1 = M;
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (c < N) {
+    long long m = m0 + rl;
+    for (; m + 96 < m1; m += 128) {
+      float v[4][8];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) load8(dy + (m + 32 * u) * ld + c, v[u]);
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] += v[u][i];
+    }
+    for (; m < m1; m += 32) {
+      float v[8];
+      load8(dy + m * ld + c, v);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) acc[i] += v[i];
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) sm[rl][cv * 8 + i] = acc[i];
+  __syncthreads();
+  if (threadIdx.x < 64 && blockIdx.x * 64 + threadIdx.x < N) {
+    float t = 0.f;
+#pragma unroll
+    for (int r = 0; r < 32; ++r) t += sm[r][threadIdx.x];
+    atomicAdd(out + blockIdx.x * 64 + threadIdx.x, t);
+  }
+}
 }  // namespace
 template <typename TX, typename TDY> void launch_wgrad_simt(const WgradArgs& a, cudaStream_t s) {
   const int tiles = cdiv(a.Cin, 64) * cdiv(a.Cout, 64);
@@ -517,7 +559,10 @@ template <typename T> void launch_colsum(const T* dy, int ld, long long M, int N
   int gy = (int)((M + 255) / 256);
   if (gy > 148 * 4) gy = 148 * 4;
   const long long rpb = (M + gy - 1) / gy;
-  colsum_kernel<T><<<dim3(cdiv(N, 64), gy), 256, 0, s>>>(dy, ld, M, N, out, rpb);
+  if (N % 8 == 0 && ld % 8 == 0 && (reinterpret_cast<uintptr_t>(dy) & (8 * sizeof(T) - 1)) == 0)
+    colsum8_kernel<T><<<dim3(cdiv(N, 64), gy), 256, 0, s>>>(dy, ld, M, N, out, rpb);
+  else
+    colsum_kernel<T><<<dim3(cdiv(N, 64), gy), 256, 0, s>>>(dy, ld, M, N, out, rpb);
   COUNT_LAUNCH();
 }
 template void launch_colsum<float>(const float*, int, long long, int, float*, cudaStream_t);

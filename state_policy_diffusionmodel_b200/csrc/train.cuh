@@ -25,7 +25,8 @@ struct GnBwdArgs {
   int HW, C;
   float eps;
 };
-template <typename T> void launch_gn_bwd(const GnBwdArgs& a, int B, cudaStream_t s);
+template <typename T> bool launch_gn_bwd(const GnBwdArgs& a, int B, cudaStream_t s);   // true: a.part needs launch_gn_part_finalize
+void launch_gn_part_finalize(const float* part, float* dgamma, float* dbeta, int B, int C, cudaStream_t s);
 
 // ---- weight gradient on CUDA cores: dw[co][ci][tap] += sum_m x[shift(m, tap)][ci] * dy[m][co] --------
 struct WgradArgs {

@@ -209,7 +209,8 @@ template <typename T> struct Train {
     }
     a.HW = p->levelH(d.level) * p->levelW(d.level); a.C = d.Cout; a.eps = 1e-5f;
     a.part = Fbuf((size_t)f.Bpad * 2 * d.Cout);
-    launch_gn_bwd<T>(a, B, s);
+    if (launch_gn_bwd<T>(a, B, s))   // batch sum of the (d gamma, d beta) partials: a parameter gradient, off the critical path
+      launch_gn_part_finalize(a.part, a.dgamma, a.dbeta, B, a.C, fork_side());
   }
 
   // Data gradient of a 3x3 conv.  The swapped-operand kernel (N = 256 pixels per MMA instead of N = Cout <= 128) only exists
@@ -655,6 +656,18 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     return tr->grads + it->second.off;
   };
   // ---- FiLM Linears, d obs_cond, vision encoder ----
+  auto fork = [&]() -> cudaStream_t {  // same contract as Train::fork_side
+    if (!tr->use_side) return s;
+    if (tr->ev_cur == tr->evs.size()) {
+      cudaEvent_t e;
+      CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      tr->evs.push_back(e);
+    }
+    cudaEvent_t e = tr->evs[tr->ev_cur++];
+    CUDA_OK(cudaEventRecord(e, s));
+    CUDA_OK(cudaStreamWaitEvent(tr->side, e, 0));
+    return tr->side;
+  };
   float* d_cond = F((size_t)B * p->G);
   if (film_tc) {
     bf16* d_film16 = H16((size_t)Bp * SPDM_FILM_WIDTH);
@@ -662,13 +675,14 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
     if (Bp > Bf) CUDA_OK(cudaMemsetAsync(d_film16 + (size_t)Bf * SPDM_FILM_WIDTH, 0, (size_t)(Bp - Bf) * SPDM_FILM_WIDTH * sizeof(bf16), s));
     // weight gradients of all six Linears in one pixel-contraction GEMM: dW [1792][GP] = d_film^T cond_mish, then row blocks -> parameters
     float* dw_all = F((size_t)SPDM_FILM_WIDTH * GP);
-    CUDA_OK(cudaMemsetAsync(dw_all, 0, (size_t)SPDM_FILM_WIDTH * GP * sizeof(float), s));
-    const int rc = wgrad_tc_launch(cond_mish16, GP, d_film16, SPDM_FILM_WIDTH, Bp, GP, SPDM_FILM_WIDTH, 1, 1, 1, dw_all, s);
+    cudaStream_t ws = fork();   // parameter gradients: side stream
+    CUDA_OK(cudaMemsetAsync(dw_all, 0, (size_t)SPDM_FILM_WIDTH * GP * sizeof(float), ws));
+    const int rc = wgrad_tc_launch(cond_mish16, GP, d_film16, SPDM_FILM_WIDTH, Bp, GP, SPDM_FILM_WIDTH, 1, 1, 1, dw_all, ws);
     REQUIRE(rc == 0, "FiLM wgrad: %s", wgrad_tc_last_error());
     for (const StageInfo& st : kStages) {
       CUDA_OK(cudaMemcpy2DAsync(G(std::string(st.name) + ".cond_encoder.2.weight"), (size_t)p->G * sizeof(float), dw_all + (size_t)st.film_off * GP,
-                                (size_t)GP * sizeof(float), (size_t)p->G * sizeof(float), (size_t)2 * st.cout, cudaMemcpyDeviceToDevice, s));
-      launch_colsum<float>(d_film + st.film_off, SPDM_FILM_WIDTH, B, 2 * st.cout, G(std::string(st.name) + ".cond_encoder.2.bias"), s);
+                                (size_t)GP * sizeof(float), (size_t)p->G * sizeof(float), (size_t)2 * st.cout, cudaMemcpyDeviceToDevice, ws));
+      launch_colsum<float>(d_film + st.film_off, SPDM_FILM_WIDTH, B, 2 * st.cout, G(std::string(st.name) + ".cond_encoder.2.bias"), ws);
     }
     bf16* d_cm16 = H16((size_t)Bp * GP);
     tc_flat("d_film", d_film16, SPDM_FILM_WIDTH, tr->film_wb16, SPDM_FILM_WIDTH, GP, Bp, d_cm16, GP, nullptr, 0);
@@ -693,18 +707,6 @@ extern "C" int spdm_train_fwd_bwd(spdm_plan* p, const float* images, const float
   float* d_enc_out = F((size_t)n_frames * 128);
   launch_gather_feat_grad(d_cond, d_enc_out, B, T, p->cfg.cond_dim, s);
   if (enc_tc) {
-    auto fork = [&]() -> cudaStream_t {  // same contract as Train::fork_side
-      if (!tr->use_side) return s;
-      if (tr->ev_cur == tr->evs.size()) {
-        cudaEvent_t e;
-        CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-        tr->evs.push_back(e);
-      }
-      cudaEvent_t e = tr->evs[tr->ev_cur++];
-      CUDA_OK(cudaEventRecord(e, s));
-      CUDA_OK(cudaStreamWaitEvent(tr->side, e, 0));
-      return tr->side;
-    };
     auto wg = [&](const bf16* x, int ld_x, const bf16* dy, int ld_dy, long long M, int Cin, int Cout, float* dst) {
       const int rc = wgrad_tc_launch(x, ld_x, dy, ld_dy, M, Cin, Cout, 1, 1, 1, dst, fork());
       REQUIRE(rc == 0, "encoder wgrad: %s", wgrad_tc_last_error());
