@@ -63,6 +63,9 @@ struct TcParams {
   // K loop walks 3 dy x 4 blocks (kernels.cu::pack_conv_pfold_bf16_kernel); fold_c1 = channel offset of a pair's second pixel
   // in the pair-row view of the input (= ld_in), fold_ldo = real leading dimension of the output (ld_out is the pair-row stride)
   int fold, fold_c1, fold_ldo;
+  // halo mode (conv_tc_swap_kernel, W == 8, 32 image rows of one sample per tile): the pixel operand of a (k block, dx) pair is loaded
+  // ONCE as a (32 + 2)-row box and serves the three dy taps through 1024-byte descriptor offsets
+  int halo;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1126,9 +1129,11 @@ __global__ void __launch_bounds__(CL_THREADS, 1) conv_chain_kernel(const ChainPa
 // tile's 256 pixel columns.  The epilogue (one 2-byte store per channel lane and pixel, half the lanes idle when WM = 64) is what
 // the narrow layers are bound by once the tile's MMAs take only a few microseconds.
 constexpr int SWAP_THREADS = 320;
+constexpr int SWAP_THREADS16 = 576;   // 16 epilogue warps: fused GroupNorm-apply epilogues of persistent launches (instruction-latency bound at 2 warps per scheduler)
 template <int STAGES, int WM>
-__global__ void __launch_bounds__(SWAP_THREADS, 1)
-conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const TcParams p) {
+__global__ void __launch_bounds__(SWAP_THREADS16, 1)
+conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w, const __grid_constant__ CUtensorMap map_h,
+                    const TcParams p) {
   constexpr int PIX_BYTES = 2 * A_STAGE_BYTES;           // 256 pixels x 64 ch
   constexpr int W_BYTES = WM * BLOCK_K * 2;              // WM weight rows x 64 k
   constexpr int NPIX = 256;
@@ -1141,8 +1146,14 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   __shared__ __align__(8) uint64_t tmem_full_bar[2];
   __shared__ __align__(8) uint64_t tmem_empty_bar[2];
+  // halo mode: a ring of HP_STAGES (32 + 2)-row pixel boxes and a ring of HW_STAGES weight tiles, each with its own barriers
+  constexpr int HP_STAGES = 3, HW_STAGES = 5;
+  constexpr int HALO_BYTES = 34 * 8 * BLOCK_K * 2;       // 34 image rows x 8 pixels x 64 channels
+  constexpr int HALO_STRIDE = 35 * 1024;
+  static_assert(HP_STAGES * HALO_STRIDE + HW_STAGES * W_BYTES <= STAGES * (PIX_BYTES + W_BYTES), "halo rings must fit the stage ring");
+  __shared__ __align__(8) uint64_t hp_full[HP_STAGES], hp_empty[HP_STAGES], hw_full[HW_STAGES], hw_empty[HW_STAGES];
   __shared__ uint32_t tmem_base_smem;
-  __shared__ float s_part[2][16][4][2][2];  // EPI_APPLY: per-sample, per-warp (lane quarter, column half) (sum, sumsq); double-buffered like TMEM
+  __shared__ float s_part[2][16][4][4][2];  // EPI_APPLY: per-sample, per-warp (lane quarter, column segment) (sum, sumsq); double-buffered like TMEM
   __shared__ float s_mr[2][16][2];       // per-sample (mean, rstd)
 
   const int warp = threadIdx.x >> 5;
@@ -1158,6 +1169,10 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     tma_prefetch_desc(&map_w);
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+#pragma unroll
+    for (int s = 0; s < HP_STAGES; ++s) { mbar_init(&hp_full[s], 1); mbar_init(&hp_empty[s], 1); }
+#pragma unroll
+    for (int s = 0; s < HW_STAGES; ++s) { mbar_init(&hw_full[s], 1); mbar_init(&hw_empty[s], 1); }
     mbar_init(&tmem_full_bar[0], 1); mbar_init(&tmem_full_bar[1], 1);
     const uint32_t n_epi_w = (blockDim.x >> 5) - 2;   // 4 or 8 epilogue warps (chosen at launch)
     mbar_init(&tmem_empty_bar[0], n_epi_w); mbar_init(&tmem_empty_bar[1], n_epi_w);   // one arrival per epilogue warp
@@ -1173,8 +1188,75 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
   TcParams pm = p;       // decode_tile works on 128-row tiles with n_tiles == 1
   pm.n_tiles = 1;
 
-  if (warp == 0) {
+  uint8_t* smem_hw = smem + HP_STAGES * HALO_STRIDE;     // halo mode: weight ring behind the pixel ring
+  if (warp == 0 && p.halo) {
+    if (lane == 0 && !(p.dbg & 16)) {   // dbg 16: MMA free-run microbenchmark (no loads, no operand waits)
+      // groups (k block kb, dx); per group one pixel box and the three dy weight tiles, in the order the MMA warp consumes them
+      const int groups = 3 * p.kb_per_tap;
+      auto wcol_of = [&](int grp, int ty) { const int kb = grp / 3, tx = grp - kb * 3; return (ty * 3 + tx) * p.Cin + kb * BLOCK_K; };
+      uint32_t n_pre = 0;
+      if ((int)blockIdx.x < total) {
+        const int c_tile = (int)blockIdx.x % c_tiles;
+        for (int w = 0; w < 3 * groups && n_pre < (uint32_t)HW_STAGES; ++w, ++n_pre) {
+          mbar_expect_tx(&hw_full[n_pre], W_BYTES);
+          tma_load_2d(smem_hw + n_pre * W_BYTES, &map_w, &hw_full[n_pre], wcol_of(w / 3, w % 3), c_tile * WM);
+        }
+      }
+      pdl_wait();
+      pdl_trigger();
+      uint32_t wkit = 0, pkit = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int c_tile = tile % c_tiles, pt = tile / c_tiles;
+        const TileCoord t0 = decode_tile(pm, 2 * pt, 0);
+        for (int grp = 0; grp < groups; ++grp, ++pkit) {
+          const int kb = grp / 3, dx = grp - kb * 3 - 1;
+          const int ps = pkit % HP_STAGES;
+          mbar_wait(&hp_empty[ps], ((pkit / HP_STAGES) & 1u) ^ 1u);
+          mbar_expect_tx(&hp_full[ps], HALO_BYTES);
+          tma_load_4d(smem + ps * HALO_STRIDE, &map_h, &hp_full[ps], kb * BLOCK_K, dx, t0.h0 - 1, t0.b0);
+          for (int ty = 0; ty < 3; ++ty, ++wkit) {
+            if (wkit < n_pre) continue;
+            const int ws = wkit % HW_STAGES;
+            mbar_wait(&hw_empty[ws], ((wkit / HW_STAGES) & 1u) ^ 1u);
+            mbar_expect_tx(&hw_full[ws], W_BYTES);
+            tma_load_2d(smem_hw + ws * W_BYTES, &map_w, &hw_full[ws], wcol_of(grp, ty), c_tile * WM);
+          }
+        }
+      }
+    }
+  } else if (warp == 1 && p.halo) {
     if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_m(WM, NPIX);
+      const int groups = 3 * p.kb_per_tap;
+      uint32_t wkit = 0, pkit = 0;
+      int lt = 0;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+        const int acc = lt & 1;
+        const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
+        mbar_wait(&tmem_empty_bar[acc], aph ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * NPIX);
+        for (int grp = 0; grp < groups; ++grp, ++pkit) {
+          const int ps = pkit % HP_STAGES;
+          if (!(p.dbg & 16)) mbar_wait(&hp_full[ps], (pkit / HP_STAGES) & 1u);
+          for (int ty = 0; ty < 3; ++ty, ++wkit) {
+            const int ws = wkit % HW_STAGES;
+            if (!(p.dbg & 16)) mbar_wait(&hw_full[ws], (wkit / HW_STAGES) & 1u);
+            tc_fence_after();
+            const uint64_t dw = make_smem_desc(smem_u32(smem_hw + ws * W_BYTES));                  // "A": weight rows of tap (dy = ty - 1, dx)
+            const uint64_t dp = make_smem_desc(smem_u32(smem + ps * HALO_STRIDE + ty * 1024));     // "B": 256 pixel rows from image row h0 - 1 + ty
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
+              umma_bf16(d_tmem, dw + (uint64_t)(2 * k), dp + (uint64_t)(2 * k), idesc, (grp > 0 || ty > 0 || k > 0) ? 1u : 0u);
+            if (!(p.dbg & 16)) umma_commit(&hw_empty[ws]);
+          }
+          if (!(p.dbg & 16)) umma_commit(&hp_empty[ps]);
+        }
+        umma_commit(&tmem_full_bar[acc]);
+      }
+    }
+  } else if (warp == 0) {
+    if (lane == 0 && !(p.dbg & 16)) {
       // k-step -> weight column, channel offset of the pixel box, (dx, dy) shift
       auto decode = [&](int it, int& wcol, int& c0, int& dx, int& dy) {
         if (p.fold) {
@@ -1238,14 +1320,14 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         for (int it = 0; it < k_iters; ++it, ++kit) {
           const int s = kit % STAGES;
           const uint32_t ph = (kit / STAGES) & 1u;
-          mbar_wait(&full_bar[s], ph);
+          if (!(p.dbg & 16)) mbar_wait(&full_bar[s], ph);
           tc_fence_after();
           const uint64_t dw = make_smem_desc(smem_u32(smem_w + s * W_BYTES));      // "A": 128 weight rows
           const uint64_t dp = make_smem_desc(smem_u32(smem_pix + s * PIX_BYTES));  // "B": 256 pixel rows
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k)
             umma_bf16(d_tmem, dw + (uint64_t)(2 * k), dp + (uint64_t)(2 * k), idesc, (it > 0 || k > 0) ? 1u : 0u);
-          umma_commit(&empty_bar[s]);
+          if (!(p.dbg & 16)) umma_commit(&empty_bar[s]);
         }
         umma_commit(&tmem_full_bar[acc]);
       }
@@ -1255,9 +1337,11 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
     // 8 epilogue warps (launched where a CTA has a single tile and the epilogue is exposed): two warps per lane quarter, each owns
     // half of the tile's pixel columns.  4 warps (persistent multi-tile launches, where the epilogue hides under the next tile's
     // MMAs and extra warps only compete for issue slots: measured -1.3 % at batch 4096): every warp walks all 256 columns.
-    const bool split = (blockDim.x >> 5) == 10;
-    const int eh = split ? (warp - 2) >> 2 : 0;
-    const int c_lo = split ? eh * (NPIX / 2) : 0, c_hi = split ? c_lo + NPIX / 2 : NPIX;
+    // 16 warps (fused-apply epilogues of persistent launches): four warps per lane quarter, 64 columns each.
+    const int ncs = ((int)(blockDim.x >> 5) - 2) >> 2;   // column segments of the tile: 1, 2 or 4
+    const bool split = ncs == 2;
+    const int eh = (warp - 2) >> 2;
+    const int c_lo = eh * (NPIX / ncs), c_hi = c_lo + NPIX / ncs;
     // TMEM lane -> output channel inside the tile
     const bool layout_b = (p.dbg & 1024) != 0;          // M = 64 alternative hypothesis: rows 0..63 in lanes 0..63
     const int ch_local = (WM == 128 || layout_b) ? q * 32 + lane : q * 16 + lane;
@@ -1273,6 +1357,11 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
       const long long row0 = (long long)pt * NPIX;      // the 256 pixel rows of the tile are contiguous
       mbar_wait(&tmem_full_bar[acc], aph);
       tc_fence_after();
+      if (p.dbg & 32) {  // microbenchmark: hand the accumulator straight back
+        tc_fence_before();
+        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        continue;
+      }
       const bool active = q < nw;
       // `ch`: element offset of this lane's channel inside an output row (pair fold: the (wo, co) row of the accumulator is pixel
       // wo of the pair, channel co); `chp`: the channel whose GroupNorm / time-embedding / FiLM parameters apply
@@ -1285,7 +1374,7 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
         // GroupNorm is tile-local.  Pass 1 over TMEM: per-sample statistics; pass 2: normalise (+GELU/temb/FiLM) and store.
         const int n_s = NPIX / pps;
         const int span2 = pps < c_hi - c_lo ? pps : c_hi - c_lo;   // columns of one sample inside this warp's column range
-        const int n_epi_thr = split ? 256 : 128;
+        const int n_epi_thr = 128 * ncs;
         if (active) {
 #pragma unroll 1
           for (int c = c_lo; c < c_hi; c += 32) {
@@ -1328,7 +1417,7 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
           const int et = (int)threadIdx.x - 64;  // 0..127 (255) over the epilogue warps
           if (et >= 0 && et < n_s) {
             // column halves that hold pixels of sample et (one, or both when the sample spans the whole tile)
-            const int h_lo = split ? (et * pps) / (NPIX / 2) : 0, h_hi = split ? ((et + 1) * pps - 1) / (NPIX / 2) : 0;
+            const int h_lo = (et * pps) / (NPIX / ncs), h_hi = ((et + 1) * pps - 1) / (NPIX / ncs);
             float ts = 0.f, tq = 0.f;
             for (int j = 0; j < nw; ++j)
               for (int hh = h_lo; hh <= h_hi; ++hh) { ts += s_part[acc][et][j][hh][0]; tq += s_part[acc][et][j][hh][1]; }
@@ -1510,6 +1599,8 @@ void launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p,
 
 struct TcGemm {
   CUtensorMap map_a, map_b, map_b256, map_wswap;
+  CUtensorMap map_halo;   // (32 + 2)-row pixel box of the swapped kernel's halo mode (has_halo)
+  bool has_halo;
   bool can_swap;    // 3x3, Cout in {64,128}, geometry allows 256-pixel tiles with per-sample statistics
   TcParams p;
   int block_n;      // 64 or 128
@@ -1565,6 +1656,15 @@ TcGemm* tc_gemm_create(const bf16* in, int ld_in, const bf16* w_packed, int Cin,
   {
     const int pps = H * W;
     g->can_swap = taps == 9 && (Cout == 64 || Cout == 128) && (pps == 16 || (pps >= 32 && pps % 32 == 0 && (pps >= 256 ? pps % 256 == 0 : 256 % pps == 0)));
+  }
+  if (g->can_swap && W == 8 && H % 32 == 0) {   // a 256-pixel tile is 32 whole image rows of one sample: halo mode
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bcap};
+    cuuint64_t strides[3] = {(cuuint64_t)ld_in * 2, (cuuint64_t)W * ld_in * 2, (cuuint64_t)H * W * ld_in * 2};
+    cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, 8u, 34u, 1u};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&g->map_halo, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    g->has_halo = r == CUDA_SUCCESS;
   }
   for (int pass = 0; pass < 3; ++pass) {  // B: 2-D (K, Cout) weights, one map per tile height
     if (pass == 1 && !g->has256) continue;
@@ -1934,6 +2034,11 @@ bool tc_gemm_fuse_apply_pays(const TcGemm* g, int B) {
   const int total = (m_tiles / 2) * ((p.Cout + BLOCK_M - 1) / BLOCK_M);
   if (total <= 2 * num_sms()) return true;
   if (!big) return false;
+  // With 8 / 16 epilogue warps on the fused launches the short-K layers of the 16x4 level gain as well (batch 4096: 64->64 39 + 23 -> 54 us,
+  // 64->128 50 + 44 -> 64 us; they lost with 4 warps: 76 us) -- every persistent swapped launch fuses.  SPDM_FUSE_SHORT=0: the old rule.
+  static int fshort = -1;
+  if (fshort < 0) { const char* e = getenv("SPDM_FUSE_SHORT"); fshort = e ? atoi(e) : 1; }
+  if (fshort) return true;
   const int k_iters = p.fold ? 12 * p.kb_per_tap : (p.W == 1 ? 1 : 3) * (p.H == 1 ? 1 : 3) * p.kb_per_tap;
   const int pps_real = p.H * p.W * (p.fold ? 2 : 1);
   return k_iters >= 18 || pps_real >= 256;
@@ -1967,7 +2072,12 @@ int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const f
     // (SPDM_FUSE_EPI8=0: A/B switch)
     static int epi8 = -1;
     if (epi8 < 0) { const char* e = getenv("SPDM_FUSE_EPI8"); epi8 = e ? atoi(e) : 1; }
-    const int threads = (p.total_tiles <= 2 * num_sms() || (epi8 && fuse)) ? SWAP_THREADS : NUM_THREADS;   // 8 epilogue warps only where the epilogue is exposed (<= 2 tiles per CTA)
+    static int epi16 = -1;   // SPDM_FUSE_EPI16=0: at most 8 epilogue warps (A/B switch)
+    if (epi16 < 0) { const char* e = getenv("SPDM_FUSE_EPI16"); epi16 = e ? atoi(e) : 1; }
+    // 8 epilogue warps only where the epilogue is exposed (<= 2 tiles per CTA); 16 for the fused apply of persistent launches, whose
+    // two passes over the accumulator outlast the tile's MMAs once the operand traffic is cut (halo mode)
+    const int threads = (fuse && epi16 && epi8 && p.total_tiles > 2 * num_sms() && pps >= 64) ? SWAP_THREADS16
+                        : ((p.total_tiles <= 2 * num_sms() || (epi8 && fuse)) ? SWAP_THREADS : NUM_THREADS);
     const int halves = (threads == SWAP_THREADS && pps >= 256) ? 2 : 1;   // then a sample of >= 256 pixels gets one partial per column half
     p.P = (pps > 256 ? pps / 256 : 1) * p.n_tiles * nw * halves;
     constexpr int STG = 4;
@@ -1975,19 +2085,24 @@ int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const f
     static int m64_mode = -1;  // SPDM_M64: 0 = off, 1 = on (TMEM layout A), 2 = on (layout B)
     if (m64_mode < 0) { const char* e = getenv("SPDM_M64"); m64_mode = e ? atoi(e) : 1; }
     const int grid = p.total_tiles < num_sms() ? p.total_tiles : num_sms();
+    // halo mode: persistent launches only (the L2 -> SM operand traffic is what bounds them: profiles/r02 summary); SPDM_NO_HALO=1 switches it off
+    static int no_halo = -1;
+    if (no_halo < 0) { const char* e = getenv("SPDM_NO_HALO"); no_halo = e ? atoi(e) : 0; }
+    p.halo = (g->has_halo && !p.fold && !no_halo && p.total_tiles > num_sms()) ? 1 : 0;
+    const CUtensorMap& map_h = g->has_halo ? g->map_halo : g->map_a;
     if (p.Cout == 64 && !fuse && m64_mode > 0) {  // 64-row MMA: no zero rows, half the operand-read time per instruction
       const int nw64 = m64_mode == 2 ? 2 : 4;
       p.P = (pps > 256 ? pps / 256 : 1) * p.n_tiles * nw64 * halves;
       if (m64_mode == 2) p.dbg |= 1024;
       static bool attr64 = false;
       if (!attr64) { cudaFuncSetAttribute(conv_tc_swap_kernel<STG, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr64 = true; }
-      launch_pdl(conv_tc_swap_kernel<STG, 64>, dim3(grid), dim3(threads), smem, s, g->map_a, g->map_b, p);
+      launch_pdl(conv_tc_swap_kernel<STG, 64>, dim3(grid), dim3(threads), smem, s, g->map_a, g->map_b, map_h, p);
       ++g_tc_launches;
       return p.P;
     }
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(conv_tc_swap_kernel<STG, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    launch_pdl(conv_tc_swap_kernel<STG, 128>, dim3(grid), dim3(threads), smem, s, g->map_a, g->map_wswap, p);
+    launch_pdl(conv_tc_swap_kernel<STG, 128>, dim3(grid), dim3(threads), smem, s, g->map_a, g->map_wswap, map_h, p);
     ++g_tc_launches;
     return p.P;
   }

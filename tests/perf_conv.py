@@ -12,7 +12,8 @@ SHAPES = [  # (name, H, W, Cin, Cout, taps)
     ("L0 128->128 3x3", 32, 8, 128, 128, 9), ("L0 128->64 3x3", 32, 8, 128, 64, 9), ("L0 64->64 3x3", 32, 8, 64, 64, 9),
     ("L1 256->256 3x3", 16, 4, 256, 256, 9), ("L2 512->512 3x3", 8, 2, 512, 512, 9), ("L3 512->512 3x3", 4, 1, 512, 512, 9),
     ("L0 64->192 1x1", 32, 8, 64, 192, 1), ("L0 64->64 1x1", 32, 8, 64, 64, 1), ("L1 128->128 1x1", 16, 4, 128, 128, 1)]
-MODES = [(0, "real"), (64, "no swap"), (64 + 128, "no swap, N<=128"), (7, "no loads/stores"), (16 + 32 + 7, "mma free-run")]
+MODES = [(0, "real"), (32, "no epilogue"), (16, "mma free-run"), (16 + 32, "mma free-run, no epilogue"), (64, "no swap"),
+         (1, "no weight loads (plain kernel)"), (2, "no pixel loads (plain kernel)")]
 
 
 def main():
