@@ -73,6 +73,14 @@ struct TcParams {
 // ---------------------------------------------------------------------------------------------
 struct TileCoord { int m_tile, n_tile, b0, h0, n0, ks; };
 
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
 
 __device__ __forceinline__ float erf_fast_tc(float x) {  // Abramowitz-Stegun 7.1.26, |err| < 1.5e-7
@@ -119,10 +127,16 @@ __device__ __forceinline__ TileCoord decode_tile(const TcParams& p, int tile, in
   return t;
 }
 
-template <int BLOCK_N, int STAGES>
+// PAIR: the CTA-pair form (cta_group::2, tc_ptx.cuh) for persistent launches of the wide layers: a cluster of two CTAs takes two
+// neighbouring M tiles of the same N tile; each CTA stages its own 128 pixel rows and HALF of the 256 weight rows per k-step
+// (32 KB instead of 48 KB: six pipeline stages instead of four in the same shared memory, a third less operand traffic), the
+// leader issues one M = 256 MMA for both.  Everything behind the accumulator (epilogue warps, statistics, fused apply) is per CTA
+// and unchanged.  map_b must be the 128-row-box weight map.  ksplit == 1, m_tiles even.
+template <int BLOCK_N, int STAGES, bool PAIR = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b, const TcParams p) {
-  constexpr int B_STAGE_BYTES = BLOCK_N * BLOCK_K * 2;
+  constexpr int B_STAGE_BYTES = (PAIR ? BLOCK_N / 2 : BLOCK_N) * BLOCK_K * 2;
+  static_assert(!PAIR || BLOCK_N == 256, "the pair form is built for 256-wide N tiles");
   constexpr int TMEM_COLS = 2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);  // power of two
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -137,6 +151,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  // tile walk: a CTA takes tiles blockIdx.x, + gridDim.x, ...; a pair takes "super tiles" (two neighbouring M tiles of one N tile)
+  const int t_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int t_total = PAIR ? p.total_tiles / 2 : p.total_tiles;
+  auto real_tile = [&](int st) {
+    if (!PAIR) return st;
+    const int j = st / p.n_tiles, n = st - j * p.n_tiles;
+    return (2 * j + (int)crank) * p.n_tiles + n;
+  };
 
   // ---- K iteration space: valid taps x 64-channel blocks ----
   const bool skip_dx = (p.taps == 9 && p.W == 1), skip_dy = (p.taps == 9 && p.H == 1);
@@ -150,12 +174,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 #pragma unroll
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
     mbar_init(&tmem_full_bar[0], 1); mbar_init(&tmem_full_bar[1], 1);
-    mbar_init(&tmem_empty_bar[0], 4); mbar_init(&tmem_empty_bar[1], 4);  // one arrival per epilogue warp
+    mbar_init(&tmem_empty_bar[0], PAIR ? 8 : 4); mbar_init(&tmem_empty_bar[1], PAIR ? 8 : 4);  // one arrival per epilogue warp (of both CTAs)
     fence_barrier_init();
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+  if (warp == 2) {
+    if constexpr (PAIR) tmem_alloc_pair<TMEM_COLS>(&tmem_base_smem);
+    else tmem_alloc<TMEM_COLS>(&tmem_base_smem);
+  }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers exist before anything is signalled across the pair
   tc_fence_after();
   const uint32_t tmem_base = tmem_base_smem;
   // Programmatic dependent launch: everything above overlapped with the previous kernel's tail.  The weights do not depend
@@ -177,25 +205,34 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           tap = (dy + 1) * 3 + (dx + 1);
         }
       };
-      const uint32_t stage_tx = ((p.dbg & 2) ? 0 : A_STAGE_BYTES) + ((p.dbg & 1) ? 0 : B_STAGE_BYTES);
+      // pair: the leader's barrier counts the bytes of both CTAs (its own expect_tx is the only arrival)
+      const uint32_t stage_tx = (((p.dbg & 2) ? 0 : A_STAGE_BYTES) + ((p.dbg & 1) ? 0 : B_STAGE_BYTES)) * (PAIR ? 2u : 1u);
+      const int b_row_off = PAIR ? (int)crank * (BLOCK_N / 2) : 0;   // this CTA's half of the weight rows
+      auto load_b = [&](int s, int tap, int kb, int n0) {
+        if (p.dbg & 1) return;
+        if constexpr (PAIR) tma_load_2d_pair(smem_b + s * B_STAGE_BYTES, &map_b, &full_bar[s], tap * p.Cin + kb * BLOCK_K, n0 + b_row_off);
+        else tma_load_2d(smem_b + s * B_STAGE_BYTES, &map_b, &full_bar[s], tap * p.Cin + kb * BLOCK_K, n0);
+      };
       uint32_t n_pre = 0;   // k-steps of the first tile whose expect_tx + weight load were issued before the wait
-      if (!(p.dbg & 16) && (int)blockIdx.x < p.total_tiles) {
-        const TileCoord t = decode_tile(p, blockIdx.x, BLOCK_N);
+      if (!(p.dbg & 16) && t_first < t_total) {
+        const TileCoord t = decode_tile(p, real_tile(t_first), BLOCK_N);
         const int it_begin = p.ksplit > 1 ? t.ks * k_iters / p.ksplit : 0;
         const int it_end = p.ksplit > 1 ? (t.ks + 1) * k_iters / p.ksplit : k_iters;
         for (int it = it_begin; it < it_end && n_pre < (uint32_t)STAGES; ++it, ++n_pre) {
           int dy, dx, tap, kb;
           tap_of(it, dy, dx, tap, kb);
-          mbar_expect_tx(&full_bar[n_pre], stage_tx);
-          if (!(p.dbg & 1)) tma_load_2d(smem_b + n_pre * B_STAGE_BYTES, &map_b, &full_bar[n_pre], tap * p.Cin + kb * BLOCK_K, t.n0);
+          if (!PAIR || crank == 0) mbar_expect_tx(&full_bar[n_pre], stage_tx);
+          load_b((int)n_pre, tap, kb, t.n0);
         }
       }
       pdl_wait();
       pdl_trigger();
       if (!(p.dbg & 16)) {
         uint32_t kit = 0;
-        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-          const TileCoord t = decode_tile(p, tile, BLOCK_N);
+        long long prod_wait = 0, prod_etx = 0, prod_b = 0, prod_a = 0;
+        const long long prod_t0 = clock64();
+        for (int st = t_first; st < t_total; st += t_step) {
+          const TileCoord t = decode_tile(p, real_tile(st), BLOCK_N);
           const int it_begin = p.ksplit > 1 ? t.ks * k_iters / p.ksplit : 0;
           const int it_end = p.ksplit > 1 ? (t.ks + 1) * k_iters / p.ksplit : k_iters;
           for (int it = it_begin; it < it_end; ++it, ++kit) {
@@ -205,25 +242,43 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
             tap_of(it, dy, dx, tap, kb);
             if (p.dbg & 8) { dx = 0; dy = 0; }
             if (kit >= n_pre) {
-              mbar_wait(&empty_bar[s], ph ^ 1u);
-              mbar_expect_tx(&full_bar[s], stage_tx);
-              if (!(p.dbg & 1)) tma_load_2d(smem_b + s * B_STAGE_BYTES, &map_b, &full_bar[s], tap * p.Cin + kb * BLOCK_K, t.n0);
+              const long long tw0 = (p.dbg & 4096) ? clock64() : 0;
+              mbar_wait(&empty_bar[s], ph ^ 1u);   // (pair: the leader's MMA commit arrives on this barrier in both CTAs)
+              if (p.dbg & 4096) prod_wait += clock64() - tw0;
+              const long long te0 = (p.dbg & 4096) ? clock64() : 0;
+              if (!PAIR || crank == 0) mbar_expect_tx(&full_bar[s], stage_tx);
+              const long long te1 = (p.dbg & 4096) ? clock64() : 0;
+              load_b(s, tap, kb, t.n0);
+              if (p.dbg & 4096) { prod_etx += te1 - te0; prod_b += clock64() - te1; }
             }
-            if (!(p.dbg & 2)) tma_load_4d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t.h0 + dy, t.b0);
+            if (!(p.dbg & 2)) {
+              const long long ta0 = (p.dbg & 4096) ? clock64() : 0;
+              if constexpr (PAIR) tma_load_4d_pair(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t.h0 + dy, t.b0);
+              else tma_load_4d(smem_a + s * A_STAGE_BYTES, &map_a, &full_bar[s], kb * BLOCK_K, dx, t.h0 + dy, t.b0);
+              if (p.dbg & 4096) prod_a += clock64() - ta0;
+            }
           }
         }
+        if ((p.dbg & 4096) && blockIdx.x == 0)
+          printf("spdm conv timing (producer, block 0): %u k-steps, %lld cycles, %lld waiting for a free stage, %lld in expect_tx, %lld issuing weight loads, %lld issuing pixel loads\n",
+                 kit, clock64() - prod_t0, prod_wait, prod_etx, prod_b, prod_a);
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BLOCK_N);
+    if (lane == 0 && (!PAIR || crank == 0)) {   // pair: the leader issues for both CTAs
+      constexpr uint32_t idesc = PAIR ? make_idesc_m(256, BLOCK_N) : make_idesc(BLOCK_N);
       uint32_t kit = 0;
       int lt = 0;
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+      long long mma_wait = 0, acc_wait = 0;
+      const long long mma_t0 = clock64();
+      for (int st = t_first; st < t_total; st += t_step, ++lt) {
+        const int tile = real_tile(st);
         const int acc = lt & 1;
         const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
-        mbar_wait(&tmem_empty_bar[acc], aph ^ 1u);  // epilogue has drained this accumulator
+        const long long ta0 = (p.dbg & 4096) ? clock64() : 0;
+        mbar_wait(&tmem_empty_bar[acc], aph ^ 1u);  // epilogue has drained this accumulator (pair: in both CTAs)
+        if (p.dbg & 4096) acc_wait += clock64() - ta0;
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         int it_begin = 0, it_end = k_iters;
@@ -231,19 +286,29 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         for (int it = it_begin; it < it_end; ++it, ++kit) {
           const int s = kit % STAGES;
           const uint32_t ph = (kit / STAGES) & 1u;
+          const long long tw0 = (p.dbg & 4096) ? clock64() : 0;
           if (!(p.dbg & 16)) mbar_wait(&full_bar[s], ph);
+          if (p.dbg & 4096) mma_wait += clock64() - tw0;
           tc_fence_after();
           const uint64_t da = make_smem_desc(smem_u32(smem_a + s * A_STAGE_BYTES));
           const uint64_t db = make_smem_desc(smem_u32(smem_b + s * B_STAGE_BYTES));
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             // advance 32 bytes along K inside the swizzle atom: +2 in the (addr >> 4) field
-            umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > it_begin || k > 0) ? 1u : 0u);
+            if constexpr (PAIR) umma_bf16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > it_begin || k > 0) ? 1u : 0u);
+            else umma_bf16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (it > it_begin || k > 0) ? 1u : 0u);
           }
-          if (!(p.dbg & 16)) umma_commit(&empty_bar[s]);  // frees the smem slot when these MMAs retire
+          if (!(p.dbg & 16)) {   // frees the smem slot when these MMAs retire
+            if constexpr (PAIR) umma_commit_pair(&empty_bar[s]);
+            else umma_commit(&empty_bar[s]);
+          }
         }
-        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        if constexpr (PAIR) umma_commit_pair(&tmem_full_bar[acc]);  // accumulator complete
+        else umma_commit(&tmem_full_bar[acc]);
       }
+      if ((p.dbg & 4096) && blockIdx.x == 0)
+        printf("spdm conv timing (MMA issuer, block 0): %u k-steps, %lld cycles, %lld waiting for operands, %lld waiting for a free accumulator\n", kit,
+               clock64() - mma_t0, mma_wait, acc_wait);
     }
   } else {
     // ================= epilogue: warps 2..5 -> TMEM lane quarters (warp % 4) =================
@@ -251,8 +316,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     const int r_t = q * 32 + lane;                 // tile row == TMEM lane
     const int rps = p.Hb * p.W;                    // rows per sample inside the tile
     const int tiles_per_sample = p.H / p.Hb;
+    // hand the accumulator back to the MMA issuer (pair: the leader's barrier collects the warps of both CTAs)
+    auto release_acc = [&](int acc) {
+      if constexpr (PAIR) mbar_arrive_cluster(&tmem_empty_bar[acc], 0u);
+      else mbar_arrive(&tmem_empty_bar[acc]);
+    };
     int lt = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++lt) {
+    for (int st = t_first; st < t_total; st += t_step, ++lt) {
+      const int tile = real_tile(st);
       const TileCoord t = decode_tile(p, tile, BLOCK_N);
       const int acc = lt & 1;
       const uint32_t aph = (uint32_t)(lt >> 1) & 1u;
@@ -267,7 +338,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
       if (p.dbg & 32) {  // microbenchmark: hand the accumulator straight back
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+        if (lane == 0) release_acc(acc);
         continue;
       }
       if (p.ksplit > 1) {  // split-K: this CTA owns one slice of the K loop; fp32 partial tile, reduced by apply_partial_kernel
@@ -280,7 +351,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (c + 32 == BLOCK_N) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) release_acc(acc);
           }
 #pragma unroll
           for (int i = 0; i < 32; i += 4)
@@ -327,7 +398,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
           if (c + 32 == BLOCK_N) {
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+            if (lane == 0) release_acc(acc);
           }
           float f[32];
 #pragma unroll
@@ -372,7 +443,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
         if (c + 32 == BLOCK_N) {  // accumulator fully read: hand it back to the MMA warp
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+          if (lane == 0) release_acc(acc);
         }
         float f[32];
 #pragma unroll
@@ -445,9 +516,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
     tc_fence_before();
   }
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();   // no CTA of the pair leaves (or frees tensor memory) while the other may still signal it
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc<TMEM_COLS>(tmem_base);
+    if constexpr (PAIR) tmem_dealloc_pair<TMEM_COLS>(tmem_base);
+    else tmem_dealloc<TMEM_COLS>(tmem_base);
   }
 }
 
@@ -467,14 +540,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant_
 //      embedding, +FiLM) and store the bf16 activation.  Neither the raw conv output nor a partial tile touches HBM.
 // Requires whole samples per 128-row tile (H == Hb) with 4..32 rows per sample; cluster size n_tiles * cl_ks <= 8.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
-}
 __device__ __forceinline__ uint32_t mapa_u32(uint32_t laddr, uint32_t rank) {
   uint32_t r;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(laddr), "r"(rank));
@@ -1595,6 +1660,33 @@ void launch_cfg(const CUtensorMap& ma, const CUtensorMap& mb, const TcParams& p,
   ++g_tc_launches;
 }
 
+// CTA-pair launch (conv_tc_kernel<256, 6, true>): clusters of two CTAs, an even grid
+bool launch_pair(const CUtensorMap& ma, const CUtensorMap& mb128, const TcParams& p, cudaStream_t s) {
+  constexpr int STG = 6;
+  constexpr int smem = STG * (A_STAGE_BYTES + 128 * BLOCK_K * 2) + 1024;
+  static bool attr = false;
+  if (!attr) {
+    cudaFuncSetAttribute(conv_tc_kernel<256, STG, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    attr = true;
+  }
+  int grid = (p.total_tiles < num_sms() ? p.total_tiles : num_sms()) & ~1;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(NUM_THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = s;
+  cudaLaunchAttribute at[2];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+  at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = g_spdm_pdl ? 2 : 1;
+  if (cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, STG, true>, ma, mb128, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  ++g_tc_launches;
+  return true;
+}
+
 }  // namespace
 
 struct TcGemm {
@@ -2112,6 +2204,14 @@ int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const f
   p.n_tiles = p.Cout / bn;
   p.total_tiles = p.m_tiles * p.n_tiles * p.ksplit;
   p.P = partials_for(p, p.n_tiles);
+  // SPDM_PAIR=1: persistent launches of the 256-wide tiles as CTA pairs (cta_group::2).  Correct (parity tests pass with it) but
+  // measured slower than the single-CTA form at batch 4096 (256->256 at 16x4: 250 vs 234 us; the whole step -0.5 %): the operand
+  // waits it was meant to shorten do not come from the stage count or the bytes per k-step (profiles/r02_conv_pipeline_probe.md).
+  static int pair = -1;
+  if (pair < 0) { const char* e = getenv("SPDM_PAIR"); pair = e ? atoi(e) : 0; }
+  if (bn == 256 && pair && g->block_n == 128 && p.ksplit == 1 && p.m_tiles % 2 == 0 && p.total_tiles >= 2 * num_sms() &&
+      !(flags & (EPI_VT | EPI_RESID | EPI_MASK)) && launch_pair(g->map_a, g->map_b, p, s))
+    return p.P;
   if (bn == 256) launch_cfg<256, 4>(g->map_a, g->map_b256, p, s);
   else if (bn == 192) launch_cfg<192, 4>(g->map_a, g->map_b, p, s);
   else if (bn == 128) launch_cfg<128, 6>(g->map_a, g->map_b, p, s);

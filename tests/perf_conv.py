@@ -14,6 +14,9 @@ SHAPES = [  # (name, H, W, Cin, Cout, taps)
     ("L0 64->192 1x1", 32, 8, 64, 192, 1), ("L0 64->64 1x1", 32, 8, 64, 64, 1), ("L1 128->128 1x1", 16, 4, 128, 128, 1)]
 MODES = [(0, "real"), (32, "no epilogue"), (16, "mma free-run"), (16 + 32, "mma free-run, no epilogue"), (64, "no swap"),
          (1, "no weight loads (plain kernel)"), (2, "no pixel loads (plain kernel)")]
+if len(sys.argv) > 2 and sys.argv[2] == "timing":   # per-role wait cycles of block 0 (plain kernel), printed by the kernel
+    MODES = [(4096, "timing"), (4096 + 1, "timing, no weight loads"), (4096 + 2, "timing, no pixel loads")]
+    SHAPES = SHAPES[3:4]
 
 
 def main():
@@ -26,7 +29,7 @@ def main():
         row = []
         for dbg, label in MODES:
             ms = ctypes.c_float()
-            rc = lib.spdm_microbench_conv(H, W, B, Cin, Cout, taps, dbg, 20, ctypes.byref(ms))
+            rc = lib.spdm_microbench_conv(H, W, B, Cin, Cout, taps, dbg, 1 if dbg & 4096 else 20, ctypes.byref(ms))
             if rc:
                 print(name, "error", lib.spdm_last_error())
                 break
