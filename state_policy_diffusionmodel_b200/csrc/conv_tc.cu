@@ -66,6 +66,7 @@ struct TcParams {
   // halo mode (conv_tc_swap_kernel, W == 8, 32 image rows of one sample per tile): the pixel operand of a (k block, dx) pair is loaded
   // ONCE as a (32 + 2)-row box and serves the three dy taps through 1024-byte descriptor offsets
   int halo;
+  int pix256;             // conv_tc_swap_kernel: map_a has a 256-row box (one pixel load per k-step instead of two)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -1366,8 +1367,8 @@ conv_tc_swap_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_cons
             mbar_expect_tx(&full_bar[s], PIX_BYTES + W_BYTES);
             tma_load_2d(smem_w + s * W_BYTES, &map_w, &full_bar[s], wcol, c_tile * WM);
           }
-          tma_load_4d(smem_pix + s * PIX_BYTES, &map_a, &full_bar[s], c0, dx, t0.h0 + dy, t0.b0);
-          tma_load_4d(smem_pix + s * PIX_BYTES + A_STAGE_BYTES, &map_a, &full_bar[s], c0, dx, t1.h0 + dy, t1.b0);
+          tma_load_4d(smem_pix + s * PIX_BYTES, &map_a, &full_bar[s], c0, dx, t0.h0 + dy, t0.b0);   // pix256: the box holds both tiles
+          if (!p.pix256) tma_load_4d(smem_pix + s * PIX_BYTES + A_STAGE_BYTES, &map_a, &full_bar[s], c0, dx, t1.h0 + dy, t1.b0);
         }
       }
     }
@@ -1693,6 +1694,8 @@ struct TcGemm {
   CUtensorMap map_a, map_b, map_b256, map_wswap;
   CUtensorMap map_halo;   // (32 + 2)-row pixel box of the swapped kernel's halo mode (has_halo)
   bool has_halo;
+  CUtensorMap map_a256;   // 256-row pixel box: the swapped kernel's whole N tile in one TMA operation (has_a256)
+  bool has_a256;
   bool can_swap;    // 3x3, Cout in {64,128}, geometry allows 256-pixel tiles with per-sample statistics
   TcParams p;
   int block_n;      // 64 or 128
@@ -1711,6 +1714,19 @@ int tc_batch_multiple(int H, int W) {
 static int partials_for(const TcParams& p, int n_tiles) {
   const int rps = p.Hb * p.W;
   return rps >= 32 ? (p.H / p.Hb) * ((rps >= 128 ? 128 : rps) / 32) * n_tiles : n_tiles;
+}
+
+// 256-row pixel box of the swapped kernel: two neighbouring 128-row tiles = 2 Hb rows of one sample (maps of >= 256 pixels) or
+// 2 Bt whole samples.  dims / strides as in the 128-row map.
+static bool encode_a256(EncodeTiledFn enc, CUtensorMap* out, const void* in, const cuuint64_t* dims, const cuuint64_t* strides, int W, int H, int Hb,
+                        int Bt, int Bcap) {
+  int Hb2 = Hb, Bt2 = Bt;
+  if (H / Hb > 1) { if ((H / Hb) % 2) return false; Hb2 = 2 * Hb; } else { Bt2 = 2 * Bt; if (Bcap % Bt2) return false; }
+  if (Hb2 > 256 || Bt2 > 256 || W > 256) return false;
+  cuuint32_t box[4] = {(cuuint32_t)BLOCK_K, (cuuint32_t)W, (cuuint32_t)Hb2, (cuuint32_t)Bt2};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 TcGemm* tc_gemm_create(const bf16* in, int ld_in, const bf16* w_packed, int Cin, int Cout, int taps, int H, int W, int Bcap) {
@@ -1748,6 +1764,11 @@ TcGemm* tc_gemm_create(const bf16* in, int ld_in, const bf16* w_packed, int Cin,
   {
     const int pps = H * W;
     g->can_swap = taps == 9 && (Cout == 64 || Cout == 128) && (pps == 16 || (pps >= 32 && pps % 32 == 0 && (pps >= 256 ? pps % 256 == 0 : 256 % pps == 0)));
+  }
+  if (g->can_swap) {
+    cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bcap};
+    cuuint64_t strides[3] = {(cuuint64_t)ld_in * 2, (cuuint64_t)W * ld_in * 2, (cuuint64_t)H * W * ld_in * 2};
+    g->has_a256 = encode_a256(enc, &g->map_a256, in, dims, strides, W, H, Hb, Bt, Bcap);
   }
   if (g->can_swap && W == 8 && H % 32 == 0) {   // a 256-pixel tile is 32 whole image rows of one sample: halo mode
     cuuint64_t dims[4] = {(cuuint64_t)Cin, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)Bcap};
@@ -1809,6 +1830,7 @@ TcGemm* tc_gemm_create_pfold(const bf16* in, int ld_in, const bf16* w_pfold, int
     CUresult r = enc(&g->map_a, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)in, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { snprintf(g_tc_err, sizeof g_tc_err, "cuTensorMapEncodeTiled(A, pair fold) failed: %d", (int)r); delete g; return nullptr; }
+    g->has_a256 = encode_a256(enc, &g->map_a256, in, dims, strides, Wp, H, Hb, Bt, Bcap);
   }
   {
     const cuuint64_t Ktot = (cuuint64_t)12 * Cin;
@@ -2182,19 +2204,23 @@ int tc_gemm_launch(const TcGemm* g, bf16* out, int ld_out, float* stats, const f
     if (no_halo < 0) { const char* e = getenv("SPDM_NO_HALO"); no_halo = e ? atoi(e) : 0; }
     p.halo = (g->has_halo && !p.fold && !no_halo && p.total_tiles > num_sms()) ? 1 : 0;
     const CUtensorMap& map_h = g->has_halo ? g->map_halo : g->map_a;
+    static int no256 = -1;   // SPDM_NO_PIX256=1: two 128-row pixel boxes per k-step as before (A/B switch)
+    if (no256 < 0) { const char* e = getenv("SPDM_NO_PIX256"); no256 = e ? atoi(e) : 0; }
+    p.pix256 = (g->has_a256 && !no256) ? 1 : 0;
+    const CUtensorMap& map_px = p.pix256 ? g->map_a256 : g->map_a;
     if (p.Cout == 64 && !fuse && m64_mode > 0) {  // 64-row MMA: no zero rows, half the operand-read time per instruction
       const int nw64 = m64_mode == 2 ? 2 : 4;
       p.P = (pps > 256 ? pps / 256 : 1) * p.n_tiles * nw64 * halves;
       if (m64_mode == 2) p.dbg |= 1024;
       static bool attr64 = false;
       if (!attr64) { cudaFuncSetAttribute(conv_tc_swap_kernel<STG, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr64 = true; }
-      launch_pdl(conv_tc_swap_kernel<STG, 64>, dim3(grid), dim3(threads), smem, s, g->map_a, g->map_b, map_h, p);
+      launch_pdl(conv_tc_swap_kernel<STG, 64>, dim3(grid), dim3(threads), smem, s, map_px, g->map_b, map_h, p);
       ++g_tc_launches;
       return p.P;
     }
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(conv_tc_swap_kernel<STG, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr = true; }
-    launch_pdl(conv_tc_swap_kernel<STG, 128>, dim3(grid), dim3(threads), smem, s, g->map_a, g->map_wswap, map_h, p);
+    launch_pdl(conv_tc_swap_kernel<STG, 128>, dim3(grid), dim3(threads), smem, s, map_px, g->map_wswap, map_h, p);
     ++g_tc_launches;
     return p.P;
   }
