@@ -20,6 +20,12 @@
 #include "tc_ptx.cuh"
 
 // 2^x through MUFU.EX2 directly (arguments are <= 0 here; exp2f() adds range-handling instructions the softmax loop is bound by)
+// three-input maximum (one FMNMX3 on sm_100)
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+  return d;
+}
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -149,8 +155,8 @@ sdpa_tc_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_constan
           if (!(c + i + 1 >= k_lo && c + i + 1 < k_hi)) p1 = 0.f;
         }
         const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-        s2[0] += __low2float(b2);
-        s2[1] += __high2float(b2);
+        s2[0] += p0;   // fp32 exponentials: see attn_head.cu
+        s2[1] += p1;
         packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
       }
       sum += s2[0] + s2[1];
@@ -349,8 +355,8 @@ sdpa_tc2_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_consta
           if (!(c + i + 1 >= k_lo && c + i + 1 < k_hi)) p1 = 0.f;
         }
         const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);   // .x (low half) = the even key
-        s2[0] += __low2float(b2);
-        s2[1] += __high2float(b2);
+        s2[0] += p0;   // fp32 exponentials: see attn_head.cu
+        s2[1] += p1;
         packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
       }
       sum += s2[0] + s2[1];
@@ -491,7 +497,7 @@ sdpa_tc_long_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
         tmem_ld_wait();
         float m4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m4[i & 3] = fmaxf(m4[i & 3], __uint_as_float(v[i]));
+        for (int i = 0; i < 32; i += 2) m4[(i >> 1) & 3] = fmax3(m4[(i >> 1) & 3], __uint_as_float(v[i]), __uint_as_float(v[i + 1]));
         m = fmaxf(m, fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3])));
       }
       mrow[h] = fmaxf(mrow[h], m);
@@ -536,8 +542,8 @@ sdpa_tc_long_kernel(const __grid_constant__ CUtensorMap map_qkv, const __grid_co
           const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), p.scale_log2, -mrow[h]));
           const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -mrow[h]));
           const __nv_bfloat162 b2 = __floats2bfloat162_rn(p0, p1);
-          s2[0] += __low2float(b2);
-          s2[1] += __high2float(b2);
+          s2[0] += p0;   // fp32 exponentials: see attn_head.cu (the bf16-rounded P differs by 2^-9 per element, unbiased)
+          s2[1] += p1;
           packed[i >> 1] = *reinterpret_cast<const uint32_t*>(&b2);
         }
         sum += s2[0] + s2[1];
