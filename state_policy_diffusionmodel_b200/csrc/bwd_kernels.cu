@@ -18,6 +18,21 @@ namespace {
 __device__ __forceinline__ float gelu_grad(float u) {  // d/du [0.5 u (1 + erf(u / sqrt 2))]
   return 0.5f * (1.0f + erff(u * 0.70710678118654752440f)) + u * 0.3989422804014327f * __expf(-0.5f * u * u);
 }
+// Derivative of the GELU the bf16 forward actually applies after GroupNorm (kernels.cu::gelu_tanh_fast / conv_tc.cu::gelu_fast_tc:
+// 0.5 y (1 + tanh(k (y + c y^3)))): one MUFU + ~10 FMA-class instructions instead of the erf polynomial + exp (the GELU launches of
+// the GroupNorm backward are issue-bound: ncu issue-active 42-48 %).  The fp32 parity path keeps the exact pair.
+template <typename T> __device__ __forceinline__ float gelu_grad_as_forward(float u) {
+  if constexpr (sizeof(T) == 4) {
+    return gelu_grad(u);
+  } else {
+    const float u2 = u * u;
+    const float inner = 0.7978845608028654f * u * fmaf(0.044715f, u2, 1.0f);
+    float th;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(inner));
+    const float dinner = fmaf(0.7978845608028654f * 3.0f * 0.044715f, u2, 0.7978845608028654f);
+    return fmaf(0.5f * u * dinner, fmaf(-th, th, 1.0f), fmaf(0.5f, th, 0.5f));
+  }
+}
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -95,7 +110,7 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(GnBwdArgs a) {
       float go = d[i];
       if (has_film) { acc_fb[i] += d[i]; acc_fs[i] = fmaf(d[i], u + te[i], acc_fs[i]); go = d[i] * fs[i]; }
       else if (has_temb) acc_fb[i] += d[i];
-      if (a.act == ACT_GELU) go *= gelu_grad(u);
+      if (a.act == ACT_GELU) go *= gelu_grad_as_forward<T>(u);
       acc_dg[i] = fmaf(go, xh, acc_dg[i]);
       acc_db[i] += go;
       const float gg = go * g[i];
@@ -157,7 +172,7 @@ __global__ void __launch_bounds__(256) gn_bwd_kernel(GnBwdArgs a) {
     for (int i = 0; i < 8; ++i) {
       const float xh = (x[i] - mean) * rstd;
       float go = d[i] * fs[i];
-      if (a.act == ACT_GELU) go *= gelu_grad(xh * g[i] + be[i]);
+      if (a.act == ACT_GELU) go *= gelu_grad_as_forward<T>(xh * g[i] + be[i]);
       x[i] = rstd * (go * g[i] - m1 - xh * m2);
     }
     store8(dx + ((size_t)b * a.HW + row) * a.ld_dx + c8, x);
@@ -221,7 +236,7 @@ __global__ void __launch_bounds__(512) gn_bwd_cached_kernel(GnBwdArgs a, int CS)
       float go = d[i];
       if (has_film) { acc_fb[i] += d[i]; acc_fs[i] = fmaf(d[i], u + te[i], acc_fs[i]); go = d[i] * fs[i]; }
       else if (has_temb) acc_fb[i] += d[i];
-      if (a.act == ACT_GELU) go *= gelu_grad(u);
+      if (a.act == ACT_GELU) go *= gelu_grad_as_forward<T>(u);
       acc_dg[i] = fmaf(go, xhv, acc_dg[i]);
       acc_db[i] += go;
       const float gv = go * g[i];
