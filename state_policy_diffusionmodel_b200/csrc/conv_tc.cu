@@ -84,12 +84,6 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }  // the 4 epilogue warps
 
-__device__ __forceinline__ float erf_fast_tc(float x) {  // Abramowitz-Stegun 7.1.26, |err| < 1.5e-7
-  const float ax = fabsf(x);
-  const float t = __frcp_rn(fmaf(0.3275911f, ax, 1.0f));
-  const float poly = t * (0.254829592f + t * (-0.284496736f + t * (1.421413741f + t * (-1.453152027f + t * 1.061405429f))));
-  return copysignf(1.0f - poly * __expf(-ax * ax), x);
-}
 // GELU through the hardware tanh (kernels.cu::gelu_tanh_fast): the fused GroupNorm-apply epilogue is issue-bound on 4 warps
 __device__ __forceinline__ float gelu_fast_tc(float y) {
   const float u = 0.7978845608028654f * fmaf(0.044715f * y * y, y, y);
